@@ -1,0 +1,322 @@
+"""CPU oracle for the GiGL hot path - TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module, and there only as the checker or the
+timed CPU baseline.  Nothing under ``gigl_b200/`` imports it.
+
+Two independent restatements of the same spec:
+
+* ``c_*``  - ctypes bindings to ``oracle/gigl_oracle.c`` (plain C, OpenMP over roots);
+* ``np_*`` - numpy / pure-python versions used to cross-check the C one on small cases.
+
+Reference files followed (relative to /root/reference): see the header of gigl_oracle.c.
+Pinning status: **parity unpinned** for the deterministic permutation (the reference's tests
+only ever run the non-deterministic shuffle); pinned for the hash (Spark xxhash64 KAT) and
+for the structural rules (reference sgs_output fixtures).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgigl_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/gigl_oracle.c (gcc) if the .so is missing or stale."""
+    src = os.path.join(_HERE, "gigl_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libgigl_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        i32, i64, u64, p = C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
+        L.oracle_xxh64_int.restype = i64
+        L.oracle_xxh64_int.argtypes = [i32, u64]
+        L.oracle_perm_full.restype = C.c_int
+        L.oracle_perm_full.argtypes = [i64, i32, i32, p]
+        L.oracle_perm_topk.restype = i64
+        L.oracle_perm_topk.argtypes = [i64, i32, i32, i32, p]
+        L.oracle_sample_khop.restype = C.c_int
+        L.oracle_sample_khop.argtypes = [i64, p, p, p, i64, p, i32, i32, i32, p, p, i32]
+        for nm in ("oracle_sage_conv_f32", "oracle_sage_conv_f64"):
+            f = getattr(L, nm)
+            f.restype = C.c_int
+            f.argtypes = [i64, i64, i32, i32, p, p, p, p, p, p, p, i32, i32]
+        for nm in ("oracle_gcn_conv_f32", "oracle_gcn_conv_f64"):
+            f = getattr(L, nm)
+            f.restype = C.c_int
+            f.argtypes = [i64, i64, i32, i32, p, p, p, p, p, p, i32]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------------------
+# hash + permutation
+# ----------------------------------------------------------------------------------------
+_P1 = np.uint64(0x9E3779B185EBCA87)
+_P2 = np.uint64(0xC2B2AE3D27D4EB4F)
+_P3 = np.uint64(0x165667B19E3779F9)
+_P5 = np.uint64(0x27D4EB2F165667C5)
+
+
+def np_xxh64_int(x, seed: int = 42) -> np.ndarray:
+    """Spark ``XXH64.hashInt(int, seed)`` on an int32 array -> signed int64 array."""
+    x = np.asarray(x).astype(np.int64).astype(np.int32)  # wrap to int32
+    with np.errstate(over="ignore"):
+        h = np.uint64(seed) + _P5 + np.uint64(4)
+        h = h ^ (x.astype(np.uint32).astype(np.uint64) * _P1)
+        h = ((h << np.uint64(23)) | (h >> np.uint64(41))) * _P2 + _P3
+        h = h ^ (h >> np.uint64(33))
+        h = h * _P2
+        h = h ^ (h >> np.uint64(29))
+        h = h * _P3
+        h = h ^ (h >> np.uint64(32))
+    return h.astype(np.int64)
+
+
+def c_xxh64_int(x: int, seed: int = 42) -> int:
+    x = ((int(x) + 2**31) % 2**32) - 2**31
+    return int(lib().oracle_xxh64_int(x, seed))
+
+
+def _wrap32(v: int) -> int:
+    return ((int(v) + 2**31) % 2**32) - 2**31
+
+
+def np_perm(size: int, internal_seed: int, current_seed: int) -> np.ndarray:
+    """0-based permutation of range(size) per SamplingStrategy.scala:47-76."""
+    i = np.arange(1, size + 1, dtype=np.int64)
+    x = i + _wrap32(internal_seed) + _wrap32(current_seed)  # exact in int64, wrapped in np_xxh64_int
+    keys = np_xxh64_int(x)
+    order = np.lexsort((i, keys))  # ascending by (key, idx)
+    return order.astype(np.int64)
+
+
+def c_perm_full(size: int, internal_seed: int, current_seed: int) -> np.ndarray:
+    out = np.empty(max(size, 1), dtype=np.int64)
+    rc = lib().oracle_perm_full(size, _wrap32(internal_seed), _wrap32(current_seed), _ptr(out))
+    assert rc == 0
+    return out[:size]
+
+
+def c_perm_topk(size: int, internal_seed: int, current_seed: int, f: int) -> np.ndarray:
+    out = np.empty(max(f, 1), dtype=np.int64)
+    n = lib().oracle_perm_topk(size, _wrap32(internal_seed), _wrap32(current_seed), f, _ptr(out))
+    return out[:n]
+
+
+# ----------------------------------------------------------------------------------------
+# graph loading rules (SGSPureSparkV1Task.scala:120-286) -> CSR by dst, rows sorted ascending
+# ----------------------------------------------------------------------------------------
+def np_build_in_csr(src, dst, n_nodes: int, is_graph_directed: bool):
+    """Edge list -> (rowptr int64 [n+1], col int32 [E]) of sorted in-neighbour lists.
+
+    Undirected (``enforceBidirectionalization`` :218-258): DISTINCT (least, greatest) then union
+    with the reverse.  Directed: duplicates kept.
+    """
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    if not is_graph_directed:
+        lo = np.minimum(src, dst)
+        hi = np.maximum(src, dst)
+        pairs = np.unique(np.stack([lo, hi], 1), axis=0) if len(lo) else np.zeros((0, 2), np.int64)
+        # Spark SQL `UNION` is UNION DISTINCT (:238-252): (lo,hi) U (hi,lo) de-duplicated, so a
+        # self loop (u,u) survives exactly once.
+        both = np.unique(np.concatenate([pairs, pairs[:, ::-1]]), axis=0)
+        src, dst = both[:, 0], both[:, 1]
+    order = np.lexsort((src, dst))
+    src, dst = src[order], dst[order]
+    rowptr = np.zeros(n_nodes + 1, dtype=np.int64)
+    np.add.at(rowptr, dst + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    return rowptr, src.astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------
+# k-hop sampling
+# ----------------------------------------------------------------------------------------
+def c_sample_khop(rowptr, col, roots, fanouts, base_seed=42, first_call_no=1, n_threads=None):
+    """-> (nbr, cnt): lists per hop of the padded-tree arrays (see gigl_oracle.c)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    roots = np.ascontiguousarray(roots, dtype=np.int32)
+    fan = np.ascontiguousarray(fanouts, dtype=np.int32)
+    n_roots = len(roots)
+    nbr, cnt = [], []
+    width = 1
+    for f in fan:
+        cnt.append(np.zeros(n_roots * width, dtype=np.int32))
+        width *= int(f)
+        nbr.append(np.full(n_roots * width, -1, dtype=np.int32))
+    pn = (C.c_void_p * len(fan))(*[a.ctypes.data for a in nbr])
+    pc = (C.c_void_p * len(fan))(*[a.ctypes.data for a in cnt])
+    if n_threads is None:
+        n_threads = os.cpu_count() or 1
+    rc = lib().oracle_sample_khop(
+        len(rowptr) - 1, _ptr(rowptr), _ptr(col), _ptr(roots), n_roots, _ptr(fan), len(fan), base_seed,
+        first_call_no, pn, pc, n_threads,
+    )
+    if rc != 0:
+        raise RuntimeError(f"oracle_sample_khop failed rc={rc}")
+    return nbr, cnt
+
+
+def np_sample_khop(rowptr, col, roots, fanouts, base_seed=42, first_call_no=1):
+    """Pure-python restatement of the same padded-tree sampler (small inputs only)."""
+    n_roots = len(roots)
+    nbr, cnt = [], []
+    width_prev = 1
+    prev_vals = [int(r) for r in roots]
+    prev_sums = [int(r) for r in roots]
+    for h, f in enumerate(fanouts, start=1):
+        f = int(f)
+        cur_seed = _wrap32(base_seed * _wrap32(first_call_no + h - 1))
+        out = np.full(n_roots * width_prev * f, -1, dtype=np.int32)
+        oc = np.zeros(n_roots * width_prev, dtype=np.int32)
+        sums = [0] * (n_roots * width_prev * f)
+        for ps in range(n_roots * width_prev):
+            v = prev_vals[ps]
+            if v < 0:
+                continue
+            m = 1
+            if h > 1:
+                fp = int(fanouts[h - 2])
+                sib0 = (ps // fp) * fp
+                sib = prev_vals[sib0 : sib0 + fp]
+                if sib.index(v) + sib0 != ps:
+                    continue
+                m = sib.count(v)
+            row = col[rowptr[v] : rowptr[v + 1]]
+            arr = np.repeat(row, m)  # sorted(m copies of a sorted list)
+            order = np_perm(len(arr), prev_sums[ps], cur_seed)[:f]
+            sel = arr[order]
+            out[ps * f : ps * f + len(sel)] = sel
+            oc[ps] = len(sel)
+            for j, s in enumerate(sel):
+                sums[ps * f + j] = _wrap32(prev_sums[ps] + int(s))
+        nbr.append(out)
+        cnt.append(oc)
+        prev_vals = [int(x) for x in out]
+        prev_sums = sums
+        width_prev *= f
+    return nbr, cnt
+
+
+def tree_to_edges(roots, nbr, fanouts):
+    """Padded tree -> per-root list of (src, dst) index pairs, src = hop-k node, dst = hop-(k-1)
+    node (SGSPureSparkV1Task.scala:615-629), one pair per sampled slot (explode semantics)."""
+    n_roots = len(roots)
+    res = [[] for _ in range(n_roots)]
+    prev = np.asarray(roots, dtype=np.int64)
+    width_prev = 1
+    for h, f in enumerate(fanouts):
+        f = int(f)
+        cur = np.asarray(nbr[h], dtype=np.int64)
+        for r in range(n_roots):
+            for ps in range(width_prev):
+                p = prev[r * width_prev + ps]
+                if p < 0:
+                    continue
+                for j in range(f):
+                    c = cur[(r * width_prev + ps) * f + j]
+                    if c >= 0:
+                        res[r].append((int(c), int(p)))
+        prev = cur
+        width_prev *= f
+    return res
+
+
+# ----------------------------------------------------------------------------------------
+# aggregate
+# ----------------------------------------------------------------------------------------
+def _coo(edge_index):
+    ei = np.asarray(edge_index)
+    return np.ascontiguousarray(ei[0], dtype=np.int64), np.ascontiguousarray(ei[1], dtype=np.int64)
+
+
+def c_sage_conv(x, edge_index, Wl, bl, Wr, relu=False, f64=False, n_threads=None):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    src, dst = _coo(edge_index)
+    Wl = np.ascontiguousarray(Wl, dtype=np.float32)
+    Wr = np.ascontiguousarray(Wr, dtype=np.float32)
+    bl = None if bl is None else np.ascontiguousarray(bl, dtype=np.float32)
+    n, F = x.shape
+    O = Wl.shape[0]
+    out = np.empty((n, O), dtype=np.float64 if f64 else np.float32)
+    fn = lib().oracle_sage_conv_f64 if f64 else lib().oracle_sage_conv_f32
+    rc = fn(n, len(src), F, O, _ptr(src), _ptr(dst), _ptr(x), _ptr(Wl), _ptr(bl), _ptr(Wr), _ptr(out),
+            int(relu), n_threads or (os.cpu_count() or 1))
+    if rc != 0:
+        raise RuntimeError(f"oracle_sage_conv failed rc={rc}")
+    return out
+
+
+def np_sage_conv(x, edge_index, Wl, bl, Wr, relu=False):
+    """fp64 numpy restatement (np.add.at == index_add_)."""
+    x = np.asarray(x, dtype=np.float64)
+    src, dst = _coo(edge_index)
+    n = x.shape[0]
+    agg = np.zeros_like(x)
+    np.add.at(agg, dst, x[src])
+    c = np.bincount(dst, minlength=n).clip(min=1)[:, None]
+    out = (agg / c) @ np.asarray(Wl, np.float64).T + x @ np.asarray(Wr, np.float64).T
+    if bl is not None:
+        out = out + np.asarray(bl, np.float64)
+    return np.maximum(out, 0) if relu else out
+
+
+def c_gcn_conv(x, edge_index, W, b, relu=False, f64=False):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    src, dst = _coo(edge_index)
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    b = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+    n, F = x.shape
+    O = W.shape[0]
+    out = np.empty((n, O), dtype=np.float64 if f64 else np.float32)
+    fn = lib().oracle_gcn_conv_f64 if f64 else lib().oracle_gcn_conv_f32
+    rc = fn(n, len(src), F, O, _ptr(src), _ptr(dst), _ptr(x), _ptr(W), _ptr(b), _ptr(out), int(relu))
+    if rc != 0:
+        raise RuntimeError(f"oracle_gcn_conv failed rc={rc}")
+    return out
+
+
+def np_gcn_conv(x, edge_index, W, b, relu=False):
+    x = np.asarray(x, dtype=np.float64)
+    src, dst = _coo(edge_index)
+    n = x.shape[0]
+    keep = src != dst
+    src = np.concatenate([src[keep], np.arange(n)])
+    dst = np.concatenate([dst[keep], np.arange(n)])
+    deg = np.bincount(dst, minlength=n).astype(np.float64)
+    dis = deg**-0.5
+    xp = x @ np.asarray(W, np.float64).T
+    out = np.zeros((n, xp.shape[1]))
+    np.add.at(out, dst, (dis[src] * dis[dst])[:, None] * xp[src])
+    if b is not None:
+        out = out + np.asarray(b, np.float64)
+    return np.maximum(out, 0) if relu else out
+
+
+def sage_model(x, edge_index, layers, f64=False):
+    """GraphSAGE (BasicGNN) forward: relu between layers, none after the last.
+    ``layers`` = [(Wl, bl, Wr), ...]  (graphsage_template_modeling_spec.py:143-148)."""
+    h = x
+    for li, (Wl, bl, Wr) in enumerate(layers):
+        last = li == len(layers) - 1
+        h = c_sage_conv(np.asarray(h, np.float32), edge_index, Wl, bl, Wr, relu=not last, f64=f64)
+    return h
