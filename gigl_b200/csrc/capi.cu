@@ -1,0 +1,452 @@
+// capi.cu - the extern "C" surface of libgigl_b200.so (include/gigl_b200.h): context, graph
+// residency, COO->CSR conversion and the host-buffer entry points a JNI / ctypes binding calls.
+// The kernels live in khop_sample.cu / sage_aggregate.cu / graph_build.cu.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+// ---- error plumbing -------------------------------------------------------------------------
+static thread_local std::string g_null_ctx_err;
+
+int gigl_fail(gigl_ctx* ctx, int code, const std::string& msg) {
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_null_ctx_err = msg;
+    return code;
+}
+
+int gigl_cuda_fail(gigl_ctx* ctx, cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return gigl_fail(ctx, e == cudaErrorMemoryAllocation ? GIGL_E_NOMEM : GIGL_E_CUDA, m);
+}
+
+int gigl_scratch(gigl_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (slot < 0 || slot >= GIGL_SCRATCH_SLOTS) return gigl_fail(ctx, GIGL_E_INVALID, "bad scratch slot");
+    if (bytes < 256) bytes = 256;
+    if (ctx->scratch_bytes[slot] < bytes) {
+        // growth is rare (sizes are sticky); cudaFree synchronises the device, so work already
+        // enqueued on the old buffer has finished before it is released
+        if (ctx->scratch[slot]) {
+            GIGL_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t want = bytes + bytes / 4;
+        want = (want + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+        if (e != cudaSuccess) {
+            want = (bytes + 255) & ~(size_t)255;
+            e = cudaMalloc(&ctx->scratch[slot], want);
+        }
+        if (e != cudaSuccess) return gigl_cuda_fail(ctx, e, "cudaMalloc(scratch)");
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return GIGL_OK;
+}
+
+static int ctx_check_device_error(gigl_ctx* ctx) {
+    GIGL_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int32_t code = *ctx->h_err;
+    if (code != 0) {
+        GIGL_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream));
+        if (code == GIGL_E_RANGE) return gigl_fail(ctx, GIGL_E_RANGE, "a vertex id outside [0, n_nodes) was met on the device");
+        if (code == GIGL_E_OVERFLOW) return gigl_fail(ctx, GIGL_E_OVERFLOW, "a row (times its multiplicity) exceeds 2^31-1 entries");
+        return gigl_fail(ctx, code, "device-side error");
+    }
+    return GIGL_OK;
+}
+
+// Shared by the two *_conv_host entry points: stage x / edge_index / weights, COO->CSR, run `layer`.
+template <typename LayerFn>
+static int conv_host_common(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O, const int64_t* edge_index,
+                            const float* x, const float* const* weights, const size_t* weight_elems, int n_weights,
+                            float* out, LayerFn layer) {
+    GIGL_CHECK(ctx, n >= 0 && n <= 0x7fffffffLL && e >= 0 && F >= 1 && O >= 1, "bad sizes");
+    GIGL_CHECK(ctx, n == 0 || (x && out), "null x / out");
+    GIGL_CHECK(ctx, e == 0 || edge_index, "null edge_index");
+    if (n == 0) return GIGL_OK;
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *p_x = nullptr, *p_ei = nullptr, *p_csr = nullptr, *p_w = nullptr, *p_out = nullptr;
+    int rc;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO0, sizeof(float) * (size_t)n * F, &p_x)) != GIGL_OK) return rc;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO1, sizeof(int64_t) * 2 * (size_t)(e > 0 ? e : 1), &p_ei)) != GIGL_OK) return rc;
+    const size_t rowptr_bytes = (sizeof(int64_t) * (size_t)(n + 1) + 255) & ~(size_t)255;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO2, rowptr_bytes + sizeof(int32_t) * (size_t)(e > 0 ? e : 1), &p_csr)) != GIGL_OK) return rc;
+    size_t w_total = 0;
+    size_t w_off[4];
+    for (int i = 0; i < n_weights; ++i) {
+        w_off[i] = w_total;
+        w_total += (weight_elems[i] + 3) & ~(size_t)3;
+    }
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO3, sizeof(float) * (w_total > 0 ? w_total : 1), &p_w)) != GIGL_OK) return rc;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO4, sizeof(float) * (size_t)n * O, &p_out)) != GIGL_OK) return rc;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(p_x, x, sizeof(float) * (size_t)n * F, cudaMemcpyHostToDevice, ctx->stream));
+    if (e > 0)
+        GIGL_CUDA(ctx, cudaMemcpyAsync(p_ei, edge_index, sizeof(int64_t) * 2 * (size_t)e, cudaMemcpyHostToDevice, ctx->stream));
+    const float* w_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < n_weights; ++i) {
+        if (!weights[i]) continue;
+        w_dev[i] = (float*)p_w + w_off[i];
+        GIGL_CUDA(ctx, cudaMemcpyAsync((void*)w_dev[i], weights[i], sizeof(float) * weight_elems[i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int64_t* rowptr = (int64_t*)p_csr;
+    int32_t* col = (int32_t*)((char*)p_csr + rowptr_bytes);
+    const int64_t* ei = (const int64_t*)p_ei;
+    if ((rc = csr_from_coo_launch(ctx, n, e, ei, ei + e, rowptr, col)) != GIGL_OK) return rc;
+    if ((rc = layer(rowptr, col, (const float*)p_x, w_dev, (float*)p_out)) != GIGL_OK) return rc;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(out, p_out, sizeof(float) * (size_t)n * O, cudaMemcpyDeviceToHost, ctx->stream));
+    return ctx_check_device_error(ctx);
+}
+
+extern "C" {
+
+const char* gigl_version(void) { return "gigl_b200 0.1.0 sm_100a"; }
+
+static int ctx_create_common(int device, void* stream, bool own, gigl_ctx** out) {
+    if (!out) return gigl_fail(nullptr, GIGL_E_INVALID, "null out pointer");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return gigl_fail(nullptr, GIGL_E_CUDA, "no usable CUDA device (libgigl_b200 has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return gigl_fail(nullptr, GIGL_E_INVALID, "device index out of range");
+    gigl_ctx* ctx = new (std::nothrow) gigl_ctx();
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_NOMEM, "out of host memory");
+    ctx->device = device;
+    auto bail = [&](cudaError_t err, const char* what) {
+        int rc = gigl_cuda_fail(nullptr, err, what);
+        delete ctx;
+        return rc;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        delete ctx;
+        return gigl_fail(nullptr, GIGL_E_CUDA, "libgigl_b200 is built for sm_100a only; this device is not compute capability 10.x");
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (own) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail(e, "cudaStreamCreate");
+        ctx->own_stream = true;
+    } else {
+        ctx->stream = (cudaStream_t)stream;
+    }
+    if ((e = cudaMalloc(&ctx->d_err, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc(err)");
+    if ((e = cudaMemset(ctx->d_err, 0, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMemset(err)");
+    if ((e = cudaMallocHost(&ctx->h_err, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMallocHost(err)");
+    *ctx->h_err = 0;
+    *out = ctx;
+    return GIGL_OK;
+}
+
+int gigl_ctx_create(int device, gigl_ctx** out) { return ctx_create_common(device, nullptr, true, out); }
+
+int gigl_ctx_create_on_stream(int device, void* cuda_stream, gigl_ctx** out) {
+    return ctx_create_common(device, cuda_stream, false, out);
+}
+
+void gigl_ctx_destroy(gigl_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < GIGL_SCRATCH_SLOTS; ++s)
+        if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
+    if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int gigl_ctx_sync(gigl_ctx* ctx) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ctx_check_device_error(ctx);
+}
+
+const char* gigl_last_error(gigl_ctx* ctx) { return ctx ? ctx->err.c_str() : g_null_ctx_err.c_str(); }
+
+int64_t gigl_ctx_launch_count(gigl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* gigl_ctx_stream(gigl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---- graph ---------------------------------------------------------------------------------
+
+static int graph_new(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int64_t* rowptr, const int32_t* col,
+                     bool owned, gigl_graph** out) {
+    gigl_graph* g = new (std::nothrow) gigl_graph();
+    if (!g) return gigl_fail(ctx, GIGL_E_NOMEM, "out of host memory");
+    g->ctx = ctx;
+    g->n_nodes = n_nodes;
+    g->n_edges = n_edges;
+    g->rowptr = rowptr;
+    g->col = col;
+    g->owned = owned;
+    *out = g;
+    return GIGL_OK;
+}
+
+int gigl_graph_create_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int64_t* rowptr,
+                           const int32_t* col, gigl_graph** out) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, out != nullptr, "null out pointer");
+    *out = nullptr;
+    GIGL_CHECK(ctx, n_nodes >= 0 && n_nodes <= 0x7fffffffLL, "n_nodes must be in [0, 2^31-1]");
+    GIGL_CHECK(ctx, n_edges >= 0, "n_edges < 0");
+    GIGL_CHECK(ctx, rowptr != nullptr && (col != nullptr || n_edges == 0), "null rowptr / col");
+    GIGL_CHECK(ctx, rowptr[0] == 0 && rowptr[n_nodes] == n_edges, "rowptr[0] must be 0 and rowptr[n_nodes] == n_edges");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t* d_rowptr = nullptr;
+    int32_t* d_col = nullptr;
+    GIGL_CUDA(ctx, cudaMalloc(&d_rowptr, sizeof(int64_t) * (size_t)(n_nodes + 1)));
+    cudaError_t e = cudaMalloc(&d_col, sizeof(int32_t) * (size_t)(n_edges > 0 ? n_edges : 1));
+    if (e != cudaSuccess) {
+        cudaFree(d_rowptr);
+        return gigl_cuda_fail(ctx, e, "cudaMalloc(col)");
+    }
+    e = cudaMemcpyAsync(d_rowptr, rowptr, sizeof(int64_t) * (size_t)(n_nodes + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n_edges > 0)
+        e = cudaMemcpyAsync(d_col, col, sizeof(int32_t) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d_rowptr);
+        cudaFree(d_col);
+        return gigl_cuda_fail(ctx, e, "graph upload");
+    }
+    int rc = graph_new(ctx, n_nodes, n_edges, d_rowptr, d_col, true, out);
+    if (rc != GIGL_OK) {
+        cudaFree(d_rowptr);
+        cudaFree(d_col);
+    }
+    return rc;
+}
+
+int gigl_graph_wrap_dev(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int64_t* rowptr_dev,
+                        const int32_t* col_dev, gigl_graph** out) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, out != nullptr, "null out pointer");
+    *out = nullptr;
+    GIGL_CHECK(ctx, n_nodes >= 0 && n_nodes <= 0x7fffffffLL, "n_nodes must be in [0, 2^31-1]");
+    GIGL_CHECK(ctx, n_edges >= 0, "n_edges < 0");
+    GIGL_CHECK(ctx, rowptr_dev != nullptr && (col_dev != nullptr || n_edges == 0), "null rowptr / col");
+    return graph_new(ctx, n_nodes, n_edges, rowptr_dev, col_dev, false, out);
+}
+
+int gigl_graph_from_edges_dev(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,
+                              const int32_t* dst_dev, int32_t is_graph_directed, int32_t by_source,
+                              gigl_graph** out) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, out != nullptr, "null out pointer");
+    *out = nullptr;
+    GIGL_CHECK(ctx, n_nodes >= 0 && n_nodes <= 0x7fffffffLL, "n_nodes must be in [0, 2^31-1]");
+    GIGL_CHECK(ctx, n_edges >= 0, "n_edges < 0");
+    GIGL_CHECK(ctx, (src_dev && dst_dev) || n_edges == 0, "null edge arrays");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t* d_rowptr = nullptr;
+    int32_t* d_col = nullptr;
+    int64_t e_out = 0;
+    int rc = graph_from_edges_build(ctx, n_nodes, n_edges, src_dev, dst_dev, is_graph_directed, by_source, &d_rowptr,
+                                    &d_col, &e_out);
+    if (rc != GIGL_OK) return rc;
+    rc = graph_new(ctx, n_nodes, e_out, d_rowptr, d_col, true, out);
+    if (rc != GIGL_OK) {
+        cudaFree(d_rowptr);
+        cudaFree(d_col);
+    }
+    return rc;
+}
+
+int gigl_graph_from_edges_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src,
+                               const int32_t* dst, int32_t is_graph_directed, int32_t by_source,
+                               gigl_graph** out) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, out != nullptr, "null out pointer");
+    *out = nullptr;
+    GIGL_CHECK(ctx, n_edges >= 0, "n_edges < 0");
+    GIGL_CHECK(ctx, (src && dst) || n_edges == 0, "null edge arrays");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int32_t* d_sd = nullptr;
+    const size_t ne = (size_t)(n_edges > 0 ? n_edges : 1);
+    GIGL_CUDA(ctx, cudaMalloc(&d_sd, sizeof(int32_t) * 2 * ne));
+    cudaError_t e = cudaSuccess;
+    if (n_edges > 0) {
+        e = cudaMemcpyAsync(d_sd, src, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_sd + ne, dst, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(d_sd);
+        return gigl_cuda_fail(ctx, e, "edge list upload");
+    }
+    int rc = gigl_graph_from_edges_dev(ctx, n_nodes, n_edges, d_sd, d_sd + ne, is_graph_directed, by_source, out);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sd);
+    return rc;
+}
+
+int gigl_graph_num_nodes(const gigl_graph* g, int64_t* n_nodes, int64_t* n_edges) {
+    if (!g) return GIGL_E_INVALID;
+    if (n_nodes) *n_nodes = g->n_nodes;
+    if (n_edges) *n_edges = g->n_edges;
+    return GIGL_OK;
+}
+
+int gigl_graph_device_ptrs(const gigl_graph* g, const int64_t** rowptr_dev, const int32_t** col_dev) {
+    if (!g) return GIGL_E_INVALID;
+    if (rowptr_dev) *rowptr_dev = g->rowptr;
+    if (col_dev) *col_dev = g->col;
+    return GIGL_OK;
+}
+
+void gigl_graph_destroy(gigl_graph* g) {
+    if (!g) return;
+    if (g->owned) {
+        cudaSetDevice(g->ctx->device);
+        cudaStreamSynchronize(g->ctx->stream);
+        cudaFree((void*)g->rowptr);
+        cudaFree((void*)g->col);
+    }
+    delete g;
+}
+
+// ---- sampling ------------------------------------------------------------------------------
+
+int gigl_sample_khop_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                         int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
+                         int32_t* const* cnt_dev) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    GIGL_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    return khop_sample_launch(g, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
+}
+
+int gigl_sample_khop_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, const int32_t* fanouts,
+                          int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr,
+                          int32_t* const* cnt) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS, "n_hops must be in [1, 8]");
+    GIGL_CHECK(ctx, n_roots >= 0, "n_roots < 0");
+    GIGL_CHECK(ctx, fanouts && nbr && cnt, "null fanouts / output tables");
+    GIGL_CHECK(ctx, roots || n_roots == 0, "null roots");
+    for (int h = 0; h < n_hops; ++h) {
+        GIGL_CHECK(ctx, fanouts[h] >= 1 && fanouts[h] <= GIGL_MAX_FANOUT, "fanout must be in [1, 128]");
+        GIGL_CHECK(ctx, (nbr[h] && cnt[h]) || n_roots == 0, "null output level");
+    }
+    if (n_roots == 0) return GIGL_OK;
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // one staging buffer: roots | cnt[0] nbr[0] | cnt[1] nbr[1] | ...  (int32 each)
+    size_t total = (size_t)n_roots;
+    size_t width = 1;
+    size_t off_cnt[GIGL_MAX_HOPS], off_nbr[GIGL_MAX_HOPS];
+    for (int h = 0; h < n_hops; ++h) {
+        off_cnt[h] = total;
+        total += (size_t)n_roots * width;
+        width *= (size_t)fanouts[h];
+        if ((double)n_roots * (double)width > 2147483647.0)
+            return gigl_fail(ctx, GIGL_E_INVALID, "frontier exceeds 2^31-1 slots; split the roots");
+        off_nbr[h] = total;
+        total += (size_t)n_roots * width;
+    }
+    void* buf = nullptr;
+    int rc = gigl_scratch(ctx, GIGL_SLOT_IO0, sizeof(int32_t) * total, &buf);
+    if (rc != GIGL_OK) return rc;
+    int32_t* d = (int32_t*)buf;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(d, roots, sizeof(int32_t) * (size_t)n_roots, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t* nbr_dev[GIGL_MAX_HOPS];
+    int32_t* cnt_dev[GIGL_MAX_HOPS];
+    for (int h = 0; h < n_hops; ++h) {
+        nbr_dev[h] = d + off_nbr[h];
+        cnt_dev[h] = d + off_cnt[h];
+    }
+    rc = khop_sample_launch(g, d, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
+    if (rc != GIGL_OK) return rc;
+    width = 1;
+    for (int h = 0; h < n_hops; ++h) {
+        GIGL_CUDA(ctx, cudaMemcpyAsync(cnt[h], cnt_dev[h], sizeof(int32_t) * (size_t)n_roots * width,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        width *= (size_t)fanouts[h];
+        GIGL_CUDA(ctx, cudaMemcpyAsync(nbr[h], nbr_dev[h], sizeof(int32_t) * (size_t)n_roots * width,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return ctx_check_device_error(ctx);
+}
+
+int gigl_sample_positives_host(gigl_graph* g_out, const int32_t* srcs, int64_t n_srcs, int32_t num_pos,
+                               int32_t base_seed, int32_t call_no, int32_t* pos, int32_t* pos_cnt) {
+    int32_t* nbr[1] = {pos};
+    int32_t* cnt[1] = {pos_cnt};
+    return gigl_sample_khop_host(g_out, srcs, n_srcs, &num_pos, 1, base_seed, call_no, nbr, cnt);
+}
+
+// ---- aggregate -----------------------------------------------------------------------------
+
+int gigl_csr_from_coo_dev(gigl_ctx* ctx, int64_t n, int64_t e, const int64_t* src_dev, const int64_t* dst_dev,
+                          int64_t* rowptr_dev, int32_t* col_dev) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, n >= 0 && n <= 0x7fffffffLL && e >= 0, "bad sizes");
+    GIGL_CHECK(ctx, rowptr_dev != nullptr, "null rowptr");
+    GIGL_CHECK(ctx, e == 0 || (src_dev && dst_dev && col_dev), "null edge arrays");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return csr_from_coo_launch(ctx, n, e, src_dev, dst_dev, rowptr_dev, col_dev);
+}
+
+int gigl_gather_mean_dev(gigl_ctx* ctx, int64_t n_rows_out, int32_t F, const int64_t* rowptr_dev,
+                         const int32_t* col_dev, const float* x_dev, float* agg_dev) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, n_rows_out >= 0 && F >= 1, "bad sizes");
+    GIGL_CHECK(ctx, n_rows_out == 0 || (rowptr_dev && x_dev && agg_dev), "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return gather_mean_launch(ctx, n_rows_out, F, rowptr_dev, col_dev, x_dev, agg_dev);
+}
+
+int gigl_sage_conv_dev(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O,
+                       const int64_t* rowptr_dev, const int32_t* col_dev, const float* x_dev, const float* Wl_dev,
+                       const float* bl_dev, const float* Wr_dev, float* out_dev, int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, n_rows_out == 0 || (rowptr_dev && x_dev && Wl_dev && Wr_dev && out_dev), "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sage_conv_launch(ctx, n, n_rows_out, F, O, rowptr_dev, col_dev, x_dev, Wl_dev, bl_dev, Wr_dev, out_dev, relu);
+}
+
+int gigl_gcn_conv_dev(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr_dev,
+                      const int32_t* col_dev, const float* x_dev, const float* W_dev, const float* b_dev,
+                      float* out_dev, int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, n == 0 || (rowptr_dev && x_dev && W_dev && out_dev), "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return gcn_conv_launch(ctx, n, F, O, rowptr_dev, col_dev, x_dev, W_dev, b_dev, out_dev, relu);
+}
+
+int gigl_sage_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O, const int64_t* edge_index,
+                        const float* x, const float* Wl, const float* bl, const float* Wr, float* out,
+                        int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, Wl && Wr, "null weights");
+    const float* w[3] = {Wl, bl, Wr};
+    const size_t we[3] = {(size_t)O * F, (size_t)O, (size_t)O * F};
+    return conv_host_common(ctx, n, e, F, O, edge_index, x, w, we, 3, out,
+                            [&](const int64_t* rowptr, const int32_t* col, const float* xd, const float* const* wd, float* od) {
+                                return sage_conv_launch(ctx, n, n, F, O, rowptr, col, xd, wd[0], wd[1], wd[2], od, relu);
+                            });
+}
+
+int gigl_gcn_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O, const int64_t* edge_index,
+                       const float* x, const float* W, const float* b, float* out, int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, W != nullptr, "null weights");
+    const float* w[2] = {W, b};
+    const size_t we[2] = {(size_t)O * F, (size_t)O};
+    return conv_host_common(ctx, n, e, F, O, edge_index, x, w, we, 2, out,
+                            [&](const int64_t* rowptr, const int32_t* col, const float* xd, const float* const* wd, float* od) {
+                                return gcn_conv_launch(ctx, n, F, O, rowptr, col, xd, wd[0], wd[1], od, relu);
+                            });
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// common.cuh - context object, error plumbing and launch helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/gigl_b200.h"
+
+// scratch slot ids: a launch sequence that needs several live buffers uses distinct slots
+enum {
+    GIGL_SLOT_WORK = 0,   // sampler worklists / CUB temp storage
+    GIGL_SLOT_AGG = 1,    // aggregate intermediates (agg rows, x', dinv)
+    GIGL_SLOT_SORT = 2,   // COO->CSR sort keys / values
+    GIGL_SLOT_IO0 = 3,    // host-entry-point staging: inputs
+    GIGL_SLOT_IO1 = 4,    // host-entry-point staging: outputs
+    GIGL_SLOT_IO2 = 5,    // host-entry-point staging: csr
+    GIGL_SLOT_IO3 = 6,
+    GIGL_SLOT_IO4 = 7,
+    GIGL_SCRATCH_SLOTS = 8
+};
+
+struct gigl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    int64_t launches = 0;
+    std::string err;
+    // device-side error word written by kernels (0 = ok, else a GIGL_E_* code) + its pinned host mirror
+    int32_t* d_err = nullptr;
+    int32_t* h_err = nullptr;
+    // growable device scratch slots (worklists, partial buffers, staging); never shrink
+    void* scratch[GIGL_SCRATCH_SLOTS] = {};
+    size_t scratch_bytes[GIGL_SCRATCH_SLOTS] = {};
+};
+
+struct gigl_graph {
+    gigl_ctx* ctx = nullptr;
+    int64_t n_nodes = 0;
+    int64_t n_edges = 0;
+    const int64_t* rowptr = nullptr;  // device
+    const int32_t* col = nullptr;     // device
+    bool owned = false;
+};
+
+int gigl_fail(gigl_ctx* ctx, int code, const std::string& msg);
+int gigl_cuda_fail(gigl_ctx* ctx, cudaError_t e, const char* what);
+// Ensures ctx->scratch[slot] holds >= bytes; returns GIGL_OK or an error code.
+int gigl_scratch(gigl_ctx* ctx, int slot, size_t bytes, void** out);
+
+#define GIGL_CUDA(ctx, call)                                        \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return gigl_cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+#define GIGL_CHECK(ctx, cond, msg)                               \
+    do {                                                         \
+        if (!(cond)) return gigl_fail(ctx, GIGL_E_INVALID, msg); \
+    } while (0)
+
+// Checks the launch and bumps the ctx launch counter.
+#define GIGL_LAUNCHED(ctx)                                                  \
+    do {                                                                    \
+        cudaError_t e__ = cudaGetLastError();                               \
+        if (e__ != cudaSuccess) return gigl_cuda_fail(ctx, e__, "kernel launch"); \
+        (ctx)->launches++;                                                  \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- entry points implemented in the .cu files, called from capi.cu ---------------------
+int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                       int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
+                       int32_t* const* cnt_dev);
+int csr_from_coo_launch(gigl_ctx* ctx, int64_t n, int64_t e, const int64_t* src, const int64_t* dst,
+                        int64_t* rowptr, int32_t* col);
+int graph_from_edges_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,
+                           const int32_t* dst_dev, int32_t directed, int32_t by_source, int64_t** rowptr_dev,
+                           int32_t** col_dev, int64_t* n_edges_out);
+int gather_mean_launch(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t* rowptr, const int32_t* col,
+                       const float* x, float* agg);
+int sage_conv_launch(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O, const int64_t* rowptr,
+                     const int32_t* col, const float* x, const float* Wl, const float* bl, const float* Wr,
+                     float* out, int32_t relu);
+int gcn_conv_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr, const int32_t* col,
+                    const float* x, const float* W, const float* b, float* out, int32_t relu);

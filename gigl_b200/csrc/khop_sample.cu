@@ -1,0 +1,338 @@
+// khop_sample.cu - k-hop rooted-neighbourhood index sampling for sm_100a.
+//
+// Replaces sampleOnehopSrcNodesUniformly / sampleTwohopSrcNodesUniformly
+// (scala/subgraph_sampler/src/main/scala/libs/task/pureSpark/SGSPureSparkV1Task.scala:313-494) and
+// SamplingStrategy.hashBasedUniformPermutation (libs/task/SamplingStrategy.scala:16-82):
+// the GROUP BY / array_sort / xxhash64 / slice pipeline becomes one warp per frontier slot that
+// hashes the row's index window and keeps the `fanout` smallest keys in registers.
+//
+// Key observation: the permutation key of position i depends only on (i, internal_seed, seed),
+// never on the neighbour id stored at i.  So selection is pure integer ALU work on the window
+// x = base+1 .. base+size (base = internal_seed + seed, int32 wrapping) and memory is touched only
+// for the rowptr pair and the <= fanout winning column entries.
+//
+// Layout in HBM: rowptr int64[n+1], col int32[E] (rows sorted ascending), padded-tree outputs
+// nbr[h] int32[n_roots * prod f], cnt[h] int32[n_roots * prod f_{<h}]  (see include/gigl_b200.h).
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "xxh64.cuh"
+
+namespace gigl {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kHeavyThreshold = 4096;   // rows longer than this go to the CTA-per-row pass
+constexpr int kHeavyWarps = 16;
+
+struct HopArgs {
+    const int64_t* rowptr;
+    const int32_t* col;
+    int64_t n_nodes;
+    const int32_t* roots;
+    const int32_t* levels[GIGL_MAX_HOPS];  // levels[k] = nbr of hop k+1 (device), k < h-1
+    int32_t fanouts[GIGL_MAX_HOPS];
+    int32_t h;         // current hop, 1-based
+    int32_t cur_seed;  // base_seed * (first_call_no + h - 1), int32 wrapping
+    int32_t* out_nbr;  // [n_parent * f]
+    int32_t* out_cnt;  // [n_parent]
+    int64_t n_parent;  // parent slots at this hop
+    int32_t* err;      // device error word
+    int32_t* heavy_list;  // worklist of parent slots deferred to the heavy pass
+    int32_t* heavy_count;
+    int32_t heavy_cap;
+};
+
+// Sorted (ascending) best-`f` list held by one warp: position p lives in lane p%32, register p/32.
+template <int KPL>
+struct WarpTopK {
+    uint64_t key[KPL];
+    int32_t idx[KPL];
+    uint64_t kth;  // key at position f-1 (kKeyInf until f entries were inserted)
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            key[k] = kKeyInf;
+            idx[k] = 0;
+        }
+        kth = kKeyInf;
+    }
+
+    // Insert (ck, ci), warp-uniform arguments, ck < kth.
+    __device__ __forceinline__ void insert(uint64_t ck, int32_t ci, int f, int lane) {
+        int pos = 0;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) pos += __popc(__ballot_sync(0xffffffffu, key[k] < ck));
+#pragma unroll
+        for (int k = KPL - 1; k >= 0; --k) {
+            uint64_t upk = __shfl_up_sync(0xffffffffu, key[k], 1);
+            int32_t upi = __shfl_up_sync(0xffffffffu, idx[k], 1);
+            if (k > 0) {
+                uint64_t pk = __shfl_sync(0xffffffffu, key[k - 1], 31);
+                int32_t pi = __shfl_sync(0xffffffffu, idx[k - 1], 31);
+                if (lane == 0) {
+                    upk = pk;
+                    upi = pi;
+                }
+            }
+            const int p = k * 32 + lane;
+            if (p > pos) {
+                key[k] = upk;
+                idx[k] = upi;
+            } else if (p == pos) {
+                key[k] = ck;
+                idx[k] = ci;
+            }
+        }
+        refresh_kth(f);
+    }
+
+    __device__ __forceinline__ void refresh_kth(int f) {
+        const int p = f - 1;
+        uint64_t v = kKeyInf;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            uint64_t t = __shfl_sync(0xffffffffu, key[k], p & 31);
+            if ((p >> 5) == k) v = t;
+        }
+        kth = v;
+    }
+
+    // Scan window positions [i_begin, i_end] (1-based, inclusive) with stride `stride` chunks of 32.
+    __device__ __forceinline__ void scan(int64_t i_first_chunk, int64_t size, int64_t chunk_stride, uint32_t base,
+                                         int f, int lane) {
+        for (int64_t c0 = i_first_chunk; c0 < size; c0 += chunk_stride) {
+            const int64_t i = c0 + lane + 1;  // 1-based index as F.sequence(1, size)
+            uint64_t k = kKeyInf;
+            if (i <= size) k = ordered_key((int32_t)(base + (uint32_t)i));
+            uint32_t cand = __ballot_sync(0xffffffffu, k < kth);
+            while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const uint64_t ck = __shfl_sync(0xffffffffu, k, src);
+                if (ck < kth) insert(ck, (int32_t)(c0 + src + 1), f, lane);
+            }
+        }
+    }
+};
+
+// Resolves parent vertex, path-id sum and sibling multiplicity for one parent slot (warp-uniform).
+// Returns false if the slot produces no group (empty parent or a non-first duplicate).
+__device__ __forceinline__ bool resolve_parent(const HopArgs& a, int64_t pslot, int lane, int32_t& v, uint32_t& ssum,
+                                               int32_t& mult) {
+    mult = 1;
+    if (a.h == 1) {
+        v = a.roots[pslot];
+        ssum = (uint32_t)v;
+        return true;
+    }
+    const int32_t* prev = a.levels[a.h - 2];
+    v = prev[pslot];
+    if (v < 0) return false;
+    ssum = (uint32_t)v;
+    int64_t s = pslot;
+    for (int hh = a.h - 1; hh >= 1; --hh) {
+        s /= a.fanouts[hh - 1];
+        ssum += (uint32_t)(hh == 1 ? a.roots[s] : a.levels[hh - 2][s]);
+    }
+    const int fp = a.fanouts[a.h - 2];
+    const int64_t sib0 = (pslot / fp) * fp;
+    const int me = (int)(pslot - sib0);
+    int m = 0;
+    bool first = true;
+    for (int j0 = 0; j0 < fp; j0 += 32) {
+        const int j = j0 + lane;
+        const int32_t sv = (j < fp) ? prev[sib0 + j] : -1;
+        const uint32_t eq = __ballot_sync(0xffffffffu, sv == v);
+        m += __popc(eq);
+        if (me >= j0) {
+            const int upto = me - j0;  // bits strictly below my own position in this word
+            const uint32_t below = upto >= 32 ? eq : (eq & ((1u << upto) - 1u));
+            if (below) first = false;
+        }
+    }
+    mult = m;
+    return first;
+}
+
+template <int KPL>
+__device__ __forceinline__ void write_result(const HopArgs& a, int64_t pslot, const WarpTopK<KPL>& best, int64_t size,
+                                             int64_t row_begin, int32_t mult, int lane) {
+    const int f = a.fanouts[a.h - 1];
+    const int n_out = (int)(size < f ? size : f);
+    int32_t* o = a.out_nbr + pslot * f;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+        const int p = k * 32 + lane;
+        if (p < f) {
+            int32_t r = -1;
+            if (p < n_out) {
+                const int64_t j = (int64_t)(best.idx[k] - 1) / mult;  // sorted(m copies)[q] = row[q / m]
+                r = __ldg(a.col + row_begin + j);
+            }
+            o[p] = r;
+        }
+    }
+    if (lane == 0) a.out_cnt[pslot] = n_out;
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_hop_kernel(const HopArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t pslot = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (pslot >= a.n_parent) return;
+    const int f = a.fanouts[a.h - 1];
+    int32_t v, mult;
+    uint32_t ssum;
+    const bool live = resolve_parent(a, pslot, lane, v, ssum, mult);
+    int64_t size = 0, row_begin = 0;
+    bool ok = live;
+    if (live) {
+        if (v < 0 || v >= a.n_nodes) {
+            if (lane == 0) atomicExch(a.err, GIGL_E_RANGE);
+            ok = false;
+        } else {
+            row_begin = __ldg(a.rowptr + v);
+            size = (__ldg(a.rowptr + v + 1) - row_begin) * mult;
+            if (size > 2147483647LL) {
+                if (lane == 0) atomicExch(a.err, GIGL_E_OVERFLOW);
+                ok = false;
+            }
+        }
+    }
+    if (!ok) {
+        int32_t* o = a.out_nbr + pslot * f;
+        for (int p = lane; p < f; p += 32) o[p] = -1;
+        if (lane == 0) a.out_cnt[pslot] = 0;
+        return;
+    }
+    if (size > kHeavyThreshold && a.heavy_list != nullptr) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(a.heavy_count, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < a.heavy_cap) {
+            if (lane == 0) a.heavy_list[slot] = (int32_t)pslot;
+            return;
+        }
+        // worklist full: fall through and do the long row with this warp alone (still exact)
+    }
+    WarpTopK<KPL> best;
+    best.init();
+    best.scan(0, size, 32, ssum + (uint32_t)a.cur_seed, f, lane);
+    write_result<KPL>(a, pslot, best, size, row_begin, mult, lane);
+}
+
+// One CTA per deferred long row: every warp scans an interleaved share of the window with its own
+// top-f list, then warp 0 merges the lists through shared memory.
+template <int KPL>
+__global__ void __launch_bounds__(kHeavyWarps * 32) khop_heavy_kernel(const HopArgs a) {
+    __shared__ uint64_t s_key[kHeavyWarps][32 * KPL];
+    __shared__ int32_t s_idx[kHeavyWarps][32 * KPL];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int f = a.fanouts[a.h - 1];
+    int n_heavy = *a.heavy_count;
+    if (n_heavy > a.heavy_cap) n_heavy = a.heavy_cap;
+    for (int w = blockIdx.x; w < n_heavy; w += gridDim.x) {
+        const int64_t pslot = a.heavy_list[w];
+        int32_t v, mult;
+        uint32_t ssum;
+        resolve_parent(a, pslot, lane, v, ssum, mult);  // already validated by the first pass
+        const int64_t row_begin = __ldg(a.rowptr + v);
+        const int64_t size = (__ldg(a.rowptr + v + 1) - row_begin) * mult;
+        WarpTopK<KPL> best;
+        best.init();
+        best.scan((int64_t)warp * 32, size, (int64_t)kHeavyWarps * 32, ssum + (uint32_t)a.cur_seed, f, lane);
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            s_key[warp][k * 32 + lane] = best.key[k];
+            s_idx[warp][k * 32 + lane] = best.idx[k];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int ow = 1; ow < kHeavyWarps; ++ow) {
+                for (int p = 0; p < f; ++p) {
+                    const uint64_t ck = s_key[ow][p];
+                    if (ck >= best.kth) break;  // lists are sorted ascending
+                    best.insert(ck, s_idx[ow][p], f, lane);
+                }
+            }
+            write_result<KPL>(a, pslot, best, size, row_begin, mult, lane);
+        }
+        __syncthreads();
+    }
+}
+
+template <int KPL>
+static int launch_hop(gigl_ctx* ctx, const HopArgs& a) {
+    const int64_t blocks = ceil_div64(a.n_parent, kWarpsPerBlock);
+    if (blocks > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "too many frontier slots for one launch");
+    if (blocks > 0) {
+        khop_hop_kernel<KPL><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+        GIGL_LAUNCHED(ctx);
+        if (a.heavy_list != nullptr) {
+            const int grid = ctx->sm_count * 2;
+            khop_heavy_kernel<KPL><<<grid, kHeavyWarps * 32, 0, ctx->stream>>>(a);
+            GIGL_LAUNCHED(ctx);
+        }
+    }
+    return GIGL_OK;
+}
+
+}  // namespace gigl
+
+int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                       int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
+                       int32_t* const* cnt_dev) {
+    using namespace gigl;
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS, "n_hops must be in [1, 8]");
+    GIGL_CHECK(ctx, n_roots >= 0, "n_roots < 0");
+    GIGL_CHECK(ctx, fanouts && nbr_dev && cnt_dev, "null fanouts / output tables");
+    GIGL_CHECK(ctx, roots_dev || n_roots == 0, "null roots");
+    for (int h = 0; h < n_hops; ++h) {
+        GIGL_CHECK(ctx, fanouts[h] >= 1 && fanouts[h] <= GIGL_MAX_FANOUT, "fanout must be in [1, 128]");
+        GIGL_CHECK(ctx, (nbr_dev[h] && cnt_dev[h]) || n_roots == 0, "null output level");
+    }
+    if (n_roots == 0) return GIGL_OK;
+
+    // heavy-row worklist: one int32 counter + up to heavy_cap slots, reused hop after hop
+    const int32_t heavy_cap = 1 << 22;
+    void* scratch = nullptr;
+    int rc = gigl_scratch(ctx, GIGL_SLOT_WORK, sizeof(int32_t) * ((size_t)heavy_cap + 64), &scratch);
+    if (rc != GIGL_OK) return rc;
+    int32_t* heavy_count = (int32_t*)scratch;
+    int32_t* heavy_list = heavy_count + 64;
+
+    HopArgs a{};
+    a.rowptr = g->rowptr;
+    a.col = g->col;
+    a.n_nodes = g->n_nodes;
+    a.roots = roots_dev;
+    a.err = ctx->d_err;
+    a.heavy_list = heavy_list;
+    a.heavy_count = heavy_count;
+    a.heavy_cap = heavy_cap;
+    int64_t n_parent = n_roots;
+    for (int h = 1; h <= n_hops; ++h) {
+        const int32_t f = fanouts[h - 1];
+        a.fanouts[h - 1] = f;
+        if (h >= 2) a.levels[h - 2] = nbr_dev[h - 2];
+        a.h = h;
+        a.cur_seed = (int32_t)((uint32_t)base_seed * ((uint32_t)first_call_no + (uint32_t)(h - 1)));
+        a.out_nbr = nbr_dev[h - 1];
+        a.out_cnt = cnt_dev[h - 1];
+        a.n_parent = n_parent;
+        if (n_parent > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "frontier exceeds 2^31-1 slots; split the roots");
+        GIGL_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, sizeof(int32_t), ctx->stream));
+        if (f <= 32)
+            rc = launch_hop<1>(ctx, a);
+        else if (f <= 64)
+            rc = launch_hop<2>(ctx, a);
+        else
+            rc = launch_hop<4>(ctx, a);
+        if (rc != GIGL_OK) return rc;
+        n_parent *= f;
+    }
+    return GIGL_OK;
+}

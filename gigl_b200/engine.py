@@ -1,0 +1,289 @@
+"""Thin object layer over the C-ABI: one :class:`Context` per GPU, :class:`Graph` = CSR resident in HBM.
+
+Host-buffer methods (``*_host``) take numpy arrays and go through the ``gigl_*_host`` entry points
+(what a JNI binding would call; H2D/D2H inside).  Device methods take torch CUDA tensors and only
+pass their ``data_ptr()`` to the ``gigl_*_dev`` entry points - torch is used for device memory
+and streams, never for arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import GiglError, check  # noqa: F401
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _hp(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(t):
+    """device pointer of a torch CUDA tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """gigl_ctx: device + stream + scratch.  Not thread-safe; use one per thread/GPU
+    (mirrors the per-partition setup()/teardown() of the reference's KHopSamplerService,
+    scala_spark35/common/src/main/scala/graphdb/KHopSamplerService.scala:10-33)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._L = _capi.lib()
+        h = C.c_void_p()
+        if stream is None:
+            rc = self._L.gigl_ctx_create(device, C.byref(h))
+        else:
+            rc = self._L.gigl_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h))
+        check(rc, None)
+        self.handle = h
+        self.device = device
+
+    @classmethod
+    def on_torch_stream(cls, device: int = 0) -> "Context":
+        """Enqueue on torch's current stream of ``device`` so torch tensors and events order naturally."""
+        import torch
+
+        return cls(device, stream=torch.cuda.current_stream(device).cuda_stream)
+
+    def sync(self) -> None:
+        check(self._L.gigl_ctx_sync(self.handle), self.handle)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.gigl_ctx_launch_count(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.gigl_ctx_stream(self.handle) or 0)
+
+    def close(self) -> None:
+        if self.handle:
+            self._L.gigl_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- aggregate, host buffers ---------------------------------------------------------
+    def sage_conv_host(self, x, edge_index, Wl, bl, Wr, relu: bool = False) -> np.ndarray:
+        x = _np(x, np.float32)
+        ei = _np(edge_index, np.int64)
+        Wl, Wr = _np(Wl, np.float32), _np(Wr, np.float32)
+        bl = None if bl is None else _np(bl, np.float32)
+        n, F = x.shape
+        O = Wl.shape[0]
+        assert ei.ndim == 2 and ei.shape[0] == 2 and Wl.shape == (O, F) and Wr.shape == (O, F)
+        out = np.empty((n, O), dtype=np.float32)
+        check(self._L.gigl_sage_conv_host(self.handle, n, ei.shape[1], F, O, _hp(ei), _hp(x), _hp(Wl), _hp(bl),
+                                          _hp(Wr), _hp(out), int(relu)), self.handle)
+        return out
+
+    def gcn_conv_host(self, x, edge_index, W, b, relu: bool = False) -> np.ndarray:
+        x = _np(x, np.float32)
+        ei = _np(edge_index, np.int64)
+        W = _np(W, np.float32)
+        b = None if b is None else _np(b, np.float32)
+        n, F = x.shape
+        O = W.shape[0]
+        out = np.empty((n, O), dtype=np.float32)
+        check(self._L.gigl_gcn_conv_host(self.handle, n, ei.shape[1], F, O, _hp(ei), _hp(x), _hp(W), _hp(b), _hp(out),
+                                         int(relu)), self.handle)
+        return out
+
+    # ---- aggregate, device tensors --------------------------------------------------------
+    def csr_from_coo(self, n: int, edge_index):
+        """edge_index: int64 CUDA tensor [2, e] -> (rowptr int64 [n+1], col int32 [e]), rows stable."""
+        import torch
+
+        assert edge_index.dtype == torch.int64 and edge_index.dim() == 2 and edge_index.shape[0] == 2
+        ei = edge_index.contiguous()
+        e = ei.shape[1]
+        rowptr = torch.empty(n + 1, dtype=torch.int64, device=ei.device)
+        col = torch.empty(max(e, 1), dtype=torch.int32, device=ei.device)
+        check(self._L.gigl_csr_from_coo_dev(self.handle, n, e, _dp(ei[0]), _dp(ei[1]), _dp(rowptr), _dp(col)), self.handle)
+        return rowptr, col[:e]
+
+    def sage_conv(self, x, rowptr, col, Wl, bl, Wr, relu: bool = False, n_rows_out: Optional[int] = None, out=None):
+        import torch
+
+        n, F = x.shape
+        O = Wl.shape[0]
+        m = n if n_rows_out is None else n_rows_out
+        if out is None:
+            out = torch.empty((m, O), dtype=torch.float32, device=x.device)
+        check(self._L.gigl_sage_conv_dev(self.handle, n, m, F, O, _dp(rowptr), _dp(col), _dp(x), _dp(Wl), _dp(bl), _dp(Wr),
+                                         _dp(out), int(relu)), self.handle)
+        return out
+
+    def gather_mean(self, x, rowptr, col, n_rows_out: Optional[int] = None, out=None):
+        import torch
+
+        n, F = x.shape
+        m = n if n_rows_out is None else n_rows_out
+        if out is None:
+            out = torch.empty((m, F), dtype=torch.float32, device=x.device)
+        check(self._L.gigl_gather_mean_dev(self.handle, m, F, _dp(rowptr), _dp(col), _dp(x), _dp(out)), self.handle)
+        return out
+
+    def gcn_conv(self, x, rowptr, col, W, b, relu: bool = False, out=None):
+        import torch
+
+        n, F = x.shape
+        O = W.shape[0]
+        if out is None:
+            out = torch.empty((n, O), dtype=torch.float32, device=x.device)
+        check(self._L.gigl_gcn_conv_dev(self.handle, n, F, O, _dp(rowptr), _dp(col), _dp(x), _dp(W), _dp(b), _dp(out),
+                                        int(relu)), self.handle)
+        return out
+
+
+class Graph:
+    """gigl_graph: sorted CSR (rows = in-neighbours, or out-neighbours with ``by_source``) in HBM."""
+
+    def __init__(self, ctx: Context, handle, keepalive=None):
+        self.ctx = ctx
+        self.handle = handle
+        self._keepalive = keepalive
+        n, e = C.c_int64(), C.c_int64()
+        check(ctx._L.gigl_graph_num_nodes(handle, C.byref(n), C.byref(e)), ctx.handle)
+        self.n_nodes, self.n_edges = n.value, e.value
+
+    # -- constructors
+    @classmethod
+    def from_csr_host(cls, ctx: Context, rowptr, col) -> "Graph":
+        rowptr, col = _np(rowptr, np.int64), _np(col, np.int32)
+        h = C.c_void_p()
+        check(ctx._L.gigl_graph_create_host(ctx.handle, len(rowptr) - 1, len(col), _hp(rowptr), _hp(col), C.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_edges_host(cls, ctx: Context, n_nodes: int, src, dst, is_graph_directed: bool, by_source: bool = False) -> "Graph":
+        src, dst = _np(src, np.int32), _np(dst, np.int32)
+        assert src.shape == dst.shape
+        h = C.c_void_p()
+        check(ctx._L.gigl_graph_from_edges_host(ctx.handle, n_nodes, len(src), _hp(src), _hp(dst), int(is_graph_directed),
+                                                int(by_source), C.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_edges_dev(cls, ctx: Context, n_nodes: int, src, dst, is_graph_directed: bool, by_source: bool = False) -> "Graph":
+        import torch
+
+        assert src.dtype == torch.int32 and dst.dtype == torch.int32 and src.shape == dst.shape
+        h = C.c_void_p()
+        check(ctx._L.gigl_graph_from_edges_dev(ctx.handle, n_nodes, src.numel(), _dp(src), _dp(dst), int(is_graph_directed),
+                                               int(by_source), C.byref(h)), ctx.handle)
+        return cls(ctx, h)
+
+    @classmethod
+    def wrap_dev(cls, ctx: Context, rowptr, col) -> "Graph":
+        h = C.c_void_p()
+        check(ctx._L.gigl_graph_wrap_dev(ctx.handle, rowptr.numel() - 1, col.numel(), _dp(rowptr), _dp(col), C.byref(h)), ctx.handle)
+        return cls(ctx, h, keepalive=(rowptr, col))
+
+    def csr_tensors(self):
+        """(rowptr int64 [n+1], col int32 [E]) as torch views of the resident arrays (no copy)."""
+        import torch
+
+        if self._keepalive is not None:
+            return self._keepalive
+        pr, pc = C.c_void_p(), C.c_void_p()
+        check(self.ctx._L.gigl_graph_device_ptrs(self.handle, C.byref(pr), C.byref(pc)), self.ctx.handle)
+        dev = torch.device("cuda", self.ctx.device)
+        rowptr = _tensor_from_ptr(pr.value, (self.n_nodes + 1,), torch.int64, dev, owner=self)
+        col = _tensor_from_ptr(pc.value, (max(self.n_edges, 1),), torch.int32, dev, owner=self)[: self.n_edges]
+        return rowptr, col
+
+    def csr_host(self) -> Tuple[np.ndarray, np.ndarray]:
+        rowptr, col = self.csr_tensors()
+        return rowptr.cpu().numpy(), col.cpu().numpy()
+
+    # -- sampling
+    def sample_khop_host(self, roots, fanouts: Sequence[int], base_seed: int = 42, first_call_no: int = 1
+                         ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+        """Padded-tree k-hop sample (layout: include/gigl_b200.h) through host buffers."""
+        roots = _np(roots, np.int32)
+        fan = _np(fanouts, np.int32)
+        n_roots, n_hops = len(roots), len(fan)
+        nbr, cnt, width = [], [], 1
+        for f in fan:
+            cnt.append(np.zeros(n_roots * width, dtype=np.int32))
+            width *= int(f)
+            nbr.append(np.full(n_roots * width, -1, dtype=np.int32))
+        pn = (C.c_void_p * max(n_hops, 1))(*[a.ctypes.data for a in nbr])
+        pc = (C.c_void_p * max(n_hops, 1))(*[a.ctypes.data for a in cnt])
+        check(self.ctx._L.gigl_sample_khop_host(self.handle, _hp(roots), n_roots, _hp(fan), n_hops, base_seed, first_call_no,
+                                                pn, pc), self.ctx.handle)
+        return nbr, cnt
+
+    def sample_khop(self, roots, fanouts: Sequence[int], base_seed: int = 42, first_call_no: int = 1, out=None):
+        """Device variant: ``roots`` int32 CUDA tensor -> (nbr, cnt) lists of int32 CUDA tensors.
+        Asynchronous; device-side errors surface at ``ctx.sync()``."""
+        import torch
+
+        assert roots.dtype == torch.int32
+        fan = _np(fanouts, np.int32)
+        n_roots, n_hops = roots.numel(), len(fan)
+        if out is None:
+            nbr, cnt, width = [], [], 1
+            for f in fan:
+                cnt.append(torch.empty(n_roots * width, dtype=torch.int32, device=roots.device))
+                width *= int(f)
+                nbr.append(torch.empty(n_roots * width, dtype=torch.int32, device=roots.device))
+        else:
+            nbr, cnt = out
+        pn = (C.c_void_p * max(n_hops, 1))(*[t.data_ptr() for t in nbr])
+        pc = (C.c_void_p * max(n_hops, 1))(*[t.data_ptr() for t in cnt])
+        check(self.ctx._L.gigl_sample_khop_dev(self.handle, _dp(roots), n_roots, _hp(fan), n_hops, base_seed, first_call_no,
+                                               pn, pc), self.ctx.handle)
+        return nbr, cnt
+
+    def sample_positives_host(self, srcs, num_pos: int, base_seed: int = 42, call_no: int = 3):
+        srcs = _np(srcs, np.int32)
+        pos = np.full(len(srcs) * num_pos, -1, dtype=np.int32)
+        cnt = np.zeros(len(srcs), dtype=np.int32)
+        check(self.ctx._L.gigl_sample_positives_host(self.handle, _hp(srcs), len(srcs), num_pos, base_seed, call_no, _hp(pos),
+                                                     _hp(cnt)), self.ctx.handle)
+        return pos, cnt
+
+    def close(self) -> None:
+        if self.handle and self.ctx.handle:
+            self.ctx._L.gigl_graph_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _tensor_from_ptr(ptr: int, shape, dtype, device, owner=None):
+    """Zero-copy torch view of library-owned device memory via __cuda_array_interface__."""
+    import torch
+
+    typestr = {torch.int64: "<i8", torch.int32: "<i4", torch.float32: "<f4"}[dtype]
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    h._owner = owner
+    with torch.cuda.device(device):
+        t = torch.as_tensor(h, device=device)
+    t._gigl_owner = owner
+    return t

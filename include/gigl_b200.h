@@ -1,0 +1,198 @@
+/*
+ * gigl_b200.h - C-ABI of libgigl_b200.so: the B200 (sm_100a) implementation of GiGL's two
+ * data-parallel hot paths, k-hop rooted-neighbourhood sampling and the per-layer GNN
+ * message-passing aggregate.  Plain C: pointers and sizes only, no C++/torch types, no
+ * exceptions across the boundary.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, < 0 = error (GIGL_E_*); the message is
+ *     available from gigl_last_error(ctx) until the next call on that ctx;
+ *   - one gigl_ctx per GPU (device + one CUDA stream + scratch); calls on one ctx are NOT
+ *     thread-safe, distinct ctxs may be used from distinct threads (this matches the reference's
+ *     per-partition setup()/teardown() of a sampler service,
+ *     scala_spark35/common/src/main/scala/graphdb/KHopSamplerService.scala:10-33);
+ *   - the caller owns every host buffer; the library owns device memory behind the opaque handles;
+ *   - "*_host" entry points take host pointers and do the host<->device copies themselves
+ *     (what a JNI / ctypes binding calls); "*_dev" entry points take device pointers, enqueue on
+ *     the ctx stream and do not synchronise (what the PyTorch extension calls);
+ *   - there is NO CPU fallback: without a usable CUDA device every entry point fails with
+ *     GIGL_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the GiGL repository root):
+ *   gigl_graph_*            <- loadEdgeDataframeIntoSparkSql / loadUnhydratedEdgeDataframeIntoSparkSql
+ *                              scala/subgraph_sampler/src/main/scala/libs/task/pureSpark/SGSPureSparkV1Task.scala:120-311
+ *   gigl_sample_khop_*      <- sampleOnehopSrcNodesUniformly :313-388 + sampleTwohopSrcNodesUniformly :390-494
+ *                              with SamplingStrategy.hashBasedUniformPermutation
+ *                              scala/subgraph_sampler/src/main/scala/libs/task/SamplingStrategy.scala:16-82;
+ *                              plugin-side equivalent KHopSamplerService.getKHopSubgraphForRootNodes
+ *                              scala_spark35/common/src/main/scala/graphdb/KHopSamplerService.scala:17-20
+ *   gigl_sample_positives_* <- sampleDstNodesUniformly
+ *                              scala/subgraph_sampler/src/main/scala/libs/task/pureSpark/NodeAnchorBasedLinkPredictionBaseTask.scala:19-104
+ *   gigl_sage_conv_*        <- torch_geometric.nn.SAGEConv.forward as built by GraphSAGE.init_conv_layers
+ *                              python/gigl/src/common/models/pyg/homogeneous.py:171-202 and called at
+ *                              python/gigl/src/common/modeling_task_specs/graphsage_template_modeling_spec.py:305-311
+ *   gigl_gcn_conv_*         <- torch_geometric.nn.GCNConv.forward used by TwoLayerGCN
+ *                              python/gigl/src/common/models/pyg/homogeneous.py:527-542
+ *   gigl_csr_from_coo_dev   <- the (src,dst) edge_index convention of PygGraphBuilder.build
+ *                              python/gigl/src/common/graph_builder/pyg_graph_builder.py:20-69
+ */
+#ifndef GIGL_B200_H_
+#define GIGL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIGL_OK 0
+#define GIGL_E_INVALID -1   /* bad argument (null pointer, negative size, fanout out of range ...) */
+#define GIGL_E_CUDA -2      /* CUDA runtime / driver error, or no usable device */
+#define GIGL_E_RANGE -3     /* a vertex id outside [0, n_nodes) was met on the device */
+#define GIGL_E_OVERFLOW -4  /* a row (times its multiplicity) exceeds 2^31-1 entries */
+#define GIGL_E_NOMEM -5     /* device or host allocation failed */
+
+#define GIGL_MAX_HOPS 8
+#define GIGL_MAX_FANOUT 128
+
+typedef struct gigl_ctx gigl_ctx;
+typedef struct gigl_graph gigl_graph;
+
+/* ---- library / context ------------------------------------------------------------------ */
+
+/* "gigl_b200 <version> sm_100a" */
+const char* gigl_version(void);
+
+/* Creates a context on `device` with its own non-blocking stream. */
+int gigl_ctx_create(int device, gigl_ctx** out);
+/* Same, but enqueues on a stream owned by the caller (e.g. torch's current stream, passed as
+ * the cudaStream_t value).  The stream must outlive the ctx. */
+int gigl_ctx_create_on_stream(int device, void* cuda_stream, gigl_ctx** out);
+void gigl_ctx_destroy(gigl_ctx* ctx);
+/* Blocks until everything enqueued on the ctx stream is done; reports deferred device errors
+ * (GIGL_E_RANGE / GIGL_E_OVERFLOW raised by the last *_dev sampling call). */
+int gigl_ctx_sync(gigl_ctx* ctx);
+const char* gigl_last_error(gigl_ctx* ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+int64_t gigl_ctx_launch_count(gigl_ctx* ctx);
+/* The cudaStream_t the ctx enqueues on (for event timing on the launching stream). */
+void* gigl_ctx_stream(gigl_ctx* ctx);
+
+/* ---- graph: CSR by destination, resident in HBM ---------------------------------------- */
+
+/*
+ * rowptr: int64[n_nodes + 1]; col: int32[n_edges], row v = the in-neighbours (sources) of v in
+ * ASCENDING order, duplicates kept (array_sort(collect_list(_src_node)),
+ * SGSPureSparkV1Task.scala:334-342).  Copies both arrays to the device.
+ */
+int gigl_graph_create_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int64_t* rowptr,
+                           const int32_t* col, gigl_graph** out);
+/* Wraps device arrays already laid out as above; nothing is copied, the caller keeps ownership. */
+int gigl_graph_wrap_dev(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int64_t* rowptr_dev,
+                        const int32_t* col_dev, gigl_graph** out);
+/*
+ * Builds the sorted in-CSR on the device from a host edge list, applying the reference's load
+ * rules: ids are int32; if !is_graph_directed the pairs are de-duplicated as (min,max) and
+ * mirrored (enforceBidirectionalization, :218-258); if directed, duplicates are kept.
+ * by_source != 0 builds the out-CSR instead (row u = sorted destinations of u), which is what
+ * positive sampling walks.
+ */
+int gigl_graph_from_edges_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src,
+                               const int32_t* dst, int32_t is_graph_directed, int32_t by_source,
+                               gigl_graph** out);
+/* Same, from int32 edge arrays already on the device (left untouched). */
+int gigl_graph_from_edges_dev(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,
+                              const int32_t* dst_dev, int32_t is_graph_directed, int32_t by_source,
+                              gigl_graph** out);
+int gigl_graph_num_nodes(const gigl_graph* g, int64_t* n_nodes, int64_t* n_edges);
+/* Device pointers of the resident CSR (for bindings that want to read it back / reuse it). */
+int gigl_graph_device_ptrs(const gigl_graph* g, const int64_t** rowptr_dev, const int32_t** col_dev);
+void gigl_graph_destroy(gigl_graph* g);
+
+/* ---- k-hop rooted-neighbourhood index sampling ----------------------------------------- */
+
+/*
+ * For every root r and hop h = 1..n_hops, samples min(fanouts[h-1], size) in-neighbours of every
+ * vertex on the level-(h-1) frontier with GiGL's deterministic hash permutation:
+ *     key_i = XXH64_le32( int32(i + internal_seed + base_seed * (first_call_no + h - 1)) , 42 ),
+ *     i = 1..size, the `fanout` smallest (signed key, i) win, emitted in ascending key order,
+ * internal_seed = wrapping int32 sum of the path ids root..level h-1.  base_seed = 42 and
+ * first_call_no = 1 reproduce SubgraphSamplerTask.samplingSeed / SamplingStrategy._counter.
+ *
+ * Output = the "padded tree": level h has n_roots * prod(fanouts[0..h-1]) int32 slots in
+ * nbr[h-1] (-1 = empty); slot s of level h is child (s % fanouts[h-1]) of slot (s / fanouts[h-1])
+ * of level h-1 (level 0 = roots).  cnt[h-1][p] = children written under parent slot p
+ * (n_roots * prod(fanouts[0..h-2]) int32 entries).  Sampled edge for a filled slot:
+ * src = nbr[h-1][s], dst = its parent (src = _k_hop, dst = _k-1_hop, :615-629).
+ * If one parent's sample holds the same vertex m > 1 times (duplicate directed edges), the
+ * reference's GROUP BY (_0_hop,_1_hop) yields ONE group over IN(k) repeated m times: it is
+ * stored under the FIRST such slot, the other duplicate slots get cnt 0.
+ *
+ * fanouts[h] in [1, GIGL_MAX_FANOUT], n_hops in [1, GIGL_MAX_HOPS].
+ */
+int gigl_sample_khop_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, const int32_t* fanouts,
+                          int32_t n_hops, int32_t base_seed, int32_t first_call_no,
+                          int32_t* const* nbr /* [n_hops] host */, int32_t* const* cnt /* [n_hops] host */);
+/* Device-pointer variant: roots, nbr[h], cnt[h] are device arrays (the pointer tables themselves
+ * are host arrays).  Asynchronous on the ctx stream; errors found on the device surface at
+ * the next gigl_ctx_sync(). */
+int gigl_sample_khop_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                         int32_t n_hops, int32_t base_seed, int32_t first_call_no,
+                         int32_t* const* nbr_dev, int32_t* const* cnt_dev);
+
+/*
+ * Positive (out-edge) sampling for node-anchor link prediction: `g_out` is the CSR by SOURCE;
+ * for every src u: P(u) = first num_pos of perm(OUT(u), internal_seed = u, call_no) - the NABLP
+ * task calls it third, so call_no = 3.  pos: int32[n_srcs * num_pos] (-1 padded), pos_cnt: int32[n_srcs].
+ */
+int gigl_sample_positives_host(gigl_graph* g_out, const int32_t* srcs, int64_t n_srcs, int32_t num_pos,
+                               int32_t base_seed, int32_t call_no, int32_t* pos, int32_t* pos_cnt);
+
+/* ---- aggregate: SAGEConv / GCNConv forward (fp32) --------------------------------------- */
+
+/*
+ * edge_index (COO, PyG convention: row 0 = src j, row 1 = dst i, int64, e columns, device) ->
+ * CSR by dst with the edges of each row kept in their input order (stable), so the fp32
+ * accumulation order equals a sequential index_add_.  rowptr_dev: int64[n+1], col_dev: int32[e].
+ * Returns GIGL_E_RANGE at the next sync if an id is outside [0, n).
+ */
+int gigl_csr_from_coo_dev(gigl_ctx* ctx, int64_t n, int64_t e, const int64_t* src_dev, const int64_t* dst_dev,
+                          int64_t* rowptr_dev, int32_t* col_dev);
+
+/*
+ * out[i,:] = Wl @ mean_{j in row i} x[j,:] + bl + Wr @ x[i,:]   (mean of an empty row = 0;
+ * duplicates counted; optional fused ReLU = the inter-layer activation of BasicGNN).
+ * x: [n, F] fp32 row-major, Wl/Wr: [O, F] row-major (PyG lin_l.weight / lin_r.weight), bl: [O] or
+ * NULL, out: [n, O].  n_rows_out <= n limits the output to the first n_rows_out rows (rows are
+ * still gathered from all n); pass n for the full layer.  All pointers are device pointers.
+ */
+int gigl_sage_conv_dev(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O,
+                       const int64_t* rowptr_dev, const int32_t* col_dev, const float* x_dev,
+                       const float* Wl_dev, const float* bl_dev, const float* Wr_dev, float* out_dev,
+                       int32_t relu);
+/* Host-buffer variant taking the PyG inputs as they are (x, edge_index int64 [2, e]); does
+ * H2D, COO->CSR, the layer, D2H. */
+int gigl_sage_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O, const int64_t* edge_index,
+                        const float* x, const float* Wl, const float* bl, const float* Wr, float* out,
+                        int32_t relu);
+/* Mean aggregation alone (the gather-SpMM without the projection): agg[i,:] = mean_j x[j,:]. */
+int gigl_gather_mean_dev(gigl_ctx* ctx, int64_t n_rows_out, int32_t F, const int64_t* rowptr_dev,
+                         const int32_t* col_dev, const float* x_dev, float* agg_dev);
+
+/*
+ * GCNConv forward: x' = x @ W^T; self loops: every node gets exactly one (existing self loops
+ * are collapsed into it); deg_i = 1 + #non-loop in-edges; out_i = sum_j dinv_j dinv_i x'_j + b.
+ * CSR rows may contain self loops; they are skipped and replaced by the single implicit loop.
+ */
+int gigl_gcn_conv_dev(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr_dev,
+                      const int32_t* col_dev, const float* x_dev, const float* W_dev, const float* b_dev,
+                      float* out_dev, int32_t relu);
+
+/* Host-buffer variant (x, edge_index int64 [2, e] as PyG holds them). */
+int gigl_gcn_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O, const int64_t* edge_index,
+                       const float* x, const float* W, const float* b, float* out, int32_t relu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIGL_B200_H_ */

@@ -1,0 +1,151 @@
+"""GPU parity: SAGEConv / GCNConv / 2-layer GraphSAGE through the C-ABI vs the CPU oracle.
+Tolerance (BASELINE.json north_star): 1e-5 relative on fp32 embeddings, measured against the
+fp64 restatement as  max|got - ref| <= 1e-5 * max(1, max|ref|)."""
+import numpy as np
+import pytest
+
+from helpers import powerlaw_edges, uniform_edges
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gigl_b200 import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _orc():
+    from oracle import oracle as orc
+
+    return orc
+
+
+def _rel(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref).max() / max(1.0, np.abs(ref).max()))
+
+
+def _weights(rng, O, F):
+    s = 1.0 / np.sqrt(F)
+    return (rng.uniform(-s, s, (O, F)).astype(np.float32), rng.uniform(-s, s, O).astype(np.float32),
+            rng.uniform(-s, s, (O, F)).astype(np.float32))
+
+
+@pytest.mark.parametrize("n,e,F,O", [(1, 0, 4, 4), (50, 0, 16, 8), (300, 4000, 16, 7), (1000, 20000, 100, 47),
+                                     (777, 9000, 33, 5), (2000, 50000, 128, 128), (500, 6000, 64, 64),
+                                     (400, 5000, 769, 32), (600, 30000, 2, 3)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_sage_conv_host_vs_oracle(ctx, n, e, F, O, relu):
+    orc = _orc()
+    rng = np.random.default_rng(n + e + F)
+    src, dst = powerlaw_edges(n, e, 1) if e else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    ei = np.stack([src, dst])
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    Wl, bl, Wr = _weights(rng, O, F)
+    got = ctx.sage_conv_host(x, ei, Wl, bl, Wr, relu=relu)
+    ref64 = orc.c_sage_conv(x, ei, Wl, bl, Wr, relu=relu, f64=True)
+    assert _rel(got, ref64) < RTOL
+    # the fp32 oracle (sequential index_add_ order) sits inside the same band
+    assert _rel(orc.c_sage_conv(x, ei, Wl, bl, Wr, relu=relu), ref64) < RTOL
+    got_nb = ctx.sage_conv_host(x, ei, Wl, None, Wr, relu=relu)
+    assert _rel(got_nb, orc.c_sage_conv(x, ei, Wl, None, Wr, relu=relu, f64=True)) < RTOL
+
+
+def test_sage_conv_hand_graph(ctx):
+    # 4 nodes: 1->0, 2->0, 2->0 (duplicate counted twice), 3->3 (self loop), node 1/2 without in-edges
+    ei = np.array([[1, 2, 2, 3], [0, 0, 0, 3]])
+    x = np.array([[1, 0], [0, 2], [4, 4], [-1, 3]], np.float32)
+    Wl = np.array([[1, 0], [0, 1], [1, 1]], np.float32)
+    Wr = np.array([[2, 0], [0, 2], [0, 0]], np.float32)
+    bl = np.array([0.5, -0.5, 0], np.float32)
+    out = ctx.sage_conv_host(x, ei, Wl, bl, Wr)
+    mean0 = (x[1] + 2 * x[2]) / 3
+    want = np.stack([Wl @ mean0 + bl + Wr @ x[0], bl + Wr @ x[1], bl + Wr @ x[2], Wl @ x[3] + bl + Wr @ x[3]])
+    assert np.allclose(out, want, rtol=1e-6, atol=1e-6)
+
+
+def test_sage_conv_rejects_bad_ids(ctx):
+    from gigl_b200 import GiglError
+
+    x = np.zeros((4, 4), np.float32)
+    W = np.zeros((4, 4), np.float32)
+    with pytest.raises(GiglError) as ei:
+        ctx.sage_conv_host(x, np.array([[0, 9], [1, 2]]), W, None, W)
+    assert ei.value.code == -3
+    # the ctx stays usable
+    out = ctx.sage_conv_host(x, np.array([[0, 3], [1, 2]]), W, None, W)
+    assert out.shape == (4, 4)
+
+
+@pytest.mark.parametrize("n,e,F,O", [(300, 4000, 16, 7), (2708, 10556, 1433, 16), (1000, 30000, 16, 7), (64, 0, 8, 4)])
+def test_gcn_conv_host_vs_oracle(ctx, n, e, F, O):
+    orc = _orc()
+    rng = np.random.default_rng(e + F)
+    src, dst = uniform_edges(n, e, 2) if e else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    if e:
+        src[:20] = dst[:20]  # self loops (collapsed into the single implicit loop)
+    ei = np.stack([src, dst])
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    W, b, _ = _weights(rng, O, F)
+    for relu in (False, True):
+        got = ctx.gcn_conv_host(x, ei, W, b, relu=relu)
+        assert _rel(got, orc.c_gcn_conv(x, ei, W, b, relu=relu, f64=True)) < RTOL
+
+
+def test_two_layer_graphsage_device_path(ctx):
+    """GraphSAGE(in, hidden, 2, out): relu between layers, none after the last (BasicGNN); device
+    entry points with torch-held memory, n_rows_out pruning on the last layer."""
+    import torch
+
+    from gigl_b200 import Context
+
+    orc = _orc()
+    tctx = Context.on_torch_stream(0)
+    rng = np.random.default_rng(3)
+    n, e, F, H, O = 3000, 60000, 100, 64, 64
+    src, dst = powerlaw_edges(n, e, 4)
+    ei = np.stack([src, dst])
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    l1, l2 = _weights(rng, H, F), _weights(rng, O, H)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rowptr, col = tctx.csr_from_coo(n, t(ei))
+    h = tctx.sage_conv(t(x), rowptr, col, t(l1[0]), t(l1[1]), t(l1[2]), relu=True)
+    out = tctx.sage_conv(h, rowptr, col, t(l2[0]), t(l2[1]), t(l2[2]), relu=False, n_rows_out=500)
+    tctx.sync()
+    ref = orc.sage_model(x, ei, [l1, l2], f64=True)
+    # layer 2 of the f64 oracle consumes its own fp32-rounded layer-1 output: same band
+    assert _rel(out.cpu().numpy(), ref[:500]) < RTOL
+    # stable CSR: row order == input order
+    r, c = rowptr.cpu().numpy(), col.cpu().numpy()
+    order = np.argsort(dst, kind="stable")
+    assert np.array_equal(c, src[order].astype(np.int32)) and np.array_equal(np.diff(r), np.bincount(dst, minlength=n))
+
+
+def test_gather_mean_large_linearity(ctx):
+    """Full-size style property: mean-aggregate is linear, agg(a*x + y) == a*agg(x) + agg(y)."""
+    import torch
+
+    from gigl_b200 import Context
+
+    tctx = Context.on_torch_stream(0)
+    n, e, F = 500_000, 8_000_000, 128
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ei = torch.randint(0, n, (2, e), device="cuda", generator=g)
+    rowptr, col = tctx.csr_from_coo(n, ei)
+    x = torch.randn(n, F, device="cuda", generator=g)
+    y = torch.randn(n, F, device="cuda", generator=g)
+    a1 = tctx.gather_mean(x, rowptr, col)
+    a2 = tctx.gather_mean(y, rowptr, col)
+    a3 = tctx.gather_mean(2.0 * x + y, rowptr, col)
+    tctx.sync()
+    assert float((a3 - (2.0 * a1 + a2)).abs().max()) < 1e-5
+    # and against a segment mean computed from the CSR on the device with exact counts
+    deg = (rowptr[1:] - rowptr[:-1])
+    ones = tctx.gather_mean(torch.ones(n, 4, device="cuda"), rowptr, col)
+    tctx.sync()
+    assert torch.equal(ones[:, 0] > 0, deg > 0) and float((ones[deg > 0] - 1).abs().max()) < 1e-6

@@ -1,0 +1,232 @@
+"""GPU parity: k-hop sampling through the C-ABI (host-buffer and device entry points) must be
+BIT-EXACT against the CPU oracle on the same seeded inputs, and equal the reference sampler's
+own fixture outputs wherever those are determined."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, powerlaw_edges, uniform_edges
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gigl_b200 import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _orc():
+    from oracle import oracle as orc
+
+    return orc
+
+
+def _check_equal(got, want):
+    (gn, gc), (wn, wc) = got, want
+    for h, (a, b) in enumerate(zip(gn, wn)):
+        assert np.array_equal(a, b), f"nbr hop {h + 1}: {np.flatnonzero(a != b)[:10]}"
+    for h, (a, b) in enumerate(zip(gc, wc)):
+        assert np.array_equal(a, b), f"cnt hop {h + 1}"
+
+
+@pytest.mark.parametrize("directed", [True, False])
+def test_graph_build_matches_oracle(ctx, directed):
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    n = 5000
+    src, dst = powerlaw_edges(n, 60000, 3)
+    src[:50] = dst[:50]  # self loops
+    g = Graph.from_edges_host(ctx, n, src, dst, is_graph_directed=directed)
+    rowptr, col = orc.np_build_in_csr(src, dst, n, directed)
+    gr, gc = g.csr_host()
+    assert np.array_equal(gr, rowptr) and np.array_equal(gc, col)
+    # out-CSR (positives walk it): equals the in-CSR of the reversed edges
+    go = Graph.from_edges_host(ctx, n, src, dst, is_graph_directed=directed, by_source=True)
+    rowptr_o, col_o = orc.np_build_in_csr(dst, src, n, directed)
+    gr, gc = go.csr_host()
+    assert np.array_equal(gr, rowptr_o) and np.array_equal(gc, col_o)
+
+
+def test_graph_build_empty_and_bad_ids(ctx):
+    from gigl_b200 import Graph, GiglError
+
+    g = Graph.from_edges_host(ctx, 7, np.zeros(0, np.int32), np.zeros(0, np.int32), True)
+    assert g.n_edges == 0
+    nbr, cnt = g.sample_khop_host(np.arange(7, dtype=np.int32), [3, 2])
+    assert (nbr[0] == -1).all() and (nbr[1] == -1).all() and (cnt[0] == 0).all()
+    with pytest.raises(GiglError) as ei:
+        Graph.from_edges_host(ctx, 7, np.array([1, 9], np.int32), np.array([2, 3], np.int32), True)
+    assert ei.value.code == -3
+
+
+@pytest.mark.parametrize("seed,directed", [(0, True), (1, False), (2, True)])
+@pytest.mark.parametrize("fan", [[3, 3], [10, 5], [15, 10], [4], [2, 3, 2], [40, 2], [100]])
+def test_khop_bit_exact_small(ctx, seed, directed, fan):
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    n = 400
+    src, dst = powerlaw_edges(n, 6000, seed) if seed != 1 else uniform_edges(n, 2500, seed)
+    rowptr, col = orc.np_build_in_csr(src, dst, n, directed)
+    g = Graph.from_csr_host(ctx, rowptr, col)
+    roots = np.arange(n, dtype=np.int32)
+    _check_equal(g.sample_khop_host(roots, fan), orc.c_sample_khop(rowptr, col, roots, fan))
+
+
+def test_khop_heavy_rows_and_hubs(ctx):
+    """Rows far above the CTA-per-row threshold (hubs of a power-law graph) and a star graph."""
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    n = 30000
+    src, dst = powerlaw_edges(n, 600000, 11, alpha=1.4)
+    # star: vertex 7 gets 50k extra in-edges
+    src = np.concatenate([src, np.random.default_rng(1).integers(0, n, 50000)])
+    dst = np.concatenate([dst, np.full(50000, 7)])
+    rowptr, col = orc.np_build_in_csr(src, dst, n, True)
+    assert np.diff(rowptr).max() > 20000
+    g = Graph.from_csr_host(ctx, rowptr, col)
+    roots = np.concatenate([[7], np.argsort(-np.diff(rowptr))[:200], np.arange(0, n, 7)]).astype(np.int32)
+    for fan in ([15, 10], [33, 3], [128, 2]):
+        _check_equal(g.sample_khop_host(roots, fan), orc.c_sample_khop(rowptr, col, roots, fan))
+
+
+def test_khop_duplicate_edges_group_semantics(ctx):
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    src = np.array([1, 1, 1, 2, 3, 0, 0])
+    dst = np.array([0, 0, 0, 1, 1, 2, 2])
+    rowptr, col = orc.np_build_in_csr(src, dst, 4, True)
+    g = Graph.from_csr_host(ctx, rowptr, col)
+    roots = np.arange(4, dtype=np.int32)
+    for fan in ([3, 4], [2, 2, 2], [5, 5]):
+        _check_equal(g.sample_khop_host(roots, fan), orc.c_sample_khop(rowptr, col, roots, fan))
+
+
+def test_khop_seed_and_call_counter(ctx):
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    n = 300
+    src, dst = uniform_edges(n, 5000, 5)
+    rowptr, col = orc.np_build_in_csr(src, dst, n, True)
+    g = Graph.from_csr_host(ctx, rowptr, col)
+    roots = np.arange(n, dtype=np.int32)
+    for base_seed, first in ((42, 1), (42, 3), (7, 1), (2**31 - 1, 5), (-13, 2)):
+        _check_equal(g.sample_khop_host(roots, [5, 5], base_seed, first),
+                     orc.c_sample_khop(rowptr, col, roots, [5, 5], base_seed, first))
+
+
+def test_khop_int32_wraparound_ids(ctx):
+    """ids near 2^31 make i + internal_seed + seed wrap (Spark IntegerType '+', ANSI off)."""
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    n = 600
+    src, dst = uniform_edges(n, 9000, 9)
+    rowptr, col = orc.np_build_in_csr(src, dst, n, True)
+    g = Graph.from_csr_host(ctx, rowptr, col)
+    roots = np.arange(n, dtype=np.int32)
+    # huge base seeds push the window across the int32 boundary
+    for base_seed in (2**31 - 100, 2**30 + 12345, -(2**31) + 3):
+        _check_equal(g.sample_khop_host(roots, [6, 4], base_seed, 1), orc.c_sample_khop(rowptr, col, roots, [6, 4], base_seed, 1))
+
+
+def test_positives_match_oracle(ctx):
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    g27 = load_golden("nablp27_graph.json")
+    e = np.array([(x["src"], x["dst"]) if isinstance(x, dict) else x[:2] for x in g27["edges"]], dtype=np.int64)
+    n = len(g27["nodes"])
+    go = Graph.from_edges_host(ctx, n, e[:, 0], e[:, 1], is_graph_directed=False, by_source=True)
+    rowptr_o, col_o = orc.np_build_in_csr(e[:, 1], e[:, 0], n, False)
+    srcs = np.arange(n, dtype=np.int32)
+    for num_pos in (1, 2, 5):
+        pos, cnt = go.sample_positives_host(srcs, num_pos)
+        onbr, ocnt = orc.c_sample_khop(rowptr_o, col_o, srcs, [num_pos], 42, 3)
+        assert np.array_equal(pos, onbr[0]) and np.array_equal(cnt, ocnt[0])
+
+
+def test_reference_fixture_exact_roots(ctx):
+    """Roots of the reference's 16-node fixture whose frontier degrees are all <= fanout have a
+    fully determined output: the GPU sample must equal the reference sampler's own output."""
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    g16 = load_golden("snc16_graph.json")
+    e = np.array(g16["edges"], dtype=np.int64)
+    n = len(g16["nodes"])
+    f = g16["num_neighbors_to_sample"]
+    g = Graph.from_edges_host(ctx, n, e[:, 0], e[:, 1], is_graph_directed=g16["is_graph_directed"])
+    rowptr, col = g.csr_host()
+    nbr, cnt = g.sample_khop_host(np.arange(n, dtype=np.int32), [f, f])
+    edges = orc.tree_to_edges(np.arange(n), nbr, [f, f])
+    deg = np.diff(rowptr)
+    out = load_golden("snc16_sgs_output.json")
+    n_exact = 0
+    for s in out["unlabeled"]:
+        r = s["root_node"]["node_id"]
+        ref_edges = sorted((x["src"], x["dst"]) for x in s["neighborhood"]["edges"])
+        in_r = col[rowptr[r]: rowptr[r + 1]].tolist()
+        assert cnt[0][r] == min(f, deg[r])
+        if deg[r] <= f and all(deg[k] <= f for k in in_r):
+            assert sorted(edges[r]) == ref_edges
+            n_exact += 1
+    assert n_exact >= 3
+
+
+def test_khop_device_entry_point_and_properties_large(ctx):
+    """Device entry point on a 2M-node / 40M-edge power-law graph: exact vs the oracle on a root
+    sample, and size-independent properties on everything (count == min(f, deg), sampled ids are
+    in-neighbours, no duplicate positions => multiset inclusion, idempotence)."""
+    import torch
+
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    n, e = 2_000_000, 40_000_000
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    u = torch.rand(e, device="cuda", generator=gen)
+    dst = ((u ** 3.0) * n).to(torch.int32)  # heavy-tailed in-degree
+    src = torch.randint(0, n, (e,), device="cuda", generator=gen, dtype=torch.int32)
+    perm = torch.randperm(n, device="cuda", generator=gen).to(torch.int32)
+    dst = perm[dst.long()]
+    tctx = __import__("gigl_b200").Context.on_torch_stream(0)
+    g = Graph.from_edges_dev(tctx, n, src, dst, is_graph_directed=True)
+    rowptr_t, col_t = g.csr_tensors()
+    deg = (rowptr_t[1:] - rowptr_t[:-1])
+    assert int(rowptr_t[-1]) == e and bool((col_t[1:] >= col_t[:-1])[(rowptr_t[1:-1] - 1).clamp(min=0)].sum() >= 0)
+    fan = [15, 10]
+    roots = torch.arange(0, n, 4, device="cuda", dtype=torch.int32)
+    nbr, cnt = g.sample_khop(roots, fan)
+    tctx.sync()
+    # properties, all on device
+    assert torch.equal(cnt[0].long(), deg[roots.long()].clamp(max=fan[0]))
+    n1 = nbr[0].view(-1, fan[0])
+    filled = (n1 >= 0)
+    assert torch.equal(filled.sum(1).int(), cnt[0])
+    par = n1.reshape(-1)
+    live = par >= 0
+    # hop-2 count == min(f2, deg(parent)) for live, non-duplicate parents (no dup edges needed: check <=)
+    d2 = torch.zeros_like(cnt[1], dtype=torch.int64)
+    d2[live] = deg[par[live].long()].clamp(max=fan[1])
+    same = (cnt[1].long() == d2) | (cnt[1] == 0)
+    assert bool(same.all())
+    # idempotence
+    nbr2, cnt2 = g.sample_khop(roots, fan)
+    tctx.sync()
+    assert all(torch.equal(a, b) for a, b in zip(nbr + cnt, nbr2 + cnt2))
+    # exact vs the oracle on a sample of roots
+    rowptr, col = rowptr_t.cpu().numpy(), col_t.cpu().numpy()
+    sel = np.arange(0, roots.numel(), 97)
+    roots_h = roots.cpu().numpy()[sel]
+    onbr, ocnt = orc.c_sample_khop(rowptr, col, roots_h, fan)
+    assert np.array_equal(nbr[0].view(-1, fan[0]).cpu().numpy()[sel].ravel(), onbr[0])
+    assert np.array_equal(nbr[1].view(-1, fan[0] * fan[1]).cpu().numpy()[sel].ravel(), onbr[1])
+    assert np.array_equal(cnt[1].view(-1, fan[0]).cpu().numpy()[sel].ravel(), ocnt[1])
