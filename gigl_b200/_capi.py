@@ -52,6 +52,19 @@ SIGNATURES = {
     "gigl_gather_mean_dev": (C.c_int, [vp, i64, i32, vp, vp, vp, vp]),
     "gigl_gcn_conv_dev": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, i32]),
     "gigl_gcn_conv_host": (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i32]),
+    "gigl_graph_set_features_host": (C.c_int, [vp, vp, i32]),
+    "gigl_graph_set_features_dev": (C.c_int, [vp, vp, i32]),
+    "gigl_graph_features_dev": (C.c_int, [vp, pvp, C.POINTER(i32)]),
+    "gigl_sage_model_create_host": (C.c_int, [vp, i32, vp, pvp, pvp, pvp, pvp]),
+    "gigl_sage_model_create_dev": (C.c_int, [vp, i32, vp, pvp, pvp, pvp, pvp]),
+    "gigl_sage_model_destroy": (None, [vp]),
+    "gigl_batch_create": (C.c_int, [vp, i64, pvp]),
+    "gigl_batch_destroy": (None, [vp]),
+    "gigl_batch_collate_dev": (C.c_int, [vp, vp, i64, vp, i32, pvp, i32, C.POINTER(i64), C.POINTER(i64)]),
+    "gigl_batch_finalize_nodes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+    "gigl_batch_export_dev": (C.c_int, [vp, vp, vp]),
+    "gigl_batch_sage_forward_dev": (C.c_int, [vp, vp, vp, i64, vp]),
+    "gigl_infer_khop_sage_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, pvp, pvp]),
 }
 
 _lib = None

@@ -1,0 +1,631 @@
+// batch_collate.cu - B sampled rooted neighbourhoods -> ONE coalesced batch graph, on the device,
+// and the layer-wise SAGE forward over it.
+//
+// Replaces the Python batch construction that defines what `x` / `edge_index` mean for the
+// aggregate:
+//   GbmlProtosTranslator.graph_data_from_GraphPb  python/gigl/src/common/translators/gbml_protos_translator.py:101-121
+//   GraphBuilder.add_graph_data / PygGraphBuilder.build   python/gigl/src/common/graph_builder/abstract_graph_builder.py:49-197,
+//                                                          pyg_graph_builder.py:20-69
+//   collate fns + coalesce   python/gigl/src/training/v1/lib/data_loaders/rooted_node_neighborhood_data_loader.py:78-,
+//                            supervised_node_classification_data_loader.py:73-117, data_loaders/utils.py:59-146
+// i.e. the union of the B subgraphs with nodes de-duplicated by id and edges de-duplicated by
+// (src, dst); the model is then run on that union and the root rows are selected
+// (graphsage_template_modeling_spec.py:305-311, :565-577).
+//
+// Device formulation (no per-node Python dicts, no x_batch copy):
+//   1. every filled tree slot becomes a 64-bit key (dst << 32 | src); one radix sort (CUB, plumbing)
+//      orders the batch's edges by (dst, src): equal keys = duplicate edges, runs of equal dst =
+//      the in-edge row of that vertex in the coalesced graph;
+//   2. a dense per-vertex map (HBM is large: 8 B x N) records each row's [beg, end) in the sorted keys;
+//   3. local ids are assigned level by level: S_L = roots, S_{l-1} = S_l + in-neighbours(S_l), so
+//      layer l only computes the rows the root outputs depend on (identical root embeddings to
+//      running every layer on every batch node, which is what the reference does);
+//   4. the gather kernel walks a row's sorted keys, skips duplicates, pulls the source feature rows
+//      (layer 1: straight from the graph-wide feature table by global id; deeper layers: through
+//      the local-id map) and writes [mean | self] rows that the projection GEMM consumes.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "common.cuh"
+
+namespace gigl {
+
+constexpr int32_t kLidAbsent = 0x7fffffff;
+constexpr int32_t kLidPending = 0x7ffffffe;
+
+static inline int bits_for64(int64_t n) {
+    int b = 1;
+    while (b < 32 && ((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+// ---- 1. tree slots -> edge keys --------------------------------------------------------------
+__global__ void tree_keys_kernel(int64_t n_slots, int32_t f, const int32_t* __restrict__ parents,
+                                 const int32_t* __restrict__ children, uint64_t dead, uint64_t* __restrict__ keys) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += stride) {
+        const int32_t src = __ldg(children + s);
+        uint64_t k = dead;
+        if (src >= 0) {
+            const int32_t dst = __ldg(parents + s / f);
+            k = ((uint64_t)(uint32_t)dst << 32) | (uint32_t)src;
+        }
+        keys[s] = k;
+    }
+}
+
+// ---- 2. row boundaries in the sorted keys -----------------------------------------------------
+// counters[0] = number of valid (non-dead) keys, counters[1] = number of unique edges
+__global__ void seg_bounds_kernel(int64_t n_slots, const uint64_t* __restrict__ keys, uint64_t dead,
+                                  int2* __restrict__ segmap, int32_t* __restrict__ counters) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int uniq = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        const uint64_t k = keys[i];
+        if (k >= dead) continue;
+        const uint64_t kp = (i > 0) ? keys[i - 1] : ~0ULL;
+        const uint64_t kn = (i + 1 < n_slots) ? keys[i + 1] : dead;
+        const uint32_t d = (uint32_t)(k >> 32);
+        if (i == 0 || (uint32_t)(kp >> 32) != d) segmap[d].x = (int32_t)i;
+        if (kn >= dead || (uint32_t)(kn >> 32) != d) segmap[d].y = (int32_t)(i + 1);
+        if (kn >= dead) counters[0] = (int32_t)(i + 1);
+        uniq += (i == 0 || kp != k);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, off);
+    if ((threadIdx.x & 31) == 0 && uniq) atomicAdd(counters + 1, uniq);
+}
+
+__global__ void seg_clear_kernel(int64_t n_slots, const uint64_t* __restrict__ keys, uint64_t dead,
+                                 int2* __restrict__ segmap) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        const uint64_t k = keys[i];
+        if (k >= dead) continue;
+        const uint64_t kp = (i > 0) ? keys[i - 1] : ~0ULL;
+        if (i == 0 || (kp >> 32) != (k >> 32)) segmap[(uint32_t)(k >> 32)] = make_int2(0, 0);
+    }
+}
+
+// ---- 3. local ids, level by level ------------------------------------------------------------
+// level_end[0] = 0, level_end[1] = n_roots, level_end[j + 1] = nodes after the j-th expansion
+__global__ void roots_assign_kernel(int64_t n_roots, const int32_t* __restrict__ roots, int64_t n_nodes,
+                                    int32_t* __restrict__ lid, int32_t* __restrict__ list, int32_t* err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_roots) return;
+    const int32_t v = roots[i];
+    if (v < 0 || v >= n_nodes) {
+        atomicExch(err, GIGL_E_RANGE);
+        list[i] = 0;
+        return;
+    }
+    list[i] = v;
+    atomicMin(lid + v, (int32_t)i);  // duplicate roots: the first slot owns the local id
+}
+
+__global__ void __launch_bounds__(256) expand_level_kernel(const int32_t* __restrict__ level_end, int level,
+                                                           const uint64_t* __restrict__ keys,
+                                                           const int2* __restrict__ segmap, int32_t* __restrict__ lid,
+                                                           int32_t* __restrict__ list, int32_t* __restrict__ n_nodes_ctr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t lo = level_end[level - 1], hi = level_end[level];
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = lo + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < hi; row += warps) {
+        const int32_t v = list[row];
+        const int2 seg = segmap[v];
+        for (int e = seg.x + lane; e < seg.y; e += 32) {
+            const int32_t s = (int32_t)(uint32_t)keys[e];
+            if (lid[s] != kLidAbsent) continue;
+            if (atomicCAS(lid + s, kLidAbsent, kLidPending) == kLidAbsent) {
+                const int32_t id = atomicAdd(n_nodes_ctr, 1);
+                list[id] = s;
+                lid[s] = id;
+            }
+        }
+    }
+}
+
+__global__ void level_snapshot_kernel(int32_t* level_end, int level, const int32_t* n_nodes_ctr) {
+    level_end[level] = *n_nodes_ctr;
+}
+
+__global__ void lid_clear_kernel(const int32_t* __restrict__ n_nodes_ctr, const int32_t* __restrict__ list,
+                                 int32_t* __restrict__ lid) {
+    const int64_t n = *n_nodes_ctr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lid[list[i]] = kLidAbsent;
+}
+
+__global__ void fill_i32_kernel(int64_t n, int32_t v, int32_t* __restrict__ p) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// ---- 4. gather: [mean of unique in-neighbours | self] rows -----------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// LPR lanes cover one 4*LPR-float chunk of a feature row; G = 32/LPR sources are in flight per step.
+// xsrc rows are indexed by global vertex id when lid == nullptr (layer 1 reads the graph-wide
+// feature table directly) or by lid[src] (deeper layers read the previous layer's rows).
+template <int LPR>
+__global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __restrict__ n_rows_dev, int64_t row_cap,
+                                                           int F, const int32_t* __restrict__ list,
+                                                           const int2* __restrict__ segmap,
+                                                           const uint64_t* __restrict__ keys,
+                                                           const float* __restrict__ xsrc, int64_t ldx,
+                                                           const int32_t* __restrict__ lid, float* __restrict__ A,
+                                                           int64_t ldA) {
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR, g = lane / LPR;
+    int64_t n_rows = *n_rows_dev;
+    if (n_rows > row_cap) n_rows = row_cap;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+        const int32_t v = __ldg(list + row);
+        const int2 seg = __ldg(segmap + v);
+        const int64_t self = lid ? row : (int64_t)v;
+        for (int c0 = 0; c0 < F; c0 += LPR * 4) {
+            const int c = c0 + sub * 4;
+            const bool active = c < F;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int n_uniq = 0;
+            for (int base = seg.x; base < seg.y; base += 32) {
+                const int cnt = min(32, seg.y - base);
+                int32_t my = -1;
+                if (lane < cnt) {
+                    const uint64_t k = __ldg(keys + base + lane);
+                    const bool dup = (base + lane > seg.x) && (__ldg(keys + base + lane - 1) == k);
+                    if (!dup) {
+                        const int32_t s = (int32_t)(uint32_t)k;
+                        my = lid ? __ldg(lid + s) : s;
+                    }
+                }
+                n_uniq += __popc(__ballot_sync(0xffffffffu, my >= 0));
+                for (int t = 0; t < cnt; t += 4 * G) {
+                    float4 val[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = t + u * G + g;
+                        const int32_t s = __shfl_sync(0xffffffffu, my, j & 31);
+                        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j < cnt && s >= 0 && active) val[u] = ldg4(xsrc + (int64_t)s * ldx + c);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc.x += val[u].x;
+                        acc.y += val[u].y;
+                        acc.z += val[u].z;
+                        acc.w += val[u].w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = LPR; off < 32; off <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+            }
+            if (g == 0 && active) {
+                const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
+                *reinterpret_cast<float4*>(A + row * ldA + c) =
+                    make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+                *reinterpret_cast<float4*>(A + row * ldA + F + c) = ldg4(xsrc + self * ldx + c);
+            }
+        }
+    }
+}
+
+// Any F / alignment.
+__global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t* __restrict__ n_rows_dev,
+                                                                  int64_t row_cap, int F,
+                                                                  const int32_t* __restrict__ list,
+                                                                  const int2* __restrict__ segmap,
+                                                                  const uint64_t* __restrict__ keys,
+                                                                  const float* __restrict__ xsrc, int64_t ldx,
+                                                                  const int32_t* __restrict__ lid,
+                                                                  float* __restrict__ A, int64_t ldA) {
+    const int lane = threadIdx.x & 31;
+    int64_t n_rows = *n_rows_dev;
+    if (n_rows > row_cap) n_rows = row_cap;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+        const int32_t v = __ldg(list + row);
+        const int2 seg = __ldg(segmap + v);
+        const int64_t self = lid ? row : (int64_t)v;
+        for (int c = lane; c < F; c += 32) {
+            float acc = 0.f;
+            int n_uniq = 0;
+            for (int e = seg.x; e < seg.y; ++e) {
+                const uint64_t k = __ldg(keys + e);
+                if (e > seg.x && __ldg(keys + e - 1) == k) continue;
+                const int32_t s0 = (int32_t)(uint32_t)k;
+                const int64_t s = lid ? __ldg(lid + s0) : s0;
+                acc += __ldg(xsrc + s * ldx + c);
+                ++n_uniq;
+            }
+            A[row * ldA + c] = acc * (1.0f / (float)(n_uniq > 1 ? n_uniq : 1));
+            A[row * ldA + F + c] = __ldg(xsrc + self * ldx + c);
+        }
+    }
+}
+
+}  // namespace gigl
+
+// =================================================================================================
+struct gigl_batch {
+    gigl_ctx* ctx = nullptr;
+    int64_t n_graph_nodes = 0;
+    int2* segmap = nullptr;   // dense [n_graph_nodes]: row [beg, end) in the sorted keys, {0,0} = no in-edge
+    int32_t* lid = nullptr;   // dense [n_graph_nodes]: local id in this batch, kLidAbsent = not in it
+    int32_t* d_ctr = nullptr; // [0] valid keys, [1] unique edges, [2] node counter, [4 + j] level_end[j]
+    int32_t* h_ctr = nullptr; // pinned mirror
+    // per-collate state
+    uint64_t* keys = nullptr;   // sorted keys of the current batch (inside `buf`)
+    void* buf = nullptr;        // keys_a | keys_b | list | cub temp
+    size_t buf_bytes = 0;
+    int32_t* list = nullptr;
+    int64_t n_slots = 0;
+    int64_t list_cap = 0;
+    uint64_t dead = 0;
+    int n_levels = 0;          // levels the forward needs (= n_layers of the collate call)
+    int n_levels_done = 0;     // level_end entries [1..n_levels_done] are valid
+    int n_hops = 0;
+    int64_t n_roots = 0;
+    bool dirty = false;
+    int64_t level_end_host[GIGL_MAX_HOPS + 2] = {};
+    int64_t n_valid_host = 0, n_unique_host = 0;
+};
+
+static constexpr int kCtrInts = 32;
+static constexpr int kLevelBase = 4;
+
+static unsigned grid1d(gigl_ctx* ctx, int64_t work, int block) {
+    int64_t g = ceil_div64(work > 0 ? work : 1, block);
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    return (unsigned)(g < cap ? g : cap);
+}
+
+int batch_create(gigl_ctx* ctx, int64_t n_graph_nodes, gigl_batch** out) {
+    using namespace gigl;
+    gigl_batch* b = new (std::nothrow) gigl_batch();
+    if (!b) return gigl_fail(ctx, GIGL_E_NOMEM, "out of host memory");
+    b->ctx = ctx;
+    b->n_graph_nodes = n_graph_nodes;
+    const size_t nn = (size_t)(n_graph_nodes > 0 ? n_graph_nodes : 1);
+    cudaError_t e = cudaMalloc(&b->segmap, sizeof(int2) * nn);
+    if (e == cudaSuccess) e = cudaMalloc(&b->lid, sizeof(int32_t) * nn);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_ctr, sizeof(int32_t) * kCtrInts);
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_ctr, sizeof(int32_t) * kCtrInts);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->segmap, 0, sizeof(int2) * nn, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_ctr, 0, sizeof(int32_t) * kCtrInts, ctx->stream);
+    if (e != cudaSuccess) {
+        if (b->segmap) cudaFree(b->segmap);
+        if (b->lid) cudaFree(b->lid);
+        if (b->d_ctr) cudaFree(b->d_ctr);
+        if (b->h_ctr) cudaFreeHost(b->h_ctr);
+        delete b;
+        return gigl_cuda_fail(ctx, e, "batch_create");
+    }
+    fill_i32_kernel<<<grid1d(ctx, n_graph_nodes, 256), 256, 0, ctx->stream>>>(n_graph_nodes, kLidAbsent, b->lid);
+    ctx->launches++;
+    *out = b;
+    return GIGL_OK;
+}
+
+static int batch_clear(gigl_batch* b) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    if (!b->dirty) return GIGL_OK;
+    if (b->n_slots > 0) {
+        seg_clear_kernel<<<grid1d(ctx, b->n_slots, 256), 256, 0, ctx->stream>>>(b->n_slots, b->keys, b->dead, b->segmap);
+        GIGL_LAUNCHED(ctx);
+    }
+    lid_clear_kernel<<<grid1d(ctx, b->list_cap, 256), 256, 0, ctx->stream>>>(b->d_ctr + 2, b->list, b->lid);
+    GIGL_LAUNCHED(ctx);
+    b->dirty = false;
+    return GIGL_OK;
+}
+
+void batch_destroy(gigl_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->segmap) cudaFree(b->segmap);
+    if (b->lid) cudaFree(b->lid);
+    if (b->d_ctr) cudaFree(b->d_ctr);
+    if (b->h_ctr) cudaFreeHost(b->h_ctr);
+    if (b->buf) cudaFree(b->buf);
+    delete b;
+}
+
+int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
+                  const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes_host, int64_t* n_edges_host) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS, "n_hops must be in [1, 8]");
+    GIGL_CHECK(ctx, n_layers >= 1 && n_layers <= GIGL_MAX_HOPS, "n_layers must be in [1, 8]");
+    GIGL_CHECK(ctx, n_roots >= 0 && n_roots <= 0x3fffffffLL, "bad n_roots");
+    GIGL_CHECK(ctx, fanouts && nbr_dev && (roots_dev || n_roots == 0), "null pointer");
+    int rc = batch_clear(b);
+    if (rc != GIGL_OK) return rc;
+    int64_t n_slots = 0, width = n_roots;
+    for (int h = 0; h < n_hops; ++h) {
+        GIGL_CHECK(ctx, fanouts[h] >= 1 && fanouts[h] <= GIGL_MAX_FANOUT, "fanout must be in [1, 128]");
+        width *= fanouts[h];
+        n_slots += width;
+        GIGL_CHECK(ctx, n_slots <= 0x7fffffffLL, "batch exceeds 2^31-1 edge slots; split the roots");
+    }
+    const int64_t list_cap = (n_roots + n_slots < b->n_graph_nodes + n_roots) ? n_roots + n_slots : b->n_graph_nodes + n_roots;
+    b->dead = (uint64_t)b->n_graph_nodes << 32;
+    const int end_bit = 32 + bits_for64(b->n_graph_nodes + 1);
+    const size_t ns = ((size_t)(n_slots > 0 ? n_slots : 1) + 31) & ~(size_t)31;
+    size_t temp_bytes = 0;
+    GIGL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                                  (int64_t)n_slots, 0, end_bit, ctx->stream));
+    const size_t list_bytes = (sizeof(int32_t) * (size_t)(list_cap > 0 ? list_cap : 1) + 255) & ~(size_t)255;
+    const size_t need = sizeof(uint64_t) * 2 * ns + list_bytes + temp_bytes + 256;
+    if (b->buf_bytes < need) {
+        if (b->buf) GIGL_CUDA(ctx, cudaFree(b->buf));
+        b->buf = nullptr;
+        b->buf_bytes = 0;
+        GIGL_CUDA(ctx, cudaMalloc(&b->buf, need + need / 8));
+        b->buf_bytes = need + need / 8;
+    }
+    uint64_t* keys_a = (uint64_t*)b->buf;
+    uint64_t* keys_b = keys_a + ns;
+    b->list = (int32_t*)(keys_b + ns);
+    void* temp = (char*)b->list + list_bytes;
+    b->keys = keys_b;
+    b->n_slots = n_slots;
+    b->list_cap = list_cap;
+    b->n_roots = n_roots;
+    b->dirty = true;
+    cudaStream_t st = ctx->stream;
+
+    // 1. keys
+    int64_t off = 0;
+    width = n_roots;
+    for (int h = 0; h < n_hops; ++h) {
+        const int32_t* parents = (h == 0) ? roots_dev : nbr_dev[h - 1];
+        width *= fanouts[h];
+        if (width > 0) {
+            tree_keys_kernel<<<grid1d(ctx, width, 256), 256, 0, st>>>(width, fanouts[h], parents, nbr_dev[h], b->dead, keys_a + off);
+            GIGL_LAUNCHED(ctx);
+        }
+        off += width;
+    }
+    // 2. sort + row bounds
+    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_ctr, 0, sizeof(int32_t) * kCtrInts, st));
+    if (n_slots > 0) {
+        GIGL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_a, keys_b, (int64_t)n_slots, 0, end_bit, st));
+        ctx->launches++;
+        seg_bounds_kernel<<<grid1d(ctx, n_slots, 256), 256, 0, st>>>(n_slots, keys_b, b->dead, b->segmap, b->d_ctr);
+        GIGL_LAUNCHED(ctx);
+    }
+    // 3. levels: level_end[1] = n_roots, then n_layers - 1 expansions
+    if (n_roots > 0) {
+        roots_assign_kernel<<<(unsigned)ceil_div64(n_roots, 256), 256, 0, st>>>(n_roots, roots_dev, b->n_graph_nodes, b->lid, b->list, ctx->d_err);
+        GIGL_LAUNCHED(ctx);
+    }
+    const int32_t init[3] = {(int32_t)n_roots, 0, (int32_t)n_roots};
+    GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + 2, &init[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + kLevelBase, &init[1], sizeof(int32_t) * 2, cudaMemcpyHostToDevice, st));
+    for (int j = 1; j < n_layers; ++j) {
+        expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->segmap, b->lid, b->list, b->d_ctr + 2);
+        GIGL_LAUNCHED(ctx);
+        level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
+        GIGL_LAUNCHED(ctx);
+    }
+    b->n_levels = n_layers;
+    b->n_levels_done = n_layers;
+    b->n_hops = n_hops;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(int32_t) * kCtrInts, cudaMemcpyDeviceToHost, st));
+    GIGL_CUDA(ctx, cudaStreamSynchronize(st));
+    b->n_valid_host = b->h_ctr[0];
+    b->n_unique_host = b->h_ctr[1];
+    for (int j = 0; j <= n_layers; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
+    if (level_sizes_host)
+        for (int j = 0; j < n_layers; ++j) level_sizes_host[j] = b->level_end_host[j + 1];
+    if (n_edges_host) *n_edges_host = b->n_unique_host;
+    return GIGL_OK;
+}
+
+// Implemented in sage_aggregate.cu: C[M, N] = A[M, K] (ld = lda) @ W[N, K]^T (ld = ldw) + bias, optional relu;
+// M is read on the device from *m_dev (clamped to m_cap).
+int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, int N, int K, const float* A, int64_t lda,
+                           const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);
+
+// ---- model: PyG GraphSAGE weights resident on the device -------------------------------------
+struct gigl_sage_model {
+    gigl_ctx* ctx = nullptr;
+    int n_layers = 0;
+    int dims[GIGL_MAX_HOPS + 1] = {};
+    int64_t ldw[GIGL_MAX_HOPS] = {};      // leading dimension of Wcat[l] (>= 2 * dims[l], multiple of 4)
+    float* wcat[GIGL_MAX_HOPS] = {};      // [dims[l+1], ldw]: row o = [lin_l.weight[o, :] | lin_r.weight[o, :] | 0]
+    float* bias[GIGL_MAX_HOPS] = {};      // lin_l.bias or nullptr
+    float* blob = nullptr;
+};
+
+int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl, const float* const* bl,
+                      const float* const* Wr, int weights_on_device, gigl_sage_model** out) {
+    GIGL_CHECK(ctx, n_layers >= 1 && n_layers <= GIGL_MAX_HOPS && dims && Wl && Wr && out, "bad model arguments");
+    size_t total = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        GIGL_CHECK(ctx, dims[l] >= 1 && dims[l + 1] >= 1 && Wl[l] && Wr[l], "bad layer");
+        const size_t ld = ((size_t)2 * dims[l] + 3) & ~(size_t)3;
+        total += (size_t)dims[l + 1] * ld + (((size_t)dims[l + 1] + 3) & ~(size_t)3);
+    }
+    gigl_sage_model* m = new (std::nothrow) gigl_sage_model();
+    if (!m) return gigl_fail(ctx, GIGL_E_NOMEM, "out of host memory");
+    m->ctx = ctx;
+    m->n_layers = n_layers;
+    cudaError_t e = cudaMalloc(&m->blob, sizeof(float) * total);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->blob, 0, sizeof(float) * total, ctx->stream);
+    size_t off = 0;
+    const cudaMemcpyKind kind = weights_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int l = 0; l < n_layers && e == cudaSuccess; ++l) {
+        const int Fi = dims[l], Fo = dims[l + 1];
+        const size_t ld = ((size_t)2 * Fi + 3) & ~(size_t)3;
+        m->dims[l] = Fi;
+        m->dims[l + 1] = Fo;
+        m->ldw[l] = (int64_t)ld;
+        m->wcat[l] = m->blob + off;
+        off += (size_t)Fo * ld;
+        e = cudaMemcpy2DAsync(m->wcat[l], sizeof(float) * ld, Wl[l], sizeof(float) * Fi, sizeof(float) * Fi, Fo, kind, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(m->wcat[l] + Fi, sizeof(float) * ld, Wr[l], sizeof(float) * Fi, sizeof(float) * Fi, Fo, kind, ctx->stream);
+        if (bl && bl[l]) {
+            m->bias[l] = m->blob + off;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(m->bias[l], bl[l], sizeof(float) * Fo, kind, ctx->stream);
+        }
+        off += ((size_t)Fo + 3) & ~(size_t)3;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // host weight buffers may be freed by the caller
+    if (e != cudaSuccess) {
+        if (m->blob) cudaFree(m->blob);
+        delete m;
+        return gigl_cuda_fail(ctx, e, "sage_model_create");
+    }
+    *out = m;
+    return GIGL_OK;
+}
+
+void sage_model_destroy(gigl_sage_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    if (m->blob) cudaFree(m->blob);
+    delete m;
+}
+
+int sage_model_dims(const gigl_sage_model* m, int32_t* n_layers, int32_t* dims) {
+    if (n_layers) *n_layers = m->n_layers;
+    if (dims)
+        for (int l = 0; l <= m->n_layers; ++l) dims[l] = m->dims[l];
+    return GIGL_OK;
+}
+
+int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx0, float* out_dev) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    const int n_layers = m->n_layers;
+    GIGL_CHECK(ctx, b->dirty && b->n_levels == n_layers, "collate the batch with n_layers == the model's layer count first");
+    GIGL_CHECK(ctx, x_dev && out_dev && ldx0 >= m->dims[0], "bad feature table");
+    if (b->n_roots == 0) return GIGL_OK;
+    cudaStream_t st = ctx->stream;
+    size_t a_elems = 0, h_elems = 0;
+    for (int l = 1; l <= n_layers; ++l) {
+        const int64_t rows = b->level_end_host[n_layers - l + 1];
+        const int64_t lda = m->ldw[l - 1];
+        if ((size_t)(rows * lda) > a_elems) a_elems = (size_t)(rows * lda);
+        if (l < n_layers && (size_t)(rows * m->dims[l]) > h_elems) h_elems = (size_t)(rows * m->dims[l]);
+    }
+    h_elems = (h_elems + 3) & ~(size_t)3;
+    void *pA = nullptr, *pH = nullptr;
+    int rc;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * (a_elems + 4), &pA)) != GIGL_OK) return rc;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO3, sizeof(float) * (2 * h_elems + 8), &pH)) != GIGL_OK) return rc;
+    float* A = (float*)pA;
+    float* hbuf[2] = {(float*)pH, (float*)pH + h_elems};
+    const float* xin = x_dev;
+    int64_t ldx = ldx0;
+    for (int l = 1; l <= n_layers; ++l) {
+        const int Fi = m->dims[l - 1], Fo = m->dims[l];
+        const int64_t rows = b->level_end_host[n_layers - l + 1];
+        const int32_t* rows_dev = b->d_ctr + kLevelBase + (n_layers - l + 1);
+        const int64_t lda = m->ldw[l - 1];
+        const int32_t* lidmap = (l == 1) ? nullptr : b->lid;
+        const int wpb = 8;
+        const unsigned grid = (unsigned)ceil_div64(rows, wpb);
+        const bool vec = (Fi % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0) && (ldx % 4 == 0);
+        if (!vec)
+            batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
+        else if (Fi <= 16)
+            batch_gather_kernel<4><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
+        else if (Fi <= 32)
+            batch_gather_kernel<8><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
+        else if (Fi <= 64)
+            batch_gather_kernel<16><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
+        else
+            batch_gather_kernel<32><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
+        GIGL_LAUNCHED(ctx);
+        float* C = (l == n_layers) ? out_dev : hbuf[l & 1];
+        rc = linear_dev_rows_launch(ctx, rows_dev, rows, Fo, 2 * Fi, A, lda, m->wcat[l - 1], lda, m->bias[l - 1], C, Fo,
+                                    l < n_layers ? 1 : 0);
+        if (rc != GIGL_OK) return rc;
+        xin = C;
+        ldx = Fo;
+    }
+    return GIGL_OK;
+}
+
+gigl_ctx* batch_ctx(gigl_batch* b) { return b->ctx; }
+
+namespace gigl {
+// compacted unique keys (dst << 32 | src, global ids) -> edge_index rows in local ids
+__global__ void export_edges_kernel(int64_t n_unique, const uint64_t* __restrict__ uniq, const int32_t* __restrict__ lid,
+                                    int64_t* __restrict__ edge_index) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_unique; i += stride) {
+        const uint64_t k = uniq[i];
+        edge_index[i] = lid[(uint32_t)k];
+        edge_index[n_unique + i] = lid[(uint32_t)(k >> 32)];
+    }
+}
+}  // namespace gigl
+
+int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    GIGL_CHECK(ctx, b->dirty, "collate a batch first");
+    cudaStream_t st = ctx->stream;
+    const int want = (b->n_hops > b->n_levels ? b->n_hops : b->n_levels) + 1;  // level_end entries [1..want]
+    if (b->n_levels_done < want && b->n_roots > 0) {
+        for (int j = b->n_levels_done; j < want; ++j) {
+            expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->segmap, b->lid, b->list, b->d_ctr + 2);
+            GIGL_LAUNCHED(ctx);
+            level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
+            GIGL_LAUNCHED(ctx);
+        }
+        b->n_levels_done = want;
+        GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(int32_t) * kCtrInts, cudaMemcpyDeviceToHost, st));
+        GIGL_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int j = 0; j <= want; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
+    }
+    if (n_nodes) *n_nodes = b->n_roots > 0 ? b->level_end_host[b->n_levels_done] : 0;
+    if (n_edges) *n_edges = b->n_unique_host;
+    return GIGL_OK;
+}
+
+int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    int64_t n_nodes = 0, n_edges = 0;
+    int rc = batch_finalize_nodes(b, &n_nodes, &n_edges);
+    if (rc != GIGL_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    if (n_nodes > 0) {
+        GIGL_CHECK(ctx, node_ids_dev != nullptr, "null node_ids");
+        GIGL_CUDA(ctx, cudaMemcpyAsync(node_ids_dev, b->list, sizeof(int32_t) * (size_t)n_nodes, cudaMemcpyDeviceToDevice, st));
+    }
+    if (n_edges > 0) {
+        GIGL_CHECK(ctx, edge_index_dev != nullptr, "null edge_index");
+        // compact the unique keys (CUB select, plumbing) into scratch, then translate to local ids
+        void* pu = nullptr;
+        size_t tb = 0;
+        GIGL_CUDA(ctx, cub::DeviceSelect::Unique(nullptr, tb, b->keys, (uint64_t*)nullptr, (int32_t*)nullptr, (int64_t)b->n_valid_host, st));
+        const size_t ub = (sizeof(uint64_t) * (size_t)b->n_valid_host + 255) & ~(size_t)255;
+        if ((rc = gigl_scratch(ctx, GIGL_SLOT_SORT, ub + tb + 256, &pu)) != GIGL_OK) return rc;
+        uint64_t* uniq = (uint64_t*)pu;
+        GIGL_CUDA(ctx, cub::DeviceSelect::Unique((char*)pu + ub, tb, b->keys, uniq, b->d_ctr + 3, (int64_t)b->n_valid_host, st));
+        ctx->launches++;
+        export_edges_kernel<<<grid1d(ctx, n_edges, 256), 256, 0, st>>>(n_edges, uniq, b->lid, edge_index_dev);
+        GIGL_LAUNCHED(ctx);
+    }
+    return GIGL_OK;
+}
+

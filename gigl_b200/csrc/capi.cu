@@ -313,6 +313,11 @@ void gigl_graph_destroy(gigl_graph* g) {
         cudaFree((void*)g->rowptr);
         cudaFree((void*)g->col);
     }
+    if (g->x_owned && g->x) {
+        cudaSetDevice(g->ctx->device);
+        cudaStreamSynchronize(g->ctx->stream);
+        cudaFree((void*)g->x);
+    }
     delete g;
 }
 
@@ -447,6 +452,167 @@ int gigl_gcn_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O
                             [&](const int64_t* rowptr, const int32_t* col, const float* xd, const float* const* wd, float* od) {
                                 return gcn_conv_launch(ctx, n, F, O, rowptr, col, xd, wd[0], wd[1], od, relu);
                             });
+}
+
+// ---- features / model / batch -----------------------------------------------------------------
+
+static void graph_drop_features(gigl_graph* g) {
+    if (g->x_owned && g->x) cudaFree((void*)g->x);
+    g->x = nullptr;
+    g->F = 0;
+    g->x_owned = false;
+}
+
+int gigl_graph_set_features_host(gigl_graph* g, const float* x, int32_t F) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, F >= 1 && (x != nullptr || g->n_nodes == 0), "bad feature table");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    graph_drop_features(g);
+    float* d = nullptr;
+    const size_t bytes = sizeof(float) * (size_t)(g->n_nodes > 0 ? g->n_nodes : 1) * (size_t)F;
+    GIGL_CUDA(ctx, cudaMalloc(&d, bytes));
+    cudaError_t e = cudaSuccess;
+    if (g->n_nodes > 0) e = cudaMemcpyAsync(d, x, sizeof(float) * (size_t)g->n_nodes * F, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return gigl_cuda_fail(ctx, e, "feature upload");
+    }
+    g->x = d;
+    g->F = F;
+    g->x_owned = true;
+    return GIGL_OK;
+}
+
+int gigl_graph_set_features_dev(gigl_graph* g, const float* x_dev, int32_t F) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    GIGL_CHECK(g->ctx, F >= 1 && x_dev != nullptr, "bad feature table");
+    graph_drop_features(g);
+    g->x = x_dev;
+    g->F = F;
+    g->x_owned = false;
+    return GIGL_OK;
+}
+
+int gigl_graph_features_dev(const gigl_graph* g, const float** x_dev, int32_t* F) {
+    if (!g) return GIGL_E_INVALID;
+    if (x_dev) *x_dev = g->x;
+    if (F) *F = g->F;
+    return GIGL_OK;
+}
+
+int gigl_sage_model_create_host(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl,
+                                const float* const* bl, const float* const* Wr, gigl_sage_model** out) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sage_model_create(ctx, n_layers, dims, Wl, bl, Wr, 0, out);
+}
+
+int gigl_sage_model_create_dev(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl_dev,
+                               const float* const* bl_dev, const float* const* Wr_dev, gigl_sage_model** out) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sage_model_create(ctx, n_layers, dims, Wl_dev, bl_dev, Wr_dev, 1, out);
+}
+
+void gigl_sage_model_destroy(gigl_sage_model* m) { sage_model_destroy(m); }
+
+int gigl_batch_create(gigl_ctx* ctx, int64_t n_graph_nodes, gigl_batch** out) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, out != nullptr && n_graph_nodes >= 0 && n_graph_nodes <= 0x7fffffffLL, "bad arguments");
+    *out = nullptr;
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return batch_create(ctx, n_graph_nodes, out);
+}
+
+void gigl_batch_destroy(gigl_batch* b) { batch_destroy(b); }
+
+int gigl_batch_collate_dev(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                           int32_t n_hops, const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes,
+                           int64_t* n_edges) {
+    if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
+    gigl_ctx* ctx = batch_ctx(b);
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = batch_collate(b, roots_dev, n_roots, fanouts, n_hops, nbr_dev, n_layers, level_sizes, n_edges);
+    if (rc != GIGL_OK) return rc;
+    return ctx_check_device_error(ctx);
+}
+
+int gigl_batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges) {
+    if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
+    GIGL_CUDA(batch_ctx(b), cudaSetDevice(batch_ctx(b)->device));
+    return batch_finalize_nodes(b, n_nodes, n_edges);
+}
+
+int gigl_batch_export_dev(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev) {
+    if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
+    GIGL_CUDA(batch_ctx(b), cudaSetDevice(batch_ctx(b)->device));
+    return batch_export(b, node_ids_dev, edge_index_dev);
+}
+
+int gigl_batch_sage_forward_dev(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx,
+                                float* out_dev) {
+    if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
+    gigl_ctx* ctx = batch_ctx(b);
+    GIGL_CHECK(ctx, m != nullptr, "null model");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return batch_sage_forward(b, m, x_dev, ldx, out_dev);
+}
+
+int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots,
+                              int64_t n_roots, const int32_t* fanouts, int32_t n_hops, int32_t base_seed,
+                              int32_t first_call_no, float* out, int32_t* const* nbr, int32_t* const* cnt) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, b != nullptr && m != nullptr && batch_ctx(b) == ctx, "batch / model must belong to the graph's ctx");
+    GIGL_CHECK(ctx, g->x != nullptr, "the graph holds no features (gigl_graph_set_features_*)");
+    GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS && fanouts, "n_hops must be in [1, 8]");
+    GIGL_CHECK(ctx, n_roots >= 0 && (roots || n_roots == 0) && (out || n_roots == 0), "bad roots / out");
+    int32_t n_layers = 0, dims[GIGL_MAX_HOPS + 1];
+    sage_model_dims(m, &n_layers, dims);
+    GIGL_CHECK(ctx, dims[0] == g->F, "model input width != feature width");
+    if (n_roots == 0) return GIGL_OK;
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t total = (size_t)n_roots, width = 1;
+    size_t off_cnt[GIGL_MAX_HOPS], off_nbr[GIGL_MAX_HOPS];
+    for (int h = 0; h < n_hops; ++h) {
+        GIGL_CHECK(ctx, fanouts[h] >= 1 && fanouts[h] <= GIGL_MAX_FANOUT, "fanout must be in [1, 128]");
+        off_cnt[h] = total;
+        total += (size_t)n_roots * width;
+        width *= (size_t)fanouts[h];
+        if ((double)n_roots * (double)width > 2147483647.0)
+            return gigl_fail(ctx, GIGL_E_INVALID, "frontier exceeds 2^31-1 slots; split the roots");
+        off_nbr[h] = total;
+        total += (size_t)n_roots * width;
+    }
+    void *buf = nullptr, *pout = nullptr;
+    int rc = gigl_scratch(ctx, GIGL_SLOT_IO0, sizeof(int32_t) * total, &buf);
+    if (rc != GIGL_OK) return rc;
+    const int O = dims[n_layers];
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO1, sizeof(float) * (size_t)n_roots * O, &pout)) != GIGL_OK) return rc;
+    int32_t* d = (int32_t*)buf;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(d, roots, sizeof(int32_t) * (size_t)n_roots, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t* nbr_dev[GIGL_MAX_HOPS];
+    int32_t* cnt_dev[GIGL_MAX_HOPS];
+    for (int h = 0; h < n_hops; ++h) {
+        nbr_dev[h] = d + off_nbr[h];
+        cnt_dev[h] = d + off_cnt[h];
+    }
+    if ((rc = khop_sample_launch(g, d, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev)) != GIGL_OK) return rc;
+    if (nbr && cnt) {  // the index sets leave while the aggregate runs
+        width = 1;
+        for (int h = 0; h < n_hops; ++h) {
+            if (cnt[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(cnt[h], cnt_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->stream));
+            width *= (size_t)fanouts[h];
+            if (nbr[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(nbr[h], nbr_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    if ((rc = batch_collate(b, d, n_roots, fanouts, n_hops, nbr_dev, n_layers, nullptr, nullptr)) != GIGL_OK) return rc;
+    if ((rc = batch_sage_forward(b, m, g->x, g->F, (float*)pout)) != GIGL_OK) return rc;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(out, pout, sizeof(float) * (size_t)n_roots * O, cudaMemcpyDeviceToHost, ctx->stream));
+    return ctx_check_device_error(ctx);
 }
 
 }  // extern "C"

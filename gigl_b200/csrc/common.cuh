@@ -42,6 +42,9 @@ struct gigl_graph {
     const int64_t* rowptr = nullptr;  // device
     const int32_t* col = nullptr;     // device
     bool owned = false;
+    const float* x = nullptr;  // device feature table [n_nodes, F] (optional)
+    int32_t F = 0;
+    bool x_owned = false;
 };
 
 int gigl_fail(gigl_ctx* ctx, int code, const std::string& msg);
@@ -86,3 +89,19 @@ int sage_conv_launch(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, in
                      float* out, int32_t relu);
 int gcn_conv_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr, const int32_t* col,
                     const float* x, const float* W, const float* b, float* out, int32_t relu);
+
+// batch_collate.cu
+struct gigl_batch;
+struct gigl_sage_model;
+int batch_create(gigl_ctx* ctx, int64_t n_graph_nodes, gigl_batch** out);
+void batch_destroy(gigl_batch* b);
+int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
+                  const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes_host, int64_t* n_edges_host);
+int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges);
+int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev);
+int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx, float* out_dev);
+gigl_ctx* batch_ctx(gigl_batch* b);
+int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl, const float* const* bl,
+                      const float* const* Wr, int weights_on_device, gigl_sage_model** out);
+void sage_model_destroy(gigl_sage_model* m);
+int sage_model_dims(const gigl_sage_model* m, int32_t* n_layers, int32_t* dims);

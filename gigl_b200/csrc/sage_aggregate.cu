@@ -231,6 +231,69 @@ __global__ void __launch_bounds__(256) linear2_kernel(int64_t M, int N, int K0, 
     }
 }
 
+// C[M, N] = A[M, K] @ W[N, K]^T + bias, optional relu; explicit leading dimensions, and M may live
+// on the device (*m_dev, clamped to M) so a batch pipeline needs no host round trip.  fp32 FFMA.
+__global__ void __launch_bounds__(256) linear_ld_kernel(const int32_t* __restrict__ m_dev, int64_t M, int N, int K,
+                                                        const float* __restrict__ A, int64_t lda,
+                                                        const float* __restrict__ W, int64_t ldw,
+                                                        const float* __restrict__ bias, float* __restrict__ C,
+                                                        int64_t ldc, int relu) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    if (m_dev) {
+        const int64_t md = *m_dev;
+        if (md < M) M = md;
+    }
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    if (m0 >= M) return;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.y * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + lk + q;
+            const int64_t m = m0 + lr;
+            const int n = n0 + lr;
+            As[lk + q][lr] = (m < M && k < K) ? __ldg(A + m * lda + k) : 0.f;
+            Bs[lk + q][lr] = (n < N && k < K) ? __ldg(W + (int64_t)n * ldw + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
+            if (relu) v = fmaxf(v, 0.f);
+            C[m * ldc + n] = v;
+        }
+    }
+}
+
 template <int MODE>
 static int launch_gather(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t* rowptr, const int32_t* col,
                          const float* x, float* out, const float* dinv, const float* bias, int relu) {
@@ -269,6 +332,18 @@ static int launch_linear2(gigl_ctx* ctx, int64_t M, int N, int K0, int K1, const
 }
 
 }  // namespace gigl
+
+int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, int N, int K, const float* A, int64_t lda,
+                           const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu) {
+    using namespace gigl;
+    if (m_cap == 0 || N == 0) return GIGL_OK;
+    const int64_t gx = ceil_div64(m_cap, BM);
+    if (gx > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "too many rows for one launch");
+    dim3 grid((unsigned)gx, (unsigned)((N + BN - 1) / BN));
+    linear_ld_kernel<<<grid, 256, 0, ctx->stream>>>(m_dev, m_cap, N, K, A, lda, W, ldw, bias, C, ldc, relu);
+    GIGL_LAUNCHED(ctx);
+    return GIGL_OK;
+}
 
 int gather_mean_launch(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t* rowptr, const int32_t* col,
                        const float* x, float* agg) {

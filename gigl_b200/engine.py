@@ -259,6 +259,46 @@ class Graph:
                                                      _hp(cnt)), self.ctx.handle)
         return pos, cnt
 
+    # -- resident features
+    def set_features_host(self, x) -> None:
+        x = _np(x, np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.n_nodes
+        check(self.ctx._L.gigl_graph_set_features_host(self.handle, _hp(x), x.shape[1]), self.ctx.handle)
+        self._x = None
+        self.F = x.shape[1]
+
+    def set_features(self, x) -> None:
+        """Wrap a [n_nodes, F] fp32 CUDA tensor (kept alive by this object)."""
+        assert x.is_cuda and x.dim() == 2 and x.shape[0] == self.n_nodes and x.is_contiguous()
+        check(self.ctx._L.gigl_graph_set_features_dev(self.handle, _dp(x), x.shape[1]), self.ctx.handle)
+        self._x = x
+        self.F = x.shape[1]
+
+    def infer_khop_sage_host(self, batch: "Batch", model: "SageModel", roots, fanouts: Sequence[int], base_seed: int = 42,
+                             first_call_no: int = 1, return_samples: bool = False, out=None, samples_out=None):
+        """roots (host) -> sample -> collate -> GraphSAGE -> root embeddings (host numpy [n_roots, O])."""
+        roots = _np(roots, np.int32)
+        fan = _np(fanouts, np.int32)
+        n_roots, n_hops = len(roots), len(fan)
+        if out is None:
+            out = np.empty((n_roots, model.dims[-1]), dtype=np.float32)
+        pn = pc = None
+        nbr = cnt = None
+        if return_samples:
+            if samples_out is None:
+                nbr, cnt, width = [], [], 1
+                for f in fan:
+                    cnt.append(np.empty(n_roots * width, dtype=np.int32))
+                    width *= int(f)
+                    nbr.append(np.empty(n_roots * width, dtype=np.int32))
+            else:
+                nbr, cnt = samples_out
+            pn = (C.c_void_p * n_hops)(*[a.ctypes.data for a in nbr])
+            pc = (C.c_void_p * n_hops)(*[a.ctypes.data for a in cnt])
+        check(self.ctx._L.gigl_infer_khop_sage_host(self.handle, batch.handle, model.handle, _hp(roots), n_roots, _hp(fan),
+                                                    n_hops, base_seed, first_call_no, _hp(out), pn, pc), self.ctx.handle)
+        return (out, nbr, cnt) if return_samples else out
+
     def close(self) -> None:
         if self.handle and self.ctx.handle:
             self.ctx._L.gigl_graph_destroy(self.handle)
@@ -269,6 +309,111 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+
+class SageModel:
+    """gigl_sage_model: torch_geometric.nn.GraphSAGE weights resident on the device.
+
+    ``layers`` = [(lin_l.weight [O,F], lin_l.bias [O] | None, lin_r.weight [O,F]), ...] as numpy arrays
+    (PyG state_dict order, graphsage_template_modeling_spec.py:143-148) or CUDA tensors."""
+
+    def __init__(self, ctx: Context, layers):
+        self.ctx = ctx
+        n = len(layers)
+        on_dev = hasattr(layers[0][0], "is_cuda")
+        if on_dev:
+            keep = [(Wl.contiguous(), None if bl is None else bl.contiguous(), Wr.contiguous()) for Wl, bl, Wr in layers]
+            ptr = lambda t: 0 if t is None else t.data_ptr()
+        else:
+            keep = [(_np(Wl, np.float32), None if bl is None else _np(bl, np.float32), _np(Wr, np.float32)) for Wl, bl, Wr in layers]
+            ptr = lambda a: 0 if a is None else a.ctypes.data
+        self.dims = [int(keep[0][0].shape[1])] + [int(k[0].shape[0]) for k in keep]
+        for l, (Wl, bl, Wr) in enumerate(keep):
+            assert tuple(Wl.shape) == (self.dims[l + 1], self.dims[l]) and tuple(Wr.shape) == tuple(Wl.shape)
+        dims = _np(self.dims, np.int32)
+        pWl = (C.c_void_p * n)(*[ptr(k[0]) for k in keep])
+        pbl = (C.c_void_p * n)(*[ptr(k[1]) for k in keep])
+        pWr = (C.c_void_p * n)(*[ptr(k[2]) for k in keep])
+        h = C.c_void_p()
+        fn = ctx._L.gigl_sage_model_create_dev if on_dev else ctx._L.gigl_sage_model_create_host
+        check(fn(ctx.handle, n, _hp(dims), pWl, pbl, pWr, C.byref(h)), ctx.handle)
+        self.handle = h
+        self.n_layers = n
+
+    def close(self) -> None:
+        if self.handle and self.ctx.handle:
+            self.ctx._L.gigl_sage_model_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """gigl_batch: reusable collation workspace (B sampled neighbourhoods -> one coalesced graph)."""
+
+    def __init__(self, ctx: Context, n_graph_nodes: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(ctx._L.gigl_batch_create(ctx.handle, n_graph_nodes, C.byref(h)), ctx.handle)
+        self.handle = h
+        self.level_sizes: List[int] = []
+        self.n_edges = 0
+
+    def collate(self, roots, fanouts: Sequence[int], nbr, n_layers: int):
+        """roots: int32 CUDA tensor; nbr: the per-hop tensors of Graph.sample_khop.  Returns level sizes."""
+        fan = _np(fanouts, np.int32)
+        n_hops = len(fan)
+        pn = (C.c_void_p * n_hops)(*[t.data_ptr() for t in nbr])
+        ls = (C.c_int64 * n_layers)()
+        ne = C.c_int64()
+        check(self.ctx._L.gigl_batch_collate_dev(self.handle, _dp(roots), roots.numel(), _hp(fan), n_hops, pn, n_layers, ls,
+                                                 C.byref(ne)), self.ctx.handle)
+        self.level_sizes = [int(v) for v in ls]
+        self.n_edges = int(ne.value)
+        self._n_roots = roots.numel()
+        self._device = roots.device
+        return self.level_sizes
+
+    def sage_forward(self, model: SageModel, x, out=None):
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+        if out is None:
+            out = torch.empty((self._n_roots, model.dims[-1]), dtype=torch.float32, device=x.device)
+        check(self.ctx._L.gigl_batch_sage_forward_dev(self.handle, model.handle, _dp_any(x), x.stride(0), _dp(out)), self.ctx.handle)
+        return out
+
+    def export(self):
+        """(node_ids int32 [n], edge_index int64 [2, e] in local ids) as CUDA tensors."""
+        import torch
+
+        n, e = C.c_int64(), C.c_int64()
+        check(self.ctx._L.gigl_batch_finalize_nodes(self.handle, C.byref(n), C.byref(e)), self.ctx.handle)
+        node_ids = torch.empty(n.value, dtype=torch.int32, device=self._device)
+        ei = torch.empty((2, e.value), dtype=torch.int64, device=self._device)
+        check(self.ctx._L.gigl_batch_export_dev(self.handle, _dp(node_ids) if n.value else None,
+                                                _dp(ei) if e.value else None), self.ctx.handle)
+        return node_ids, ei
+
+    def close(self) -> None:
+        if self.handle and self.ctx.handle:
+            self.ctx._L.gigl_batch_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _dp_any(t):
+    assert t.is_cuda
+    return C.c_void_p(t.data_ptr())
 
 
 def _tensor_from_ptr(ptr: int, shape, dtype, device, owner=None):

@@ -192,6 +192,83 @@ int gigl_gcn_conv_dev(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int6
 int gigl_gcn_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O, const int64_t* edge_index,
                        const float* x, const float* W, const float* b, float* out, int32_t relu);
 
+/* ---- resident node features ------------------------------------------------------------- */
+
+/*
+ * The graph-wide feature table x[n_nodes, F] fp32 (row v = _node_features of node v, the flattened
+ * featureKeys of loadNodeDataframeIntoSparkSql, SGSPureSparkV1Task.scala:90-104).  *_host copies it
+ * to HBM (owned by the graph); *_dev wraps a device array the caller keeps alive.
+ */
+int gigl_graph_set_features_host(gigl_graph* g, const float* x, int32_t F);
+int gigl_graph_set_features_dev(gigl_graph* g, const float* x_dev, int32_t F);
+int gigl_graph_features_dev(const gigl_graph* g, const float** x_dev, int32_t* F);
+
+/* ---- model: GraphSAGE weights resident on the device ------------------------------------ */
+
+typedef struct gigl_sage_model gigl_sage_model;
+/*
+ * torch_geometric.nn.GraphSAGE(in, hidden, num_layers, out) as the reference builds it
+ * (graphsage_template_modeling_spec.py:143-148; homogeneous.py:171-202): layer l maps dims[l] ->
+ * dims[l+1]; Wl[l] = convs.{l}.lin_l.weight [dims[l+1], dims[l]], bl[l] = convs.{l}.lin_l.bias
+ * (or NULL), Wr[l] = convs.{l}.lin_r.weight.  ReLU between layers, none after the last.
+ * The weights are copied (host or device source) and re-laid out as [Wl | Wr] per layer.
+ */
+int gigl_sage_model_create_host(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl,
+                                const float* const* bl, const float* const* Wr, gigl_sage_model** out);
+int gigl_sage_model_create_dev(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl_dev,
+                               const float* const* bl_dev, const float* const* Wr_dev, gigl_sage_model** out);
+void gigl_sage_model_destroy(gigl_sage_model* m);
+
+/* ---- batch: B sampled neighbourhoods -> one coalesced graph -> root embeddings ----------- */
+
+typedef struct gigl_batch gigl_batch;
+/*
+ * A reusable collation workspace for graphs of n_graph_nodes vertices (dense per-vertex maps in
+ * HBM: 12 bytes x n_graph_nodes).  Replaces the per-batch Python graph building of
+ * python/gigl/src/common/graph_builder/pyg_graph_builder.py:20-69 and the collate functions of
+ * python/gigl/src/training/v1/lib/data_loaders/ (see gigl_b200/csrc/batch_collate.cu).
+ */
+int gigl_batch_create(gigl_ctx* ctx, int64_t n_graph_nodes, gigl_batch** out);
+void gigl_batch_destroy(gigl_batch* b);
+/*
+ * Coalesces the padded-tree sample of gigl_sample_khop_dev (same roots / fanouts / nbr tables, all
+ * on the device) into the batch graph: nodes de-duplicated by id, edges de-duplicated by
+ * (src, dst).  n_layers = the depth of the model that will run on it: local ids are ordered so
+ * that the first level_sizes[j] nodes are exactly those whose layer-(n_layers - j) output the root
+ * embeddings depend on (level_sizes[0] = n_roots).  Synchronises the stream once to return the
+ * sizes.  level_sizes: host int64[n_layers]; n_edges: unique edges of the batch graph.
+ */
+int gigl_batch_collate_dev(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                           int32_t n_hops, const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes,
+                           int64_t* n_edges);
+/*
+ * The batch graph as the reference's PygGraphBuilder would hand it to the model.
+ * gigl_batch_finalize_nodes gives every remaining batch node a local id (the levels above only
+ * cover what the root outputs need) and returns the sizes; gigl_batch_export_dev then writes
+ * node_ids int32[n_nodes] (local id -> global id; roots first) and edge_index int64[2, n_edges]
+ * in LOCAL ids (row 0 = src, row 1 = dst; sorted by (dst, src) global id), both device arrays.
+ */
+int gigl_batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges);
+int gigl_batch_export_dev(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev);
+/*
+ * model(x, edge_index)[root rows] on the collated batch: out_dev [n_roots, dims[n_layers]] fp32.
+ * x_dev is the graph-wide feature table indexed by GLOBAL node id (row stride ldx floats).
+ */
+int gigl_batch_sage_forward_dev(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx,
+                                float* out_dev);
+
+/*
+ * One call from host buffers: roots (host) -> k-hop sample -> collate -> GraphSAGE forward ->
+ * root embeddings (host).  The graph must hold features (gigl_graph_set_features_*).  If nbr / cnt
+ * are non-NULL the padded-tree index sets are returned too (layout of gigl_sample_khop_host).
+ * This is the entry point a JNI / ctypes binding of the reference's sampler + inferencer pair
+ * calls per batch (KHopSamplerService.getKHopSubgraphForRootNodes + BaseInferencer.infer_batch,
+ * python/gigl/src/inference/v1/lib/base_inferencer.py:23-57).
+ */
+int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots,
+                              int64_t n_roots, const int32_t* fanouts, int32_t n_hops, int32_t base_seed,
+                              int32_t first_call_no, float* out, int32_t* const* nbr, int32_t* const* cnt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,3 +320,46 @@ def sage_model(x, edge_index, layers, f64=False):
         last = li == len(layers) - 1
         h = c_sage_conv(np.asarray(h, np.float32), edge_index, Wl, bl, Wr, relu=not last, f64=f64)
     return h
+
+
+# ----------------------------------------------------------------------------------------
+# batch collation (what `x` / `edge_index` mean for the aggregate)
+# ----------------------------------------------------------------------------------------
+def np_collate(roots, nbr, fanouts):
+    """Union of the B sampled subgraphs as the reference's GraphBuilder / collate fns build it
+    (python/gigl/src/common/graph_builder/abstract_graph_builder.py:49-197, pyg_graph_builder.py:20-69,
+    training/v1/lib/data_loaders/rooted_node_neighborhood_data_loader.py:78-): nodes de-duplicated
+    by id, edges de-duplicated by (src, dst).
+
+    -> (node_ids int64 [n] with the roots first (first occurrence order), edge_index int64 [2, e] in
+    local ids sorted by (dst, src) global id, root_index int64 [B])."""
+    roots = np.asarray(roots, dtype=np.int64)
+    parents = roots
+    keys = []
+    for h, f in enumerate(fanouts):
+        ch = np.asarray(nbr[h], dtype=np.int64)
+        par = np.repeat(parents, int(f))
+        ok = ch >= 0
+        keys.append((par[ok] << 32) | ch[ok])
+        parents = ch
+    keys = np.unique(np.concatenate(keys)) if keys else np.zeros(0, np.int64)
+    dst, src = keys >> 32, keys & 0xFFFFFFFF
+    seen = {}
+    for r in roots.tolist():
+        seen.setdefault(r, len(seen))
+    rest = np.setdiff1d(np.unique(np.concatenate([dst, src])), roots)
+    node_ids = np.concatenate([np.fromiter(seen.keys(), dtype=np.int64, count=len(seen)), rest])
+    lut = {int(v): i for i, v in enumerate(node_ids.tolist())}
+    loc = np.vectorize(lut.__getitem__, otypes=[np.int64])
+    ei = np.stack([loc(src), loc(dst)]) if len(keys) else np.zeros((2, 0), np.int64)
+    root_index = loc(roots) if len(roots) else np.zeros(0, np.int64)
+    return node_ids, ei, root_index
+
+
+def batch_sage_embeddings(x_global, roots, nbr, fanouts, layers, f64=False):
+    """Reference inference on one batch: collate, run GraphSAGE on the WHOLE batch graph, select
+    the root rows (graphsage_template_modeling_spec.py:565-577)."""
+    node_ids, ei, root_index = np_collate(roots, nbr, fanouts)
+    xb = np.ascontiguousarray(np.asarray(x_global)[node_ids], dtype=np.float32)
+    out = sage_model(xb, ei, layers, f64=f64)
+    return out[root_index]

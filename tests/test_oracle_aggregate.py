@@ -88,3 +88,34 @@ def test_gcn_random_c_vs_numpy():
     ref = orc.np_gcn_conv(x, ei, W, b)
     np.testing.assert_allclose(orc.c_gcn_conv(x, ei, W, b, f64=True), ref, rtol=1e-9, atol=1e-12)
     assert np.abs(orc.c_gcn_conv(x, ei, W, b) - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_collate_is_union_of_per_root_subgraphs():
+    O = orc
+    """np_collate == the reference's GraphBuilder semantics: union of the per-root edge sets with
+    nodes / edges de-duplicated; roots come first; embeddings select the root rows."""
+    from helpers import powerlaw_edges
+
+    src, dst = powerlaw_edges(400, 5000, 2)
+    rowptr, col = O.np_build_in_csr(src, dst, 400, True)
+    roots = np.array([5, 9, 5, 100, 399], dtype=np.int32)
+    fan = [4, 3]
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, fan)
+    nodes, ei, ri = O.np_collate(roots, nbr, fan)
+    want = set()
+    for lst in O.tree_to_edges(roots, nbr, fan):
+        want |= set(lst)
+    got = set(zip(nodes[ei[0]].tolist(), nodes[ei[1]].tolist()))
+    assert got == want and ei.shape[1] == len(want)
+    assert len(set(nodes.tolist())) == len(nodes) and np.array_equal(nodes[ri], roots)
+    assert set(nodes.tolist()) == set(roots.tolist()) | {s for s, _ in want} | {d for _, d in want}
+    # embeddings: whole-batch forward then root rows; duplicate roots get identical rows
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((400, 6)).astype(np.float32)
+    layers = [(rng.standard_normal((5, 6)).astype(np.float32), rng.standard_normal(5).astype(np.float32),
+               rng.standard_normal((5, 6)).astype(np.float32)),
+              (rng.standard_normal((3, 5)).astype(np.float32), None, rng.standard_normal((3, 5)).astype(np.float32))]
+    out = O.batch_sage_embeddings(x, roots, nbr, fan, layers, f64=True)
+    assert out.shape == (5, 3) and np.array_equal(out[0], out[2])
+    full = O.sage_model(x[nodes], ei, layers, f64=True)
+    assert np.array_equal(out, full[ri])
