@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py - the hot path of BASELINE.json on N B200s of one node.
+
+A "step" = one batch of B roots through the whole path: k-hop rooted-neighbourhood sampling
+(fanout [15, 10], GiGL's deterministic hash permutation) -> batch collation -> 2-layer GraphSAGE
+over the coalesced batch graph -> root embeddings.  Workload at N = 1 is BASELINE.json configs[1]:
+the ogbn-products-shaped synthetic graph (N = 2,449,029, 61.86M undirected pairs mirrored,
+F = 100 fp32, 100 -> 256 -> 47), whole CSR + features HBM-resident.  At N > 1 every rank holds a
+replica and samples its own contiguous range of roots (weak scaling, no data-path collective).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sampled-subgraphs/sec"
+UNIT = "subgraphs/s"
+WORKLOADS = {
+    # name: nodes, undirected input pairs, F, hidden, out
+    "products-like": dict(nodes=2_449_029, pairs=61_859_140, F=100, H=256, O=47),
+    "toy-1k": dict(nodes=1_000, pairs=5_000, F=16, H=16, O=7),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gigl_b200", choices=["gigl_b200", "reference"])
+    ap.add_argument("--workload", default="products-like", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=65536, help="roots per step per GPU")
+    ap.add_argument("--fanout", default="15,10")
+    ap.add_argument("--cpu-sample-roots", type=int, default=8192, help="roots per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [c.strip() for c in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def root_batches(n_nodes, rank, world, batch, n_steps, start_step=0):
+    """Roots = all nodes in id order, rank r owning [r*N/P, (r+1)*N/P); step s takes the
+    next `batch` ids of the rank's range (wrapping)."""
+    lo, hi = rank * n_nodes // world, (rank + 1) * n_nodes // world
+    span = hi - lo
+    out = []
+    for s in range(start_step, start_step + n_steps):
+        out.append((lo + (np.arange(batch, dtype=np.int64) + s * batch) % span).astype(np.int32))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU pipeline = the reference algorithm restated (oracle/): sampler in C + OpenMP, collation in
+# numpy, aggregate with torch's own CPU kernels.  Timed as the baseline; never the product path.
+# ----------------------------------------------------------------------------------------------
+def cpu_step(O, rowptr, col, x, roots, fan, layers, threads):
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, fan, n_threads=threads)
+    t1 = time.perf_counter()
+    node_ids, ei, root_idx = O.np_collate_fast(roots, nbr, fan)
+    xb = x[node_ids]
+    t2 = time.perf_counter()
+    out = O.torch_sage_forward(xb, ei, layers, n_threads=threads)[root_idx]
+    return out, ei.shape[1], t1, t2
+
+
+def run_cpu_baseline(rowptr, col, x, fan, layers, n_nodes, n_roots, steps, warmup):
+    from oracle import oracle as O
+
+    threads = os.cpu_count() or 1
+    batches = root_batches(n_nodes, 0, 1, n_roots, steps + warmup)
+    for b in batches[:warmup]:
+        cpu_step(O, rowptr, col, x, b, fan, layers, threads)
+    t_s = t_c = t_a = 0.0
+    edges = 0
+    t0 = time.perf_counter()
+    for b in batches[warmup:]:
+        ta = time.perf_counter()
+        _, e, t1, t2 = cpu_step(O, rowptr, col, x, b, fan, layers, threads)
+        tb = time.perf_counter()
+        t_s += t1 - ta
+        t_c += t2 - t1
+        t_a += tb - t2
+        edges += e * len(layers)
+    dt = time.perf_counter() - t0
+    return {"value": n_roots * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} step(s) x {n_roots} roots (ids in order) of the same graph/fanout/model; C+OpenMP sampler, numpy collate, "
+                      f"torch-CPU SAGE on the whole batch graph as the reference does",
+            "seconds": dt, "phase_seconds": {"sample": t_s, "collate": t_c, "aggregate": t_a},
+            "aggregated_edges_per_s": edges / max(t_a, 1e-9)}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ----------------------------------------------------------------------------------------------
+def build_inputs_torch(wl, dev):
+    """Synthetic graph + features + weights (seeded; identical on every box)."""
+    from gigl_b200 import synth
+
+    src, dst = synth.rmat_edges_torch(wl["nodes"], wl["pairs"], dev)
+    x = synth.features_torch(wl["nodes"], wl["F"], dev)
+    layers = synth.sage_weights(np.random.default_rng(synth.GEN_SEED), [wl["F"], wl["H"], wl["O"]])
+    return src, dst, x, layers
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; Spark / PyG are not runnable
+    here) on the host cores, same workload / metric."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    wl = WORKLOADS[args.workload]
+    fan = [int(v) for v in args.fanout.split(",")]
+    dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+    src, dst, x, layers = build_inputs_torch(wl, dev)  # input preparation only (torch ops, not timed)
+    rowptr, col = O.torch_build_in_csr(src, dst, wl["nodes"], False)
+    rowptr, col, x = rowptr.cpu().numpy(), col.cpu().numpy(), x.cpu().numpy()
+    del src, dst
+    n_roots = args.cpu_sample_roots
+    res = run_cpu_baseline(rowptr, col, x, fan, layers, wl["nodes"], n_roots, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, wl, fan, n_roots, "each step is a bounded sample of the workload"),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "phase_seconds": res["phase_seconds"], "aggregated_edges_per_s": res["aggregated_edges_per_s"],
+            "cpu_model": cpu_model()}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl, fan, batch, note):
+    return {"workload": f"BASELINE.json configs[1] shape: {args.workload} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
+                        f"N={wl['nodes']}, {wl['pairs']} undirected pairs de-duplicated+mirrored, F={wl['F']} fp32, "
+                        f"2-hop fanout {fan}, GraphSAGE {wl['F']}->{wl['H']}->{wl['O']} inference on the coalesced batch graph",
+            "roots_per_step_per_gpu": batch, "fanout": fan, "seed": {"generator": 20260101, "sampler_base_seed": 42, "first_call_no": 1},
+            "residency": "whole CSR + feature table resident in HBM on every GPU (replicated); roots sharded by contiguous id range",
+            "l2": "every step reads different roots from a 0.98 GB feature table + 0.5 GB CSR (>> 126 MB L2); no flush needed",
+            "note": note}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gigl_b200 import Batch, Context, Graph, SageModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    fan = [int(v) for v in args.fanout.split(",")]
+    B = min(args.batch, wl["nodes"] // world)
+    K, W = args.steps, args.warmup
+
+    ctx = Context.on_torch_stream(local)
+    src, dst, x, layers = build_inputs_torch(wl, dev)
+    g = Graph.from_edges_dev(ctx, wl["nodes"], src, dst, is_graph_directed=False)
+    del src, dst
+    g.set_features(x)
+    model = SageModel(ctx, layers)
+    batch = Batch(ctx, wl["nodes"])
+    ctx.sync()
+    torch.cuda.empty_cache()
+
+    batches = root_batches(wl["nodes"], rank, world, B, K + W)
+    roots_dev = [torch.from_numpy(b).to(dev) for b in batches]
+    O_dim = wl["O"]
+    out = torch.empty((B, O_dim), dtype=torch.float32, device=dev)
+    nbr, cnt = g.sample_khop(roots_dev[0], fan)
+
+    def step(i):
+        g.sample_khop(roots_dev[i], fan, out=(nbr, cnt))
+        batch.collate(roots_dev[i], fan, nbr, 2)
+        batch.sage_forward(model, x, out=out)
+        return batch.n_edges
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement (value) ---------------------------------------------------
+    for i in range(W):
+        step(i)
+    ctx.set_timing(True)
+    ctx.reset_timing()
+    l0 = ctx.launch_count
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    e1_total = 0
+    for i in range(W, W + K):
+        e1_total += step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    launches = ctx.launch_count - l0
+    timings = ctx.timings()
+    ctx.set_timing(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # edges aggregated per step: layer 1 reduces every unique batch edge, layer 2 those into roots (untimed recount)
+    e2_total = 0
+    n1_total = 0
+    for i in range(W, W + K):
+        g.sample_khop(roots_dev[i], fan, out=(nbr, cnt))
+        sizes = batch.collate(roots_dev[i], fan, nbr, 2)
+        n1_total += sizes[1]
+        _, ei = batch.export()
+        e2_total += int((ei[1] < B).sum().item())
+    agg_edges = e1_total + e2_total
+
+    # ---- roofline of the dominant kernel: the layer-1 gather ------------------------------------
+    peak, peak_src = measured_peaks()
+    F = wl["F"]
+    g_ms, g_n = timings.get("gather_l1", (0.0, 0))
+    # algorithmic bytes per launch: per unique edge one source row + its sorted key, per output row the
+    # segment descriptor + node id + self row read + [mean | self] row written
+    alg_bytes = (e1_total * (4 * F + 8) + n1_total * (8 + 4 + 4 * F + 8 * F)) / max(K, 1)
+    achieved = alg_bytes / (g_ms / max(g_n, 1) * 1e-3) / 1e9 if g_n else None
+    phase_ms = {k: v[0] / K for k, v in timings.items()}
+    roofline = {"kernel": "batch_gather_kernel<32> (layer-1 gather over the coalesced batch graph; + split-row parts/finish launches)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "ms_per_launch": g_ms / max(g_n, 1), "share_of_step": (g_ms / K) / (ms / K)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("gather_l1_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the host entry point (pinned host buffers, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        roots_pin = [torch.from_numpy(b).pin_memory() for b in batches]
+        out_pin = torch.empty((B, O_dim), dtype=torch.float32).pin_memory()
+        nbr_pin, cnt_pin, width = [], [], 1
+        for f in fan:
+            cnt_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
+            width *= f
+            nbr_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
+        s_out = ([t.numpy() for t in nbr_pin], [t.numpy() for t in cnt_pin])
+        for i in range(W):
+            g.infer_khop_sage_host(batch, model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(), samples_out=s_out)
+        barrier()
+        ev0.record()
+        for i in range(W, W + K):
+            g.infer_khop_sage_host(batch, model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(), samples_out=s_out)
+        ev1.record()
+        barrier()
+        ms_e = ev0.elapsed_time(ev1)  # device time on the launching stream (the host call itself is synchronous)
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        d2h = B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin)
+        e2e = {"value": world * B * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e / K, "api": "gigl_infer_khop_sage_host (roots in pinned host memory -> padded-tree index sets + "
+                                              "root embeddings back in pinned host memory)"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rowptr_t, col_t = g.csr_tensors()
+        cpu = run_cpu_baseline(rowptr_t.cpu().numpy(), col_t.cpu().numpy(), x.cpu().numpy(), fan, layers, wl["nodes"],
+                               args.cpu_sample_roots, 3, 1)
+        cpu["cpu_model"] = cpu_model()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, wl, fan, B, "value: roots already on the device; e2e: host buffers"),
+                "aggregated_edges_per_sec": world * agg_edges / (ms * 1e-3),
+                "aggregate_only_edges_per_sec": agg_edges / K / max(1e-9, sum(phase_ms.get(k, 0.0) for k in
+                                                                              ("gather_l1", "gather_deep", "gemm_l1", "gemm_deep")) * 1e-3),
+                "sample_only_subgraphs_per_sec": B / max(1e-9, phase_ms.get("sample", 0.0) * 1e-3),
+                "phase_ms_per_step": phase_ms, "unique_edges_per_step": e1_total / K, "layer1_rows_per_step": n1_total / K,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,11 @@ SIGNATURES = {
     "gigl_last_error": (cp, [vp]),
     "gigl_ctx_launch_count": (i64, [vp]),
     "gigl_ctx_stream": (vp, [vp]),
+    "gigl_ctx_set_timing": (C.c_int, [vp, i32]),
+    "gigl_ctx_reset_timing": (C.c_int, [vp]),
+    "gigl_ctx_get_timing": (C.c_int, [vp, i32, C.POINTER(C.c_double), C.POINTER(i64)]),
+    "gigl_timing_num_tags": (i32, []),
+    "gigl_timing_tag_name": (cp, [i32]),
     "gigl_graph_create_host": (C.c_int, [vp, i64, i64, vp, vp, pvp]),
     "gigl_graph_wrap_dev": (C.c_int, [vp, i64, i64, vp, vp, pvp]),
     "gigl_graph_from_edges_host": (C.c_int, [vp, i64, i64, vp, vp, i32, i32, pvp]),
@@ -43,6 +48,7 @@ SIGNATURES = {
     "gigl_graph_num_nodes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "gigl_graph_device_ptrs": (C.c_int, [vp, pvp, pvp]),
     "gigl_graph_destroy": (None, [vp]),
+    "gigl_graph_set_hash_index": (C.c_int, [vp, i32]),
     "gigl_sample_khop_host": (C.c_int, [vp, vp, i64, vp, i32, i32, i32, pvp, pvp]),
     "gigl_sample_khop_dev": (C.c_int, [vp, vp, i64, vp, i32, i32, i32, pvp, pvp]),
     "gigl_sample_positives_host": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp]),

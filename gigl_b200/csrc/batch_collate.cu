@@ -146,6 +146,72 @@ __global__ void fill_i32_kernel(int64_t n, int32_t v, int32_t* __restrict__ p) {
 // ---- 4. gather: [mean of unique in-neighbours | self] rows -----------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+constexpr int kSplitThreshold = 256;  // rows longer than this are split into parts ...
+constexpr int kPartEdges = 128;       // ... of this many sorted keys, one warp each
+constexpr int kGatherUnroll = 8;      // independent 16-byte loads in flight per lane
+
+// Sum of the unique sources of keys[e_beg, e_end) (a slice of the row that starts at row_beg) for
+// feature columns [c, c+4) of this lane; every lane group g walks its own subset, the caller
+// reduces across groups.  n_uniq counts the slice's unique keys (warp-uniform).
+template <int LPR>
+__device__ __forceinline__ void gather_range(int row_beg, int e_beg, int e_end, int c, bool active,
+                                             const uint64_t* __restrict__ keys, const float* __restrict__ xsrc,
+                                             int64_t ldx, const int32_t* __restrict__ lid, int lane, int g,
+                                             float4& acc, int& n_uniq) {
+    constexpr int G = 32 / LPR;
+    for (int base = e_beg; base < e_end; base += 32) {
+        const int cnt = min(32, e_end - base);
+        int32_t my = -1;
+        if (lane < cnt) {
+            const uint64_t k = __ldg(keys + base + lane);
+            const bool dup = (base + lane > row_beg) && (__ldg(keys + base + lane - 1) == k);
+            if (!dup) {
+                const int32_t s = (int32_t)(uint32_t)k;
+                my = lid ? __ldg(lid + s) : s;
+            }
+        }
+        n_uniq += __popc(__ballot_sync(0xffffffffu, my >= 0));
+        for (int t = 0; t < cnt; t += kGatherUnroll * G) {
+            float4 val[kGatherUnroll];
+#pragma unroll
+            for (int u = 0; u < kGatherUnroll; ++u) {
+                const int j = t + u * G + g;
+                const int32_t s = __shfl_sync(0xffffffffu, my, j & 31);
+                val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < cnt && s >= 0 && active) val[u] = ldg4(xsrc + (int64_t)s * ldx + c);
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherUnroll; ++u) {
+                acc.x += val[u].x;
+                acc.y += val[u].y;
+                acc.z += val[u].z;
+                acc.w += val[u].w;
+            }
+        }
+    }
+}
+
+template <int LPR>
+__device__ __forceinline__ void reduce_groups(float4& acc) {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+}
+
+// Work lists of the split path: hctr[0] = parts claimed, hctr[1] = heavy rows claimed.
+struct HeavyLists {
+    int32_t* hctr;
+    int2* items;       // [part_cap]  (row, part index)
+    int4* rows;        // [part_cap]  (row, first item, n_parts, -)
+    float* partial;    // [part_cap, F]
+    int32_t* pcnt;     // [part_cap]
+    int32_t part_cap;
+};
+
 // LPR lanes cover one 4*LPR-float chunk of a feature row; G = 32/LPR sources are in flight per step.
 // xsrc rows are indexed by global vertex id when lid == nullptr (layer 1 reads the graph-wide
 // feature table directly) or by lid[src] (deeper layers read the previous layer's rows).
@@ -156,8 +222,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
                                                            const uint64_t* __restrict__ keys,
                                                            const float* __restrict__ xsrc, int64_t ldx,
                                                            const int32_t* __restrict__ lid, float* __restrict__ A,
-                                                           int64_t ldA) {
-    constexpr int G = 32 / LPR;
+                                                           int64_t ldA, const HeavyLists hl) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, g = lane / LPR;
     int64_t n_rows = *n_rows_dev;
@@ -167,54 +232,94 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
         const int32_t v = __ldg(list + row);
         const int2 seg = __ldg(segmap + v);
         const int64_t self = lid ? row : (int64_t)v;
+        const int len = seg.y - seg.x;
+        if (len > kSplitThreshold && hl.items != nullptr) {
+            const int n_parts = (len + kPartEdges - 1) / kPartEdges;
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(hl.hctr, n_parts);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot + n_parts <= hl.part_cap) {
+                if (lane == 0) hl.rows[atomicAdd(hl.hctr + 1, 1)] = make_int4((int)row, slot, n_parts, 0);
+                for (int p = lane; p < n_parts; p += 32) hl.items[slot + p] = make_int2((int)row, p);
+                continue;
+            }
+            // lists full (cannot happen with the host-side sizing): do the long row here
+        }
         for (int c0 = 0; c0 < F; c0 += LPR * 4) {
             const int c = c0 + sub * 4;
             const bool active = c < F;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             int n_uniq = 0;
-            for (int base = seg.x; base < seg.y; base += 32) {
-                const int cnt = min(32, seg.y - base);
-                int32_t my = -1;
-                if (lane < cnt) {
-                    const uint64_t k = __ldg(keys + base + lane);
-                    const bool dup = (base + lane > seg.x) && (__ldg(keys + base + lane - 1) == k);
-                    if (!dup) {
-                        const int32_t s = (int32_t)(uint32_t)k;
-                        my = lid ? __ldg(lid + s) : s;
-                    }
-                }
-                n_uniq += __popc(__ballot_sync(0xffffffffu, my >= 0));
-                for (int t = 0; t < cnt; t += 4 * G) {
-                    float4 val[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = t + u * G + g;
-                        const int32_t s = __shfl_sync(0xffffffffu, my, j & 31);
-                        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j < cnt && s >= 0 && active) val[u] = ldg4(xsrc + (int64_t)s * ldx + c);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        acc.x += val[u].x;
-                        acc.y += val[u].y;
-                        acc.z += val[u].z;
-                        acc.w += val[u].w;
-                    }
-                }
-            }
-#pragma unroll
-            for (int off = LPR; off < 32; off <<= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
-                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
-            }
+            gather_range<LPR>(seg.x, seg.x, seg.y, c, active, keys, xsrc, ldx, lid, lane, g, acc, n_uniq);
+            reduce_groups<LPR>(acc);
             if (g == 0 && active) {
                 const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
                 *reinterpret_cast<float4*>(A + row * ldA + c) =
                     make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
                 *reinterpret_cast<float4*>(A + row * ldA + F + c) = ldg4(xsrc + self * ldx + c);
             }
+        }
+    }
+}
+
+// One warp per (row, part): partial sums of kPartEdges sorted keys.
+template <int LPR>
+__global__ void __launch_bounds__(256) batch_gather_parts_kernel(int F, const int32_t* __restrict__ list,
+                                                                 const int2* __restrict__ segmap,
+                                                                 const uint64_t* __restrict__ keys,
+                                                                 const float* __restrict__ xsrc, int64_t ldx,
+                                                                 const int32_t* __restrict__ lid, const HeavyLists hl) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR, g = lane / LPR;
+    int n_items = hl.hctr[0];
+    if (n_items > hl.part_cap) n_items = hl.part_cap;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n_items; it += warps) {
+        const int2 item = hl.items[it];
+        const int2 seg = __ldg(segmap + __ldg(list + item.x));
+        const int e_beg = seg.x + item.y * kPartEdges;
+        const int e_end = min(seg.y, e_beg + kPartEdges);
+        for (int c0 = 0; c0 < F; c0 += LPR * 4) {
+            const int c = c0 + sub * 4;
+            const bool active = c < F;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int n_uniq = 0;
+            gather_range<LPR>(seg.x, e_beg, e_end, c, active, keys, xsrc, ldx, lid, lane, g, acc, n_uniq);
+            reduce_groups<LPR>(acc);
+            if (g == 0 && active) *reinterpret_cast<float4*>(hl.partial + (int64_t)it * F + c) = acc;
+            if (lane == 0 && c0 == 0) hl.pcnt[it] = n_uniq;
+        }
+    }
+}
+
+// One warp per split row: parts summed in part order (deterministic), then [mean | self].
+__global__ void __launch_bounds__(256) batch_gather_finish_kernel(int F, const float* __restrict__ xsrc, int64_t ldx,
+                                                                  const int32_t* __restrict__ list,
+                                                                  const int32_t* __restrict__ lid,
+                                                                  float* __restrict__ A, int64_t ldA,
+                                                                  const HeavyLists hl) {
+    const int lane = threadIdx.x & 31;
+    const int n_heavy = hl.hctr[1];
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int hr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); hr < n_heavy; hr += warps) {
+        const int4 r = hl.rows[hr];
+        const int64_t row = r.x;
+        const int64_t self = lid ? row : (int64_t)__ldg(list + row);
+        int n_uniq = 0;
+        for (int p = 0; p < r.z; ++p) n_uniq += hl.pcnt[r.y + p];
+        const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
+        for (int c = lane * 4; c < F; c += 128) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = 0; p < r.z; ++p) {
+                const float4 t = *reinterpret_cast<const float4*>(hl.partial + (int64_t)(r.y + p) * F + c);
+                acc.x += t.x;
+                acc.y += t.y;
+                acc.z += t.z;
+                acc.w += t.w;
+            }
+            *reinterpret_cast<float4*>(A + row * ldA + c) =
+                make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+            *reinterpret_cast<float4*>(A + row * ldA + F + c) = ldg4(xsrc + self * ldx + c);
         }
     }
 }
@@ -350,7 +455,9 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CHECK(ctx, n_layers >= 1 && n_layers <= GIGL_MAX_HOPS, "n_layers must be in [1, 8]");
     GIGL_CHECK(ctx, n_roots >= 0 && n_roots <= 0x3fffffffLL, "bad n_roots");
     GIGL_CHECK(ctx, fanouts && nbr_dev && (roots_dev || n_roots == 0), "null pointer");
+    int tc = gigl_timer_begin(ctx, GIGL_T_COLLATE_MAPS);
     int rc = batch_clear(b);
+    gigl_timer_end(ctx, tc);
     if (rc != GIGL_OK) return rc;
     int64_t n_slots = 0, width = n_roots;
     for (int h = 0; h < n_hops; ++h) {
@@ -389,6 +496,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     // 1. keys
     int64_t off = 0;
     width = n_roots;
+    int th = gigl_timer_begin(ctx, GIGL_T_COLLATE_KEYS);
     for (int h = 0; h < n_hops; ++h) {
         const int32_t* parents = (h == 0) ? roots_dev : nbr_dev[h - 1];
         width *= fanouts[h];
@@ -398,11 +506,17 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
         }
         off += width;
     }
+    gigl_timer_end(ctx, th);
     // 2. sort + row bounds
     GIGL_CUDA(ctx, cudaMemsetAsync(b->d_ctr, 0, sizeof(int32_t) * kCtrInts, st));
     if (n_slots > 0) {
+        th = gigl_timer_begin(ctx, GIGL_T_COLLATE_SORT);
         GIGL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_a, keys_b, (int64_t)n_slots, 0, end_bit, st));
         ctx->launches++;
+        gigl_timer_end(ctx, th);
+    }
+    th = gigl_timer_begin(ctx, GIGL_T_COLLATE_MAPS);
+    if (n_slots > 0) {
         seg_bounds_kernel<<<grid1d(ctx, n_slots, 256), 256, 0, st>>>(n_slots, keys_b, b->dead, b->segmap, b->d_ctr);
         GIGL_LAUNCHED(ctx);
     }
@@ -420,6 +534,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
         level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
         GIGL_LAUNCHED(ctx);
     }
+    gigl_timer_end(ctx, th);
     b->n_levels = n_layers;
     b->n_levels_done = n_layers;
     b->n_hops = n_hops;
@@ -541,19 +656,53 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         const int32_t* lidmap = (l == 1) ? nullptr : b->lid;
         const int wpb = 8;
         const unsigned grid = (unsigned)ceil_div64(rows, wpb);
+        int tg = gigl_timer_begin(ctx, l == 1 ? GIGL_T_GATHER_L1 : GIGL_T_GATHER_DEEP);
         const bool vec = (Fi % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0) && (ldx % 4 == 0);
-        if (!vec)
+        if (!vec) {
             batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
-        else if (Fi <= 16)
-            batch_gather_kernel<4><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
-        else if (Fi <= 32)
-            batch_gather_kernel<8><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
-        else if (Fi <= 64)
-            batch_gather_kernel<16><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
-        else
-            batch_gather_kernel<32><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
-        GIGL_LAUNCHED(ctx);
+            GIGL_LAUNCHED(ctx);
+        } else {
+            // split-row work lists (sized from the collate's valid-key count; see kSplitThreshold)
+            const int64_t part_cap = b->n_valid_host / kPartEdges + b->n_valid_host / kSplitThreshold + 16;
+            const size_t o_items = 256;
+            const size_t o_rows = o_items + ((sizeof(int2) * (size_t)part_cap + 255) & ~(size_t)255);
+            const size_t o_pcnt = o_rows + ((sizeof(int4) * (size_t)part_cap + 255) & ~(size_t)255);
+            const size_t o_part = o_pcnt + ((sizeof(int32_t) * (size_t)part_cap + 255) & ~(size_t)255);
+            const size_t hbytes = o_part + sizeof(float) * (size_t)part_cap * Fi;
+            void* ph = nullptr;
+            if ((rc = gigl_scratch(ctx, GIGL_SLOT_WORK, hbytes, &ph)) != GIGL_OK) return rc;
+            HeavyLists hl;
+            hl.hctr = (int32_t*)ph;
+            hl.items = (int2*)((char*)ph + o_items);
+            hl.rows = (int4*)((char*)ph + o_rows);
+            hl.pcnt = (int32_t*)((char*)ph + o_pcnt);
+            hl.partial = (float*)((char*)ph + o_part);
+            hl.part_cap = (int32_t)part_cap;
+            GIGL_CUDA(ctx, cudaMemsetAsync(hl.hctr, 0, 2 * sizeof(int32_t), st));
+            const int hgrid = ctx->sm_count * 4;
+#define GIGL_GATHER(LPR)                                                                                                  \
+    do {                                                                                                                  \
+        batch_gather_kernel<LPR><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx,    \
+                                                            lidmap, A, lda, hl);                                          \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+        batch_gather_parts_kernel<LPR><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, hl);     \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+    } while (0)
+            if (Fi <= 16)
+                GIGL_GATHER(4);
+            else if (Fi <= 32)
+                GIGL_GATHER(8);
+            else if (Fi <= 64)
+                GIGL_GATHER(16);
+            else
+                GIGL_GATHER(32);
+#undef GIGL_GATHER
+            batch_gather_finish_kernel<<<hgrid, 256, 0, st>>>(Fi, xin, ldx, b->list, lidmap, A, lda, hl);
+            GIGL_LAUNCHED(ctx);
+        }
+        gigl_timer_end(ctx, tg);
         float* C = (l == n_layers) ? out_dev : hbuf[l & 1];
+        gigl_timed tgemm(ctx, l == 1 ? GIGL_T_GEMM_L1 : GIGL_T_GEMM_DEEP);
         rc = linear_dev_rows_launch(ctx, rows_dev, rows, Fo, 2 * Fi, A, lda, m->wcat[l - 1], lda, m->bias[l - 1], C, Fo,
                                     l < n_layers ? 1 : 0);
         if (rc != GIGL_OK) return rc;

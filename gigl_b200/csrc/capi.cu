@@ -50,6 +50,38 @@ int gigl_scratch(gigl_ctx* ctx, int slot, size_t bytes, void** out) {
     return GIGL_OK;
 }
 
+// ---- phase timing ---------------------------------------------------------------------------
+static void timer_flush(gigl_ctx* ctx) {
+    if (ctx->t_used == 0) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < ctx->t_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->t_pool[i].a, ctx->t_pool[i].b) == cudaSuccess) {
+            ctx->t_ms[ctx->t_pool[i].tag] += ms;
+            ctx->t_n[ctx->t_pool[i].tag] += 1;
+        }
+    }
+    ctx->t_used = 0;
+    cudaGetLastError();
+}
+
+int gigl_timer_begin(gigl_ctx* ctx, int tag) {
+    if (!ctx->timing) return -1;
+    if (ctx->t_used == ctx->t_cap) timer_flush(ctx);
+    const int h = ctx->t_used++;
+    ctx->t_pool[h].tag = tag;
+    cudaEventRecord(ctx->t_pool[h].a, ctx->stream);
+    return h;
+}
+
+void gigl_timer_end(gigl_ctx* ctx, int handle) {
+    if (handle < 0) return;
+    cudaEventRecord(ctx->t_pool[handle].b, ctx->stream);
+}
+
+static const char* kTimerNames[GIGL_T_COUNT] = {"sample", "collate_keys", "collate_sort", "collate_maps", "gather_l1",
+                                                "gather_deep", "gemm_l1", "gemm_deep", "gather_full", "gemm_full"};
+
 static int ctx_check_device_error(gigl_ctx* ctx) {
     GIGL_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -160,10 +192,58 @@ void gigl_ctx_destroy(gigl_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int s = 0; s < GIGL_SCRATCH_SLOTS; ++s)
         if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
+    if (ctx->t_pool) {
+        for (int i = 0; i < ctx->t_cap; ++i) {
+            cudaEventDestroy(ctx->t_pool[i].a);
+            cudaEventDestroy(ctx->t_pool[i].b);
+        }
+        delete[] ctx->t_pool;
+    }
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int gigl_ctx_set_timing(gigl_ctx* ctx, int32_t enabled) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (enabled && !ctx->t_pool) {
+        const int cap = 1024;
+        ctx->t_pool = new (std::nothrow) gigl_timer_pair[cap];
+        if (!ctx->t_pool) return gigl_fail(ctx, GIGL_E_NOMEM, "out of host memory");
+        for (int i = 0; i < cap; ++i) {
+            GIGL_CUDA(ctx, cudaEventCreate(&ctx->t_pool[i].a));
+            GIGL_CUDA(ctx, cudaEventCreate(&ctx->t_pool[i].b));
+            ctx->t_cap = i + 1;
+        }
+    }
+    if (!enabled) timer_flush(ctx);
+    ctx->timing = enabled != 0;
+    return GIGL_OK;
+}
+
+int gigl_ctx_reset_timing(gigl_ctx* ctx) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    timer_flush(ctx);
+    for (int i = 0; i < GIGL_T_COUNT; ++i) {
+        ctx->t_ms[i] = 0.0;
+        ctx->t_n[i] = 0;
+    }
+    return GIGL_OK;
+}
+
+int32_t gigl_timing_num_tags(void) { return GIGL_T_COUNT; }
+
+const char* gigl_timing_tag_name(int32_t tag) { return (tag >= 0 && tag < GIGL_T_COUNT) ? kTimerNames[tag] : ""; }
+
+int gigl_ctx_get_timing(gigl_ctx* ctx, int32_t tag, double* total_ms, int64_t* count) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, tag >= 0 && tag < GIGL_T_COUNT, "bad timing tag");
+    timer_flush(ctx);
+    if (total_ms) *total_ms = ctx->t_ms[tag];
+    if (count) *count = ctx->t_n[tag];
+    return GIGL_OK;
 }
 
 int gigl_ctx_sync(gigl_ctx* ctx) {
@@ -313,6 +393,12 @@ void gigl_graph_destroy(gigl_graph* g) {
         cudaFree((void*)g->rowptr);
         cudaFree((void*)g->col);
     }
+    if (g->hx_keys || g->hx_offs) {
+        cudaSetDevice(g->ctx->device);
+        cudaStreamSynchronize(g->ctx->stream);
+        if (g->hx_keys) cudaFree(g->hx_keys);
+        if (g->hx_offs) cudaFree(g->hx_offs);
+    }
     if (g->x_owned && g->x) {
         cudaSetDevice(g->ctx->device);
         cudaStreamSynchronize(g->ctx->stream);
@@ -322,6 +408,12 @@ void gigl_graph_destroy(gigl_graph* g) {
 }
 
 // ---- sampling ------------------------------------------------------------------------------
+
+int gigl_graph_set_hash_index(gigl_graph* g, int32_t enabled) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    g->hx_enabled = enabled != 0;
+    return GIGL_OK;
+}
 
 int gigl_sample_khop_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
                          int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,

@@ -20,6 +20,26 @@ enum {
     GIGL_SCRATCH_SLOTS = 8
 };
 
+// timing tags: device time per phase, measured with CUDA events on the ctx stream when enabled
+enum {
+    GIGL_T_SAMPLE = 0,     // k-hop sampling kernels (all hops)
+    GIGL_T_COLLATE_KEYS,   // tree slots -> edge keys
+    GIGL_T_COLLATE_SORT,   // radix sort of the keys
+    GIGL_T_COLLATE_MAPS,   // row bounds + level / local-id assignment (+ cleanup of the previous batch)
+    GIGL_T_GATHER_L1,      // layer-1 gather (reads the graph-wide feature table): main + split-row launches
+    GIGL_T_GATHER_DEEP,    // gathers of layers >= 2
+    GIGL_T_GEMM_L1,        // layer-1 projection
+    GIGL_T_GEMM_DEEP,      // projections of layers >= 2
+    GIGL_T_GATHER_FULL,    // full-graph gather (gigl_sage_conv_dev / gigl_gather_mean_dev)
+    GIGL_T_GEMM_FULL,
+    GIGL_T_COUNT
+};
+
+struct gigl_timer_pair {
+    cudaEvent_t a, b;
+    int tag;
+};
+
 struct gigl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -33,6 +53,22 @@ struct gigl_ctx {
     // growable device scratch slots (worklists, partial buffers, staging); never shrink
     void* scratch[GIGL_SCRATCH_SLOTS] = {};
     size_t scratch_bytes[GIGL_SCRATCH_SLOTS] = {};
+    // phase timing (off by default)
+    bool timing = false;
+    gigl_timer_pair* t_pool = nullptr;
+    int t_cap = 0, t_used = 0;
+    double t_ms[GIGL_T_COUNT] = {};
+    int64_t t_n[GIGL_T_COUNT] = {};
+};
+
+// Begin / end of a timed phase on the ctx stream (no-ops unless timing is enabled).
+int gigl_timer_begin(gigl_ctx* ctx, int tag);
+void gigl_timer_end(gigl_ctx* ctx, int handle);
+struct gigl_timed {  // RAII helper
+    gigl_ctx* ctx;
+    int h;
+    gigl_timed(gigl_ctx* c, int tag) : ctx(c), h(gigl_timer_begin(c, tag)) {}
+    ~gigl_timed() { gigl_timer_end(ctx, h); }
 };
 
 struct gigl_graph {
@@ -45,6 +81,13 @@ struct gigl_graph {
     const float* x = nullptr;  // device feature table [n_nodes, F] (optional)
     int32_t F = 0;
     bool x_owned = false;
+    // hash-window index of the sampler (khop_sample.cu), built lazily on the first sampling call
+    uint64_t* hx_keys = nullptr;
+    uint16_t* hx_offs = nullptr;
+    uint64_t hx_limit = 0;
+    int32_t hx_l_log2 = 0;
+    int32_t hx_cap = 0;
+    bool hx_enabled = true;
 };
 
 int gigl_fail(gigl_ctx* ctx, int code, const std::string& msg);

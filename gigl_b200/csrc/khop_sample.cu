@@ -40,6 +40,13 @@ struct HopArgs {
     int32_t* heavy_list;  // worklist of parent slots deferred to the heavy pass
     int32_t* heavy_count;
     int32_t heavy_cap;
+    // hash-window index (see build_hash_index_kernel): per block of 2^l_log2 consecutive hash inputs
+    // the `cap` smallest keys, ascending, with their offsets inside the block; nullptr = disabled
+    const uint64_t* hx_keys;
+    const uint16_t* hx_offs;
+    uint64_t hx_limit;  // inputs [0, hx_limit) are covered
+    int32_t hx_l_log2;
+    int32_t hx_cap;
 };
 
 // Sorted (ascending) best-`f` list held by one warp: position p lives in lane p%32, register p/32.
@@ -48,6 +55,7 @@ struct WarpTopK {
     uint64_t key[KPL];
     int32_t idx[KPL];
     uint64_t kth;  // key at position f-1 (kKeyInf until f entries were inserted)
+    bool empty;    // nothing inserted yet (warp-uniform)
 
     __device__ __forceinline__ void init() {
 #pragma unroll
@@ -56,10 +64,12 @@ struct WarpTopK {
             idx[k] = 0;
         }
         kth = kKeyInf;
+        empty = true;
     }
 
     // Insert (ck, ci), warp-uniform arguments, ck < kth.
     __device__ __forceinline__ void insert(uint64_t ck, int32_t ci, int f, int lane) {
+        empty = false;
         int pos = 0;
 #pragma unroll
         for (int k = 0; k < KPL; ++k) pos += __popc(__ballot_sync(0xffffffffu, key[k] < ck));
@@ -98,6 +108,31 @@ struct WarpTopK {
         kth = v;
     }
 
+    // First 32 candidates of an EMPTY list (KPL == 1 fast path): a 32-lane bitonic sort of
+    // (key, idx) instead of 32 serial insertions.  k = kKeyInf marks an absent candidate.
+    __device__ __forceinline__ void seed_sorted32(uint64_t k, int32_t i, int f, int lane) {
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, k, stride);
+                const int32_t oi = __shfl_xor_sync(0xffffffffu, i, stride);
+                const bool up = ((lane & size) == 0);           // ascending block?
+                const bool lower = ((lane & stride) == 0);      // I hold the lower position of the pair
+                const bool take_min = (up == lower);
+                const bool other_less = ok < k;
+                if (take_min == other_less) {
+                    k = ok;
+                    i = oi;
+                }
+            }
+        }
+        key[0] = k;
+        idx[0] = i;
+        empty = false;
+        refresh_kth(f);
+    }
+
     // Scan window positions [i_begin, i_end] (1-based, inclusive) with stride `stride` chunks of 32.
     __device__ __forceinline__ void scan(int64_t i_first_chunk, int64_t size, int64_t chunk_stride, uint32_t base,
                                          int f, int lane) {
@@ -105,6 +140,10 @@ struct WarpTopK {
             const int64_t i = c0 + lane + 1;  // 1-based index as F.sequence(1, size)
             uint64_t k = kKeyInf;
             if (i <= size) k = ordered_key((int32_t)(base + (uint32_t)i));
+            if (KPL == 1 && empty) {  // warp-uniform
+                seed_sorted32(k, (int32_t)i, f, lane);
+                continue;
+            }
             uint32_t cand = __ballot_sync(0xffffffffu, k < kth);
             while (cand) {
                 const int src = __ffs(cand) - 1;
@@ -176,6 +215,97 @@ __device__ __forceinline__ void write_result(const HopArgs& a, int64_t pslot, co
     if (lane == 0) a.out_cnt[pslot] = n_out;
 }
 
+// ---- hash-window index ----------------------------------------------------------------------
+// The permutation key of window position i is H(base + i): a row of `size` entries asks for the f
+// smallest values of the FIXED sequence H(x) over the window x in [base+1, base+size].  For long
+// rows (hubs) almost all of that hashing is shared between windows, so the sequence is indexed
+// once per graph: for every aligned block of L = 2^l_log2 inputs the `cap` smallest keys (sorted)
+// and their offsets.  A window then costs < 2L hashes (its unaligned head and tail) plus one
+// 8-byte read per covered block (the block minimum prunes nearly all of them), instead of `size`
+// hashes.  Bit-exact by construction: the same keys, the same (key, idx) order.
+template <int KPL>
+__global__ void __launch_bounds__(256) build_hash_index_kernel(int64_t n_blocks, int l_log2, int cap,
+                                                               uint64_t* __restrict__ keys,
+                                                               uint16_t* __restrict__ offs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
+        WarpTopK<KPL> best;
+        best.init();
+        const uint32_t base = (uint32_t)((b << l_log2) - 1);  // x = base + i, i = 1..L
+        best.scan(0, (int64_t)1 << l_log2, 32, base, cap, lane);
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            const int p = k * 32 + lane;
+            if (p < cap) {
+                keys[b * cap + p] = best.key[k];
+                offs[b * cap + p] = (uint16_t)(best.idx[k] - 1);
+            }
+        }
+    }
+}
+
+// Top-f of one row's window, through the index when it covers the window.
+template <int KPL>
+__device__ __forceinline__ void select_row(const HopArgs& a, WarpTopK<KPL>& best, int64_t size, uint32_t base, int f,
+                                           int lane) {
+    if (a.hx_keys != nullptr) {
+        const uint64_t lo = (uint64_t)base + 1, hi = (uint64_t)base + (uint64_t)size;
+        const int lg = a.hx_l_log2;
+        if (hi < a.hx_limit && (size >> lg) != 0) {
+            const uint64_t b0 = (lo + ((1ULL << lg) - 1)) >> lg, b1 = (hi + 1) >> lg;  // full blocks [b0, b1)
+            if (b0 < b1) {
+                const int64_t head_end = (int64_t)((b0 << lg) - lo);             // i in [1, head_end]
+                const int64_t tail_begin = (int64_t)((b1 << lg) - (uint64_t)base);  // first tail i
+                best.scan(0, head_end, 32, base, f, lane);
+                best.scan(tail_begin - 1, size, 32, base, f, lane);
+                const int cap = a.hx_cap;
+                for (uint64_t bb = b0; bb < b1; bb += 32) {
+                    const uint64_t myb = bb + lane;
+                    uint64_t head = kKeyInf;
+                    if (myb < b1) head = __ldg(a.hx_keys + myb * cap);
+                    uint32_t cand = __ballot_sync(0xffffffffu, head < best.kth);
+                    while (cand) {
+                        const int src = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        if (__shfl_sync(0xffffffffu, head, src) >= best.kth) continue;
+                        const uint64_t blk = bb + src;
+#pragma unroll
+                        for (int k = 0; k < KPL; ++k) {
+                            const int p = k * 32 + lane;
+                            uint64_t ek = kKeyInf;
+                            uint32_t eo = 0;
+                            if (p < cap) {
+                                ek = __ldg(a.hx_keys + blk * cap + p);
+                                eo = __ldg(a.hx_offs + blk * cap + p);
+                            }
+                            uint32_t c2 = __ballot_sync(0xffffffffu, ek < best.kth);
+                            while (c2) {
+                                const int s2 = __ffs(c2) - 1;
+                                c2 &= c2 - 1;
+                                const uint64_t ck = __shfl_sync(0xffffffffu, ek, s2);
+                                const uint32_t co = __shfl_sync(0xffffffffu, eo, s2);
+                                if (ck >= best.kth) break;  // entries are ascending
+                                const uint32_t x = (uint32_t)(blk << lg) + co;
+                                best.insert(ck, (int32_t)(x - base), f, lane);
+                            }
+                        }
+                    }
+                }
+                return;
+            }
+        }
+    }
+    best.scan(0, size, 32, base, f, lane);
+}
+
+__device__ __forceinline__ bool row_uses_index(const HopArgs& a, int64_t size, uint32_t base) {
+    if (a.hx_keys == nullptr) return false;
+    const uint64_t lo = (uint64_t)base + 1, hi = (uint64_t)base + (uint64_t)size;
+    const int lg = a.hx_l_log2;
+    return hi < a.hx_limit && ((lo + ((1ULL << lg) - 1)) >> lg) < ((hi + 1) >> lg);
+}
+
 template <int KPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_hop_kernel(const HopArgs a) {
     const int lane = threadIdx.x & 31;
@@ -206,7 +336,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_hop_kernel(const Hop
         if (lane == 0) a.out_cnt[pslot] = 0;
         return;
     }
-    if (size > kHeavyThreshold && a.heavy_list != nullptr) {
+    const uint32_t base = ssum + (uint32_t)a.cur_seed;
+    if (size > kHeavyThreshold && a.heavy_list != nullptr && !row_uses_index(a, size, base)) {
         int slot = 0;
         if (lane == 0) slot = atomicAdd(a.heavy_count, 1);
         slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -218,7 +349,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_hop_kernel(const Hop
     }
     WarpTopK<KPL> best;
     best.init();
-    best.scan(0, size, 32, ssum + (uint32_t)a.cur_seed, f, lane);
+    select_row<KPL>(a, best, size, base, f, lane);
     write_result<KPL>(a, pslot, best, size, row_begin, mult, lane);
 }
 
@@ -263,6 +394,47 @@ __global__ void __launch_bounds__(kHeavyWarps * 32) khop_heavy_kernel(const HopA
     }
 }
 
+static int ensure_hash_index(gigl_graph* g, int fmax, int n_hops) {
+    gigl_ctx* ctx = g->ctx;
+    if (!g->hx_enabled) return GIGL_OK;
+    const int cap = fmax <= 16 ? 16 : fmax <= 32 ? 32 : fmax <= 64 ? 64 : 128;
+    int lg = 0;
+    while ((1 << lg) < 8 * cap) ++lg;
+    uint64_t want = (uint64_t)n_hops * (uint64_t)g->n_nodes + (1ULL << 21);
+    if (want > (1ULL << 31)) want = 1ULL << 31;
+    const int64_t n_blocks = (int64_t)(want >> lg);
+    const uint64_t limit = (uint64_t)n_blocks << lg;
+    if (g->hx_keys && g->hx_cap == cap && g->hx_limit >= limit) return GIGL_OK;
+    GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (g->hx_keys) cudaFree(g->hx_keys);
+    if (g->hx_offs) cudaFree(g->hx_offs);
+    g->hx_keys = nullptr;
+    g->hx_offs = nullptr;
+    g->hx_limit = 0;
+    if (n_blocks == 0) return GIGL_OK;
+    cudaError_t e = cudaMalloc(&g->hx_keys, sizeof(uint64_t) * (size_t)n_blocks * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&g->hx_offs, sizeof(uint16_t) * (size_t)n_blocks * cap);
+    if (e != cudaSuccess) {  // the index is an accelerator, not a requirement: run without it
+        if (g->hx_keys) cudaFree(g->hx_keys);
+        g->hx_keys = nullptr;
+        g->hx_offs = nullptr;
+        cudaGetLastError();
+        return GIGL_OK;
+    }
+    const int grid = ctx->sm_count * 8;
+    if (cap <= 32)
+        build_hash_index_kernel<1><<<grid, 256, 0, ctx->stream>>>(n_blocks, lg, cap, g->hx_keys, g->hx_offs);
+    else if (cap == 64)
+        build_hash_index_kernel<2><<<grid, 256, 0, ctx->stream>>>(n_blocks, lg, cap, g->hx_keys, g->hx_offs);
+    else
+        build_hash_index_kernel<4><<<grid, 256, 0, ctx->stream>>>(n_blocks, lg, cap, g->hx_keys, g->hx_offs);
+    GIGL_LAUNCHED(ctx);
+    g->hx_cap = cap;
+    g->hx_l_log2 = lg;
+    g->hx_limit = limit;
+    return GIGL_OK;
+}
+
 template <int KPL>
 static int launch_hop(gigl_ctx* ctx, const HopArgs& a) {
     const int64_t blocks = ceil_div64(a.n_parent, kWarpsPerBlock);
@@ -304,7 +476,16 @@ int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
     int32_t* heavy_count = (int32_t*)scratch;
     int32_t* heavy_list = heavy_count + 64;
 
+    int fmax = 0;
+    for (int h = 0; h < n_hops; ++h) fmax = fanouts[h] > fmax ? fanouts[h] : fmax;
+    if ((rc = ensure_hash_index(g, fmax, n_hops)) != GIGL_OK) return rc;
+
     HopArgs a{};
+    a.hx_keys = g->hx_enabled ? g->hx_keys : nullptr;
+    a.hx_offs = g->hx_offs;
+    a.hx_limit = g->hx_limit;
+    a.hx_l_log2 = g->hx_l_log2;
+    a.hx_cap = g->hx_cap;
     a.rowptr = g->rowptr;
     a.col = g->col;
     a.n_nodes = g->n_nodes;
@@ -314,6 +495,7 @@ int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
     a.heavy_count = heavy_count;
     a.heavy_cap = heavy_cap;
     int64_t n_parent = n_roots;
+    gigl_timed timed(ctx, GIGL_T_SAMPLE);
     for (int h = 1; h <= n_hops; ++h) {
         const int32_t f = fanouts[h - 1];
         a.fanouts[h - 1] = f;

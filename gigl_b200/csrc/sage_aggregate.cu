@@ -347,6 +347,7 @@ int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, i
 
 int gather_mean_launch(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t* rowptr, const int32_t* col,
                        const float* x, float* agg) {
+    gigl_timed t(ctx, GIGL_T_GATHER_FULL);
     return gigl::launch_gather<0>(ctx, n_rows, F, rowptr, col, x, agg, nullptr, nullptr, 0);
 }
 
@@ -360,8 +361,12 @@ int sage_conv_launch(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, in
     int rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * (size_t)n_rows_out * (size_t)F, &scratch);
     if (rc != GIGL_OK) return rc;
     float* agg = (float*)scratch;
-    rc = gigl::launch_gather<0>(ctx, n_rows_out, F, rowptr, col, x, agg, nullptr, nullptr, 0);
+    {
+        gigl_timed t(ctx, GIGL_T_GATHER_FULL);
+        rc = gigl::launch_gather<0>(ctx, n_rows_out, F, rowptr, col, x, agg, nullptr, nullptr, 0);
+    }
     if (rc != GIGL_OK) return rc;
+    gigl_timed t(ctx, GIGL_T_GEMM_FULL);
     return gigl::launch_linear2(ctx, n_rows_out, O, F, F, agg, x, Wl, Wr, bl, out, relu);
 }
 

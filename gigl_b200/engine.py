@@ -66,6 +66,23 @@ class Context:
     def stream(self) -> int:
         return int(self._L.gigl_ctx_stream(self.handle) or 0)
 
+    # ---- phase timing ----------------------------------------------------------------------
+    def set_timing(self, enabled: bool) -> None:
+        check(self._L.gigl_ctx_set_timing(self.handle, int(enabled)), self.handle)
+
+    def reset_timing(self) -> None:
+        check(self._L.gigl_ctx_reset_timing(self.handle), self.handle)
+
+    def timings(self) -> dict:
+        """{tag: (total device ms, launches of that phase)} accumulated since the last reset (synchronises)."""
+        out = {}
+        for t in range(self._L.gigl_timing_num_tags()):
+            ms, n = C.c_double(), C.c_int64()
+            check(self._L.gigl_ctx_get_timing(self.handle, t, C.byref(ms), C.byref(n)), self.handle)
+            if n.value:
+                out[self._L.gigl_timing_tag_name(t).decode()] = (ms.value, n.value)
+        return out
+
     def close(self) -> None:
         if self.handle:
             self._L.gigl_ctx_destroy(self.handle)
@@ -212,6 +229,10 @@ class Graph:
         return rowptr.cpu().numpy(), col.cpu().numpy()
 
     # -- sampling
+    def set_hash_index(self, enabled: bool) -> None:
+        """Switch the sampler's hash-window index on/off (results are identical either way)."""
+        check(self.ctx._L.gigl_graph_set_hash_index(self.handle, int(enabled)), self.ctx.handle)
+
     def sample_khop_host(self, roots, fanouts: Sequence[int], base_seed: int = 42, first_call_no: int = 1
                          ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
         """Padded-tree k-hop sample (layout: include/gigl_b200.h) through host buffers."""

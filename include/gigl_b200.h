@@ -77,6 +77,18 @@ const char* gigl_last_error(gigl_ctx* ctx);
 int64_t gigl_ctx_launch_count(gigl_ctx* ctx);
 /* The cudaStream_t the ctx enqueues on (for event timing on the launching stream). */
 void* gigl_ctx_stream(gigl_ctx* ctx);
+/*
+ * Phase timing: when enabled, the library brackets its kernel groups with CUDA events on the ctx
+ * stream and accumulates device milliseconds per tag ("sample", "collate_sort", "gather_l1",
+ * "gemm_l1", ...; see gigl_timing_tag_name).  This is the hook the reference's coarse wall timers
+ * (gigl/common/metrics/decorators.py:68-111) and TorchProfiler wrapper occupy; bench.py reads its
+ * per-kernel roofline from it.  gigl_ctx_get_timing synchronises the stream.
+ */
+int gigl_ctx_set_timing(gigl_ctx* ctx, int32_t enabled);
+int gigl_ctx_reset_timing(gigl_ctx* ctx);
+int gigl_ctx_get_timing(gigl_ctx* ctx, int32_t tag, double* total_ms, int64_t* count);
+int32_t gigl_timing_num_tags(void);
+const char* gigl_timing_tag_name(int32_t tag);
 
 /* ---- graph: CSR by destination, resident in HBM ---------------------------------------- */
 
@@ -130,6 +142,13 @@ void gigl_graph_destroy(gigl_graph* g);
  *
  * fanouts[h] in [1, GIGL_MAX_FANOUT], n_hops in [1, GIGL_MAX_HOPS].
  */
+/*
+ * The sampler keeps a per-graph index of the hash sequence (block-wise smallest keys) so that a
+ * hub row costs O(L + size / L) instead of O(size) hash evaluations; results are bit-identical
+ * with and without it.  enabled = 0 switches it off (tests compare both paths); default on.
+ */
+int gigl_graph_set_hash_index(gigl_graph* g, int32_t enabled);
+
 int gigl_sample_khop_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, const int32_t* fanouts,
                           int32_t n_hops, int32_t base_seed, int32_t first_call_no,
                           int32_t* const* nbr /* [n_hops] host */, int32_t* const* cnt /* [n_hops] host */);

@@ -363,3 +363,76 @@ def batch_sage_embeddings(x_global, roots, nbr, fanouts, layers, f64=False):
     xb = np.ascontiguousarray(np.asarray(x_global)[node_ids], dtype=np.float32)
     out = sage_model(xb, ei, layers, f64=f64)
     return out[root_index]
+
+
+def np_collate_fast(roots, nbr, fanouts):
+    """Vectorised np_collate (same result up to the order of the non-root nodes, which here is
+    ascending id); used by the timed CPU baseline where the python-dict version would dominate."""
+    roots = np.asarray(roots, dtype=np.int64)
+    parents = roots
+    keys = []
+    for h, f in enumerate(fanouts):
+        ch = np.asarray(nbr[h], dtype=np.int64)
+        par = np.repeat(parents, int(f))
+        ok = ch >= 0
+        keys.append((par[ok] << 32) | ch[ok])
+        parents = ch
+    keys = np.unique(np.concatenate(keys)) if keys else np.zeros(0, np.int64)
+    dst, src = keys >> 32, keys & 0xFFFFFFFF
+    uroots, first = np.unique(roots, return_index=True)
+    uroots = uroots[np.argsort(first, kind="stable")]  # first-occurrence order
+    rest = np.setdiff1d(np.unique(np.concatenate([dst, src])), uroots, assume_unique=True)
+    node_ids = np.concatenate([uroots, rest])
+    order = np.argsort(node_ids, kind="stable")
+    sorted_ids = node_ids[order]
+
+    def loc(v):
+        return order[np.searchsorted(sorted_ids, v)]
+
+    ei = np.stack([loc(src), loc(dst)]) if len(keys) else np.zeros((2, 0), np.int64)
+    return node_ids, ei, loc(roots) if len(roots) else np.zeros(0, np.int64)
+
+
+def torch_sage_forward(x, edge_index, layers, n_threads=None):
+    """The reference's aggregate on the CPU with torch itself: PyG 2.5.3 SAGEConv(mean) restated as
+    index_add_ + F.linear, GraphSAGE/BasicGNN layer loop with ReLU between
+    layers (homogeneous.py:107-153, graphsage_template_modeling_spec.py:143-148).  This is the
+    timed CPU baseline of the aggregate half: torch's own multi-threaded
+    CPU kernels, all host threads."""
+    import torch
+    import torch.nn.functional as F
+
+    if n_threads:
+        torch.set_num_threads(int(n_threads))
+    with torch.no_grad():
+        h = torch.as_tensor(x, dtype=torch.float32)
+        ei = torch.as_tensor(edge_index, dtype=torch.int64)
+        src, dst = ei[0], ei[1]
+        n = h.shape[0]
+        cnt = torch.zeros(n, dtype=torch.float32).index_add_(0, dst, torch.ones(dst.numel(), dtype=torch.float32))
+        inv = 1.0 / cnt.clamp(min=1.0)
+        for li, (Wl, bl, Wr) in enumerate(layers):
+            agg = torch.zeros_like(h).index_add_(0, dst, h.index_select(0, src)) * inv[:, None]
+            out = F.linear(agg, torch.as_tensor(Wl), None if bl is None else torch.as_tensor(bl)) + F.linear(h, torch.as_tensor(Wr))
+            h = out.relu_() if li < len(layers) - 1 else out
+        return h.numpy()
+
+
+def torch_build_in_csr(src, dst, n_nodes: int, is_graph_directed: bool):
+    """np_build_in_csr with torch tensor ops (any device): used to prepare BASELINE-size inputs for
+    the CPU reference arm without going through the product library."""
+    import torch
+
+    src = src.to(torch.int64)
+    dst = dst.to(torch.int64)
+    if not is_graph_directed:
+        lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+        pairs = torch.unique((lo << 32) | hi)
+        lo, hi = pairs >> 32, pairs & 0xFFFFFFFF
+        both = torch.unique(torch.cat([(hi << 32) | lo, (lo << 32) | hi]))  # key = dst << 32 | src, UNION DISTINCT
+    else:
+        both, _ = torch.sort((dst << 32) | src)
+    d, s = both >> 32, both & 0xFFFFFFFF
+    rowptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=src.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(d, minlength=n_nodes), 0)
+    return rowptr, s.to(torch.int32)

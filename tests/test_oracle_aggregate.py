@@ -119,3 +119,33 @@ def test_collate_is_union_of_per_root_subgraphs():
     assert out.shape == (5, 3) and np.array_equal(out[0], out[2])
     full = O.sage_model(x[nodes], ei, layers, f64=True)
     assert np.array_equal(out, full[ri])
+
+
+def test_fast_collate_torch_forward_and_torch_csr_agree_with_the_plain_oracle():
+    from helpers import powerlaw_edges
+
+    O = orc
+    n = 600
+    src, dst = powerlaw_edges(n, 9000, 7)
+    for directed in (True, False):
+        rowptr, col = O.np_build_in_csr(src, dst, n, directed)
+        tr, tc = O.torch_build_in_csr(torch.from_numpy(src), torch.from_numpy(dst), n, directed)
+        assert np.array_equal(tr.numpy(), rowptr) and np.array_equal(tc.numpy(), col)
+    roots = np.array([3, 50, 3, 77, 599, 12], dtype=np.int32)
+    fan = [5, 3]
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, fan)
+    n1, e1, r1 = O.np_collate(roots, nbr, fan)
+    n2, e2, r2 = O.np_collate_fast(roots, nbr, fan)
+    assert np.array_equal(n1[r1], n2[r2]) and set(n1.tolist()) == set(n2.tolist())
+    k1 = np.sort((n1[e1[1]] << 32) | n1[e1[0]])
+    k2 = np.sort((n2[e2[1]] << 32) | n2[e2[0]])
+    assert np.array_equal(k1, k2)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, 10)).astype(np.float32)
+    layers = [(rng.standard_normal((8, 10)).astype(np.float32), rng.standard_normal(8).astype(np.float32),
+               rng.standard_normal((8, 10)).astype(np.float32)),
+              (rng.standard_normal((4, 8)).astype(np.float32), rng.standard_normal(4).astype(np.float32),
+               rng.standard_normal((4, 8)).astype(np.float32))]
+    a = O.sage_model(x[n2], e2, layers, f64=True)
+    b = O.torch_sage_forward(x[n2], e2, layers)
+    assert np.abs(a - b).max() / max(1.0, np.abs(a).max()) < 1e-5
