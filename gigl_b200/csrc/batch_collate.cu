@@ -191,6 +191,15 @@ __device__ __forceinline__ void gather_range(int row_beg, int e_beg, int e_end, 
     }
 }
 
+// The projection runs as 3xTF32 on the tensor cores (gemm_tcgen05.cu): its A operand is stored
+// already split, hi = the value with the 13 low mantissa bits cleared (a TF32 number), lo = v - hi.
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ void store_split4(float* __restrict__ hi, float* __restrict__ lo, int64_t off, float4 v) {
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
 template <int LPR>
 __device__ __forceinline__ void reduce_groups(float4& acc) {
 #pragma unroll
@@ -221,8 +230,8 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
                                                            const int2* __restrict__ segmap,
                                                            const uint64_t* __restrict__ keys,
                                                            const float* __restrict__ xsrc, int64_t ldx,
-                                                           const int32_t* __restrict__ lid, float* __restrict__ A,
-                                                           int64_t ldA, const HeavyLists hl) {
+                                                           const int32_t* __restrict__ lid, float* __restrict__ A_hi,
+                                                           float* __restrict__ A_lo, int64_t ldA, const HeavyLists hl) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, g = lane / LPR;
     int64_t n_rows = *n_rows_dev;
@@ -254,9 +263,8 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
             reduce_groups<LPR>(acc);
             if (g == 0 && active) {
                 const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
-                *reinterpret_cast<float4*>(A + row * ldA + c) =
-                    make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
-                *reinterpret_cast<float4*>(A + row * ldA + F + c) = ldg4(xsrc + self * ldx + c);
+                store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
+                store_split4(A_hi, A_lo, row * ldA + F + c, ldg4(xsrc + self * ldx + c));
             }
         }
     }
@@ -296,8 +304,8 @@ __global__ void __launch_bounds__(256) batch_gather_parts_kernel(int F, const in
 __global__ void __launch_bounds__(256) batch_gather_finish_kernel(int F, const float* __restrict__ xsrc, int64_t ldx,
                                                                   const int32_t* __restrict__ list,
                                                                   const int32_t* __restrict__ lid,
-                                                                  float* __restrict__ A, int64_t ldA,
-                                                                  const HeavyLists hl) {
+                                                                  float* __restrict__ A_hi, float* __restrict__ A_lo,
+                                                                  int64_t ldA, const HeavyLists hl) {
     const int lane = threadIdx.x & 31;
     const int n_heavy = hl.hctr[1];
     const int warps = gridDim.x * (blockDim.x >> 5);
@@ -317,9 +325,8 @@ __global__ void __launch_bounds__(256) batch_gather_finish_kernel(int F, const f
                 acc.z += t.z;
                 acc.w += t.w;
             }
-            *reinterpret_cast<float4*>(A + row * ldA + c) =
-                make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
-            *reinterpret_cast<float4*>(A + row * ldA + F + c) = ldg4(xsrc + self * ldx + c);
+            store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
+            store_split4(A_hi, A_lo, row * ldA + F + c, ldg4(xsrc + self * ldx + c));
         }
     }
 }
@@ -332,7 +339,8 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
                                                                   const uint64_t* __restrict__ keys,
                                                                   const float* __restrict__ xsrc, int64_t ldx,
                                                                   const int32_t* __restrict__ lid,
-                                                                  float* __restrict__ A, int64_t ldA) {
+                                                                  float* __restrict__ A_hi, float* __restrict__ A_lo,
+                                                                  int64_t ldA) {
     const int lane = threadIdx.x & 31;
     int64_t n_rows = *n_rows_dev;
     if (n_rows > row_cap) n_rows = row_cap;
@@ -352,8 +360,12 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
                 acc += __ldg(xsrc + s * ldx + c);
                 ++n_uniq;
             }
-            A[row * ldA + c] = acc * (1.0f / (float)(n_uniq > 1 ? n_uniq : 1));
-            A[row * ldA + F + c] = __ldg(xsrc + self * ldx + c);
+            const float m = acc * (1.0f / (float)(n_uniq > 1 ? n_uniq : 1));
+            const float sv = __ldg(xsrc + self * ldx + c);
+            A_hi[row * ldA + c] = tf32_hi(m);
+            A_lo[row * ldA + c] = m - tf32_hi(m);
+            A_hi[row * ldA + F + c] = tf32_hi(sv);
+            A_lo[row * ldA + F + c] = sv - tf32_hi(sv);
         }
     }
 }
@@ -549,10 +561,6 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     return GIGL_OK;
 }
 
-// Implemented in sage_aggregate.cu: C[M, N] = A[M, K] (ld = lda) @ W[N, K]^T (ld = ldw) + bias, optional relu;
-// M is read on the device from *m_dev (clamped to m_cap).
-int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, int N, int K, const float* A, int64_t lda,
-                           const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);
 
 // ---- model: PyG GraphSAGE weights resident on the device -------------------------------------
 struct gigl_sage_model {
@@ -561,6 +569,8 @@ struct gigl_sage_model {
     int dims[GIGL_MAX_HOPS + 1] = {};
     int64_t ldw[GIGL_MAX_HOPS] = {};      // leading dimension of Wcat[l] (>= 2 * dims[l], multiple of 4)
     float* wcat[GIGL_MAX_HOPS] = {};      // [dims[l+1], ldw]: row o = [lin_l.weight[o, :] | lin_r.weight[o, :] | 0]
+    float* w_hi[GIGL_MAX_HOPS] = {};      // TF32 split of wcat (3xTF32 projection, gemm_tcgen05.cu)
+    float* w_lo[GIGL_MAX_HOPS] = {};
     float* bias[GIGL_MAX_HOPS] = {};      // lin_l.bias or nullptr
     float* blob = nullptr;
 };
@@ -572,7 +582,7 @@ int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
     for (int l = 0; l < n_layers; ++l) {
         GIGL_CHECK(ctx, dims[l] >= 1 && dims[l + 1] >= 1 && Wl[l] && Wr[l], "bad layer");
         const size_t ld = ((size_t)2 * dims[l] + 3) & ~(size_t)3;
-        total += (size_t)dims[l + 1] * ld + (((size_t)dims[l + 1] + 3) & ~(size_t)3);
+        total += 3 * (size_t)dims[l + 1] * ld + (((size_t)dims[l + 1] + 3) & ~(size_t)3);
     }
     gigl_sage_model* m = new (std::nothrow) gigl_sage_model();
     if (!m) return gigl_fail(ctx, GIGL_E_NOMEM, "out of host memory");
@@ -589,7 +599,9 @@ int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
         m->dims[l + 1] = Fo;
         m->ldw[l] = (int64_t)ld;
         m->wcat[l] = m->blob + off;
-        off += (size_t)Fo * ld;
+        m->w_hi[l] = m->blob + off + (size_t)Fo * ld;
+        m->w_lo[l] = m->blob + off + 2 * (size_t)Fo * ld;
+        off += 3 * (size_t)Fo * ld;
         e = cudaMemcpy2DAsync(m->wcat[l], sizeof(float) * ld, Wl[l], sizeof(float) * Fi, sizeof(float) * Fi, Fo, kind, ctx->stream);
         if (e == cudaSuccess)
             e = cudaMemcpy2DAsync(m->wcat[l] + Fi, sizeof(float) * ld, Wr[l], sizeof(float) * Fi, sizeof(float) * Fi, Fo, kind, ctx->stream);
@@ -599,6 +611,9 @@ int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
         }
         off += ((size_t)Fo + 3) & ~(size_t)3;
     }
+    for (int l = 0; l < n_layers && e == cudaSuccess; ++l)
+        if (split_tf32_launch(ctx, dims[l + 1], (int)m->ldw[l], m->wcat[l], m->ldw[l], m->w_hi[l], m->w_lo[l], m->ldw[l]) != GIGL_OK)
+            e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // host weight buffers may be freed by the caller
     if (e != cudaSuccess) {
         if (m->blob) cudaFree(m->blob);
@@ -629,8 +644,8 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
     gigl_ctx* ctx = b->ctx;
     const int n_layers = m->n_layers;
     GIGL_CHECK(ctx, b->dirty && b->n_levels == n_layers, "collate the batch with n_layers == the model's layer count first");
-    GIGL_CHECK(ctx, x_dev && out_dev && ldx0 >= m->dims[0], "bad feature table");
     if (b->n_roots == 0) return GIGL_OK;
+    GIGL_CHECK(ctx, x_dev && out_dev && ldx0 >= m->dims[0], "bad feature table");
     cudaStream_t st = ctx->stream;
     size_t a_elems = 0, h_elems = 0;
     for (int l = 1; l <= n_layers; ++l) {
@@ -642,9 +657,11 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
     h_elems = (h_elems + 3) & ~(size_t)3;
     void *pA = nullptr, *pH = nullptr;
     int rc;
-    if ((rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * (a_elems + 4), &pA)) != GIGL_OK) return rc;
+    a_elems = (a_elems + 63) & ~(size_t)63;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * 2 * a_elems, &pA)) != GIGL_OK) return rc;
     if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO3, sizeof(float) * (2 * h_elems + 8), &pH)) != GIGL_OK) return rc;
-    float* A = (float*)pA;
+    float* A_hi = (float*)pA;
+    float* A_lo = A_hi + a_elems;
     float* hbuf[2] = {(float*)pH, (float*)pH + h_elems};
     const float* xin = x_dev;
     int64_t ldx = ldx0;
@@ -659,7 +676,7 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         int tg = gigl_timer_begin(ctx, l == 1 ? GIGL_T_GATHER_L1 : GIGL_T_GATHER_DEEP);
         const bool vec = (Fi % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0) && (ldx % 4 == 0);
         if (!vec) {
-            batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A, lda);
+            batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A_hi, A_lo, lda);
             GIGL_LAUNCHED(ctx);
         } else {
             // split-row work lists (sized from the collate's valid-key count; see kSplitThreshold)
@@ -683,7 +700,7 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
 #define GIGL_GATHER(LPR)                                                                                                  \
     do {                                                                                                                  \
         batch_gather_kernel<LPR><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx,    \
-                                                            lidmap, A, lda, hl);                                          \
+                                                            lidmap, A_hi, A_lo, lda, hl);                                 \
         GIGL_LAUNCHED(ctx);                                                                                               \
         batch_gather_parts_kernel<LPR><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, hl);     \
         GIGL_LAUNCHED(ctx);                                                                                               \
@@ -697,14 +714,14 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
             else
                 GIGL_GATHER(32);
 #undef GIGL_GATHER
-            batch_gather_finish_kernel<<<hgrid, 256, 0, st>>>(Fi, xin, ldx, b->list, lidmap, A, lda, hl);
+            batch_gather_finish_kernel<<<hgrid, 256, 0, st>>>(Fi, xin, ldx, b->list, lidmap, A_hi, A_lo, lda, hl);
             GIGL_LAUNCHED(ctx);
         }
         gigl_timer_end(ctx, tg);
         float* C = (l == n_layers) ? out_dev : hbuf[l & 1];
         gigl_timed tgemm(ctx, l == 1 ? GIGL_T_GEMM_L1 : GIGL_T_GEMM_DEEP);
-        rc = linear_dev_rows_launch(ctx, rows_dev, rows, Fo, 2 * Fi, A, lda, m->wcat[l - 1], lda, m->bias[l - 1], C, Fo,
-                                    l < n_layers ? 1 : 0);
+        rc = linear_tc_launch(ctx, rows, Fo, 2 * Fi, A_hi, A_lo, lda, m->w_hi[l - 1], m->w_lo[l - 1], lda, m->bias[l - 1], C, Fo,
+                              l < n_layers ? 1 : 0);
         if (rc != GIGL_OK) return rc;
         xin = C;
         ldx = Fo;

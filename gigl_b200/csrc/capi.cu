@@ -595,6 +595,28 @@ int gigl_graph_features_dev(const gigl_graph* g, const float** x_dev, int32_t* F
     return GIGL_OK;
 }
 
+int gigl_linear_dev(gigl_ctx* ctx, int64_t M, int32_t N, int32_t K, const float* A_dev, int64_t lda, const float* W_dev,
+                    int64_t ldw, const float* bias_dev, float* C_dev, int64_t ldc, int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, M >= 0 && N >= 1 && K >= 1 && lda >= K && ldw >= K && ldc >= N, "bad sizes");
+    if (M == 0) return GIGL_OK;
+    GIGL_CHECK(ctx, A_dev && W_dev && C_dev, "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // split both operands into TF32 hi / lo halves (pitch padded to 4 floats), then 3xTF32 on tcgen05
+    const int64_t ldp = ((int64_t)K + 3) & ~(int64_t)3;
+    const size_t a_el = ((size_t)M * ldp + 63) & ~(size_t)63, w_el = ((size_t)N * ldp + 63) & ~(size_t)63;
+    void* buf = nullptr;
+    int rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * 2 * (a_el + w_el), &buf);
+    if (rc != GIGL_OK) return rc;
+    float* a_hi = (float*)buf;
+    float* a_lo = a_hi + a_el;
+    float* w_hi = a_lo + a_el;
+    float* w_lo = w_hi + w_el;
+    if ((rc = split_tf32_launch(ctx, M, K, A_dev, lda, a_hi, a_lo, ldp)) != GIGL_OK) return rc;
+    if ((rc = split_tf32_launch(ctx, N, K, W_dev, ldw, w_hi, w_lo, ldp)) != GIGL_OK) return rc;
+    return linear_tc_launch(ctx, M, N, K, a_hi, a_lo, ldp, w_hi, w_lo, ldp, bias_dev, C_dev, ldc, relu);
+}
+
 int gigl_sage_model_create_host(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl,
                                 const float* const* bl, const float* const* Wr, gigl_sage_model** out) {
     if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");

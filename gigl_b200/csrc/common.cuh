@@ -148,3 +148,11 @@ int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
                       const float* const* Wr, int weights_on_device, gigl_sage_model** out);
 void sage_model_destroy(gigl_sage_model* m);
 int sage_model_dims(const gigl_sage_model* m, int32_t* n_layers, int32_t* dims);
+
+// gemm_tcgen05.cu: C[M, N] = (A_hi + A_lo)[M, K] @ (W_hi + W_lo)[N, K]^T + bias as 3xTF32 on tcgen05 (TMA-fed, TMEM accumulators)
+int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, const float* A_lo, int64_t lda,
+                     const float* W_hi, const float* W_lo, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);
+int split_tf32_launch(gigl_ctx* ctx, int64_t rows, int cols, const float* x, int64_t ldx, float* hi, float* lo, int64_t ldo);
+// sage_aggregate.cu: fp32 FFMA projection with explicit leading dimensions (M optionally read on the device)
+int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, int N, int K, const float* A, int64_t lda,
+                           const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);

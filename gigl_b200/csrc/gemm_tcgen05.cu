@@ -1,0 +1,376 @@
+// gemm_tcgen05.cu - the layer's weight projection on the 5th-gen tensor cores (sm_100a).
+//
+//   C[M, N] = A[M, K] @ W[N, K]^T + bias  (optional ReLU),  fp32 in / fp32 out,
+//
+// i.e. F.linear of torch_geometric SAGEConv's lin_l / lin_r (fused as [mean | self] @ [Wl | Wr]^T;
+// reference call site python/gigl/src/common/models/pyg/homogeneous.py:192-201) and GCNConv's lin.
+//
+// Precision: the parity bound is 1e-5 relative on fp32 embeddings, which single-pass TF32
+// (10-bit mantissa) cannot meet, so every operand is split into two TF32 terms
+// (x = hi + lo, hi = x with the low 13 mantissa bits cleared, lo = x - hi, exact in fp32) and
+// three tensor-core products are accumulated in fp32 in TMEM:  hi*hi + lo*hi + hi*lo  (3xTF32,
+// relative error ~2^-21).  The split of A is done by the producer of A (the gather kernel writes
+// both halves), the split of W once at model-creation time, so this kernel is a pure
+// TMA -> tcgen05.mma -> TMEM -> epilogue pipeline:
+//
+//   warp 0      : TMA producer - four 128-byte-swizzled K-major tiles per stage (A_hi, A_lo, W_hi, W_lo)
+//   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N<=256, K=8)
+//   warps 2..5  : epilogue - tcgen05.ld the accumulator (each warp its own 32-lane quarter),
+//                 bias + ReLU, fp32 rows to global memory
+//
+// Persistent over the M tiles (grid = min(tiles, SMs)), accumulators double-buffered in TMEM so
+// the epilogue of tile t overlaps the MMAs of tile t+1, smem ring of 2..4 stages.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace gigl {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;              // 32 fp32 = 128 bytes = one swizzle span
+constexpr int kUmmaK = 8;                // tf32
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 27;  // bounded waits: a protocol bug traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle: 8-row x 128-byte atoms, 1024 bytes apart (SBO); LBO unused; version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct GemmParams {
+    int64_t M;
+    int N, K;
+    int n_pad;        // UMMA N of one tile (multiple of 16, <= 256)
+    int n_tiles_n;    // tiles along N
+    int stages;
+    uint32_t tmem_cols;
+    const float* bias;
+    float* C;
+    int64_t ldc;
+    int relu;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                     const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment of every tile is required by the 128-byte swizzle
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = kBlockM * kBlockK * 4;          // 16 KB
+    const uint32_t w_bytes = (uint32_t)p.n_pad * kBlockK * 4;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    // bars: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2]
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * p.stages;
+    const uint32_t bar_tfull = bar_empty + 8 * p.stages;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+    const uint32_t smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles_m = (p.M + kBlockM - 1) / kBlockM;
+    const int64_t n_tiles = n_tiles_m * p.n_tiles_n;
+    const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (int)((tile / p.n_tiles_n) * kBlockM);
+                const int n0 = (int)((tile % p.n_tiles_n) * p.n_pad);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    mbar_expect_tx(full, stage_bytes);
+                    tma_load_2d(sa, &tm_a_hi, full, kb * kBlockK, m0);
+                    tma_load_2d(sa + a_bytes, &tm_a_lo, full, kb * kBlockK, m0);
+                    tma_load_2d(sa + 2 * a_bytes, &tm_w_hi, full, kb * kBlockK, n0);
+                    tma_load_2d(sa + 2 * a_bytes + w_bytes, &tm_w_lo, full, kb * kBlockK, n0);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = n_pad, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1;
+                mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.n_pad;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint64_t d_ah = umma_desc_sw128(sa), d_al = umma_desc_sw128(sa + a_bytes);
+                    const uint64_t d_wh = umma_desc_sw128(sa + 2 * a_bytes), d_wl = umma_desc_sw128(sa + 2 * a_bytes + w_bytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // +32 bytes inside the swizzle span
+                        umma_tf32(tmem_d, d_al + adv, d_wh + adv, idesc, (kb | k) != 0);
+                        umma_tf32(tmem_d, d_ah + adv, d_wl + adv, idesc, 1);
+                        umma_tf32(tmem_d, d_ah + adv, d_wh + adv, idesc, 1);
+                    }
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1;
+            const int64_t m0 = (tile / p.n_tiles_n) * kBlockM;
+            const int n0 = (int)((tile % p.n_tiles_n) * p.n_pad);
+            mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+            tc_fence_after();
+            const int64_t row = m0 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.n_pad;
+            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (row < p.M) {
+                    float* crow = p.C + row * p.ldc + n0 + c0;
+                    const int ncol = p.N - (n0 + c0);  // valid columns from here
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float f = __uint_as_float(v[j]);
+                        if (p.bias != nullptr && j < ncol) f += __ldg(p.bias + n0 + c0 + j);
+                        if (p.relu) f = fmaxf(f, 0.f);
+                        o[j] = f;
+                    }
+                    if (vec_ok && ncol >= 16 && ((n0 + c0) % 4 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(crow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < ncol) crow[j] = o[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exactly a TF32 value), lo = x - hi.
+__global__ void split_tf32_kernel(int64_t rows, int cols, const float* __restrict__ x, int64_t ldx,
+                                  float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
+    const int64_t total = rows * cols;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / cols;
+        const int c = (int)(i - r * cols);
+        const float v = x[r * ldx + c];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[r * ldo + c] = h;
+        lo[r * ldo + c] = v - h;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row pitch ld (floats): box = [box_rows, 32 floats], 128-byte swizzle, OOB -> 0
+static int make_map(gigl_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    bool reused) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return gigl_fail(ctx, GIGL_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, reused ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return gigl_fail(ctx, GIGL_E_CUDA, "cuTensorMapEncodeTiled failed (pointer / pitch must be 16-byte aligned)");
+    return GIGL_OK;
+}
+
+}  // namespace gigl
+
+// A_hi / A_lo: [M, K] with pitch lda; W_hi / W_lo: [N, K] with pitch ldw; all 16-byte aligned, pitches % 4 == 0.
+int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, const float* A_lo, int64_t lda,
+                     const float* W_hi, const float* W_lo, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu) {
+    using namespace gigl;
+    if (M == 0 || N == 0) return GIGL_OK;
+    GIGL_CHECK(ctx, K >= 1 && lda % 4 == 0 && ldw % 4 == 0, "tensor-core projection needs pitches that are multiples of 4 floats");
+    GIGL_CHECK(ctx, M <= 0x7fffffffLL, "too many rows");
+    GemmParams p{};
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    const int n_cap = 256;
+    p.n_tiles_n = (N + n_cap - 1) / n_cap;
+    const int n_per = (N + p.n_tiles_n - 1) / p.n_tiles_n;
+    p.n_pad = (n_per + 15) & ~15;
+    const size_t stage_bytes = 2 * (size_t)kBlockM * kBlockK * 4 + 2 * (size_t)p.n_pad * kBlockK * 4;
+    int stages = (int)((220 * 1024 - 1024 - 256) / stage_bytes);
+    if (stages > 4) stages = 4;
+    GIGL_CHECK(ctx, stages >= 2, "tile does not fit in shared memory");
+    p.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * p.n_pad)) cols <<= 1;
+    p.tmem_cols = cols;
+    p.bias = bias;
+    p.C = C;
+    p.ldc = ldc;
+    p.relu = relu;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    int rc;
+    if ((rc = make_map(ctx, &ta_hi, A_hi, M, K, lda, kBlockM, false)) != GIGL_OK) return rc;
+    if ((rc = make_map(ctx, &ta_lo, A_lo, M, K, lda, kBlockM, false)) != GIGL_OK) return rc;
+    if ((rc = make_map(ctx, &tw_hi, W_hi, N, K, ldw, p.n_pad, true)) != GIGL_OK) return rc;
+    if ((rc = make_map(ctx, &tw_lo, W_lo, N, K, ldw, p.n_pad, true)) != GIGL_OK) return rc;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GIGL_CUDA(ctx, cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int64_t n_tiles = ((M + kBlockM - 1) / kBlockM) * p.n_tiles_n;
+    const int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
+    linear_tf32x3_kernel<<<grid, kGemmThreads, smem, ctx->stream>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+    GIGL_LAUNCHED(ctx);
+    return GIGL_OK;
+}
+
+int split_tf32_launch(gigl_ctx* ctx, int64_t rows, int cols, const float* x, int64_t ldx, float* hi, float* lo, int64_t ldo) {
+    if (rows == 0 || cols == 0) return GIGL_OK;
+    int64_t g = ceil_div64(rows * cols, 256);
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    gigl::split_tf32_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, ctx->stream>>>(rows, cols, x, ldx, hi, lo, ldo);
+    GIGL_LAUNCHED(ctx);
+    return GIGL_OK;
+}

@@ -145,6 +145,19 @@ class Context:
                                          _dp(out), int(relu)), self.handle)
         return out
 
+    def linear(self, A, W, bias=None, relu: bool = False, out=None):
+        """F.linear(A, W, bias) on the tensor cores (3xTF32): A [M, K], W [N, K] fp32 CUDA tensors."""
+        import torch
+
+        assert A.is_cuda and W.is_cuda and A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] == W.shape[1]
+        M, K = A.shape
+        N = W.shape[0]
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        check(self._L.gigl_linear_dev(self.handle, M, N, K, _dp_any(A), A.stride(0), _dp_any(W), W.stride(0),
+                                      None if bias is None else _dp(bias), _dp_any(out), out.stride(0), int(relu)), self.handle)
+        return out
+
     def gather_mean(self, x, rowptr, col, n_rows_out: Optional[int] = None, out=None):
         import torch
 

@@ -211,6 +211,15 @@ int gigl_gcn_conv_dev(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int6
 int gigl_gcn_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O, const int64_t* edge_index,
                        const float* x, const float* W, const float* b, float* out, int32_t relu);
 
+/*
+ * F.linear on the tensor cores: C[M, N] = A[M, K] @ W[N, K]^T + bias (optional ReLU), fp32 in and
+ * out, computed as 3xTF32 on tcgen05 (relative error ~2^-21, inside the 1e-5 parity bound).  This
+ * is the weight projection of SAGEConv (lin_l / lin_r) and GCNConv (lin); exposed on its own for
+ * the PyTorch binding and the tests.  Row pitches lda / ldw / ldc are in floats.
+ */
+int gigl_linear_dev(gigl_ctx* ctx, int64_t M, int32_t N, int32_t K, const float* A_dev, int64_t lda, const float* W_dev,
+                    int64_t ldw, const float* bias_dev, float* C_dev, int64_t ldc, int32_t relu);
+
 /* ---- resident node features ------------------------------------------------------------- */
 
 /*

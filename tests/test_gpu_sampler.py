@@ -234,3 +234,34 @@ def test_khop_device_entry_point_and_properties_large(ctx):
     assert np.array_equal(nbr[0].view(-1, fan[0]).cpu().numpy()[sel].ravel(), onbr[0])
     assert np.array_equal(nbr[1].view(-1, fan[0] * fan[1]).cpu().numpy()[sel].ravel(), onbr[1])
     assert np.array_equal(cnt[1].view(-1, fan[0]).cpu().numpy()[sel].ravel(), ocnt[1])
+
+
+@pytest.mark.parametrize("fan", [[15, 10], [40, 3], [100], [16, 32]])
+def test_hash_window_index_is_bit_exact(ctx, fan):
+    """The sampler's per-graph index of the hash sequence (block minima) must not change a single
+    sampled id: index on == index off == oracle, on a graph whose hubs span many index blocks and
+    whose light rows straddle block boundaries."""
+    from gigl_b200 import Graph
+
+    orc = _orc()
+    rng = np.random.default_rng(9)
+    n = 30000
+    src, dst = powerlaw_edges(n, 400000, 13, alpha=1.4)
+    hubs = rng.permutation(n)[:3]
+    src = np.concatenate([src, rng.integers(0, n, 60000), rng.integers(0, n, 9000), rng.integers(0, n, 700)])
+    dst = np.concatenate([dst, np.full(60000, hubs[0]), np.full(9000, hubs[1]), np.full(700, hubs[2])])
+    g = Graph.from_edges_host(ctx, n, src, dst, is_graph_directed=True)
+    rowptr, col = orc.np_build_in_csr(src, dst, n, True)
+    roots = np.concatenate([hubs, rng.permutation(n)[:4000]]).astype(np.int32)
+    want = orc.c_sample_khop(rowptr, col, roots, fan)
+    g.set_hash_index(True)
+    got_on = g.sample_khop_host(roots, fan)
+    g.set_hash_index(False)
+    got_off = g.sample_khop_host(roots, fan)
+    _check_equal(got_on, want)
+    _check_equal(got_off, want)
+    # other seeds / call numbers shift the windows against the block grid
+    g.set_hash_index(True)
+    for seed, call in ((42, 3), (7, 1), (123456, 2)):
+        _check_equal(g.sample_khop_host(roots[:500], fan, base_seed=seed, first_call_no=call),
+                     orc.c_sample_khop(rowptr, col, roots[:500], fan, base_seed=seed, first_call_no=call))
