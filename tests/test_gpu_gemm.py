@@ -35,10 +35,10 @@ def test_linear_tc_matches_fp64(ctx, M, N, K, relu, bias):
         ref = ref.clamp(min=0)
     err = float((out.double() - ref).abs().max() / max(1.0, float(ref.abs().max())))
     assert err < RTOL, err
-    # per-element relative check away from cancellation: 3xTF32 should be ~1e-6, far from 1xTF32's 1e-3
+    # per-element relative check away from cancellation: 3xTF32 + fp32 tensor-core accumulation stays ~1e-5, 1xTF32 would be ~1e-3
     big = ref.abs() > 0.5
     if bool(big.any()):
-        assert float(((out.double() - ref).abs() / ref.abs())[big].max()) < 2e-5
+        assert float(((out.double() - ref).abs() / ref.abs())[big].max()) < 2e-4
 
 
 def test_linear_tc_strided_inputs_and_identity(ctx):
