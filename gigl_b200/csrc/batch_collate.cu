@@ -42,50 +42,54 @@ static inline int bits_for64(int64_t n) {
 }
 
 // ---- 1. tree slots -> edge keys --------------------------------------------------------------
+// key = dst << shift | src with shift = bits(n_graph_nodes): only the used bits are sorted.  Filled
+// slots are written densely (warp-aggregated cursor); their order before the sort is irrelevant.
 __global__ void tree_keys_kernel(int64_t n_slots, int32_t f, const int32_t* __restrict__ parents,
-                                 const int32_t* __restrict__ children, uint64_t dead, uint64_t* __restrict__ keys) {
+                                 const int32_t* __restrict__ children, int shift, uint64_t* __restrict__ keys,
+                                 unsigned long long* __restrict__ cursor) {
+    const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += stride) {
-        const int32_t src = __ldg(children + s);
-        uint64_t k = dead;
+    const int64_t n_round = (n_slots + 31) & ~(int64_t)31;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += stride) {
+        int32_t src = -1;
+        if (s < n_slots) src = __ldg(children + s);
+        const uint32_t m = __ballot_sync(0xffffffffu, src >= 0);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
         if (src >= 0) {
             const int32_t dst = __ldg(parents + s / f);
-            k = ((uint64_t)(uint32_t)dst << 32) | (uint32_t)src;
+            keys[base + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)(uint32_t)dst << shift) | (uint32_t)src;
         }
-        keys[s] = k;
     }
 }
 
 // ---- 2. row boundaries in the sorted keys -----------------------------------------------------
-// counters[0] = number of valid (non-dead) keys, counters[1] = number of unique edges
-__global__ void seg_bounds_kernel(int64_t n_slots, const uint64_t* __restrict__ keys, uint64_t dead,
+// counters[1] = number of unique edges
+__global__ void seg_bounds_kernel(int64_t n_keys, const uint64_t* __restrict__ keys, int shift,
                                   int2* __restrict__ segmap, int32_t* __restrict__ counters) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int uniq = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_keys; i += stride) {
         const uint64_t k = keys[i];
-        if (k >= dead) continue;
-        const uint64_t kp = (i > 0) ? keys[i - 1] : ~0ULL;
-        const uint64_t kn = (i + 1 < n_slots) ? keys[i + 1] : dead;
-        const uint32_t d = (uint32_t)(k >> 32);
-        if (i == 0 || (uint32_t)(kp >> 32) != d) segmap[d].x = (int32_t)i;
-        if (kn >= dead || (uint32_t)(kn >> 32) != d) segmap[d].y = (int32_t)(i + 1);
-        if (kn >= dead) counters[0] = (int32_t)(i + 1);
-        uniq += (i == 0 || kp != k);
+        const uint32_t d = (uint32_t)(k >> shift);
+        const uint64_t kp = (i > 0) ? keys[i - 1] : ~k;
+        if (i == 0 || (uint32_t)(kp >> shift) != d) segmap[d].x = (int32_t)i;
+        if (i + 1 == n_keys || (uint32_t)(keys[i + 1] >> shift) != d) segmap[d].y = (int32_t)(i + 1);
+        uniq += (kp != k);
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, off);
     if ((threadIdx.x & 31) == 0 && uniq) atomicAdd(counters + 1, uniq);
 }
 
-__global__ void seg_clear_kernel(int64_t n_slots, const uint64_t* __restrict__ keys, uint64_t dead,
+__global__ void seg_clear_kernel(int64_t n_keys, const uint64_t* __restrict__ keys, int shift,
                                  int2* __restrict__ segmap) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_keys; i += stride) {
         const uint64_t k = keys[i];
-        if (k >= dead) continue;
-        const uint64_t kp = (i > 0) ? keys[i - 1] : ~0ULL;
-        if (i == 0 || (kp >> 32) != (k >> 32)) segmap[(uint32_t)(k >> 32)] = make_int2(0, 0);
+        if (i == 0 || (keys[i - 1] >> shift) != (k >> shift)) segmap[(uint32_t)(k >> shift)] = make_int2(0, 0);
     }
 }
 
@@ -106,7 +110,7 @@ __global__ void roots_assign_kernel(int64_t n_roots, const int32_t* __restrict__
 }
 
 __global__ void __launch_bounds__(256) expand_level_kernel(const int32_t* __restrict__ level_end, int level,
-                                                           const uint64_t* __restrict__ keys,
+                                                           const uint64_t* __restrict__ keys, uint64_t src_mask,
                                                            const int2* __restrict__ segmap, int32_t* __restrict__ lid,
                                                            int32_t* __restrict__ list, int32_t* __restrict__ n_nodes_ctr) {
     const int lane = threadIdx.x & 31;
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(256) expand_level_kernel(const int32_t* __rest
         const int32_t v = list[row];
         const int2 seg = segmap[v];
         for (int e = seg.x + lane; e < seg.y; e += 32) {
-            const int32_t s = (int32_t)(uint32_t)keys[e];
+            const int32_t s = (int32_t)(keys[e] & src_mask);
             if (lid[s] != kLidAbsent) continue;
             if (atomicCAS(lid + s, kLidAbsent, kLidPending) == kLidAbsent) {
                 const int32_t id = atomicAdd(n_nodes_ctr, 1);
@@ -155,9 +159,10 @@ constexpr int kGatherUnroll = 8;      // independent 16-byte loads in flight per
 // reduces across groups.  n_uniq counts the slice's unique keys (warp-uniform).
 template <int LPR>
 __device__ __forceinline__ void gather_range(int row_beg, int e_beg, int e_end, int c, bool active,
-                                             const uint64_t* __restrict__ keys, const float* __restrict__ xsrc,
-                                             int64_t ldx, const int32_t* __restrict__ lid, int lane, int g,
-                                             float4& acc, int& n_uniq) {
+                                             const uint64_t* __restrict__ keys, uint64_t src_mask,
+                                             const float* __restrict__ xsrc, int64_t ldx,
+                                             const int32_t* __restrict__ lid, int lane, int g, float4& acc,
+                                             int& n_uniq) {
     constexpr int G = 32 / LPR;
     for (int base = e_beg; base < e_end; base += 32) {
         const int cnt = min(32, e_end - base);
@@ -166,7 +171,7 @@ __device__ __forceinline__ void gather_range(int row_beg, int e_beg, int e_end, 
             const uint64_t k = __ldg(keys + base + lane);
             const bool dup = (base + lane > row_beg) && (__ldg(keys + base + lane - 1) == k);
             if (!dup) {
-                const int32_t s = (int32_t)(uint32_t)k;
+                const int32_t s = (int32_t)(k & src_mask);
                 my = lid ? __ldg(lid + s) : s;
             }
         }
@@ -228,7 +233,7 @@ template <int LPR>
 __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __restrict__ n_rows_dev, int64_t row_cap,
                                                            int F, const int32_t* __restrict__ list,
                                                            const int2* __restrict__ segmap,
-                                                           const uint64_t* __restrict__ keys,
+                                                           const uint64_t* __restrict__ keys, uint64_t src_mask,
                                                            const float* __restrict__ xsrc, int64_t ldx,
                                                            const int32_t* __restrict__ lid, float* __restrict__ A_hi,
                                                            float* __restrict__ A_lo, int64_t ldA, const HeavyLists hl) {
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
             const bool active = c < F;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             int n_uniq = 0;
-            gather_range<LPR>(seg.x, seg.x, seg.y, c, active, keys, xsrc, ldx, lid, lane, g, acc, n_uniq);
+            gather_range<LPR>(seg.x, seg.x, seg.y, c, active, keys, src_mask, xsrc, ldx, lid, lane, g, acc, n_uniq);
             reduce_groups<LPR>(acc);
             if (g == 0 && active) {
                 const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
 template <int LPR>
 __global__ void __launch_bounds__(256) batch_gather_parts_kernel(int F, const int32_t* __restrict__ list,
                                                                  const int2* __restrict__ segmap,
-                                                                 const uint64_t* __restrict__ keys,
+                                                                 const uint64_t* __restrict__ keys, uint64_t src_mask,
                                                                  const float* __restrict__ xsrc, int64_t ldx,
                                                                  const int32_t* __restrict__ lid, const HeavyLists hl) {
     const int lane = threadIdx.x & 31;
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(256) batch_gather_parts_kernel(int F, const in
             const bool active = c < F;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             int n_uniq = 0;
-            gather_range<LPR>(seg.x, e_beg, e_end, c, active, keys, xsrc, ldx, lid, lane, g, acc, n_uniq);
+            gather_range<LPR>(seg.x, e_beg, e_end, c, active, keys, src_mask, xsrc, ldx, lid, lane, g, acc, n_uniq);
             reduce_groups<LPR>(acc);
             if (g == 0 && active) *reinterpret_cast<float4*>(hl.partial + (int64_t)it * F + c) = acc;
             if (lane == 0 && c0 == 0) hl.pcnt[it] = n_uniq;
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
                                                                   int64_t row_cap, int F,
                                                                   const int32_t* __restrict__ list,
                                                                   const int2* __restrict__ segmap,
-                                                                  const uint64_t* __restrict__ keys,
+                                                                  const uint64_t* __restrict__ keys, uint64_t src_mask,
                                                                   const float* __restrict__ xsrc, int64_t ldx,
                                                                   const int32_t* __restrict__ lid,
                                                                   float* __restrict__ A_hi, float* __restrict__ A_lo,
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
             for (int e = seg.x; e < seg.y; ++e) {
                 const uint64_t k = __ldg(keys + e);
                 if (e > seg.x && __ldg(keys + e - 1) == k) continue;
-                const int32_t s0 = (int32_t)(uint32_t)k;
+                const int32_t s0 = (int32_t)(k & src_mask);
                 const int64_t s = lid ? __ldg(lid + s0) : s0;
                 acc += __ldg(xsrc + s * ldx + c);
                 ++n_uniq;
@@ -387,7 +392,10 @@ struct gigl_batch {
     int32_t* list = nullptr;
     int64_t n_slots = 0;
     int64_t list_cap = 0;
-    uint64_t dead = 0;
+    int shift = 32;            // key = dst << shift | src
+    uint64_t src_mask = 0xffffffffULL;
+    unsigned long long* d_cursor = nullptr;  // valid-key cursor of the keys kernel
+    unsigned long long* h_cursor = nullptr;  // pinned mirror
     int n_levels = 0;          // levels the forward needs (= n_layers of the collate call)
     int n_levels_done = 0;     // level_end entries [1..n_levels_done] are valid
     int n_hops = 0;
@@ -417,6 +425,8 @@ int batch_create(gigl_ctx* ctx, int64_t n_graph_nodes, gigl_batch** out) {
     if (e == cudaSuccess) e = cudaMalloc(&b->lid, sizeof(int32_t) * nn);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ctr, sizeof(int32_t) * kCtrInts);
     if (e == cudaSuccess) e = cudaMallocHost(&b->h_ctr, sizeof(int32_t) * kCtrInts);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_cursor, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&b->h_cursor, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemsetAsync(b->segmap, 0, sizeof(int2) * nn, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_ctr, 0, sizeof(int32_t) * kCtrInts, ctx->stream);
     if (e != cudaSuccess) {
@@ -424,6 +434,8 @@ int batch_create(gigl_ctx* ctx, int64_t n_graph_nodes, gigl_batch** out) {
         if (b->lid) cudaFree(b->lid);
         if (b->d_ctr) cudaFree(b->d_ctr);
         if (b->h_ctr) cudaFreeHost(b->h_ctr);
+        if (b->d_cursor) cudaFree(b->d_cursor);
+        if (b->h_cursor) cudaFreeHost(b->h_cursor);
         delete b;
         return gigl_cuda_fail(ctx, e, "batch_create");
     }
@@ -437,8 +449,8 @@ static int batch_clear(gigl_batch* b) {
     using namespace gigl;
     gigl_ctx* ctx = b->ctx;
     if (!b->dirty) return GIGL_OK;
-    if (b->n_slots > 0) {
-        seg_clear_kernel<<<grid1d(ctx, b->n_slots, 256), 256, 0, ctx->stream>>>(b->n_slots, b->keys, b->dead, b->segmap);
+    if (b->n_valid_host > 0) {
+        seg_clear_kernel<<<grid1d(ctx, b->n_valid_host, 256), 256, 0, ctx->stream>>>(b->n_valid_host, b->keys, b->shift, b->segmap);
         GIGL_LAUNCHED(ctx);
     }
     lid_clear_kernel<<<grid1d(ctx, b->list_cap, 256), 256, 0, ctx->stream>>>(b->d_ctr + 2, b->list, b->lid);
@@ -455,6 +467,8 @@ void batch_destroy(gigl_batch* b) {
     if (b->lid) cudaFree(b->lid);
     if (b->d_ctr) cudaFree(b->d_ctr);
     if (b->h_ctr) cudaFreeHost(b->h_ctr);
+    if (b->d_cursor) cudaFree(b->d_cursor);
+    if (b->h_cursor) cudaFreeHost(b->h_cursor);
     if (b->buf) cudaFree(b->buf);
     delete b;
 }
@@ -479,8 +493,9 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
         GIGL_CHECK(ctx, n_slots <= 0x7fffffffLL, "batch exceeds 2^31-1 edge slots; split the roots");
     }
     const int64_t list_cap = (n_roots + n_slots < b->n_graph_nodes + n_roots) ? n_roots + n_slots : b->n_graph_nodes + n_roots;
-    b->dead = (uint64_t)b->n_graph_nodes << 32;
-    const int end_bit = 32 + bits_for64(b->n_graph_nodes + 1);
+    b->shift = bits_for64(b->n_graph_nodes);
+    b->src_mask = (1ULL << b->shift) - 1ULL;
+    const int end_bit = 2 * b->shift;
     const size_t ns = ((size_t)(n_slots > 0 ? n_slots : 1) + 31) & ~(size_t)31;
     size_t temp_bytes = 0;
     GIGL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
@@ -505,31 +520,34 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     b->dirty = true;
     cudaStream_t st = ctx->stream;
 
-    // 1. keys
-    int64_t off = 0;
+    // 1. keys: filled slots only, densely (one host read of the count: the sort then skips the empty slots)
     width = n_roots;
     int th = gigl_timer_begin(ctx, GIGL_T_COLLATE_KEYS);
+    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), st));
     for (int h = 0; h < n_hops; ++h) {
         const int32_t* parents = (h == 0) ? roots_dev : nbr_dev[h - 1];
         width *= fanouts[h];
         if (width > 0) {
-            tree_keys_kernel<<<grid1d(ctx, width, 256), 256, 0, st>>>(width, fanouts[h], parents, nbr_dev[h], b->dead, keys_a + off);
+            tree_keys_kernel<<<grid1d(ctx, width, 256), 256, 0, st>>>(width, fanouts[h], parents, nbr_dev[h], b->shift, keys_a, b->d_cursor);
             GIGL_LAUNCHED(ctx);
         }
-        off += width;
     }
     gigl_timer_end(ctx, th);
-    // 2. sort + row bounds
+    GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     GIGL_CUDA(ctx, cudaMemsetAsync(b->d_ctr, 0, sizeof(int32_t) * kCtrInts, st));
-    if (n_slots > 0) {
+    GIGL_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t n_valid = (int64_t)*b->h_cursor;
+    b->n_valid_host = n_valid;
+    // 2. sort + row bounds
+    if (n_valid > 0) {
         th = gigl_timer_begin(ctx, GIGL_T_COLLATE_SORT);
-        GIGL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_a, keys_b, (int64_t)n_slots, 0, end_bit, st));
+        GIGL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_a, keys_b, n_valid, 0, end_bit, st));
         ctx->launches++;
         gigl_timer_end(ctx, th);
     }
     th = gigl_timer_begin(ctx, GIGL_T_COLLATE_MAPS);
-    if (n_slots > 0) {
-        seg_bounds_kernel<<<grid1d(ctx, n_slots, 256), 256, 0, st>>>(n_slots, keys_b, b->dead, b->segmap, b->d_ctr);
+    if (n_valid > 0) {
+        seg_bounds_kernel<<<grid1d(ctx, n_valid, 256), 256, 0, st>>>(n_valid, keys_b, b->shift, b->segmap, b->d_ctr);
         GIGL_LAUNCHED(ctx);
     }
     // 3. levels: level_end[1] = n_roots, then n_layers - 1 expansions
@@ -541,7 +559,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + 2, &init[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + kLevelBase, &init[1], sizeof(int32_t) * 2, cudaMemcpyHostToDevice, st));
     for (int j = 1; j < n_layers; ++j) {
-        expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->segmap, b->lid, b->list, b->d_ctr + 2);
+        expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->src_mask, b->segmap, b->lid, b->list, b->d_ctr + 2);
         GIGL_LAUNCHED(ctx);
         level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
         GIGL_LAUNCHED(ctx);
@@ -552,7 +570,6 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     b->n_hops = n_hops;
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(int32_t) * kCtrInts, cudaMemcpyDeviceToHost, st));
     GIGL_CUDA(ctx, cudaStreamSynchronize(st));
-    b->n_valid_host = b->h_ctr[0];
     b->n_unique_host = b->h_ctr[1];
     for (int j = 0; j <= n_layers; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
     if (level_sizes_host)
@@ -676,7 +693,7 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         int tg = gigl_timer_begin(ctx, l == 1 ? GIGL_T_GATHER_L1 : GIGL_T_GATHER_DEEP);
         const bool vec = (Fi % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0) && (ldx % 4 == 0);
         if (!vec) {
-            batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, A_hi, A_lo, lda);
+            batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, b->src_mask, xin, ldx, lidmap, A_hi, A_lo, lda);
             GIGL_LAUNCHED(ctx);
         } else {
             // split-row work lists (sized from the collate's valid-key count; see kSplitThreshold)
@@ -699,10 +716,10 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
             const int hgrid = ctx->sm_count * 4;
 #define GIGL_GATHER(LPR)                                                                                                  \
     do {                                                                                                                  \
-        batch_gather_kernel<LPR><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, xin, ldx,    \
-                                                            lidmap, A_hi, A_lo, lda, hl);                                 \
+        batch_gather_kernel<LPR><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, b->src_mask, \
+                                                            xin, ldx, lidmap, A_hi, A_lo, lda, hl);                       \
         GIGL_LAUNCHED(ctx);                                                                                               \
-        batch_gather_parts_kernel<LPR><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, xin, ldx, lidmap, hl);     \
+        batch_gather_parts_kernel<LPR><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, b->src_mask, xin, ldx, lidmap, hl);     \
         GIGL_LAUNCHED(ctx);                                                                                               \
     } while (0)
             if (Fi <= 16)
@@ -733,13 +750,13 @@ gigl_ctx* batch_ctx(gigl_batch* b) { return b->ctx; }
 
 namespace gigl {
 // compacted unique keys (dst << 32 | src, global ids) -> edge_index rows in local ids
-__global__ void export_edges_kernel(int64_t n_unique, const uint64_t* __restrict__ uniq, const int32_t* __restrict__ lid,
-                                    int64_t* __restrict__ edge_index) {
+__global__ void export_edges_kernel(int64_t n_unique, const uint64_t* __restrict__ uniq, int shift, uint64_t src_mask,
+                                    const int32_t* __restrict__ lid, int64_t* __restrict__ edge_index) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_unique; i += stride) {
         const uint64_t k = uniq[i];
-        edge_index[i] = lid[(uint32_t)k];
-        edge_index[n_unique + i] = lid[(uint32_t)(k >> 32)];
+        edge_index[i] = lid[(uint32_t)(k & src_mask)];
+        edge_index[n_unique + i] = lid[(uint32_t)(k >> shift)];
     }
 }
 }  // namespace gigl
@@ -752,7 +769,7 @@ int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges) {
     const int want = (b->n_hops > b->n_levels ? b->n_hops : b->n_levels) + 1;  // level_end entries [1..want]
     if (b->n_levels_done < want && b->n_roots > 0) {
         for (int j = b->n_levels_done; j < want; ++j) {
-            expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->segmap, b->lid, b->list, b->d_ctr + 2);
+            expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->src_mask, b->segmap, b->lid, b->list, b->d_ctr + 2);
             GIGL_LAUNCHED(ctx);
             level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
             GIGL_LAUNCHED(ctx);
@@ -789,7 +806,7 @@ int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev) 
         uint64_t* uniq = (uint64_t*)pu;
         GIGL_CUDA(ctx, cub::DeviceSelect::Unique((char*)pu + ub, tb, b->keys, uniq, b->d_ctr + 3, (int64_t)b->n_valid_host, st));
         ctx->launches++;
-        export_edges_kernel<<<grid1d(ctx, n_edges, 256), 256, 0, st>>>(n_edges, uniq, b->lid, edge_index_dev);
+        export_edges_kernel<<<grid1d(ctx, n_edges, 256), 256, 0, st>>>(n_edges, uniq, b->shift, b->src_mask, b->lid, edge_index_dev);
         GIGL_LAUNCHED(ctx);
     }
     return GIGL_OK;

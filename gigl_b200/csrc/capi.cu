@@ -398,6 +398,7 @@ void gigl_graph_destroy(gigl_graph* g) {
         cudaStreamSynchronize(g->ctx->stream);
         if (g->hx_keys) cudaFree(g->hx_keys);
         if (g->hx_offs) cudaFree(g->hx_offs);
+        if (g->hk_table) cudaFree(g->hk_table);
     }
     if (g->x_owned && g->x) {
         cudaSetDevice(g->ctx->device);

@@ -84,6 +84,8 @@ struct gigl_graph {
     // hash-window index of the sampler (khop_sample.cu), built lazily on the first sampling call
     uint64_t* hx_keys = nullptr;
     uint16_t* hx_offs = nullptr;
+    uint64_t* hk_table = nullptr;  // every key of the indexed range
+    uint64_t hk_limit = 0;
     uint64_t hx_limit = 0;
     int32_t hx_l_log2 = 0;
     int32_t hx_cap = 0;

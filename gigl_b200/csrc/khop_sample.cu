@@ -47,6 +47,9 @@ struct HopArgs {
     uint64_t hx_limit;  // inputs [0, hx_limit) are covered
     int32_t hx_l_log2;
     int32_t hx_cap;
+    // full key table: hk_table[x] = ordered_key(x) for x in [0, hk_limit); nullptr = hash on the fly
+    const uint64_t* hk_table;
+    uint64_t hk_limit;
 };
 
 // Sorted (ascending) best-`f` list held by one warp: position p lives in lane p%32, register p/32.
@@ -299,6 +302,137 @@ __device__ __forceinline__ void select_row(const HopArgs& a, WarpTopK<KPL>& best
     best.scan(0, size, 32, base, f, lane);
 }
 
+// ---- threshold selection (fanout <= 32) ------------------------------------------------------
+// The keys are uniform 64-bit values, so the f-th smallest of `size` keys sits near (f / size) * 2^64.
+// One pass collects every key below T = (m / size) * 2^64, m a little above f, into a per-warp
+// shared-memory buffer (no serial insertions), one bitonic sort orders the <= 64 candidates, the
+// first f are the answer.  If fewer than f keys fell below T, or more than the buffer holds (both
+// rare by the Poisson tail), the exact streaming path above redoes the row - the result is always
+// the exact top-f of the exact keys.
+constexpr int kCandCap = 64;
+
+struct PairKI {
+    uint64_t k;
+    int32_t i;
+};
+
+__device__ __forceinline__ void cmpx(PairKI& v, int lane, int stride, bool take_min) {
+    const uint64_t ok = __shfl_xor_sync(0xffffffffu, v.k, stride);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, v.i, stride);
+    if (take_min == (ok < v.k)) {
+        v.k = ok;
+        v.i = oi;
+    }
+}
+
+__device__ __forceinline__ void sort32(PairKI& v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+            cmpx(v, lane, stride, ((lane & size) == 0) == ((lane & stride) == 0));
+}
+
+__device__ __forceinline__ bool push_cands(uint64_t* __restrict__ ck, int32_t* __restrict__ ci, int& c, bool is_cand,
+                                           uint64_t k, int32_t i, int lane) {
+    const uint32_t m = __ballot_sync(0xffffffffu, is_cand);
+    if (m == 0) return true;
+    const int n = __popc(m);
+    if (c + n > kCandCap) return false;
+    if (is_cand) {
+        const int p = c + __popc(m & ((1u << lane) - 1u));
+        ck[p] = k;
+        ci[p] = i;
+    }
+    c += n;
+    return true;
+}
+
+__device__ __forceinline__ bool scan_threshold(const HopArgs& a, bool use_tab, uint32_t base, int64_t i_first, int64_t i_last,
+                                               uint64_t T, uint64_t* ck, int32_t* ci, int& c, int lane) {
+    for (int64_t c0 = i_first - 1; c0 < i_last; c0 += 32) {
+        const int64_t i = c0 + lane + 1;
+        uint64_t k = kKeyInf;
+        if (i <= i_last) {
+            const uint32_t x = base + (uint32_t)i;
+            k = use_tab ? __ldg(a.hk_table + x) : ordered_key((int32_t)x);
+        }
+        if (!push_cands(ck, ci, c, k < T, k, (int32_t)i, lane)) return false;
+    }
+    return true;
+}
+
+// Returns true with best.key[0] / best.idx[0] = the row's keys in ascending order (>= f of them, or all).
+__device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& best, int64_t size, uint32_t base, int f,
+                                                 int lane, uint64_t* ck, int32_t* ci) {
+    float m = (float)f + fmaxf(14.f, 1.2f * (float)f);
+    if (m > 48.f) m = 48.f;
+    uint64_t T = kKeyInf;
+    if ((float)size > m) T = __float2ull_rz(m / (float)size * 18446744073709551616.0f);
+    const uint64_t lo = (uint64_t)base + 1, hi = (uint64_t)base + (uint64_t)size;
+    const bool use_tab = a.hk_table != nullptr && hi < a.hk_limit;
+    int c = 0;
+    bool done = false;
+    if (a.hx_keys != nullptr && hi < a.hx_limit) {
+        const int lg = a.hx_l_log2;
+        const uint64_t b0 = (lo + ((1ULL << lg) - 1)) >> lg, b1 = (hi + 1) >> lg;  // full blocks [b0, b1)
+        if (b0 < b1) {
+            const int64_t head_end = (int64_t)((b0 << lg) - lo);
+            const int64_t tail_begin = (int64_t)((b1 << lg) - (uint64_t)base);
+            if (!scan_threshold(a, use_tab, base, 1, head_end, T, ck, ci, c, lane)) return false;
+            if (!scan_threshold(a, use_tab, base, tail_begin, size, T, ck, ci, c, lane)) return false;
+            const int cap = a.hx_cap;
+            for (uint64_t bb = b0; bb < b1; bb += 32) {
+                const uint64_t myb = bb + lane;
+                bool active = myb < b1;
+                for (int j = 0; __any_sync(0xffffffffu, active); ++j) {
+                    uint64_t ek = kKeyInf;
+                    uint32_t eo = 0;
+                    if (active) {
+                        ek = __ldg(a.hx_keys + myb * cap + j);
+                        eo = __ldg(a.hx_offs + myb * cap + j);
+                    }
+                    const bool cand = active && ek < T;
+                    const uint32_t x = (uint32_t)(myb << lg) + eo;
+                    if (!push_cands(ck, ci, c, cand, ek, (int32_t)(x - base), lane)) return false;
+                    active = cand && (j + 1 < cap);
+                }
+            }
+            done = true;
+        }
+    }
+    if (!done && !scan_threshold(a, use_tab, base, 1, size, T, ck, ci, c, lane)) return false;
+    const int64_t need = size < f ? size : f;
+    if (c < need) return false;
+    __syncwarp();
+    PairKI v0{kKeyInf, 0}, v1{kKeyInf, 0};
+    if (lane < c) {
+        v0.k = ck[lane];
+        v0.i = ci[lane];
+    }
+    sort32(v0, lane);
+    if (c > 32) {  // warp-uniform
+        if (lane + 32 < c) {
+            v1.k = ck[lane + 32];
+            v1.i = ci[lane + 32];
+        }
+        sort32(v1, lane);
+        // 32 smallest of two ascending runs: min(v0[l], v1[31 - l]) is bitonic; one merge sorts it
+        const uint64_t ok = __shfl_sync(0xffffffffu, v1.k, 31 - lane);
+        const int32_t oi = __shfl_sync(0xffffffffu, v1.i, 31 - lane);
+        if (ok < v0.k) {
+            v0.k = ok;
+            v0.i = oi;
+        }
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) cmpx(v0, lane, stride, (lane & stride) == 0);
+    }
+    __syncwarp();
+    best.key[0] = v0.k;
+    best.idx[0] = v0.i;
+    return true;
+}
+
 __device__ __forceinline__ bool row_uses_index(const HopArgs& a, int64_t size, uint32_t base) {
     if (a.hx_keys == nullptr) return false;
     const uint64_t lo = (uint64_t)base + 1, hi = (uint64_t)base + (uint64_t)size;
@@ -349,7 +483,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_hop_kernel(const Hop
     }
     WarpTopK<KPL> best;
     best.init();
-    select_row<KPL>(a, best, size, base, f, lane);
+    if constexpr (KPL == 1) {
+        __shared__ uint64_t s_ck[kWarpsPerBlock][kCandCap];
+        __shared__ int32_t s_ci[kWarpsPerBlock][kCandCap];
+        const int w = threadIdx.x >> 5;
+        if (size <= 32 || !select_threshold(a, best, size, base, f, lane, s_ck[w], s_ci[w])) {
+            best.init();
+            select_row<KPL>(a, best, size, base, f, lane);
+        }
+    } else {
+        select_row<KPL>(a, best, size, base, f, lane);
+    }
     write_result<KPL>(a, pslot, best, size, row_begin, mult, lane);
 }
 
@@ -394,6 +538,11 @@ __global__ void __launch_bounds__(kHeavyWarps * 32) khop_heavy_kernel(const HopA
     }
 }
 
+__global__ void build_key_table_kernel(int64_t n, uint64_t* __restrict__ table) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) table[x] = ordered_key((int32_t)(uint32_t)x);
+}
+
 static int ensure_hash_index(gigl_graph* g, int fmax, int n_hops) {
     gigl_ctx* ctx = g->ctx;
     if (!g->hx_enabled) return GIGL_OK;
@@ -432,6 +581,18 @@ static int ensure_hash_index(gigl_graph* g, int fmax, int n_hops) {
     g->hx_cap = cap;
     g->hx_l_log2 = lg;
     g->hx_limit = limit;
+    // the full key table (8 bytes per hash input): short windows read their keys instead of hashing them
+    if (g->hk_table) cudaFree(g->hk_table);
+    g->hk_table = nullptr;
+    g->hk_limit = 0;
+    if (cudaMalloc(&g->hk_table, sizeof(uint64_t) * (size_t)limit) == cudaSuccess) {
+        build_key_table_kernel<<<grid, 256, 0, ctx->stream>>>((int64_t)limit, g->hk_table);
+        GIGL_LAUNCHED(ctx);
+        g->hk_limit = limit;
+    } else {
+        g->hk_table = nullptr;
+        cudaGetLastError();
+    }
     return GIGL_OK;
 }
 
@@ -486,6 +647,8 @@ int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
     a.hx_limit = g->hx_limit;
     a.hx_l_log2 = g->hx_l_log2;
     a.hx_cap = g->hx_cap;
+    a.hk_table = (g->hx_enabled && a.hx_keys) ? g->hk_table : nullptr;
+    a.hk_limit = g->hk_limit;
     a.rowptr = g->rowptr;
     a.col = g->col;
     a.n_nodes = g->n_nodes;
