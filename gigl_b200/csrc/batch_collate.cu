@@ -44,24 +44,54 @@ static inline int bits_for64(int64_t n) {
 // ---- 1. tree slots -> edge keys --------------------------------------------------------------
 // key = dst << shift | src with shift = bits(n_graph_nodes): only the used bits are sorted.  Filled
 // slots are written densely (warp-aggregated cursor); their order before the sort is irrelevant.
-__global__ void tree_keys_kernel(int64_t n_slots, int32_t f, const int32_t* __restrict__ parents,
-                                 const int32_t* __restrict__ children, int shift, uint64_t* __restrict__ keys,
-                                 unsigned long long* __restrict__ cursor) {
-    const int lane = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n_round = (n_slots + 31) & ~(int64_t)31;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += stride) {
-        int32_t src = -1;
-        if (s < n_slots) src = __ldg(children + s);
-        const uint32_t m = __ballot_sync(0xffffffffu, src >= 0);
-        if (m == 0) continue;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (src >= 0) {
-            const int32_t dst = __ldg(parents + s / f);
-            keys[base + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)(uint32_t)dst << shift) | (uint32_t)src;
+constexpr int kKeysPerThread = 4;
+__global__ void __launch_bounds__(256) tree_keys_kernel(int64_t n_slots, int32_t f, const int32_t* __restrict__ parents,
+                                                        const int32_t* __restrict__ children, int shift,
+                                                        uint64_t* __restrict__ keys, unsigned long long* __restrict__ cursor) {
+    __shared__ int s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per_block = 256 * kKeysPerThread;
+    const int64_t n_iter = (n_slots + per_block - 1) / per_block;
+    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {  // block-uniform trip count
+        // thread t owns slots base + t*4 .. +3 (contiguous per thread: 16-byte loads)
+        const int64_t s0 = it * per_block + (int64_t)threadIdx.x * kKeysPerThread;
+        int32_t src[kKeysPerThread];
+        int mine = 0;
+#pragma unroll
+        for (int q = 0; q < kKeysPerThread; ++q) {
+            src[q] = (s0 + q < n_slots) ? __ldg(children + s0 + q) : -1;
+            mine += src[q] >= 0;
         }
+        // exclusive prefix of `mine` inside the warp, then across the 8 warps, then ONE global atomic per block
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int t = s_warp[w];
+                s_warp[w] = tot;
+                tot += t;
+            }
+            s_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ULL;
+        }
+        __syncthreads();
+        unsigned long long pos = s_base + (unsigned long long)(s_warp[warp] + incl - mine);
+#pragma unroll
+        for (int q = 0; q < kKeysPerThread; ++q) {
+            if (src[q] >= 0) {
+                const int32_t dst = __ldg(parents + (s0 + q) / f);
+                keys[pos++] = ((uint64_t)(uint32_t)dst << shift) | (uint32_t)src[q];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -109,25 +139,66 @@ __global__ void roots_assign_kernel(int64_t n_roots, const int32_t* __restrict__
     atomicMin(lid + v, (int32_t)i);  // duplicate roots: the first slot owns the local id
 }
 
+// New local ids are claimed with atomicCAS on the dense map, but handed out in bulk: winners are staged
+// in shared memory and the block takes ONE range from the global counter per 8 rows (a single hot
+// counter with one atomic per node serialises in the L2 atomic unit).
+constexpr int kStageCap = 1024;
 __global__ void __launch_bounds__(256) expand_level_kernel(const int32_t* __restrict__ level_end, int level,
                                                            const uint64_t* __restrict__ keys, uint64_t src_mask,
                                                            const int2* __restrict__ segmap, int32_t* __restrict__ lid,
                                                            int32_t* __restrict__ list, int32_t* __restrict__ n_nodes_ctr) {
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_cnt, s_base;
+    __shared__ int32_t s_stage[kStageCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t lo = level_end[level - 1], hi = level_end[level];
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t row = lo + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < hi; row += warps) {
-        const int32_t v = list[row];
-        const int2 seg = segmap[v];
-        for (int e = seg.x + lane; e < seg.y; e += 32) {
-            const int32_t s = (int32_t)(keys[e] & src_mask);
-            if (lid[s] != kLidAbsent) continue;
-            if (atomicCAS(lid + s, kLidAbsent, kLidPending) == kLidAbsent) {
-                const int32_t id = atomicAdd(n_nodes_ctr, 1);
-                list[id] = s;
-                lid[s] = id;
+    const int64_t step = (int64_t)gridDim.x * 8;
+    for (int64_t row0 = lo + (int64_t)blockIdx.x * 8; row0 < hi; row0 += step) {  // block-uniform trip count
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int64_t row = row0 + warp;
+        if (row < hi) {
+            const int32_t v = list[row];
+            const int2 seg = segmap[v];
+            for (int e0 = seg.x; e0 < seg.y; e0 += 32) {
+                const int e = e0 + lane;
+                int32_t sv = -1;
+                bool won = false;
+                if (e < seg.y) {
+                    sv = (int32_t)(keys[e] & src_mask);
+                    if (lid[sv] == kLidAbsent) won = atomicCAS(lid + sv, kLidAbsent, kLidPending) == kLidAbsent;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, won);
+                if (m == 0) continue;
+                const int n = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&s_cnt, n);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot + n <= kStageCap) {
+                    if (won) s_stage[slot + rank] = sv;
+                } else {  // stage full (very long rows): undo and take ids straight from the global counter
+                    int base = 0;
+                    if (lane == 0) {
+                        atomicSub(&s_cnt, n);
+                        base = atomicAdd(n_nodes_ctr, n);
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (won) {
+                        list[base + rank] = sv;
+                        lid[sv] = base + rank;
+                    }
+                }
             }
         }
+        __syncthreads();
+        const int n_staged = s_cnt;
+        if (threadIdx.x == 0 && n_staged > 0) s_base = atomicAdd(n_nodes_ctr, n_staged);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_staged; i += blockDim.x) {
+            const int32_t sv = s_stage[i];
+            list[s_base + i] = sv;
+            lid[sv] = s_base + i;
+        }
+        __syncthreads();
     }
 }
 
@@ -226,9 +297,38 @@ struct HeavyLists {
     int32_t part_cap;
 };
 
+// Sum of the already-resolved sources of one 32-key chunk (`my` per lane, -1 = skip).
+template <int LPR>
+__device__ __forceinline__ void gather_chunk(int32_t my, int cnt, int c, bool active, const float* __restrict__ xsrc,
+                                             int64_t ldx, int g, float4& acc) {
+    constexpr int G = 32 / LPR;
+    for (int t = 0; t < cnt; t += kGatherUnroll * G) {
+        float4 val[kGatherUnroll];
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            const int j = t + u * G + g;
+            const int32_t s = __shfl_sync(0xffffffffu, my, j & 31);
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < cnt && s >= 0 && active) val[u] = ldg4(xsrc + (int64_t)s * ldx + c);
+        }
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            acc.x += val[u].x;
+            acc.y += val[u].y;
+            acc.z += val[u].z;
+            acc.w += val[u].w;
+        }
+    }
+}
+
 // LPR lanes cover one 4*LPR-float chunk of a feature row; G = 32/LPR sources are in flight per step.
 // xsrc rows are indexed by global vertex id when lid == nullptr (layer 1 reads the graph-wide
 // feature table directly) or by lid[src] (deeper layers read the previous layer's rows).
+//
+// Persistent warps, one row per iteration.  A row needs a chain of dependent random loads before
+// its first feature byte moves (node id -> row bounds -> sorted keys -> local id), ~2 us of pure
+// latency; the chain is software-pipelined across iterations: while row i is gathered, the node
+// id of row i+4, the bounds of row i+3, the keys of row i+2 and the local ids of row i+1 are in flight.
 template <int LPR>
 __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __restrict__ n_rows_dev, int64_t row_cap,
                                                            int F, const int32_t* __restrict__ list,
@@ -241,12 +341,37 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
     const int sub = lane % LPR, g = lane / LPR;
     int64_t n_rows = *n_rows_dev;
     if (n_rows > row_cap) n_rows = row_cap;
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
-        const int32_t v = __ldg(list + row);
-        const int2 seg = __ldg(segmap + v);
-        const int64_t self = lid ? row : (int64_t)v;
-        const int len = seg.y - seg.x;
+    const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t last = n_rows - 1;
+#define GIGL_ROW(r) ((r) < n_rows ? (r) : last)
+    // first chunk of a row: key per lane (kKeyNone beyond the row), duplicates of the lower lane masked later
+    constexpr uint64_t kKeyNone = ~0ULL;
+    auto load_keys = [&](const int2& seg) -> uint64_t {
+        const int e = seg.x + lane;
+        return e < seg.y ? __ldg(keys + e) : kKeyNone;
+    };
+    auto resolve = [&](uint64_t k) -> int32_t {  // -1 for absent / duplicate, else the source row index
+        const uint64_t kp = __shfl_up_sync(0xffffffffu, k, 1);
+        if (k == kKeyNone || (lane > 0 && kp == k)) return -1;
+        const int32_t sv = (int32_t)(k & src_mask);
+        return lid ? __ldg(lid + sv) : sv;
+    };
+    int32_t vA = __ldg(list + row), vB = __ldg(list + GIGL_ROW(row + W)), vC = __ldg(list + GIGL_ROW(row + 2 * W)),
+            vD = __ldg(list + GIGL_ROW(row + 3 * W));
+    int2 segA = __ldg(segmap + vA), segB = __ldg(segmap + vB), segC = __ldg(segmap + vC);
+    uint64_t kB = load_keys(segB);
+    int32_t myA = resolve(load_keys(segA));
+    for (; row < n_rows; row += W) {
+        // ---- prefetch stage of the pipeline ----
+        const int32_t vE = __ldg(list + GIGL_ROW(row + 4 * W));
+        const int2 segD = __ldg(segmap + vD);
+        const uint64_t kC = load_keys(segC);
+        const int32_t myB = resolve(kB);
+        // ---- row A ----
+        const int len = segA.y - segA.x;
+        bool deferred = false;
         if (len > kSplitThreshold && hl.items != nullptr) {
             const int n_parts = (len + kPartEdges - 1) / kPartEdges;
             int slot = 0;
@@ -255,24 +380,43 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
             if (slot + n_parts <= hl.part_cap) {
                 if (lane == 0) hl.rows[atomicAdd(hl.hctr + 1, 1)] = make_int4((int)row, slot, n_parts, 0);
                 for (int p = lane; p < n_parts; p += 32) hl.items[slot + p] = make_int2((int)row, p);
-                continue;
+                deferred = true;
             }
-            // lists full (cannot happen with the host-side sizing): do the long row here
+            // else: lists full (cannot happen with the host-side sizing): do the long row here
         }
-        for (int c0 = 0; c0 < F; c0 += LPR * 4) {
-            const int c = c0 + sub * 4;
-            const bool active = c < F;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int n_uniq = 0;
-            gather_range<LPR>(seg.x, seg.x, seg.y, c, active, keys, src_mask, xsrc, ldx, lid, lane, g, acc, n_uniq);
-            reduce_groups<LPR>(acc);
-            if (g == 0 && active) {
-                const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
-                store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
-                store_split4(A_hi, A_lo, row * ldA + F + c, ldg4(xsrc + self * ldx + c));
+        if (!deferred) {
+            const int64_t self = lid ? row : (int64_t)vA;
+            const int cnt0 = len < 32 ? len : 32;
+            for (int c0 = 0; c0 < F; c0 += LPR * 4) {
+                const int c = c0 + sub * 4;
+                const bool active = c < F;
+                float4 selfv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g == 0 && active) selfv = ldg4(xsrc + self * ldx + c);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int n_uniq = __popc(__ballot_sync(0xffffffffu, myA >= 0));
+                gather_chunk<LPR>(myA, cnt0, c, active, xsrc, ldx, g, acc);
+                if (len > 32)
+                    gather_range<LPR>(segA.x, segA.x + 32, segA.y, c, active, keys, src_mask, xsrc, ldx, lid, lane, g, acc, n_uniq);
+                reduce_groups<LPR>(acc);
+                if (g == 0 && active) {
+                    const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
+                    store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
+                    store_split4(A_hi, A_lo, row * ldA + F + c, selfv);
+                }
             }
         }
+        // ---- rotate ----
+        vA = vB;
+        vB = vC;
+        vC = vD;
+        vD = vE;
+        segA = segB;
+        segB = segC;
+        segC = segD;
+        kB = kC;
+        myA = myB;
     }
+#undef GIGL_ROW
 }
 
 // One warp per (row, part): partial sums of kPartEdges sorted keys.
@@ -528,7 +672,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
         const int32_t* parents = (h == 0) ? roots_dev : nbr_dev[h - 1];
         width *= fanouts[h];
         if (width > 0) {
-            tree_keys_kernel<<<grid1d(ctx, width, 256), 256, 0, st>>>(width, fanouts[h], parents, nbr_dev[h], b->shift, keys_a, b->d_cursor);
+            tree_keys_kernel<<<grid1d(ctx, ceil_div64(width, kKeysPerThread), 256), 256, 0, st>>>(width, fanouts[h], parents, nbr_dev[h], b->shift, keys_a, b->d_cursor);
             GIGL_LAUNCHED(ctx);
         }
     }
@@ -689,7 +833,8 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         const int64_t lda = m->ldw[l - 1];
         const int32_t* lidmap = (l == 1) ? nullptr : b->lid;
         const int wpb = 8;
-        const unsigned grid = (unsigned)ceil_div64(rows, wpb);
+        const int64_t gfull = ceil_div64(rows, wpb), gcap = (int64_t)ctx->sm_count * 3;  // 80 registers -> 3 CTAs per SM
+        const unsigned grid = (unsigned)(gfull < gcap ? gfull : gcap);  // persistent warps (grid-stride over rows)
         int tg = gigl_timer_begin(ctx, l == 1 ? GIGL_T_GATHER_L1 : GIGL_T_GATHER_DEEP);
         const bool vec = (Fi % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0) && (ldx % 4 == 0);
         if (!vec) {
