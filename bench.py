@@ -114,15 +114,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def root_batches(n_nodes, rank, world, batch, n_steps, start_step=0):
-    """Roots = all nodes in id order, rank r owning [r*N/P, (r+1)*N/P); step s takes the
-    next `batch` ids of the rank's range (wrapping)."""
-    lo, hi = rank * n_nodes // world, (rank + 1) * n_nodes // world
-    span = hi - lo
-    out = []
-    for s in range(start_step, start_step + n_steps):
-        out.append((lo + (np.arange(batch, dtype=np.int64) + s * batch) % span).astype(np.int32))
-    return out
+from gigl_b200.sharding import max_over_ranks, root_batches  # noqa: E402
 
 
 # ----------------------------------------------------------------------------------------------
@@ -293,10 +285,7 @@ def run_ours(args):
     launches = ctx.launch_count - l0
     timings = ctx.timings()
     ctx.set_timing(False)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms, dev)
     value = world * B * K / (ms * 1e-3)
 
     # edges aggregated per step: layer 1 reduces every unique batch edge, layer 2 those into roots (untimed recount)
@@ -350,10 +339,7 @@ def run_ours(args):
         ev1.record()
         barrier()
         ms_e = ev0.elapsed_time(ev1)  # device time on the launching stream (the host call itself is synchronous)
-        if world > 1:
-            t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e = float(t.item())
+        ms_e = max_over_ranks(ms_e, dev)
         d2h = B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin)
         e2e = {"value": world * B * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / K, "api": "gigl_infer_khop_sage_host (roots in pinned host memory -> padded-tree index sets + "

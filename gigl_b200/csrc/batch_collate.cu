@@ -419,6 +419,184 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
 #undef GIGL_ROW
 }
 
+// ---- cp.async-staged gather (feature rows wider than 64 floats) ------------------------------
+// Same row walk and metadata pipeline as batch_gather_kernel, but the neighbour rows are not staged
+// in registers: every lane copies ITS 16-byte column slice of each neighbour row straight into a
+// private shared-memory ring with cp.async (LDGSTS, L2-only), two buffers of SB rows per warp, and
+// sums it back from there.  A lane only ever reads bytes it copied itself, so no warp barrier is
+// needed, the bytes in flight are bounded by shared memory (8 KB per warp) instead of registers,
+// and the first unit of the NEXT row is already in flight while the last unit of a row is summed.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int CPL, int SB>
+__global__ void __launch_bounds__(256) batch_gather_async_kernel(const int32_t* __restrict__ n_rows_dev, int64_t row_cap,
+                                                                 int F, const int32_t* __restrict__ list,
+                                                                 const int2* __restrict__ segmap,
+                                                                 const uint64_t* __restrict__ keys, uint64_t src_mask,
+                                                                 const float* __restrict__ xsrc, int64_t ldx,
+                                                                 const int32_t* __restrict__ lid,
+                                                                 float* __restrict__ A_hi, float* __restrict__ A_lo,
+                                                                 int64_t ldA, const HeavyLists hl) {
+    extern __shared__ float4 s_ring_all[];
+    constexpr int kSlot = CPL * 32;  // float4 per staged row
+    const int lane = threadIdx.x & 31;
+    float4* ring = s_ring_all + (size_t)(threadIdx.x >> 5) * (2 * SB * kSlot);
+    int64_t n_rows = *n_rows_dev;
+    if (n_rows > row_cap) n_rows = row_cap;
+    const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t last = n_rows - 1;
+#define GIGL_ROW(r) ((r) < n_rows ? (r) : last)
+    constexpr uint64_t kKeyNone = ~0ULL;
+    auto load_keys = [&](int beg, int end) -> uint64_t {
+        const int e = beg + lane;
+        return e < end ? __ldg(keys + e) : kKeyNone;
+    };
+    // -1 for absent / duplicate, else the source row index; `prev` = the key just below this chunk
+    auto resolve = [&](uint64_t k, uint64_t prev) -> int32_t {
+        uint64_t kp = __shfl_up_sync(0xffffffffu, k, 1);
+        if (lane == 0) kp = prev;
+        if (k == kKeyNone || kp == k) return -1;
+        const int32_t sv = (int32_t)(k & src_mask);
+        return lid ? __ldg(lid + sv) : sv;
+    };
+    // copies unit [e0, e0 + SB) of a chunk whose per-lane sources are `my` (chunk starts at entry c_beg)
+    auto issue = [&](int buf, int32_t my, int e0, int len) {
+#pragma unroll
+        for (int jj = 0; jj < SB; ++jj) {
+            const int e = e0 + jj;
+            const int32_t sv = __shfl_sync(0xffffffffu, my, e & 31);
+            if (e < len) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int c = (q * 32 + lane) * 4;
+                    if (c < F)
+                        cp_async16(ring + (buf * SB + jj) * kSlot + q * 32 + lane, xsrc + (sv >= 0 ? (int64_t)sv * ldx : 0) + c,
+                                   sv >= 0 ? 16 : 0);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    int32_t vA = __ldg(list + row), vB = __ldg(list + GIGL_ROW(row + W)), vC = __ldg(list + GIGL_ROW(row + 2 * W)),
+            vD = __ldg(list + GIGL_ROW(row + 3 * W));
+    int2 segA = __ldg(segmap + vA), segB = __ldg(segmap + vB), segC = __ldg(segmap + vC);
+    uint64_t kB = load_keys(segB.x, segB.y);
+    int32_t myA = resolve(load_keys(segA.x, segA.y), kKeyNone);
+    int ub = 0;              // buffer the next unit of the current row goes to / comes from
+    bool pre_issued = false; // unit 0 of row A is already in flight in buffer `ub`
+    for (; row < n_rows; row += W) {
+        // ---- prefetch stage of the metadata pipeline ----
+        const int32_t vE = __ldg(list + GIGL_ROW(row + 4 * W));
+        const int2 segD = __ldg(segmap + vD);
+        const uint64_t kC = load_keys(segC.x, segC.y);
+        const int32_t myB = resolve(kB, kKeyNone);
+        const int lenB = (row + W < n_rows) ? segB.y - segB.x : 0;
+        const bool b_inline = lenB > 0 && !(lenB > kSplitThreshold && hl.items != nullptr);
+        // ---- row A ----
+        const int len = segA.y - segA.x;
+        bool deferred = false;
+        if (len > kSplitThreshold && hl.items != nullptr) {
+            const int n_parts = (len + kPartEdges - 1) / kPartEdges;
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(hl.hctr, n_parts);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot + n_parts <= hl.part_cap) {
+                if (lane == 0) hl.rows[atomicAdd(hl.hctr + 1, 1)] = make_int4((int)row, slot, n_parts, 0);
+                for (int p = lane; p < n_parts; p += 32) hl.items[slot + p] = make_int2((int)row, p);
+                deferred = true;
+            }
+        }
+        bool next_pre = false;
+        if (!deferred) {
+            const int64_t self = lid ? row : (int64_t)vA;
+            float4 selfv[CPL], acc[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int c = (q * 32 + lane) * 4;
+                selfv[q] = c < F ? ldg4(xsrc + self * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            int n_uniq = 0;
+            const int n_units = (len + SB - 1) / SB;
+            int32_t my = myA;
+            if (n_units > 0) n_uniq = __popc(__ballot_sync(0xffffffffu, my >= 0));
+            if (n_units > 0 && !pre_issued) issue(ub, my, 0, len);
+            for (int u = 0; u < n_units; ++u) {
+                // put the next unit in flight (of this row, or unit 0 of the next row) before summing this one
+                bool more = false;
+                int32_t my_next = my;
+                if (u + 1 < n_units) {
+                    const int e0 = (u + 1) * SB;
+                    if ((e0 & 31) == 0) {  // next unit starts a new 32-key chunk of a long row
+                        const uint64_t prev = __ldg(keys + segA.x + e0 - 1);
+                        my_next = resolve(load_keys(segA.x + e0, segA.y), prev);
+                        n_uniq += __popc(__ballot_sync(0xffffffffu, my_next >= 0));
+                    }
+                    issue(ub ^ 1, my_next, e0, len);
+                    more = true;
+                } else if (b_inline) {
+                    issue(ub ^ 1, myB, 0, lenB);
+                    more = true;
+                    next_pre = true;
+                }
+                if (more)
+                    cp_async_wait<1>();
+                else
+                    cp_async_wait<0>();
+                const int cnt = min(SB, len - u * SB);
+#pragma unroll
+                for (int jj = 0; jj < SB; ++jj) {
+                    if (jj < cnt) {
+#pragma unroll
+                        for (int q = 0; q < CPL; ++q) {
+                            if ((q * 32 + lane) * 4 < F) {
+                                const float4 t = ring[(ub * SB + jj) * kSlot + q * 32 + lane];
+                                acc[q].x += t.x;
+                                acc[q].y += t.y;
+                                acc[q].z += t.z;
+                                acc[q].w += t.w;
+                            }
+                        }
+                    }
+                }
+                my = my_next;
+                ub ^= 1;
+            }
+            const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int c = (q * 32 + lane) * 4;
+                if (c < F) {
+                    store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc[q].x * scale, acc[q].y * scale, acc[q].z * scale, acc[q].w * scale));
+                    store_split4(A_hi, A_lo, row * ldA + F + c, selfv[q]);
+                }
+            }
+        }
+        pre_issued = next_pre;
+        // ---- rotate ----
+        vA = vB;
+        vB = vC;
+        vC = vD;
+        vD = vE;
+        segA = segB;
+        segB = segC;
+        segC = segD;
+        kB = kC;
+        myA = myB;
+    }
+#undef GIGL_ROW
+}
+
 // One warp per (row, part): partial sums of kPartEdges sorted keys.
 template <int LPR>
 __global__ void __launch_bounds__(256) batch_gather_parts_kernel(int F, const int32_t* __restrict__ list,
@@ -867,15 +1045,32 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         batch_gather_parts_kernel<LPR><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, b->src_mask, xin, ldx, lidmap, hl);     \
         GIGL_LAUNCHED(ctx);                                                                                               \
     } while (0)
+#define GIGL_GATHER_ASYNC(CPL, SB)                                                                                        \
+    do {                                                                                                                  \
+        const size_t shm = (size_t)wpb * 2 * SB * CPL * 32 * sizeof(float4);                                              \
+        GIGL_CUDA(ctx, cudaFuncSetAttribute(batch_gather_async_kernel<CPL, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
+        batch_gather_async_kernel<CPL, SB><<<grid, wpb * 32, shm, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys,  \
+                                                                        b->src_mask, xin, ldx, lidmap, A_hi, A_lo, lda, hl); \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+        batch_gather_parts_kernel<32><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, b->src_mask, xin, ldx, lidmap, hl); \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+    } while (0)
             if (Fi <= 16)
                 GIGL_GATHER(4);
             else if (Fi <= 32)
                 GIGL_GATHER(8);
             else if (Fi <= 64)
                 GIGL_GATHER(16);
+            else if (Fi <= 128)
+                GIGL_GATHER_ASYNC(1, 8);
+            else if (Fi <= 256)
+                GIGL_GATHER_ASYNC(2, 4);
+            else if (Fi <= 512)
+                GIGL_GATHER_ASYNC(4, 2);
             else
                 GIGL_GATHER(32);
 #undef GIGL_GATHER
+#undef GIGL_GATHER_ASYNC
             batch_gather_finish_kernel<<<hgrid, 256, 0, st>>>(Fi, xin, ldx, b->list, lidmap, A_hi, A_lo, lda, hl);
             GIGL_LAUNCHED(ctx);
         }

@@ -1,0 +1,91 @@
+"""Turn the ncu captures brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/ncu_summarize.py <round-tag> <launches.csv> <full.ncu-rep>
+
+Writes profiles/<tag>_launches.md (every kernel's share of the profiled command, from the
+`--metrics gpu__time_duration.sum` pass), profiles/<tag>_kernels.md (the `--set full` metrics of the
+hot kernels) and profiles/traffic.json (DRAM bytes per launch of the layer-1 gather, read by bench.py)."""
+import collections
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag, launches_csv, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+
+
+def to_us(v, u):
+    v = float(v.replace(",", ""))
+    return {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}.get(u, v)
+
+
+with open(launches_csv) as f:
+    lines = [ln for ln in f if not ln.startswith("==")]
+rd = csv.reader(lines)
+hdr = next(rd)
+ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+agg = collections.OrderedDict()
+for r in rd:
+    if len(r) <= vi:
+        continue
+    try:
+        t = to_us(r[vi], r[ui])
+    except ValueError:
+        continue
+    name = re.sub(r"\(.*", "", r[ki]).replace("void ", "")
+    a = agg.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += t
+ours = {k: v for k, v in agg.items() if "gigl::" in k or "DeviceRadixSort" in k or "DeviceSelect" in k}
+tot = sum(v[1] for v in ours.values())
+with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
+    f.write(f"# {tag}: launch list of `bench.py --steps 2 --warmup 1` under `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n")
+    f.write("Library kernels only (gigl::* and the CUB sort/select they call); torch kernels of the synthetic-input generation are left out. "
+            "Times are cold-cache and serialised: compare SHARES, not absolutes. Includes the one-time graph build / index build launches.\n\n")
+    f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+    for k, (n, t) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"| `{k[:100]}` | {n} | {t:.1f} | {100 * t / tot:.1f}% |\n")
+    f.write(f"\nTotal {tot:.1f} us.\n")
+
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+want = ["launch__grid_size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "smsp__inst_executed.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
+idx = [(w, hdr.index(w)) for w in want if w in hdr]
+ni = hdr.index("Kernel Name")
+
+
+def gb(v, u):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}.get(u, 1.0)
+
+
+traffic = collections.defaultdict(list)
+with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md"), "w") as f:
+    f.write(f"# {tag}: `ncu --set full --clock-control none` of the hot kernels inside `bench.py` (products-like, B=65536, fanout [15,10])\n\n")
+    f.write("| kernel | " + " | ".join(w for w, _ in idx) + " |\n|---|" + "---:|" * len(idx) + "\n")
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[ni]).replace("void ", "")
+        f.write(f"| `{name[:60]}` | " + " | ".join(f"{r[i]} {units[i]}" for _, i in idx) + " |\n")
+        rd_i, wr_i, g_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("launch__grid_size")
+        traffic[name].append((int(float(r[g_i])), gb(r[rd_i], units[rd_i]) + gb(r[wr_i], units[wr_i])))
+# layer-1 gather = the LARGER of the two batch_gather_kernel launches per step (+ its parts launch)
+out = {}
+main = [t for k, v in traffic.items() if "batch_gather_kernel" in k for t in v]
+parts = [t for k, v in traffic.items() if "batch_gather_parts" in k for t in v]
+if main:
+    l1 = max(t[1] for t in main)
+    p1 = max((t[1] for t in parts), default=0.0)
+    out["gather_l1_dram_bytes_per_launch"] = (l1 + p1) * 1e9
+    out["gather_l1_main_kernel_dram_GB"] = l1
+    out["gather_l1_parts_kernel_dram_GB"] = p1
+    out["source"] = f"profiles/{tag}_kernels.md"
+json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+print(json.dumps(out))

@@ -47,7 +47,8 @@ def _setup(ctx, dev, n, e, F, directed, seed, gen=powerlaw_edges):
 
 
 @pytest.mark.parametrize("directed", [True, False])
-@pytest.mark.parametrize("fan,dims", [([3, 2], [16, 8, 4]), ([15, 10], [100, 64, 47]), ([4, 3, 2], [12, 8, 8, 5]), ([5], [7, 3])])
+@pytest.mark.parametrize("fan,dims", [([3, 2], [16, 8, 4]), ([15, 10], [100, 64, 47]), ([4, 3, 2], [12, 8, 8, 5]), ([5], [7, 3]),
+                                      ([5, 4], [200, 300, 24]), ([3, 2], [600, 8, 4]), ([40, 3], [128, 256, 16])])
 def test_collate_and_forward_match_oracle(env, directed, fan, dims):
     import torch
 
