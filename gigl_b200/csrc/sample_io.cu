@@ -1,0 +1,493 @@
+// sample_io.cu - host side of the sampler's file contract (no device code in this file):
+//   * TFRecord framing (u64 length, masked crc32c of the length, payload, masked crc32c of the payload) as
+//     written by the reference through the Spark TFRecord connector with recordType=ByteArray
+//     (scala/common/src/main/scala/utils/TFRecordIO.scala:53-69) and read with tf.data.TFRecordDataset
+//     (python/gigl/src/training/v1/lib/data_loaders/tf_records_iterable_dataset.py:78);
+//   * tf.Example decoding of the preprocessed node / edge tables
+//     (loadNodeDataframeIntoSparkSql / loadEdgeDataframeIntoSparkSql, SGSPureSparkV1Task.scala:52-311);
+//   * hydration + protobuf encoding of the sampled index sets into RootedNodeNeighborhood /
+//     SupervisedNodeClassificationSample messages
+//     (proto/snapchat/research/gbml/training_samples_schema.proto:16-31, graph_schema.proto:5-31;
+//     reference: createKthHydratedNeighborhood / createSubgraph / castToRootedNodeNeighborhoodProtoSchema,
+//     SGSPureSparkV1Task.scala:496-820, 1019-1040, and SupervisedNodeClassificationTask.scala:166-236, 320-337).
+// Output volume (about (1 + f1 + f1*f2) * F * 4 bytes per root) makes this a host-bandwidth job: the
+// encoder is two OpenMP passes over the roots (sizes, then bytes) into one contiguous buffer.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/gigl_b200.h"
+
+namespace {
+
+// ---- crc32c (Castagnoli), slicing-by-8 tables + SSE4.2 when the CPU has it ---------------------
+uint32_t g_crc_tab[8][256];
+bool g_crc_init = false;
+
+void crc_init() {
+    if (g_crc_init) return;
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
+        g_crc_tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+        for (int t = 1; t < 8; ++t) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xFF];
+    g_crc_init = true;
+}
+
+uint32_t crc32c_sw(uint32_t crc, const uint8_t* p, size_t n) {
+    crc = ~crc;
+    while (n >= 8) {
+        uint64_t v;
+        memcpy(&v, p, 8);
+        v ^= crc;
+        crc = g_crc_tab[7][v & 0xFF] ^ g_crc_tab[6][(v >> 8) & 0xFF] ^ g_crc_tab[5][(v >> 16) & 0xFF] ^ g_crc_tab[4][(v >> 24) & 0xFF] ^
+              g_crc_tab[3][(v >> 32) & 0xFF] ^ g_crc_tab[2][(v >> 40) & 0xFF] ^ g_crc_tab[1][(v >> 48) & 0xFF] ^ g_crc_tab[0][v >> 56];
+        p += 8;
+        n -= 8;
+    }
+    while (n--) crc = (crc >> 8) ^ g_crc_tab[0][(crc ^ *p++) & 0xFF];
+    return ~crc;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("sse4.2"))) uint32_t crc32c_hw(uint32_t crc, const uint8_t* p, size_t n) {
+    uint64_t c = (uint32_t)~crc;
+    while (n >= 8) {
+        uint64_t v;
+        memcpy(&v, p, 8);
+        c = __builtin_ia32_crc32di(c, v);
+        p += 8;
+        n -= 8;
+    }
+    uint32_t c32 = (uint32_t)c;
+    while (n--) c32 = __builtin_ia32_crc32qi(c32, *p++);
+    return ~c32;
+}
+#endif
+
+uint32_t crc32c(const uint8_t* p, size_t n) {
+#if defined(__x86_64__)
+    static const bool hw = __builtin_cpu_supports("sse4.2");
+    if (hw) return crc32c_hw(0, p, n);
+#endif
+    crc_init();
+    return crc32c_sw(0, p, n);
+}
+
+inline uint32_t mask_crc(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xA282EAD8u; }
+
+// ---- protobuf wire helpers ----------------------------------------------------------------------
+inline int varint_size(uint64_t v) {
+    int n = 1;
+    while (v >= 0x80) {
+        v >>= 7;
+        ++n;
+    }
+    return n;
+}
+inline uint8_t* put_varint(uint8_t* p, uint64_t v) {
+    while (v >= 0x80) {
+        *p++ = (uint8_t)(v | 0x80);
+        v >>= 7;
+    }
+    *p++ = (uint8_t)v;
+    return p;
+}
+inline bool get_varint(const uint8_t*& p, const uint8_t* end, uint64_t& v) {
+    v = 0;
+    for (int shift = 0; shift < 64 && p < end; shift += 7) {
+        const uint8_t b = *p++;
+        v |= (uint64_t)(b & 0x7F) << shift;
+        if (!(b & 0x80)) return true;
+    }
+    return false;
+}
+
+// Node { uint32 node_id = 1; optional uint32 condensed_node_type = 2; repeated float feature_values = 3 [packed]; }
+inline size_t node_size(uint32_t id, int32_t type, int F) {
+    size_t n = 0;
+    if (id != 0) n += 1 + varint_size(id);  // proto3 implicit presence: 0 is not written
+    if (type >= 0) n += 1 + varint_size((uint32_t)type);
+    if (F > 0) n += 1 + varint_size((uint64_t)F * 4) + (size_t)F * 4;
+    return n;
+}
+inline uint8_t* put_node(uint8_t* p, uint32_t id, int32_t type, const float* feat, int F) {
+    if (id != 0) {
+        *p++ = 0x08;
+        p = put_varint(p, id);
+    }
+    if (type >= 0) {
+        *p++ = 0x10;
+        p = put_varint(p, (uint32_t)type);
+    }
+    if (F > 0) {
+        *p++ = 0x1A;
+        p = put_varint(p, (uint64_t)F * 4);
+        memcpy(p, feat, (size_t)F * 4);  // little-endian host
+        p += (size_t)F * 4;
+    }
+    return p;
+}
+// Edge { uint32 src_node_id = 1; uint32 dst_node_id = 2; optional uint32 condensed_edge_type = 3; repeated float feature_values = 4; }
+inline size_t edge_size(uint32_t src, uint32_t dst, int32_t type) {
+    size_t n = 0;
+    if (src != 0) n += 1 + varint_size(src);
+    if (dst != 0) n += 1 + varint_size(dst);
+    if (type >= 0) n += 1 + varint_size((uint32_t)type);
+    return n;
+}
+inline uint8_t* put_edge(uint8_t* p, uint32_t src, uint32_t dst, int32_t type) {
+    if (src != 0) {
+        *p++ = 0x08;
+        p = put_varint(p, src);
+    }
+    if (dst != 0) {
+        *p++ = 0x10;
+        p = put_varint(p, dst);
+    }
+    if (type >= 0) {
+        *p++ = 0x18;
+        p = put_varint(p, (uint32_t)type);
+    }
+    return p;
+}
+
+struct RootPlan {
+    std::vector<uint32_t> nodes;                       // distinct, first-seen order: hop 1.., then the root if new
+    std::vector<std::pair<uint32_t, uint32_t>> edges;  // (src = hop-k node, dst = hop-(k-1) node), one per filled slot
+};
+
+// Walks the padded tree of root r (layout: include/gigl_b200.h).
+void plan_root(int64_t r, const int32_t* roots, const int32_t* fanouts, int n_hops, const int32_t* const* nbr, RootPlan& out) {
+    out.nodes.clear();
+    out.edges.clear();
+    int64_t width_prev = 1;
+    for (int h = 0; h < n_hops; ++h) {
+        const int f = fanouts[h];
+        const int32_t* cur = nbr[h];
+        for (int64_t ps = 0; ps < width_prev; ++ps) {
+            const int64_t pslot = r * width_prev + ps;
+            const int32_t parent = (h == 0) ? roots[r] : nbr[h - 1][pslot];
+            if (parent < 0) continue;
+            for (int j = 0; j < f; ++j) {
+                const int32_t c = cur[pslot * f + j];
+                if (c < 0) continue;
+                out.edges.emplace_back((uint32_t)c, (uint32_t)parent);
+                out.nodes.push_back((uint32_t)c);
+            }
+        }
+        width_prev *= f;
+    }
+    out.nodes.push_back((uint32_t)roots[r]);
+    // array_distinct keeping first occurrences
+    std::vector<std::pair<uint32_t, uint32_t>> tmp(out.nodes.size());
+    for (size_t i = 0; i < out.nodes.size(); ++i) tmp[i] = {out.nodes[i], (uint32_t)i};
+    std::sort(tmp.begin(), tmp.end());
+    size_t m = 0;
+    for (size_t i = 0; i < tmp.size(); ++i)
+        if (i == 0 || tmp[i].first != tmp[i - 1].first) tmp[m++] = tmp[i];
+    tmp.resize(m);
+    std::sort(tmp.begin(), tmp.end(), [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) { return a.second < b.second; });
+    out.nodes.resize(m);
+    for (size_t i = 0; i < m; ++i) out.nodes[i] = tmp[i].first;
+}
+
+struct Sizes {
+    size_t root_node, graph, labels, message;
+};
+
+Sizes message_sizes(const RootPlan& pl, uint32_t root, int32_t ntype, int32_t etype, int F, bool with_label, int32_t label,
+                    size_t label_type_len) {
+    Sizes s{};
+    s.root_node = node_size(root, ntype, F);
+    s.graph = 0;
+    for (uint32_t v : pl.nodes) {
+        const size_t ns = node_size(v, ntype, F);
+        s.graph += 1 + varint_size(ns) + ns;
+    }
+    for (const auto& e : pl.edges) {
+        const size_t es = edge_size(e.first, e.second, etype);
+        s.graph += 1 + varint_size(es) + es;
+    }
+    s.labels = 0;
+    if (with_label) {
+        size_t ls = 0;
+        if (label_type_len) ls += 1 + varint_size(label_type_len) + label_type_len;
+        if (label != 0) ls += 1 + varint_size((uint64_t)(int64_t)label);  // int32: negative values sign-extend to 10 bytes
+        s.labels = 1 + varint_size(ls) + ls;
+    }
+    s.message = 1 + varint_size(s.root_node) + s.root_node;
+    if (s.graph > 0) s.message += 1 + varint_size(s.graph) + s.graph;
+    s.message += s.labels;
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t gigl_crc32c_masked(const void* data, int64_t n) { return mask_crc(crc32c((const uint8_t*)data, (size_t)n)); }
+
+void gigl_free_host(void* p) { free(p); }
+
+int gigl_encode_samples_host(int32_t kind, int64_t n_roots, const int32_t* roots, const int32_t* fanouts, int32_t n_hops,
+                             const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
+                             int32_t condensed_edge_type, const int32_t* labels, const char* label_type, int32_t tfrecord_framing,
+                             uint8_t** out, int64_t* out_bytes, int64_t* record_offsets) {
+    if (!out || !out_bytes || n_roots < 0 || n_hops < 1 || n_hops > GIGL_MAX_HOPS || !fanouts || !nbr || (n_roots > 0 && !roots))
+        return GIGL_E_INVALID;
+    if (kind != 0 && kind != 1) return GIGL_E_INVALID;
+    if (kind == 1 && !labels) return GIGL_E_INVALID;
+    if (F < 0 || (F > 0 && !x)) return GIGL_E_INVALID;
+    *out = nullptr;
+    *out_bytes = 0;
+    const size_t lt_len = label_type ? strlen(label_type) : 0;
+    std::vector<int64_t> rec((size_t)n_roots + 1, 0);
+    const int64_t no_label = INT32_MIN;
+    // pass 1: sizes
+#pragma omp parallel
+    {
+        RootPlan pl;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t r = 0; r < n_roots; ++r) {
+            const uint32_t root = (uint32_t)roots[r];
+            int32_t label = 0;
+            if (kind == 1) {
+                label = labels[root];
+                if (label == no_label) {  // unlabeled node: no SupervisedNodeClassificationSample (inner join with the labels)
+                    rec[(size_t)r + 1] = 0;
+                    continue;
+                }
+            }
+            plan_root(r, roots, fanouts, n_hops, nbr, pl);
+            const Sizes s = message_sizes(pl, root, condensed_node_type, condensed_edge_type, F, kind == 1, label, lt_len);
+            rec[(size_t)r + 1] = (int64_t)s.message + (tfrecord_framing ? 16 : 0);
+        }
+    }
+    for (int64_t r = 0; r < n_roots; ++r) rec[(size_t)r + 1] += rec[(size_t)r];
+    const int64_t total = rec[(size_t)n_roots];
+    uint8_t* buf = (uint8_t*)malloc((size_t)(total > 0 ? total : 1));
+    if (!buf) return GIGL_E_NOMEM;
+    // pass 2: bytes
+#pragma omp parallel
+    {
+        RootPlan pl;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t r = 0; r < n_roots; ++r) {
+            if (rec[(size_t)r + 1] == rec[(size_t)r]) continue;
+            const uint32_t root = (uint32_t)roots[r];
+            const int32_t label = kind == 1 ? labels[root] : 0;
+            plan_root(r, roots, fanouts, n_hops, nbr, pl);
+            const Sizes s = message_sizes(pl, root, condensed_node_type, condensed_edge_type, F, kind == 1, label, lt_len);
+            uint8_t* p = buf + rec[(size_t)r];
+            uint8_t* payload = p;
+            if (tfrecord_framing) {
+                const uint64_t len = s.message;
+                memcpy(p, &len, 8);
+                const uint32_t c = mask_crc(crc32c(p, 8));
+                memcpy(p + 8, &c, 4);
+                p += 12;
+                payload = p;
+            }
+            // root_node = 1
+            *p++ = 0x0A;
+            p = put_varint(p, s.root_node);
+            p = put_node(p, root, condensed_node_type, F > 0 ? x + (size_t)root * F : nullptr, F);
+            // neighborhood = 2 : Graph { repeated Node nodes = 2; repeated Edge edges = 3; }
+            if (s.graph > 0) {
+                *p++ = 0x12;
+                p = put_varint(p, s.graph);
+                for (uint32_t v : pl.nodes) {
+                    *p++ = 0x12;
+                    p = put_varint(p, node_size(v, condensed_node_type, F));
+                    p = put_node(p, v, condensed_node_type, F > 0 ? x + (size_t)v * F : nullptr, F);
+                }
+                for (const auto& e : pl.edges) {
+                    *p++ = 0x1A;
+                    p = put_varint(p, edge_size(e.first, e.second, condensed_edge_type));
+                    p = put_edge(p, e.first, e.second, condensed_edge_type);
+                }
+            }
+            // root_node_labels = 3 : Label { string label_type = 1; int32 label = 2; }
+            if (kind == 1) {
+                size_t ls = 0;
+                if (lt_len) ls += 1 + varint_size(lt_len) + lt_len;
+                if (label != 0) ls += 1 + varint_size((uint64_t)(int64_t)label);
+                *p++ = 0x1A;
+                p = put_varint(p, ls);
+                if (lt_len) {
+                    *p++ = 0x0A;
+                    p = put_varint(p, lt_len);
+                    memcpy(p, label_type, lt_len);
+                    p += lt_len;
+                }
+                if (label != 0) {
+                    *p++ = 0x10;
+                    p = put_varint(p, (uint64_t)(int64_t)label);
+                }
+            }
+            if (tfrecord_framing) {
+                const uint32_t c = mask_crc(crc32c(payload, (size_t)(p - payload)));
+                memcpy(p, &c, 4);
+                p += 4;
+            }
+        }
+    }
+    if (record_offsets) memcpy(record_offsets, rec.data(), sizeof(int64_t) * ((size_t)n_roots + 1));
+    *out = buf;
+    *out_bytes = total;
+    return GIGL_OK;
+}
+
+// ---- TFRecord reading + tf.Example decoding ----------------------------------------------------------
+// Splits a TFRecord byte stream into records; verifies both checksums when verify != 0.
+// offsets / lengths: caller arrays of capacity max_records; returns the number of records, or < 0.
+int64_t gigl_tfrecord_index_host(const uint8_t* data, int64_t n_bytes, int32_t verify, int64_t* offsets, int64_t* lengths,
+                                 int64_t max_records) {
+    if (!data || n_bytes < 0) return GIGL_E_INVALID;
+    int64_t pos = 0, n = 0;
+    while (pos < n_bytes) {
+        if (pos + 12 > n_bytes) return GIGL_E_INVALID;
+        uint64_t len;
+        uint32_t c;
+        memcpy(&len, data + pos, 8);
+        memcpy(&c, data + pos + 8, 4);
+        if (verify && c != mask_crc(crc32c(data + pos, 8))) return GIGL_E_INVALID;
+        if (len > (uint64_t)(n_bytes - pos - 16)) return GIGL_E_INVALID;
+        if (verify) {
+            memcpy(&c, data + pos + 12 + len, 4);
+            if (c != mask_crc(crc32c(data + pos + 12, (size_t)len))) return GIGL_E_INVALID;
+        }
+        if (offsets && lengths) {
+            if (n >= max_records) return GIGL_E_OVERFLOW;
+            offsets[n] = pos + 12;
+            lengths[n] = (int64_t)len;
+        }
+        ++n;
+        pos += 16 + (int64_t)len;
+    }
+    return n;
+}
+
+// Decodes one named feature of every tf.Example record into a dense column.
+// dtype: 0 = int64 (Int64List, written to out_i64), 1 = float (FloatList -> out_f32; an Int64List is cast, which is what
+// `cast(col as array<float>)` does in loadNodeDataframeIntoSparkSql :90-104).  width = values per record (records with a
+// different count are an error).  Returns GIGL_OK, or GIGL_E_RANGE if a record lacks the feature.
+int gigl_examples_column_host(const uint8_t* data, int64_t n_records, const int64_t* offsets, const int64_t* lengths,
+                              const char* name, int32_t dtype, int32_t width, int64_t* out_i64, float* out_f32) {
+    if (!data || !offsets || !lengths || !name || width < 1 || (dtype == 0 && !out_i64) || (dtype == 1 && !out_f32) || dtype < 0 || dtype > 1)
+        return GIGL_E_INVALID;
+    const size_t name_len = strlen(name);
+    int rc_all = GIGL_OK;
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < n_records; ++r) {
+        const uint8_t* p = data + offsets[r];
+        const uint8_t* end = p + lengths[r];
+        bool found = false;
+        int rc = GIGL_OK;
+        // Example { Features features = 1; }  Features { map<string, Feature> feature = 1; }
+        while (p < end && rc == GIGL_OK && !found) {
+            uint64_t tag, len;
+            if (!get_varint(p, end, tag)) { rc = GIGL_E_INVALID; break; }
+            if ((tag & 7) != 2) { rc = GIGL_E_INVALID; break; }
+            if (!get_varint(p, end, len) || len > (uint64_t)(end - p)) { rc = GIGL_E_INVALID; break; }
+            const uint8_t* fend = p + len;
+            if ((tag >> 3) != 1) { p = fend; continue; }
+            const uint8_t* q = p;  // Features
+            while (q < fend && !found) {
+                uint64_t t2, l2;
+                if (!get_varint(q, fend, t2) || (t2 & 7) != 2 || !get_varint(q, fend, l2) || l2 > (uint64_t)(fend - q)) { rc = GIGL_E_INVALID; break; }
+                const uint8_t* eend = q + l2;  // one map entry { string key = 1; Feature value = 2; }
+                const uint8_t* e = q;
+                const uint8_t* key = nullptr;
+                size_t key_len = 0;
+                const uint8_t* val = nullptr;
+                size_t val_len = 0;
+                while (e < eend) {
+                    uint64_t t3, l3;
+                    if (!get_varint(e, eend, t3) || (t3 & 7) != 2 || !get_varint(e, eend, l3) || l3 > (uint64_t)(eend - e)) { rc = GIGL_E_INVALID; break; }
+                    if ((t3 >> 3) == 1) { key = e; key_len = (size_t)l3; }
+                    if ((t3 >> 3) == 2) { val = e; val_len = (size_t)l3; }
+                    e += l3;
+                }
+                if (rc != GIGL_OK) break;
+                if (key && key_len == name_len && memcmp(key, name, name_len) == 0) {
+                    found = true;
+                    // Feature { oneof kind { BytesList bytes_list = 1; FloatList float_list = 2; Int64List int64_list = 3; } }
+                    const uint8_t* v = val;
+                    const uint8_t* vend = val + val_len;
+                    int count = 0;
+                    while (v && v < vend && rc == GIGL_OK) {
+                        uint64_t t4, l4;
+                        if (!get_varint(v, vend, t4) || (t4 & 7) != 2 || !get_varint(v, vend, l4) || l4 > (uint64_t)(vend - v)) { rc = GIGL_E_INVALID; break; }
+                        const uint8_t* lend = v + l4;
+                        const int kindf = (int)(t4 >> 3);
+                        // FloatList { repeated float value = 1 [packed] }  Int64List { repeated int64 value = 1 [packed] }
+                        const uint8_t* w = v;
+                        while (w < lend && rc == GIGL_OK) {
+                            uint64_t t5;
+                            if (!get_varint(w, lend, t5)) { rc = GIGL_E_INVALID; break; }
+                            if (kindf == 2) {
+                                if ((t5 & 7) == 2) {  // packed floats
+                                    uint64_t l5;
+                                    if (!get_varint(w, lend, l5) || l5 > (uint64_t)(lend - w) || (l5 & 3)) { rc = GIGL_E_INVALID; break; }
+                                    for (uint64_t i = 0; i < l5; i += 4) {
+                                        float fv;
+                                        memcpy(&fv, w + i, 4);
+                                        if (count < width) { if (dtype == 1) out_f32[r * width + count] = fv; else out_i64[r * width + count] = (int64_t)fv; }
+                                        ++count;
+                                    }
+                                    w += l5;
+                                } else if ((t5 & 7) == 5) {
+                                    if (lend - w < 4) { rc = GIGL_E_INVALID; break; }
+                                    float fv;
+                                    memcpy(&fv, w, 4);
+                                    w += 4;
+                                    if (count < width) { if (dtype == 1) out_f32[r * width + count] = fv; else out_i64[r * width + count] = (int64_t)fv; }
+                                    ++count;
+                                } else { rc = GIGL_E_INVALID; }
+                            } else if (kindf == 3) {
+                                if ((t5 & 7) == 2) {  // packed varints
+                                    uint64_t l5;
+                                    if (!get_varint(w, lend, l5) || l5 > (uint64_t)(lend - w)) { rc = GIGL_E_INVALID; break; }
+                                    const uint8_t* pend = w + l5;
+                                    while (w < pend) {
+                                        uint64_t iv;
+                                        if (!get_varint(w, pend, iv)) { rc = GIGL_E_INVALID; break; }
+                                        if (count < width) { if (dtype == 0) out_i64[r * width + count] = (int64_t)iv; else out_f32[r * width + count] = (float)(int64_t)iv; }
+                                        ++count;
+                                    }
+                                } else if ((t5 & 7) == 0) {
+                                    uint64_t iv;
+                                    if (!get_varint(w, lend, iv)) { rc = GIGL_E_INVALID; break; }
+                                    if (count < width) { if (dtype == 0) out_i64[r * width + count] = (int64_t)iv; else out_f32[r * width + count] = (float)(int64_t)iv; }
+                                    ++count;
+                                } else { rc = GIGL_E_INVALID; }
+                            } else {
+                                rc = GIGL_E_INVALID;  // bytes_list columns are not numeric
+                            }
+                        }
+                        v = lend;
+                    }
+                    if (rc == GIGL_OK && count != width) rc = GIGL_E_INVALID;
+                }
+                q = eend;
+            }
+            p = fend;
+        }
+        if (rc == GIGL_OK && !found) rc = GIGL_E_RANGE;
+        if (rc != GIGL_OK) {
+#pragma omp critical
+            rc_all = rc;
+        }
+    }
+    return rc_all;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+"""Host mirror of the sampler's file contract (include/gigl_b200.h, "the sampler's file contract"):
+TFRecord files of tf.Example rows in, TFRecord files of serialized sample protos out.
+
+Reference: scala/common/src/main/scala/utils/TFRecordIO.scala:21-69 (read / write),
+SGSPureSparkV1Task.scala:52-311 (node / edge table loading), :496-820 and :1019-1040 (hydration, proto schema).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import GiglError
+
+INT32_MIN = -(2 ** 31)
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise GiglError(rc, what)
+
+
+def crc32c_masked(data: bytes) -> int:
+    return int(_capi.lib().gigl_crc32c_masked(data, len(data)))
+
+
+def list_tfrecord_files(uri_prefix: str) -> List[str]:
+    """A `tfrecordUriPrefix` names a directory (or a file-name prefix) of TFRecord part files."""
+    p = uri_prefix[len("file://"):] if uri_prefix.startswith("file://") else uri_prefix
+    if os.path.isdir(p):
+        files = sorted(f for f in glob.glob(os.path.join(p, "*")) if os.path.isfile(f) and not os.path.basename(f).startswith(("_", ".")))
+    else:
+        files = sorted(f for f in glob.glob(p + "*") if os.path.isfile(f))
+    if not files:
+        raise FileNotFoundError(f"no TFRecord files under {uri_prefix!r}")
+    return files
+
+
+class ExampleTable:
+    """All tf.Example records of a set of TFRecord files, decoded column by column in native code."""
+
+    def __init__(self, data: bytes, verify: bool = True):
+        self._L = _capi.lib()
+        self.data = np.frombuffer(data, dtype=np.uint8)
+        n = self._L.gigl_tfrecord_index_host(self.data.ctypes.data, len(self.data), int(verify), None, None, 0)
+        if n < 0:
+            raise GiglError(int(n), "malformed TFRecord stream (framing or crc32c)")
+        self.n = int(n)
+        self.offsets = np.zeros(max(self.n, 1), dtype=np.int64)
+        self.lengths = np.zeros(max(self.n, 1), dtype=np.int64)
+        if self.n:
+            m = self._L.gigl_tfrecord_index_host(self.data.ctypes.data, len(self.data), 0, self.offsets.ctypes.data,
+                                                 self.lengths.ctypes.data, self.n)
+            assert m == self.n
+
+    @classmethod
+    def from_files(cls, files: Sequence[str], verify: bool = True) -> "ExampleTable":
+        return cls(b"".join(open(f, "rb").read() for f in files), verify)
+
+    def record(self, i: int) -> bytes:
+        o, l = int(self.offsets[i]), int(self.lengths[i])
+        return self.data[o:o + l].tobytes()
+
+    def width(self, name: str) -> int:
+        """Values per record of feature `name` (probed on the first record)."""
+        if self.n == 0:
+            return 1
+        feats = parse_example(self.record(0))
+        if name not in feats:
+            raise KeyError(f"feature {name!r} not in the tf.Example records (have {sorted(feats)})")
+        return max(len(feats[name]), 1)
+
+    def column(self, name: str, dtype: str, width: Optional[int] = None) -> np.ndarray:
+        """dtype 'int64' or 'float32' -> array [n] (width 1) or [n, width]."""
+        w = self.width(name) if width is None else width
+        if dtype == "int64":
+            out = np.zeros((self.n, w), dtype=np.int64)
+            rc = self._L.gigl_examples_column_host(self.data.ctypes.data, self.n, self.offsets.ctypes.data, self.lengths.ctypes.data,
+                                                   name.encode(), 0, w, out.ctypes.data, None)
+        else:
+            out = np.zeros((self.n, w), dtype=np.float32)
+            rc = self._L.gigl_examples_column_host(self.data.ctypes.data, self.n, self.offsets.ctypes.data, self.lengths.ctypes.data,
+                                                   name.encode(), 1, w, None, out.ctypes.data)
+        _check(rc, f"decoding tf.Example feature {name!r}")
+        return out[:, 0] if w == 1 and width is None else out
+
+
+def encode_samples(roots, fanouts, nbr, x: Optional[np.ndarray] = None, kind: str = "rnn", condensed_node_type: int = 0,
+                   condensed_edge_type: int = 0, labels: Optional[np.ndarray] = None, label_type: str = "",
+                   tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
+    """Padded-tree index sets -> serialized RootedNodeNeighborhood ('rnn') or SupervisedNodeClassificationSample ('snc')
+    messages, one per root.  Returns (bytes, record_offsets [n_roots + 1])."""
+    L = _capi.lib()
+    roots = np.ascontiguousarray(roots, dtype=np.int32)
+    fan = np.ascontiguousarray(fanouts, dtype=np.int32)
+    nbr = [np.ascontiguousarray(a, dtype=np.int32) for a in nbr]
+    F = 0
+    xp = None
+    if x is not None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        F = x.shape[1]
+        xp = x.ctypes.data
+    lp = None
+    if kind == "snc":
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        lp = labels.ctypes.data
+    pn = (C.c_void_p * len(fan))(*[a.ctypes.data for a in nbr])
+    out = C.c_void_p()
+    nbytes = C.c_int64()
+    offs = np.zeros(len(roots) + 1, dtype=np.int64)
+    rc = L.gigl_encode_samples_host(0 if kind == "rnn" else 1, len(roots), roots.ctypes.data, fan.ctypes.data, len(fan), pn, xp, F,
+                                    condensed_node_type, condensed_edge_type, lp, label_type.encode(), int(tfrecord_framing),
+                                    C.byref(out), C.byref(nbytes), offs.ctypes.data)
+    _check(rc, "gigl_encode_samples_host")
+    try:
+        data = C.string_at(out.value, nbytes.value)
+    finally:
+        L.gigl_free_host(out)
+    return data, offs
+
+
+# ---- a minimal protobuf wire reader (tests, tooling): no generated code needed --------------------
+def _varint(buf: bytes, pos: int) -> Tuple[int, int]:
+    v = shift = 0
+    while True:
+        b = buf[pos]
+        pos += 1
+        v |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return v, pos
+        shift += 7
+
+
+def parse_fields(buf: bytes) -> List[Tuple[int, int, object]]:
+    """[(field number, wire type, value)]: varints as int, length-delimited as bytes, fixed32/64 as bytes."""
+    out, pos = [], 0
+    while pos < len(buf):
+        tag, pos = _varint(buf, pos)
+        fn, wt = tag >> 3, tag & 7
+        if wt == 0:
+            v, pos = _varint(buf, pos)
+        elif wt == 2:
+            ln, pos = _varint(buf, pos)
+            v = buf[pos:pos + ln]
+            pos += ln
+        elif wt == 5:
+            v = buf[pos:pos + 4]
+            pos += 4
+        elif wt == 1:
+            v = buf[pos:pos + 8]
+            pos += 8
+        else:
+            raise ValueError(f"unsupported wire type {wt}")
+        out.append((fn, wt, v))
+    return out
+
+
+def parse_example(buf: bytes) -> Dict[str, list]:
+    """tf.Example -> {feature name: list of python values}."""
+    feats = {}
+    for fn, _, features in parse_fields(buf):
+        if fn != 1:
+            continue
+        for _, _, entry in parse_fields(features):
+            key, val = None, b""
+            for f2, _, v in parse_fields(entry):
+                if f2 == 1:
+                    key = v.decode()
+                elif f2 == 2:
+                    val = v
+            vals = []
+            for kind, _, lst in parse_fields(val):
+                for _, wt, v in parse_fields(lst):
+                    if kind == 2:  # FloatList
+                        vals += list(np.frombuffer(v, dtype="<f4")) if wt == 2 else [float(np.frombuffer(v, dtype="<f4")[0])]
+                    elif kind == 3:  # Int64List
+                        if wt == 2:
+                            p = 0
+                            while p < len(v):
+                                iv, p = _varint(v, p)
+                                vals.append(iv - (1 << 64) if iv >> 63 else iv)
+                        else:
+                            vals.append(v - (1 << 64) if v >> 63 else v)
+                    else:
+                        vals.append(v)
+            feats[key] = vals
+    return feats
+
+
+def _parse_node(buf: bytes) -> dict:
+    d = {"node_id": 0, "condensed_node_type": None, "feature_values": []}
+    for fn, wt, v in parse_fields(buf):
+        if fn == 1:
+            d["node_id"] = v
+        elif fn == 2:
+            d["condensed_node_type"] = v
+        elif fn == 3:
+            d["feature_values"] += list(np.frombuffer(v, dtype="<f4")) if wt == 2 else [float(np.frombuffer(v, dtype="<f4")[0])]
+    return d
+
+
+def _parse_edge(buf: bytes) -> dict:
+    d = {"src_node_id": 0, "dst_node_id": 0, "condensed_edge_type": None, "feature_values": []}
+    for fn, wt, v in parse_fields(buf):
+        if fn == 1:
+            d["src_node_id"] = v
+        elif fn == 2:
+            d["dst_node_id"] = v
+        elif fn == 3:
+            d["condensed_edge_type"] = v
+        elif fn == 4:
+            d["feature_values"] += list(np.frombuffer(v, dtype="<f4")) if wt == 2 else [float(np.frombuffer(v, dtype="<f4")[0])]
+    return d
+
+
+def parse_sample(buf: bytes) -> dict:
+    """RootedNodeNeighborhood / SupervisedNodeClassificationSample bytes -> plain dict."""
+    d = {"root_node": None, "nodes": [], "edges": [], "root_node_labels": []}
+    for fn, _, v in parse_fields(buf):
+        if fn == 1:
+            d["root_node"] = _parse_node(v)
+        elif fn == 2:
+            for f2, _, g in parse_fields(v):
+                if f2 == 2:
+                    d["nodes"].append(_parse_node(g))
+                elif f2 == 3:
+                    d["edges"].append(_parse_edge(g))
+        elif fn == 3:
+            lab = {"label_type": "", "label": 0}
+            for f2, _, g in parse_fields(v):
+                if f2 == 1:
+                    lab["label_type"] = g.decode()
+                elif f2 == 2:
+                    lab["label"] = g - (1 << 64) if g >> 63 else g
+            d["root_node_labels"].append(lab)
+    return d
+
+
+def split_tfrecords(data: bytes, verify: bool = True) -> List[bytes]:
+    t = ExampleTable(data, verify)
+    return [t.record(i) for i in range(t.n)]

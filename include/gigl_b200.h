@@ -297,6 +297,44 @@ int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_mode
                               int64_t n_roots, const int32_t* fanouts, int32_t n_hops, int32_t base_seed,
                               int32_t first_call_no, float* out, int32_t* const* nbr, int32_t* const* cnt);
 
+/* ---- the sampler's file contract: TFRecord + tf.Example + sample protos (host code) ----------- */
+
+/* masked crc32c of TFRecord framing: rotr15(crc32c(data)) + 0xA282EAD8 */
+uint32_t gigl_crc32c_masked(const void* data, int64_t n);
+/* frees buffers returned by gigl_encode_samples_host */
+void gigl_free_host(void* p);
+/*
+ * Hydrates the padded-tree index sets of gigl_sample_khop_host into serialized sample protos, one
+ * per root, in root order:
+ *   kind 0: RootedNodeNeighborhood { root_node, neighborhood { nodes, edges } }
+ *   kind 1: SupervisedNodeClassificationSample { ..., root_node_labels [{label_type, label}] } for the
+ *           roots that carry a label (labels[node] != INT32_MIN), as the reference's inner join does
+ * (proto/snapchat/research/gbml/training_samples_schema.proto:16-31; reference: SGSPureSparkV1Task.scala:496-820,
+ * 1019-1040, SupervisedNodeClassificationTask.scala:166-236).  nodes = array_distinct(hop nodes ++ root), every node
+ * with its feature row x[node, :] (x may be NULL with F = 0) and condensed_node_type (>= 0, or -1 to leave it
+ * unset); edges = one per filled tree slot, src = hop-k node, dst = its parent (:615-629), with
+ * condensed_edge_type.  tfrecord_framing != 0 wraps every message as a TFRecord (what
+ * TFRecordIO.writeDatasetToTfrecord emits, TFRecordIO.scala:53-69).  *out is malloc'd (gigl_free_host);
+ * record_offsets (optional, n_roots + 1) gives each root's byte range (empty for skipped roots).
+ */
+int gigl_encode_samples_host(int32_t kind, int64_t n_roots, const int32_t* roots, const int32_t* fanouts, int32_t n_hops,
+                             const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
+                             int32_t condensed_edge_type, const int32_t* labels, const char* label_type, int32_t tfrecord_framing,
+                             uint8_t** out, int64_t* out_bytes, int64_t* record_offsets);
+/*
+ * Splits a TFRecord byte stream into records (payload offsets / lengths, arrays of capacity max_records; pass NULL
+ * arrays to only count).  verify != 0 checks both masked crc32c fields.  Returns the record count or GIGL_E_*.
+ */
+int64_t gigl_tfrecord_index_host(const uint8_t* data, int64_t n_bytes, int32_t verify, int64_t* offsets, int64_t* lengths,
+                                 int64_t max_records);
+/*
+ * Decodes feature `name` of every tf.Example record into a dense column of `width` values per record: dtype 0 = int64
+ * (out_i64), dtype 1 = float (out_f32; an Int64List is cast, as `cast(col as array<float>)` does at
+ * SGSPureSparkV1Task.scala:90-104).  GIGL_E_RANGE if a record lacks the feature.
+ */
+int gigl_examples_column_host(const uint8_t* data, int64_t n_records, const int64_t* offsets, const int64_t* lengths,
+                              const char* name, int32_t dtype, int32_t width, int64_t* out_i64, float* out_f32);
+
 #ifdef __cplusplus
 }
 #endif
