@@ -59,6 +59,10 @@ SIGNATURES = {
     "gigl_gcn_conv_dev": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, i32]),
     "gigl_gcn_conv_host": (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i32]),
     "gigl_linear_dev": (C.c_int, [vp, i64, i32, i32, vp, i64, vp, i64, vp, vp, i64, i32]),
+    "gigl_sage_conv_train_fwd_dev": (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+    "gigl_sage_conv_bwd_dev": (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+    "gigl_gcn_conv_bwd_dev": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+    "gigl_linear_tn_dev": (C.c_int, [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, i32]),
     "gigl_graph_set_features_host": (C.c_int, [vp, vp, i32]),
     "gigl_graph_set_features_dev": (C.c_int, [vp, vp, i32]),
     "gigl_graph_features_dev": (C.c_int, [vp, pvp, C.POINTER(i32)]),

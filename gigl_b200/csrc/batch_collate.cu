@@ -268,12 +268,15 @@ __device__ __forceinline__ void gather_range(int row_beg, int e_beg, int e_end, 
 }
 
 // The projection runs as 3xTF32 on the tensor cores (gemm_tcgen05.cu): its A operand is stored
-// already split, hi = the value with the 13 low mantissa bits cleared (a TF32 number), lo = v - hi.
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// already split, hi = the value rounded to TF32, lo = (v - hi) rounded to TF32 (gigl_split_tf32).
 __device__ __forceinline__ void store_split4(float* __restrict__ hi, float* __restrict__ lo, int64_t off, float4 v) {
-    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    float4 h, l;
+    gigl_split_tf32(v.x, h.x, l.x);
+    gigl_split_tf32(v.y, h.y, l.y);
+    gigl_split_tf32(v.z, h.z, l.z);
+    gigl_split_tf32(v.w, h.w, l.w);
     *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    *reinterpret_cast<float4*>(lo + off) = l;
 }
 
 template <int LPR>
@@ -689,10 +692,8 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
             }
             const float m = acc * (1.0f / (float)(n_uniq > 1 ? n_uniq : 1));
             const float sv = __ldg(xsrc + self * ldx + c);
-            A_hi[row * ldA + c] = tf32_hi(m);
-            A_lo[row * ldA + c] = m - tf32_hi(m);
-            A_hi[row * ldA + F + c] = tf32_hi(sv);
-            A_lo[row * ldA + F + c] = sv - tf32_hi(sv);
+            gigl_split_tf32(m, A_hi[row * ldA + c], A_lo[row * ldA + c]);
+            gigl_split_tf32(sv, A_hi[row * ldA + F + c], A_lo[row * ldA + F + c]);
         }
     }
 }

@@ -618,6 +618,46 @@ int gigl_linear_dev(gigl_ctx* ctx, int64_t M, int32_t N, int32_t K, const float*
     return linear_tc_launch(ctx, M, N, K, a_hi, a_lo, ldp, w_hi, w_lo, ldp, bias_dev, C_dev, ldc, relu);
 }
 
+int gigl_sage_conv_train_fwd_dev(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O, const int64_t* rowptr_dev,
+                                 const int32_t* col_dev, const float* x_dev, const float* Wl_dev, const float* bl_dev,
+                                 const float* Wr_dev, float* out_dev, float* saved_dev, int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, n_rows_out == 0 || (rowptr_dev && x_dev && Wl_dev && Wr_dev && out_dev && saved_dev), "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sage_conv_train_fwd_launch(ctx, n, n_rows_out, F, O, rowptr_dev, col_dev, x_dev, Wl_dev, bl_dev, Wr_dev, out_dev, saved_dev, relu);
+}
+
+int gigl_sage_conv_bwd_dev(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O, const int64_t* rowptr_dev,
+                           const int64_t* t_rowptr_dev, const int32_t* t_col_dev, const float* saved_dev, const float* Wl_dev,
+                           const float* Wr_dev, const float* out_dev, const float* grad_out_dev, float* grad_x_dev,
+                           float* grad_Wl_dev, float* grad_bl_dev, float* grad_Wr_dev, int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, rowptr_dev && saved_dev && Wl_dev && Wr_dev && grad_out_dev, "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sage_conv_bwd_launch(ctx, n, n_rows_out, F, O, rowptr_dev, t_rowptr_dev, t_col_dev, saved_dev, Wl_dev, Wr_dev, out_dev,
+                                grad_out_dev, grad_x_dev, grad_Wl_dev, grad_bl_dev, grad_Wr_dev, relu);
+}
+
+int gigl_gcn_conv_bwd_dev(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr_dev, const int32_t* col_dev,
+                          const int64_t* t_rowptr_dev, const int32_t* t_col_dev, const float* x_dev, const float* W_dev,
+                          const float* out_dev, const float* grad_out_dev, float* grad_x_dev, float* grad_W_dev, float* grad_b_dev,
+                          int32_t relu) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, n == 0 || (rowptr_dev && x_dev && W_dev && grad_out_dev), "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return gcn_conv_bwd_launch(ctx, n, F, O, rowptr_dev, col_dev, t_rowptr_dev, t_col_dev, x_dev, W_dev, out_dev, grad_out_dev,
+                               grad_x_dev, grad_W_dev, grad_b_dev, relu);
+}
+
+int gigl_linear_tn_dev(gigl_ctx* ctx, int64_t R, int32_t M, int32_t N, const float* G_dev, int64_t ldg, const float* A_dev,
+                       int64_t lda, float* C_dev, int64_t ldc, int32_t accumulate) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, R >= 0 && M >= 1 && N >= 1 && ldg >= M && lda >= N && ldc >= N && C_dev, "bad sizes");
+    GIGL_CHECK(ctx, R == 0 || (G_dev && A_dev), "null pointer");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    return linear_tn_launch(ctx, R, M, N, G_dev, ldg, A_dev, lda, C_dev, ldc, accumulate);
+}
+
 int gigl_sage_model_create_host(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl,
                                 const float* const* bl, const float* const* Wr, gigl_sage_model** out) {
     if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");

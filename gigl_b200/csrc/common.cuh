@@ -116,6 +116,22 @@ int gigl_scratch(gigl_ctx* ctx, int slot, size_t bytes, void** out);
         (ctx)->launches++;                                                  \
     } while (0)
 
+#ifdef __CUDACC__
+// 3xTF32 operand split: hi = v rounded to nearest TF32 (10-bit mantissa), lo = (v - hi) rounded to TF32 as well, so
+// the tensor core's own truncation of its inputs is a no-op and every error term (lo rounding, the dropped lo*lo
+// product) is <= 2^-22 relative and unbiased - truncating instead gives a one-sided 2^-20 error that adds up linearly
+// along long reductions (measured on the backward pass of hub rows).
+__device__ __forceinline__ float gigl_tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void gigl_split_tf32(float v, float& hi, float& lo) {
+    hi = gigl_tf32_rna(v);
+    lo = gigl_tf32_rna(v - hi);
+}
+#endif
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- entry points implemented in the .cu files, called from capi.cu ---------------------
@@ -155,6 +171,22 @@ int sage_model_dims(const gigl_sage_model* m, int32_t* n_layers, int32_t* dims);
 int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, const float* A_lo, int64_t lda,
                      const float* W_hi, const float* W_lo, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);
 int split_tf32_launch(gigl_ctx* ctx, int64_t rows, int cols, const float* x, int64_t ldx, float* hi, float* lo, int64_t ldo);
+// gemm_tn_tcgen05.cu: C = G^T A (weight gradients; split-K over the rows, deterministic), column sums (bias gradient)
+int linear_tn_tc_launch(gigl_ctx* ctx, int64_t R, int M, int N, const float* G_hi, const float* G_lo, int64_t ldg, const float* A_hi,
+                        const float* A_lo, int64_t lda, float* C0, int64_t ldc0, int n0_valid, int n_split, float* C1, int64_t ldc1,
+                        int n1_valid, int accumulate);
+int colsum_launch(gigl_ctx* ctx, int64_t R, int M, const float* G, int64_t ldg, float* out, int accumulate);
+// sage_aggregate.cu: training forms (forward that keeps [mean | self], backward)
+int sage_conv_train_fwd_launch(gigl_ctx* ctx, int64_t n, int64_t m, int32_t F, int32_t O, const int64_t* rowptr, const int32_t* col,
+                               const float* x, const float* Wl, const float* bl, const float* Wr, float* out, float* A_save, int32_t relu);
+int sage_conv_bwd_launch(gigl_ctx* ctx, int64_t n, int64_t m, int32_t F, int32_t O, const int64_t* rowptr, const int64_t* t_rowptr,
+                         const int32_t* t_col, const float* A_save, const float* Wl, const float* Wr, const float* out,
+                         const float* grad_out, float* grad_x, float* grad_Wl, float* grad_bl, float* grad_Wr, int32_t relu);
+int gcn_conv_bwd_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr, const int32_t* col, const int64_t* t_rowptr,
+                        const int32_t* t_col, const float* x, const float* W, const float* out, const float* grad_out, float* grad_x,
+                        float* grad_W, float* grad_b, int32_t relu);
+int linear_tn_launch(gigl_ctx* ctx, int64_t R, int M, int N, const float* G, int64_t ldg, const float* A, int64_t lda, float* C,
+                     int64_t ldc, int accumulate);
 // sage_aggregate.cu: fp32 FFMA projection with explicit leading dimensions (M optionally read on the device)
 int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, int N, int K, const float* A, int64_t lda,
                            const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);

@@ -7,7 +7,7 @@
 //
 // Precision: the parity bound is 1e-5 relative on fp32 embeddings, which single-pass TF32
 // (10-bit mantissa) cannot meet, so every operand is split into two TF32 terms
-// (x = hi + lo, hi = x with the low 13 mantissa bits cleared, lo = x - hi, exact in fp32) and
+// (x ~ hi + lo, hi = x rounded to TF32, lo = (x - hi) rounded to TF32; common.cuh gigl_split_tf32) and
 // three tensor-core products are accumulated in fp32 in TMEM:  hi*hi + lo*hi + hi*lo  (3xTF32,
 // relative error ~2^-21).  The split of A is done by the producer of A (the gather kernel writes
 // both halves), the split of W once at model-creation time, so this kernel is a pure
@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace gigl {
 
@@ -31,76 +32,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;              // 32 fp32 = 128 bytes = one swizzle span
 constexpr int kUmmaK = 8;                // tf32
 constexpr int kGemmThreads = 192;
-constexpr uint32_t kSpinLimit = 1u << 27;  // bounded waits: a protocol bug traps instead of hanging the GPU
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > kSpinLimit) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, 128-byte swizzle: 8-row x 128-byte atoms, 1024 bytes apart (SBO); LBO unused; version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                             // descriptor version
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(addr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct GemmParams {
     int64_t M;
@@ -271,7 +203,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     }
 }
 
-// x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exactly a TF32 value), lo = x - hi.
+// x -> (hi, lo): hi = x rounded to the nearest TF32 value, lo = (x - hi) rounded to TF32.
 __global__ void split_tf32_kernel(int64_t rows, int cols, const float* __restrict__ x, int64_t ldx,
                                   float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
     const int64_t total = rows * cols;
@@ -280,27 +212,10 @@ __global__ void split_tf32_kernel(int64_t rows, int cols, const float* __restric
         const int64_t r = i / cols;
         const int c = (int)(i - r * cols);
         const float v = x[r * ldx + c];
-        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        hi[r * ldo + c] = h;
-        lo[r * ldo + c] = v - h;
+        gigl_split_tf32(v, hi[r * ldo + c], lo[r * ldo + c]);
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
 
 // 2-D fp32 tensor [rows, cols] with row pitch ld (floats): box = [box_rows, 32 floats], 128-byte swizzle, OOB -> 0
 static int make_map(gigl_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,

@@ -158,6 +158,20 @@ class Context:
                                       None if bias is None else _dp(bias), _dp_any(out), out.stride(0), int(relu)), self.handle)
         return out
 
+    def linear_tn(self, G, A, out=None, accumulate: bool = False):
+        """G[R, M]^T @ A[R, N] -> [M, N] (the weight gradient of F.linear) on the tensor cores, deterministic."""
+        import torch
+
+        assert G.is_cuda and A.is_cuda and G.shape[0] == A.shape[0]
+        assert G.shape[0] == 0 or (G.stride(1) == 1 and A.stride(1) == 1)
+        R, M = G.shape
+        N = A.shape[1]
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=G.device)
+        check(self._L.gigl_linear_tn_dev(self.handle, R, M, N, _dp_any(G), max(G.stride(0), M), _dp_any(A), max(A.stride(0), N), _dp_any(out),
+                                         out.stride(0), int(accumulate)), self.handle)
+        return out
+
     def gather_mean(self, x, rowptr, col, n_rows_out: Optional[int] = None, out=None):
         import torch
 

@@ -220,6 +220,43 @@ int gigl_gcn_conv_host(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int32_t O
 int gigl_linear_dev(gigl_ctx* ctx, int64_t M, int32_t N, int32_t K, const float* A_dev, int64_t lda, const float* W_dev,
                     int64_t ldw, const float* bias_dev, float* C_dev, int64_t ldc, int32_t relu);
 
+/* ---- aggregate: training forms (forward that keeps its inputs, backward) ------------------- */
+
+/*
+ * What `loss.backward()` runs for the layers above when the reference trains
+ * (python/gigl/src/common/modeling_task_specs/graphsage_template_modeling_spec.py:299-367,
+ * node_classification_modeling_task_spec.py:134-173; torch autograd through torch_geometric SAGEConv / GCNConv).
+ *
+ * gigl_sage_conv_train_fwd_dev = gigl_sage_conv_dev that also leaves [mean | self] of the n_rows_out output rows in
+ * saved_dev: fp32 [n_rows_out, 2 * Fp], Fp = (F + 3) & ~3 (zero padded), which the backward pass re-uses.
+ */
+int gigl_sage_conv_train_fwd_dev(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O, const int64_t* rowptr_dev,
+                                 const int32_t* col_dev, const float* x_dev, const float* Wl_dev, const float* bl_dev,
+                                 const float* Wr_dev, float* out_dev, float* saved_dev, int32_t relu);
+/*
+ * Gradients of gigl_sage_conv_train_fwd_dev.  grad_out: [n_rows_out, O]; out_dev: the forward output (only read when
+ * relu != 0, for the mask); rowptr_dev: the forward CSR by dst (row degrees); t_rowptr_dev / t_col_dev: the same edges as
+ * a CSR by SOURCE over all n nodes (row j = destinations of j; gigl_csr_from_coo_dev with src / dst swapped) - needed
+ * only when grad_x_dev != NULL.  Outputs (any may be NULL to skip, the two weight gradients go together):
+ *   grad_x [n, F] = A^T (grad W_l) / deg + grad W_r,  grad_Wl / grad_Wr [O, F],  grad_bl [O].
+ * Deterministic: no float atomics anywhere (transposed gather + split-K partials summed in fixed order).
+ */
+int gigl_sage_conv_bwd_dev(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O, const int64_t* rowptr_dev,
+                           const int64_t* t_rowptr_dev, const int32_t* t_col_dev, const float* saved_dev, const float* Wl_dev,
+                           const float* Wr_dev, const float* out_dev, const float* grad_out_dev, float* grad_x_dev,
+                           float* grad_Wl_dev, float* grad_bl_dev, float* grad_Wr_dev, int32_t relu);
+/* Gradients of gigl_gcn_conv_dev (x, W as in the forward; out_dev only read when relu != 0). */
+int gigl_gcn_conv_bwd_dev(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr_dev, const int32_t* col_dev,
+                          const int64_t* t_rowptr_dev, const int32_t* t_col_dev, const float* x_dev, const float* W_dev,
+                          const float* out_dev, const float* grad_out_dev, float* grad_x_dev, float* grad_W_dev, float* grad_b_dev,
+                          int32_t relu);
+/*
+ * C[M, N] (+)= G[R, M]^T @ A[R, N] on tcgen05 (3xTF32, operands read MN-major straight from their row-major
+ * layout, split-K over R with a fixed-order reduction): the weight gradient of F.linear.  Pitches in floats.
+ */
+int gigl_linear_tn_dev(gigl_ctx* ctx, int64_t R, int32_t M, int32_t N, const float* G_dev, int64_t ldg, const float* A_dev,
+                       int64_t lda, float* C_dev, int64_t ldc, int32_t accumulate);
+
 /* ---- resident node features ------------------------------------------------------------- */
 
 /*

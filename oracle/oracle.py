@@ -436,3 +436,73 @@ def torch_build_in_csr(src, dst, n_nodes: int, is_graph_directed: bool):
     rowptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=src.device)
     rowptr[1:] = torch.cumsum(torch.bincount(d, minlength=n_nodes), 0)
     return rowptr, s.to(torch.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Training reference: the restated layers under torch CPU autograd (what `loss.backward()` does in
+# node_classification_modeling_task_spec.py:134-173 / graphsage_template_modeling_spec.py:299-367).
+# ----------------------------------------------------------------------------------------------
+def torch_sage_grads(x, edge_index, layers, grad_out=None, level_sizes=None, f64=True, x_requires_grad=True):
+    """GraphSAGE forward + backward on the CPU in fp64 (or fp32).  ``grad_out`` is d(loss)/d(output) (defaults to ones).
+    Returns (out, grad_x, [(gWl, gbl, gWr), ...]).  ``level_sizes`` prunes like gigl_b200.nn.GraphSAGE (same numbers on
+    the kept rows)."""
+    import torch
+    import torch.nn.functional as F
+
+    dt = torch.float64 if f64 else torch.float32
+    h = torch.tensor(np.asarray(x), dtype=dt, requires_grad=x_requires_grad)
+    x0 = h
+    ei = torch.as_tensor(np.asarray(edge_index), dtype=torch.int64)
+    src, dst = ei[0], ei[1]
+    n = h.shape[0]
+    cnt = torch.zeros(n, dtype=dt).index_add_(0, dst, torch.ones(dst.numel(), dtype=dt))
+    inv = 1.0 / cnt.clamp(min=1.0)
+    params = []
+    L = len(layers)
+    for li, (Wl, bl, Wr) in enumerate(layers):
+        Wl_t = torch.tensor(np.asarray(Wl), dtype=dt, requires_grad=True)
+        Wr_t = torch.tensor(np.asarray(Wr), dtype=dt, requires_grad=True)
+        bl_t = None if bl is None else torch.tensor(np.asarray(bl), dtype=dt, requires_grad=True)
+        params.append((Wl_t, bl_t, Wr_t))
+        n_in = h.shape[0]
+        keep = (src < n_in) & (dst < n_in)
+        s, d = src[keep], dst[keep]
+        agg = torch.zeros((n_in, h.shape[1]), dtype=dt).index_add(0, d, h.index_select(0, s)) * inv[:n_in, None]
+        out = F.linear(agg, Wl_t, bl_t) + F.linear(h, Wr_t)
+        if li < L - 1:
+            out = out.relu()
+        if level_sizes is not None:
+            out = out[: int(level_sizes[L - 1 - li])]
+        h = out
+    g = torch.ones_like(h) if grad_out is None else torch.as_tensor(np.asarray(grad_out), dtype=dt)
+    h.backward(g)
+    grads = [(p[0].grad.numpy(), None if p[1] is None else p[1].grad.numpy(), p[2].grad.numpy()) for p in params]
+    return h.detach().numpy(), (x0.grad.numpy() if x_requires_grad else None), grads
+
+
+def torch_gcn_grads(x, edge_index, W, b, relu=False, grad_out=None, f64=True):
+    """GCNConv forward + backward under torch CPU autograd: (out, grad_x, grad_W, grad_b)."""
+    import torch
+
+    dt = torch.float64 if f64 else torch.float32
+    xt = torch.tensor(np.asarray(x), dtype=dt, requires_grad=True)
+    Wt = torch.tensor(np.asarray(W), dtype=dt, requires_grad=True)
+    bt = None if b is None else torch.tensor(np.asarray(b), dtype=dt, requires_grad=True)
+    ei = torch.as_tensor(np.asarray(edge_index), dtype=torch.int64)
+    n = xt.shape[0]
+    keep = ei[0] != ei[1]
+    loops = torch.arange(n, dtype=torch.int64)
+    src = torch.cat([ei[0][keep], loops])
+    dst = torch.cat([ei[1][keep], loops])
+    deg = torch.zeros(n, dtype=dt).index_add_(0, dst, torch.ones(dst.numel(), dtype=dt))
+    dinv = deg.pow(-0.5)
+    w = dinv[src] * dinv[dst]
+    xp = xt @ Wt.t()
+    out = torch.zeros((n, Wt.shape[0]), dtype=dt).index_add(0, dst, xp.index_select(0, src) * w[:, None])
+    if bt is not None:
+        out = out + bt
+    if relu:
+        out = out.relu()
+    g = torch.ones_like(out) if grad_out is None else torch.as_tensor(np.asarray(grad_out), dtype=dt)
+    out.backward(g)
+    return out.detach().numpy(), xt.grad.numpy(), Wt.grad.numpy(), None if bt is None else bt.grad.numpy()
