@@ -17,7 +17,8 @@ enum {
     GIGL_SLOT_IO2 = 5,    // host-entry-point staging: csr
     GIGL_SLOT_IO3 = 6,
     GIGL_SLOT_IO4 = 7,
-    GIGL_SCRATCH_SLOTS = 8
+    GIGL_SLOT_SAVE = 8,   // [mean | self] of an inference-only layer / operand halves of the GCN projection
+    GIGL_SCRATCH_SLOTS = 9
 };
 
 // timing tags: device time per phase, measured with CUDA events on the ctx stream when enabled
@@ -187,6 +188,3 @@ int gcn_conv_bwd_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const in
                         float* grad_W, float* grad_b, int32_t relu);
 int linear_tn_launch(gigl_ctx* ctx, int64_t R, int M, int N, const float* G, int64_t ldg, const float* A, int64_t lda, float* C,
                      int64_t ldc, int accumulate);
-// sage_aggregate.cu: fp32 FFMA projection with explicit leading dimensions (M optionally read on the device)
-int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, int N, int K, const float* A, int64_t lda,
-                           const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);

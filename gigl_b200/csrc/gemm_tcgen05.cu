@@ -40,6 +40,8 @@ struct GemmParams {
     int n_pad;        // UMMA N of one tile (multiple of 16, <= 256)
     int n_tiles_n;    // tiles along N
     int stages;
+    int nbuf;         // TMEM accumulator buffers (2 = the epilogue of tile t overlaps the MMAs of tile t + 1)
+    int split_acc;    // 1 = the two small products (lo*hi, hi*lo) accumulate in their own TMEM columns (long K)
     uint32_t tmem_cols;
     const float* bias;
     float* C;
@@ -125,10 +127,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             uint32_t phase = 0;
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & 1;
-                mbar_wait(bar_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);
+                const uint32_t acc = p.nbuf == 2 ? (it & 1) : 0;
+                const uint32_t use = p.nbuf == 2 ? (it >> 1) : it;
+                mbar_wait(bar_tempty + 8 * acc, (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.n_pad;
+                const uint32_t acc_cols = (uint32_t)p.n_pad << p.split_acc;
+                const uint32_t tmem_d = tmem_base + acc * acc_cols;
+                const uint32_t tmem_s = tmem_d + (uint32_t)p.n_pad;  // small-term accumulator (split_acc only)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
@@ -138,9 +143,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                         const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // +32 bytes inside the swizzle span
-                        umma_tf32(tmem_d, d_al + adv, d_wh + adv, idesc, (kb | k) != 0);
-                        umma_tf32(tmem_d, d_ah + adv, d_wl + adv, idesc, 1);
-                        umma_tf32(tmem_d, d_ah + adv, d_wh + adv, idesc, 1);
+                        if (p.split_acc) {
+                            // the accumulator add truncates: keeping the 2^-11-sized terms out of the big sum costs it
+                            // one rounding per k step instead of three
+                            umma_tf32(tmem_s, d_al + adv, d_wh + adv, idesc, (kb | k) != 0);
+                            umma_tf32(tmem_s, d_ah + adv, d_wl + adv, idesc, 1);
+                            umma_tf32(tmem_d, d_ah + adv, d_wh + adv, idesc, (kb | k) != 0);
+                        } else {
+                            umma_tf32(tmem_d, d_al + adv, d_wh + adv, idesc, (kb | k) != 0);
+                            umma_tf32(tmem_d, d_ah + adv, d_wl + adv, idesc, 1);
+                            umma_tf32(tmem_d, d_ah + adv, d_wh + adv, idesc, 1);
+                        }
                     }
                     umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
                     if (++stage == p.stages) {
@@ -157,16 +170,24 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1;
+            const uint32_t acc = p.nbuf == 2 ? (it & 1) : 0;
+            const uint32_t use = p.nbuf == 2 ? (it >> 1) : it;
             const int64_t m0 = (tile / p.n_tiles_n) * kBlockM;
             const int n0 = (int)((tile % p.n_tiles_n) * p.n_pad);
-            mbar_wait(bar_tfull + 8 * acc, (it >> 1) & 1);
+            mbar_wait(bar_tfull + 8 * acc, use & 1);
             tc_fence_after();
             const int64_t row = m0 + quarter * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.n_pad;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ((uint32_t)p.n_pad << p.split_acc);
             for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
+                if (p.split_acc) {
+                    uint32_t sm[16];
+                    tmem_ld16(taddr + p.n_pad + c0, sm);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(sm[j]));
+                }
                 tmem_ld_wait();
                 if (row < p.M) {
                     float* crow = p.C + row * p.ldc + n0 + c0;
@@ -255,8 +276,11 @@ int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, 
     if (stages > 4) stages = 4;
     GIGL_CHECK(ctx, stages >= 2, "tile does not fit in shared memory");
     p.stages = stages;
+    // long reductions: separate accumulator for the small products (see the MMA issue loop); TMEM has 512 columns
+    p.split_acc = K > 512 ? 1 : 0;
+    p.nbuf = (2 * (p.n_pad << p.split_acc) <= 512) ? 2 : 1;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * p.n_pad)) cols <<= 1;
+    while (cols < (uint32_t)(p.nbuf * (p.n_pad << p.split_acc))) cols <<= 1;
     p.tmem_cols = cols;
     p.bias = bias;
     p.C = C;

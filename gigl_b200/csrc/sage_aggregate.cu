@@ -5,12 +5,14 @@
 // (TwoLayerGCN), called from graphsage_template_modeling_spec.py:305-311 / :565-577:
 //   SAGE: out_i = Wl @ mean_{j->i} x_j + bl + Wr @ x_i          GCN: out_i = sum_j dinv_j dinv_i (W x_j) + b
 //
-// Round-1 structure: (1) gather-mean over CSR-by-dst rows, one warp per destination row, float4
-// loads, sub-warp neighbour groups for narrow features, warp-shuffle segment reduce;
-// (2) projection [agg | x] @ [Wl | Wr]^T + b as a shared-memory tiled fp32 GEMM with the bias /
-// ReLU epilogue fused.  fp32 FFMA keeps the 1e-5 relative parity bound; the tensor-core
-// (3xTF32 tcgen05) projection is the planned replacement.
+// Structure: (1) gather-mean over CSR-by-dst rows, one warp per destination row, float4 loads, sub-warp neighbour
+// groups for narrow features, warp-shuffle segment reduce, written as [mean | self]; (2) projection
+// [mean | self] @ [Wl | Wr]^T + b on tcgen05 as 3xTF32 (gemm_tcgen05.cu) with the bias / ReLU epilogue fused;
+// (3) backward: transposed gather for the input gradient, tcgen05 TN GEMM for the weight gradients
+// (gemm_tn_tcgen05.cu).
 #include <cuda_runtime.h>
+
+#include <initializer_list>
 
 #include "common.cuh"
 
@@ -193,132 +195,6 @@ __global__ void gcn_dinv_kernel(int64_t n, const int64_t* __restrict__ rowptr, c
     if (lane == 0) dinv[row] = 1.0f / sqrtf((float)(c + 1));
 }
 
-// C[M,N] = [A0 | A1][M, K0+K1] @ [B0 | B1][N, K0+K1]^T + bias, optional relu.  fp32 FFMA.
-// 64x64 block tile, BK = 16, 256 threads, 4x4 register tile per thread.
-constexpr int BM = 64, BN = 64, BK = 16;
-__global__ void __launch_bounds__(256) linear2_kernel(int64_t M, int N, int K0, int K1, const float* __restrict__ A0,
-                                                      const float* __restrict__ A1, const float* __restrict__ B0,
-                                                      const float* __restrict__ B1, const float* __restrict__ bias,
-                                                      float* __restrict__ C, int relu) {
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int K = K0 + K1;
-    // loader mapping: 64 rows x 16 k = 1024 elements, 4 per thread: row = tid/4, k = (tid%4)*4 .. +3
-    const int lr = tid >> 2, lk = (tid & 3) * 4;
-    for (int k0 = 0; k0 < K; k0 += BK) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = k0 + lk + q;
-            float a = 0.f, b = 0.f;
-            const int64_t m = m0 + lr;
-            if (m < M && k < K) a = (k < K0) ? __ldg(A0 + m * K0 + k) : __ldg(A1 + m * K1 + (k - K0));
-            const int n = n0 + lr;
-            if (n < N && k < K) b = (k < K0) ? __ldg(B0 + (int64_t)n * K0 + k) : __ldg(B1 + (int64_t)n * K1 + (k - K0));
-            As[lk + q][lr] = a;
-            Bs[lk + q][lr] = b;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t m = m0 + ty * 4 + i;
-        if (m >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= N) continue;
-            float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
-            if (relu) v = fmaxf(v, 0.f);
-            C[m * N + n] = v;
-        }
-    }
-}
-
-// C[M, N] = A[M, K] @ W[N, K]^T + bias, optional relu; explicit leading dimensions, and M may live
-// on the device (*m_dev, clamped to M) so a batch pipeline needs no host round trip.  fp32 FFMA.
-__global__ void __launch_bounds__(256) linear_ld_kernel(const int32_t* __restrict__ m_dev, int64_t M, int N, int K,
-                                                        const float* __restrict__ A, int64_t lda,
-                                                        const float* __restrict__ W, int64_t ldw,
-                                                        const float* __restrict__ bias, float* __restrict__ C,
-                                                        int64_t ldc, int relu) {
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
-    if (m_dev) {
-        const int64_t md = *m_dev;
-        if (md < M) M = md;
-    }
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
-    if (m0 >= M) return;
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    const int n0 = blockIdx.y * BN;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const int lr = tid >> 2, lk = (tid & 3) * 4;
-    for (int k0 = 0; k0 < K; k0 += BK) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = k0 + lk + q;
-            const int64_t m = m0 + lr;
-            const int n = n0 + lr;
-            As[lk + q][lr] = (m < M && k < K) ? __ldg(A + m * lda + k) : 0.f;
-            Bs[lk + q][lr] = (n < N && k < K) ? __ldg(W + (int64_t)n * ldw + k) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t m = m0 + ty * 4 + i;
-        if (m >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= N) continue;
-            float v = acc[i][j] + (bias ? __ldg(bias + n) : 0.f);
-            if (relu) v = fmaxf(v, 0.f);
-            C[m * ldc + n] = v;
-        }
-    }
-}
-
 template <int MODE>
 static int launch_gather(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t* rowptr, const int32_t* col,
                          const float* x, float* out, const float* dinv, const float* bias, int relu, int64_t ldx = 0,
@@ -349,30 +225,24 @@ static int launch_gather(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t
     return GIGL_OK;
 }
 
-static int launch_linear2(gigl_ctx* ctx, int64_t M, int N, int K0, int K1, const float* A0, const float* A1,
-                          const float* B0, const float* B1, const float* bias, float* C, int relu) {
-    if (M == 0 || N == 0) return GIGL_OK;
-    const int64_t gx = ceil_div64(M, BM);
-    if (gx > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "too many rows for one launch");
-    dim3 grid((unsigned)gx, (unsigned)((N + BN - 1) / BN));
-    linear2_kernel<<<grid, 256, 0, ctx->stream>>>(M, N, K0, K1, A0, A1, B0, B1, bias, C, relu);
-    GIGL_LAUNCHED(ctx);
-    return GIGL_OK;
-}
+// carve a scratch slot into 256-byte aligned float arrays
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base((char*)b) {}
+    float* take(size_t elems) {
+        float* p = (float*)(base + off);
+        off += (elems * sizeof(float) + 255) & ~(size_t)255;
+        return p;
+    }
+    static size_t need(std::initializer_list<size_t> elems) {
+        size_t t = 0;
+        for (size_t e : elems) t += (e * sizeof(float) + 255) & ~(size_t)255;
+        return t;
+    }
+};
 
 }  // namespace gigl
-
-int linear_dev_rows_launch(gigl_ctx* ctx, const int32_t* m_dev, int64_t m_cap, int N, int K, const float* A, int64_t lda,
-                           const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu) {
-    using namespace gigl;
-    if (m_cap == 0 || N == 0) return GIGL_OK;
-    const int64_t gx = ceil_div64(m_cap, BM);
-    if (gx > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "too many rows for one launch");
-    dim3 grid((unsigned)gx, (unsigned)((N + BN - 1) / BN));
-    linear_ld_kernel<<<grid, 256, 0, ctx->stream>>>(m_dev, m_cap, N, K, A, lda, W, ldw, bias, C, ldc, relu);
-    GIGL_LAUNCHED(ctx);
-    return GIGL_OK;
-}
 
 int gather_mean_launch(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t* rowptr, const int32_t* col,
                        const float* x, float* agg) {
@@ -386,17 +256,11 @@ int sage_conv_launch(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, in
     GIGL_CHECK(ctx, n >= 0 && n_rows_out >= 0 && n_rows_out <= n, "bad row counts");
     GIGL_CHECK(ctx, F >= 1 && O >= 1, "bad feature dims");
     if (n_rows_out == 0) return GIGL_OK;
-    void* scratch = nullptr;
-    int rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * (size_t)n_rows_out * (size_t)F, &scratch);
+    // inference: same kernels as the training forward ([mean | self] staged in library scratch, projection on tcgen05)
+    void* a = nullptr;
+    int rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, sizeof(float) * (size_t)n_rows_out * 2 * (size_t)((F + 3) & ~3), &a);
     if (rc != GIGL_OK) return rc;
-    float* agg = (float*)scratch;
-    {
-        gigl_timed t(ctx, GIGL_T_GATHER_FULL);
-        rc = gigl::launch_gather<0>(ctx, n_rows_out, F, rowptr, col, x, agg, nullptr, nullptr, 0);
-    }
-    if (rc != GIGL_OK) return rc;
-    gigl_timed t(ctx, GIGL_T_GEMM_FULL);
-    return gigl::launch_linear2(ctx, n_rows_out, O, F, F, agg, x, Wl, Wr, bl, out, relu);
+    return sage_conv_train_fwd_launch(ctx, n, n_rows_out, F, O, rowptr, col, x, Wl, bl, Wr, out, (float*)a, relu);
 }
 
 int gcn_conv_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr, const int32_t* col,
@@ -410,8 +274,19 @@ int gcn_conv_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_
     if (rc != GIGL_OK) return rc;
     float* xp = (float*)scratch;
     float* dinv = xp + xp_elems;
-    rc = gigl::launch_linear2(ctx, n, O, F, 0, x, nullptr, W, nullptr, nullptr, xp, 0);
-    if (rc != GIGL_OK) return rc;
+    {   // x' = x W^T on the tensor cores (3xTF32)
+        gigl_timed t(ctx, GIGL_T_GEMM_FULL);
+        const int Fp = (F + 3) & ~3;
+        const size_t x_el = (size_t)n * Fp, w_el = (size_t)O * Fp;
+        void* hb = nullptr;
+        if ((rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, gigl::Carver::need({x_el, x_el, w_el, w_el}), &hb)) != GIGL_OK) return rc;
+        gigl::Carver cv(hb);
+        float *x_hi = cv.take(x_el), *x_lo = cv.take(x_el), *w_hi = cv.take(w_el), *w_lo = cv.take(w_el);
+        if (Fp != F) GIGL_CUDA(ctx, cudaMemsetAsync(hb, 0, cv.off, ctx->stream));
+        if ((rc = split_tf32_launch(ctx, n, F, x, F, x_hi, x_lo, Fp)) != GIGL_OK) return rc;
+        if ((rc = split_tf32_launch(ctx, O, F, W, F, w_hi, w_lo, Fp)) != GIGL_OK) return rc;
+        if ((rc = linear_tc_launch(ctx, n, O, Fp, x_hi, x_lo, Fp, w_hi, w_lo, Fp, nullptr, xp, O, 0)) != GIGL_OK) return rc;
+    }
     const int wpb = 8;
     gigl::gcn_dinv_kernel<<<(unsigned)ceil_div64(n, wpb), wpb * 32, 0, ctx->stream>>>(n, rowptr, col, dinv);
     GIGL_LAUNCHED(ctx);
@@ -494,23 +369,6 @@ static inline unsigned grid_for(gigl_ctx* ctx, int64_t work, int per_block = 256
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     return (unsigned)(g < cap ? g : cap);
 }
-
-// carve a scratch slot into 256-byte aligned float arrays
-struct Carver {
-    char* base;
-    size_t off = 0;
-    explicit Carver(void* b) : base((char*)b) {}
-    float* take(size_t elems) {
-        float* p = (float*)(base + off);
-        off += (elems * sizeof(float) + 255) & ~(size_t)255;
-        return p;
-    }
-    static size_t need(std::initializer_list<size_t> elems) {
-        size_t t = 0;
-        for (size_t e : elems) t += (e * sizeof(float) + 255) & ~(size_t)255;
-        return t;
-    }
-};
 
 }  // namespace gigl
 
