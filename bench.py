@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-roots", type=int, default=8192, help="roots per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard-features", action="store_true",
+                    help="features sharded by node range over the N GPUs and mapped as one flat table (remote rows over NVLink) "
+                         "instead of replicated")
     return ap.parse_args()
 
 
@@ -220,11 +223,15 @@ def run_reference(args):
 
 
 def workload_config(args, wl, fan, batch, note):
+    residency = ("whole CSR + feature table resident in HBM on every GPU (replicated); roots sharded by contiguous id range"
+                 if not getattr(args, "shard_features", False) else
+                 "CSR replicated; feature table sharded by contiguous node range over the GPUs and mapped as one flat array "
+                 "(cuMemMap of peer shards): remote neighbour rows are loaded over NVLink inside the gather kernel")
     return {"workload": f"BASELINE.json configs[1] shape: {args.workload} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
                         f"N={wl['nodes']}, {wl['pairs']} undirected pairs de-duplicated+mirrored, F={wl['F']} fp32, "
                         f"2-hop fanout {fan}, GraphSAGE {wl['F']}->{wl['H']}->{wl['O']} inference on the coalesced batch graph",
             "roots_per_step_per_gpu": batch, "fanout": fan, "seed": {"generator": 20260101, "sampler_base_seed": 42, "first_call_no": 1},
-            "residency": "whole CSR + feature table resident in HBM on every GPU (replicated); roots sharded by contiguous id range",
+            "residency": residency,
             "l2": "every step reads different roots from a 0.98 GB feature table + 0.5 GB CSR (>> 126 MB L2); no flush needed",
             "note": note}
 
@@ -251,6 +258,17 @@ def run_ours(args):
     src, dst, x, layers = build_inputs_torch(wl, dev)
     g = Graph.from_edges_dev(ctx, wl["nodes"], src, dst, is_graph_directed=False)
     del src, dst
+    table = None
+    if args.shard_features:
+        from gigl_b200.sharding import ShardedFeatureTable
+
+        table = ShardedFeatureTable(ctx, wl["nodes"], wl["F"], rank, world, tag=os.environ.get("MASTER_PORT", "0"))
+        table.local[: table.row_hi - table.row_lo].copy_(x[table.row_lo:table.row_hi])  # this rank keeps only its rows
+        del x
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        x = table.table[: wl["nodes"]]
     g.set_features(x)
     model = SageModel(ctx, layers)
     batch = Batch(ctx, wl["nodes"])
@@ -374,6 +392,12 @@ def run_ours(args):
                 "phase_ms_per_step": phase_ms, "unique_edges_per_step": e1_total / K, "layer1_rows_per_step": n1_total / K,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
+    if table is not None:
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        g.close()
+        table.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -66,6 +66,11 @@ SIGNATURES = {
     "gigl_graph_set_features_host": (C.c_int, [vp, vp, i32]),
     "gigl_graph_set_features_dev": (C.c_int, [vp, vp, i32]),
     "gigl_graph_features_dev": (C.c_int, [vp, pvp, C.POINTER(i32)]),
+    "gigl_shared_table_row_granule": (C.c_int, [vp, i32, C.POINTER(i64)]),
+    "gigl_shared_table_create": (C.c_int, [vp, i32, i32, i64, i32, pvp, C.POINTER(i32)]),
+    "gigl_shared_table_attach": (C.c_int, [vp, i32, i32]),
+    "gigl_shared_table_ptrs": (C.c_int, [vp, pvp, pvp, C.POINTER(i64)]),
+    "gigl_shared_table_destroy": (None, [vp]),
     "gigl_sage_model_create_host": (C.c_int, [vp, i32, vp, pvp, pvp, pvp, pvp]),
     "gigl_sage_model_create_dev": (C.c_int, [vp, i32, vp, pvp, pvp, pvp, pvp]),
     "gigl_sage_model_destroy": (None, [vp]),

@@ -29,3 +29,106 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ----------------------------------------------------------------------------------------------
+# Node features sharded over the GPUs of the box, one flat array on every GPU (csrc/shared_table.cu)
+# ----------------------------------------------------------------------------------------------
+def shard_rows(n_nodes: int, world: int, granule: int) -> int:
+    """Rows per shard: ceil(n_nodes / world) rounded up to the mapping granule (shard k = rows [k*rps, (k+1)*rps))."""
+    per = -(-n_nodes // world)
+    return -(-per // granule) * granule
+
+
+def _uds_name(tag: str, rank: int) -> str:
+    return f"\0gigl_b200_{tag}_{rank}"  # abstract namespace: no file to clean up
+
+
+def exchange_fds(my_fd: int, rank: int, world: int, tag: str, timeout: float = 120.0):
+    """Every rank hands a duplicate of ``my_fd`` to every peer over Unix sockets (SCM_RIGHTS) and gets theirs:
+    returns {peer_rank: fd}.  All processes must be on one host (one box = one NVSwitch domain)."""
+    import socket
+    import threading
+    import time
+
+    if world == 1:
+        return {}
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(_uds_name(tag, rank))
+    srv.listen(world)
+    srv.settimeout(timeout)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            with conn:
+                conn.recv(4)
+                socket.send_fds(conn, [b"fd"], [my_fd])
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    got = {}
+    for peer in range(world):
+        if peer == rank:
+            continue
+        deadline = time.time() + timeout
+        while True:
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            try:
+                c.connect(_uds_name(tag, peer))
+                break
+            except (ConnectionRefusedError, FileNotFoundError):
+                c.close()
+                if time.time() > deadline:
+                    raise TimeoutError(f"rank {rank}: peer {peer} never opened its fd socket")
+                time.sleep(0.05)
+        with c:
+            c.sendall(b"gimm")
+            _, fds, _, _ = socket.recv_fds(c, 16, 1)
+            got[peer] = fds[0]
+    th.join(timeout)
+    srv.close()
+    return got
+
+
+class ShardedFeatureTable:
+    """The [n_nodes, F] fp32 feature table with shard ``rank`` resident on this GPU and every other shard mapped from
+    its owner's memory, as ONE flat CUDA array (``.table``, a torch view usable by ``Graph.set_features`` /
+    ``Batch.sage_forward``).  ``.local`` is this rank's slice (rows [rank * rows_per_shard, ...)) to fill."""
+
+    def __init__(self, ctx, n_nodes: int, F: int, rank: int, world: int, tag: str = "0"):
+        import ctypes as C
+        import os
+
+        import torch
+
+        from ._capi import check
+        from .engine import _tensor_from_ptr
+
+        L = ctx._L
+        self.ctx, self.n_nodes, self.F, self.rank, self.world = ctx, n_nodes, F, rank, world
+        g = C.c_int64()
+        check(L.gigl_shared_table_row_granule(ctx.handle, F, C.byref(g)), ctx.handle)
+        self.rows_per_shard = shard_rows(n_nodes, world, g.value)
+        h, fd = C.c_void_p(), C.c_int32(-1)
+        check(L.gigl_shared_table_create(ctx.handle, world, rank, self.rows_per_shard, F, C.byref(h), C.byref(fd)), ctx.handle)
+        self.handle = h
+        peers = exchange_fds(fd.value, rank, world, tag)
+        for peer, pfd in sorted(peers.items()):
+            try:
+                check(L.gigl_shared_table_attach(h, peer, pfd), ctx.handle)
+            finally:
+                os.close(pfd)  # the driver keeps its own reference to the allocation
+        base, mine, total = C.c_void_p(), C.c_void_p(), C.c_int64()
+        L.gigl_shared_table_ptrs(h, C.byref(base), C.byref(mine), C.byref(total))
+        dev = torch.device("cuda", ctx.device)
+        self.table = _tensor_from_ptr(base.value, (total.value, F), torch.float32, dev, owner=self)
+        self.local = _tensor_from_ptr(mine.value, (self.rows_per_shard, F), torch.float32, dev, owner=self)
+        self.row_lo = rank * self.rows_per_shard
+        self.row_hi = min(n_nodes, (rank + 1) * self.rows_per_shard)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.table = self.local = None
+            self.ctx._L.gigl_shared_table_destroy(self.handle)
+            self.handle = None

@@ -268,6 +268,28 @@ int gigl_graph_set_features_host(gigl_graph* g, const float* x, int32_t F);
 int gigl_graph_set_features_dev(gigl_graph* g, const float* x_dev, int32_t F);
 int gigl_graph_features_dev(const gigl_graph* g, const float** x_dev, int32_t* F);
 
+/* ---- node features sharded over the GPUs of one NVSwitch box ------------------------------- */
+
+/*
+ * the feature table is sharded by contiguous node-id range, shard k on GPU k, and stitched
+ * into ONE flat virtual array on every GPU with the CUDA virtual memory API (cuMemCreate / cuMemMap): row v lives at
+ * base + v * F floats everywhere, a remote row is an ordinary load routed over NVLink.  The result is handed to
+ * gigl_graph_set_features_dev / gigl_batch_sage_forward_dev like any device array.  One process per GPU:
+ *   1. every rank: gigl_shared_table_create(... my_shard = rank ...) -> a POSIX file descriptor of its shard;
+ *   2. the ranks exchange the descriptors (Unix socket SCM_RIGHTS; gigl_b200/sharding.py);
+ *   3. every rank: gigl_shared_table_attach(shard k, fd of rank k) for all k != rank.
+ * rows_per_shard must be a multiple of gigl_shared_table_row_granule(F) (physical allocations are mapped at the
+ * driver's allocation granularity, typically 2 MiB).
+ */
+typedef struct gigl_shared_table gigl_shared_table;
+int gigl_shared_table_row_granule(gigl_ctx* ctx, int32_t F, int64_t* rows);
+int gigl_shared_table_create(gigl_ctx* ctx, int32_t n_shards, int32_t my_shard, int64_t rows_per_shard, int32_t F,
+                             gigl_shared_table** out, int32_t* export_fd);
+int gigl_shared_table_attach(gigl_shared_table* t, int32_t shard, int32_t fd);
+/* base of the flat table [n_shards * rows_per_shard, F], the start of this rank's own shard, total rows */
+int gigl_shared_table_ptrs(const gigl_shared_table* t, float** base_dev, float** my_shard_dev, int64_t* total_rows);
+void gigl_shared_table_destroy(gigl_shared_table* t);
+
 /* ---- model: GraphSAGE weights resident on the device ------------------------------------ */
 
 typedef struct gigl_sage_model gigl_sage_model;

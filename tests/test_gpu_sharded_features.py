@@ -1,0 +1,115 @@
+"""GPU: the node-feature table sharded over the GPUs of the box and mapped as one flat array (csrc/shared_table.cu).
+world = 1 runs on any B200; the 2-process test needs two GPUs (`gpurun --gpus 2`) and is skipped otherwise."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph_and_model(rng, n, F):
+    from gigl_b200 import synth
+
+    src = rng.integers(0, n, 12 * n)
+    dst = (rng.zipf(1.7, 12 * n) - 1) % n
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    layers = synth.sage_weights(rng, [F, 32, 8])
+    return src, dst, x, layers
+
+
+def test_single_shard_table_is_an_ordinary_feature_table():
+    import torch
+
+    from gigl_b200 import Batch, Context, Graph, SageModel
+    from gigl_b200.sharding import ShardedFeatureTable
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(0)
+    n, F, fan = 5000, 20, [6, 4]
+    src, dst, x, layers = _graph_and_model(rng, n, F)
+    ctx = Context.on_torch_stream(0)
+    t = ShardedFeatureTable(ctx, n, F, 0, 1, tag=f"t{os.getpid()}")
+    assert t.rows_per_shard >= n and t.table.shape == (t.rows_per_shard, F)
+    t.local[:n].copy_(torch.from_numpy(x))
+    g = Graph.from_edges_host(ctx, n, src, dst, is_graph_directed=False)
+    roots = torch.arange(0, n, 5, dtype=torch.int32, device="cuda")
+    nbr, _ = g.sample_khop(roots, fan)
+    b = Batch(ctx, n)
+    b.collate(roots, fan, nbr, 2)
+    emb = b.sage_forward(SageModel(ctx, layers), t.table[:n]).cpu().numpy()
+    rowptr, col = g.csr_host()
+    onbr, _ = O.c_sample_khop(rowptr, col, roots.cpu().numpy(), fan)
+    ref = O.batch_sage_embeddings(x, roots.cpu().numpy(), onbr, fan, layers, f64=True)
+    assert np.abs(emb - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    ctx.sync()
+    t.close()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from gigl_b200 import Batch, Context, Graph, SageModel
+    from gigl_b200.sharding import ShardedFeatureTable, root_range
+
+    rng = np.random.default_rng(7)  # same graph / features / weights on every rank
+    n, F, fan = 20000, 36, [8, 5]
+    src, dst, x, layers = _graph_and_model(rng, n, F)
+    ctx = Context.on_torch_stream(rank)
+    t = ShardedFeatureTable(ctx, n, F, rank, world, tag=str(port))
+    lo, hi = t.row_lo, t.row_hi
+    t.local[: hi - lo].copy_(torch.from_numpy(x[lo:hi]))  # every rank fills ONLY its own rows
+    torch.cuda.synchronize()
+    dist.barrier()
+    whole = t.table[:n].cpu().numpy()  # remote rows come over NVLink
+    table_ok = bool(np.array_equal(whole, x))
+    g = Graph.from_edges_host(ctx, n, src, dst, is_graph_directed=False)
+    r0, r1 = root_range(n, rank, world)
+    roots = torch.arange(r0, r1, 3, dtype=torch.int32, device="cuda")
+    nbr, _ = g.sample_khop(roots, fan)
+    b = Batch(ctx, n)
+    b.collate(roots, fan, nbr, 2)
+    model = SageModel(ctx, layers)
+    emb_sharded = b.sage_forward(model, t.table[:n]).clone()
+    emb_replica = b.sage_forward(model, torch.from_numpy(x).cuda())
+    same = bool(torch.equal(emb_sharded, emb_replica))  # same kernel, same order: bit-identical
+    torch.cuda.synchronize()
+    dist.barrier()
+    q.put((rank, table_ok, same, int(roots.numel())))
+    t.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_shards_are_one_flat_table_and_give_identical_embeddings():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, table_ok, same, n_roots in res:
+        assert table_ok, f"rank {rank}: the flat table differs from the features the ranks wrote"
+        assert same and n_roots > 0

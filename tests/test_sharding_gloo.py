@@ -58,3 +58,34 @@ def test_two_rank_root_sharding_and_timing_reduction():
         assert np.array_equal(cover, np.arange(1000))
     b = sharding.root_batches(10, 0, 1, 4, 4)
     assert [x.tolist() for x in b] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 0, 1], [2, 3, 4, 5]]
+
+
+def _fd_worker(rank, world, tag, q):
+    # every rank owns a pipe; the peers receive its WRITE end through exchange_fds and write their rank into it
+    r_fd, w_fd = os.pipe()
+    got = sharding.exchange_fds(w_fd, rank, world, tag, timeout=60)
+    assert sorted(got) == [p for p in range(world) if p != rank]
+    for peer, fd in got.items():
+        os.write(fd, bytes([rank]))
+        os.close(fd)
+    seen = sorted(os.read(r_fd, 1)[0] for _ in range(world - 1))
+    q.put((rank, seen))
+
+
+def test_fd_exchange_between_processes_and_shard_arithmetic():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    tag = f"test{os.getpid()}"
+    procs = [ctx.Process(target=_fd_worker, args=(r, world, tag, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: [1, 2], 1: [0, 2], 2: [0, 1]}
+    # shards: multiples of the granule, together covering every node
+    assert sharding.shard_rows(2_449_029, 8, 131072) == 393216 and 8 * 393216 >= 2_449_029
+    assert sharding.shard_rows(1000, 1, 4096) == 4096 and sharding.shard_rows(8192, 2, 4096) == 4096
+    assert sharding.exchange_fds(0, 0, 1, tag) == {}
