@@ -125,7 +125,7 @@ class ShardedFeatureTable:
         self.table = _tensor_from_ptr(base.value, (total.value, F), torch.float32, dev, owner=self)
         self.local = _tensor_from_ptr(mine.value, (self.rows_per_shard, F), torch.float32, dev, owner=self)
         self.row_lo = rank * self.rows_per_shard
-        self.row_hi = min(n_nodes, (rank + 1) * self.rows_per_shard)
+        self.row_hi = max(self.row_lo, min(n_nodes, (rank + 1) * self.rows_per_shard))
 
     def close(self):
         if getattr(self, "handle", None):

@@ -56,6 +56,16 @@ def _free_port():
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception as e:  # surface the failure in the parent instead of a queue timeout
+        import traceback
+
+        q.put((rank, False, False, -1, traceback.format_exc()))
+        raise
+
+
+def _worker_body(rank, world, port, q):
     import torch
     import torch.distributed as dist
 
@@ -66,11 +76,12 @@ def _worker(rank, world, port, q):
     from gigl_b200.sharding import ShardedFeatureTable, root_range
 
     rng = np.random.default_rng(7)  # same graph / features / weights on every rank
-    n, F, fan = 20000, 36, [8, 5]
+    n, F, fan = 40000, 32, [8, 5]  # F = 32 -> 16384-row mapping granule -> shards of 32768 rows: both ranks own rows
     src, dst, x, layers = _graph_and_model(rng, n, F)
     ctx = Context.on_torch_stream(rank)
     t = ShardedFeatureTable(ctx, n, F, rank, world, tag=str(port))
     lo, hi = t.row_lo, t.row_hi
+    assert hi > lo, "test sizes must give every rank rows"
     t.local[: hi - lo].copy_(torch.from_numpy(x[lo:hi]))  # every rank fills ONLY its own rows
     torch.cuda.synchronize()
     dist.barrier()
@@ -88,7 +99,7 @@ def _worker(rank, world, port, q):
     same = bool(torch.equal(emb_sharded, emb_replica))  # same kernel, same order: bit-identical
     torch.cuda.synchronize()
     dist.barrier()
-    q.put((rank, table_ok, same, int(roots.numel())))
+    q.put((rank, table_ok, same, int(roots.numel()), ""))
     t.close()
     dist.destroy_process_group()
 
@@ -106,10 +117,18 @@ def test_two_gpu_shards_are_one_flat_table_and_give_identical_embeddings():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
-    for rank, table_ok, same, n_roots in res:
+    res = []
+    try:
+        for _ in range(world):
+            item = q.get(timeout=90)
+            assert not item[4], item[4]
+            res.append(item)
+    finally:
+        for p in procs:
+            p.join(timeout=30 if len(res) == world else 1)
+            if p.is_alive():
+                p.terminate()
+    for rank, table_ok, same, n_roots, err in sorted(res):
         assert table_ok, f"rank {rank}: the flat table differs from the features the ranks wrote"
         assert same and n_roots > 0
+    assert all(p.exitcode == 0 for p in procs)
