@@ -45,6 +45,9 @@ struct gigl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // second stream + event for device->host copies that overlap the kernels of the same call (host entry points)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ready = nullptr;
     int sm_count = 148;
     int64_t launches = 0;
     std::string err;
