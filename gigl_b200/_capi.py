@@ -45,6 +45,7 @@ SIGNATURES = {
     "gigl_graph_wrap_dev": (C.c_int, [vp, i64, i64, vp, vp, pvp]),
     "gigl_graph_from_edges_host": (C.c_int, [vp, i64, i64, vp, vp, i32, i32, pvp]),
     "gigl_graph_from_edges_dev": (C.c_int, [vp, i64, i64, vp, vp, i32, i32, pvp]),
+    "gigl_edge_rows_host": (C.c_int, [vp, i64, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]),
     "gigl_graph_num_nodes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "gigl_graph_device_ptrs": (C.c_int, [vp, pvp, pvp]),
     "gigl_graph_destroy": (None, [vp]),
@@ -83,6 +84,8 @@ SIGNATURES = {
     "gigl_crc32c_masked": (C.c_uint32, [vp, i64]),
     "gigl_free_host": (None, [vp]),
     "gigl_encode_samples_host": (C.c_int, [i32, i64, vp, vp, i32, pvp, vp, i32, i32, i32, vp, cp, i32, pvp, C.POINTER(i64), vp]),
+    "gigl_encode_samples_ex_host": (C.c_int, [i32, i64, i64, vp, vp, i32, pvp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, cp, i32, vp, vp,
+                                              i32, pvp, C.POINTER(i64), vp]),
     "gigl_tfrecord_index_host": (i64, [vp, i64, i32, vp, vp, i64]),
     "gigl_examples_column_host": (C.c_int, [vp, i64, vp, vp, cp, i32, i32, vp, vp]),
     "gigl_infer_khop_sage_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, pvp, pvp]),

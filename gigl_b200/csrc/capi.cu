@@ -373,6 +373,40 @@ int gigl_graph_from_edges_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, 
     return rc;
 }
 
+int gigl_edge_rows_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                        int32_t is_graph_directed, int32_t* edge_rows, int64_t rows_cap, int64_t* n_rows) {
+    if (!ctx) return gigl_fail(nullptr, GIGL_E_INVALID, "null ctx");
+    GIGL_CHECK(ctx, n_rows != nullptr, "null n_rows");
+    *n_rows = 0;
+    GIGL_CHECK(ctx, n_edges >= 0 && rows_cap >= 0, "negative size");
+    GIGL_CHECK(ctx, n_edges <= 0x7fffffffLL, "edge record index must fit int32");
+    GIGL_CHECK(ctx, (src && dst) || n_edges == 0, "null edge arrays");
+    GIGL_CHECK(ctx, edge_rows || rows_cap == 0, "null edge_rows");
+    if (n_edges == 0) return GIGL_OK;
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int32_t *d_sd = nullptr, *d_rows = nullptr;
+    const size_t ne = (size_t)n_edges;
+    GIGL_CUDA(ctx, cudaMalloc(&d_sd, sizeof(int32_t) * 2 * ne));
+    cudaError_t e = cudaMalloc(&d_rows, sizeof(int32_t) * (size_t)(rows_cap > 0 ? rows_cap : 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sd, src, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sd + ne, dst, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d_sd);
+        cudaFree(d_rows);
+        return gigl_cuda_fail(ctx, e, "edge list upload");
+    }
+    int rc = edge_rows_build(ctx, n_nodes, n_edges, d_sd, d_sd + ne, is_graph_directed, d_rows, rows_cap, n_rows);
+    if (rc == GIGL_OK && *n_rows > 0) {
+        e = cudaMemcpyAsync(edge_rows, d_rows, sizeof(int32_t) * (size_t)*n_rows, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = gigl_cuda_fail(ctx, e, "edge-row download");
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sd);
+    cudaFree(d_rows);
+    return rc;
+}
+
 int gigl_graph_num_nodes(const gigl_graph* g, int64_t* n_nodes, int64_t* n_edges) {
     if (!g) return GIGL_E_INVALID;
     if (n_nodes) *n_nodes = g->n_nodes;

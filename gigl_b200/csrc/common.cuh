@@ -147,6 +147,8 @@ int csr_from_coo_launch(gigl_ctx* ctx, int64_t n, int64_t e, const int64_t* src,
 int graph_from_edges_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,
                            const int32_t* dst_dev, int32_t directed, int32_t by_source, int64_t** rowptr_dev,
                            int32_t** col_dev, int64_t* n_edges_out);
+int edge_rows_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev, const int32_t* dst_dev,
+                    int32_t directed, int32_t* rows_dev, int64_t rows_cap, int64_t* n_rows_out);
 int gather_mean_launch(gigl_ctx* ctx, int64_t n_rows, int32_t F, const int64_t* rowptr, const int32_t* col,
                        const float* x, float* agg);
 int sage_conv_launch(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, int32_t O, const int64_t* rowptr,

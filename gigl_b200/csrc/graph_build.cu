@@ -269,3 +269,119 @@ int graph_from_edges_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, cons
     *n_edges_out = e_final;
     return GIGL_OK;
 }
+
+// ---- edge-row map: which input edge record hydrates every slot of the CSR ---------------------------------------
+// hydrateEdges joins the sampled (src, dst) pairs with the hydrated edge table on (_from, _to)
+// (SGSPureSparkV1Task.scala:540-563), so the encoder needs, per CSR slot, the input record that carries its features.
+// Same key order as graph_from_edges_build (by destination), with the record index riding along as the sort value:
+//   directed   - every record is its own slot; equal (dst, src) keys keep input order (stable radix sort);
+//   undirected - one record per (least, greatest) pair survives enforceBidirectionalization (:218-258; the reference's
+//                dropDuplicates keeps an arbitrary one, this build keeps the lowest record index) and hydrates both
+//                orientations.
+namespace gigl {
+
+__global__ void iota32_kernel(int64_t e, int32_t* __restrict__ v) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) v[i] = (int32_t)i;
+}
+
+__global__ void mirror_pairs_kernel(int64_t m, const uint64_t* __restrict__ uniq, const int32_t* __restrict__ rep,
+                                    uint64_t* __restrict__ out_k, int32_t* __restrict__ out_v, unsigned long long* n_dead) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long dead = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const uint64_t k = uniq[i];
+        const uint32_t lo = (uint32_t)(k >> 32), hi = (uint32_t)k;
+        const bool no_mirror = (k == kDeadKey || lo == hi);  // a self loop survives once (UNION is distinct)
+        out_k[2 * i] = k;
+        out_v[2 * i] = rep[i];
+        out_k[2 * i + 1] = no_mirror ? kDeadKey : (((uint64_t)hi << 32) | lo);
+        out_v[2 * i + 1] = rep[i];
+        dead += (k == kDeadKey ? 2 : (no_mirror ? 1 : 0));
+    }
+    if (dead) atomicAdd(n_dead, dead);
+}
+
+}  // namespace gigl
+
+int edge_rows_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev, const int32_t* dst_dev,
+                    int32_t directed, int32_t* rows_dev, int64_t rows_cap, int64_t* n_rows_out) {
+    using namespace gigl;
+    *n_rows_out = 0;
+    if (n_edges == 0) return GIGL_OK;
+    cudaStream_t st = ctx->stream;
+    const size_t cap = (size_t)n_edges * (directed ? 1 : 2);
+    uint64_t *k0 = nullptr, *k1 = nullptr;
+    int32_t *v0 = nullptr, *v1 = nullptr;
+    void* temp = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        cudaFree(k0);
+        cudaFree(k1);
+        cudaFree(v0);
+        cudaFree(v1);
+        cudaFree(temp);
+        cudaFree(d_cnt);
+    };
+#define ER_CUDA(call)                                \
+    do {                                             \
+        cudaError_t e__ = (call);                    \
+        if (e__ != cudaSuccess) {                    \
+            cleanup();                               \
+            return gigl_cuda_fail(ctx, e__, #call);  \
+        }                                            \
+    } while (0)
+    ER_CUDA(cudaMalloc(&k0, sizeof(uint64_t) * cap));
+    ER_CUDA(cudaMalloc(&k1, sizeof(uint64_t) * cap));
+    ER_CUDA(cudaMalloc(&v0, sizeof(int32_t) * cap));
+    ER_CUDA(cudaMalloc(&v1, sizeof(int32_t) * cap));
+    ER_CUDA(cudaMalloc(&d_cnt, sizeof(unsigned long long) * 2));
+    ER_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2, st));
+    size_t tb = 0, tb2 = 0;
+    ER_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, v1, (int64_t)cap, 0, 64, st));
+    if (!directed) ER_CUDA(cub::DeviceSelect::UniqueByKey(nullptr, tb2, k1, v1, k0, v0, d_cnt, (int64_t)n_edges, st));
+    if (tb2 > tb) tb = tb2;
+    ER_CUDA(cudaMalloc(&temp, tb > 0 ? tb : 256));
+    edge_keys_kernel<<<grid_for(ctx, n_edges, 256), 256, 0, st>>>(n_edges, src_dev, dst_dev, n_nodes, directed, 0, k0, ctx->d_err);
+    iota32_kernel<<<grid_for(ctx, n_edges, 256), 256, 0, st>>>(n_edges, v0);
+    ctx->launches += 2;
+    ER_CUDA(cudaGetLastError());
+    ER_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, k0, k1, v0, v1, (int64_t)n_edges, 0, 64, st));
+    ctx->launches++;
+    int64_t e_final = n_edges;
+    const int32_t* rows = v1;
+    if (!directed) {
+        ER_CUDA(cub::DeviceSelect::UniqueByKey(temp, tb, k1, v1, k0, v0, d_cnt, (int64_t)n_edges, st));
+        unsigned long long m = 0;
+        ER_CUDA(cudaMemcpyAsync(&m, d_cnt, sizeof(m), cudaMemcpyDeviceToHost, st));
+        ER_CUDA(cudaStreamSynchronize(st));
+        mirror_pairs_kernel<<<grid_for(ctx, (int64_t)m, 256), 256, 0, st>>>((int64_t)m, k0, v0, k1, v1, d_cnt + 1);
+        ER_CUDA(cudaGetLastError());
+        ER_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, k1, k0, v1, v0, (int64_t)(2 * m), 0, 64, st));
+        ctx->launches += 3;
+        unsigned long long dead = 0;  // dead keys (the missing mirror of a self loop) sort last
+        ER_CUDA(cudaMemcpyAsync(&dead, d_cnt + 1, sizeof(dead), cudaMemcpyDeviceToHost, st));
+        ER_CUDA(cudaStreamSynchronize(st));
+        e_final = (int64_t)(2 * m - dead);
+        rows = v0;
+    }
+    int32_t code = 0;
+    ER_CUDA(cudaMemcpyAsync(&code, ctx->d_err, sizeof(code), cudaMemcpyDeviceToHost, st));
+    ER_CUDA(cudaStreamSynchronize(st));
+    if (code != 0) {
+        cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), st);
+        cleanup();
+        return gigl_fail(ctx, GIGL_E_RANGE, "edge endpoint outside [0, n_nodes)");
+    }
+    if (e_final > rows_cap) {
+        cleanup();
+        return gigl_fail(ctx, GIGL_E_INVALID, "edge-row buffer smaller than the CSR");
+    }
+    ER_CUDA(cudaMemcpyAsync(rows_dev, rows, sizeof(int32_t) * (size_t)e_final, cudaMemcpyDeviceToDevice, st));
+    ER_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+#undef ER_CUDA
+    *n_rows_out = e_final;
+    return GIGL_OK;
+}

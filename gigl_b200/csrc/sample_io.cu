@@ -134,15 +134,16 @@ inline uint8_t* put_node(uint8_t* p, uint32_t id, int32_t type, const float* fea
     }
     return p;
 }
-// Edge { uint32 src_node_id = 1; uint32 dst_node_id = 2; optional uint32 condensed_edge_type = 3; repeated float feature_values = 4; }
-inline size_t edge_size(uint32_t src, uint32_t dst, int32_t type) {
+// Edge { uint32 src_node_id = 1; uint32 dst_node_id = 2; optional uint32 condensed_edge_type = 3; repeated float feature_values = 4 [packed]; }
+inline size_t edge_size(uint32_t src, uint32_t dst, int32_t type, int Fe) {
     size_t n = 0;
     if (src != 0) n += 1 + varint_size(src);
     if (dst != 0) n += 1 + varint_size(dst);
     if (type >= 0) n += 1 + varint_size((uint32_t)type);
+    if (Fe > 0) n += 1 + varint_size((uint64_t)Fe * 4) + (size_t)Fe * 4;
     return n;
 }
-inline uint8_t* put_edge(uint8_t* p, uint32_t src, uint32_t dst, int32_t type) {
+inline uint8_t* put_edge(uint8_t* p, uint32_t src, uint32_t dst, int32_t type, const float* feat, int Fe) {
     if (src != 0) {
         *p++ = 0x08;
         p = put_varint(p, src);
@@ -155,38 +156,86 @@ inline uint8_t* put_edge(uint8_t* p, uint32_t src, uint32_t dst, int32_t type) {
         *p++ = 0x18;
         p = put_varint(p, (uint32_t)type);
     }
+    if (Fe > 0) {
+        *p++ = 0x22;
+        p = put_varint(p, (uint64_t)Fe * 4);
+        memcpy(p, feat, (size_t)Fe * 4);
+        p += (size_t)Fe * 4;
+    }
     return p;
 }
 
-struct RootPlan {
-    std::vector<uint32_t> nodes;                       // distinct, first-seen order: hop 1.., then the root if new
-    std::vector<std::pair<uint32_t, uint32_t>> edges;  // (src = hop-k node, dst = hop-(k-1) node), one per filled slot
+// Host-side tables the hydration joins read (all optional except the trees).
+struct Tables {
+    const int32_t* roots;
+    const int32_t* fanouts;
+    int n_hops;
+    const int32_t* const* nbr;
+    const float* x;
+    int F;
+    int32_t ntype, etype;
+    const int64_t* rowptr;  // in-CSR by destination, rows ascending (nullptr: one feature-less Edge per filled slot)
+    const int32_t* col;
+    const int32_t* edge_rows;  // CSR slot -> row of edge_feat (nullptr: slot index itself)
+    const float* ef;
+    int Fe;
 };
 
-// Walks the padded tree of root r (layout: include/gigl_b200.h).
-void plan_root(int64_t r, const int32_t* roots, const int32_t* fanouts, int n_hops, const int32_t* const* nbr, RootPlan& out) {
-    out.nodes.clear();
-    out.edges.clear();
+struct EdgeRef {
+    uint32_t src, dst;
+    int64_t row;  // row of the edge-feature table, -1 = none
+};
+
+struct RootPlan {
+    std::vector<uint32_t> nodes;     // distinct, first-seen order
+    std::vector<EdgeRef> edges;      // src = hop-k node, dst = hop-(k-1) node
+    std::vector<EdgeRef> pos_edges;  // NodeAnchorBasedLinkPredictionSample.pos_edges
+    std::vector<std::pair<uint32_t, uint32_t>> tmp;
+};
+
+// hydrateEdges: the sampled pair (src -> dst) INNER JOINs the hydrated edge table on (_from, _to)
+// (SGSPureSparkV1Task.scala:540-563): one Edge per matching record - exactly one for undirected graphs, one per
+// duplicate record for directed graphs that carry duplicates.
+void join_edge(const Tables& t, uint32_t src, uint32_t dst, std::vector<EdgeRef>& out) {
+    if (!t.rowptr) {
+        out.push_back({src, dst, -1});
+        return;
+    }
+    const int32_t* b = t.col + t.rowptr[dst];
+    const int32_t* e = t.col + t.rowptr[dst + 1];
+    auto r = std::equal_range(b, e, (int32_t)src);
+    for (const int32_t* q = r.first; q != r.second; ++q) {
+        const int64_t slot = q - t.col;
+        out.push_back({src, dst, t.Fe > 0 ? (t.edge_rows ? (int64_t)t.edge_rows[slot] : slot) : -1});
+    }
+}
+
+// Walks the padded tree of roots[r] (layout: include/gigl_b200.h), appending its edges and (non-distinct) nodes.
+void walk_tree(const Tables& t, int64_t r, RootPlan& out) {
     int64_t width_prev = 1;
-    for (int h = 0; h < n_hops; ++h) {
-        const int f = fanouts[h];
-        const int32_t* cur = nbr[h];
+    for (int h = 0; h < t.n_hops; ++h) {
+        const int f = t.fanouts[h];
+        const int32_t* cur = t.nbr[h];
         for (int64_t ps = 0; ps < width_prev; ++ps) {
             const int64_t pslot = r * width_prev + ps;
-            const int32_t parent = (h == 0) ? roots[r] : nbr[h - 1][pslot];
+            const int32_t parent = (h == 0) ? t.roots[r] : t.nbr[h - 1][pslot];
             if (parent < 0) continue;
             for (int j = 0; j < f; ++j) {
                 const int32_t c = cur[pslot * f + j];
                 if (c < 0) continue;
-                out.edges.emplace_back((uint32_t)c, (uint32_t)parent);
+                join_edge(t, (uint32_t)c, (uint32_t)parent, out.edges);
                 out.nodes.push_back((uint32_t)c);
             }
         }
         width_prev *= f;
     }
-    out.nodes.push_back((uint32_t)roots[r]);
-    // array_distinct keeping first occurrences
-    std::vector<std::pair<uint32_t, uint32_t>> tmp(out.nodes.size());
+    out.nodes.push_back((uint32_t)t.roots[r]);
+}
+
+// array_distinct keeping first occurrences
+void distinct_nodes(RootPlan& out) {
+    auto& tmp = out.tmp;
+    tmp.resize(out.nodes.size());
     for (size_t i = 0; i < out.nodes.size(); ++i) tmp[i] = {out.nodes[i], (uint32_t)i};
     std::sort(tmp.begin(), tmp.end());
     size_t m = 0;
@@ -198,21 +247,79 @@ void plan_root(int64_t r, const int32_t* roots, const int32_t* fanouts, int n_ho
     for (size_t i = 0; i < m; ++i) out.nodes[i] = tmp[i].first;
 }
 
+// array_distinct over Edge structs (src, dst, type, feature_values): two records of one (src, dst) pair collapse only
+// when their feature rows are byte-identical.
+void distinct_edges(const Tables& t, std::vector<EdgeRef>& e) {
+    std::sort(e.begin(), e.end(), [](const EdgeRef& a, const EdgeRef& b) {
+        return a.src != b.src ? a.src < b.src : a.dst != b.dst ? a.dst < b.dst : a.row < b.row;
+    });
+    size_t m = 0;
+    for (size_t i = 0; i < e.size(); ++i) {
+        bool dup = false;
+        for (size_t k = m; k-- > 0 && e[k].src == e[i].src && e[k].dst == e[i].dst;) {
+            if (e[k].row == e[i].row || t.Fe == 0 ||
+                memcmp(t.ef + (size_t)e[k].row * t.Fe, t.ef + (size_t)e[i].row * t.Fe, sizeof(float) * (size_t)t.Fe) == 0) {
+                dup = true;
+                break;
+            }
+        }
+        if (!dup) e[m++] = e[i];
+    }
+    e.resize(m);
+}
+
+void plan_root(const Tables& t, int64_t r, RootPlan& out) {
+    out.nodes.clear();
+    out.edges.clear();
+    out.pos_edges.clear();
+    walk_tree(t, r, out);
+    distinct_nodes(out);
+}
+
+// NodeAnchorBasedLinkPredictionSample of anchor roots[r]: neighbourhood = array_distinct(root's ++ every positive's)
+// (lookupDstNodeNeighborhood + the merge at NodeAnchorBasedLinkPredictionTask.scala:186-209; a directed source-only
+// anchor has an empty tree of its own and keeps the positives' neighbourhoods + itself, formNeighborhoodForSrcOnlyNodes
+// NodeAnchorBasedLinkPredictionBaseTask.scala:200-278), pos_edges = hydrateTaskBasedEdges (:280-334).
+// Returns false if the anchor has no positive (no sample: the INNER JOINs drop it).
+bool plan_anchor(const Tables& t, int64_t r, int num_pos, const int32_t* pos, const int64_t* pos_tree, RootPlan& out) {
+    out.nodes.clear();
+    out.edges.clear();
+    out.pos_edges.clear();
+    bool any = false;
+    for (int j = 0; j < num_pos; ++j) any |= pos[r * num_pos + j] >= 0;
+    if (!any) return false;
+    walk_tree(t, r, out);
+    const uint32_t root = (uint32_t)t.roots[r];
+    for (int j = 0; j < num_pos; ++j) {
+        const int32_t p = pos[r * num_pos + j];
+        if (p < 0) continue;
+        if (pos_tree[r * num_pos + j] >= 0) walk_tree(t, pos_tree[r * num_pos + j], out);
+        else out.nodes.push_back((uint32_t)p);
+        join_edge(t, root, (uint32_t)p, out.pos_edges);  // (_src_node = root, _dst_node = positive)
+    }
+    // first-seen order with the root's own neighbourhood first
+    distinct_nodes(out);
+    distinct_edges(t, out.edges);
+    return !out.pos_edges.empty();
+}
+
 struct Sizes {
-    size_t root_node, graph, labels, message;
+    size_t root_node, graph, labels, pos, message;
 };
 
-Sizes message_sizes(const RootPlan& pl, uint32_t root, int32_t ntype, int32_t etype, int F, bool with_label, int32_t label,
-                    size_t label_type_len) {
+inline const float* ef_row(const Tables& t, const EdgeRef& e) { return (t.Fe > 0 && e.row >= 0) ? t.ef + (size_t)e.row * t.Fe : nullptr; }
+inline int ef_len(const Tables& t, const EdgeRef& e) { return (t.Fe > 0 && e.row >= 0) ? t.Fe : 0; }
+
+Sizes message_sizes(const Tables& t, const RootPlan& pl, uint32_t root, bool with_label, int32_t label, size_t label_type_len) {
     Sizes s{};
-    s.root_node = node_size(root, ntype, F);
+    s.root_node = node_size(root, t.ntype, t.F);
     s.graph = 0;
     for (uint32_t v : pl.nodes) {
-        const size_t ns = node_size(v, ntype, F);
+        const size_t ns = node_size(v, t.ntype, t.F);
         s.graph += 1 + varint_size(ns) + ns;
     }
     for (const auto& e : pl.edges) {
-        const size_t es = edge_size(e.first, e.second, etype);
+        const size_t es = edge_size(e.src, e.dst, t.etype, ef_len(t, e));
         s.graph += 1 + varint_size(es) + es;
     }
     s.labels = 0;
@@ -222,10 +329,136 @@ Sizes message_sizes(const RootPlan& pl, uint32_t root, int32_t ntype, int32_t et
         if (label != 0) ls += 1 + varint_size((uint64_t)(int64_t)label);  // int32: negative values sign-extend to 10 bytes
         s.labels = 1 + varint_size(ls) + ls;
     }
+    s.pos = 0;
+    for (const auto& e : pl.pos_edges) {
+        const size_t es = edge_size(e.src, e.dst, t.etype, ef_len(t, e));
+        s.pos += 1 + varint_size(es) + es;
+    }
     s.message = 1 + varint_size(s.root_node) + s.root_node;
     if (s.graph > 0) s.message += 1 + varint_size(s.graph) + s.graph;
-    s.message += s.labels;
+    s.message += s.labels + s.pos;
     return s;
+}
+
+inline uint8_t* put_graph_body(const Tables& t, const RootPlan& pl, uint8_t* p) {
+    // Graph { repeated Node nodes = 2; repeated Edge edges = 3; }
+    for (uint32_t v : pl.nodes) {
+        *p++ = 0x12;
+        p = put_varint(p, node_size(v, t.ntype, t.F));
+        p = put_node(p, v, t.ntype, t.F > 0 ? t.x + (size_t)v * t.F : nullptr, t.F);
+    }
+    for (const auto& e : pl.edges) {
+        *p++ = 0x1A;
+        p = put_varint(p, edge_size(e.src, e.dst, t.etype, ef_len(t, e)));
+        p = put_edge(p, e.src, e.dst, t.etype, ef_row(t, e), ef_len(t, e));
+    }
+    return p;
+}
+
+int encode_samples(int32_t kind, int64_t n_roots, int64_t n_emit, const Tables& t, const int32_t* labels, const char* label_type,
+                   int32_t num_pos, const int32_t* pos, const int64_t* pos_tree, int32_t tfrecord_framing, uint8_t** out,
+                   int64_t* out_bytes, int64_t* record_offsets) {
+    *out = nullptr;
+    *out_bytes = 0;
+    const size_t lt_len = label_type ? strlen(label_type) : 0;
+    std::vector<int64_t> rec((size_t)n_emit + 1, 0);
+    const int64_t no_label = INT32_MIN;
+    // two passes over the roots: sizes, then bytes
+    uint8_t* buf = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma omp parallel
+        {
+            RootPlan pl;
+#pragma omp for schedule(dynamic, 256)
+            for (int64_t r = 0; r < n_emit; ++r) {
+                if (pass == 1 && rec[(size_t)r + 1] == rec[(size_t)r]) continue;
+                const uint32_t root = (uint32_t)t.roots[r];
+                int32_t label = 0;
+                if (kind == 1) {
+                    label = labels[root];
+                    if (label == no_label) continue;  // unlabeled node: no SupervisedNodeClassificationSample (inner join with the labels)
+                }
+                if (kind == 2) {
+                    if (!plan_anchor(t, r, num_pos, pos, pos_tree, pl)) continue;
+                } else {
+                    plan_root(t, r, pl);
+                }
+                const Sizes s = message_sizes(t, pl, root, kind == 1, label, lt_len);
+                if (pass == 0) {
+                    rec[(size_t)r + 1] = (int64_t)s.message + (tfrecord_framing ? 16 : 0);
+                    continue;
+                }
+                uint8_t* p = buf + rec[(size_t)r];
+                uint8_t* payload = p;
+                if (tfrecord_framing) {
+                    const uint64_t len = s.message;
+                    memcpy(p, &len, 8);
+                    const uint32_t c = mask_crc(crc32c(p, 8));
+                    memcpy(p + 8, &c, 4);
+                    p += 12;
+                    payload = p;
+                }
+                // root_node = 1
+                *p++ = 0x0A;
+                p = put_varint(p, s.root_node);
+                p = put_node(p, root, t.ntype, t.F > 0 ? t.x + (size_t)root * t.F : nullptr, t.F);
+                if (kind == 2) {
+                    // neighborhood = 3, pos_edges = 4 (hard_neg_edges = 2 and neg_edges = 5 stay empty:
+                    // castToTrainingSampleProtoSchema, NodeAnchorBasedLinkPredictionBaseTask.scala:388-406)
+                    if (s.graph > 0) {
+                        *p++ = 0x1A;
+                        p = put_varint(p, s.graph);
+                        p = put_graph_body(t, pl, p);
+                    }
+                    for (const auto& e : pl.pos_edges) {
+                        *p++ = 0x22;
+                        p = put_varint(p, edge_size(e.src, e.dst, t.etype, ef_len(t, e)));
+                        p = put_edge(p, e.src, e.dst, t.etype, ef_row(t, e), ef_len(t, e));
+                    }
+                } else {
+                    // neighborhood = 2
+                    if (s.graph > 0) {
+                        *p++ = 0x12;
+                        p = put_varint(p, s.graph);
+                        p = put_graph_body(t, pl, p);
+                    }
+                }
+                // root_node_labels = 3 : Label { string label_type = 1; int32 label = 2; }
+                if (kind == 1) {
+                    size_t ls = 0;
+                    if (lt_len) ls += 1 + varint_size(lt_len) + lt_len;
+                    if (label != 0) ls += 1 + varint_size((uint64_t)(int64_t)label);
+                    *p++ = 0x1A;
+                    p = put_varint(p, ls);
+                    if (lt_len) {
+                        *p++ = 0x0A;
+                        p = put_varint(p, lt_len);
+                        memcpy(p, label_type, lt_len);
+                        p += lt_len;
+                    }
+                    if (label != 0) {
+                        *p++ = 0x10;
+                        p = put_varint(p, (uint64_t)(int64_t)label);
+                    }
+                }
+                if (tfrecord_framing) {
+                    const uint32_t c = mask_crc(crc32c(payload, (size_t)(p - payload)));
+                    memcpy(p, &c, 4);
+                    p += 4;
+                }
+            }
+        }
+        if (pass == 0) {
+            for (int64_t r = 0; r < n_emit; ++r) rec[(size_t)r + 1] += rec[(size_t)r];
+            const int64_t total = rec[(size_t)n_emit];
+            buf = (uint8_t*)malloc((size_t)(total > 0 ? total : 1));
+            if (!buf) return GIGL_E_NOMEM;
+        }
+    }
+    if (record_offsets) memcpy(record_offsets, rec.data(), sizeof(int64_t) * ((size_t)n_emit + 1));
+    *out = buf;
+    *out_bytes = rec[(size_t)n_emit];
+    return GIGL_OK;
 }
 
 }  // namespace
@@ -240,109 +473,33 @@ int gigl_encode_samples_host(int32_t kind, int64_t n_roots, const int32_t* roots
                              const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
                              int32_t condensed_edge_type, const int32_t* labels, const char* label_type, int32_t tfrecord_framing,
                              uint8_t** out, int64_t* out_bytes, int64_t* record_offsets) {
-    if (!out || !out_bytes || n_roots < 0 || n_hops < 1 || n_hops > GIGL_MAX_HOPS || !fanouts || !nbr || (n_roots > 0 && !roots))
-        return GIGL_E_INVALID;
     if (kind != 0 && kind != 1) return GIGL_E_INVALID;
+    return gigl_encode_samples_ex_host(kind, n_roots, n_roots, roots, fanouts, n_hops, nbr, x, F, condensed_node_type, condensed_edge_type,
+                                       nullptr, nullptr, nullptr, nullptr, 0, labels, label_type, 0, nullptr, nullptr, tfrecord_framing,
+                                       out, out_bytes, record_offsets);
+}
+
+int gigl_encode_samples_ex_host(int32_t kind, int64_t n_roots, int64_t n_emit, const int32_t* roots, const int32_t* fanouts,
+                                int32_t n_hops, const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
+                                int32_t condensed_edge_type, const int64_t* rowptr, const int32_t* col, const int32_t* edge_rows,
+                                const float* edge_feat, int32_t Fe, const int32_t* labels, const char* label_type, int32_t num_pos,
+                                const int32_t* pos, const int64_t* pos_tree, int32_t tfrecord_framing, uint8_t** out,
+                                int64_t* out_bytes, int64_t* record_offsets) {
+    if (!out || !out_bytes || n_roots < 0 || n_emit < 0 || n_emit > n_roots || n_hops < 1 || n_hops > GIGL_MAX_HOPS || !fanouts || !nbr ||
+        (n_roots > 0 && !roots))
+        return GIGL_E_INVALID;
+    if (kind < 0 || kind > 2) return GIGL_E_INVALID;
     if (kind == 1 && !labels) return GIGL_E_INVALID;
+    if (kind == 2 && (num_pos < 1 || !pos || !pos_tree)) return GIGL_E_INVALID;
     if (F < 0 || (F > 0 && !x)) return GIGL_E_INVALID;
-    *out = nullptr;
-    *out_bytes = 0;
-    const size_t lt_len = label_type ? strlen(label_type) : 0;
-    std::vector<int64_t> rec((size_t)n_roots + 1, 0);
-    const int64_t no_label = INT32_MIN;
-    // pass 1: sizes
-#pragma omp parallel
-    {
-        RootPlan pl;
-#pragma omp for schedule(dynamic, 256)
-        for (int64_t r = 0; r < n_roots; ++r) {
-            const uint32_t root = (uint32_t)roots[r];
-            int32_t label = 0;
-            if (kind == 1) {
-                label = labels[root];
-                if (label == no_label) {  // unlabeled node: no SupervisedNodeClassificationSample (inner join with the labels)
-                    rec[(size_t)r + 1] = 0;
-                    continue;
-                }
-            }
-            plan_root(r, roots, fanouts, n_hops, nbr, pl);
-            const Sizes s = message_sizes(pl, root, condensed_node_type, condensed_edge_type, F, kind == 1, label, lt_len);
-            rec[(size_t)r + 1] = (int64_t)s.message + (tfrecord_framing ? 16 : 0);
-        }
-    }
-    for (int64_t r = 0; r < n_roots; ++r) rec[(size_t)r + 1] += rec[(size_t)r];
-    const int64_t total = rec[(size_t)n_roots];
-    uint8_t* buf = (uint8_t*)malloc((size_t)(total > 0 ? total : 1));
-    if (!buf) return GIGL_E_NOMEM;
-    // pass 2: bytes
-#pragma omp parallel
-    {
-        RootPlan pl;
-#pragma omp for schedule(dynamic, 256)
-        for (int64_t r = 0; r < n_roots; ++r) {
-            if (rec[(size_t)r + 1] == rec[(size_t)r]) continue;
-            const uint32_t root = (uint32_t)roots[r];
-            const int32_t label = kind == 1 ? labels[root] : 0;
-            plan_root(r, roots, fanouts, n_hops, nbr, pl);
-            const Sizes s = message_sizes(pl, root, condensed_node_type, condensed_edge_type, F, kind == 1, label, lt_len);
-            uint8_t* p = buf + rec[(size_t)r];
-            uint8_t* payload = p;
-            if (tfrecord_framing) {
-                const uint64_t len = s.message;
-                memcpy(p, &len, 8);
-                const uint32_t c = mask_crc(crc32c(p, 8));
-                memcpy(p + 8, &c, 4);
-                p += 12;
-                payload = p;
-            }
-            // root_node = 1
-            *p++ = 0x0A;
-            p = put_varint(p, s.root_node);
-            p = put_node(p, root, condensed_node_type, F > 0 ? x + (size_t)root * F : nullptr, F);
-            // neighborhood = 2 : Graph { repeated Node nodes = 2; repeated Edge edges = 3; }
-            if (s.graph > 0) {
-                *p++ = 0x12;
-                p = put_varint(p, s.graph);
-                for (uint32_t v : pl.nodes) {
-                    *p++ = 0x12;
-                    p = put_varint(p, node_size(v, condensed_node_type, F));
-                    p = put_node(p, v, condensed_node_type, F > 0 ? x + (size_t)v * F : nullptr, F);
-                }
-                for (const auto& e : pl.edges) {
-                    *p++ = 0x1A;
-                    p = put_varint(p, edge_size(e.first, e.second, condensed_edge_type));
-                    p = put_edge(p, e.first, e.second, condensed_edge_type);
-                }
-            }
-            // root_node_labels = 3 : Label { string label_type = 1; int32 label = 2; }
-            if (kind == 1) {
-                size_t ls = 0;
-                if (lt_len) ls += 1 + varint_size(lt_len) + lt_len;
-                if (label != 0) ls += 1 + varint_size((uint64_t)(int64_t)label);
-                *p++ = 0x1A;
-                p = put_varint(p, ls);
-                if (lt_len) {
-                    *p++ = 0x0A;
-                    p = put_varint(p, lt_len);
-                    memcpy(p, label_type, lt_len);
-                    p += lt_len;
-                }
-                if (label != 0) {
-                    *p++ = 0x10;
-                    p = put_varint(p, (uint64_t)(int64_t)label);
-                }
-            }
-            if (tfrecord_framing) {
-                const uint32_t c = mask_crc(crc32c(payload, (size_t)(p - payload)));
-                memcpy(p, &c, 4);
-                p += 4;
-            }
-        }
-    }
-    if (record_offsets) memcpy(record_offsets, rec.data(), sizeof(int64_t) * ((size_t)n_roots + 1));
-    *out = buf;
-    *out_bytes = total;
-    return GIGL_OK;
+    if (Fe < 0 || (Fe > 0 && (!edge_feat || !rowptr || !col))) return GIGL_E_INVALID;
+    if ((rowptr == nullptr) != (col == nullptr)) return GIGL_E_INVALID;
+    if (kind == 2)
+        for (int64_t i = 0; i < n_emit * num_pos; ++i)
+            if (pos_tree[i] >= n_roots || (pos[i] >= 0 && pos_tree[i] >= 0 && roots[pos_tree[i]] != pos[i])) return GIGL_E_INVALID;
+    const Tables t{roots, fanouts, n_hops, nbr, x, F, condensed_node_type, condensed_edge_type, rowptr, col, edge_rows, edge_feat, Fe};
+    return encode_samples(kind, n_roots, n_emit, t, labels, label_type, num_pos, pos, pos_tree, tfrecord_framing, out, out_bytes,
+                          record_offsets);
 }
 
 // ---- TFRecord reading + tf.Example decoding ----------------------------------------------------------

@@ -121,6 +121,17 @@ class Context:
         return out
 
     # ---- aggregate, device tensors --------------------------------------------------------
+    def edge_rows_host(self, n_nodes: int, src, dst, is_graph_directed: bool) -> np.ndarray:
+        """Input edge record that hydrates every slot of the in-CSR `Graph.from_edges_host` builds from the same
+        arguments (gigl_edge_rows_host)."""
+        src, dst = _np(src, np.int32), _np(dst, np.int32)
+        cap = len(src) * (1 if is_graph_directed else 2)
+        rows = np.empty(max(cap, 1), dtype=np.int32)
+        n = C.c_int64()
+        check(self._L.gigl_edge_rows_host(self.handle, n_nodes, len(src), _hp(src), _hp(dst), int(is_graph_directed), _hp(rows), cap,
+                                          C.byref(n)), self.handle)
+        return rows[: n.value]
+
     def csr_from_coo(self, n: int, edge_index):
         """edge_index: int64 CUDA tensor [2, e] -> (rowptr int64 [n+1], col int32 [e]), rows stable."""
         import torch

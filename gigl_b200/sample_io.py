@@ -89,15 +89,25 @@ class ExampleTable:
         return out[:, 0] if w == 1 and width is None else out
 
 
+_KINDS = {"rnn": 0, "snc": 1, "nablp": 2}
+
+
 def encode_samples(roots, fanouts, nbr, x: Optional[np.ndarray] = None, kind: str = "rnn", condensed_node_type: int = 0,
                    condensed_edge_type: int = 0, labels: Optional[np.ndarray] = None, label_type: str = "",
-                   tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
-    """Padded-tree index sets -> serialized RootedNodeNeighborhood ('rnn') or SupervisedNodeClassificationSample ('snc')
-    messages, one per root.  Returns (bytes, record_offsets [n_roots + 1])."""
+                   tfrecord_framing: bool = True, csr: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+                   edge_rows: Optional[np.ndarray] = None, edge_feat: Optional[np.ndarray] = None, n_emit: Optional[int] = None,
+                   pos: Optional[np.ndarray] = None, pos_tree: Optional[np.ndarray] = None) -> Tuple[bytes, np.ndarray]:
+    """Padded-tree index sets -> serialized RootedNodeNeighborhood ('rnn'), SupervisedNodeClassificationSample ('snc') or
+    NodeAnchorBasedLinkPredictionSample ('nablp') messages, one per emitting root (include/gigl_b200.h,
+    gigl_encode_samples_ex_host).  `csr` = host (rowptr, col) of the in-CSR turns every sampled pair into one Edge per
+    matching edge record (the reference's join) and, with `edge_feat` [records, Fe] + `edge_rows`, hydrates edge
+    features.  'nablp': the first `n_emit` roots are anchors with positives `pos` [n_emit, num_pos] (-1 = none) whose
+    trees sit at `pos_tree` (indices into roots).  Returns (bytes, record_offsets [n_emit + 1])."""
     L = _capi.lib()
     roots = np.ascontiguousarray(roots, dtype=np.int32)
     fan = np.ascontiguousarray(fanouts, dtype=np.int32)
     nbr = [np.ascontiguousarray(a, dtype=np.int32) for a in nbr]
+    n_emit = len(roots) if n_emit is None else int(n_emit)
     F = 0
     xp = None
     if x is not None:
@@ -108,14 +118,34 @@ def encode_samples(roots, fanouts, nbr, x: Optional[np.ndarray] = None, kind: st
     if kind == "snc":
         labels = np.ascontiguousarray(labels, dtype=np.int32)
         lp = labels.ctypes.data
+    rp = cl = er = efp = None
+    Fe = 0
+    if csr is not None:
+        rowptr = np.ascontiguousarray(csr[0], dtype=np.int64)
+        col = np.ascontiguousarray(csr[1], dtype=np.int32)
+        rp, cl = rowptr.ctypes.data, col.ctypes.data
+        if edge_feat is not None and edge_feat.size:
+            edge_feat = np.ascontiguousarray(edge_feat, dtype=np.float32)
+            Fe = edge_feat.shape[1]
+            efp = edge_feat.ctypes.data
+            if edge_rows is not None:
+                edge_rows = np.ascontiguousarray(edge_rows, dtype=np.int32)
+                er = edge_rows.ctypes.data
+    num_pos = 0
+    pp = ptp = None
+    if kind == "nablp":
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(n_emit, -1)
+        pos_tree = np.ascontiguousarray(pos_tree, dtype=np.int64).reshape(n_emit, -1)
+        num_pos = pos.shape[1]
+        pp, ptp = pos.ctypes.data, pos_tree.ctypes.data
     pn = (C.c_void_p * len(fan))(*[a.ctypes.data for a in nbr])
     out = C.c_void_p()
     nbytes = C.c_int64()
-    offs = np.zeros(len(roots) + 1, dtype=np.int64)
-    rc = L.gigl_encode_samples_host(0 if kind == "rnn" else 1, len(roots), roots.ctypes.data, fan.ctypes.data, len(fan), pn, xp, F,
-                                    condensed_node_type, condensed_edge_type, lp, label_type.encode(), int(tfrecord_framing),
-                                    C.byref(out), C.byref(nbytes), offs.ctypes.data)
-    _check(rc, "gigl_encode_samples_host")
+    offs = np.zeros(n_emit + 1, dtype=np.int64)
+    rc = L.gigl_encode_samples_ex_host(_KINDS[kind], len(roots), n_emit, roots.ctypes.data, fan.ctypes.data, len(fan), pn, xp, F,
+                                       condensed_node_type, condensed_edge_type, rp, cl, er, efp, Fe, lp, label_type.encode(),
+                                       num_pos, pp, ptp, int(tfrecord_framing), C.byref(out), C.byref(nbytes), offs.ctypes.data)
+    _check(rc, "gigl_encode_samples_ex_host")
     try:
         data = C.string_at(out.value, nbytes.value)
     finally:
@@ -237,6 +267,23 @@ def parse_sample(buf: bytes) -> dict:
                 elif f2 == 2:
                     lab["label"] = g - (1 << 64) if g >> 63 else g
             d["root_node_labels"].append(lab)
+    return d
+
+
+def parse_nablp_sample(buf: bytes) -> dict:
+    """NodeAnchorBasedLinkPredictionSample bytes -> plain dict (training_samples_schema.proto:34-53)."""
+    d = {"root_node": None, "nodes": [], "edges": [], "pos_edges": [], "hard_neg_edges": [], "neg_edges": []}
+    for fn, _, v in parse_fields(buf):
+        if fn == 1:
+            d["root_node"] = _parse_node(v)
+        elif fn == 3:
+            for f2, _, g in parse_fields(v):
+                if f2 == 2:
+                    d["nodes"].append(_parse_node(g))
+                elif f2 == 3:
+                    d["edges"].append(_parse_edge(g))
+        elif fn in (2, 4, 5):
+            d[{2: "hard_neg_edges", 4: "pos_edges", 5: "neg_edges"}[fn]].append(_parse_edge(v))
     return d
 
 

@@ -4,23 +4,34 @@
 
 the argv of `Main.main` (scala/subgraph_sampler/src/main/scala/Main.scala:12-16; submitted by
 python/gigl/src/subgraph_sampler/subgraph_sampler.py:290-300).  It reads the node / edge tf.Example TFRecords named by
-`sharedConfig.preprocessedMetadataUri`, keeps the graph as a sorted CSR in HBM, samples every node's 2-hop
-neighbourhood with the CUDA kernel (GiGL's deterministic hash permutation, `samplingSeed = 42`), hydrates and writes
-`RootedNodeNeighborhood` TFRecords to `...unlabeledTfrecordUriPrefix` FIRST and then
-`SupervisedNodeClassificationSample` TFRecords to `...labeledTfrecordUriPrefix`
-(SupervisedNodeClassificationTask.scala:29-124).
+`sharedConfig.preprocessedMetadataUri`, keeps the graph as a sorted CSR in HBM, samples every node's k-hop
+neighbourhood with the CUDA kernel (GiGL's deterministic hash permutation, `samplingSeed = 42`), hydrates node and edge
+features and writes, picking the task as `TaskRunner.runTask` does (libs/TaskRunner.scala:16-82):
 
-Scope (DESIGN.md section 8): homogeneous graphs, node-classification task output, local / file:// URIs, node features;
-edge features and the link-prediction sample types are not emitted yet.  The reference's default permutation strategy is
-the unseedable Spark shuffle; this implementation always uses the seeded hash permutation (a valid uniform sample;
-bit-exact to the reference's `permutation_strategy: deterministic`).
+  * node-based task  - `RootedNodeNeighborhood` TFRecords to `...unlabeledTfrecordUriPrefix` FIRST, then
+    `SupervisedNodeClassificationSample` TFRecords to `...labeledTfrecordUriPrefix`
+    (SupervisedNodeClassificationTask.scala:29-124);
+  * node-anchor-based link prediction - `RootedNodeNeighborhood` TFRecords of every node to
+    `nodeTypeToRandomNegativeTfrecordUriPrefix[dstNodeType]` FIRST, then `NodeAnchorBasedLinkPredictionSample`
+    TFRecords (positives = seeded out-edge samples, permutation call no. 3; merged neighbourhood of root and
+    positives) to `nodeAnchorBasedLinkPredictionOutput.tfrecordUriPrefix` (NodeAnchorBasedLinkPredictionTask.scala:28-312).
+
+Fanouts come from `numNeighborsToSample` (both hops, as the pure-Spark tasks do) or, when present, from
+`subgraphSamplingStrategy` (`globalRandomUniform`, or a linear `messagePassingPaths` chain of INCOMING `randomUniform`
+ops over the one edge type - the per-hop fanouts that only the reference's spark35 path can express,
+scala_spark35/.../SamplingOpDAG.scala:19-51).
+
+Scope (DESIGN.md): homogeneous graphs (one node type, one edge type), local / file:// URIs.  User-defined positive /
+negative labels, branching sampling DAGs and `gs://` are not implemented and raise.  The reference's default
+permutation strategy is the unseedable Spark shuffle; this implementation always uses the seeded hash permutation (a
+valid uniform sample; bit-exact to the reference's `permutation_strategy: deterministic`).
 """
 from __future__ import annotations
 
 import os
 import sys
 import time
-from typing import Optional
+from typing import List, Optional
 
 import numpy as np
 import yaml
@@ -49,6 +60,56 @@ def _first(d: dict):
     return int(k), d[k]
 
 
+def fanouts_from_config(sgs: dict) -> List[int]:
+    """Per-hop fanouts of `datasetConfig.subgraphSamplerConfig`."""
+    strat = sgs.get("subgraphSamplingStrategy") or {}
+    if "globalRandomUniform" in strat:
+        gru = strat["globalRandomUniform"]
+        f = int((gru.get("randomUniformSpec") or {}).get("numNodesToSample", 0))
+        hops = int(gru.get("numHops", 0))
+        if f < 1 or hops < 1:
+            raise ValueError("globalRandomUniform needs numHops >= 1 and randomUniformSpec.numNodesToSample >= 1")
+        return [f] * hops
+    if "messagePassingPaths" in strat:
+        paths = strat["messagePassingPaths"].get("paths") or []
+        if len(paths) != 1:
+            raise ValueError("exactly one messagePassingPath (one root node type) is supported")
+        ops = paths[0].get("samplingOps") or []
+        by_input = {}
+        for op in ops:
+            ins = op.get("inputOpNames") or []
+            if len(ins) > 1 or "randomUniform" not in op or op.get("samplingDirection", "INCOMING") != "INCOMING":
+                raise ValueError("only linear chains of INCOMING randomUniform sampling ops are supported")
+            key = ins[0] if ins else None
+            if key in by_input:
+                raise ValueError("branching sampling DAGs are not supported")
+            by_input[key] = op
+        fan, cur = [], None
+        while cur in by_input:
+            op = by_input[cur]
+            fan.append(int(op["randomUniform"].get("numNodesToSample", 0)))
+            cur = op.get("opName")
+        if len(fan) != len(ops) or not fan or min(fan) < 1:
+            raise ValueError("sampling ops do not form one chain from the root with numNodesToSample >= 1")
+        return fan
+    fanout = int(sgs.get("numNeighborsToSample", 0))
+    if fanout < 1:
+        raise ValueError("datasetConfig.subgraphSamplerConfig.numNeighborsToSample must be >= 1")
+    return [fanout, fanout]  # numHops is deprecated and fixed to 2 in the reference (scala/subgraph_sampler/README.md:39-42)
+
+
+def _feature_matrix(table: "sio.ExampleTable", keys) -> Optional[np.ndarray]:
+    """flatten(array(cast(col as array<float>) ...)) over the feature keys IN METADATA ORDER; scalars become
+    1-element arrays (SGSPureSparkV1Task.scala:90-104, 176-193)."""
+    cols = [table.column(k, "float32", table.width(k)) for k in (keys or [])]
+    return np.concatenate(cols, axis=1) if cols else None
+
+
+def _write(dir_: str, part: int, data: bytes) -> None:
+    with open(os.path.join(dir_, f"part-{part:05d}.tfrecord"), "wb") as f:
+        f.write(data)
+
+
 def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] = None, root: Optional[str] = None,
         device: int = 0, batch_roots: int = 1 << 20, log=print) -> dict:
     root = root or os.getcwd()
@@ -57,55 +118,75 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
     shared = cfg.get("sharedConfig", {})
     meta = _load_yaml(shared["preprocessedMetadataUri"], root)
     sgs = cfg.get("datasetConfig", {}).get("subgraphSamplerConfig", {})
-    fanout = int(sgs.get("numNeighborsToSample", 0))
-    if fanout < 1:
-        raise ValueError("datasetConfig.subgraphSamplerConfig.numNeighborsToSample must be >= 1")
-    fanouts = [fanout, fanout]  # numHops is deprecated and fixed to 2 in the reference (scala/subgraph_sampler/README.md:39-42)
+    fanouts = fanouts_from_config(sgs)
     directed = bool(shared.get("isGraphDirected", False))
-    skip_labeled = bool(shared.get("shouldSkipTraining", False)) and bool(shared.get("shouldSkipModelEvaluation", False))
+    skip_main = bool(shared.get("shouldSkipTraining", False)) and bool(shared.get("shouldSkipModelEvaluation", False))
     max_train = int(sgs.get("numMaxTrainingSamplesToOutput", 0) or 0)
-    out = shared["flattenedGraphMetadata"]["supervisedNodeClassificationOutput"]
+    task_meta = cfg.get("taskMetadata", {})
+    is_nablp = "nodeAnchorBasedLinkPredictionTaskMetadata" in task_meta
+    flat = shared["flattenedGraphMetadata"]
 
     ntype, nmeta = _first(meta["condensedNodeTypeToPreprocessedMetadata"])
     etype, emeta = _first(meta["condensedEdgeTypeToPreprocessedMetadata"])
-    # ---- node table: ids, features in featureKeys order (scalars become 1-element arrays, :90-104), labels
+    if is_nablp and (emeta.get("positiveEdgeInfo") or emeta.get("negativeEdgeInfo")):
+        raise NotImplementedError("user-defined positive / negative edges (UserDefinedLabelsNodeAnchorBasedLinkPredictionTask)")
+    # ---- node table: ids, features in featureKeys order, labels
     nodes = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(nmeta["tfrecordUriPrefix"], root)))
     node_id = nodes.column(nmeta["nodeIdKey"], "int64").astype(np.int64)
-    cols = [nodes.column(k, "float32", nodes.width(k)) for k in (nmeta.get("featureKeys") or [])]
-    # ---- edge table
-    edges = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(emeta["mainEdgeInfo"]["tfrecordUriPrefix"], root)))
+    feat = _feature_matrix(nodes, nmeta.get("featureKeys"))
+    # ---- edge table (+ features)
+    main = emeta["mainEdgeInfo"]
+    edges = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(main["tfrecordUriPrefix"], root)))
     src = edges.column(emeta["srcNodeIdKey"], "int64")
     dst = edges.column(emeta["dstNodeIdKey"], "int64")
+    ef = _feature_matrix(edges, main.get("featureKeys"))
     n_nodes = int(max(node_id.max(initial=-1), src.max(initial=-1), dst.max(initial=-1)) + 1)
     x = None
-    if cols:
-        feat = np.concatenate(cols, axis=1)
+    if feat is not None:
         x = np.zeros((n_nodes, feat.shape[1]), dtype=np.float32)
         x[node_id] = feat
-    labels = None
-    label_key = (nmeta.get("labelKeys") or [None])[0]
-    if label_key and not skip_labeled:
-        labels = np.full(n_nodes, sio.INT32_MIN, dtype=np.int32)
-        labels[node_id] = nodes.column(label_key, "int64").astype(np.int32)
-    log(f"[{job_name}] loaded {len(node_id)} nodes (F={0 if x is None else x.shape[1]}), {len(src)} edges in {time.time() - t0:.2f}s")
+    log(f"[{job_name}] loaded {len(node_id)} nodes (F={0 if x is None else x.shape[1]}), {len(src)} edges "
+        f"(Fe={0 if ef is None else ef.shape[1]}) in {time.time() - t0:.2f}s; fanouts {fanouts}")
 
     ctx = Context(device)
-    g = Graph.from_edges_host(ctx, n_nodes, src.astype(np.int32), dst.astype(np.int32), is_graph_directed=directed)
+    src32, dst32 = src.astype(np.int32), dst.astype(np.int32)
+    g = Graph.from_edges_host(ctx, n_nodes, src32, dst32, is_graph_directed=directed)
+    # the hydration join needs the CSR on the host when edges carry features or (directed) may carry duplicate records
+    csr = g.csr_host() if (ef is not None or directed) else None
+    edge_rows = ctx.edge_rows_host(n_nodes, src32, dst32, directed) if ef is not None else None
+    hyd = dict(condensed_node_type=ntype, condensed_edge_type=etype, csr=csr, edge_rows=edge_rows, edge_feat=ef)
     roots_all = np.sort(node_id).astype(np.int32)  # every node of the node table gets exactly one RootedNodeNeighborhood
-    stats = {"n_nodes": n_nodes, "n_edges_csr": g.n_edges, "rnn": 0, "snc": 0}
+    stats = {"n_nodes": n_nodes, "n_edges_csr": g.n_edges, "rnn": 0, "snc": 0, "nablp": 0, "fanouts": fanouts}
+    t1 = time.time()
+    if is_nablp:
+        _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32, n_nodes, directed, sgs, skip_main, max_train,
+                   batch_roots, stats)
+    else:
+        _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n_nodes, skip_main, max_train, batch_roots, stats)
+    stats["seconds_sample_and_write"] = time.time() - t1
+    stats["seconds_total"] = time.time() - t0
+    log(f"[{job_name}] wrote {stats['rnn']} RootedNodeNeighborhood + {stats['snc']} SupervisedNodeClassificationSample + "
+        f"{stats['nablp']} NodeAnchorBasedLinkPredictionSample records in {stats['seconds_sample_and_write']:.2f}s")
+    return stats
+
+
+def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n_nodes, skip_main, max_train, batch_roots, stats):
+    out = flat["supervisedNodeClassificationOutput"]
+    labels = None
+    label_key = (nmeta.get("labelKeys") or [None])[0]
+    if label_key and not skip_main:
+        labels = np.full(n_nodes, sio.INT32_MIN, dtype=np.int32)
+        labels[node_id] = nodes.column(label_key, "int64").astype(np.int32)
     unl_dir = _resolve(out["unlabeledTfrecordUriPrefix"], root)
     lab_dir = _resolve(out["labeledTfrecordUriPrefix"], root)
     os.makedirs(unl_dir, exist_ok=True)
     if labels is not None:
         os.makedirs(lab_dir, exist_ok=True)
-    t1 = time.time()
-    part = 0
-    for s in range(0, len(roots_all), batch_roots):
+    for part, s in enumerate(range(0, len(roots_all), batch_roots)):
         roots = roots_all[s:s + batch_roots]
         nbr, cnt = g.sample_khop_host(roots, fanouts, base_seed=SAMPLING_SEED, first_call_no=1)
-        data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="rnn", condensed_node_type=ntype, condensed_edge_type=etype)
-        with open(os.path.join(unl_dir, f"part-{part:05d}.tfrecord"), "wb") as f:  # RootedNodeNeighborhood first
-            f.write(data)
+        data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="rnn", **hyd)
+        _write(unl_dir, part, data)  # RootedNodeNeighborhood first
         stats["rnn"] += len(roots)
         if labels is not None:
             # isolated nodes (no sampled in-edge) are NOT training samples (includeIsolatedNodesInTrainingSamples = false, :43-44)
@@ -114,17 +195,61 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
             if max_train > 0:
                 keep = roots[(cnt[0] > 0) & (labels[roots] != sio.INT32_MIN)][max(0, max_train - stats["snc"]):]
                 lab[keep] = sio.INT32_MIN
-            data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="snc", condensed_node_type=ntype, condensed_edge_type=etype,
-                                            labels=lab, label_type=label_key)
-            with open(os.path.join(lab_dir, f"part-{part:05d}.tfrecord"), "wb") as f:
-                f.write(data)
+            data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="snc", labels=lab, label_type=label_key, **hyd)
+            _write(lab_dir, part, data)
             stats["snc"] += int((np.diff(offs) > 0).sum())
-        part += 1
-    stats["seconds_sample_and_write"] = time.time() - t1
-    stats["seconds_total"] = time.time() - t0
-    log(f"[{job_name}] wrote {stats['rnn']} RootedNodeNeighborhood + {stats['snc']} SupervisedNodeClassificationSample "
-        f"records in {stats['seconds_sample_and_write']:.2f}s")
-    return stats
+
+
+def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32, n_nodes, directed, sgs, skip_main, max_train,
+               batch_roots, stats):
+    out = flat["nodeAnchorBasedLinkPredictionOutput"]
+    sup = cfg["taskMetadata"]["nodeAnchorBasedLinkPredictionTaskMetadata"]["supervisionEdgeTypes"]
+    dst_type = sup[0]["dstNodeType"]
+    neg_map = out.get("nodeTypeToRandomNegativeTfrecordUriPrefix") or {}
+    if dst_type not in neg_map:
+        raise KeyError(f"nodeTypeToRandomNegativeTfrecordUriPrefix is missing the dstNodeType {dst_type!r} of the first supervision "
+                       "edge type")  # the reference throws here too (NodeAnchorBasedLinkPredictionTask.scala:101-108)
+    rnn_dir = _resolve(neg_map[dst_type], root)
+    main_dir = _resolve(out["tfrecordUriPrefix"], root)
+    os.makedirs(rnn_dir, exist_ok=True)
+    num_pos = int(sgs.get("numPositiveSamples", 0))
+    g_out = None
+    if not skip_main:
+        if num_pos < 1:
+            raise ValueError("datasetConfig.subgraphSamplerConfig.numPositiveSamples must be >= 1")
+        os.makedirs(main_dir, exist_ok=True)
+        # positives walk the out-CSR (row u = sorted destinations of u); undirected graphs are symmetric
+        g_out = g if not directed else Graph.from_edges_host(ctx, n_nodes, src32, dst32, is_graph_directed=True, by_source=True)
+    for part, s in enumerate(range(0, len(roots_all), batch_roots)):
+        roots = roots_all[s:s + batch_roots]
+        n = len(roots)
+        pos = None
+        sample_roots = roots
+        if g_out is not None:
+            pos, pcnt = g_out.sample_positives_host(roots, num_pos, base_seed=SAMPLING_SEED, call_no=3)
+            pos = pos.reshape(n, num_pos)
+            if max_train > 0:
+                # numMaxTrainingSamplesToOutput: the reference keeps an arbitrary `LIMIT n` of the anchors
+                # (downsampleNumberOfNodes, SGSPureSparkV1Task.scala:1042-1081); this keeps the first n by node id
+                anchors = np.flatnonzero(pcnt > 0)
+                pos[anchors[max(0, max_train - stats["nablp"]):]] = -1
+            extra = np.setdiff1d(pos[pos >= 0], roots)  # positives whose trees are not in this batch
+            sample_roots = np.concatenate([roots, extra.astype(np.int32)])
+        nbr, cnt = g.sample_khop_host(sample_roots, fanouts, base_seed=SAMPLING_SEED, first_call_no=1)
+        width, own = 1, []
+        for f in fanouts:
+            width *= f
+            own.append(nbr[len(own)][: n * width])
+        data, _ = sio.encode_samples(roots, fanouts, own, x, kind="rnn", **hyd)
+        _write(rnn_dir, part, data)  # RootedNodeNeighborhood (random negatives) first
+        stats["rnn"] += n
+        if pos is not None:
+            order = np.argsort(sample_roots, kind="stable")
+            where = order[np.searchsorted(sample_roots[order], np.where(pos >= 0, pos, sample_roots[0]))]
+            pos_tree = np.where(pos >= 0, where, -1).astype(np.int64)
+            data, offs = sio.encode_samples(sample_roots, fanouts, nbr, x, kind="nablp", n_emit=n, pos=pos, pos_tree=pos_tree, **hyd)
+            _write(main_dir, part, data)
+            stats["nablp"] += int((np.diff(offs) > 0).sum())
 
 
 def main(argv=None) -> int:

@@ -116,6 +116,16 @@ int gigl_graph_from_edges_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, 
 int gigl_graph_from_edges_dev(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,
                               const int32_t* dst_dev, int32_t is_graph_directed, int32_t by_source,
                               gigl_graph** out);
+/*
+ * Edge-row map of the in-CSR that gigl_graph_from_edges_host builds from the same arguments: edge_rows[j] = index of
+ * the input edge record that hydrates CSR slot j (its feature row), what hydrateEdges' join on (_from, _to) looks up
+ * (SGSPureSparkV1Task.scala:540-563).  Directed: slot order among equal (dst, src) keys is input order.  Undirected:
+ * one record per (least, greatest) pair survives (enforceBidirectionalization :218-258 keeps an arbitrary duplicate;
+ * this build keeps the lowest record index) and serves both orientations.  rows_cap = capacity of edge_rows (>= the
+ * CSR's edge count); *n_rows = entries written.
+ */
+int gigl_edge_rows_host(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                        int32_t is_graph_directed, int32_t* edge_rows, int64_t rows_cap, int64_t* n_rows);
 int gigl_graph_num_nodes(const gigl_graph* g, int64_t* n_nodes, int64_t* n_edges);
 /* Device pointers of the resident CSR (for bindings that want to read it back / reuse it). */
 int gigl_graph_device_ptrs(const gigl_graph* g, const int64_t** rowptr_dev, const int32_t** col_dev);
@@ -380,6 +390,28 @@ int gigl_encode_samples_host(int32_t kind, int64_t n_roots, const int32_t* roots
                              const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
                              int32_t condensed_edge_type, const int32_t* labels, const char* label_type, int32_t tfrecord_framing,
                              uint8_t** out, int64_t* out_bytes, int64_t* record_offsets);
+/*
+ * Extended form: edge hydration and the link-prediction sample type.
+ *   rowptr / col (host copies of the in-CSR, optional): every sampled pair (src -> dst) becomes one Edge per matching
+ *     edge record, which is hydrateEdges' INNER JOIN on (_from, _to) (SGSPureSparkV1Task.scala:540-563): one for
+ *     undirected graphs, one per duplicate record for directed graphs that carry duplicates.  With edge_feat
+ *     [n_records, Fe] the Edge carries feature_values = edge_feat[edge_rows[slot]] (edge_rows from gigl_edge_rows_host;
+ *     NULL = the CSR slot index itself).
+ *   kind 2: NodeAnchorBasedLinkPredictionSample { root_node, pos_edges, neighborhood } for the first n_emit roots (the
+ *     anchors); roots[n_emit..n_roots) only supply the trees of positives that are not anchors of this call.
+ *     pos [n_emit * num_pos] = sampled positive destinations (gigl_sample_positives_host; -1 = none), pos_tree = index
+ *     into roots of each positive's tree (-1 = none).  neighborhood = array_distinct(the anchor's ++ every positive's)
+ *     over nodes and over hydrated edges (NodeAnchorBasedLinkPredictionTask.scala:186-209,
+ *     NodeAnchorBasedLinkPredictionBaseTask.scala:106-198); pos_edges = (anchor -> positive), hydrated (:280-334);
+ *     hard_neg_edges / neg_edges stay empty (:388-406).  Anchors without a positive emit nothing.
+ * For kinds 0 / 1 pass n_emit = n_roots.  record_offsets has n_emit + 1 entries.
+ */
+int gigl_encode_samples_ex_host(int32_t kind, int64_t n_roots, int64_t n_emit, const int32_t* roots, const int32_t* fanouts,
+                                int32_t n_hops, const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
+                                int32_t condensed_edge_type, const int64_t* rowptr, const int32_t* col, const int32_t* edge_rows,
+                                const float* edge_feat, int32_t Fe, const int32_t* labels, const char* label_type, int32_t num_pos,
+                                const int32_t* pos, const int64_t* pos_tree, int32_t tfrecord_framing, uint8_t** out,
+                                int64_t* out_bytes, int64_t* record_offsets);
 /*
  * Splits a TFRecord byte stream into records (payload offsets / lengths, arrays of capacity max_records; pass NULL
  * arrays to only count).  verify != 0 checks both masked crc32c fields.  Returns the record count or GIGL_E_*.

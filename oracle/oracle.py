@@ -242,6 +242,89 @@ def tree_to_edges(roots, nbr, fanouts):
 
 
 # ----------------------------------------------------------------------------------------
+# hydration + sample assembly (pure python, small inputs): the SQL of SGSPureSparkV1Task.scala:496-820,
+# NodeAnchorBasedLinkPredictionBaseTask.scala:19-334 and NodeAnchorBasedLinkPredictionTask.scala:146-312
+# restated over python lists / dicts.  Arrays that Spark builds with collect_list have no defined
+# order, so samples are returned in a canonical (sorted) form and compared as multisets.
+# ----------------------------------------------------------------------------------------
+def np_hydrated_edge_table(src, dst, is_graph_directed: bool, edge_feat=None):
+    """loadEdgeDataframeIntoSparkSql (:120-286): {(from, to): [feature tuple per record]}.
+    Directed: every input record, duplicates kept.  Undirected: one record per (least, greatest) pair (the
+    reference's dropDuplicates keeps an arbitrary one; this restatement keeps the FIRST input record), unioned
+    with its reverse (UNION DISTINCT: a self loop once)."""
+    src = [int(v) for v in src]
+    dst = [int(v) for v in dst]
+    feat = [tuple(np.asarray(edge_feat[i], dtype=np.float32).tolist()) if edge_feat is not None else () for i in range(len(src))]
+    table = {}
+    if is_graph_directed:
+        for s_, d_, f_ in zip(src, dst, feat):
+            table.setdefault((s_, d_), []).append(f_)
+        return table
+    seen = {}
+    for s_, d_, f_ in zip(src, dst, feat):
+        seen.setdefault((min(s_, d_), max(s_, d_)), f_)
+    for (lo, hi), f_ in seen.items():
+        table[(lo, hi)] = [f_]
+        table[(hi, lo)] = [f_]
+    return table
+
+
+def np_sample_positives(out_rowptr, out_col, srcs, num_pos, base_seed=42, call_no=3):
+    """sampleDstNodesUniformly (NodeAnchorBasedLinkPredictionBaseTask.scala:19-104): per source with an out-edge the
+    first num_pos of perm(sorted destinations, internal seed = the source id, seed x call_no)."""
+    cur_seed = _wrap32(base_seed * _wrap32(call_no))
+    res = {}
+    for u in srcs:
+        u = int(u)
+        row = np.asarray(out_col[out_rowptr[u] : out_rowptr[u + 1]])
+        if len(row):
+            res[u] = [int(v) for v in row[np_perm(len(row), u, cur_seed)[:num_pos]]]
+    return res
+
+
+def _neighborhood(root, tree_edges, table):
+    """createSubgraph: edges = CONCAT(hop edges) with every sampled pair joined to its edge records (hydrateEdges),
+    nodes = array_distinct(hop nodes ++ root)."""
+    edges = [(c, p_, f_) for c, p_ in tree_edges for f_ in table.get((c, p_), [])]
+    nodes = {root} | {c for c, _ in tree_edges}
+    return edges, nodes
+
+
+def np_assemble_rnn(roots, nbr, fanouts, table):
+    """{root: (sorted edge multiset [(src, dst, feat)], sorted node ids)} for every root (isolated roots: no edges,
+    nodes = [root]; createRootedNodeNeighborhoodSubgraph :847-1017)."""
+    te = tree_to_edges(roots, nbr, fanouts)
+    out = {}
+    for i, r in enumerate(roots):
+        e, n = _neighborhood(int(r), te[i], table)
+        out[int(r)] = (sorted(e), sorted(n))
+    return out
+
+
+def np_assemble_nablp(roots, nbr, fanouts, table, positives):
+    """{anchor: (sorted distinct edges, sorted node ids, sorted pos_edges)}; `roots` must cover every anchor and every
+    positive.  Anchor = any node with a sampled positive: for nodes with in-edges the merge of
+    NodeAnchorBasedLinkPredictionTask.scala:186-209, for directed source-only nodes formNeighborhoodForSrcOnlyNodes
+    (NodeAnchorBasedLinkPredictionBaseTask.scala:200-278); both reduce to
+    array_distinct(own neighbourhood ++ positives' neighbourhoods) plus the root node."""
+    te = tree_to_edges(roots, nbr, fanouts)
+    idx = {int(r): i for i, r in enumerate(roots)}
+    out = {}
+    for u, ps in positives.items():
+        if not ps:
+            continue
+        e, n = _neighborhood(u, te[idx[u]], table)
+        for p_ in ps:
+            pe, pn = _neighborhood(p_, te[idx[p_]], table)
+            e += pe
+            n |= pn
+        pos_edges = [(u, p_, f_) for p_ in ps for f_ in table.get((u, p_), [])]  # hydrateTaskBasedEdges :280-334
+        if pos_edges:
+            out[u] = (sorted(set(e)), sorted(n), sorted(pos_edges))
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # aggregate
 # ----------------------------------------------------------------------------------------
 def _coo(edge_index):

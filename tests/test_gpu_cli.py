@@ -12,6 +12,15 @@ from helpers import GOLDEN, load_golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module")
+def ctx():
+    from gigl_b200 import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
 def _write_fixture(tmp):
     for name, sub in (("snc16_node_data.tfrecord.b64", "node_data"), ("snc16_edge_data.tfrecord.b64", "edge_data")):
         os.makedirs(tmp / sub, exist_ok=True)
@@ -66,3 +75,125 @@ def test_sampler_component_on_reference_fixture(tmp_path):
     for r, s in snc.items():
         assert s["root_node_labels"][0]["label_type"] == "node_label"
         assert sorted((d["src_node_id"], d["dst_node_id"]) for d in s["edges"]) == sorted(want[r])
+
+
+def _nablp_fixture(tmp, directed, n=40, e=220, with_edge_feat=True, strategy=None, num_pos=2):
+    from helpers import powerlaw_edges, tf_example, tfrecord_bytes
+
+    src, dst = powerlaw_edges(n, e, seed=21)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((n, 3)).astype(np.float32)
+    ef = rng.standard_normal((e, 2)).astype(np.float32)
+    os.makedirs(tmp / "node_data", exist_ok=True)
+    os.makedirs(tmp / "edge_data", exist_ok=True)
+    order = rng.permutation(n)
+    (tmp / "node_data" / "data.tfrecord").write_bytes(tfrecord_bytes(
+        [tf_example({"node_id": int(v), "emb": x[v, :2].tolist(), "score": float(x[v, 2])}) for v in order]))
+    (tmp / "edge_data" / "data.tfrecord").write_bytes(tfrecord_bytes(
+        [tf_example({"src": int(a), "dst": int(b), "w": ef[i].tolist()}) for i, (a, b) in enumerate(zip(src, dst))]))
+    main = {"tfrecordUriPrefix": "edge_data"}
+    if with_edge_feat:
+        main.update({"featureKeys": ["w"], "featureDim": 2})
+    meta = {"condensedEdgeTypeToPreprocessedMetadata": {"0": {"dstNodeIdKey": "dst", "srcNodeIdKey": "src", "mainEdgeInfo": main}},
+            "condensedNodeTypeToPreprocessedMetadata": {"0": {"featureDim": 3, "featureKeys": ["emb", "score"], "nodeIdKey": "node_id",
+                                                               "tfrecordUriPrefix": "node_data"}}}
+    sgs = {"numPositiveSamples": num_pos}
+    if strategy is None:
+        sgs.update({"numHops": 2, "numNeighborsToSample": 3})
+    else:
+        sgs["subgraphSamplingStrategy"] = strategy
+    et = {"dstNodeType": "user", "relation": "friend", "srcNodeType": "user"}
+    cfg = {"graphMetadata": {"edgeTypes": [et], "nodeTypes": ["user"]},
+           "taskMetadata": {"nodeAnchorBasedLinkPredictionTaskMetadata": {"supervisionEdgeTypes": [et]}},
+           "datasetConfig": {"subgraphSamplerConfig": sgs},
+           "sharedConfig": {"isGraphDirected": directed, "preprocessedMetadataUri": "preprocessed_metadata.yaml",
+                            "flattenedGraphMetadata": {"nodeAnchorBasedLinkPredictionOutput": {
+                                "tfrecordUriPrefix": "output/nablp/samples/",
+                                "nodeTypeToRandomNegativeTfrecordUriPrefix": {"user": "output/random_negatives/user/"}}}}}
+    (tmp / "preprocessed_metadata.yaml").write_text(yaml.safe_dump(meta))
+    (tmp / "frozen_gbml_config.yaml").write_text(yaml.safe_dump(cfg))
+    return src, dst, x, ef
+
+
+def _canon(sample, key="edges"):
+    return sorted((e["src_node_id"], e["dst_node_id"], tuple(np.float32(e["feature_values"]).tolist())) for e in sample[key])
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_link_prediction_component_matches_restated_reference(tmp_path, directed):
+    """NodeAnchorBasedLinkPredictionTask end to end (TFRecords in, RootedNodeNeighborhood + NodeAnchorBasedLinkPredictionSample
+    TFRecords out, node and edge features hydrated) against the oracle's restatement of the reference SQL.  Small batches
+    force positives whose trees live outside the anchor batch."""
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+    from oracle import oracle as O
+
+    n = 40
+    src, dst, x, ef = _nablp_fixture(tmp_path, directed)
+    stats = subgraph_sampler.run("frozen_gbml_config.yaml", "nablp_job", None, root=str(tmp_path), batch_roots=16, log=lambda *_: None)
+    rowptr, col = O.np_build_in_csr(src, dst, n, directed)
+    orow, ocol = O.np_build_in_csr(dst, src, n, directed)
+    roots = np.arange(n, dtype=np.int32)
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, [3, 3])
+    table = O.np_hydrated_edge_table(src, dst, directed, ef)
+    want_rnn = O.np_assemble_rnn(roots, nbr, [3, 3], table)
+    want = O.np_assemble_nablp(roots, nbr, [3, 3], table, O.np_sample_positives(orow, ocol, roots, 2))
+    rnn_b = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "output/random_negatives/user/")))
+    rnn = {s["root_node"]["node_id"]: s for s in map(sio.parse_sample, sio.split_tfrecords(rnn_b, verify=True))}
+    assert sorted(rnn) == list(range(n)) and stats["rnn"] == n
+    for r in range(n):
+        assert _canon(rnn[r]) == want_rnn[r][0] and sorted(v["node_id"] for v in rnn[r]["nodes"]) == want_rnn[r][1]
+        for v in rnn[r]["nodes"]:
+            assert np.array_equal(np.float32(v["feature_values"]), x[v["node_id"]])
+    main_b = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "output/nablp/samples/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_nablp_sample, sio.split_tfrecords(main_b, verify=True))}
+    assert sorted(got) == sorted(want) and stats["nablp"] == len(want)
+    for u, (we, wn, wp) in want.items():
+        assert _canon(got[u]) == we and _canon(got[u], "pos_edges") == wp
+        assert sorted(v["node_id"] for v in got[u]["nodes"]) == wn
+
+
+def test_per_hop_fanouts_from_sampling_strategy(tmp_path):
+    """`subgraphSamplingStrategy.messagePassingPaths` as a linear chain gives per-hop fanouts [4, 2]; `globalRandomUniform`
+    gives [f] * numHops (subgraph_sampling_strategy.proto:38-79)."""
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+    from oracle import oracle as O
+
+    et = {"dstNodeType": "user", "relation": "friend", "srcNodeType": "user"}
+    strat = {"messagePassingPaths": {"paths": [{"rootNodeType": "user", "samplingOps": [
+        {"opName": "hop2", "edgeType": et, "inputOpNames": ["hop1"], "randomUniform": {"numNodesToSample": 2}},
+        {"opName": "hop1", "edgeType": et, "randomUniform": {"numNodesToSample": 4}}]}]}}
+    assert subgraph_sampler.fanouts_from_config({"subgraphSamplingStrategy": strat}) == [4, 2]
+    assert subgraph_sampler.fanouts_from_config({"subgraphSamplingStrategy": {"globalRandomUniform": {
+        "numHops": 3, "randomUniformSpec": {"numNodesToSample": 5}}}}) == [5, 5, 5]
+    with pytest.raises(ValueError):
+        subgraph_sampler.fanouts_from_config({"subgraphSamplingStrategy": {"messagePassingPaths": {"paths": [{"samplingOps": [
+            {"opName": "a", "randomUniform": {"numNodesToSample": 2}}, {"opName": "b", "randomUniform": {"numNodesToSample": 2}}]}]}}})
+    n = 40
+    src, dst, x, ef = _nablp_fixture(tmp_path, False, with_edge_feat=False, strategy=strat, num_pos=1)
+    stats = subgraph_sampler.run("frozen_gbml_config.yaml", "dag_job", None, root=str(tmp_path), log=lambda *_: None)
+    assert stats["fanouts"] == [4, 2]
+    rowptr, col = O.np_build_in_csr(src, dst, n, False)
+    roots = np.arange(n, dtype=np.int32)
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, [4, 2])
+    want = O.tree_to_edges(roots, nbr, [4, 2])
+    rnn_b = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "output/random_negatives/user/")))
+    rnn = {s["root_node"]["node_id"]: s for s in map(sio.parse_sample, sio.split_tfrecords(rnn_b, verify=True))}
+    for r in range(n):
+        assert sorted((e["src_node_id"], e["dst_node_id"]) for e in rnn[r]["edges"]) == sorted(want[r])
+
+
+def test_edge_rows_match_numpy(ctx):
+    from helpers import powerlaw_edges
+    from test_sample_assembly import np_edge_rows
+    from gigl_b200 import Graph
+
+    for directed in (False, True):
+        n, e = 300, 5000
+        src, dst = powerlaw_edges(n, e, seed=8)
+        g = Graph.from_edges_host(ctx, n, src, dst, is_graph_directed=directed)
+        rows = ctx.edge_rows_host(n, src, dst, directed)
+        assert len(rows) == g.n_edges
+        assert np.array_equal(rows, np_edge_rows(src, dst, n, directed))
+    assert len(ctx.edge_rows_host(5, np.zeros(0, np.int32), np.zeros(0, np.int32), True)) == 0

@@ -1,0 +1,167 @@
+"""CPU: hydration + sample assembly of the host encoder (gigl_encode_samples_ex_host) against the oracle's pure-python
+restatement of the reference SQL (oracle.np_assemble_*): edge features, duplicate edge records of directed graphs,
+NodeAnchorBasedLinkPredictionSample merging, and the reference sampler's own NABLP fixture output."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, powerlaw_edges
+
+from gigl_b200 import sample_io as sio
+from oracle import oracle as O
+
+
+def np_edge_rows(src, dst, n, directed):
+    """Feature row per slot of np_build_in_csr's CSR (numpy twin of gigl_edge_rows_host)."""
+    src, dst = np.asarray(src, np.int64), np.asarray(dst, np.int64)
+    idx = np.arange(len(src))
+    if not directed:
+        lo, hi = np.minimum(src, dst), np.maximum(src, dst)
+        order = np.lexsort((idx, hi, lo))
+        lo, hi, idx = lo[order], hi[order], idx[order]
+        first = np.ones(len(lo), bool)
+        first[1:] = (lo[1:] != lo[:-1]) | (hi[1:] != hi[:-1])
+        lo, hi, idx = lo[first], hi[first], idx[first]
+        loop = lo == hi
+        src = np.concatenate([lo, hi[~loop]])
+        dst = np.concatenate([hi, lo[~loop]])
+        idx = np.concatenate([idx, idx[~loop]])
+    order = np.lexsort((idx, src, dst))
+    return idx[order].astype(np.int32)
+
+
+def _feat(t, v):
+    return tuple(np.asarray(v, dtype=np.float32).tolist())
+
+
+def _decode_rnn(data):
+    out = {}
+    for rec in sio.split_tfrecords(data, verify=True):
+        s = sio.parse_sample(rec)
+        out[s["root_node"]["node_id"]] = s
+    return out
+
+
+def _edges(sample, key="edges"):
+    return sorted((e["src_node_id"], e["dst_node_id"], _feat(None, e["feature_values"])) for e in sample[key])
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_rnn_edge_hydration_matches_the_restated_join(directed):
+    n, e = 60, 400
+    src, dst = powerlaw_edges(n, e, seed=5)  # heavy tail => duplicate records, self loops
+    rng = np.random.default_rng(1)
+    ef = rng.standard_normal((e, 3)).astype(np.float32)
+    x = rng.standard_normal((n, 4)).astype(np.float32)
+    rowptr, col = O.np_build_in_csr(src, dst, n, directed)
+    rows = np_edge_rows(src, dst, n, directed)
+    assert len(rows) == len(col)
+    roots = np.arange(n, dtype=np.int32)
+    fan = [4, 3]
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, fan)
+    table = O.np_hydrated_edge_table(src, dst, directed, ef)
+    want = O.np_assemble_rnn(roots, nbr, fan, table)
+    data, offs = sio.encode_samples(roots, fan, nbr, x, kind="rnn", csr=(rowptr, col), edge_rows=rows, edge_feat=ef)
+    got = _decode_rnn(data)
+    assert sorted(got) == list(range(n))
+    n_dup = 0
+    for r in range(n):
+        we, wn = want[r]
+        assert _edges(got[r]) == we
+        assert sorted(v["node_id"] for v in got[r]["nodes"]) == wn
+        for v in got[r]["nodes"]:
+            assert np.array_equal(np.float32(v["feature_values"]), x[v["node_id"]])
+        n_dup += len(we) - len(set((a, b) for a, b, _ in we))
+    if directed:
+        assert n_dup > 0  # the duplicate-record join really was exercised
+    # without edge features the same join still multiplies duplicate records of a directed graph
+    data2, _ = sio.encode_samples(roots, fan, nbr, x, kind="rnn", csr=(rowptr, col))
+    got2 = _decode_rnn(data2)
+    for r in range(n):
+        assert [(a, b) for a, b, _ in _edges(got2[r])] == [(a, b) for a, b, _ in want[r][0]]
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_nablp_assembly_matches_the_restated_sql(directed):
+    n, e = 50, 260
+    src, dst = powerlaw_edges(n, e, seed=11)
+    rng = np.random.default_rng(2)
+    ef = rng.standard_normal((e, 2)).astype(np.float32)
+    ef[rng.integers(0, e, 40)] = 0.5  # some duplicate records with byte-identical features (array_distinct merges them)
+    x = rng.standard_normal((n, 3)).astype(np.float32)
+    rowptr, col = O.np_build_in_csr(src, dst, n, directed)
+    out_rowptr, out_col = O.np_build_in_csr(dst, src, n, directed)
+    rows = np_edge_rows(src, dst, n, directed)
+    roots = np.arange(n, dtype=np.int32)
+    fan = [3, 3]
+    num_pos = 2
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, fan)
+    positives = O.np_sample_positives(out_rowptr, out_col, roots, num_pos)
+    table = O.np_hydrated_edge_table(src, dst, directed, ef)
+    want = O.np_assemble_nablp(roots, nbr, fan, table, positives)
+    pos = np.full((n, num_pos), -1, np.int32)
+    for u, ps in positives.items():
+        pos[u, : len(ps)] = ps
+    pos_tree = np.where(pos >= 0, pos, -1).astype(np.int64)  # roots = arange(n): the tree of node p is tree p
+    data, offs = sio.encode_samples(roots, fan, nbr, x, kind="nablp", csr=(rowptr, col), edge_rows=rows, edge_feat=ef,
+                                    pos=pos, pos_tree=pos_tree)
+    got = {}
+    for rec in sio.split_tfrecords(data, verify=True):
+        s = sio.parse_nablp_sample(rec)
+        got[s["root_node"]["node_id"]] = s
+    assert sorted(got) == sorted(want) and len(want) > 10
+    src_only = 0
+    for u, (we, wn, wp) in want.items():
+        s = got[u]
+        assert _edges(s) == we
+        assert sorted(v["node_id"] for v in s["nodes"]) == wn
+        assert _edges(s, "pos_edges") == wp
+        assert s["hard_neg_edges"] == [] and s["neg_edges"] == []
+        assert np.array_equal(np.float32(s["root_node"]["feature_values"]), x[u])
+        src_only += rowptr[u + 1] == rowptr[u]
+    if directed:
+        assert src_only > 0  # source-only anchors (formNeighborhoodForSrcOnlyNodes) were exercised
+    # anchors only: the positives' trees ride behind the anchors
+    anchors = np.array(sorted(want)[:7], dtype=np.int32)
+    extra = np.array(sorted({p for a in anchors for p in positives[int(a)]} - set(anchors.tolist())), dtype=np.int32)
+    roots2 = np.concatenate([anchors, extra])
+    nbr2, _ = O.c_sample_khop(rowptr, col, roots2, fan)
+    where = {int(v): i for i, v in enumerate(roots2)}
+    pos2 = pos[anchors]
+    pt2 = np.array([[where[int(p)] if p >= 0 else -1 for p in row] for row in pos2], dtype=np.int64)
+    data2, offs2 = sio.encode_samples(roots2, fan, nbr2, x, kind="nablp", csr=(rowptr, col), edge_rows=rows, edge_feat=ef,
+                                      n_emit=len(anchors), pos=pos2, pos_tree=pt2)
+    assert len(offs2) == len(anchors) + 1
+    recs = sio.split_tfrecords(data2)
+    assert len(recs) == len(anchors)
+    for a, rec in zip(anchors, recs):
+        s = sio.parse_nablp_sample(rec)
+        assert _edges(s) == want[int(a)][0] and _edges(s, "pos_edges") == want[int(a)][2]
+
+
+def test_nablp_structure_of_the_reference_fixture_output():
+    """The reference sampler's own NodeAnchorBasedLinkPredictionSample output (16-node fixture, fanout 2, produced
+    with the unseedable shuffle) obeys the merge rule the encoder implements: every positive's sampled 1-hop
+    in-edges are inside the merged neighbourhood, edges are distinct, nodes = {root} U endpoints U positives."""
+    g = load_golden("snc16_graph.json")
+    src, dst = np.array(g["edges"]).T
+    rowptr, col = O.np_build_in_csr(src, dst, 16, False)
+    deg = np.diff(rowptr)
+    out = load_golden("nablp16_sgs_output.json")
+    for s in out["nablp"]:
+        r = s["root_node"]["node_id"]
+        edges = [(e["src"], e["dst"]) for e in s["neighborhood"]["edges"]]
+        assert len(edges) == len(set(edges))  # array_distinct
+        ids = sorted(v["node_id"] for v in s["neighborhood"]["nodes"])
+        assert ids == sorted({r} | {a for a, _ in edges} | {b for _, b in edges} | {pe["dst"] for pe in s["pos_edges"]})
+        for v in [r] + [pe["dst"] for pe in s["pos_edges"]]:
+            assert len({a for a, b in edges if b == v}) >= min(2, deg[v])  # each merged tree brings its hop-1 edges
+    # our encoder on the same graph produces samples for exactly the same anchors (every non-isolated node)
+    roots = np.arange(16, dtype=np.int32)
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, [2, 2])
+    positives = O.np_sample_positives(rowptr, col, roots, 2)  # undirected: the out-CSR is the in-CSR
+    pos = np.full((16, 2), -1, np.int32)
+    for u, ps in positives.items():
+        pos[u, : len(ps)] = ps
+    data, _ = sio.encode_samples(roots, [2, 2], nbr, None, kind="nablp", csr=(rowptr, col), pos=pos, pos_tree=pos.astype(np.int64))
+    ours = {sio.parse_nablp_sample(r)["root_node"]["node_id"] for r in sio.split_tfrecords(data)}
+    assert ours == {s["root_node"]["node_id"] for s in out["nablp"]}
