@@ -31,9 +31,11 @@ if ROOT not in sys.path:
 METRIC = "sampled-subgraphs/sec"
 UNIT = "subgraphs/s"
 WORKLOADS = {
-    # name: nodes, undirected input pairs, F, hidden, out
-    "products-like": dict(nodes=2_449_029, pairs=61_859_140, F=100, H=256, O=47),
-    "toy-1k": dict(nodes=1_000, pairs=5_000, F=16, H=16, O=7),
+    # name: nodes, input edge records (undirected pairs unless directed), F, hidden, out, BASELINE.json config it mirrors
+    "products-like": dict(nodes=2_449_029, pairs=61_859_140, F=100, H=256, O=47, directed=False, cfg="configs[1]"),
+    "toy-1k": dict(nodes=1_000, pairs=5_000, F=16, H=16, O=7, directed=False, cfg="configs[0]"),
+    # N = 1e8, E = 1e9 directed RMAT, F = 128; every GPU holds the whole CSR (4.8 GB) + features (51 GB)
+    "g1b": dict(nodes=100_000_000, pairs=1_000_000_000, F=128, H=128, O=128, directed=True, cfg="configs[3]"),
 }
 
 
@@ -138,7 +140,7 @@ def cpu_step(O, rowptr, col, x, roots, fan, layers, threads):
     nbr, _ = O.c_sample_khop(rowptr, col, roots, fan, n_threads=threads)
     t1 = time.perf_counter()
     node_ids, ei, root_idx = O.np_collate_fast(roots, nbr, fan)
-    xb = x[node_ids]
+    xb = x(node_ids) if callable(x) else x[node_ids]
     t2 = time.perf_counter()
     out = O.torch_sage_forward(xb, ei, layers, n_threads=threads)[root_idx]
     return out, ei.shape[1], t1, t2
@@ -206,7 +208,7 @@ def run_reference(args):
     fan = [int(v) for v in args.fanout.split(",")]
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     src, dst, x, layers = build_inputs_torch(wl, dev)  # input preparation only (torch ops, not timed)
-    rowptr, col = O.torch_build_in_csr(src, dst, wl["nodes"], False)
+    rowptr, col = O.torch_build_in_csr(src, dst, wl["nodes"], wl["directed"])
     rowptr, col, x = rowptr.cpu().numpy(), col.cpu().numpy(), x.cpu().numpy()
     del src, dst
     n_roots = args.cpu_sample_roots
@@ -227,12 +229,15 @@ def workload_config(args, wl, fan, batch, note):
                  if not getattr(args, "shard_features", False) else
                  "CSR replicated; feature table sharded by contiguous node range over the GPUs and mapped as one flat array "
                  "(cuMemMap of peer shards): remote neighbour rows are loaded over NVLink inside the gather kernel")
-    return {"workload": f"BASELINE.json configs[1] shape: {args.workload} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
-                        f"N={wl['nodes']}, {wl['pairs']} undirected pairs de-duplicated+mirrored, F={wl['F']} fp32, "
+    edges = (f"{wl['pairs']} directed edges (duplicates kept)" if wl["directed"] else
+             f"{wl['pairs']} undirected pairs de-duplicated+mirrored")
+    return {"workload": f"BASELINE.json {wl['cfg']} shape: {args.workload} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
+                        f"N={wl['nodes']}, {edges}, F={wl['F']} fp32, "
                         f"2-hop fanout {fan}, GraphSAGE {wl['F']}->{wl['H']}->{wl['O']} inference on the coalesced batch graph",
             "roots_per_step_per_gpu": batch, "fanout": fan, "seed": {"generator": 20260101, "sampler_base_seed": 42, "first_call_no": 1},
             "residency": residency,
-            "l2": "every step reads different roots from a 0.98 GB feature table + 0.5 GB CSR (>> 126 MB L2); no flush needed",
+            "l2": f"every step reads different roots from a {wl['nodes'] * wl['F'] * 4 / 1e9:.2f} GB feature table + the CSR "
+                  "(>> 126 MB L2); no flush needed",
             "note": note}
 
 
@@ -256,7 +261,7 @@ def run_ours(args):
 
     ctx = Context.on_torch_stream(local)
     src, dst, x, layers = build_inputs_torch(wl, dev)
-    g = Graph.from_edges_dev(ctx, wl["nodes"], src, dst, is_graph_directed=False)
+    g = Graph.from_edges_dev(ctx, wl["nodes"], src, dst, is_graph_directed=wl["directed"])
     del src, dst
     table = None
     if args.shard_features:
@@ -377,8 +382,15 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rowptr_t, col_t = g.csr_tensors()
-        cpu = run_cpu_baseline(rowptr_t.cpu().numpy(), col_t.cpu().numpy(), x.cpu().numpy(), fan, layers, wl["nodes"],
+        if x.numel() * 4 > (8 << 30):
+            # a table this large is not copied to the host: the baseline's feature lookup reads the device copy
+            x_host = lambda ids: x[torch.from_numpy(ids).to(dev)].cpu().numpy()  # noqa: E731
+        else:
+            x_host = x.cpu().numpy()
+        cpu = run_cpu_baseline(rowptr_t.cpu().numpy(), col_t.cpu().numpy(), x_host, fan, layers, wl["nodes"],
                                args.cpu_sample_roots, 3, 1)
+        if callable(x_host):
+            cpu["sample"] += "; batch feature rows fetched from the device-resident table"
         cpu["cpu_model"] = cpu_model()
 
     if rank == 0:
