@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgigl_b200.so")
+LIB_PATH = os.environ.get("GIGL_B200_LIB") or os.path.join(_HERE, "lib", "libgigl_b200.so")  # env override: kernel-variant experiments
 
 OK, E_INVALID, E_CUDA, E_RANGE, E_OVERFLOW, E_NOMEM = 0, -1, -2, -3, -4, -5
 MAX_HOPS, MAX_FANOUT = 8, 128

@@ -2,6 +2,8 @@
 // residency, COO->CSR conversion and the host-buffer entry points a JNI / ctypes binding calls.
 // The kernels live in khop_sample.cu / sage_aggregate.cu / graph_build.cu.
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <cstdio>
 #include <cstring>
@@ -791,36 +793,60 @@ int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_mode
         nbr_dev[h] = d + off_nbr[h];
         cnt_dev[h] = d + off_cnt[h];
     }
+    // The index sets (59.5 MB for B = 65536, [15, 10]) leave on a second stream while the aggregate runs.  Measured
+    // on B200: a device-to-host copy that overlaps the SAMPLER or the collation sort slows them by about the copy's
+    // own duration (both live on L2-resident tables - the 56 MB hash-key table, the radix-sort buffers - and the copy
+    // streams 48 MB through the same L2), while the gather / projection kernels stream gigabytes through L2 anyway.
+    // So the copies are released after collation and ride under the aggregate (0.9 ms of PCIe under 1.4 ms of kernels).
+    const bool copying = nbr && cnt;
+    static const bool dbg = getenv("GIGL_DEBUG_TIMELINE") != nullptr;
+    cudaEvent_t ev[8] = {};
+    if (dbg) {
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], ctx->stream);
+    }
+    if (copying && !ctx->copy_stream) {
+        GIGL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        GIGL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ready, cudaEventDisableTiming));
+    }
     if ((rc = khop_sample_launch(g, d, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev)) != GIGL_OK) return rc;
-    bool copying = false;
-    if (nbr && cnt) {
-        // the index sets leave on a second stream while collation and the aggregate run on the ctx stream (both only
-        // read them); for B = 65536, [15, 10] that is 59.5 MB of PCIe time hidden behind ~2 ms of kernels
-        if (!ctx->copy_stream) {
-            GIGL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            GIGL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ready, cudaEventDisableTiming));
-        }
+    if (dbg) cudaEventRecord(ev[2], ctx->stream);
+    if ((rc = batch_collate(b, d, n_roots, fanouts, n_hops, nbr_dev, n_layers, nullptr, nullptr)) != GIGL_OK) return rc;
+    if (dbg) cudaEventRecord(ev[4], ctx->stream);
+    if (copying) {
         GIGL_CUDA(ctx, cudaEventRecord(ctx->copy_ready, ctx->stream));
         GIGL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ready, 0));
+        if (dbg) cudaEventRecord(ev[1], ctx->copy_stream);
         width = 1;
         for (int h = 0; h < n_hops; ++h) {
             if (cnt[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(cnt[h], cnt_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->copy_stream));
             width *= (size_t)fanouts[h];
             if (nbr[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(nbr[h], nbr_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->copy_stream));
         }
-        copying = true;
+        if (dbg) cudaEventRecord(ev[3], ctx->copy_stream);
     }
-    rc = batch_collate(b, d, n_roots, fanouts, n_hops, nbr_dev, n_layers, nullptr, nullptr);
-    if (rc == GIGL_OK) rc = batch_sage_forward(b, m, g->x, g->F, (float*)pout);
+    rc = batch_sage_forward(b, m, g->x, g->F, (float*)pout);
     if (rc != GIGL_OK) {
         if (copying) cudaStreamSynchronize(ctx->copy_stream);  // nothing may still be writing the caller's buffers
         return rc;
     }
+    if (dbg) cudaEventRecord(ev[5], ctx->stream);
     GIGL_CUDA(ctx, cudaMemcpyAsync(out, pout, sizeof(float) * (size_t)n_roots * O, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dbg) cudaEventRecord(ev[6], ctx->stream);
     if (copying) {
         // join: the ctx stream (and whoever times it) is not done before the index sets have landed
         GIGL_CUDA(ctx, cudaEventRecord(ctx->copy_ready, ctx->copy_stream));
         GIGL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ready, 0));
+    }
+    if (dbg) {
+        cudaEventRecord(ev[7], ctx->stream);
+        cudaEventSynchronize(ev[7]);
+        float t[8] = {};
+        for (int i = 1; i < 8; ++i)
+            if (copying || (i != 1 && i != 3)) cudaEventElapsedTime(&t[i], ev[0], ev[i]);
+        fprintf(stderr, "[timeline ms] first copy start %.3f | sampled %.3f | copies done %.3f | collated %.3f | forward %.3f | out copied %.3f | joined %.3f\n",
+                t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+        for (auto& e : ev) cudaEventDestroy(e);
     }
     return ctx_check_device_error(ctx);
 }

@@ -141,7 +141,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // ---- entry points implemented in the .cu files, called from capi.cu ---------------------
 int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
                        int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
-                       int32_t* const* cnt_dev);
+                       int32_t* const* cnt_dev, int32_t hop_first = 1, int32_t hop_last = 0);  // hops [hop_first, hop_last], 0 = n_hops
 int csr_from_coo_launch(gigl_ctx* ctx, int64_t n, int64_t e, const int64_t* src, const int64_t* dst,
                         int64_t* rowptr, int32_t* col);
 int graph_from_edges_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,

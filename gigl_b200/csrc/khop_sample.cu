@@ -14,6 +14,7 @@
 // Layout in HBM: rowptr int64[n+1], col int32[E] (rows sorted ascending), padded-tree outputs
 // nbr[h] int32[n_roots * prod f], cnt[h] int32[n_roots * prod f_{<h}]  (see include/gigl_b200.h).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "xxh64.cuh"
@@ -21,6 +22,9 @@
 namespace gigl {
 
 constexpr int kWarpsPerBlock = 8;
+#ifndef KHOP_MIN_BLOCKS
+#define KHOP_MIN_BLOCKS 8  // the kernels are latency-bound: 64 resident warps per SM (32 registers) beat 40 (46 registers) by 16 %
+#endif
 constexpr int kHeavyThreshold = 4096;   // rows longer than this go to the CTA-per-row pass
 constexpr int kHeavyWarps = 16;
 
@@ -40,6 +44,7 @@ struct HopArgs {
     int32_t* heavy_list;  // worklist of parent slots deferred to the heavy pass
     int32_t* heavy_count;
     int32_t heavy_cap;
+    unsigned long long* tile_counter;  // next tile of khop_tile_kernel (zeroed per launch)
     // hash-window index (see build_hash_index_kernel): per block of 2^l_log2 consecutive hash inputs
     // the `cap` smallest keys, ascending, with their offsets inside the block; nullptr = disabled
     const uint64_t* hx_keys;
@@ -333,6 +338,18 @@ __device__ __forceinline__ void sort32(PairKI& v, int lane) {
             cmpx(v, lane, stride, ((lane & size) == 0) == ((lane & stride) == 0));
 }
 
+__device__ __forceinline__ void cmpx_u32(uint32_t& v, int stride, bool take_min) {
+    const uint32_t o = __shfl_xor_sync(0xffffffffu, v, stride);
+    v = take_min ? min(v, o) : max(v, o);
+}
+
+__device__ __forceinline__ void sort32_u32(uint32_t& v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_u32(v, stride, ((lane & size) == 0) == ((lane & stride) == 0));
+}
+
 __device__ __forceinline__ bool push_cands(uint64_t* __restrict__ ck, int32_t* __restrict__ ci, int& c, bool is_cand,
                                            uint64_t k, int32_t i, int lane) {
     const uint32_t m = __ballot_sync(0xffffffffu, is_cand);
@@ -405,6 +422,38 @@ __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& 
     const int64_t need = size < f ? size : f;
     if (c < need) return false;
     __syncwarp();
+    if (need < 32) {
+        // Order the candidates on ONE 32-bit word each: the top 26 significant bits of the key (every candidate is
+        // below T, so bits above T's highest bit are zero) over the candidate's 6-bit buffer slot.  A 32-lane bitonic
+        // network on such words is one shuffle and one min/max per stage instead of three shuffles and a 64-bit
+        // compare.  Two candidates agreeing on those 26 bits inside the first need + 1 positions (about 1e-5 of the
+        // rows) would make the order ambiguous: the row is then redone by the exact streaming path.
+        int shift = 38;
+        if (T != kKeyInf) {
+            const int nbits = 64 - __clzll((long long)T);
+            shift = nbits > 26 ? nbits - 26 : 0;
+        }
+        uint32_t v0 = 0xFFFFFFFFu, v1 = 0xFFFFFFFFu;
+        if (lane < c) v0 = ((uint32_t)(ck[lane] >> shift) << 6) | (uint32_t)lane;
+        sort32_u32(v0, lane);
+        if (c > 32) {  // warp-uniform
+            if (lane + 32 < c) v1 = ((uint32_t)(ck[lane + 32] >> shift) << 6) | (uint32_t)(lane + 32);
+            sort32_u32(v1, lane);
+            // 32 smallest of two ascending runs: min(v0[l], v1[31 - l]) is bitonic; one merge sorts it
+            v0 = min(v0, __shfl_sync(0xffffffffu, v1, 31 - lane));
+#pragma unroll
+            for (int stride = 16; stride > 0; stride >>= 1) cmpx_u32(v0, stride, (lane & stride) == 0);
+        }
+        const uint32_t up = __shfl_up_sync(0xffffffffu, v0, 1);
+        const bool tie = lane >= 1 && lane <= need && v0 != 0xFFFFFFFFu && (v0 >> 6) == (up >> 6);
+        if (__any_sync(0xffffffffu, tie)) return false;
+        if (lane < need) {
+            best.key[0] = ck[v0 & 63u];
+            best.idx[0] = ci[v0 & 63u];
+        }
+        __syncwarp();
+        return true;
+    }
     PairKI v0{kKeyInf, 0}, v1{kKeyInf, 0};
     if (lane < c) {
         v0.k = ck[lane];
@@ -441,7 +490,7 @@ __device__ __forceinline__ bool row_uses_index(const HopArgs& a, int64_t size, u
 }
 
 template <int KPL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_hop_kernel(const HopArgs a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop_kernel(const HopArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t pslot = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (pslot >= a.n_parent) return;
@@ -495,6 +544,144 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_hop_kernel(const Hop
         select_row<KPL>(a, best, size, base, f, lane);
     }
     write_result<KPL>(a, pslot, best, size, row_begin, mult, lane);
+}
+
+// ---- tile form of the hop kernel (fanout <= 32) ---------------------------------------------------
+// khop_hop_kernel is latency-bound (ncu: 41 % of the stall samples wait on global loads, DRAM 7 % busy): every warp
+// walks ONE row through four dependent round trips (parent slot -> rowptr pair -> key window -> winning col entries).
+// Here a warp owns a tile of 32 consecutive parent slots:
+//   A. lane l resolves slot l's metadata (parent vertex, path-id sum, sibling multiplicity, rowptr pair): the same
+//      loads, but 32 rows share each round trip;
+//   B. the rows are selected one after the other by the whole warp (metadata broadcast with shuffles); the winners'
+//      col offsets go to shared memory instead of being dereferenced;
+//   C. the tile's col entries are loaded in one batch (up to f independent loads per lane) and written as one
+//      contiguous run of 32 * f outputs.
+// Same keys, same (key, idx) order, same outputs as khop_hop_kernel.
+constexpr int kTileRows = 32;
+#ifndef KHOP_TILE_MIN_BLOCKS
+#define KHOP_TILE_MIN_BLOCKS 6
+#endif
+
+template <int MAXF>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) khop_tile_kernel(const HopArgs a) {
+    __shared__ uint64_t s_ck[kWarpsPerBlock][kCandCap];
+    __shared__ int32_t s_ci[kWarpsPerBlock][kCandCap];
+    __shared__ int32_t s_off[kWarpsPerBlock][kTileRows * MAXF];  // winner's offset inside its row, -1 = empty, -2 = row deferred
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int f = a.fanouts[a.h - 1];
+    const int64_t n_tiles = (a.n_parent + kTileRows - 1) / kTileRows;
+    // persistent warps: tiles are handed out by an atomic counter, so a launch has no tail of half-empty waves and the
+    // cheap tiles (empty parents) do not leave SMs idle behind the expensive ones
+    for (;;) {
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(a.tile_counter, 1ULL);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_tiles) return;
+    const int64_t tile0 = (int64_t)tile * kTileRows;
+    const int n_rows = (int)min((int64_t)kTileRows, a.n_parent - tile0);
+    const int64_t pslot = tile0 + lane;
+
+    // ---- A: lane-parallel metadata
+    int32_t v = -1, mult = 1;
+    uint32_t ssum = 0;
+    int state = 0;  // 0 = no group (all -1), 1 = select here, 2 = deferred to the heavy pass
+    int64_t size = 0, row_begin = 0;
+    if (lane < n_rows) {
+        bool live = true;
+        if (a.h == 1) {
+            v = a.roots[pslot];
+            ssum = (uint32_t)v;
+        } else {
+            const int32_t* prev = a.levels[a.h - 2];
+            v = prev[pslot];
+            live = v >= 0;
+            if (live) {
+                ssum = (uint32_t)v;
+                int64_t s = pslot;
+                for (int hh = a.h - 1; hh >= 1; --hh) {
+                    s /= a.fanouts[hh - 1];
+                    ssum += (uint32_t)(hh == 1 ? a.roots[s] : a.levels[hh - 2][s]);
+                }
+                const int fp = a.fanouts[a.h - 2];
+                const int64_t sib0 = (pslot / fp) * fp;
+                int m = 0;
+                for (int j = 0; j < fp; ++j) {
+                    const bool eq = prev[sib0 + j] == v;
+                    m += eq;
+                    if (eq && sib0 + j < pslot) live = false;  // a non-first duplicate produces no group
+                }
+                mult = m;
+            }
+        }
+        if (live) {
+            if (v < 0 || v >= a.n_nodes) {
+                atomicExch(a.err, GIGL_E_RANGE);
+            } else {
+                row_begin = __ldg(a.rowptr + v);
+                size = (__ldg(a.rowptr + v + 1) - row_begin) * mult;
+                if (size > 2147483647LL) {
+                    atomicExch(a.err, GIGL_E_OVERFLOW);
+                    size = 0;
+                } else {
+                    state = 1;
+                }
+            }
+        }
+    }
+    const uint32_t base = ssum + (uint32_t)a.cur_seed;
+    if (state == 1 && size > kHeavyThreshold && a.heavy_list != nullptr && !row_uses_index(a, size, base)) {
+        const int slot = atomicAdd(a.heavy_count, 1);
+        if (slot < a.heavy_cap) {
+            a.heavy_list[slot] = (int32_t)pslot;
+            state = 2;
+        }
+    }
+
+    // ---- B: one row at a time, whole warp
+    int32_t* off = s_off[w];
+    for (int r = 0; r < n_rows; ++r) {
+        const int r_state = __shfl_sync(0xffffffffu, state, r);
+        const int64_t r_size = __shfl_sync(0xffffffffu, size, r);
+        if (r_state != 1 || r_size == 0) {
+            if (lane < f) off[r * f + lane] = (r_state == 2) ? -2 : -1;
+            continue;
+        }
+        const uint32_t r_base = __shfl_sync(0xffffffffu, base, r);
+        const int32_t r_mult = __shfl_sync(0xffffffffu, mult, r);
+        WarpTopK<1> best;
+        best.init();
+        if (!select_threshold(a, best, r_size, r_base, f, lane, s_ck[w], s_ci[w])) {
+            best.init();
+            select_row<1>(a, best, r_size, r_base, f, lane);
+        }
+        int32_t q = best.idx[0] - 1;
+        if (r_mult != 1) q /= r_mult;  // sorted(m copies)[q] = row[q / m]
+        if (lane < f) off[r * f + lane] = (lane < r_size) ? q : -1;
+    }
+    __syncwarp();
+
+    // ---- C: batched col loads, contiguous writes
+    int32_t* out = a.out_nbr + tile0 * f;
+    const int total = n_rows * f;
+    for (int i0 = 0; i0 < total; i0 += 32 * 4) {
+        int32_t val[4], o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            o[u] = (i < total) ? off[i] : -2;
+            const int64_t rb = __shfl_sync(0xffffffffu, row_begin, (i < total) ? i / f : 0);
+            val[u] = (o[u] >= 0) ? __ldg(a.col + rb + o[u]) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            if (o[u] != -2) out[i] = val[u];  // -2: past the tile, or a row the heavy pass writes
+        }
+    }
+    if (lane < n_rows && state != 2) a.out_cnt[pslot] = (state == 1) ? (int32_t)min(size, (int64_t)f) : 0;
+    __syncwarp();  // s_off is reused by the next tile
+    }
 }
 
 // One CTA per deferred long row: every warp scans an interleaved share of the window with its own
@@ -597,11 +784,20 @@ static int ensure_hash_index(gigl_graph* g, int fmax, int n_hops) {
 }
 
 template <int KPL>
-static int launch_hop(gigl_ctx* ctx, const HopArgs& a) {
-    const int64_t blocks = ceil_div64(a.n_parent, kWarpsPerBlock);
+static int launch_hop(gigl_ctx* ctx, const HopArgs& a, bool tiled) {
+    const int64_t blocks = ceil_div64(a.n_parent, kWarpsPerBlock * (tiled && KPL == 1 ? kTileRows : 1));
     if (blocks > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "too many frontier slots for one launch");
     if (blocks > 0) {
-        khop_hop_kernel<KPL><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+        if (tiled && KPL == 1) {
+            const int64_t cap = (int64_t)ctx->sm_count * KHOP_TILE_MIN_BLOCKS;
+            const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+            if (a.fanouts[a.h - 1] <= 16)
+                khop_tile_kernel<16><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+            else
+                khop_tile_kernel<32><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+        } else {
+            khop_hop_kernel<KPL><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+        }
         GIGL_LAUNCHED(ctx);
         if (a.heavy_list != nullptr) {
             const int grid = ctx->sm_count * 2;
@@ -616,7 +812,7 @@ static int launch_hop(gigl_ctx* ctx, const HopArgs& a) {
 
 int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
                        int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
-                       int32_t* const* cnt_dev) {
+                       int32_t* const* cnt_dev, int32_t hop_first, int32_t hop_last) {
     using namespace gigl;
     gigl_ctx* ctx = g->ctx;
     GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS, "n_hops must be in [1, 8]");
@@ -657,25 +853,35 @@ int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
     a.heavy_list = heavy_list;
     a.heavy_count = heavy_count;
     a.heavy_cap = heavy_cap;
+    a.tile_counter = (unsigned long long*)(heavy_count + 2);
     int64_t n_parent = n_roots;
+    static const bool tiled = [] {  // GIGL_KHOP_TILE=0: the warp-per-row kernel (A/B measurements)
+        const char* e = getenv("GIGL_KHOP_TILE");
+        return !(e && e[0] == '0');
+    }();
     gigl_timed timed(ctx, GIGL_T_SAMPLE);
-    for (int h = 1; h <= n_hops; ++h) {
+    if (hop_last <= 0 || hop_last > n_hops) hop_last = n_hops;
+    for (int h = 1; h <= hop_last; ++h) {
         const int32_t f = fanouts[h - 1];
         a.fanouts[h - 1] = f;
         if (h >= 2) a.levels[h - 2] = nbr_dev[h - 2];
+        if (h < hop_first) {  // levels below hop_first were sampled by an earlier call
+            n_parent *= f;
+            continue;
+        }
         a.h = h;
         a.cur_seed = (int32_t)((uint32_t)base_seed * ((uint32_t)first_call_no + (uint32_t)(h - 1)));
         a.out_nbr = nbr_dev[h - 1];
         a.out_cnt = cnt_dev[h - 1];
         a.n_parent = n_parent;
         if (n_parent > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "frontier exceeds 2^31-1 slots; split the roots");
-        GIGL_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, sizeof(int32_t), ctx->stream));
+        GIGL_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, sizeof(int32_t) * 4, ctx->stream));  // + the tile counter
         if (f <= 32)
-            rc = launch_hop<1>(ctx, a);
+            rc = launch_hop<1>(ctx, a, tiled);
         else if (f <= 64)
-            rc = launch_hop<2>(ctx, a);
+            rc = launch_hop<2>(ctx, a, false);
         else
-            rc = launch_hop<4>(ctx, a);
+            rc = launch_hop<4>(ctx, a, false);
         if (rc != GIGL_OK) return rc;
         n_parent *= f;
     }
