@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-roots", type=int, default=8192, help="roots per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-graph", action="store_true")
     ap.add_argument("--shard-features", action="store_true",
                     help="features sharded by node range over the N GPUs and mapped as one flat table (remote rows over NVLink) "
                          "instead of replicated")
@@ -346,11 +347,32 @@ def run_ours(args):
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "ms_per_launch": g_ms / max(g_n, 1), "share_of_step": (g_ms / K) / (ms / K)}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and args.workload == "products-like" and B == 65536 and not args.shard_features:
         try:
             roofline["traffic"] = json.load(open(prof)).get("gather_l1_dram_bytes_per_launch")
         except Exception:
             pass
+
+    # ---- the aggregate over the WHOLE graph (every node a row, every CSR edge reduced once): the full-graph form the
+    # Trainer's nn modules and layer-wise inference use; reported beside the batch numbers, outside the timed step
+    full = None
+    if not args.no_full_graph:
+        rowptr_t, col_t = g.csr_tensors()
+        agg = torch.empty((wl["nodes"], F), dtype=torch.float32, device=dev)
+        ctx.gather_mean(x, rowptr_t, col_t, out=agg)
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        fe0.record()
+        for _ in range(5):
+            ctx.gather_mean(x, rowptr_t, col_t, out=agg)
+        fe1.record()
+        barrier()
+        f_ms = max_over_ranks(fe0.elapsed_time(fe1) / 5, dev)
+        f_bytes = g.n_edges * (4 * F + 4) + (wl["nodes"] + 1) * 8 + wl["nodes"] * 4 * F  # SURVEY 8(d) bytes_A without the projection
+        full = {"op": "gigl_gather_mean_dev over the whole CSR (SAGEConv mean aggregate of every node)", "edges": int(g.n_edges),
+                "ms": f_ms, "aggregated_edges_per_sec": world * g.n_edges / (f_ms * 1e-3), "algorithmic_GBps_per_gpu": f_bytes / f_ms / 1e6,
+                "frac_of_hbm_peak": f_bytes / f_ms / 1e6 / peak}
+        del agg
 
     # ---- end to end through the host entry point (pinned host buffers, copies inside the timed region) ----
     e2e = None
@@ -402,7 +424,7 @@ def run_ours(args):
                                                                               ("gather_l1", "gather_deep", "gemm_l1", "gemm_deep")) * 1e-3),
                 "sample_only_subgraphs_per_sec": B / max(1e-9, phase_ms.get("sample", 0.0) * 1e-3),
                 "phase_ms_per_step": phase_ms, "unique_edges_per_step": e1_total / K, "layer1_rows_per_step": n1_total / K,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+                "roofline": roofline, "full_graph_aggregate": full, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
     if table is not None:
         ctx.sync()
