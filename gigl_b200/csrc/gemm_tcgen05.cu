@@ -22,6 +22,7 @@
 // the epilogue of tile t overlaps the MMAs of tile t+1, smem ring of 2..4 stages.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -32,6 +33,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;              // 32 fp32 = 128 bytes = one swizzle span
 constexpr int kUmmaK = 8;                // tf32
 constexpr int kGemmThreads = 192;
+constexpr int kEpiPitch = 36;             // floats per row of an epilogue warp's 32 x 32 staging tile
+constexpr size_t kEpiBytes = 4 * 32 * kEpiPitch * sizeof(float);
 
 
 struct GemmParams {
@@ -47,6 +50,7 @@ struct GemmParams {
     float* C;
     int64_t ldc;
     int relu;
+    int dbg;  // GIGL_GEMM_DBG (timing experiments only): 1 = no MMA, 2 = no W loads, 4 = no A loads, 8 = no epilogue stores
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -106,11 +110,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    mbar_expect_tx(full, stage_bytes);
-                    tma_load_2d(sa, &tm_a_hi, full, kb * kBlockK, m0);
-                    tma_load_2d(sa + a_bytes, &tm_a_lo, full, kb * kBlockK, m0);
-                    tma_load_2d(sa + 2 * a_bytes, &tm_w_hi, full, kb * kBlockK, n0);
-                    tma_load_2d(sa + 2 * a_bytes + w_bytes, &tm_w_lo, full, kb * kBlockK, n0);
+                    mbar_expect_tx(full, ((p.dbg & 4) ? 0 : 2 * a_bytes) + ((p.dbg & 2) ? 0 : 2 * w_bytes));
+                    if (!(p.dbg & 4)) {
+                        tma_load_2d(sa, &tm_a_hi, full, kb * kBlockK, m0);
+                        tma_load_2d(sa + a_bytes, &tm_a_lo, full, kb * kBlockK, m0);
+                    }
+                    if (!(p.dbg & 2)) {
+                        tma_load_2d(sa + 2 * a_bytes, &tm_w_hi, full, kb * kBlockK, n0);
+                        tma_load_2d(sa + 2 * a_bytes + w_bytes, &tm_w_lo, full, kb * kBlockK, n0);
+                    }
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -141,7 +149,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                     const uint64_t d_ah = umma_desc_sw128(sa), d_al = umma_desc_sw128(sa + a_bytes);
                     const uint64_t d_wh = umma_desc_sw128(sa + 2 * a_bytes), d_wl = umma_desc_sw128(sa + 2 * a_bytes + w_bytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    for (int k = 0; k < ((p.dbg & 1) ? 0 : kBlockK / kUmmaK); ++k) {
                         const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // +32 bytes inside the swizzle span
                         if (p.split_acc) {
                             // the accumulator add truncates: keeping the 2^-11-sized terms out of the big sum costs it
@@ -166,8 +174,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        // tcgen05.ld hands every lane one accumulator ROW, so storing straight from the registers writes 32 different
+        // rows per instruction, 16 bytes each (measured: the stores alone were 0.23 ms of a 0.38 ms projection).  Each
+        // warp therefore turns its 32 x 32 chunk around through a private shared-memory tile (row pitch 36 floats: the
+        // float4 accesses of both directions are conflict-free) and writes 4 rows x 128 contiguous bytes per instruction.
         const int quarter = warp & 3;
-        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+        float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256) + (warp - 2) * (32 * kEpiPitch);
+        const int rr = lane >> 3, cc = (lane & 7) * 4;  // read-back role: row within a group of 4, first of 4 columns
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = p.nbuf == 2 ? (it & 1) : 0;
@@ -176,40 +191,62 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             const int n0 = (int)((tile % p.n_tiles_n) * p.n_pad);
             mbar_wait(bar_tfull + 8 * acc, use & 1);
             tc_fence_after();
-            const int64_t row = m0 + quarter * 32 + lane;
+            const int64_t row0 = m0 + quarter * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ((uint32_t)p.n_pad << p.split_acc);
-            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                if (p.split_acc) {
-                    uint32_t sm[16];
-                    tmem_ld16(taddr + p.n_pad + c0, sm);
+            for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int cb = c0 + half * 16;
+                    if (cb >= p.n_pad) break;  // n_pad is a multiple of 16, not of 32
+                    uint32_t v[16];
+                    tmem_ld16(taddr + cb, v);
+                    if (p.split_acc) {
+                        uint32_t sm[16];
+                        tmem_ld16(taddr + p.n_pad + cb, sm);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(sm[j]));
+                    }
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(sm[j]));
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<uint4*>(stg + lane * kEpiPitch + half * 16 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
-                tmem_ld_wait();
-                if (row < p.M) {
-                    float* crow = p.C + row * p.ldc + n0 + c0;
-                    const int ncol = p.N - (n0 + c0);  // valid columns from here
-                    float o[16];
+                __syncwarp();
+                const int col = n0 + c0 + cc;     // first of this lane's 4 output columns
+                const int ncol = p.N - col;       // valid columns from there
+                if (!(p.dbg & 8)) {
+                    if (vec_ok && ncol >= 4 && c0 + cc < p.n_pad) {
+                        const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float f = __uint_as_float(v[j]);
-                        if (p.bias != nullptr && j < ncol) f += __ldg(p.bias + n0 + c0 + j);
-                        if (p.relu) f = fmaxf(f, 0.f);
-                        o[j] = f;
-                    }
-                    if (vec_ok && ncol >= 16 && ((n0 + c0) % 4 == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(crow + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < ncol) crow[j] = o[j];
+                        for (int r = 0; r < 32; r += 4) {
+                            const int64_t row = row0 + r + rr;
+                            float4 o = *reinterpret_cast<const float4*>(stg + (r + rr) * kEpiPitch + cc);
+                            o.x += bv.x;
+                            o.y += bv.y;
+                            o.z += bv.z;
+                            o.w += bv.w;
+                            if (p.relu) {
+                                o.x = fmaxf(o.x, 0.f);
+                                o.y = fmaxf(o.y, 0.f);
+                                o.z = fmaxf(o.z, 0.f);
+                                o.w = fmaxf(o.w, 0.f);
+                            }
+                            if (row < p.M) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = o;
+                        }
+                    } else if (ncol > 0 && c0 + cc < p.n_pad) {
+                        for (int r = 0; r < 32; r += 4) {
+                            const int64_t row = row0 + r + rr;
+                            if (row >= p.M) continue;
+                            for (int j = 0; j < 4 && j < ncol; ++j) {
+                                float f = stg[(r + rr) * kEpiPitch + cc + j] + (p.bias ? __ldg(p.bias + col + j) : 0.f);
+                                if (p.relu) f = fmaxf(f, 0.f);
+                                p.C[row * p.ldc + col + j] = f;
+                            }
+                        }
                     }
                 }
+                __syncwarp();  // the tile is rewritten by the next chunk
             }
             tc_fence_before();
             __syncwarp();
@@ -272,7 +309,7 @@ int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, 
     const int n_per = (N + p.n_tiles_n - 1) / p.n_tiles_n;
     p.n_pad = (n_per + 15) & ~15;
     const size_t stage_bytes = 2 * (size_t)kBlockM * kBlockK * 4 + 2 * (size_t)p.n_pad * kBlockK * 4;
-    int stages = (int)((220 * 1024 - 1024 - 256) / stage_bytes);
+    int stages = (int)((227 * 1024 - 1024 - 256 - kEpiBytes) / stage_bytes);
     if (stages > 4) stages = 4;
     GIGL_CHECK(ctx, stages >= 2, "tile does not fit in shared memory");
     p.stages = stages;
@@ -286,13 +323,15 @@ int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, 
     p.C = C;
     p.ldc = ldc;
     p.relu = relu;
+    static const int dbg = getenv("GIGL_GEMM_DBG") ? atoi(getenv("GIGL_GEMM_DBG")) : 0;
+    p.dbg = dbg;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
     int rc;
     if ((rc = make_map(ctx, &ta_hi, A_hi, M, K, lda, kBlockM, false)) != GIGL_OK) return rc;
     if ((rc = make_map(ctx, &ta_lo, A_lo, M, K, lda, kBlockM, false)) != GIGL_OK) return rc;
     if ((rc = make_map(ctx, &tw_hi, W_hi, N, K, ldw, p.n_pad, true)) != GIGL_OK) return rc;
     if ((rc = make_map(ctx, &tw_lo, W_lo, N, K, ldw, p.n_pad, true)) != GIGL_OK) return rc;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/ + kEpiBytes;
     static bool attr_set = false;
     if (!attr_set) {
         GIGL_CUDA(ctx, cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
