@@ -139,55 +139,45 @@ __global__ void roots_assign_kernel(int64_t n_roots, const int32_t* __restrict__
     atomicMin(lid + v, (int32_t)i);  // duplicate roots: the first slot owns the local id
 }
 
-// New local ids are claimed with atomicCAS on the dense map, but handed out in bulk: winners are staged
-// in shared memory and the block takes ONE range from the global counter per 8 rows (a single hot
-// counter with one atomic per node serialises in the L2 atomic unit).
+// New local ids are claimed with atomicCAS on the dense map, but handed out in bulk: winners are staged in shared
+// memory and the block takes ONE range from the global counter per 1024 keys (a single hot counter with one atomic per
+// node serialises in the L2 atomic unit).  The work is cut by KEY, not by row: a thread takes sorted keys and asks
+// whether the key's destination sits on the level being expanded (lid[dst] in [lo, hi); neighbouring keys share the
+// destination, so the lookup is a cached read).  A row-per-warp walk had the longest row of the batch - a hub that is
+// the hop-1 neighbour of thousands of roots - as its critical path (170 us measured; 25 us of key traffic).
 constexpr int kStageCap = 1024;
-__global__ void __launch_bounds__(256) expand_level_kernel(const int32_t* __restrict__ level_end, int level,
-                                                           const uint64_t* __restrict__ keys, uint64_t src_mask,
-                                                           const int2* __restrict__ segmap, int32_t* __restrict__ lid,
-                                                           int32_t* __restrict__ list, int32_t* __restrict__ n_nodes_ctr) {
+constexpr int kExpandKpt = kStageCap / 256;  // keys per thread per block iteration
+__global__ void __launch_bounds__(256) expand_level_kernel(const int32_t* __restrict__ level_end, int level, int64_t n_keys,
+                                                           const uint64_t* __restrict__ keys, int shift, uint64_t src_mask,
+                                                           int32_t* __restrict__ lid, int32_t* __restrict__ list,
+                                                           int32_t* __restrict__ n_nodes_ctr) {
     __shared__ int s_cnt, s_base;
     __shared__ int32_t s_stage[kStageCap];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t lo = level_end[level - 1], hi = level_end[level];
-    const int64_t step = (int64_t)gridDim.x * 8;
-    for (int64_t row0 = lo + (int64_t)blockIdx.x * 8; row0 < hi; row0 += step) {  // block-uniform trip count
+    const int lane = threadIdx.x & 31;
+    const int32_t lo = level_end[level - 1], hi = level_end[level];
+    const int64_t step = (int64_t)gridDim.x * kStageCap;
+    for (int64_t base = (int64_t)blockIdx.x * kStageCap; base < n_keys; base += step) {  // block-uniform trip count
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        const int64_t row = row0 + warp;
-        if (row < hi) {
-            const int32_t v = list[row];
-            const int2 seg = segmap[v];
-            for (int e0 = seg.x; e0 < seg.y; e0 += 32) {
-                const int e = e0 + lane;
-                int32_t sv = -1;
-                bool won = false;
-                if (e < seg.y) {
-                    sv = (int32_t)(keys[e] & src_mask);
+#pragma unroll
+        for (int u = 0; u < kExpandKpt; ++u) {
+            const int64_t e = base + u * 256 + threadIdx.x;
+            int32_t sv = -1;
+            bool won = false;
+            if (e < n_keys) {
+                const uint64_t k = keys[e];
+                const int32_t ld = lid[(uint32_t)(k >> shift)];  // ids of this level were all assigned by earlier launches
+                if (ld >= lo && ld < hi) {
+                    sv = (int32_t)(k & src_mask);
                     if (lid[sv] == kLidAbsent) won = atomicCAS(lid + sv, kLidAbsent, kLidPending) == kLidAbsent;
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, won);
-                if (m == 0) continue;
-                const int n = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
-                int slot = 0;
-                if (lane == 0) slot = atomicAdd(&s_cnt, n);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (slot + n <= kStageCap) {
-                    if (won) s_stage[slot + rank] = sv;
-                } else {  // stage full (very long rows): undo and take ids straight from the global counter
-                    int base = 0;
-                    if (lane == 0) {
-                        atomicSub(&s_cnt, n);
-                        base = atomicAdd(n_nodes_ctr, n);
-                    }
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (won) {
-                        list[base + rank] = sv;
-                        lid[sv] = base + rank;
-                    }
-                }
             }
+            const uint32_t m = __ballot_sync(0xffffffffu, won);
+            if (m == 0) continue;
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&s_cnt, __popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (won) s_stage[slot + __popc(m & ((1u << lane) - 1u))] = sv;  // <= kStageCap winners per iteration by construction
         }
         __syncthreads();
         const int n_staged = s_cnt;
@@ -222,7 +212,7 @@ __global__ void fill_i32_kernel(int64_t n, int32_t v, int32_t* __restrict__ p) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 constexpr int kSplitThreshold = 256;  // rows longer than this are split into parts ...
-constexpr int kPartEdges = 128;       // ... of this many sorted keys, one warp each
+constexpr int kPartEdges = 64;        // ... of this many sorted keys, one warp each
 constexpr int kGatherUnroll = 8;      // independent 16-byte loads in flight per lane
 
 // Sum of the unique sources of keys[e_beg, e_end) (a slice of the row that starts at row_beg) for
@@ -882,8 +872,11 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + 2, &init[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + kLevelBase, &init[1], sizeof(int32_t) * 2, cudaMemcpyHostToDevice, st));
     for (int j = 1; j < n_layers; ++j) {
-        expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->src_mask, b->segmap, b->lid, b->list, b->d_ctr + 2);
-        GIGL_LAUNCHED(ctx);
+        if (n_valid > 0) {
+            expand_level_kernel<<<grid1d(ctx, ceil_div64(n_valid, kExpandKpt), 256), 256, 0, st>>>(b->d_ctr + kLevelBase, j, n_valid, b->keys, b->shift,
+                                                                                                      b->src_mask, b->lid, b->list, b->d_ctr + 2);
+            GIGL_LAUNCHED(ctx);
+        }
         level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
         GIGL_LAUNCHED(ctx);
     }
@@ -1110,8 +1103,11 @@ int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges) {
     const int want = (b->n_hops > b->n_levels ? b->n_hops : b->n_levels) + 1;  // level_end entries [1..want]
     if (b->n_levels_done < want && b->n_roots > 0) {
         for (int j = b->n_levels_done; j < want; ++j) {
-            expand_level_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_ctr + kLevelBase, j, b->keys, b->src_mask, b->segmap, b->lid, b->list, b->d_ctr + 2);
-            GIGL_LAUNCHED(ctx);
+            if (b->n_valid_host > 0) {
+                expand_level_kernel<<<grid1d(ctx, ceil_div64(b->n_valid_host, kExpandKpt), 256), 256, 0, st>>>(
+                    b->d_ctr + kLevelBase, j, b->n_valid_host, b->keys, b->shift, b->src_mask, b->lid, b->list, b->d_ctr + 2);
+                GIGL_LAUNCHED(ctx);
+            }
             level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
             GIGL_LAUNCHED(ctx);
         }
