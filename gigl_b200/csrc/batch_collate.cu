@@ -212,7 +212,8 @@ __global__ void fill_i32_kernel(int64_t n, int32_t v, int32_t* __restrict__ p) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 constexpr int kSplitThreshold = 256;  // rows longer than this are split into parts ...
-constexpr int kPartEdges = 64;        // ... of this many sorted keys, one warp each
+constexpr int kPartEdges = 64;        // ... of this many sorted keys, one warp each (32 for rows wider than 128 floats:
+                                      // a part is a chain of dependent load batches, and wide rows take two column passes)
 constexpr int kGatherUnroll = 8;      // independent 16-byte loads in flight per lane
 
 // Sum of the unique sources of keys[e_beg, e_end) (a slice of the row that starts at row_beg) for
@@ -288,6 +289,7 @@ struct HeavyLists {
     float* partial;    // [part_cap, F]
     int32_t* pcnt;     // [part_cap]
     int32_t part_cap;
+    int32_t part_edges;  // sorted keys per part
 };
 
 // Sum of the already-resolved sources of one 32-key chunk (`my` per lane, -1 = skip).
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
         const int len = segA.y - segA.x;
         bool deferred = false;
         if (len > kSplitThreshold && hl.items != nullptr) {
-            const int n_parts = (len + kPartEdges - 1) / kPartEdges;
+            const int n_parts = (len + hl.part_edges - 1) / hl.part_edges;
             int slot = 0;
             if (lane == 0) slot = atomicAdd(hl.hctr, n_parts);
             slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -499,7 +501,7 @@ __global__ void __launch_bounds__(256) batch_gather_async_kernel(const int32_t* 
         const int len = segA.y - segA.x;
         bool deferred = false;
         if (len > kSplitThreshold && hl.items != nullptr) {
-            const int n_parts = (len + kPartEdges - 1) / kPartEdges;
+            const int n_parts = (len + hl.part_edges - 1) / hl.part_edges;
             int slot = 0;
             if (lane == 0) slot = atomicAdd(hl.hctr, n_parts);
             slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -605,8 +607,8 @@ __global__ void __launch_bounds__(256) batch_gather_parts_kernel(int F, const in
     for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n_items; it += warps) {
         const int2 item = hl.items[it];
         const int2 seg = __ldg(segmap + __ldg(list + item.x));
-        const int e_beg = seg.x + item.y * kPartEdges;
-        const int e_end = min(seg.y, e_beg + kPartEdges);
+        const int e_beg = seg.x + item.y * hl.part_edges;
+        const int e_end = min(seg.y, e_beg + hl.part_edges);
         for (int c0 = 0; c0 < F; c0 += LPR * 4) {
             const int c = c0 + sub * 4;
             const bool active = c < F;
@@ -1014,7 +1016,8 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
             GIGL_LAUNCHED(ctx);
         } else {
             // split-row work lists (sized from the collate's valid-key count; see kSplitThreshold)
-            const int64_t part_cap = b->n_valid_host / kPartEdges + b->n_valid_host / kSplitThreshold + 16;
+            const int part_edges = Fi > 128 ? kPartEdges / 2 : kPartEdges;
+            const int64_t part_cap = b->n_valid_host / part_edges + b->n_valid_host / kSplitThreshold + 16;
             const size_t o_items = 256;
             const size_t o_rows = o_items + ((sizeof(int2) * (size_t)part_cap + 255) & ~(size_t)255);
             const size_t o_pcnt = o_rows + ((sizeof(int4) * (size_t)part_cap + 255) & ~(size_t)255);
@@ -1029,6 +1032,7 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
             hl.pcnt = (int32_t*)((char*)ph + o_pcnt);
             hl.partial = (float*)((char*)ph + o_part);
             hl.part_cap = (int32_t)part_cap;
+            hl.part_edges = part_edges;
             GIGL_CUDA(ctx, cudaMemsetAsync(hl.hctr, 0, 2 * sizeof(int32_t), st));
             const int hgrid = ctx->sm_count * 4;
 #define GIGL_GATHER(LPR)                                                                                                  \

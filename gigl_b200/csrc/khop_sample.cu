@@ -735,7 +735,8 @@ static int ensure_hash_index(gigl_graph* g, int fmax, int n_hops) {
     if (!g->hx_enabled) return GIGL_OK;
     const int cap = fmax <= 16 ? 16 : fmax <= 32 ? 32 : fmax <= 64 ? 64 : 128;
     int lg = 0;
-    while ((1 << lg) < 8 * cap) ++lg;
+    static const int lmul = getenv("GIGL_HX_LMUL") ? atoi(getenv("GIGL_HX_LMUL")) : 8;  // block length / cap (experiments)
+    while ((1 << lg) < lmul * cap) ++lg;
     uint64_t want = (uint64_t)n_hops * (uint64_t)g->n_nodes + (1ULL << 21);
     if (want > (1ULL << 31)) want = 1ULL << 31;
     const int64_t n_blocks = (int64_t)(want >> lg);
