@@ -342,7 +342,7 @@ def run_ours(args):
     alg_bytes = (e1_total * (4 * F + 8) + n1_total * (8 + 4 + 4 * F + 8 * F)) / max(K, 1)
     achieved = alg_bytes / (g_ms / max(g_n, 1) * 1e-3) / 1e9 if g_n else None
     phase_ms = {k: v[0] / K for k, v in timings.items()}
-    roofline = {"kernel": "batch_gather_kernel<32> (layer-1 gather over the coalesced batch graph; + split-row parts/finish launches)",
+    roofline = {"kernel": "batch_gather_async_kernel<1, 8> (layer-1 gather over the coalesced batch graph; + split-row parts/finish launches)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "ms_per_launch": g_ms / max(g_n, 1), "share_of_step": (g_ms / K) / (ms / K)}

@@ -622,33 +622,59 @@ __global__ void __launch_bounds__(256) batch_gather_parts_kernel(int F, const in
     }
 }
 
-// One warp per split row: parts summed in part order (deterministic), then [mean | self].
-__global__ void __launch_bounds__(256) batch_gather_finish_kernel(int F, const float* __restrict__ xsrc, int64_t ldx,
-                                                                  const int32_t* __restrict__ list,
-                                                                  const int32_t* __restrict__ lid,
-                                                                  float* __restrict__ A_hi, float* __restrict__ A_lo,
-                                                                  int64_t ldA, const HeavyLists hl) {
-    const int lane = threadIdx.x & 31;
+// One CTA per split row: warp w sums parts w, w + 8, ... in order, the eight warp sums are added in warp order
+// (a fixed tree, so the result does not depend on scheduling), then [mean | self].  A hub row has thousands of parts:
+// one warp walking them alone was a 40 us critical path for a few KB of work.
+constexpr int kFinishWarps = 8;
+__global__ void __launch_bounds__(kFinishWarps * 32) batch_gather_finish_kernel(int F, const float* __restrict__ xsrc, int64_t ldx,
+                                                                              const int32_t* __restrict__ list,
+                                                                              const int32_t* __restrict__ lid,
+                                                                              float* __restrict__ A_hi, float* __restrict__ A_lo,
+                                                                              int64_t ldA, const HeavyLists hl) {
+    __shared__ float4 s_acc[kFinishWarps][32];
+    __shared__ int s_cnt[kFinishWarps];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_heavy = hl.hctr[1];
-    const int warps = gridDim.x * (blockDim.x >> 5);
-    for (int hr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); hr < n_heavy; hr += warps) {
+    for (int hr = blockIdx.x; hr < n_heavy; hr += gridDim.x) {
         const int4 r = hl.rows[hr];
         const int64_t row = r.x;
         const int64_t self = lid ? row : (int64_t)__ldg(list + row);
-        int n_uniq = 0;
-        for (int p = 0; p < r.z; ++p) n_uniq += hl.pcnt[r.y + p];
-        const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
-        for (int c = lane * 4; c < F; c += 128) {
+        int cnt = 0;
+        for (int p = w * 32 + lane; p < r.z; p += kFinishWarps * 32) cnt += hl.pcnt[r.y + p];
+#pragma unroll
+        for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0) s_cnt[w] = cnt;
+        for (int c0 = 0; c0 < F; c0 += 128) {
+            const int c = c0 + lane * 4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int p = 0; p < r.z; ++p) {
-                const float4 t = *reinterpret_cast<const float4*>(hl.partial + (int64_t)(r.y + p) * F + c);
-                acc.x += t.x;
-                acc.y += t.y;
-                acc.z += t.z;
-                acc.w += t.w;
+            if (c < F) {
+                for (int p = w; p < r.z; p += kFinishWarps) {
+                    const float4 t = *reinterpret_cast<const float4*>(hl.partial + (int64_t)(r.y + p) * F + c);
+                    acc.x += t.x;
+                    acc.y += t.y;
+                    acc.z += t.z;
+                    acc.w += t.w;
+                }
             }
-            store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
-            store_split4(A_hi, A_lo, row * ldA + F + c, ldg4(xsrc + self * ldx + c));
+            s_acc[w][lane] = acc;
+            __syncthreads();
+            if (w == 0 && c < F) {
+                int n_uniq = 0;
+#pragma unroll
+                for (int k = 0; k < kFinishWarps; ++k) n_uniq += s_cnt[k];
+                const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
+#pragma unroll
+                for (int k = 1; k < kFinishWarps; ++k) {
+                    const float4 t = s_acc[k][lane];
+                    acc.x += t.x;
+                    acc.y += t.y;
+                    acc.z += t.z;
+                    acc.w += t.w;
+                }
+                store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
+                store_split4(A_hi, A_lo, row * ldA + F + c, ldg4(xsrc + self * ldx + c));
+            }
+            __syncthreads();
         }
     }
 }

@@ -76,9 +76,9 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md"), "w") as f:
         f.write(f"| `{name[:60]}` | " + " | ".join(f"{r[i]} {units[i]}" for _, i in idx) + " |\n")
         rd_i, wr_i, g_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("launch__grid_size")
         traffic[name].append((int(float(r[g_i])), gb(r[rd_i], units[rd_i]) + gb(r[wr_i], units[wr_i])))
-# layer-1 gather = the LARGER of the two batch_gather_kernel launches per step (+ its parts launch)
+# layer-1 gather = the LARGER of the two main gather launches per step (+ its parts launch)
 out = {}
-main = [t for k, v in traffic.items() if "batch_gather_kernel" in k for t in v]
+main = [t for k, v in traffic.items() if ("batch_gather_kernel" in k or "batch_gather_async_kernel" in k) for t in v]
 parts = [t for k, v in traffic.items() if "batch_gather_parts" in k for t in v]
 if main:
     l1 = max(t[1] for t in main)
