@@ -166,6 +166,14 @@ inline uint8_t* put_edge(uint8_t* p, uint32_t src, uint32_t dst, int32_t type, c
 }
 
 // Host-side tables the hydration joins read (all optional except the trees).
+struct ETab {  // one hydrated edge table (main / user-defined positive / user-defined negative)
+    const int64_t* rowptr;     // in-CSR by destination, rows ascending (nullptr: one feature-less Edge per sampled pair)
+    const int32_t* col;
+    const int32_t* edge_rows;  // CSR slot -> row of ef (nullptr: the slot index itself)
+    const float* ef;
+    int Fe;
+};
+
 struct Tables {
     const int32_t* roots;
     const int32_t* fanouts;
@@ -174,39 +182,38 @@ struct Tables {
     const float* x;
     int F;
     int32_t ntype, etype;
-    const int64_t* rowptr;  // in-CSR by destination, rows ascending (nullptr: one feature-less Edge per filled slot)
-    const int32_t* col;
-    const int32_t* edge_rows;  // CSR slot -> row of edge_feat (nullptr: slot index itself)
-    const float* ef;
-    int Fe;
+    ETab tab[3];  // 0 = main edges, 1 = positive label edges, 2 = negative label edges
 };
 
 struct EdgeRef {
     uint32_t src, dst;
-    int64_t row;  // row of the edge-feature table, -1 = none
+    int64_t row;  // row of the table's feature matrix, -1 = none
+    int tag;      // which ETab hydrates it
 };
 
 struct RootPlan {
     std::vector<uint32_t> nodes;     // distinct, first-seen order
     std::vector<EdgeRef> edges;      // src = hop-k node, dst = hop-(k-1) node
     std::vector<EdgeRef> pos_edges;  // NodeAnchorBasedLinkPredictionSample.pos_edges
+    std::vector<EdgeRef> neg_edges;  // NodeAnchorBasedLinkPredictionSample.hard_neg_edges
     std::vector<std::pair<uint32_t, uint32_t>> tmp;
 };
 
-// hydrateEdges: the sampled pair (src -> dst) INNER JOINs the hydrated edge table on (_from, _to)
-// (SGSPureSparkV1Task.scala:540-563): one Edge per matching record - exactly one for undirected graphs, one per
-// duplicate record for directed graphs that carry duplicates.
-void join_edge(const Tables& t, uint32_t src, uint32_t dst, std::vector<EdgeRef>& out) {
-    if (!t.rowptr) {
-        out.push_back({src, dst, -1});
+// hydrateEdges / hydrateTaskBasedEdges: the sampled pair (src -> dst) INNER JOINs the hydrated edge table on
+// (_from, _to) (SGSPureSparkV1Task.scala:540-563, NodeAnchorBasedLinkPredictionBaseTask.scala:280-334): one Edge per
+// matching record - exactly one for undirected graphs, one per duplicate record for directed tables with duplicates.
+void join_edge(const Tables& t, int tag, uint32_t src, uint32_t dst, std::vector<EdgeRef>& out) {
+    const ETab& e = t.tab[tag];
+    if (!e.rowptr) {
+        out.push_back({src, dst, -1, tag});
         return;
     }
-    const int32_t* b = t.col + t.rowptr[dst];
-    const int32_t* e = t.col + t.rowptr[dst + 1];
-    auto r = std::equal_range(b, e, (int32_t)src);
+    const int32_t* b = e.col + e.rowptr[dst];
+    const int32_t* en = e.col + e.rowptr[dst + 1];
+    auto r = std::equal_range(b, en, (int32_t)src);
     for (const int32_t* q = r.first; q != r.second; ++q) {
-        const int64_t slot = q - t.col;
-        out.push_back({src, dst, t.Fe > 0 ? (t.edge_rows ? (int64_t)t.edge_rows[slot] : slot) : -1});
+        const int64_t slot = q - e.col;
+        out.push_back({src, dst, e.Fe > 0 ? (e.edge_rows ? (int64_t)e.edge_rows[slot] : slot) : -1, tag});
     }
 }
 
@@ -223,7 +230,7 @@ void walk_tree(const Tables& t, int64_t r, RootPlan& out) {
             for (int j = 0; j < f; ++j) {
                 const int32_t c = cur[pslot * f + j];
                 if (c < 0) continue;
-                join_edge(t, (uint32_t)c, (uint32_t)parent, out.edges);
+                join_edge(t, 0, (uint32_t)c, (uint32_t)parent, out.edges);
                 out.nodes.push_back((uint32_t)c);
             }
         }
@@ -257,8 +264,9 @@ void distinct_edges(const Tables& t, std::vector<EdgeRef>& e) {
     for (size_t i = 0; i < e.size(); ++i) {
         bool dup = false;
         for (size_t k = m; k-- > 0 && e[k].src == e[i].src && e[k].dst == e[i].dst;) {
-            if (e[k].row == e[i].row || t.Fe == 0 ||
-                memcmp(t.ef + (size_t)e[k].row * t.Fe, t.ef + (size_t)e[i].row * t.Fe, sizeof(float) * (size_t)t.Fe) == 0) {
+            const ETab& m = t.tab[0];
+            if (e[k].row == e[i].row || m.Fe == 0 ||
+                memcmp(m.ef + (size_t)e[k].row * m.Fe, m.ef + (size_t)e[i].row * m.Fe, sizeof(float) * (size_t)m.Fe) == 0) {
                 dup = true;
                 break;
             }
@@ -272,19 +280,23 @@ void plan_root(const Tables& t, int64_t r, RootPlan& out) {
     out.nodes.clear();
     out.edges.clear();
     out.pos_edges.clear();
+    out.neg_edges.clear();
     walk_tree(t, r, out);
     distinct_nodes(out);
 }
 
-// NodeAnchorBasedLinkPredictionSample of anchor roots[r]: neighbourhood = array_distinct(root's ++ every positive's)
-// (lookupDstNodeNeighborhood + the merge at NodeAnchorBasedLinkPredictionTask.scala:186-209; a directed source-only
-// anchor has an empty tree of its own and keeps the positives' neighbourhoods + itself, formNeighborhoodForSrcOnlyNodes
-// NodeAnchorBasedLinkPredictionBaseTask.scala:200-278), pos_edges = hydrateTaskBasedEdges (:280-334).
-// Returns false if the anchor has no positive (no sample: the INNER JOINs drop it).
-bool plan_anchor(const Tables& t, int64_t r, int num_pos, const int32_t* pos, const int64_t* pos_tree, RootPlan& out) {
+// NodeAnchorBasedLinkPredictionSample of anchor roots[r]: neighbourhood = array_distinct(root's ++ every positive's ++
+// every hard negative's) (lookupDstNodeNeighborhood + the merges at NodeAnchorBasedLinkPredictionTask.scala:186-209 and
+// UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:405-581; a directed source-only anchor has an empty tree of
+// its own and keeps the labels' neighbourhoods + itself, NodeAnchorBasedLinkPredictionBaseTask.scala:200-278),
+// pos_edges / hard_neg_edges = hydrateTaskBasedEdges against the table the labels were sampled from (:280-334).
+// Returns false if the anchor has no positive (no sample: the INNER JOINs drop it; negatives are LEFT JOINed).
+bool plan_anchor(const Tables& t, int64_t r, int num_pos, const int32_t* pos, const int64_t* pos_tree, int num_neg, const int32_t* neg,
+                 const int64_t* neg_tree, RootPlan& out) {
     out.nodes.clear();
     out.edges.clear();
     out.pos_edges.clear();
+    out.neg_edges.clear();
     bool any = false;
     for (int j = 0; j < num_pos; ++j) any |= pos[r * num_pos + j] >= 0;
     if (!any) return false;
@@ -295,20 +307,30 @@ bool plan_anchor(const Tables& t, int64_t r, int num_pos, const int32_t* pos, co
         if (p < 0) continue;
         if (pos_tree[r * num_pos + j] >= 0) walk_tree(t, pos_tree[r * num_pos + j], out);
         else out.nodes.push_back((uint32_t)p);
-        join_edge(t, root, (uint32_t)p, out.pos_edges);  // (_src_node = root, _dst_node = positive)
+        join_edge(t, 1, root, (uint32_t)p, out.pos_edges);  // (_src_node = root, _dst_node = positive)
+    }
+    if (out.pos_edges.empty()) return false;
+    for (int j = 0; j < num_neg; ++j) {
+        const int32_t q = neg[r * num_neg + j];
+        if (q < 0) continue;
+        if (neg_tree[r * num_neg + j] >= 0) walk_tree(t, neg_tree[r * num_neg + j], out);
+        else out.nodes.push_back((uint32_t)q);
+        join_edge(t, 2, root, (uint32_t)q, out.neg_edges);
     }
     // first-seen order with the root's own neighbourhood first
     distinct_nodes(out);
     distinct_edges(t, out.edges);
-    return !out.pos_edges.empty();
+    return true;
 }
 
 struct Sizes {
-    size_t root_node, graph, labels, pos, message;
+    size_t root_node, graph, labels, pos, neg, message;
 };
 
-inline const float* ef_row(const Tables& t, const EdgeRef& e) { return (t.Fe > 0 && e.row >= 0) ? t.ef + (size_t)e.row * t.Fe : nullptr; }
-inline int ef_len(const Tables& t, const EdgeRef& e) { return (t.Fe > 0 && e.row >= 0) ? t.Fe : 0; }
+inline int ef_len(const Tables& t, const EdgeRef& e) { return (t.tab[e.tag].Fe > 0 && e.row >= 0) ? t.tab[e.tag].Fe : 0; }
+inline const float* ef_row(const Tables& t, const EdgeRef& e) {
+    return ef_len(t, e) ? t.tab[e.tag].ef + (size_t)e.row * t.tab[e.tag].Fe : nullptr;
+}
 
 Sizes message_sizes(const Tables& t, const RootPlan& pl, uint32_t root, bool with_label, int32_t label, size_t label_type_len) {
     Sizes s{};
@@ -334,9 +356,14 @@ Sizes message_sizes(const Tables& t, const RootPlan& pl, uint32_t root, bool wit
         const size_t es = edge_size(e.src, e.dst, t.etype, ef_len(t, e));
         s.pos += 1 + varint_size(es) + es;
     }
+    s.neg = 0;
+    for (const auto& e : pl.neg_edges) {
+        const size_t es = edge_size(e.src, e.dst, t.etype, ef_len(t, e));
+        s.neg += 1 + varint_size(es) + es;
+    }
     s.message = 1 + varint_size(s.root_node) + s.root_node;
     if (s.graph > 0) s.message += 1 + varint_size(s.graph) + s.graph;
-    s.message += s.labels + s.pos;
+    s.message += s.labels + s.pos + s.neg;
     return s;
 }
 
@@ -356,8 +383,8 @@ inline uint8_t* put_graph_body(const Tables& t, const RootPlan& pl, uint8_t* p) 
 }
 
 int encode_samples(int32_t kind, int64_t n_roots, int64_t n_emit, const Tables& t, const int32_t* labels, const char* label_type,
-                   int32_t num_pos, const int32_t* pos, const int64_t* pos_tree, int32_t tfrecord_framing, uint8_t** out,
-                   int64_t* out_bytes, int64_t* record_offsets) {
+                   int32_t num_pos, const int32_t* pos, const int64_t* pos_tree, int32_t num_neg, const int32_t* neg,
+                   const int64_t* neg_tree, int32_t tfrecord_framing, uint8_t** out, int64_t* out_bytes, int64_t* record_offsets) {
     *out = nullptr;
     *out_bytes = 0;
     const size_t lt_len = label_type ? strlen(label_type) : 0;
@@ -379,7 +406,7 @@ int encode_samples(int32_t kind, int64_t n_roots, int64_t n_emit, const Tables& 
                     if (label == no_label) continue;  // unlabeled node: no SupervisedNodeClassificationSample (inner join with the labels)
                 }
                 if (kind == 2) {
-                    if (!plan_anchor(t, r, num_pos, pos, pos_tree, pl)) continue;
+                    if (!plan_anchor(t, r, num_pos, pos, pos_tree, num_neg, neg, neg_tree, pl)) continue;
                 } else {
                     plan_root(t, r, pl);
                 }
@@ -403,8 +430,13 @@ int encode_samples(int32_t kind, int64_t n_roots, int64_t n_emit, const Tables& 
                 p = put_varint(p, s.root_node);
                 p = put_node(p, root, t.ntype, t.F > 0 ? t.x + (size_t)root * t.F : nullptr, t.F);
                 if (kind == 2) {
-                    // neighborhood = 3, pos_edges = 4 (hard_neg_edges = 2 and neg_edges = 5 stay empty:
-                    // castToTrainingSampleProtoSchema, NodeAnchorBasedLinkPredictionBaseTask.scala:388-406)
+                    // hard_neg_edges = 2 (user-defined negatives only), neighborhood = 3, pos_edges = 4; neg_edges = 5 stays
+                    // empty (castToTrainingSampleProtoSchema, NodeAnchorBasedLinkPredictionBaseTask.scala:388-426)
+                    for (const auto& e : pl.neg_edges) {
+                        *p++ = 0x12;
+                        p = put_varint(p, edge_size(e.src, e.dst, t.etype, ef_len(t, e)));
+                        p = put_edge(p, e.src, e.dst, t.etype, ef_row(t, e), ef_len(t, e));
+                    }
                     if (s.graph > 0) {
                         *p++ = 0x1A;
                         p = put_varint(p, s.graph);
@@ -479,6 +511,21 @@ int gigl_encode_samples_host(int32_t kind, int64_t n_roots, const int32_t* roots
                                        out, out_bytes, record_offsets);
 }
 
+static bool etab_ok(const gigl_edge_table* e) {
+    if (!e) return true;
+    if ((e->rowptr == nullptr) != (e->col == nullptr)) return false;
+    return e->n_feat >= 0 && (e->n_feat == 0 || (e->feat && e->rowptr));
+}
+static ETab etab_of(const gigl_edge_table* e) {
+    if (!e) return ETab{nullptr, nullptr, nullptr, nullptr, 0};
+    return ETab{e->rowptr, e->col, e->edge_rows, e->feat, e->n_feat};
+}
+static bool labels_ok(int64_t n_emit, int64_t n_roots, const int32_t* roots, int32_t n, const int32_t* ids, const int64_t* trees) {
+    for (int64_t i = 0; i < n_emit * n; ++i)
+        if (trees[i] >= n_roots || (ids[i] >= 0 && trees[i] >= 0 && roots[trees[i]] != ids[i])) return false;
+    return true;
+}
+
 int gigl_encode_samples_ex_host(int32_t kind, int64_t n_roots, int64_t n_emit, const int32_t* roots, const int32_t* fanouts,
                                 int32_t n_hops, const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
                                 int32_t condensed_edge_type, const int64_t* rowptr, const int32_t* col, const int32_t* edge_rows,
@@ -492,14 +539,34 @@ int gigl_encode_samples_ex_host(int32_t kind, int64_t n_roots, int64_t n_emit, c
     if (kind == 1 && !labels) return GIGL_E_INVALID;
     if (kind == 2 && (num_pos < 1 || !pos || !pos_tree)) return GIGL_E_INVALID;
     if (F < 0 || (F > 0 && !x)) return GIGL_E_INVALID;
-    if (Fe < 0 || (Fe > 0 && (!edge_feat || !rowptr || !col))) return GIGL_E_INVALID;
-    if ((rowptr == nullptr) != (col == nullptr)) return GIGL_E_INVALID;
-    if (kind == 2)
-        for (int64_t i = 0; i < n_emit * num_pos; ++i)
-            if (pos_tree[i] >= n_roots || (pos[i] >= 0 && pos_tree[i] >= 0 && roots[pos_tree[i]] != pos[i])) return GIGL_E_INVALID;
-    const Tables t{roots, fanouts, n_hops, nbr, x, F, condensed_node_type, condensed_edge_type, rowptr, col, edge_rows, edge_feat, Fe};
-    return encode_samples(kind, n_roots, n_emit, t, labels, label_type, num_pos, pos, pos_tree, tfrecord_framing, out, out_bytes,
-                          record_offsets);
+    const gigl_edge_table main_tab{rowptr, col, edge_rows, edge_feat, Fe};
+    if (!etab_ok(&main_tab)) return GIGL_E_INVALID;
+    if (kind == 2 && !labels_ok(n_emit, n_roots, roots, num_pos, pos, pos_tree)) return GIGL_E_INVALID;
+    const ETab m = etab_of(&main_tab);
+    const Tables t{roots, fanouts, n_hops, nbr, x, F, condensed_node_type, condensed_edge_type, {m, m, ETab{nullptr, nullptr, nullptr, nullptr, 0}}};
+    return encode_samples(kind, n_roots, n_emit, t, labels, label_type, num_pos, pos, pos_tree, 0, nullptr, nullptr, tfrecord_framing, out,
+                          out_bytes, record_offsets);
+}
+
+int gigl_encode_link_samples_host(int64_t n_roots, int64_t n_emit, const int32_t* roots, const int32_t* fanouts, int32_t n_hops,
+                                  const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
+                                  int32_t condensed_edge_type, const gigl_edge_table* main_edges, const gigl_edge_table* pos_edges,
+                                  const gigl_edge_table* neg_edges, int32_t num_pos, const int32_t* pos, const int64_t* pos_tree,
+                                  int32_t num_neg, const int32_t* neg, const int64_t* neg_tree, int32_t tfrecord_framing, uint8_t** out,
+                                  int64_t* out_bytes, int64_t* record_offsets) {
+    if (!out || !out_bytes || n_roots < 0 || n_emit < 0 || n_emit > n_roots || n_hops < 1 || n_hops > GIGL_MAX_HOPS || !fanouts || !nbr ||
+        (n_roots > 0 && !roots))
+        return GIGL_E_INVALID;
+    if (num_pos < 1 || !pos || !pos_tree || num_neg < 0 || (num_neg > 0 && (!neg || !neg_tree))) return GIGL_E_INVALID;
+    if (F < 0 || (F > 0 && !x)) return GIGL_E_INVALID;
+    if (!etab_ok(main_edges) || !etab_ok(pos_edges) || !etab_ok(neg_edges)) return GIGL_E_INVALID;
+    if (!labels_ok(n_emit, n_roots, roots, num_pos, pos, pos_tree)) return GIGL_E_INVALID;
+    if (num_neg > 0 && !labels_ok(n_emit, n_roots, roots, num_neg, neg, neg_tree)) return GIGL_E_INVALID;
+    const ETab m = etab_of(main_edges);
+    const Tables t{roots, fanouts, n_hops, nbr, x, F, condensed_node_type, condensed_edge_type,
+                   {m, pos_edges ? etab_of(pos_edges) : m, etab_of(neg_edges)}};
+    return encode_samples(2, n_roots, n_emit, t, nullptr, nullptr, num_pos, pos, pos_tree, num_neg, neg, neg_tree, tfrecord_framing, out,
+                          out_bytes, record_offsets);
 }
 
 // ---- TFRecord reading + tf.Example decoding ----------------------------------------------------------

@@ -153,6 +153,66 @@ def encode_samples(roots, fanouts, nbr, x: Optional[np.ndarray] = None, kind: st
     return data, offs
 
 
+class HostEdgeTable:
+    """Host arrays of one hydrated edge table (main / user-defined positive / negative) for the sample encoder:
+    in-CSR by destination + the input record behind every CSR slot + the records' feature rows."""
+
+    def __init__(self, csr: Optional[Tuple[np.ndarray, np.ndarray]] = None, edge_rows: Optional[np.ndarray] = None,
+                 edge_feat: Optional[np.ndarray] = None):
+        self.rowptr = self.col = self.edge_rows = self.feat = None
+        if csr is not None:
+            self.rowptr = np.ascontiguousarray(csr[0], dtype=np.int64)
+            self.col = np.ascontiguousarray(csr[1], dtype=np.int32)
+            if edge_feat is not None and edge_feat.size:
+                self.feat = np.ascontiguousarray(edge_feat, dtype=np.float32)
+                if edge_rows is not None:
+                    self.edge_rows = np.ascontiguousarray(edge_rows, dtype=np.int32)
+
+    def struct(self) -> "_capi.EdgeTable":
+        p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        return _capi.EdgeTable(p(self.rowptr), p(self.col), p(self.edge_rows), p(self.feat), 0 if self.feat is None else self.feat.shape[1])
+
+
+def encode_link_samples(roots, fanouts, nbr, x: Optional[np.ndarray], n_emit: int, pos, pos_tree, main: HostEdgeTable,
+                        pos_table: Optional[HostEdgeTable] = None, neg=None, neg_tree=None, neg_table: Optional[HostEdgeTable] = None,
+                        condensed_node_type: int = 0, condensed_edge_type: int = 0, tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
+    """NodeAnchorBasedLinkPredictionSample messages with positives (and optional hard negatives) that were sampled
+    from - and are hydrated against - their own edge tables (gigl_encode_link_samples_host).  `pos_table` None = the
+    main table.  Returns (bytes, record_offsets [n_emit + 1])."""
+    L = _capi.lib()
+    roots = np.ascontiguousarray(roots, dtype=np.int32)
+    fan = np.ascontiguousarray(fanouts, dtype=np.int32)
+    nbr = [np.ascontiguousarray(a, dtype=np.int32) for a in nbr]
+    F, xp = 0, None
+    if x is not None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        F, xp = x.shape[1], x.ctypes.data
+    pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(n_emit, -1)
+    pos_tree = np.ascontiguousarray(pos_tree, dtype=np.int64).reshape(n_emit, -1)
+    num_neg, ngp, ntp = 0, None, None
+    if neg is not None:
+        neg = np.ascontiguousarray(neg, dtype=np.int32).reshape(n_emit, -1)
+        neg_tree = np.ascontiguousarray(neg_tree, dtype=np.int64).reshape(n_emit, -1)
+        num_neg, ngp, ntp = neg.shape[1], neg.ctypes.data, neg_tree.ctypes.data
+    tm = main.struct()
+    tp = pos_table.struct() if pos_table is not None else None
+    tn = neg_table.struct() if neg_table is not None else None
+    pn = (C.c_void_p * len(fan))(*[a.ctypes.data for a in nbr])
+    out = C.c_void_p()
+    nbytes = C.c_int64()
+    offs = np.zeros(n_emit + 1, dtype=np.int64)
+    rc = L.gigl_encode_link_samples_host(len(roots), n_emit, roots.ctypes.data, fan.ctypes.data, len(fan), pn, xp, F, condensed_node_type,
+                                         condensed_edge_type, C.addressof(tm), C.addressof(tp) if tp is not None else None,
+                                         C.addressof(tn) if tn is not None else None, pos.shape[1], pos.ctypes.data, pos_tree.ctypes.data,
+                                         num_neg, ngp, ntp, int(tfrecord_framing), C.byref(out), C.byref(nbytes), offs.ctypes.data)
+    _check(rc, "gigl_encode_link_samples_host")
+    try:
+        data = C.string_at(out.value, nbytes.value)
+    finally:
+        L.gigl_free_host(out)
+    return data, offs
+
+
 # ---- a minimal protobuf wire reader (tests, tooling): no generated code needed --------------------
 def _varint(buf: bytes, pos: int) -> Tuple[int, int]:
     v = shift = 0

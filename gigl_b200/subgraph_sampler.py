@@ -21,8 +21,12 @@ Fanouts come from `numNeighborsToSample` (both hops, as the pure-Spark tasks do)
 ops over the one edge type - the per-hop fanouts that only the reference's spark35 path can express,
 scala_spark35/.../SamplingOpDAG.scala:19-51).
 
-Scope (DESIGN.md): homogeneous graphs (one node type, one edge type), local / file:// URIs.  User-defined positive /
-negative labels, branching sampling DAGs and `gs://` are not implemented and raise.  The reference's default
+User-defined positive / negative label edges (`positiveEdgeInfo` / `negativeEdgeInfo` of the edge type,
+UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:54-581) are sampled from and hydrated against their own tables
+(`numUserDefinedPositiveSamples` / `numUserDefinedNegativeSamples`; negatives fill `hard_neg_edges`).
+
+Scope (DESIGN.md): homogeneous graphs (one node type, one edge type), local / file:// URIs.  Branching sampling DAGs
+and `gs://` are not implemented and raise.  The reference's default
 permutation strategy is the unseedable Spark shuffle; this implementation always uses the seeded hash permutation (a
 valid uniform sample; bit-exact to the reference's `permutation_strategy: deterministic`).
 """
@@ -128,8 +132,6 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
 
     ntype, nmeta = _first(meta["condensedNodeTypeToPreprocessedMetadata"])
     etype, emeta = _first(meta["condensedEdgeTypeToPreprocessedMetadata"])
-    if is_nablp and (emeta.get("positiveEdgeInfo") or emeta.get("negativeEdgeInfo")):
-        raise NotImplementedError("user-defined positive / negative edges (UserDefinedLabelsNodeAnchorBasedLinkPredictionTask)")
     # ---- node table: ids, features in featureKeys order, labels
     nodes = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(nmeta["tfrecordUriPrefix"], root)))
     node_id = nodes.column(nmeta["nodeIdKey"], "int64").astype(np.int64)
@@ -141,6 +143,16 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
     dst = edges.column(emeta["dstNodeIdKey"], "int64")
     ef = _feature_matrix(edges, main.get("featureKeys"))
     n_nodes = int(max(node_id.max(initial=-1), src.max(initial=-1), dst.max(initial=-1)) + 1)
+    # user-defined label edges (UserDefinedLabelsNodeAnchorBasedLinkPredictionTask): their own tf.Example tables
+    label_tables = {}
+    if is_nablp:
+        for usage, key in (("pos", "positiveEdgeInfo"), ("neg", "negativeEdgeInfo")):
+            info = emeta.get(key)
+            if info and info.get("tfrecordUriPrefix"):
+                t = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(info["tfrecordUriPrefix"], root)))
+                ls, ld = t.column(emeta["srcNodeIdKey"], "int64"), t.column(emeta["dstNodeIdKey"], "int64")
+                label_tables[usage] = (ls.astype(np.int32), ld.astype(np.int32), _feature_matrix(t, info.get("featureKeys")))
+                n_nodes = int(max(n_nodes, ls.max(initial=-1) + 1, ld.max(initial=-1) + 1))
     x = None
     if feat is not None:
         x = np.zeros((n_nodes, feat.shape[1]), dtype=np.float32)
@@ -160,7 +172,7 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
     t1 = time.time()
     if is_nablp:
         _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32, n_nodes, directed, sgs, skip_main, max_train,
-                   batch_roots, stats)
+                   batch_roots, stats, label_tables)
     else:
         _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n_nodes, skip_main, max_train, batch_roots, stats)
     stats["seconds_sample_and_write"] = time.time() - t1
@@ -200,8 +212,18 @@ def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n
             stats["snc"] += int((np.diff(offs) > 0).sum())
 
 
+def _label_table(ctx, n_nodes, ls, ld, feat):
+    """A user-defined label table (never bidirectionalised: only MAIN edges are, SGSPureSparkV1Task.scala:262-273):
+    the out-CSR the labels are sampled from + the host table their edges are hydrated against."""
+    g_out = Graph.from_edges_host(ctx, n_nodes, ls, ld, is_graph_directed=True, by_source=True)
+    g_in = Graph.from_edges_host(ctx, n_nodes, ls, ld, is_graph_directed=True)
+    tab = sio.HostEdgeTable(g_in.csr_host(), ctx.edge_rows_host(n_nodes, ls, ld, True) if feat is not None else None, feat)
+    g_in.close()
+    return g_out, tab
+
+
 def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32, n_nodes, directed, sgs, skip_main, max_train,
-               batch_roots, stats):
+               batch_roots, stats, label_tables):
     out = flat["nodeAnchorBasedLinkPredictionOutput"]
     sup = cfg["taskMetadata"]["nodeAnchorBasedLinkPredictionTaskMetadata"]["supervisionEdgeTypes"]
     dst_type = sup[0]["dstNodeType"]
@@ -212,28 +234,48 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
     rnn_dir = _resolve(neg_map[dst_type], root)
     main_dir = _resolve(out["tfrecordUriPrefix"], root)
     os.makedirs(rnn_dir, exist_ok=True)
-    num_pos = int(sgs.get("numPositiveSamples", 0))
-    g_out = None
+    g_pos = g_neg = pos_tab = neg_tab = None
+    num_pos = num_neg = 0
+    main_tab = sio.HostEdgeTable(hyd["csr"], hyd["edge_rows"], hyd["edge_feat"])
     if not skip_main:
-        if num_pos < 1:
-            raise ValueError("datasetConfig.subgraphSamplerConfig.numPositiveSamples must be >= 1")
         os.makedirs(main_dir, exist_ok=True)
-        # positives walk the out-CSR (row u = sorted destinations of u); undirected graphs are symmetric
-        g_out = g if not directed else Graph.from_edges_host(ctx, n_nodes, src32, dst32, is_graph_directed=True, by_source=True)
+        if "pos" in label_tables:
+            num_pos = int(sgs.get("numUserDefinedPositiveSamples", 0))
+            if num_pos < 1:  # the reference asserts this (UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:81-88)
+                raise ValueError("numUserDefinedPositiveSamples must be > 0 when user-defined positive edges are provided")
+            g_pos, pos_tab = _label_table(ctx, n_nodes, *label_tables["pos"])
+        else:
+            num_pos = int(sgs.get("numPositiveSamples", 0))
+            if num_pos < 1:
+                raise ValueError("datasetConfig.subgraphSamplerConfig.numPositiveSamples must be >= 1")
+            # positives walk the out-CSR (row u = sorted destinations of u); undirected graphs are symmetric
+            g_pos = g if not directed else Graph.from_edges_host(ctx, n_nodes, src32, dst32, is_graph_directed=True, by_source=True)
+        if "neg" in label_tables:
+            num_neg = int(sgs.get("numUserDefinedNegativeSamples", 0))
+            if num_neg < 1:
+                raise ValueError("numUserDefinedNegativeSamples must be > 0 when user-defined negative edges are provided")
+            g_neg, neg_tab = _label_table(ctx, n_nodes, *label_tables["neg"])
     for part, s in enumerate(range(0, len(roots_all), batch_roots)):
         roots = roots_all[s:s + batch_roots]
         n = len(roots)
-        pos = None
+        pos = neg = None
         sample_roots = roots
-        if g_out is not None:
-            pos, pcnt = g_out.sample_positives_host(roots, num_pos, base_seed=SAMPLING_SEED, call_no=3)
+        if g_pos is not None:
+            # permutation call numbers: hop 1 = 1, hop 2 = 2, positives = 3, user-defined negatives = 4 (the JVM-global
+            # counter of SamplingStrategy.scala:14,36,79 in the order the task calls it)
+            pos, pcnt = g_pos.sample_positives_host(roots, num_pos, base_seed=SAMPLING_SEED, call_no=3)
             pos = pos.reshape(n, num_pos)
             if max_train > 0:
                 # numMaxTrainingSamplesToOutput: the reference keeps an arbitrary `LIMIT n` of the anchors
                 # (downsampleNumberOfNodes, SGSPureSparkV1Task.scala:1042-1081); this keeps the first n by node id
                 anchors = np.flatnonzero(pcnt > 0)
                 pos[anchors[max(0, max_train - stats["nablp"]):]] = -1
-            extra = np.setdiff1d(pos[pos >= 0], roots)  # positives whose trees are not in this batch
+            labels = pos[pos >= 0]
+            if g_neg is not None:
+                neg, _ = g_neg.sample_positives_host(roots, num_neg, base_seed=SAMPLING_SEED, call_no=4)
+                neg = neg.reshape(n, num_neg)
+                labels = np.concatenate([labels, neg[neg >= 0]])
+            extra = np.setdiff1d(labels, roots)  # label nodes whose trees are not in this batch
             sample_roots = np.concatenate([roots, extra.astype(np.int32)])
         nbr, cnt = g.sample_khop_host(sample_roots, fanouts, base_seed=SAMPLING_SEED, first_call_no=1)
         width, own = 1, []
@@ -245,9 +287,15 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
         stats["rnn"] += n
         if pos is not None:
             order = np.argsort(sample_roots, kind="stable")
-            where = order[np.searchsorted(sample_roots[order], np.where(pos >= 0, pos, sample_roots[0]))]
-            pos_tree = np.where(pos >= 0, where, -1).astype(np.int64)
-            data, offs = sio.encode_samples(sample_roots, fanouts, nbr, x, kind="nablp", n_emit=n, pos=pos, pos_tree=pos_tree, **hyd)
+            sorted_roots = sample_roots[order]
+
+            def tree_of(ids):
+                where = order[np.searchsorted(sorted_roots, np.where(ids >= 0, ids, sorted_roots[0]))]
+                return np.where(ids >= 0, where, -1).astype(np.int64)
+
+            data, offs = sio.encode_link_samples(sample_roots, fanouts, nbr, x, n, pos, tree_of(pos), main_tab, pos_tab, neg,
+                                                 tree_of(neg) if neg is not None else None, neg_tab,
+                                                 condensed_node_type=hyd["condensed_node_type"], condensed_edge_type=hyd["condensed_edge_type"])
             _write(main_dir, part, data)
             stats["nablp"] += int((np.diff(offs) > 0).sum())
 

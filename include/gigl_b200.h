@@ -413,6 +413,33 @@ int gigl_encode_samples_ex_host(int32_t kind, int64_t n_roots, int64_t n_emit, c
                                 const int32_t* pos, const int64_t* pos_tree, int32_t tfrecord_framing, uint8_t** out,
                                 int64_t* out_bytes, int64_t* record_offsets);
 /*
+ * One hydrated edge table as the sample encoder joins against it: the in-CSR by destination (host copies; rows
+ * ascending, duplicates kept), the input record behind every CSR slot (gigl_edge_rows_host; NULL = the slot index) and
+ * the records' feature rows [n_records, n_feat].  rowptr == NULL: every sampled pair matches exactly one feature-less
+ * record.
+ */
+typedef struct gigl_edge_table {
+    const int64_t* rowptr;
+    const int32_t* col;
+    const int32_t* edge_rows;
+    const float* feat;
+    int32_t n_feat;
+} gigl_edge_table;
+/*
+ * NodeAnchorBasedLinkPredictionSample with user-defined labels
+ * (UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:54-581): as kind 2 of gigl_encode_samples_ex_host, but the
+ * positives were sampled from - and pos_edges are hydrated against - pos_edges (NULL = the main table, i.e. sampled
+ * from the graph's own out-edges), and up to num_neg hard negatives per anchor from neg_edges fill hard_neg_edges
+ * (neg / neg_tree laid out like pos / pos_tree; num_neg = 0: none).  An anchor needs a positive; negatives are
+ * optional (LEFT JOIN, :405-430).  The neighbourhood is array_distinct(anchor's ++ positives' ++ negatives').
+ */
+int gigl_encode_link_samples_host(int64_t n_roots, int64_t n_emit, const int32_t* roots, const int32_t* fanouts, int32_t n_hops,
+                                  const int32_t* const* nbr, const float* x, int32_t F, int32_t condensed_node_type,
+                                  int32_t condensed_edge_type, const gigl_edge_table* main_edges, const gigl_edge_table* pos_edges,
+                                  const gigl_edge_table* neg_edges, int32_t num_pos, const int32_t* pos, const int64_t* pos_tree,
+                                  int32_t num_neg, const int32_t* neg, const int64_t* neg_tree, int32_t tfrecord_framing, uint8_t** out,
+                                  int64_t* out_bytes, int64_t* record_offsets);
+/*
  * Splits a TFRecord byte stream into records (payload offsets / lengths, arrays of capacity max_records; pass NULL
  * arrays to only count).  verify != 0 checks both masked crc32c fields.  Returns the record count or GIGL_E_*.
  */

@@ -301,14 +301,19 @@ def np_assemble_rnn(roots, nbr, fanouts, table):
     return out
 
 
-def np_assemble_nablp(roots, nbr, fanouts, table, positives):
-    """{anchor: (sorted distinct edges, sorted node ids, sorted pos_edges)}; `roots` must cover every anchor and every
-    positive.  Anchor = any node with a sampled positive: for nodes with in-edges the merge of
-    NodeAnchorBasedLinkPredictionTask.scala:186-209, for directed source-only nodes formNeighborhoodForSrcOnlyNodes
-    (NodeAnchorBasedLinkPredictionBaseTask.scala:200-278); both reduce to
-    array_distinct(own neighbourhood ++ positives' neighbourhoods) plus the root node."""
+def np_assemble_nablp(roots, nbr, fanouts, table, positives, pos_table=None, negatives=None, neg_table=None):
+    """{anchor: (sorted distinct edges, sorted node ids, sorted pos_edges[, sorted hard_neg_edges])}; `roots` must
+    cover every anchor, positive and negative.  Anchor = any node with a sampled positive: for nodes with in-edges the
+    merge of NodeAnchorBasedLinkPredictionTask.scala:186-209, for directed source-only nodes
+    formNeighborhoodForSrcOnlyNodes (NodeAnchorBasedLinkPredictionBaseTask.scala:200-278); both reduce to
+    array_distinct(own neighbourhood ++ positives' neighbourhoods) plus the root node.
+    User-defined labels (UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:54-581): positives / negatives were
+    sampled from their own edge tables (`pos_table` / `neg_table`, directed, duplicates kept) and are hydrated against
+    them; negatives are LEFT JOINed (an anchor needs a positive only) and their neighbourhoods merge in too; with
+    `negatives` given every value carries a 4th element, the hard_neg_edges."""
     te = tree_to_edges(roots, nbr, fanouts)
     idx = {int(r): i for i, r in enumerate(roots)}
+    pos_table = table if pos_table is None else pos_table
     out = {}
     for u, ps in positives.items():
         if not ps:
@@ -318,9 +323,19 @@ def np_assemble_nablp(roots, nbr, fanouts, table, positives):
             pe, pn = _neighborhood(p_, te[idx[p_]], table)
             e += pe
             n |= pn
-        pos_edges = [(u, p_, f_) for p_ in ps for f_ in table.get((u, p_), [])]  # hydrateTaskBasedEdges :280-334
-        if pos_edges:
+        pos_edges = [(u, p_, f_) for p_ in ps for f_ in pos_table.get((u, p_), [])]  # hydrateTaskBasedEdges :280-334
+        if not pos_edges:
+            continue
+        if negatives is None:
             out[u] = (sorted(set(e)), sorted(n), sorted(pos_edges))
+            continue
+        neg_edges = []
+        for q_ in negatives.get(u, []):
+            qe, qn = _neighborhood(q_, te[idx[q_]], table)
+            e += qe
+            n |= qn
+            neg_edges += [(u, q_, f_) for f_ in neg_table.get((u, q_), [])]
+        out[u] = (sorted(set(e)), sorted(n), sorted(pos_edges), sorted(neg_edges))
     return out
 
 

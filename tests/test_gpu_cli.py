@@ -197,3 +197,48 @@ def test_edge_rows_match_numpy(ctx):
         assert len(rows) == g.n_edges
         assert np.array_equal(rows, np_edge_rows(src, dst, n, directed))
     assert len(ctx.edge_rows_host(5, np.zeros(0, np.int32), np.zeros(0, np.int32), True)) == 0
+
+
+def test_user_defined_labels_component_matches_restated_reference(tmp_path):
+    """UserDefinedLabelsNodeAnchorBasedLinkPredictionTask end to end: positive / negative label edges in their own
+    TFRecord tables (with label-edge features), sampled with permutation calls 3 / 4, hydrated against their tables."""
+    from helpers import tf_example, tfrecord_bytes
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+    from oracle import oracle as O
+
+    n = 40
+    src, dst, x, ef = _nablp_fixture(tmp_path, True)
+    rng = np.random.default_rng(9)
+    psrc, pdst = rng.integers(0, n, 50), rng.integers(0, n, 50)
+    nsrc, ndst = rng.integers(0, n // 2, 30), rng.integers(0, n, 30)
+    pef = rng.standard_normal((50, 1)).astype(np.float32)
+    for sub, (a, b, f) in (("pos_edges", (psrc, pdst, pef)), ("neg_edges", (nsrc, ndst, None))):
+        os.makedirs(tmp_path / sub, exist_ok=True)
+        recs = [tf_example({"src": int(u), "dst": int(v), **({"lw": [float(f[i, 0])]} if f is not None else {})})
+                for i, (u, v) in enumerate(zip(a, b))]
+        (tmp_path / sub / "data.tfrecord").write_bytes(tfrecord_bytes(recs))
+    meta = yaml.safe_load((tmp_path / "preprocessed_metadata.yaml").read_text())
+    em = meta["condensedEdgeTypeToPreprocessedMetadata"]["0"]
+    em["positiveEdgeInfo"] = {"tfrecordUriPrefix": "pos_edges", "featureKeys": ["lw"], "featureDim": 1}
+    em["negativeEdgeInfo"] = {"tfrecordUriPrefix": "neg_edges"}
+    (tmp_path / "preprocessed_metadata.yaml").write_text(yaml.safe_dump(meta))
+    cfg = yaml.safe_load((tmp_path / "frozen_gbml_config.yaml").read_text())
+    cfg["datasetConfig"]["subgraphSamplerConfig"].update({"numUserDefinedPositiveSamples": 2, "numUserDefinedNegativeSamples": 2})
+    (tmp_path / "frozen_gbml_config.yaml").write_text(yaml.safe_dump(cfg))
+    stats = subgraph_sampler.run("frozen_gbml_config.yaml", "udl_job", None, root=str(tmp_path), batch_roots=16, log=lambda *_: None)
+    rowptr, col = O.np_build_in_csr(src, dst, n, True)
+    roots = np.arange(n, dtype=np.int32)
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, [3, 3])
+    p_out, n_out = O.np_build_in_csr(pdst, psrc, n, True), O.np_build_in_csr(ndst, nsrc, n, True)
+    want = O.np_assemble_nablp(roots, nbr, [3, 3], O.np_hydrated_edge_table(src, dst, True, ef),
+                               O.np_sample_positives(p_out[0], p_out[1], roots, 2, call_no=3),
+                               pos_table=O.np_hydrated_edge_table(psrc, pdst, True, pef),
+                               negatives=O.np_sample_positives(n_out[0], n_out[1], roots, 2, call_no=4),
+                               neg_table=O.np_hydrated_edge_table(nsrc, ndst, True, None))
+    main_b = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "output/nablp/samples/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_nablp_sample, sio.split_tfrecords(main_b, verify=True))}
+    assert sorted(got) == sorted(want) and stats["nablp"] == len(want) and stats["rnn"] == n
+    for u, (we, wn, wp, wneg) in want.items():
+        assert _canon(got[u]) == we and sorted(v["node_id"] for v in got[u]["nodes"]) == wn
+        assert _canon(got[u], "pos_edges") == wp and _canon(got[u], "hard_neg_edges") == wneg

@@ -165,3 +165,57 @@ def test_nablp_structure_of_the_reference_fixture_output():
     data, _ = sio.encode_samples(roots, [2, 2], nbr, None, kind="nablp", csr=(rowptr, col), pos=pos, pos_tree=pos.astype(np.int64))
     ours = {sio.parse_nablp_sample(r)["root_node"]["node_id"] for r in sio.split_tfrecords(data)}
     assert ours == {s["root_node"]["node_id"] for s in out["nablp"]}
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_user_defined_labels_assembly_matches_the_restated_sql(directed):
+    """UserDefinedLabelsNodeAnchorBasedLinkPredictionTask: positives / hard negatives come from their own (directed,
+    duplicate-keeping, feature-carrying) edge tables; negatives are optional per anchor."""
+    n, e = 45, 200
+    src, dst = powerlaw_edges(n, e, seed=31)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((n, 2)).astype(np.float32)
+    ef = rng.standard_normal((e, 2)).astype(np.float32)
+    psrc, pdst = rng.integers(0, n, 60), rng.integers(0, n, 60)
+    pdst[:6], psrc[:6] = pdst[6:12], psrc[6:12]  # duplicate label records
+    pef = rng.standard_normal((60, 3)).astype(np.float32)
+    nsrc, ndst = rng.integers(0, n // 2, 40), rng.integers(0, n, 40)  # only some anchors have negatives
+    nef = rng.standard_normal((40, 1)).astype(np.float32)
+    rowptr, col = O.np_build_in_csr(src, dst, n, directed)
+    roots = np.arange(n, dtype=np.int32)
+    fan = [3, 2]
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, fan)
+    num_pos, num_neg = 2, 3
+    # label tables are never bidirectionalised (loadEdgeDataframeIntoSparkSql: only MAIN edges are, :262-273)
+    p_out = O.np_build_in_csr(pdst, psrc, n, True)
+    n_out = O.np_build_in_csr(ndst, nsrc, n, True)
+    positives = O.np_sample_positives(p_out[0], p_out[1], roots, num_pos, call_no=3)
+    negatives = O.np_sample_positives(n_out[0], n_out[1], roots, num_neg, call_no=4)
+    want = O.np_assemble_nablp(roots, nbr, fan, O.np_hydrated_edge_table(src, dst, directed, ef), positives,
+                               pos_table=O.np_hydrated_edge_table(psrc, pdst, True, pef), negatives=negatives,
+                               neg_table=O.np_hydrated_edge_table(nsrc, ndst, True, nef))
+
+    def dense(d, k):
+        a = np.full((n, k), -1, np.int32)
+        for u, vs in d.items():
+            a[u, : len(vs)] = vs
+        return a
+
+    pos, neg = dense(positives, num_pos), dense(negatives, num_neg)
+    main = sio.HostEdgeTable((rowptr, col), np_edge_rows(src, dst, n, directed), ef)
+    ptab = sio.HostEdgeTable(O.np_build_in_csr(psrc, pdst, n, True), np_edge_rows(psrc, pdst, n, True), pef)
+    ntab = sio.HostEdgeTable(O.np_build_in_csr(nsrc, ndst, n, True), np_edge_rows(nsrc, ndst, n, True), nef)
+    data, offs = sio.encode_link_samples(roots, fan, nbr, x, n, pos, pos.astype(np.int64), main, ptab, neg, neg.astype(np.int64), ntab)
+    got = {}
+    for rec in sio.split_tfrecords(data, verify=True):
+        s = sio.parse_nablp_sample(rec)
+        got[s["root_node"]["node_id"]] = s
+    assert sorted(got) == sorted(want) and len(want) > 10
+    with_neg = 0
+    for u, (we, wn, wp, wneg) in want.items():
+        s = got[u]
+        assert _edges(s) == we and sorted(v["node_id"] for v in s["nodes"]) == wn
+        assert _edges(s, "pos_edges") == wp and _edges(s, "hard_neg_edges") == wneg
+        assert all(len(pe["feature_values"]) == 3 for pe in s["pos_edges"]) and s["neg_edges"] == []
+        with_neg += bool(wneg)
+    assert 0 < with_neg < len(want)  # the LEFT JOIN was exercised both ways
