@@ -254,6 +254,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not land on stdout beside the JSON line
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     fan = [int(v) for v in args.fanout.split(",")]
