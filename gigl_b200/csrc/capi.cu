@@ -462,6 +462,72 @@ int gigl_sample_khop_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_root
     return khop_sample_launch(g, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
 }
 
+int gigl_sample_op_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
+                       const int32_t* const* chain_nbr_dev, int32_t base_seed, int32_t call_no, int32_t* nbr_out_dev,
+                       int32_t* cnt_out_dev) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, depth >= 1 && depth <= GIGL_MAX_HOPS && chain_fanouts, "depth must be in [1, 8]");
+    GIGL_CHECK(ctx, (nbr_out_dev && cnt_out_dev) || n_roots == 0, "null output");
+    GIGL_CHECK(ctx, depth == 1 || chain_nbr_dev, "null ancestor levels");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int32_t* nbr[GIGL_MAX_HOPS];
+    int32_t* cnt[GIGL_MAX_HOPS];
+    for (int h = 0; h + 1 < depth; ++h) {
+        GIGL_CHECK(ctx, chain_nbr_dev[h] || n_roots == 0, "null ancestor level");
+        nbr[h] = const_cast<int32_t*>(chain_nbr_dev[h]);  // read only: hops below `depth` are not sampled by this call
+        cnt[h] = cnt_out_dev;                              // never written
+    }
+    nbr[depth - 1] = nbr_out_dev;
+    cnt[depth - 1] = cnt_out_dev;
+    const int32_t first_call_no = (int32_t)((uint32_t)call_no - (uint32_t)(depth - 1));
+    return khop_sample_launch(g, roots_dev, n_roots, chain_fanouts, depth, base_seed, first_call_no, nbr, cnt, depth, depth);
+}
+
+int gigl_sample_op_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
+                        const int32_t* const* chain_nbr, int32_t base_seed, int32_t call_no, int32_t* nbr_out, int32_t* cnt_out) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, depth >= 1 && depth <= GIGL_MAX_HOPS && chain_fanouts, "depth must be in [1, 8]");
+    GIGL_CHECK(ctx, n_roots >= 0 && (roots || n_roots == 0) && ((nbr_out && cnt_out) || n_roots == 0), "bad roots / output");
+    if (n_roots == 0) return GIGL_OK;
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // staging: roots | ancestor levels ... | cnt_out | nbr_out
+    size_t width = 1, total = (size_t)n_roots;
+    size_t off[GIGL_MAX_HOPS + 1];
+    for (int h = 0; h < depth; ++h) {
+        GIGL_CHECK(ctx, chain_fanouts[h] >= 1 && chain_fanouts[h] <= GIGL_MAX_FANOUT, "fanout must be in [1, 128]");
+        if (h + 1 == depth) {
+            off[depth] = total;  // cnt_out: one per parent slot
+            total += (size_t)n_roots * width;
+        }
+        width *= (size_t)chain_fanouts[h];
+        if ((double)n_roots * (double)width > 2147483647.0) return gigl_fail(ctx, GIGL_E_INVALID, "frontier exceeds 2^31-1 slots; split the roots");
+        off[h] = total;
+        total += (size_t)n_roots * width;
+    }
+    void* buf = nullptr;
+    int rc = gigl_scratch(ctx, GIGL_SLOT_IO0, sizeof(int32_t) * total, &buf);
+    if (rc != GIGL_OK) return rc;
+    int32_t* d = (int32_t*)buf;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(d, roots, sizeof(int32_t) * (size_t)n_roots, cudaMemcpyHostToDevice, ctx->stream));
+    const int32_t* chain_dev[GIGL_MAX_HOPS];
+    width = 1;
+    for (int h = 0; h + 1 < depth; ++h) {
+        width *= (size_t)chain_fanouts[h];
+        GIGL_CHECK(ctx, chain_nbr && chain_nbr[h], "null ancestor level");
+        GIGL_CUDA(ctx, cudaMemcpyAsync(d + off[h], chain_nbr[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyHostToDevice, ctx->stream));
+        chain_dev[h] = d + off[h];
+    }
+    const size_t parents = (size_t)n_roots * width;
+    rc = gigl_sample_op_dev(g, d, n_roots, depth, chain_fanouts, chain_dev, base_seed, call_no, d + off[depth - 1], d + off[depth]);
+    if (rc != GIGL_OK) return rc;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(cnt_out, d + off[depth], sizeof(int32_t) * parents, cudaMemcpyDeviceToHost, ctx->stream));
+    GIGL_CUDA(ctx, cudaMemcpyAsync(nbr_out, d + off[depth - 1], sizeof(int32_t) * parents * (size_t)chain_fanouts[depth - 1],
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    return ctx_check_device_error(ctx);
+}
+
 int gigl_sample_khop_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, const int32_t* fanouts,
                           int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr,
                           int32_t* const* cnt) {

@@ -310,6 +310,38 @@ class Graph:
                                                pn, pc), self.ctx.handle)
         return nbr, cnt
 
+    def sample_op(self, roots, chain_fanouts: Sequence[int], chain_nbr: Sequence, call_no: int, base_seed: int = 42):
+        """One SamplingOp over this graph's edge type (gigl_sample_op_dev): expands the frontier `chain_nbr[-1]` (or the
+        roots when the chain is empty).  chain_fanouts = the ancestors' fanouts followed by this op's.  Device tensors in,
+        (nbr, cnt) device tensors out."""
+        import torch
+
+        fan = _np(chain_fanouts, np.int32)
+        depth = len(fan)
+        assert len(chain_nbr) == depth - 1, "one ancestor level per ancestor fanout"
+        n_roots = int(roots.numel())
+        parents = n_roots * int(np.prod(fan[:-1], dtype=np.int64))
+        nbr = torch.empty(parents * int(fan[-1]), dtype=torch.int32, device=roots.device)
+        cnt = torch.empty(parents, dtype=torch.int32, device=roots.device)
+        pn = (C.c_void_p * max(depth - 1, 1))(*[t.data_ptr() for t in chain_nbr])
+        check(self.ctx._L.gigl_sample_op_dev(self.handle, _dp(roots), n_roots, depth, _hp(fan), pn, base_seed, call_no, _dp(nbr), _dp(cnt)),
+              self.ctx.handle)
+        return nbr, cnt
+
+    def sample_op_host(self, roots, chain_fanouts: Sequence[int], chain_nbr: Sequence[np.ndarray], call_no: int, base_seed: int = 42):
+        """Host-buffer form of :meth:`sample_op` (gigl_sample_op_host)."""
+        roots = _np(roots, np.int32)
+        fan = _np(chain_fanouts, np.int32)
+        depth = len(fan)
+        chain = [_np(a, np.int32) for a in chain_nbr]
+        parents = len(roots) * int(np.prod(fan[:-1], dtype=np.int64))
+        nbr = np.full(parents * int(fan[-1]), -1, dtype=np.int32)
+        cnt = np.zeros(parents, dtype=np.int32)
+        pn = (C.c_void_p * max(depth - 1, 1))(*[a.ctypes.data for a in chain])
+        check(self.ctx._L.gigl_sample_op_host(self.handle, _hp(roots), len(roots), depth, _hp(fan), pn, base_seed, call_no, _hp(nbr),
+                                              _hp(cnt)), self.ctx.handle)
+        return nbr, cnt
+
     def sample_positives_host(self, srcs, num_pos: int, base_seed: int = 42, call_no: int = 3):
         srcs = _np(srcs, np.int32)
         pos = np.full(len(srcs) * num_pos, -1, dtype=np.int32)

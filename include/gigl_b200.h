@@ -170,6 +170,25 @@ int gigl_sample_khop_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_root
                          int32_t* const* nbr_dev, int32_t* const* cnt_dev);
 
 /*
+ * One sampling op of a SamplingOpDAG (subgraph_sampling_strategy.proto:38-58; the per-op expansion of
+ * GraphDBSampler.getKHopSubgraphForRootNode, scala_spark35/subgraph_sampler/src/main/scala/libs/sampler/GraphDBSampler.scala:40-148):
+ * expands the frontier its parent op produced (or the roots, depth = 1) over ONE edge type, whose CSR `g` holds - by
+ * destination for an INCOMING op, by source (by_source build) for an OUTGOING one.  The op sits at `depth` in its chain
+ * root -> ... -> op: chain_fanouts[0 .. depth) are the fanouts of its ancestors and its own (last), chain_nbr[0 .. depth-1)
+ * the ancestors' padded-tree outputs (the layout of gigl_sample_khop_*).  Output: nbr_out [n_roots * prod chain_fanouts],
+ * cnt_out [n_roots * prod chain_fanouts[0 .. depth-1)].  Same permutation as gigl_sample_khop_*: key =
+ * XXH64(i + path-id sum + base_seed * call_no), so a linear chain of ops with call_no = 1, 2, ... over one graph equals
+ * gigl_sample_khop_* exactly; a tree-shaped DAG gives every op its own call_no (its 1-based position in the DAG).
+ * The reference's graph-DB samplers have no reproducible sampling (LocalDbClient.scala:186,204 is `Set.take(n)`), so
+ * this is a valid uniform sample, not a bit-level restatement.
+ */
+int gigl_sample_op_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
+                       const int32_t* const* chain_nbr_dev, int32_t base_seed, int32_t call_no, int32_t* nbr_out_dev,
+                       int32_t* cnt_out_dev);
+int gigl_sample_op_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
+                        const int32_t* const* chain_nbr, int32_t base_seed, int32_t call_no, int32_t* nbr_out, int32_t* cnt_out);
+
+/*
  * Positive (out-edge) sampling for node-anchor link prediction: `g_out` is the CSR by SOURCE;
  * for every src u: P(u) = first num_pos of perm(OUT(u), internal_seed = u, call_no) - the NABLP
  * task calls it third, so call_no = 3.  pos: int32[n_srcs * num_pos] (-1 padded), pos_cnt: int32[n_srcs].

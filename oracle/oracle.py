@@ -217,6 +217,47 @@ def np_sample_khop(rowptr, col, roots, fanouts, base_seed=42, first_call_no=1):
     return nbr, cnt
 
 
+def np_sample_chain(csrs, roots, fanouts, call_nos, base_seed=42):
+    """np_sample_khop with a CSR and a permutation call number PER HOP: one root-to-op chain of a SamplingOp DAG
+    (subgraph_sampling_strategy.proto:38-58), hop h expanding over csrs[h] = (rowptr, col) of that op's edge type."""
+    n_roots = len(roots)
+    nbr, cnt = [], []
+    width_prev = 1
+    prev_vals = [int(r) for r in roots]
+    prev_sums = [int(r) for r in roots]
+    for h, f in enumerate(fanouts):
+        f = int(f)
+        rowptr, col = csrs[h]
+        cur_seed = _wrap32(base_seed * _wrap32(call_nos[h]))
+        out = np.full(n_roots * width_prev * f, -1, dtype=np.int32)
+        oc = np.zeros(n_roots * width_prev, dtype=np.int32)
+        sums = [0] * (n_roots * width_prev * f)
+        for ps in range(n_roots * width_prev):
+            v = prev_vals[ps]
+            if v < 0:
+                continue
+            m = 1
+            if h > 0:
+                fp = int(fanouts[h - 1])
+                sib0 = (ps // fp) * fp
+                sib = prev_vals[sib0 : sib0 + fp]
+                if sib.index(v) + sib0 != ps:
+                    continue
+                m = sib.count(v)
+            arr = np.repeat(col[rowptr[v] : rowptr[v + 1]], m)
+            sel = arr[np_perm(len(arr), prev_sums[ps], cur_seed)[:f]]
+            out[ps * f : ps * f + len(sel)] = sel
+            oc[ps] = len(sel)
+            for j, s_ in enumerate(sel):
+                sums[ps * f + j] = _wrap32(prev_sums[ps] + int(s_))
+        nbr.append(out)
+        cnt.append(oc)
+        prev_vals = [int(x) for x in out]
+        prev_sums = sums
+        width_prev *= f
+    return nbr, cnt
+
+
 def tree_to_edges(roots, nbr, fanouts):
     """Padded tree -> per-root list of (src, dst) index pairs, src = hop-k node, dst = hop-(k-1)
     node (SGSPureSparkV1Task.scala:615-629), one pair per sampled slot (explode semantics)."""
