@@ -90,6 +90,7 @@ SIGNATURES = {
                                               i32, pvp, C.POINTER(i64), vp]),
     "gigl_encode_link_samples_host": (C.c_int, [i64, i64, vp, vp, i32, pvp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, pvp,
                                                 C.POINTER(i64), vp]),
+    "gigl_encode_dag_samples_host": (C.c_int, [i64, vp, i32, i32, vp, i32, vp, i32, pvp, C.POINTER(i64), vp]),
     "gigl_tfrecord_index_host": (i64, [vp, i64, i32, vp, vp, i64]),
     "gigl_examples_column_host": (C.c_int, [vp, i64, vp, vp, cp, i32, i32, vp, vp]),
     "gigl_infer_khop_sage_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, pvp, pvp]),
@@ -100,6 +101,17 @@ SIGNATURES = {
 class EdgeTable(C.Structure):
     """gigl_edge_table (include/gigl_b200.h)."""
     _fields_ = [("rowptr", vp), ("col", vp), ("edge_rows", vp), ("feat", vp), ("n_feat", i32)]
+
+
+
+class DagOp(C.Structure):
+    """gigl_dag_op (include/gigl_b200.h)."""
+    _fields_ = [("parent", i32), ("fanout", i32), ("condensed_edge_type", i32), ("result_node_type", i32), ("outgoing", i32), ("nbr", vp)]
+
+
+class NodeTable(C.Structure):
+    """gigl_node_table (include/gigl_b200.h)."""
+    _fields_ = [("x", vp), ("n_feat", i32)]
 
 
 _lib = None

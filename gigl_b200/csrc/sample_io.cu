@@ -569,6 +569,139 @@ int gigl_encode_link_samples_host(int64_t n_roots, int64_t n_emit, const int32_t
                           out_bytes, record_offsets);
 }
 
+// ---- typed (heterogeneous) RootedNodeNeighborhoods from the ops of a SamplingOp DAG -------------------------------
+// GraphDBSampler.getKHopSubgraphForRootNode unions the ops' edge and node SETS and adds the root
+// (scala_spark35/subgraph_sampler/src/main/scala/libs/sampler/GraphDBSampler.scala:129-148); nodes are then hydrated with
+// their type's feature row (SGSTask.hydrateRnn, scala_spark35/.../libs/utils/SGSTask.scala:200-337).
+int gigl_encode_dag_samples_host(int64_t n_roots, const int32_t* roots, int32_t root_node_type, int32_t n_ops, const gigl_dag_op* ops,
+                                 int32_t n_node_types, const gigl_node_table* node_tables, int32_t tfrecord_framing, uint8_t** out,
+                                 int64_t* out_bytes, int64_t* record_offsets) {
+    if (!out || !out_bytes || n_roots < 0 || (n_roots > 0 && !roots) || n_ops < 0 || (n_ops > 0 && !ops) || n_node_types < 0 ||
+        (n_node_types > 0 && !node_tables) || root_node_type < 0)
+        return GIGL_E_INVALID;
+    std::vector<int64_t> width((size_t)n_ops, 1);
+    for (int o = 0; o < n_ops; ++o) {
+        const gigl_dag_op& op = ops[o];
+        if (op.parent >= o || op.parent < -1 || op.fanout < 1 || op.fanout > GIGL_MAX_FANOUT || (n_roots > 0 && !op.nbr) ||
+            op.result_node_type < 0 || op.condensed_edge_type < -1)
+            return GIGL_E_INVALID;  // ops come in topological order
+        width[(size_t)o] = (op.parent < 0 ? 1 : width[(size_t)op.parent]) * op.fanout;
+    }
+    for (int t = 0; t < n_node_types; ++t)
+        if (node_tables[t].n_feat < 0 || (node_tables[t].n_feat > 0 && !node_tables[t].x)) return GIGL_E_INVALID;
+    *out = nullptr;
+    *out_bytes = 0;
+    auto feat_of = [&](int32_t type, uint32_t id, int& F) -> const float* {
+        F = (type < n_node_types) ? node_tables[type].n_feat : 0;
+        return F > 0 ? node_tables[type].x + (size_t)id * F : nullptr;
+    };
+    struct TNode {
+        int32_t type;
+        uint32_t id;
+        bool operator<(const TNode& b) const { return type != b.type ? type < b.type : id < b.id; }
+        bool operator==(const TNode& b) const { return type == b.type && id == b.id; }
+    };
+    struct TEdge {
+        int32_t type;
+        uint32_t src, dst;
+        bool operator<(const TEdge& b) const { return type != b.type ? type < b.type : src != b.src ? src < b.src : dst < b.dst; }
+        bool operator==(const TEdge& b) const { return type == b.type && src == b.src && dst == b.dst; }
+    };
+    std::vector<int64_t> rec((size_t)n_roots + 1, 0);
+    uint8_t* buf = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma omp parallel
+        {
+            std::vector<TNode> nodes;
+            std::vector<TEdge> edges;
+#pragma omp for schedule(dynamic, 256)
+            for (int64_t r = 0; r < n_roots; ++r) {
+                nodes.clear();
+                edges.clear();
+                const uint32_t root = (uint32_t)roots[r];
+                nodes.push_back({root_node_type, root});
+                for (int o = 0; o < n_ops; ++o) {
+                    const gigl_dag_op& op = ops[o];
+                    const int64_t w = width[(size_t)o];
+                    for (int64_t s_ = r * w; s_ < (r + 1) * w; ++s_) {
+                        const int32_t c = op.nbr[s_];
+                        if (c < 0) continue;
+                        const int32_t par = op.parent < 0 ? roots[r] : ops[op.parent].nbr[s_ / op.fanout];
+                        if (par < 0) continue;
+                        nodes.push_back({op.result_node_type, (uint32_t)c});
+                        edges.push_back(op.outgoing ? TEdge{op.condensed_edge_type, (uint32_t)par, (uint32_t)c}
+                                                    : TEdge{op.condensed_edge_type, (uint32_t)c, (uint32_t)par});
+                    }
+                }
+                std::sort(nodes.begin(), nodes.end());
+                nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+                std::sort(edges.begin(), edges.end());
+                edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+                int Fr = 0;
+                const float* xr = feat_of(root_node_type, root, Fr);
+                const size_t root_sz = node_size(root, root_node_type, Fr);
+                size_t graph = 0;
+                for (const TNode& v : nodes) {
+                    int F = 0;
+                    feat_of(v.type, v.id, F);
+                    const size_t ns = node_size(v.id, v.type, F);
+                    graph += 1 + varint_size(ns) + ns;
+                }
+                for (const TEdge& e : edges) {
+                    const size_t es = edge_size(e.src, e.dst, e.type, 0);
+                    graph += 1 + varint_size(es) + es;
+                }
+                const size_t message = 1 + varint_size(root_sz) + root_sz + 1 + varint_size(graph) + graph;
+                if (pass == 0) {
+                    rec[(size_t)r + 1] = (int64_t)message + (tfrecord_framing ? 16 : 0);
+                    continue;
+                }
+                uint8_t* p = buf + rec[(size_t)r];
+                uint8_t* payload = p;
+                if (tfrecord_framing) {
+                    const uint64_t len = message;
+                    memcpy(p, &len, 8);
+                    const uint32_t c = mask_crc(crc32c(p, 8));
+                    memcpy(p + 8, &c, 4);
+                    p += 12;
+                    payload = p;
+                }
+                *p++ = 0x0A;  // root_node = 1
+                p = put_varint(p, root_sz);
+                p = put_node(p, root, root_node_type, xr, Fr);
+                *p++ = 0x12;  // neighborhood = 2 : Graph { nodes = 2, edges = 3 }
+                p = put_varint(p, graph);
+                for (const TNode& v : nodes) {
+                    int F = 0;
+                    const float* xv = feat_of(v.type, v.id, F);
+                    *p++ = 0x12;
+                    p = put_varint(p, node_size(v.id, v.type, F));
+                    p = put_node(p, v.id, v.type, xv, F);
+                }
+                for (const TEdge& e : edges) {
+                    *p++ = 0x1A;
+                    p = put_varint(p, edge_size(e.src, e.dst, e.type, 0));
+                    p = put_edge(p, e.src, e.dst, e.type, nullptr, 0);
+                }
+                if (tfrecord_framing) {
+                    const uint32_t c = mask_crc(crc32c(payload, (size_t)(p - payload)));
+                    memcpy(p, &c, 4);
+                    p += 4;
+                }
+            }
+        }
+        if (pass == 0) {
+            for (int64_t r = 0; r < n_roots; ++r) rec[(size_t)r + 1] += rec[(size_t)r];
+            buf = (uint8_t*)malloc((size_t)(rec[(size_t)n_roots] > 0 ? rec[(size_t)n_roots] : 1));
+            if (!buf) return GIGL_E_NOMEM;
+        }
+    }
+    if (record_offsets) memcpy(record_offsets, rec.data(), sizeof(int64_t) * ((size_t)n_roots + 1));
+    *out = buf;
+    *out_bytes = rec[(size_t)n_roots];
+    return GIGL_OK;
+}
+
 // ---- TFRecord reading + tf.Example decoding ----------------------------------------------------------
 // Splits a TFRecord byte stream into records; verifies both checksums when verify != 0.
 // offsets / lengths: caller arrays of capacity max_records; returns the number of records, or < 0.

@@ -213,6 +213,41 @@ def encode_link_samples(roots, fanouts, nbr, x: Optional[np.ndarray], n_emit: in
     return data, offs
 
 
+def encode_dag_samples(roots, root_node_type: int, ops: Sequence[dict], node_tables: Sequence[Optional[np.ndarray]],
+                       tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
+    """Typed RootedNodeNeighborhood messages from the ops of a SamplingOp DAG (gigl_encode_dag_samples_host).
+    ops (topological order): dicts with parent (index or -1), fanout, condensed_edge_type, result_node_type, outgoing,
+    nbr (the op's padded-tree output).  node_tables[t] = feature matrix of condensed node type t (or None)."""
+    L = _capi.lib()
+    roots = np.ascontiguousarray(roots, dtype=np.int32)
+    keep = []
+    c_ops = (_capi.DagOp * max(len(ops), 1))()
+    for i, o in enumerate(ops):
+        nbr = np.ascontiguousarray(o["nbr"], dtype=np.int32)
+        keep.append(nbr)
+        c_ops[i] = _capi.DagOp(int(o["parent"]), int(o["fanout"]), int(o["condensed_edge_type"]), int(o["result_node_type"]),
+                               int(bool(o.get("outgoing", False))), nbr.ctypes.data)
+    c_tabs = (_capi.NodeTable * max(len(node_tables), 1))()
+    for t, x in enumerate(node_tables):
+        if x is not None and x.size:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            keep.append(x)
+            c_tabs[t] = _capi.NodeTable(x.ctypes.data, x.shape[1])
+        else:
+            c_tabs[t] = _capi.NodeTable(None, 0)
+    out = C.c_void_p()
+    nbytes = C.c_int64()
+    offs = np.zeros(len(roots) + 1, dtype=np.int64)
+    rc = L.gigl_encode_dag_samples_host(len(roots), roots.ctypes.data, int(root_node_type), len(ops), C.addressof(c_ops), len(node_tables),
+                                        C.addressof(c_tabs), int(tfrecord_framing), C.byref(out), C.byref(nbytes), offs.ctypes.data)
+    _check(rc, "gigl_encode_dag_samples_host")
+    try:
+        data = C.string_at(out.value, nbytes.value)
+    finally:
+        L.gigl_free_host(out)
+    return data, offs
+
+
 # ---- a minimal protobuf wire reader (tests, tooling): no generated code needed --------------------
 def _varint(buf: bytes, pos: int) -> Tuple[int, int]:
     v = shift = 0

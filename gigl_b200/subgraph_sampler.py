@@ -25,8 +25,12 @@ User-defined positive / negative label edges (`positiveEdgeInfo` / `negativeEdge
 UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:54-581) are sampled from and hydrated against their own tables
 (`numUserDefinedPositiveSamples` / `numUserDefinedNegativeSamples`; negatives fill `hard_neg_edges`).
 
-Scope (DESIGN.md): homogeneous graphs (one node type, one edge type), local / file:// URIs.  Branching sampling DAGs
-and `gs://` are not implemented and raise.  The reference's default
+Graphs with several node / edge types go through `subgraphSamplingStrategy.messagePassingPaths` (one tree-shaped
+SamplingOp DAG per root node type, INCOMING / OUTGOING ops; `gigl_b200.dag`) and emit typed `RootedNodeNeighborhood`
+TFRecords per node type, as `GraphDBNodeAnchorBasedLinkPredictionTask.scala:100-190` does.
+
+Scope (DESIGN.md): local / file:// URIs.  Sampling ops with several input ops, the typed task's
+NodeAnchorBasedLinkPredictionSample output and `gs://` are not implemented.  The reference's default
 permutation strategy is the unseedable Spark shuffle; this implementation always uses the seeded hash permutation (a
 valid uniform sample; bit-exact to the reference's `permutation_strategy: deterministic`).
 """
@@ -122,7 +126,6 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
     shared = cfg.get("sharedConfig", {})
     meta = _load_yaml(shared["preprocessedMetadataUri"], root)
     sgs = cfg.get("datasetConfig", {}).get("subgraphSamplerConfig", {})
-    fanouts = fanouts_from_config(sgs)
     directed = bool(shared.get("isGraphDirected", False))
     skip_main = bool(shared.get("shouldSkipTraining", False)) and bool(shared.get("shouldSkipModelEvaluation", False))
     max_train = int(sgs.get("numMaxTrainingSamplesToOutput", 0) or 0)
@@ -130,6 +133,9 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
     is_nablp = "nodeAnchorBasedLinkPredictionTaskMetadata" in task_meta
     flat = shared["flattenedGraphMetadata"]
 
+    if len(meta["condensedNodeTypeToPreprocessedMetadata"]) > 1 or len(meta["condensedEdgeTypeToPreprocessedMetadata"]) > 1:
+        return _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0)
+    fanouts = fanouts_from_config(sgs)
     ntype, nmeta = _first(meta["condensedNodeTypeToPreprocessedMetadata"])
     etype, emeta = _first(meta["condensedEdgeTypeToPreprocessedMetadata"])
     # ---- node table: ids, features in featureKeys order, labels
@@ -298,6 +304,91 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
                                                  condensed_node_type=hyd["condensed_node_type"], condensed_edge_type=hyd["condensed_edge_type"])
             _write(main_dir, part, data)
             stats["nablp"] += int((np.diff(offs) > 0).sum())
+
+
+def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> dict:
+    """Several node / edge types: one SamplingOp DAG per root node type (`subgraphSamplingStrategy.messagePassingPaths`, the
+    only strategy the reference's typed path accepts - SubgraphSamplingStrategyWrapper.scala:10-22), one kernel launch per
+    op over that edge type's CSR, typed RootedNodeNeighborhood TFRecords per node type
+    (GraphDBNodeAnchorBasedLinkPredictionTask.scala:100-190).  The NodeAnchorBasedLinkPredictionSample output of the
+    typed task is not emitted."""
+    import torch
+
+    from . import dag
+
+    shared = cfg["sharedConfig"]
+    gm = cfg["graphMetadata"]
+    node_type_of = {int(k): v for k, v in gm["condensedNodeTypeMap"].items()}
+    cnt_of = {v: k for k, v in node_type_of.items()}
+    cet_of = {(e["srcNodeType"], e["relation"], e["dstNodeType"]): int(k) for k, e in gm["condensedEdgeTypeMap"].items()}
+    strat = (sgs.get("subgraphSamplingStrategy") or {}).get("messagePassingPaths")
+    if not strat:
+        raise ValueError("graphs with several node / edge types need subgraphSamplingStrategy.messagePassingPaths")
+    flat = shared["flattenedGraphMetadata"]
+    if "nodeAnchorBasedLinkPredictionOutput" in flat:
+        out_dirs = dict(flat["nodeAnchorBasedLinkPredictionOutput"].get("nodeTypeToRandomNegativeTfrecordUriPrefix") or {})
+    else:
+        sup = cfg["taskMetadata"]["nodeBasedTaskMetadata"]["supervisionNodeTypes"]
+        out_dirs = {sup[0]: flat["supervisedNodeClassificationOutput"]["unlabeledTfrecordUriPrefix"]}
+    # ---- node tables per condensed node type
+    ids, tables, n_max = {}, [None] * (max(node_type_of) + 1), 0
+    for k, nmeta in meta["condensedNodeTypeToPreprocessedMetadata"].items():
+        t = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(nmeta["tfrecordUriPrefix"], root)))
+        nid = t.column(nmeta["nodeIdKey"], "int64").astype(np.int64)
+        feat = _feature_matrix(t, nmeta.get("featureKeys"))
+        ids[int(k)] = np.sort(nid).astype(np.int32)
+        if feat is not None:
+            x = np.zeros((int(nid.max(initial=-1)) + 1, feat.shape[1]), dtype=np.float32)
+            x[nid] = feat
+            tables[int(k)] = x
+        n_max = max(n_max, int(nid.max(initial=-1)) + 1)
+    # ---- edge tables per condensed edge type
+    edges = {}
+    for k, emeta in meta["condensedEdgeTypeToPreprocessedMetadata"].items():
+        t = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(emeta["mainEdgeInfo"]["tfrecordUriPrefix"], root)))
+        es, ed = t.column(emeta["srcNodeIdKey"], "int64"), t.column(emeta["dstNodeIdKey"], "int64")
+        edges[int(k)] = (es.astype(np.int32), ed.astype(np.int32))
+        n_max = max(n_max, int(es.max(initial=-1)) + 1, int(ed.max(initial=-1)) + 1)
+    for tt, x in enumerate(tables):  # ids above a type's own table (seen only as edge endpoints) hydrate as zeros
+        if x is not None and x.shape[0] < n_max:
+            tables[tt] = np.concatenate([x, np.zeros((n_max - x.shape[0], x.shape[1]), np.float32)])
+    log(f"[{job_name}] loaded {len(ids)} node types, {len(edges)} edge types in {time.time() - t0:.2f}s")
+    ctx = Context.on_torch_stream(device)
+    dev = torch.device("cuda", device)
+    graphs = {}
+    stats = {"rnn": 0, "snc": 0, "nablp": 0, "rnn_per_node_type": {}, "n_nodes": n_max}
+    t1 = time.time()
+    for path in strat.get("paths") or []:
+        rtype = path["rootNodeType"]
+        if rtype not in out_dirs:
+            continue
+        ops = dag.ops_from_config(path)
+        planned = dag.plan(ops, rtype)
+        for p in planned:  # CSR per (edge type, direction), built on first use
+            key = (p.op.edge_type, p.op.sampling_direction)
+            if key not in graphs:
+                es, ed = edges[cet_of[p.op.edge_type]]
+                graphs[key] = Graph.from_edges_host(ctx, n_max, es, ed, is_graph_directed=True, by_source=p.op.sampling_direction == dag.OUTGOING)
+        out_dir = _resolve(out_dirs[rtype], root)
+        os.makedirs(out_dir, exist_ok=True)
+        index = {p.op.op_name: i for i, p in enumerate(planned)}
+        roots_all = ids[cnt_of[rtype]]
+        for part, s in enumerate(range(0, len(roots_all), batch_roots)):
+            roots = roots_all[s:s + batch_roots]
+            res = dag.sample_dag(graphs, torch.from_numpy(roots).to(dev), ops, rtype, base_seed=SAMPLING_SEED)
+            ctx.sync()
+            enc = [dict(parent=-1 if p.parent is None else index[p.parent], fanout=p.op.num_nodes_to_sample,
+                        condensed_edge_type=cet_of[p.op.edge_type], result_node_type=cnt_of[p.op.result_node_type],
+                        outgoing=p.op.sampling_direction == dag.OUTGOING, nbr=res[p.op.op_name][0].cpu().numpy()) for p in planned]
+            data, _ = sio.encode_dag_samples(roots, cnt_of[rtype], enc, tables)
+            _write(out_dir, part, data)
+            stats["rnn"] += len(roots)
+            stats["rnn_per_node_type"][rtype] = stats["rnn_per_node_type"].get(rtype, 0) + len(roots)
+    stats["seconds_sample_and_write"] = time.time() - t1
+    stats["seconds_total"] = time.time() - t0
+    log(f"[{job_name}] wrote typed RootedNodeNeighborhood records {stats['rnn_per_node_type']} in {stats['seconds_sample_and_write']:.2f}s "
+        "(typed NodeAnchorBasedLinkPredictionSample output is not emitted)")
+    return stats
 
 
 def main(argv=None) -> int:

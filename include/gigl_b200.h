@@ -459,6 +459,28 @@ int gigl_encode_link_samples_host(int64_t n_roots, int64_t n_emit, const int32_t
                                   int32_t num_neg, const int32_t* neg, const int64_t* neg_tree, int32_t tfrecord_framing, uint8_t** out,
                                   int64_t* out_bytes, int64_t* record_offsets);
 /*
+ * Typed (heterogeneous) RootedNodeNeighborhoods from the ops of a SamplingOp DAG (gigl_sample_op_*): per root the union
+ * of the ops' edge and node SETS plus the root (GraphDBSampler.getKHopSubgraphForRootNode,
+ * scala_spark35/subgraph_sampler/src/main/scala/libs/sampler/GraphDBSampler.scala:129-148), every node carrying its
+ * condensed node type and that type's feature row (SGSTask.hydrateRnn, .../libs/utils/SGSTask.scala:200-337), every
+ * edge its condensed edge type (edge features are not hydrated here).  ops are in topological order (parent < own index).
+ */
+typedef struct gigl_dag_op {
+    int32_t parent;              /* index of the input op, -1 = the op expands the root */
+    int32_t fanout;
+    int32_t condensed_edge_type;
+    int32_t result_node_type;    /* condensed node type of the sampled nodes */
+    int32_t outgoing;            /* 0 = INCOMING: Edge(sampled -> frontier node); 1 = OUTGOING: Edge(frontier node -> sampled) */
+    const int32_t* nbr;          /* the op's padded-tree output (host), n_roots * prod(fanouts along its chain) */
+} gigl_dag_op;
+typedef struct gigl_node_table {
+    const float* x;              /* [n_nodes_of_type, n_feat] (host), NULL with n_feat = 0 */
+    int32_t n_feat;
+} gigl_node_table;
+int gigl_encode_dag_samples_host(int64_t n_roots, const int32_t* roots, int32_t root_node_type, int32_t n_ops, const gigl_dag_op* ops,
+                                 int32_t n_node_types, const gigl_node_table* node_tables /* by condensed node type */,
+                                 int32_t tfrecord_framing, uint8_t** out, int64_t* out_bytes, int64_t* record_offsets);
+/*
  * Splits a TFRecord byte stream into records (payload offsets / lengths, arrays of capacity max_records; pass NULL
  * arrays to only count).  verify != 0 checks both masked crc32c fields.  Returns the record count or GIGL_E_*.
  */

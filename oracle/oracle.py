@@ -380,6 +380,29 @@ def np_assemble_nablp(roots, nbr, fanouts, table, positives, pos_table=None, neg
     return out
 
 
+def np_assemble_dag_rnn(roots, root_node_type, ops):
+    """{root: (sorted distinct typed edges [(edge_type, src, dst)], sorted distinct typed nodes [(node_type, id)])}:
+    the union of the ops' edge / node sets plus the root (GraphDBSampler.scala:129-148).  ops: dicts with parent,
+    fanout, condensed_edge_type, result_node_type, outgoing, nbr (padded tree), in topological order."""
+    out = {}
+    width = []
+    for o in ops:
+        width.append((1 if o["parent"] < 0 else width[o["parent"]]) * int(o["fanout"]))
+    for r, root in enumerate(roots):
+        nodes, edges = {(int(root_node_type), int(root))}, set()
+        for o, w in zip(ops, width):
+            nbr = np.asarray(o["nbr"])
+            for s_ in range(r * w, (r + 1) * w):
+                c = int(nbr[s_])
+                if c < 0:
+                    continue
+                par = int(root) if o["parent"] < 0 else int(np.asarray(ops[o["parent"]]["nbr"])[s_ // int(o["fanout"])])
+                nodes.add((int(o["result_node_type"]), c))
+                edges.add((int(o["condensed_edge_type"]), par, c) if o.get("outgoing") else (int(o["condensed_edge_type"]), c, par))
+        out[int(root)] = (sorted(edges), sorted(nodes))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # aggregate
 # ----------------------------------------------------------------------------------------

@@ -242,3 +242,78 @@ def test_user_defined_labels_component_matches_restated_reference(tmp_path):
     for u, (we, wn, wp, wneg) in want.items():
         assert _canon(got[u]) == we and sorted(v["node_id"] for v in got[u]["nodes"]) == wn
         assert _canon(got[u], "pos_edges") == wp and _canon(got[u], "hard_neg_edges") == wneg
+
+
+def test_typed_component_writes_rnn_per_node_type(tmp_path):
+    """Two node types / two edge types with per-type SamplingOp DAGs (the shape of the reference's heterogeneous fixture,
+    scala/common/src/test/assets/subgraph_sampler/heterogeneous): typed RootedNodeNeighborhood TFRecords per node type."""
+    from helpers import tf_example, tfrecord_bytes
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(17)
+    n_a, n_p = 30, 45  # authors, papers
+    a2p = (rng.integers(0, n_a, 150), rng.integers(0, n_p, 150))
+    p2a = (a2p[1].copy(), a2p[0].copy())
+    xa = rng.standard_normal((n_a, 2)).astype(np.float32)
+    xp = rng.standard_normal((n_p, 3)).astype(np.float32)
+    for sub, recs in (("nodes_author", [tf_example({"node_id": int(i), "f": xa[i].tolist()}) for i in range(n_a)]),
+                      ("nodes_paper", [tf_example({"node_id": int(i), "g": xp[i].tolist()}) for i in range(n_p)]),
+                      ("edges_a2p", [tf_example({"src": int(u), "dst": int(v)}) for u, v in zip(*a2p)]),
+                      ("edges_p2a", [tf_example({"src": int(u), "dst": int(v)}) for u, v in zip(*p2a)])):
+        os.makedirs(tmp_path / sub, exist_ok=True)
+        (tmp_path / sub / "data.tfrecord").write_bytes(tfrecord_bytes(recs))
+    et0 = {"srcNodeType": "author", "relation": "author_to_paper", "dstNodeType": "paper"}
+    et1 = {"srcNodeType": "paper", "relation": "paper_to_author", "dstNodeType": "author"}
+    meta = {"condensedNodeTypeToPreprocessedMetadata": {
+                "0": {"nodeIdKey": "node_id", "featureKeys": ["f"], "tfrecordUriPrefix": "nodes_author"},
+                "1": {"nodeIdKey": "node_id", "featureKeys": ["g"], "tfrecordUriPrefix": "nodes_paper"}},
+            "condensedEdgeTypeToPreprocessedMetadata": {
+                "0": {"srcNodeIdKey": "src", "dstNodeIdKey": "dst", "mainEdgeInfo": {"tfrecordUriPrefix": "edges_a2p"}},
+                "1": {"srcNodeIdKey": "src", "dstNodeIdKey": "dst", "mainEdgeInfo": {"tfrecordUriPrefix": "edges_p2a"}}}}
+    paths = [{"rootNodeType": "paper", "samplingOps": [
+                 {"opName": "writers", "edgeType": et0, "randomUniform": {"numNodesToSample": 3}},
+                 {"opName": "their_papers", "edgeType": et1, "inputOpNames": ["writers"], "randomUniform": {"numNodesToSample": 2}}]},
+             {"rootNodeType": "author", "samplingOps": [
+                 {"opName": "papers", "edgeType": et1, "randomUniform": {"numNodesToSample": 2}},
+                 {"opName": "written", "edgeType": et0, "randomUniform": {"numNodesToSample": 2}, "samplingDirection": "OUTGOING"}]}]
+    cfg = {"graphMetadata": {"condensedEdgeTypeMap": {"0": et0, "1": et1}, "condensedNodeTypeMap": {"0": "author", "1": "paper"},
+                             "edgeTypes": [et0, et1], "nodeTypes": ["author", "paper"]},
+           "taskMetadata": {"nodeAnchorBasedLinkPredictionTaskMetadata": {"supervisionEdgeTypes": [et1]}},
+           "datasetConfig": {"subgraphSamplerConfig": {"numPositiveSamples": 1, "subgraphSamplingStrategy": {"messagePassingPaths": {"paths": paths}}}},
+           "sharedConfig": {"isGraphDirected": True, "preprocessedMetadataUri": "preprocessed_metadata.yaml",
+                            "flattenedGraphMetadata": {"nodeAnchorBasedLinkPredictionOutput": {
+                                "tfrecordUriPrefix": "out/nablp/",
+                                "nodeTypeToRandomNegativeTfrecordUriPrefix": {"author": "out/rnn/author/", "paper": "out/rnn/paper/"}}}}}
+    (tmp_path / "preprocessed_metadata.yaml").write_text(yaml.safe_dump(meta))
+    (tmp_path / "frozen_gbml_config.yaml").write_text(yaml.safe_dump(cfg))
+    stats = subgraph_sampler.run("frozen_gbml_config.yaml", "typed_job", None, root=str(tmp_path), batch_roots=20, log=lambda *_: None)
+    assert stats["rnn_per_node_type"] == {"paper": n_p, "author": n_a}
+    n = max(n_a, n_p)
+    inc = lambda e: O.np_build_in_csr(e[0], e[1], n, True)  # noqa: E731
+    outg = lambda e: O.np_build_in_csr(e[1], e[0], n, True)  # noqa: E731
+    # paper roots: writers <- author_to_paper (call 1), their_papers <- paper_to_author (call 2)
+    roots = np.arange(n_p, dtype=np.int32)
+    ch, _ = O.np_sample_chain([inc(a2p), inc(p2a)], roots, [3, 2], [1, 2])
+    want = O.np_assemble_dag_rnn(roots, 1, [dict(parent=-1, fanout=3, condensed_edge_type=0, result_node_type=0, nbr=ch[0]),
+                                            dict(parent=0, fanout=2, condensed_edge_type=1, result_node_type=1, nbr=ch[1])])
+    raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "out/rnn/paper/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_sample, sio.split_tfrecords(raw, verify=True))}
+    assert sorted(got) == list(range(n_p))
+    for r in range(n_p):
+        assert sorted((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"]) for e in got[r]["edges"]) == want[r][0]
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == want[r][1]
+        for v in got[r]["nodes"]:
+            assert np.array_equal(np.float32(v["feature_values"]), (xa if v["condensed_node_type"] == 0 else xp)[v["node_id"]])
+    # author roots: papers <- paper_to_author (call 1), written -> author_to_paper OUTGOING (call 2)
+    roots = np.arange(n_a, dtype=np.int32)
+    c1, _ = O.np_sample_chain([inc(p2a)], roots, [2], [1])
+    c2, _ = O.np_sample_chain([outg(a2p)], roots, [2], [2])
+    want = O.np_assemble_dag_rnn(roots, 0, [dict(parent=-1, fanout=2, condensed_edge_type=1, result_node_type=1, nbr=c1[0]),
+                                            dict(parent=-1, fanout=2, condensed_edge_type=0, result_node_type=1, outgoing=True, nbr=c2[0])])
+    raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "out/rnn/author/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_sample, sio.split_tfrecords(raw, verify=True))}
+    for r in range(n_a):
+        assert sorted((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"]) for e in got[r]["edges"]) == want[r][0]
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == want[r][1]

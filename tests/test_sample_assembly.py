@@ -219,3 +219,46 @@ def test_user_defined_labels_assembly_matches_the_restated_sql(directed):
         assert all(len(pe["feature_values"]) == 3 for pe in s["pos_edges"]) and s["neg_edges"] == []
         with_neg += bool(wneg)
     assert 0 < with_neg < len(want)  # the LEFT JOIN was exercised both ways
+
+
+def test_typed_rnn_from_a_sampling_op_dag_matches_the_restated_union():
+    """Heterogeneous RootedNodeNeighborhoods: union of the ops' typed edge / node sets + the root, nodes hydrated with
+    their own type's features (GraphDBSampler.scala:129-148, SGSTask.hydrateRnn)."""
+    rng = np.random.default_rng(21)
+    n_user, n_item, n = 40, 25, 40
+    follows = (rng.integers(0, n_user, 250), rng.integers(0, n_user, 250))     # user -> user, condensed edge type 0
+    shown = (rng.integers(0, n_item, 200), rng.integers(0, n_user, 200))       # item -> user, 1
+    clicks = (rng.integers(0, n_user, 220), rng.integers(0, n_item, 220))      # user -> item, 2
+    inc = lambda e: O.np_build_in_csr(e[0], e[1], n, True)  # noqa: E731
+    outg = lambda e: O.np_build_in_csr(e[1], e[0], n, True)  # noqa: E731
+    roots = np.arange(n_user, dtype=np.int32)
+    # ops: friends (users <- follows), seen (items shown to the user), clickers (users who clicked a seen item),
+    #      their_clicks (items the friends clicked, OUTGOING over clicks)
+    friends, _ = O.np_sample_chain([inc(follows)], roots, [3], [1])
+    seen, _ = O.np_sample_chain([inc(shown)], roots, [2], [2])
+    clickers, _ = O.np_sample_chain([inc(shown), inc(clicks)], roots, [2, 2], [2, 3])
+    their, _ = O.np_sample_chain([inc(follows), outg(clicks)], roots, [3, 2], [1, 4])
+    ops = [dict(parent=-1, fanout=3, condensed_edge_type=0, result_node_type=0, nbr=friends[0]),
+           dict(parent=-1, fanout=2, condensed_edge_type=1, result_node_type=1, nbr=seen[0]),
+           dict(parent=1, fanout=2, condensed_edge_type=2, result_node_type=0, nbr=clickers[1]),
+           dict(parent=0, fanout=2, condensed_edge_type=2, result_node_type=1, outgoing=True, nbr=their[1])]
+    xu = rng.standard_normal((n_user, 3)).astype(np.float32)
+    xi = rng.standard_normal((n_item, 5)).astype(np.float32)
+    want = O.np_assemble_dag_rnn(roots, 0, ops)
+    data, offs = sio.encode_dag_samples(roots, 0, ops, [xu, xi])
+    recs = sio.split_tfrecords(data, verify=True)
+    assert len(recs) == n_user and offs[-1] == len(data)
+    n_out_edges = 0
+    for r, rec in zip(roots, recs):
+        s = sio.parse_sample(rec)
+        assert s["root_node"]["node_id"] == r and s["root_node"]["condensed_node_type"] == 0
+        assert np.array_equal(np.float32(s["root_node"]["feature_values"]), xu[r])
+        we, wn = want[int(r)]
+        assert sorted((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"]) for e in s["edges"]) == we
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in s["nodes"]) == wn
+        for v in s["nodes"]:
+            tab = xu if v["condensed_node_type"] == 0 else xi
+            assert np.array_equal(np.float32(v["feature_values"]), tab[v["node_id"]])
+        # an OUTGOING op's edges point away from the frontier: user (friend) -> item over `clicks`
+        n_out_edges += sum(1 for t, a, b in we if t == 2 and (0, a) in wn and (1, b) in wn)
+    assert n_out_edges > 0
