@@ -33,6 +33,7 @@ UNIT = "subgraphs/s"
 WORKLOADS = {
     # name: nodes, input edge records (undirected pairs unless directed), F, hidden, out, BASELINE.json config it mirrors
     "products-like": dict(nodes=2_449_029, pairs=61_859_140, F=100, H=256, O=47, directed=False, cfg="configs[1]"),
+    "products-like-f128": dict(nodes=2_449_029, pairs=61_859_140, F=128, H=256, O=47, directed=False, cfg="configs[1] (F = 128 variant)"),
     "toy-1k": dict(nodes=1_000, pairs=5_000, F=16, H=16, O=7, directed=False, cfg="configs[0]"),
     # N = 1e8, E = 1e9 directed RMAT, F = 128; every GPU holds the whole CSR (4.8 GB) + features (51 GB)
     "g1b": dict(nodes=100_000_000, pairs=1_000_000_000, F=128, H=128, O=128, directed=True, cfg="configs[3]"),
@@ -229,7 +230,8 @@ def workload_config(args, wl, fan, batch, note):
     residency = ("whole CSR + feature table resident in HBM on every GPU (replicated); roots sharded by contiguous id range"
                  if not getattr(args, "shard_features", False) else
                  "CSR replicated; feature table sharded by contiguous node range over the GPUs and mapped as one flat array "
-                 "(cuMemMap of peer shards): remote neighbour rows are loaded over NVLink inside the gather kernel")
+                 "(cuMemMap of peer shards, rows pitched to 128-byte multiples): remote neighbour rows are loaded over NVLink "
+                 "inside the gather kernel")
     edges = (f"{wl['pairs']} directed edges (duplicates kept)" if wl["directed"] else
              f"{wl['pairs']} undirected pairs de-duplicated+mirrored")
     return {"workload": f"BASELINE.json {wl['cfg']} shape: {args.workload} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
@@ -269,13 +271,15 @@ def run_ours(args):
     if args.shard_features:
         from gigl_b200.sharding import ShardedFeatureTable
 
-        table = ShardedFeatureTable(ctx, wl["nodes"], wl["F"], rank, world, tag=os.environ.get("MASTER_PORT", "0"))
-        table.local[: table.row_hi - table.row_lo].copy_(x[table.row_lo:table.row_hi])  # this rank keeps only its rows
+        # rows pitched to whole 128-byte lines: remote rows cross NVLink as full lines (2x the link efficiency at F = 100)
+        pitch = -(-wl["F"] // 32) * 32
+        table = ShardedFeatureTable(ctx, wl["nodes"], pitch, rank, world, tag=os.environ.get("MASTER_PORT", "0"))
+        table.local[: table.row_hi - table.row_lo, : wl["F"]].copy_(x[table.row_lo:table.row_hi])  # this rank keeps only its rows
         del x
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        x = table.table[: wl["nodes"]]
+        x = table.table[: wl["nodes"], : wl["F"]]
     g.set_features(x)
     model = SageModel(ctx, layers)
     batch = Batch(ctx, wl["nodes"])
@@ -357,7 +361,7 @@ def run_ours(args):
     # ---- the aggregate over the WHOLE graph (every node a row, every CSR edge reduced once): the full-graph form the
     # Trainer's nn modules and layer-wise inference use; reported beside the batch numbers, outside the timed step
     full = None
-    if not args.no_full_graph:
+    if not args.no_full_graph and not args.shard_features:
         rowptr_t, col_t = g.csr_tensors()
         agg = torch.empty((wl["nodes"], F), dtype=torch.float32, device=dev)
         ctx.gather_mean(x, rowptr_t, col_t, out=agg)

@@ -68,6 +68,7 @@ SIGNATURES = {
     "gigl_linear_tn_dev": (C.c_int, [vp, i64, i32, i32, vp, i64, vp, i64, vp, i64, i32]),
     "gigl_graph_set_features_host": (C.c_int, [vp, vp, i32]),
     "gigl_graph_set_features_dev": (C.c_int, [vp, vp, i32]),
+    "gigl_graph_set_features_pitched_dev": (C.c_int, [vp, vp, i32, i64]),
     "gigl_graph_features_dev": (C.c_int, [vp, pvp, C.POINTER(i32)]),
     "gigl_shared_table_row_granule": (C.c_int, [vp, i32, C.POINTER(i64)]),
     "gigl_shared_table_create": (C.c_int, [vp, i32, i32, i64, i32, pvp, C.POINTER(i32)]),

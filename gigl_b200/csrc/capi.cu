@@ -679,16 +679,20 @@ int gigl_graph_set_features_host(gigl_graph* g, const float* x, int32_t F) {
     }
     g->x = d;
     g->F = F;
+    g->ldx = F;
     g->x_owned = true;
     return GIGL_OK;
 }
 
-int gigl_graph_set_features_dev(gigl_graph* g, const float* x_dev, int32_t F) {
+int gigl_graph_set_features_dev(gigl_graph* g, const float* x_dev, int32_t F) { return gigl_graph_set_features_pitched_dev(g, x_dev, F, F); }
+
+int gigl_graph_set_features_pitched_dev(gigl_graph* g, const float* x_dev, int32_t F, int64_t row_pitch) {
     if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
-    GIGL_CHECK(g->ctx, F >= 1 && x_dev != nullptr, "bad feature table");
+    GIGL_CHECK(g->ctx, F >= 1 && x_dev != nullptr && row_pitch >= F, "bad feature table");
     graph_drop_features(g);
     g->x = x_dev;
     g->F = F;
+    g->ldx = row_pitch;
     g->x_owned = false;
     return GIGL_OK;
 }
@@ -891,7 +895,7 @@ int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_mode
         }
         if (dbg) cudaEventRecord(ev[3], ctx->copy_stream);
     }
-    rc = batch_sage_forward(b, m, g->x, g->F, (float*)pout);
+    rc = batch_sage_forward(b, m, g->x, g->ldx, (float*)pout);
     if (rc != GIGL_OK) {
         if (copying) cudaStreamSynchronize(ctx->copy_stream);  // nothing may still be writing the caller's buffers
         return rc;

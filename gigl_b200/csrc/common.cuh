@@ -82,8 +82,9 @@ struct gigl_graph {
     const int64_t* rowptr = nullptr;  // device
     const int32_t* col = nullptr;     // device
     bool owned = false;
-    const float* x = nullptr;  // device feature table [n_nodes, F] (optional)
+    const float* x = nullptr;  // device feature table [n_nodes, F] (optional), row pitch ldx floats
     int32_t F = 0;
+    int64_t ldx = 0;
     bool x_owned = false;
     // hash-window index of the sampler (khop_sample.cu), built lazily on the first sampling call
     uint64_t* hx_keys = nullptr;

@@ -359,9 +359,9 @@ class Graph:
         self.F = x.shape[1]
 
     def set_features(self, x) -> None:
-        """Wrap a [n_nodes, F] fp32 CUDA tensor (kept alive by this object)."""
-        assert x.is_cuda and x.dim() == 2 and x.shape[0] == self.n_nodes and x.is_contiguous()
-        check(self.ctx._L.gigl_graph_set_features_dev(self.handle, _dp(x), x.shape[1]), self.ctx.handle)
+        """Wrap a [n_nodes, F] fp32 CUDA tensor (kept alive by this object); rows may be pitched (x.stride(0) >= F)."""
+        assert x.is_cuda and x.dim() == 2 and x.shape[0] == self.n_nodes and x.stride(1) == 1 and x.stride(0) >= x.shape[1]
+        check(self.ctx._L.gigl_graph_set_features_pitched_dev(self.handle, C.c_void_p(x.data_ptr()), x.shape[1], x.stride(0)), self.ctx.handle)
         self._x = x
         self.F = x.shape[1]
 
