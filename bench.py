@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-graph", action="store_true")
+    ap.add_argument("--pitch-features", action="store_true", help="experiment: replicated feature rows pitched to 128-byte multiples")
     ap.add_argument("--shard-features", action="store_true",
                     help="features sharded by node range over the N GPUs and mapped as one flat table (remote rows over NVLink) "
                          "instead of replicated")
@@ -256,7 +257,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not land on stdout beside the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL's banner must not land on stdout beside the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     fan = [int(v) for v in args.fanout.split(",")]
@@ -280,6 +282,10 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         x = table.table[: wl["nodes"], : wl["F"]]
+    if args.pitch_features and not args.shard_features:
+        xp = torch.zeros((wl["nodes"], -(-wl["F"] // 32) * 32), dtype=torch.float32, device=dev)
+        xp[:, : wl["F"]] = x
+        x = xp[:, : wl["F"]]
     g.set_features(x)
     model = SageModel(ctx, layers)
     batch = Batch(ctx, wl["nodes"])
