@@ -92,6 +92,7 @@ SIGNATURES = {
     "gigl_encode_link_samples_host": (C.c_int, [i64, i64, vp, vp, i32, pvp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, pvp,
                                                 C.POINTER(i64), vp]),
     "gigl_encode_dag_samples_host": (C.c_int, [i64, vp, i32, i32, vp, i32, vp, i32, pvp, C.POINTER(i64), vp]),
+    "gigl_encode_typed_samples_host": (C.c_int, [i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, vp, i32, pvp, C.POINTER(i64), vp]),
     "gigl_tfrecord_index_host": (i64, [vp, i64, i32, vp, vp, i64]),
     "gigl_examples_column_host": (C.c_int, [vp, i64, vp, vp, cp, i32, i32, vp, vp]),
     "gigl_infer_khop_sage_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, pvp, pvp]),
@@ -113,6 +114,11 @@ class DagOp(C.Structure):
 class NodeTable(C.Structure):
     """gigl_node_table (include/gigl_b200.h)."""
     _fields_ = [("x", vp), ("n_feat", i32)]
+
+
+class DagTree(C.Structure):
+    """gigl_dag_tree (include/gigl_b200.h)."""
+    _fields_ = [("n_roots", i64), ("roots", vp), ("root_node_type", i32), ("n_ops", i32), ("ops", vp)]
 
 
 _lib = None

@@ -569,89 +569,186 @@ int gigl_encode_link_samples_host(int64_t n_roots, int64_t n_emit, const int32_t
                           out_bytes, record_offsets);
 }
 
-// ---- typed (heterogeneous) RootedNodeNeighborhoods from the ops of a SamplingOp DAG -------------------------------
+}  // extern "C"
+
+// ---- typed (heterogeneous) samples from the ops of a SamplingOp DAG -------------------------------------------------
 // GraphDBSampler.getKHopSubgraphForRootNode unions the ops' edge and node SETS and adds the root
 // (scala_spark35/subgraph_sampler/src/main/scala/libs/sampler/GraphDBSampler.scala:129-148); nodes are then hydrated with
-// their type's feature row (SGSTask.hydrateRnn, scala_spark35/.../libs/utils/SGSTask.scala:200-337).
-int gigl_encode_dag_samples_host(int64_t n_roots, const int32_t* roots, int32_t root_node_type, int32_t n_ops, const gigl_dag_op* ops,
-                                 int32_t n_node_types, const gigl_node_table* node_tables, int32_t tfrecord_framing, uint8_t** out,
-                                 int64_t* out_bytes, int64_t* record_offsets) {
-    if (!out || !out_bytes || n_roots < 0 || (n_roots > 0 && !roots) || n_ops < 0 || (n_ops > 0 && !ops) || n_node_types < 0 ||
-        (n_node_types > 0 && !node_tables) || root_node_type < 0)
-        return GIGL_E_INVALID;
-    std::vector<int64_t> width((size_t)n_ops, 1);
-    for (int o = 0; o < n_ops; ++o) {
-        const gigl_dag_op& op = ops[o];
-        if (op.parent >= o || op.parent < -1 || op.fanout < 1 || op.fanout > GIGL_MAX_FANOUT || (n_roots > 0 && !op.nbr) ||
+// their type's feature row and - when an edge type of the DAG carries features - edges LEFT JOIN the hydrated edge table
+// on (_from, _to, _condensed_edge_type) (SGSTask.hydrateRnn, scala_spark35/.../libs/utils/SGSTask.scala:200-337).  The
+// typed task's main sample merges the anchor's neighbourhood with its positives' by key
+// (GraphDBNodeAnchorBasedLinkPredictionTask.scala:283-470, GraphPbWrappers.mergeGraphs :43-68).
+namespace {
+
+struct TNode {
+    int32_t type;
+    uint32_t id;
+    bool operator<(const TNode& b) const { return type != b.type ? type < b.type : id < b.id; }
+    bool operator==(const TNode& b) const { return type == b.type && id == b.id; }
+};
+struct TEdge {
+    int32_t type;
+    uint32_t src, dst;
+    int64_t row;  // feature row of the type's edge table, -1 = none
+    bool operator<(const TEdge& b) const {
+        return type != b.type ? type < b.type : src != b.src ? src < b.src : dst != b.dst ? dst < b.dst : row < b.row;
+    }
+    bool same_key(const TEdge& b) const { return type == b.type && src == b.src && dst == b.dst; }
+};
+
+struct TypedCtx {
+    int32_t n_node_types;
+    const gigl_node_table* node_tables;
+    int32_t n_edge_types;
+    const gigl_edge_table* edge_tables;  // nullptr: edges pass through un-hydrated
+
+    const float* node_feat(int32_t type, uint32_t id, int& F) const {
+        F = (type >= 0 && type < n_node_types) ? node_tables[type].n_feat : 0;
+        return F > 0 ? node_tables[type].x + (size_t)id * F : nullptr;
+    }
+    const gigl_edge_table* etab(int32_t type) const {
+        return (edge_tables && type >= 0 && type < n_edge_types && edge_tables[type].rowptr) ? &edge_tables[type] : nullptr;
+    }
+    int edge_feat_len(const TEdge& e) const {
+        const gigl_edge_table* t = etab(e.type);
+        return (t && t->n_feat > 0 && e.row >= 0) ? t->n_feat : 0;
+    }
+    const float* edge_feat(const TEdge& e) const {
+        const int Fe = edge_feat_len(e);
+        return Fe ? edge_tables[e.type].feat + (size_t)e.row * Fe : nullptr;
+    }
+    // LEFT JOIN of one (type, src, dst) key with the type's edge records: one Edge per matching record (all_records), or
+    // the first one only (the by-key merge of mergeGraphs); a key without a record / without a table stays feature-less.
+    void hydrate(bool enabled, const TEdge& key, bool all_records, std::vector<TEdge>& out) const {
+        const gigl_edge_table* t = enabled ? etab(key.type) : nullptr;
+        if (!t) {
+            out.push_back({key.type, key.src, key.dst, -1});
+            return;
+        }
+        const int32_t* b = t->col + t->rowptr[key.dst];
+        const int32_t* en = t->col + t->rowptr[key.dst + 1];
+        auto r = std::equal_range(b, en, (int32_t)key.src);
+        if (r.first == r.second) {
+            out.push_back({key.type, key.src, key.dst, -1});
+            return;
+        }
+        for (const int32_t* q = r.first; q != r.second; ++q) {
+            const int64_t slot = q - t->col;
+            out.push_back({key.type, key.src, key.dst, t->n_feat > 0 ? (t->edge_rows ? (int64_t)t->edge_rows[slot] : slot) : -1});
+            if (!all_records) break;
+        }
+    }
+};
+
+bool dag_tree_ok(const gigl_dag_tree* t, std::vector<int64_t>& width) {
+    if (!t || t->n_roots < 0 || (t->n_roots > 0 && !t->roots) || t->n_ops < 0 || (t->n_ops > 0 && !t->ops) || t->root_node_type < 0) return false;
+    width.assign((size_t)t->n_ops, 1);
+    for (int o = 0; o < t->n_ops; ++o) {
+        const gigl_dag_op& op = t->ops[o];
+        if (op.parent >= o || op.parent < -1 || op.fanout < 1 || op.fanout > GIGL_MAX_FANOUT || (t->n_roots > 0 && !op.nbr) ||
             op.result_node_type < 0 || op.condensed_edge_type < -1)
-            return GIGL_E_INVALID;  // ops come in topological order
+            return false;  // ops come in topological order
         width[(size_t)o] = (op.parent < 0 ? 1 : width[(size_t)op.parent]) * op.fanout;
     }
-    for (int t = 0; t < n_node_types; ++t)
-        if (node_tables[t].n_feat < 0 || (node_tables[t].n_feat > 0 && !node_tables[t].x)) return GIGL_E_INVALID;
+    return true;
+}
+
+// appends the (non-distinct) typed nodes and edge keys of root r's sampled DAG, the root included
+void walk_dag(const gigl_dag_tree& t, const std::vector<int64_t>& width, int64_t r, std::vector<TNode>& nodes, std::vector<TEdge>& edges) {
+    nodes.push_back({t.root_node_type, (uint32_t)t.roots[r]});
+    for (int o = 0; o < t.n_ops; ++o) {
+        const gigl_dag_op& op = t.ops[o];
+        const int64_t w = width[(size_t)o];
+        for (int64_t s_ = r * w; s_ < (r + 1) * w; ++s_) {
+            const int32_t c = op.nbr[s_];
+            if (c < 0) continue;
+            const int32_t par = op.parent < 0 ? t.roots[r] : t.ops[op.parent].nbr[s_ / op.fanout];
+            if (par < 0) continue;
+            nodes.push_back({op.result_node_type, (uint32_t)c});
+            edges.push_back(op.outgoing ? TEdge{op.condensed_edge_type, (uint32_t)par, (uint32_t)c, -1}
+                                        : TEdge{op.condensed_edge_type, (uint32_t)c, (uint32_t)par, -1});
+        }
+    }
+}
+
+template <class T>
+void sort_unique(std::vector<T>& v) {
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end(), [](const T& a, const T& b) { return !(a < b) && !(b < a); }), v.end());
+}
+
+int encode_typed(int32_t kind, const gigl_dag_tree* anchors, const gigl_dag_tree* targets, int32_t num_pos, const int32_t* pos,
+                 const int64_t* pos_tree, int32_t pos_edge_type, int32_t include_isolated, int32_t hydrate_flags, const TypedCtx& tc,
+                 int32_t tfrecord_framing, uint8_t** out, int64_t* out_bytes, int64_t* record_offsets) {
+    std::vector<int64_t> aw, tw;
+    if (!out || !out_bytes || !dag_tree_ok(anchors, aw) || (kind != 0 && kind != 2)) return GIGL_E_INVALID;
+    if (kind == 2 && (num_pos < 0 || (num_pos > 0 && anchors->n_roots > 0 && (!pos || !pos_tree)) || !dag_tree_ok(targets, tw)))
+        return GIGL_E_INVALID;
+    const int64_t n_roots = anchors->n_roots;
+    if (kind == 2)
+        for (int64_t i = 0; i < n_roots * num_pos; ++i)
+            if (pos[i] >= 0 && (pos_tree[i] < -1 || pos_tree[i] >= targets->n_roots || (pos_tree[i] >= 0 && targets->roots[pos_tree[i]] != pos[i])))
+                return GIGL_E_INVALID;
     *out = nullptr;
     *out_bytes = 0;
-    auto feat_of = [&](int32_t type, uint32_t id, int& F) -> const float* {
-        F = (type < n_node_types) ? node_tables[type].n_feat : 0;
-        return F > 0 ? node_tables[type].x + (size_t)id * F : nullptr;
-    };
-    struct TNode {
-        int32_t type;
-        uint32_t id;
-        bool operator<(const TNode& b) const { return type != b.type ? type < b.type : id < b.id; }
-        bool operator==(const TNode& b) const { return type == b.type && id == b.id; }
-    };
-    struct TEdge {
-        int32_t type;
-        uint32_t src, dst;
-        bool operator<(const TEdge& b) const { return type != b.type ? type < b.type : src != b.src ? src < b.src : dst < b.dst; }
-        bool operator==(const TEdge& b) const { return type == b.type && src == b.src && dst == b.dst; }
-    };
+    const bool hyd_graph = hydrate_flags & 1, hyd_pos = hydrate_flags & 2;
     std::vector<int64_t> rec((size_t)n_roots + 1, 0);
     uint8_t* buf = nullptr;
     for (int pass = 0; pass < 2; ++pass) {
 #pragma omp parallel
         {
             std::vector<TNode> nodes;
-            std::vector<TEdge> edges;
+            std::vector<TEdge> keys, edges, pos_keys, pos_edges;
 #pragma omp for schedule(dynamic, 256)
             for (int64_t r = 0; r < n_roots; ++r) {
+                if (pass == 1 && rec[(size_t)r + 1] == rec[(size_t)r]) continue;
                 nodes.clear();
+                keys.clear();
                 edges.clear();
-                const uint32_t root = (uint32_t)roots[r];
-                nodes.push_back({root_node_type, root});
-                for (int o = 0; o < n_ops; ++o) {
-                    const gigl_dag_op& op = ops[o];
-                    const int64_t w = width[(size_t)o];
-                    for (int64_t s_ = r * w; s_ < (r + 1) * w; ++s_) {
-                        const int32_t c = op.nbr[s_];
-                        if (c < 0) continue;
-                        const int32_t par = op.parent < 0 ? roots[r] : ops[op.parent].nbr[s_ / op.fanout];
-                        if (par < 0) continue;
-                        nodes.push_back({op.result_node_type, (uint32_t)c});
-                        edges.push_back(op.outgoing ? TEdge{op.condensed_edge_type, (uint32_t)par, (uint32_t)c}
-                                                    : TEdge{op.condensed_edge_type, (uint32_t)c, (uint32_t)par});
-                    }
+                pos_keys.clear();
+                pos_edges.clear();
+                const uint32_t root = (uint32_t)anchors->roots[r];
+                const int32_t rtype = anchors->root_node_type;
+                if (kind == 2) {
+                    for (int j = 0; j < num_pos; ++j)
+                        if (pos[r * num_pos + j] >= 0) pos_keys.push_back({pos_edge_type, root, (uint32_t)pos[r * num_pos + j], -1});
+                    if (pos_keys.empty() && !include_isolated) continue;  // INNER JOIN with the positives (:404-420)
                 }
-                std::sort(nodes.begin(), nodes.end());
-                nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
-                std::sort(edges.begin(), edges.end());
-                edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+                walk_dag(*anchors, aw, r, nodes, keys);
+                if (kind == 2) {
+                    for (int j = 0; j < num_pos; ++j) {
+                        const int32_t pnode = pos[r * num_pos + j];
+                        if (pnode < 0) continue;
+                        const int64_t tr = pos_tree[r * num_pos + j];
+                        if (tr >= 0) walk_dag(*targets, tw, tr, nodes, keys);
+                        else nodes.push_back({targets->root_node_type, (uint32_t)pnode});
+                    }
+                    sort_unique(pos_keys);  // the query result is parsed into a SET of edges (GraphDBSampler.scala:196-205)
+                    for (const TEdge& k : pos_keys) tc.hydrate(hyd_pos, k, true, pos_edges);
+                }
+                sort_unique(nodes);
+                sort_unique(keys);
+                // RootedNodeNeighborhood: collect_list over the LEFT JOIN = one Edge per record; main sample: merged by key
+                for (const TEdge& k : keys) tc.hydrate(hyd_graph, k, kind == 0, edges);
                 int Fr = 0;
-                const float* xr = feat_of(root_node_type, root, Fr);
-                const size_t root_sz = node_size(root, root_node_type, Fr);
-                size_t graph = 0;
+                const float* xr = tc.node_feat(rtype, root, Fr);
+                const size_t root_sz = node_size(root, rtype, Fr);
+                size_t graph = 0, pos_sz = 0;
                 for (const TNode& v : nodes) {
                     int F = 0;
-                    feat_of(v.type, v.id, F);
+                    tc.node_feat(v.type, v.id, F);
                     const size_t ns = node_size(v.id, v.type, F);
                     graph += 1 + varint_size(ns) + ns;
                 }
                 for (const TEdge& e : edges) {
-                    const size_t es = edge_size(e.src, e.dst, e.type, 0);
+                    const size_t es = edge_size(e.src, e.dst, e.type, tc.edge_feat_len(e));
                     graph += 1 + varint_size(es) + es;
                 }
-                const size_t message = 1 + varint_size(root_sz) + root_sz + 1 + varint_size(graph) + graph;
+                for (const TEdge& e : pos_edges) {
+                    const size_t es = edge_size(e.src, e.dst, e.type, tc.edge_feat_len(e));
+                    pos_sz += 1 + varint_size(es) + es;
+                }
+                const size_t message = 1 + varint_size(root_sz) + root_sz + 1 + varint_size(graph) + graph + pos_sz;
                 if (pass == 0) {
                     rec[(size_t)r + 1] = (int64_t)message + (tfrecord_framing ? 16 : 0);
                     continue;
@@ -668,20 +765,28 @@ int gigl_encode_dag_samples_host(int64_t n_roots, const int32_t* roots, int32_t 
                 }
                 *p++ = 0x0A;  // root_node = 1
                 p = put_varint(p, root_sz);
-                p = put_node(p, root, root_node_type, xr, Fr);
-                *p++ = 0x12;  // neighborhood = 2 : Graph { nodes = 2, edges = 3 }
+                p = put_node(p, root, rtype, xr, Fr);
+                // neighborhood: field 2 of RootedNodeNeighborhood, field 3 of NodeAnchorBasedLinkPredictionSample
+                *p++ = kind == 2 ? 0x1A : 0x12;
                 p = put_varint(p, graph);
-                for (const TNode& v : nodes) {
+                for (const TNode& v : nodes) {  // Graph { nodes = 2, edges = 3 }
                     int F = 0;
-                    const float* xv = feat_of(v.type, v.id, F);
+                    const float* xv = tc.node_feat(v.type, v.id, F);
                     *p++ = 0x12;
                     p = put_varint(p, node_size(v.id, v.type, F));
                     p = put_node(p, v.id, v.type, xv, F);
                 }
                 for (const TEdge& e : edges) {
+                    const int Fe = tc.edge_feat_len(e);
                     *p++ = 0x1A;
-                    p = put_varint(p, edge_size(e.src, e.dst, e.type, 0));
-                    p = put_edge(p, e.src, e.dst, e.type, nullptr, 0);
+                    p = put_varint(p, edge_size(e.src, e.dst, e.type, Fe));
+                    p = put_edge(p, e.src, e.dst, e.type, tc.edge_feat(e), Fe);
+                }
+                for (const TEdge& e : pos_edges) {  // pos_edges = 4
+                    const int Fe = tc.edge_feat_len(e);
+                    *p++ = 0x22;
+                    p = put_varint(p, edge_size(e.src, e.dst, e.type, Fe));
+                    p = put_edge(p, e.src, e.dst, e.type, tc.edge_feat(e), Fe);
                 }
                 if (tfrecord_framing) {
                     const uint32_t c = mask_crc(crc32c(payload, (size_t)(p - payload)));
@@ -700,6 +805,41 @@ int gigl_encode_dag_samples_host(int64_t n_roots, const int32_t* roots, int32_t 
     *out = buf;
     *out_bytes = rec[(size_t)n_roots];
     return GIGL_OK;
+}
+
+bool typed_tables_ok(int32_t n_node_types, const gigl_node_table* node_tables, int32_t n_edge_types, const gigl_edge_table* edge_tables) {
+    if (n_node_types < 0 || (n_node_types > 0 && !node_tables) || n_edge_types < 0) return false;
+    for (int t = 0; t < n_node_types; ++t)
+        if (node_tables[t].n_feat < 0 || (node_tables[t].n_feat > 0 && !node_tables[t].x)) return false;
+    if (edge_tables)
+        for (int t = 0; t < n_edge_types; ++t)
+            if (edge_tables[t].rowptr && (!edge_tables[t].col || edge_tables[t].n_feat < 0 || (edge_tables[t].n_feat > 0 && !edge_tables[t].feat)))
+                return false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gigl_encode_dag_samples_host(int64_t n_roots, const int32_t* roots, int32_t root_node_type, int32_t n_ops, const gigl_dag_op* ops,
+                                 int32_t n_node_types, const gigl_node_table* node_tables, int32_t tfrecord_framing, uint8_t** out,
+                                 int64_t* out_bytes, int64_t* record_offsets) {
+    if (!typed_tables_ok(n_node_types, node_tables, 0, nullptr)) return GIGL_E_INVALID;
+    const gigl_dag_tree tree{n_roots, roots, root_node_type, n_ops, ops};
+    const TypedCtx tc{n_node_types, node_tables, 0, nullptr};
+    return encode_typed(0, &tree, nullptr, 0, nullptr, nullptr, -1, 0, 0, tc, tfrecord_framing, out, out_bytes, record_offsets);
+}
+
+int gigl_encode_typed_samples_host(int32_t kind, const gigl_dag_tree* anchors, const gigl_dag_tree* targets, int32_t num_pos,
+                                   const int32_t* pos, const int64_t* pos_tree, int32_t pos_condensed_edge_type, int32_t include_isolated,
+                                   int32_t hydrate_flags, int32_t n_node_types, const gigl_node_table* node_tables, int32_t n_edge_types,
+                                   const gigl_edge_table* edge_tables, int32_t tfrecord_framing, uint8_t** out, int64_t* out_bytes,
+                                   int64_t* record_offsets) {
+    if (!typed_tables_ok(n_node_types, node_tables, n_edge_types, edge_tables)) return GIGL_E_INVALID;
+    const TypedCtx tc{n_node_types, node_tables, n_edge_types, edge_tables};
+    return encode_typed(kind, anchors, targets, num_pos, pos, pos_tree, pos_condensed_edge_type, include_isolated, hydrate_flags, tc,
+                        tfrecord_framing, out, out_bytes, record_offsets);
 }
 
 // ---- TFRecord reading + tf.Example decoding ----------------------------------------------------------

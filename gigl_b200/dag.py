@@ -2,10 +2,11 @@
 only the reference's spark35 graph-DB path expresses (`SamplingOpDAG.from`, scala_spark35/common/src/main/scala/types/
 SamplingOpDAG.scala:19-51; `GraphDBSampler.getKHopSubgraphForRootNode`, .../libs/sampler/GraphDBSampler.scala:40-148).
 
-Every op expands the result nodes of its parent op (or the root) over ONE edge type with a uniform fanout.  Ops with at
+Every op expands the result nodes of its input ops (or the root) over ONE edge type with a uniform fanout.  Ops with at
 most one input (tree-shaped DAGs: chains that branch) map one to one onto `gigl_sample_op_*` launches - one kernel
-launch per op over that edge type's CSR, ancestors' padded trees as the frontier.  Ops with several inputs (the union
-of several parents' results) are not supported.
+launch per op over that edge type's CSR, ancestors' padded trees as the frontier.  An op with several inputs (the union
+of several parents' results, GraphDBSampler.scala:66-82) runs once per input - one launch per (op, input) instance -
+and its result set is the union of the instances' outputs.
 
 The reference's graph-DB clients do not sample reproducibly (`LocalDbClient.scala:186,204` takes `Set.take(n)`; Nebula
 samples server-side), so there is nothing bit-level to match: each op draws GiGL's seeded hash permutation with the op's
@@ -54,38 +55,53 @@ def ops_from_config(path: dict) -> List[SamplingOp]:
 @dataclass
 class PlannedOp:
     op: SamplingOp
-    call_no: int                  # 1-based position in DAG order = the permutation call number
-    parent: Optional[str]         # op_name of the input op, None = expands the root
-    chain: List[str]              # op names from the root down to and including this op
+    call_no: int                  # 1-based position of the op in DAG order = the permutation call number
+    parent: Optional[str]         # key of the input instance, None = expands the root
+    chain: List[str]              # instance keys from the root down to and including this one
+    key: str = ""                 # unique instance key: the op name, or "op@parent-key" for an op with several inputs
+    fanouts: List[int] = field(default_factory=list)   # num_nodes_to_sample along `chain`
 
 
 def plan(ops: Sequence[SamplingOp], root_node_type: str) -> List[PlannedOp]:
-    """Topological order with type checks: an op's frontier type must be its parent's result type (the root type for
-    root ops)."""
+    """Topological order with type checks: an op's frontier type must be the result type of each of its inputs (the root
+    type for root ops).  An op with several inputs expands the union of its inputs' result nodes
+    (GraphDBSampler.scala:66-82); here that is one INSTANCE per input - each expands that input's padded tree - and the
+    op's result set is the union of its instances' outputs.  Instances of one op share its call number."""
     by_name = {o.op_name: o for o in ops}
     if len(by_name) != len(ops):
         raise ValueError("duplicate op names")
-    planned: Dict[str, PlannedOp] = {}
+    instances: Dict[str, List[PlannedOp]] = {}   # op name -> its planned instances
     order: List[PlannedOp] = []
     pending = list(ops)
+    n_done = 0
     while pending:
         progressed = False
         for o in list(pending):
-            if len(o.input_op_names) > 1:
-                raise ValueError(f"op {o.op_name!r} has several input ops: only tree-shaped DAGs are supported")
             if o.num_nodes_to_sample < 1:
                 raise ValueError(f"op {o.op_name!r}: numNodesToSample must be >= 1")
-            par = o.input_op_names[0] if o.input_op_names else None
-            if par is not None and par not in by_name:
-                raise ValueError(f"op {o.op_name!r} names an unknown input op {par!r}")
-            if par is not None and par not in planned:
+            if len(set(o.input_op_names)) != len(o.input_op_names):
+                raise ValueError(f"op {o.op_name!r} names an input op twice")
+            for par in o.input_op_names:
+                if par not in by_name:
+                    raise ValueError(f"op {o.op_name!r} names an unknown input op {par!r}")
+            if any(par not in instances for par in o.input_op_names):
                 continue
-            want = root_node_type if par is None else planned[par].op.result_node_type
-            if o.frontier_node_type != want:
-                raise ValueError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {want!r}")
-            p = PlannedOp(o, len(order) + 1, par, (planned[par].chain if par else []) + [o.op_name])
-            planned[o.op_name] = p
-            order.append(p)
+            n_done += 1
+            made = []
+            if not o.input_op_names:
+                if o.frontier_node_type != root_node_type:
+                    raise ValueError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {root_node_type!r}")
+                made.append(PlannedOp(o, n_done, None, [o.op_name], o.op_name, [o.num_nodes_to_sample]))
+            for par in o.input_op_names:
+                want = by_name[par].result_node_type
+                if o.frontier_node_type != want:
+                    raise ValueError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {want!r}")
+                for pi in instances[par]:
+                    single = len(o.input_op_names) == 1 and len(instances[par]) == 1
+                    key = o.op_name if single else f"{o.op_name}@{pi.key}"
+                    made.append(PlannedOp(o, n_done, pi.key, pi.chain + [key], key, pi.fanouts + [o.num_nodes_to_sample]))
+            instances[o.op_name] = made
+            order += made
             pending.remove(o)
             progressed = True
         if not progressed:
@@ -94,15 +110,28 @@ def plan(ops: Sequence[SamplingOp], root_node_type: str) -> List[PlannedOp]:
 
 
 def sample_dag(graphs: Dict[Tuple[Tuple[str, str, str], str], "object"], roots, ops: Sequence[SamplingOp], root_node_type: str,
-               base_seed: int = 42):
-    """Runs every op on the device.  `graphs[(edge_type, direction)]` = the :class:`gigl_b200.Graph` of that edge type,
-    built by destination for INCOMING ops and `by_source=True` for OUTGOING ones.  `roots`: int32 CUDA tensor.
-    Returns {op_name: (nbr, cnt, chain_fanouts)} with the padded-tree layout of `Graph.sample_khop`."""
+               base_seed: int = 42, call_no_offset: int = 0):
+    """Runs every op instance on the device.  `graphs[(edge_type, direction)]` = the :class:`gigl_b200.Graph` of that edge
+    type, built by destination for INCOMING ops and `by_source=True` for OUTGOING ones.  `roots`: int32 CUDA tensor.
+    Returns {instance key: (nbr, cnt, chain_fanouts)} with the padded-tree layout of `Graph.sample_khop` (the key is the op
+    name unless the op has several inputs, see :func:`plan`)."""
     res = {}
     for p in plan(ops, root_node_type):
-        fan = [next(q for q in ops if q.op_name == name).num_nodes_to_sample for name in p.chain]
-        chain_nbr = [res[name][0] for name in p.chain[:-1]]
+        chain_nbr = [res[k][0] for k in p.chain[:-1]]
         g = graphs[(p.op.edge_type, p.op.sampling_direction)]
-        nbr, cnt = g.sample_op(roots, fan, chain_nbr, p.call_no, base_seed)
-        res[p.op.op_name] = (nbr, cnt, fan)
+        nbr, cnt = g.sample_op(roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, base_seed)
+        res[p.key] = (nbr, cnt, p.fanouts)
     return res
+
+
+def encoder_ops(planned: Sequence[PlannedOp], res: dict, cet_of: dict, cnt_of: dict) -> List[dict]:
+    """The planned instances + their sampled padded trees as the op dicts `sample_io.encode_typed_samples` takes.
+    cet_of: edge type triple -> condensed edge type; cnt_of: node type name -> condensed node type."""
+    index = {p.key: i for i, p in enumerate(planned)}
+    out = []
+    for p in planned:
+        nbr = res[p.key][0]
+        out.append(dict(parent=-1 if p.parent is None else index[p.parent], fanout=p.op.num_nodes_to_sample,
+                        condensed_edge_type=cet_of[p.op.edge_type], result_node_type=cnt_of[p.op.result_node_type],
+                        outgoing=p.op.sampling_direction == OUTGOING, nbr=nbr.cpu().numpy() if hasattr(nbr, "cpu") else nbr))
+    return out

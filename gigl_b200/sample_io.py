@@ -248,6 +248,72 @@ def encode_dag_samples(roots, root_node_type: int, ops: Sequence[dict], node_tab
     return data, offs
 
 
+def _dag_tree(roots, root_node_type: int, ops: Sequence[dict], keep: list) -> "_capi.DagTree":
+    roots = np.ascontiguousarray(roots, dtype=np.int32)
+    c_ops = (_capi.DagOp * max(len(ops), 1))()
+    for i, o in enumerate(ops):
+        nbr = np.ascontiguousarray(o["nbr"], dtype=np.int32)
+        keep.append(nbr)
+        c_ops[i] = _capi.DagOp(int(o["parent"]), int(o["fanout"]), int(o["condensed_edge_type"]), int(o["result_node_type"]),
+                               int(bool(o.get("outgoing", False))), nbr.ctypes.data)
+    keep += [roots, c_ops]
+    return _capi.DagTree(len(roots), roots.ctypes.data, int(root_node_type), len(ops), C.addressof(c_ops))
+
+
+def encode_typed_samples(roots, root_node_type: int, ops: Sequence[dict], node_tables: Sequence[Optional[np.ndarray]],
+                         edge_tables: Optional[Sequence[Optional["HostEdgeTable"]]] = None, kind: str = "rnn", pos=None, pos_tree=None,
+                         pos_condensed_edge_type: int = -1, target_roots=None, target_node_type: int = 0,
+                         target_ops: Optional[Sequence[dict]] = None, include_isolated: bool = False, hydrate_edges: bool = True,
+                         hydrate_pos_edges: bool = True, tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
+    """Typed RootedNodeNeighborhood (kind "rnn") / NodeAnchorBasedLinkPredictionSample (kind "nablp") messages from sampled
+    SamplingOp DAGs, with edge hydration (gigl_encode_typed_samples_host).  ops as in :func:`encode_dag_samples`;
+    edge_tables[t] = :class:`HostEdgeTable` of condensed edge type t (None entries / None = not hydrated).  nablp: pos
+    [n_roots, num_pos] positive node ids (-1 = none), pos_tree = their index in target_roots (-1 = the node alone),
+    target_* = the sampled DAG of the positives' node type."""
+    L = _capi.lib()
+    keep: list = []
+    anchors = _dag_tree(roots, root_node_type, ops, keep)
+    n = int(anchors.n_roots)
+    c_tabs = (_capi.NodeTable * max(len(node_tables), 1))()
+    for t, x in enumerate(node_tables):
+        if x is not None and x.size:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            keep.append(x)
+            c_tabs[t] = _capi.NodeTable(x.ctypes.data, x.shape[1])
+        else:
+            c_tabs[t] = _capi.NodeTable(None, 0)
+    c_et, n_et = None, 0
+    if edge_tables is not None:
+        n_et = len(edge_tables)
+        c_et = (_capi.EdgeTable * max(n_et, 1))()
+        for t, tab in enumerate(edge_tables):
+            c_et[t] = tab.struct() if tab is not None else _capi.EdgeTable(None, None, None, None, 0)
+        keep.append(edge_tables)
+    targets, num_pos, pos_p, tree_p = None, 0, None, None
+    if kind == "nablp":
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(n, -1)
+        pos_tree = np.ascontiguousarray(pos_tree, dtype=np.int64).reshape(n, -1)
+        num_pos = pos.shape[1]
+        targets = _dag_tree(target_roots if target_roots is not None else np.zeros(0, np.int32), target_node_type, target_ops or [], keep)
+        pos_p, tree_p = pos.ctypes.data, pos_tree.ctypes.data
+    elif kind != "rnn":
+        raise ValueError(f"kind must be 'rnn' or 'nablp', got {kind!r}")
+    out = C.c_void_p()
+    nbytes = C.c_int64()
+    offs = np.zeros(n + 1, dtype=np.int64)
+    rc = L.gigl_encode_typed_samples_host(2 if kind == "nablp" else 0, C.addressof(anchors), C.addressof(targets) if targets is not None else None,
+                                          num_pos, pos_p, tree_p, int(pos_condensed_edge_type), int(include_isolated),
+                                          int(bool(hydrate_edges)) | (int(bool(hydrate_pos_edges)) << 1), len(node_tables), C.addressof(c_tabs),
+                                          n_et, C.addressof(c_et) if c_et is not None else None, int(tfrecord_framing), C.byref(out),
+                                          C.byref(nbytes), offs.ctypes.data)
+    _check(rc, "gigl_encode_typed_samples_host")
+    try:
+        data = C.string_at(out.value, nbytes.value)
+    finally:
+        L.gigl_free_host(out)
+    return data, offs
+
+
 # ---- a minimal protobuf wire reader (tests, tooling): no generated code needed --------------------
 def _varint(buf: bytes, pos: int) -> Tuple[int, int]:
     v = shift = 0

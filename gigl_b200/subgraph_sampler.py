@@ -25,12 +25,12 @@ User-defined positive / negative label edges (`positiveEdgeInfo` / `negativeEdge
 UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:54-581) are sampled from and hydrated against their own tables
 (`numUserDefinedPositiveSamples` / `numUserDefinedNegativeSamples`; negatives fill `hard_neg_edges`).
 
-Graphs with several node / edge types go through `subgraphSamplingStrategy.messagePassingPaths` (one tree-shaped
-SamplingOp DAG per root node type, INCOMING / OUTGOING ops; `gigl_b200.dag`) and emit typed `RootedNodeNeighborhood`
-TFRecords per node type, as `GraphDBNodeAnchorBasedLinkPredictionTask.scala:100-190` does.
+Graphs with several node / edge types go through `subgraphSamplingStrategy.messagePassingPaths` (one SamplingOp DAG per
+root node type, INCOMING / OUTGOING ops, ops with several inputs; `gigl_b200.dag`) and emit typed, hydrated
+`RootedNodeNeighborhood` TFRecords per node type and the typed `NodeAnchorBasedLinkPredictionSample` TFRecords of the
+first supervision edge type, as `GraphDBNodeAnchorBasedLinkPredictionTask.scala:100-495` does.
 
-Scope (DESIGN.md): local / file:// URIs.  Sampling ops with several input ops, the typed task's
-NodeAnchorBasedLinkPredictionSample output and `gs://` are not implemented.  The reference's default
+Scope (DESIGN.md): local / file:// URIs; `gs://` is not implemented.  The reference's default
 permutation strategy is the unseedable Spark shuffle; this implementation always uses the seeded hash permutation (a
 valid uniform sample; bit-exact to the reference's `permutation_strategy: deterministic`).
 """
@@ -309,9 +309,11 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
 def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> dict:
     """Several node / edge types: one SamplingOp DAG per root node type (`subgraphSamplingStrategy.messagePassingPaths`, the
     only strategy the reference's typed path accepts - SubgraphSamplingStrategyWrapper.scala:10-22), one kernel launch per
-    op over that edge type's CSR, typed RootedNodeNeighborhood TFRecords per node type
-    (GraphDBNodeAnchorBasedLinkPredictionTask.scala:100-190).  The NodeAnchorBasedLinkPredictionSample output of the
-    typed task is not emitted."""
+    op instance over that edge type's CSR.  Outputs as GraphDBNodeAnchorBasedLinkPredictionTask.run writes them
+    (scala_spark35/.../libs/task/graphdb/GraphDBNodeAnchorBasedLinkPredictionTask.scala:100-495): typed, hydrated
+    RootedNodeNeighborhood TFRecords per anchor / target node type FIRST, then - for a link-prediction task that trains or
+    evaluates - NodeAnchorBasedLinkPredictionSample TFRecords for the first supervision edge type: positives = an OUTGOING
+    uniform sample of `numPositiveSamples` over that edge type, neighbourhood = the anchor's merged with its positives'."""
     import torch
 
     from . import dag
@@ -325,11 +327,19 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
     if not strat:
         raise ValueError("graphs with several node / edge types need subgraphSamplingStrategy.messagePassingPaths")
     flat = shared["flattenedGraphMetadata"]
+    task_meta = cfg.get("taskMetadata", {})
+    sup_et = None
     if "nodeAnchorBasedLinkPredictionOutput" in flat:
         out_dirs = dict(flat["nodeAnchorBasedLinkPredictionOutput"].get("nodeTypeToRandomNegativeTfrecordUriPrefix") or {})
+        sup = (task_meta.get("nodeAnchorBasedLinkPredictionTaskMetadata") or {}).get("supervisionEdgeTypes") or []
+        if sup:
+            sup_et = (sup[0]["srcNodeType"], sup[0]["relation"], sup[0]["dstNodeType"])  # phase 1: one supervision edge type (:139)
     else:
-        sup = cfg["taskMetadata"]["nodeBasedTaskMetadata"]["supervisionNodeTypes"]
+        sup = task_meta["nodeBasedTaskMetadata"]["supervisionNodeTypes"]
         out_dirs = {sup[0]: flat["supervisedNodeClassificationOutput"]["unlabeledTfrecordUriPrefix"]}
+    skip_main = bool(shared.get("shouldSkipTraining", False)) and bool(shared.get("shouldSkipModelEvaluation", False))
+    include_isolated = bool(shared.get("shouldIncludeIsolatedNodesInTraining", False))
+    max_train = int(sgs.get("numMaxTrainingSamplesToOutput", 0) or 0)
     # ---- node tables per condensed node type
     ids, tables, n_max = {}, [None] * (max(node_type_of) + 1), 0
     for k, nmeta in meta["condensedNodeTypeToPreprocessedMetadata"].items():
@@ -342,12 +352,14 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
             x[nid] = feat
             tables[int(k)] = x
         n_max = max(n_max, int(nid.max(initial=-1)) + 1)
-    # ---- edge tables per condensed edge type
-    edges = {}
+    # ---- edge tables per condensed edge type (+ features)
+    edges, edge_feat = {}, {}
     for k, emeta in meta["condensedEdgeTypeToPreprocessedMetadata"].items():
-        t = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(emeta["mainEdgeInfo"]["tfrecordUriPrefix"], root)))
+        main = emeta["mainEdgeInfo"]
+        t = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(main["tfrecordUriPrefix"], root)))
         es, ed = t.column(emeta["srcNodeIdKey"], "int64"), t.column(emeta["dstNodeIdKey"], "int64")
         edges[int(k)] = (es.astype(np.int32), ed.astype(np.int32))
+        edge_feat[int(k)] = _feature_matrix(t, main.get("featureKeys"))
         n_max = max(n_max, int(es.max(initial=-1)) + 1, int(ed.max(initial=-1)) + 1)
     for tt, x in enumerate(tables):  # ids above a type's own table (seen only as edge endpoints) hydrate as zeros
         if x is not None and x.shape[0] < n_max:
@@ -356,38 +368,99 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
     ctx = Context.on_torch_stream(device)
     dev = torch.device("cuda", device)
     graphs = {}
+
+    def graph_of(edge_type, direction):
+        key = (edge_type, direction)  # CSR per (edge type, direction), built on first use
+        if key not in graphs:
+            es, ed = edges[cet_of[edge_type]]
+            graphs[key] = Graph.from_edges_host(ctx, n_max, es, ed, is_graph_directed=True, by_source=direction == dag.OUTGOING)
+        return graphs[key]
+
+    edge_tabs = None
+
+    def edge_tables():
+        """Host copies of every edge type's records as the hydration join reads them (built once, on first need)."""
+        nonlocal edge_tabs
+        if edge_tabs is None:
+            edge_tabs = [None] * (max(edges) + 1)
+            for k, (es, ed) in edges.items():
+                g_in = Graph.from_edges_host(ctx, n_max, es, ed, is_graph_directed=True)
+                ef = edge_feat[k]
+                edge_tabs[k] = sio.HostEdgeTable(g_in.csr_host(), ctx.edge_rows_host(n_max, es, ed, True) if ef is not None else None, ef)
+                g_in.close()
+        return edge_tabs
+
+    dags = {}
+    for path in strat.get("paths") or []:
+        ops = dag.ops_from_config(path)
+        planned = dag.plan(ops, path["rootNodeType"])
+        for p in planned:
+            graph_of(p.op.edge_type, p.op.sampling_direction)
+        # hydrateRnn joins the edges only if an edge type of the DAG's ROOT ops carries features (:186-193, 283-291)
+        hydrate = any(edge_feat[cet_of[p.op.edge_type]] is not None for p in planned if p.parent is None)
+        dags[path["rootNodeType"]] = (ops, planned, hydrate)
+
+    def sample(rtype, roots):
+        ops, planned, _ = dags[rtype]
+        res = dag.sample_dag(graphs, torch.from_numpy(roots).to(dev), ops, rtype, base_seed=SAMPLING_SEED)
+        ctx.sync()
+        return dag.encoder_ops(planned, res, cet_of, cnt_of)
+
     stats = {"rnn": 0, "snc": 0, "nablp": 0, "rnn_per_node_type": {}, "n_nodes": n_max}
     t1 = time.time()
-    for path in strat.get("paths") or []:
-        rtype = path["rootNodeType"]
+    for rtype in dags:
         if rtype not in out_dirs:
             continue
-        ops = dag.ops_from_config(path)
-        planned = dag.plan(ops, rtype)
-        for p in planned:  # CSR per (edge type, direction), built on first use
-            key = (p.op.edge_type, p.op.sampling_direction)
-            if key not in graphs:
-                es, ed = edges[cet_of[p.op.edge_type]]
-                graphs[key] = Graph.from_edges_host(ctx, n_max, es, ed, is_graph_directed=True, by_source=p.op.sampling_direction == dag.OUTGOING)
         out_dir = _resolve(out_dirs[rtype], root)
         os.makedirs(out_dir, exist_ok=True)
-        index = {p.op.op_name: i for i, p in enumerate(planned)}
         roots_all = ids[cnt_of[rtype]]
+        hydrate = dags[rtype][2]
         for part, s in enumerate(range(0, len(roots_all), batch_roots)):
             roots = roots_all[s:s + batch_roots]
-            res = dag.sample_dag(graphs, torch.from_numpy(roots).to(dev), ops, rtype, base_seed=SAMPLING_SEED)
-            ctx.sync()
-            enc = [dict(parent=-1 if p.parent is None else index[p.parent], fanout=p.op.num_nodes_to_sample,
-                        condensed_edge_type=cet_of[p.op.edge_type], result_node_type=cnt_of[p.op.result_node_type],
-                        outgoing=p.op.sampling_direction == dag.OUTGOING, nbr=res[p.op.op_name][0].cpu().numpy()) for p in planned]
-            data, _ = sio.encode_dag_samples(roots, cnt_of[rtype], enc, tables)
+            data, _ = sio.encode_typed_samples(roots, cnt_of[rtype], sample(rtype, roots), tables, edge_tables() if hydrate else None,
+                                               kind="rnn", hydrate_edges=hydrate)
             _write(out_dir, part, data)
             stats["rnn"] += len(roots)
             stats["rnn_per_node_type"][rtype] = stats["rnn_per_node_type"].get(rtype, 0) + len(roots)
+    # ---- main samples of the link-prediction task
+    if sup_et is not None and not skip_main and "tfrecordUriPrefix" in flat["nodeAnchorBasedLinkPredictionOutput"]:
+        a_type, t_type = sup_et[0], sup_et[2]
+        if a_type not in dags or t_type not in dags:
+            raise KeyError(f"messagePassingPaths needs a path for the anchor type {a_type!r} and the target type {t_type!r}")
+        num_pos = int(sgs.get("numPositiveSamples", 0))
+        if num_pos < 1:
+            raise ValueError("datasetConfig.subgraphSamplerConfig.numPositiveSamples must be >= 1")
+        g_pos = graph_of(sup_et, dag.OUTGOING)
+        pos_cet = cet_of[sup_et]
+        hyd_graph = dags[a_type][2] or dags[t_type][2]
+        hyd_pos = edge_feat[pos_cet] is not None  # posEdgeHasEdgeFeatures (:344-346)
+        pos_call = len(dags[a_type][0]) + 1  # the positives are drawn after the anchor's own ops (= call 3 after a 2-hop chain)
+        main_dir = _resolve(flat["nodeAnchorBasedLinkPredictionOutput"]["tfrecordUriPrefix"], root)
+        os.makedirs(main_dir, exist_ok=True)
+        anchors_all = ids[cnt_of[a_type]]
+        if max_train > 0:
+            # numMaxTrainingSamplesToOutput: the reference draws a random `.sample(fraction)` of the anchors' RNNs before the
+            # join with the positives (:232-262); this keeps the first n by node id
+            anchors_all = anchors_all[:max_train]
+        for part, s in enumerate(range(0, len(anchors_all), batch_roots)):
+            roots = anchors_all[s:s + batch_roots]
+            pos, _ = g_pos.sample_op(torch.from_numpy(roots).to(dev), [num_pos], [], pos_call, SAMPLING_SEED)
+            ctx.sync()
+            pos = pos.cpu().numpy().reshape(len(roots), num_pos)
+            t_roots = np.unique(pos[pos >= 0]).astype(np.int32)
+            tree = np.where(pos >= 0, np.searchsorted(t_roots, np.maximum(pos, 0)), -1).astype(np.int64)
+            need = hyd_graph or hyd_pos
+            data, offs = sio.encode_typed_samples(roots, cnt_of[a_type], sample(a_type, roots), tables, edge_tables() if need else None,
+                                                  kind="nablp", pos=pos, pos_tree=tree, pos_condensed_edge_type=pos_cet,
+                                                  target_roots=t_roots, target_node_type=cnt_of[t_type],
+                                                  target_ops=sample(t_type, t_roots) if len(t_roots) else [],
+                                                  include_isolated=include_isolated, hydrate_edges=hyd_graph, hydrate_pos_edges=hyd_pos)
+            _write(main_dir, part, data)
+            stats["nablp"] += int((np.diff(offs) > 0).sum())
     stats["seconds_sample_and_write"] = time.time() - t1
     stats["seconds_total"] = time.time() - t0
-    log(f"[{job_name}] wrote typed RootedNodeNeighborhood records {stats['rnn_per_node_type']} in {stats['seconds_sample_and_write']:.2f}s "
-        "(typed NodeAnchorBasedLinkPredictionSample output is not emitted)")
+    log(f"[{job_name}] wrote typed RootedNodeNeighborhood records {stats['rnn_per_node_type']} + {stats['nablp']} "
+        f"NodeAnchorBasedLinkPredictionSample records in {stats['seconds_sample_and_write']:.2f}s")
     return stats
 
 

@@ -485,6 +485,37 @@ int gigl_encode_dag_samples_host(int64_t n_roots, const int32_t* roots, int32_t 
                                  int32_t n_node_types, const gigl_node_table* node_tables /* by condensed node type */,
                                  int32_t tfrecord_framing, uint8_t** out, int64_t* out_bytes, int64_t* record_offsets);
 /*
+ * The typed task's two outputs with edge hydration (GraphDBNodeAnchorBasedLinkPredictionTask.run,
+ * scala_spark35/subgraph_sampler/src/main/scala/libs/task/graphdb/GraphDBNodeAnchorBasedLinkPredictionTask.scala:100-495).
+ * A gigl_dag_tree is one batch of roots of ONE node type with the padded-tree outputs of that type's SamplingOp DAG.  An op
+ * with several input ops appears once per input (one gigl_dag_op per (op, parent) pair): the union of those entries is
+ * the op's result set, as GraphDBSampler.scala:66-82 expands the union of its parents' result nodes.
+ *   kind 0: RootedNodeNeighborhood per anchor root = gigl_encode_dag_samples_host plus edge hydration.
+ *   kind 2: NodeAnchorBasedLinkPredictionSample per anchor root: pos_edges = the distinct (anchor -> positive) edges of
+ *     pos [n_roots * num_pos] (-1 = none; sampled by an OUTGOING op over the supervision edge type,
+ *     GraphDBSampler.samplePositiveEdgeNeighborhoods :175-215) with condensed type pos_condensed_edge_type;
+ *     neighborhood = the anchor's DAG merged BY KEY with the DAG of every positive (pos_tree = index of the positive in
+ *     targets->roots, -1 = the positive node alone) - mergeGraphs (GraphPbWrappers.scala:43-68) keeps one Edge per
+ *     (src, dst, type).  Anchors without a positive emit nothing unless include_isolated != 0
+ *     (sharedConfig.shouldIncludeIsolatedNodesInTraining, the LEFT JOIN at :384-402).
+ * edge_tables[t] (optional) = the records of condensed edge type t as an in-CSR by destination (+ feature rows):
+ * hydrate_flags bit 0 joins the neighbourhood's edges against it (SGSTask.hydrateRnn's LEFT JOIN on (_from, _to, type):
+ * kind 0 emits one Edge per matching record, kind 2 the first), bit 1 the pos_edges (:349-377); an edge without a record or
+ * a table stays feature-less.  record_offsets has anchors->n_roots + 1 entries.
+ */
+typedef struct gigl_dag_tree {
+    int64_t n_roots;
+    const int32_t* roots;
+    int32_t root_node_type;      /* condensed node type of the roots */
+    int32_t n_ops;
+    const gigl_dag_op* ops;      /* topological order */
+} gigl_dag_tree;
+int gigl_encode_typed_samples_host(int32_t kind, const gigl_dag_tree* anchors, const gigl_dag_tree* targets, int32_t num_pos,
+                                   const int32_t* pos, const int64_t* pos_tree, int32_t pos_condensed_edge_type, int32_t include_isolated,
+                                   int32_t hydrate_flags, int32_t n_node_types, const gigl_node_table* node_tables, int32_t n_edge_types,
+                                   const gigl_edge_table* edge_tables /* by condensed edge type, or NULL */, int32_t tfrecord_framing,
+                                   uint8_t** out, int64_t* out_bytes, int64_t* record_offsets);
+/*
  * Splits a TFRecord byte stream into records (payload offsets / lengths, arrays of capacity max_records; pass NULL
  * arrays to only count).  verify != 0 checks both masked crc32c fields.  Returns the record count or GIGL_E_*.
  */

@@ -403,6 +403,60 @@ def np_assemble_dag_rnn(roots, root_node_type, ops):
     return out
 
 
+def np_typed_edge_records(tables):
+    """{condensed edge type: (src, dst, feat or None)} -> {type: {(src, dst): [feature tuple (or None) per record, input order]}}:
+    the hydrated edge view keyed the way SGSTask.hydrateRnn joins it (_from, _to, _condensed_edge_type)."""
+    out = {}
+    for t, (src, dst, feat) in tables.items():
+        d = {}
+        for i, (a, b) in enumerate(zip(src, dst)):
+            d.setdefault((int(a), int(b)), []).append(None if feat is None else tuple(np.float32(feat[i]).tolist()))
+        out[int(t)] = d
+    return out
+
+
+def _typed_join(key, records, all_records):
+    """LEFT JOIN of one (type, src, dst) key with the records of its type: [(type, src, dst, feat or None)]."""
+    t, a, b = key
+    recs = records[t].get((a, b)) if records is not None and t in records else None
+    if not recs:
+        return [(t, a, b, None)]
+    return [(t, a, b, f) for f in (recs if all_records else recs[:1])]
+
+
+def np_hydrate_typed_rnn(sets, records):
+    """np_assemble_dag_rnn output -> {root: (hydrated edges [(type, src, dst, feat)], nodes)}: collect_list over the LEFT
+    JOIN with the hydrated edge view = one Edge per matching record (SGSTask.scala:243-262)."""
+    return {r: (sorted((e for k in edges for e in _typed_join(k, records, True)), key=lambda e: (e[0], e[1], e[2], e[3] or ())), nodes)
+            for r, (edges, nodes) in sets.items()}
+
+
+def np_assemble_typed_nablp(anchor_sets, target_sets, target_node_type, pos, pos_edge_type, records=None, hydrate_edges=True,
+                            hydrate_pos=True, include_isolated=False):
+    """The typed task's NodeAnchorBasedLinkPredictionSample (GraphDBNodeAnchorBasedLinkPredictionTask.scala:283-470):
+    anchor_sets / target_sets = np_assemble_dag_rnn of the anchors / of the positives' node type (keyed by node id), pos
+    {anchor: [positive ids]}.  pos_edges = the SET of (anchor -> positive) edges, LEFT JOINed with the edge records (one
+    per record); neighbourhood = mergeGraphs(anchor's, positives') = distinct by key (GraphPbWrappers.scala:43-68), one
+    record per key.  Anchors without a positive are dropped unless include_isolated.
+    Returns {anchor: (pos_edges, edges, nodes)}."""
+    out = {}
+    for a, (edges, nodes) in anchor_sets.items():
+        plist = sorted({int(p) for p in pos.get(a, []) if p >= 0})
+        if not plist and not include_isolated:
+            continue
+        eset, nset = set(edges), set(nodes)
+        for p_ in plist:
+            if p_ in target_sets:
+                eset |= set(target_sets[p_][0])
+                nset |= set(target_sets[p_][1])
+            else:
+                nset.add((int(target_node_type), p_))
+        pe = [e for p_ in plist for e in _typed_join((int(pos_edge_type), int(a), p_), records if hydrate_pos else None, True)]
+        ee = [e for k in sorted(eset) for e in _typed_join(k, records if hydrate_edges else None, False)]
+        out[int(a)] = (sorted(pe, key=lambda e: (e[0], e[1], e[2], e[3] or ())), ee, sorted(nset))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # aggregate
 # ----------------------------------------------------------------------------------------

@@ -317,3 +317,115 @@ def test_typed_component_writes_rnn_per_node_type(tmp_path):
     for r in range(n_a):
         assert sorted((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"]) for e in got[r]["edges"]) == want[r][0]
         assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == want[r][1]
+    # main samples: supervision edge type paper -paper_to_author-> author; positives = OUTGOING sample over it from every paper
+    # (call 3 = after the paper DAG's two ops), neighbourhood = the paper's merged with the author DAG of its positive
+    roots = np.arange(n_p, dtype=np.int32)
+    pos, _ = O.np_sample_chain([outg(p2a)], roots, [1], [3])
+    paper_sets = O.np_assemble_dag_rnn(roots, 1, [dict(parent=-1, fanout=3, condensed_edge_type=0, result_node_type=0, nbr=ch[0]),
+                                                  dict(parent=0, fanout=2, condensed_edge_type=1, result_node_type=1, nbr=ch[1])])
+    want = O.np_assemble_typed_nablp(paper_sets, want, 0, {int(r): [int(pos[0][r])] for r in roots}, 1)
+    raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "out/nablp/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_nablp_sample, sio.split_tfrecords(raw, verify=True))}
+    assert sorted(got) == sorted(want) and stats["nablp"] == len(want) and 0 < len(want) <= n_p
+    for r, (wpe, we, wn) in want.items():
+        assert got[r]["root_node"]["condensed_node_type"] == 1
+        assert sorted((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"]) for e in got[r]["pos_edges"]) == [e[:3] for e in wpe]
+        assert sorted((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"]) for e in got[r]["edges"]) == [e[:3] for e in we]
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == wn
+
+
+def test_typed_component_hydrates_edge_features_and_isolated_anchors(tmp_path):
+    """user / item graph whose supervision edge type carries edge features and duplicate records: RootedNodeNeighborhoods
+    carry one Edge per record, main samples one per key, pos_edges one per record; shouldIncludeIsolatedNodesInTraining
+    keeps the anchors without a positive; an op with two input ops."""
+    from helpers import tf_example, tfrecord_bytes
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(19)
+    n_u, n_i = 36, 20
+    n = max(n_u, n_i)
+    follows = (rng.integers(0, n_u, 160), rng.integers(0, n_u, 160))
+    clicks = (rng.integers(0, n_u // 2, 120), rng.integers(0, n_i, 120))  # the upper half of the users never clicks: isolated anchors
+    clicks[0][90:] = clicks[0][:30]
+    clicks[1][90:] = clicks[1][:30]
+    cf = rng.standard_normal((120, 2)).astype(np.float32)
+    xu = rng.standard_normal((n_u, 2)).astype(np.float32)
+    for sub, recs in (("nodes_user", [tf_example({"node_id": int(i), "f": xu[i].tolist()}) for i in range(n_u)]),
+                      ("nodes_item", [tf_example({"node_id": int(i)}) for i in range(n_i)]),
+                      ("edges_follows", [tf_example({"src": int(u), "dst": int(v)}) for u, v in zip(*follows)]),
+                      ("edges_clicks", [tf_example({"src": int(u), "dst": int(v), "w": cf[j].tolist()}) for j, (u, v) in enumerate(zip(*clicks))])):
+        os.makedirs(tmp_path / sub, exist_ok=True)
+        (tmp_path / sub / "data.tfrecord").write_bytes(tfrecord_bytes(recs))
+    et0 = {"srcNodeType": "user", "relation": "follows", "dstNodeType": "user"}
+    et1 = {"srcNodeType": "user", "relation": "clicks", "dstNodeType": "item"}
+    meta = {"condensedNodeTypeToPreprocessedMetadata": {
+                "0": {"nodeIdKey": "node_id", "featureKeys": ["f"], "tfrecordUriPrefix": "nodes_user"},
+                "1": {"nodeIdKey": "node_id", "tfrecordUriPrefix": "nodes_item"}},
+            "condensedEdgeTypeToPreprocessedMetadata": {
+                "0": {"srcNodeIdKey": "src", "dstNodeIdKey": "dst", "mainEdgeInfo": {"tfrecordUriPrefix": "edges_follows"}},
+                "1": {"srcNodeIdKey": "src", "dstNodeIdKey": "dst", "mainEdgeInfo": {"tfrecordUriPrefix": "edges_clicks", "featureKeys": ["w"]}}}}
+    paths = [{"rootNodeType": "user", "samplingOps": [
+                 {"opName": "liked", "edgeType": et1, "randomUniform": {"numNodesToSample": 2}, "samplingDirection": "OUTGOING"},
+                 {"opName": "friends", "edgeType": et0, "randomUniform": {"numNodesToSample": 2}},
+                 {"opName": "co_clickers", "edgeType": et1, "inputOpNames": ["liked"], "randomUniform": {"numNodesToSample": 2}},
+                 {"opName": "fans", "edgeType": et0, "inputOpNames": ["friends", "co_clickers"], "randomUniform": {"numNodesToSample": 2}}]},
+             {"rootNodeType": "item", "samplingOps": [
+                 {"opName": "clickers", "edgeType": et1, "randomUniform": {"numNodesToSample": 3}}]}]
+    cfg = {"graphMetadata": {"condensedEdgeTypeMap": {"0": et0, "1": et1}, "condensedNodeTypeMap": {"0": "user", "1": "item"},
+                             "edgeTypes": [et0, et1], "nodeTypes": ["user", "item"]},
+           "taskMetadata": {"nodeAnchorBasedLinkPredictionTaskMetadata": {"supervisionEdgeTypes": [et1]}},
+           "datasetConfig": {"subgraphSamplerConfig": {"numPositiveSamples": 2, "subgraphSamplingStrategy": {"messagePassingPaths": {"paths": paths}}}},
+           "sharedConfig": {"isGraphDirected": True, "preprocessedMetadataUri": "preprocessed_metadata.yaml",
+                            "shouldIncludeIsolatedNodesInTraining": True,
+                            "flattenedGraphMetadata": {"nodeAnchorBasedLinkPredictionOutput": {
+                                "tfrecordUriPrefix": "out/nablp/",
+                                "nodeTypeToRandomNegativeTfrecordUriPrefix": {"user": "out/rnn/user/", "item": "out/rnn/item/"}}}}}
+    (tmp_path / "preprocessed_metadata.yaml").write_text(yaml.safe_dump(meta))
+    (tmp_path / "frozen_gbml_config.yaml").write_text(yaml.safe_dump(cfg))
+    stats = subgraph_sampler.run("frozen_gbml_config.yaml", "typed_ef_job", None, root=str(tmp_path), batch_roots=16, log=lambda *_: None)
+    assert stats["rnn_per_node_type"] == {"user": n_u, "item": n_i} and stats["nablp"] == n_u
+    inc = lambda e: O.np_build_in_csr(e[0], e[1], n, True)  # noqa: E731
+    outg = lambda e: O.np_build_in_csr(e[1], e[0], n, True)  # noqa: E731
+    records = O.np_typed_edge_records({0: (follows[0], follows[1], None), 1: (clicks[0], clicks[1], cf)})
+    users = np.arange(n_u, dtype=np.int32)
+    liked, _ = O.np_sample_chain([outg(clicks)], users, [2], [1])
+    friends, _ = O.np_sample_chain([inc(follows)], users, [2], [2])
+    co, _ = O.np_sample_chain([outg(clicks), inc(clicks)], users, [2, 2], [1, 3])
+    fans_a, _ = O.np_sample_chain([inc(follows), inc(follows)], users, [2, 2], [2, 4])
+    fans_b, _ = O.np_sample_chain([outg(clicks), inc(clicks), inc(follows)], users, [2, 2, 2], [1, 3, 4])
+    uops = [dict(parent=-1, fanout=2, condensed_edge_type=1, result_node_type=1, outgoing=True, nbr=liked[0]),
+            dict(parent=-1, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=friends[0]),
+            dict(parent=0, fanout=2, condensed_edge_type=1, result_node_type=0, nbr=co[1]),
+            dict(parent=1, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=fans_a[1]),
+            dict(parent=2, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=fans_b[2])]
+    items = np.arange(n_i, dtype=np.int32)
+    clk, _ = O.np_sample_chain([inc(clicks)], items, [3], [1])
+    iops = [dict(parent=-1, fanout=3, condensed_edge_type=1, result_node_type=0, nbr=clk[0])]
+    user_sets, item_sets = O.np_assemble_dag_rnn(users, 0, uops), O.np_assemble_dag_rnn(items, 1, iops)
+
+    def canon(sample, key="edges"):
+        return sorted(((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"], tuple(np.float32(e["feature_values"]).tolist()) or None)
+                       for e in sample[key]), key=lambda e: (e[0], e[1], e[2], e[3] or ()))
+
+    # RootedNodeNeighborhoods: the user DAG's root ops include `clicks` (features) -> edges hydrated, one per record
+    want = O.np_hydrate_typed_rnn(user_sets, records)
+    raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "out/rnn/user/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_sample, sio.split_tfrecords(raw, verify=True))}
+    dup = 0
+    for r in range(n_u):
+        assert canon(got[r]) == want[r][0] and sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == want[r][1]
+        dup += len(want[r][0]) - len({e[:3] for e in want[r][0]})
+    assert dup > 0
+    # main samples: positives = 2 OUTGOING clicks per user, drawn as call 5 (after the user DAG's four ops)
+    pos, pcnt = O.np_sample_chain([outg(clicks)], users, [2], [5])
+    want = O.np_assemble_typed_nablp(user_sets, item_sets, 1, {int(r): pos[0][2 * r:2 * r + 2].tolist() for r in users}, 1, records,
+                                     include_isolated=True)
+    raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "out/nablp/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_nablp_sample, sio.split_tfrecords(raw, verify=True))}
+    assert sorted(got) == list(range(n_u)) and (pcnt[0] == 0).any()
+    for r, (wpe, we, wn) in want.items():
+        assert canon(got[r], "pos_edges") == wpe
+        assert canon(got[r]) == sorted(we, key=lambda e: (e[0], e[1], e[2], e[3] or ()))
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == wn

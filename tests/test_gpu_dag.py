@@ -70,12 +70,50 @@ def test_linear_chain_of_ops_equals_khop():
         assert torch.equal(res[name][0], nbr[h]) and torch.equal(res[name][1], cnt[h])
 
 
+def test_op_with_several_inputs_runs_once_per_input():
+    """An op with two input ops expands the union of their result nodes (GraphDBSampler.scala:66-82): one instance per
+    input, each equal to the oracle's chain through that input; a child of such an op has one instance per instance."""
+    import torch
+    from gigl_b200 import Context, Graph, dag
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(13)
+    n, n_user, et = _typed_graph(rng)
+    ctx = Context.on_torch_stream(0)
+    follows, shown, clicks = ("user", "follows", "user"), ("item", "shown_to", "user"), ("user", "clicks", "item")
+    ops = [dag.SamplingOp("friends", follows, 3),
+           dag.SamplingOp("seen", shown, 2),
+           dag.SamplingOp("clickers", clicks, 2, ["seen"]),
+           dag.SamplingOp("mixed", follows, 2, ["friends", "clickers"]),
+           dag.SamplingOp("deep", shown, 2, ["mixed"])]
+    planned = dag.plan(ops, "user")
+    assert [p.key for p in planned] == ["friends", "seen", "clickers", "mixed@friends", "mixed@clickers", "deep@mixed@friends",
+                                        "deep@mixed@clickers"]
+    assert [p.call_no for p in planned] == [1, 2, 3, 4, 4, 5, 5]
+    graphs = {(k, dag.INCOMING): Graph.from_edges_host(ctx, n, s, d, is_graph_directed=True) for k, (s, d) in et.items()}
+    csr = {k: O.np_build_in_csr(s, d, n, True) for k, (s, d) in et.items()}
+    roots = np.arange(0, n_user, 2, dtype=np.int32)
+    res = dag.sample_dag(graphs, torch.from_numpy(roots).cuda(), ops, "user")
+    ctx.sync()
+    by_key = {p.key: p for p in planned}
+    for p in planned:
+        chain = [by_key[k] for k in p.chain]
+        want_nbr, want_cnt = O.np_sample_chain([csr[c.op.edge_type] for c in chain], roots, p.fanouts, [c.call_no for c in chain])
+        assert np.array_equal(res[p.key][0].cpu().numpy(), want_nbr[-1]), p.key
+        assert np.array_equal(res[p.key][1].cpu().numpy(), want_cnt[-1]), p.key
+    assert (res["deep@mixed@clickers"][1].cpu().numpy() > 0).any()
+    enc = dag.encoder_ops(planned, res, {follows: 0, shown: 1, clicks: 2}, {"user": 0, "item": 1})
+    assert [o["parent"] for o in enc] == [-1, -1, 1, 0, 2, 3, 4]
+
+
 def test_plan_rejects_unsupported_dags():
     from gigl_b200 import dag
 
     et = ("user", "follows", "user")
     with pytest.raises(ValueError):
-        dag.plan([dag.SamplingOp("a", et, 2), dag.SamplingOp("b", et, 2), dag.SamplingOp("c", et, 2, ["a", "b"])], "user")
+        dag.plan([dag.SamplingOp("a", et, 2), dag.SamplingOp("c", et, 2, ["a", "a"])], "user")  # the same input twice
+    with pytest.raises(ValueError):
+        dag.plan([dag.SamplingOp("a", et, 2), dag.SamplingOp("c", et, 2, ["a", "nope"])], "user")
     with pytest.raises(ValueError):
         dag.plan([dag.SamplingOp("a", ("item", "shown_to", "user"), 2), dag.SamplingOp("b", et, 2, ["a"])], "user")  # b expands users, a yields items
     with pytest.raises(ValueError):

@@ -262,3 +262,115 @@ def test_typed_rnn_from_a_sampling_op_dag_matches_the_restated_union():
         # an OUTGOING op's edges point away from the frontier: user (friend) -> item over `clicks`
         n_out_edges += sum(1 for t, a, b in we if t == 2 and (0, a) in wn and (1, b) in wn)
     assert n_out_edges > 0
+
+
+def _typed_fixture(seed=33):
+    """user / item graph with three edge types; `clicks` carries 2 features and duplicate records, `follows` none."""
+    rng = np.random.default_rng(seed)
+    n_user, n_item, n = 40, 25, 40
+    et = {0: (rng.integers(0, n_user, 250), rng.integers(0, n_user, 250), None),                                   # user -follows-> user
+          1: (rng.integers(0, n_item, 200), rng.integers(0, n_user, 200), rng.standard_normal((200, 1)).astype(np.float32)),  # item -shown_to-> user
+          2: (rng.integers(0, n_user, 260), rng.integers(0, n_item, 260), rng.standard_normal((260, 2)).astype(np.float32))}  # user -clicks-> item
+    et[2][0][200:] = et[2][0][:60]  # duplicate (src, dst) records with their own feature rows
+    et[2][1][200:] = et[2][1][:60]
+    inc = {t: O.np_build_in_csr(e[0], e[1], n, True) for t, e in et.items()}
+    outg = {t: O.np_build_in_csr(e[1], e[0], n, True) for t, e in et.items()}
+    tabs = [sio.HostEdgeTable(inc[t], np_edge_rows(et[t][0], et[t][1], n, True), et[t][2]) for t in range(3)]
+    xu = rng.standard_normal((n, 3)).astype(np.float32)
+    xi = rng.standard_normal((n, 5)).astype(np.float32)
+    return n_user, n_item, n, et, inc, outg, tabs, xu, xi
+
+
+def _typed_edges(sample, key="edges"):
+    return sorted(((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"], _feat(None, e["feature_values"]) or None)
+                   for e in sample[key]), key=lambda e: (e[0], e[1], e[2], e[3] or ()))
+
+
+def _user_dag(inc, outg, roots):
+    """friends (1), seen (2), clickers <- seen (3), mixed <- {friends, clickers} over follows (4, two instances),
+    their_clicks <- friends OUTGOING over clicks (5)."""
+    friends, _ = O.np_sample_chain([inc[0]], roots, [3], [1])
+    seen, _ = O.np_sample_chain([inc[1]], roots, [2], [2])
+    clickers, _ = O.np_sample_chain([inc[1], inc[2]], roots, [2, 2], [2, 3])
+    mixed_a, _ = O.np_sample_chain([inc[0], inc[0]], roots, [3, 2], [1, 4])
+    mixed_b, _ = O.np_sample_chain([inc[1], inc[2], inc[0]], roots, [2, 2, 2], [2, 3, 4])
+    their, _ = O.np_sample_chain([inc[0], outg[2]], roots, [3, 2], [1, 5])
+    return [dict(parent=-1, fanout=3, condensed_edge_type=0, result_node_type=0, nbr=friends[0]),
+            dict(parent=-1, fanout=2, condensed_edge_type=1, result_node_type=1, nbr=seen[0]),
+            dict(parent=1, fanout=2, condensed_edge_type=2, result_node_type=0, nbr=clickers[1]),
+            dict(parent=0, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=mixed_a[1]),
+            dict(parent=2, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=mixed_b[2]),
+            dict(parent=0, fanout=2, condensed_edge_type=2, result_node_type=1, outgoing=True, nbr=their[1])]
+
+
+def test_typed_rnn_edge_hydration_and_multi_input_ops():
+    """Typed RootedNodeNeighborhoods with the LEFT JOIN against per-type edge records (SGSTask.scala:243-262): one Edge per
+    matching record, features of the record; an op with two input ops contributes the union of its two instances."""
+    n_user, n_item, n, et, inc, outg, tabs, xu, xi = _typed_fixture()
+    roots = np.arange(n_user, dtype=np.int32)
+    ops = _user_dag(inc, outg, roots)
+    records = O.np_typed_edge_records(et)
+    want = O.np_hydrate_typed_rnn(O.np_assemble_dag_rnn(roots, 0, ops), records)
+    data, offs = sio.encode_typed_samples(roots, 0, ops, [xu, xi], tabs, kind="rnn")
+    recs = sio.split_tfrecords(data, verify=True)
+    assert len(recs) == n_user and offs[-1] == len(data)
+    multi = dup = 0
+    for r, rec in zip(roots, recs):
+        s = sio.parse_sample(rec)
+        we, wn = want[int(r)]
+        assert _typed_edges(s) == we
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in s["nodes"]) == wn
+        keys = [e[:3] for e in we]
+        dup += len(keys) - len(set(keys))
+        a = {int(c) for c in ops[3]["nbr"][r * 6:(r + 1) * 6] if c >= 0}
+        b = {int(c) for c in ops[4]["nbr"][r * 8:(r + 1) * 8] if c >= 0}
+        multi += bool(a - b) and bool(b - a)
+        assert {(0, v) for v in a | b} <= set(wn)
+    assert dup > 0 and multi > 0  # duplicate records were joined; both instances of the two-input op contributed
+    # hydration switched off: the same keys, no features, one Edge per key
+    data0, _ = sio.encode_typed_samples(roots, 0, ops, [xu, xi], tabs, kind="rnn", hydrate_edges=False)
+    plain, _ = sio.encode_dag_samples(roots, 0, ops, [xu, xi])
+    assert data0 == plain
+
+
+@pytest.mark.parametrize("include_isolated", [False, True])
+def test_typed_nablp_assembly_matches_the_restated_merge(include_isolated):
+    """The typed task's main samples: supervision edge type user -clicks-> item; positives = OUTGOING sample over clicks;
+    neighbourhood = anchor's DAG merged by key with the item DAG of every positive."""
+    n_user, n_item, n, et, inc, outg, tabs, xu, xi = _typed_fixture(seed=34)
+    roots = np.arange(n_user, dtype=np.int32)
+    ops = _user_dag(inc, outg, roots)
+    num_pos = 2
+    pos, pcnt = O.np_sample_chain([outg[2]], roots, [num_pos], [len(ops) + 1])
+    pos = pos[0].reshape(n_user, num_pos)
+    assert (pcnt[0] == 0).any() and (pcnt[0] > 0).any()
+    # item DAG: clickers of the item (1), then what those users were shown (2)
+    items = np.unique(pos[pos >= 0]).astype(np.int32)
+    items = items[items % 5 != 0]  # some positives have no tree in this call: they contribute the node alone
+    t1, _ = O.np_sample_chain([inc[2]], items, [2], [1])
+    t2, _ = O.np_sample_chain([inc[2], inc[1]], items, [2, 2], [1, 2])
+    tops = [dict(parent=-1, fanout=2, condensed_edge_type=2, result_node_type=0, nbr=t1[0]),
+            dict(parent=0, fanout=2, condensed_edge_type=1, result_node_type=1, nbr=t2[1])]
+    tree = np.where(pos >= 0, np.searchsorted(items, np.maximum(pos, 0)), -1)
+    tree = np.where((tree >= 0) & (tree < len(items)) & (items[np.minimum(tree, len(items) - 1)] == pos), tree, -1)
+    records = O.np_typed_edge_records(et)
+    want = O.np_assemble_typed_nablp(O.np_assemble_dag_rnn(roots, 0, ops), O.np_assemble_dag_rnn(items, 1, tops), 1,
+                                     {int(r): pos[i].tolist() for i, r in enumerate(roots)}, 2, records, include_isolated=include_isolated)
+    data, offs = sio.encode_typed_samples(roots, 0, ops, [xu, xi], tabs, kind="nablp", pos=pos, pos_tree=tree, pos_condensed_edge_type=2,
+                                          target_roots=items, target_node_type=1, target_ops=tops, include_isolated=include_isolated)
+    got = {}
+    for rec in sio.split_tfrecords(data, verify=True):
+        s = sio.parse_nablp_sample(rec)
+        got[s["root_node"]["node_id"]] = s
+    assert sorted(got) == sorted(want)
+    assert (len(got) == n_user) == include_isolated
+    assert int((np.diff(offs) > 0).sum()) == len(got)
+    for a, (wpe, we, wn) in want.items():
+        s = got[a]
+        assert np.array_equal(np.float32(s["root_node"]["feature_values"]), xu[a]) and s["root_node"]["condensed_node_type"] == 0
+        assert _typed_edges(s, "pos_edges") == wpe
+        assert _typed_edges(s) == sorted(we, key=lambda e: (e[0], e[1], e[2], e[3] or ()))
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in s["nodes"]) == wn
+        assert not s["hard_neg_edges"] and not s["neg_edges"]
+        for v in s["nodes"]:
+            assert np.array_equal(np.float32(v["feature_values"]), (xu if v["condensed_node_type"] == 0 else xi)[v["node_id"]])
