@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--shard-features", action="store_true",
                     help="features sharded by node range over the N GPUs and mapped as one flat table (remote rows over NVLink) "
                          "instead of replicated")
+    ap.add_argument("--halo", default="staged", choices=["staged", "direct"],
+                    help="--shard-features only: 'staged' copies each unique batch node's row into local HBM once per step and "
+                         "gathers from the copy; 'direct' loads one (mostly remote) row per unique edge inside the gather kernel")
     return ap.parse_args()
 
 
@@ -130,6 +133,34 @@ def measured_peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """N > 1 only: pins this rank's threads to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is
+    allocated, so the e2e path's host buffers live on the socket the GPU's PCIe link hangs off (with 8 ranks placed by
+    the scheduler, half of the device-to-host copies otherwise cross the socket interconnect).  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        idx = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[device_index])
+            except (ValueError, IndexError):
+                idx = device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {w * 64 + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 from gigl_b200.sharding import max_over_ranks, root_batches  # noqa: E402
@@ -231,8 +262,10 @@ def workload_config(args, wl, fan, batch, note):
     residency = ("whole CSR + feature table resident in HBM on every GPU (replicated); roots sharded by contiguous id range"
                  if not getattr(args, "shard_features", False) else
                  "CSR replicated; feature table sharded by contiguous node range over the GPUs and mapped as one flat array "
-                 "(cuMemMap of peer shards, rows pitched to 128-byte multiples): remote neighbour rows are loaded over NVLink "
-                 "inside the gather kernel")
+                 "(cuMemMap of peer shards, rows pitched to 128-byte multiples): " +
+                 ("the row of every unique batch node is copied over NVLink into a per-batch table once per step (halo staging), "
+                  "layer 1 gathers from the copy" if getattr(args, "halo", "staged") == "staged" else
+                  "remote neighbour rows are loaded over NVLink inside the gather kernel, one per unique edge"))
     edges = (f"{wl['pairs']} directed edges (duplicates kept)" if wl["directed"] else
              f"{wl['pairs']} undirected pairs de-duplicated+mirrored")
     return {"workload": f"BASELINE.json {wl['cfg']} shape: {args.workload} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
@@ -254,6 +287,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None  # before CUDA / pinned allocations
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -289,6 +323,8 @@ def run_ours(args):
     g.set_features(x)
     model = SageModel(ctx, layers)
     batch = Batch(ctx, wl["nodes"])
+    if args.shard_features and args.halo == "staged":
+        batch.set_halo_staging(True)
     ctx.sync()
     torch.cuda.empty_cache()
 
@@ -408,7 +444,7 @@ def run_ours(args):
         ms_e = max_over_ranks(ms_e, dev)
         d2h = B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin)
         e2e = {"value": world * B * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e / K, "api": "gigl_infer_khop_sage_host (roots in pinned host memory -> padded-tree index sets + "
+               "ms_per_step": ms_e / K, "host_cpus_bound": numa_cpus, "api": "gigl_infer_khop_sage_host (roots in pinned host memory -> padded-tree index sets + "
                                               "root embeddings back in pinned host memory)"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------

@@ -716,6 +716,58 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
     }
 }
 
+
+// ---- remote-neighbour feature halo -------------------------------------------------------------------
+// With the feature table sharded over the box (shared_table.cu) a batch node's row may live in a peer's HBM.  The
+// layer-1 gather reads one source row per unique EDGE; staging reads one row per unique NODE: xb[l, :] = x[list[l], :]
+// for every local id l, local or over NVLink, after which the gather runs on local memory through `lid`.  One warp per
+// row, U rows per warp in flight (a remote row is a ~2 us round trip; 148 SMs x 64 warps x 4 rows x 400 B ~ 15 MB
+// in flight).
+template <int CPL>
+__global__ void __launch_bounds__(256) halo_stage_kernel(const int32_t* __restrict__ n_nodes_dev, int64_t row_cap, int F,
+                                                         const int32_t* __restrict__ list, const float* __restrict__ x,
+                                                         int64_t ldx, float* __restrict__ xb, int64_t ldb) {
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    int64_t n = *n_nodes_dev;
+    if (n > row_cap) n = row_cap;
+    const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * U; r0 < n; r0 += W * U) {
+        int32_t v[U];
+        float4 val[U][CPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (r0 + u < n) ? __ldg(list + r0 + u) : -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int c = (q * 32 + lane) * 4;
+                val[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v[u] >= 0 && c < F) val[u][q] = ldg4(x + (int64_t)v[u] * ldx + c);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int c = (q * 32 + lane) * 4;
+                if (v[u] >= 0 && c < F) *reinterpret_cast<float4*>(xb + (r0 + u) * ldb + c) = val[u][q];
+            }
+    }
+}
+
+__global__ void __launch_bounds__(256) halo_stage_scalar_kernel(const int32_t* __restrict__ n_nodes_dev, int64_t row_cap, int F,
+                                                                const int32_t* __restrict__ list, const float* __restrict__ x,
+                                                                int64_t ldx, float* __restrict__ xb, int64_t ldb) {
+    int64_t n = *n_nodes_dev;
+    if (n > row_cap) n = row_cap;
+    const int lane = threadIdx.x & 31;
+    const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += W) {
+        const int32_t v = __ldg(list + r);
+        for (int c = lane; c < F; c += 32) xb[r * ldb + c] = __ldg(x + (int64_t)v * ldx + c);
+    }
+}
+
 }  // namespace gigl
 
 // =================================================================================================
@@ -744,6 +796,7 @@ struct gigl_batch {
     bool dirty = false;
     int64_t level_end_host[GIGL_MAX_HOPS + 2] = {};
     int64_t n_valid_host = 0, n_unique_host = 0;
+    bool halo_staging = false;  // layer 1 reads a per-batch copy of the unique nodes' rows (batch_set_halo_staging)
 };
 
 static constexpr int kCtrInts = 32;
@@ -1026,12 +1079,40 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
     float* hbuf[2] = {(float*)pH, (float*)pH + h_elems};
     const float* xin = x_dev;
     int64_t ldx = ldx0;
+    bool staged = false;
+    if (b->halo_staging) {
+        // every batch node gets a local id (the levels above stop at what the root outputs need), then one row per node
+        int64_t n_nodes = 0;
+        if ((rc = batch_finalize_nodes(b, &n_nodes, nullptr)) != GIGL_OK) return rc;
+        const int F0 = m->dims[0];
+        const int64_t ldb = (F0 + 3) & ~3;
+        void* pX = nullptr;
+        if ((rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, sizeof(float) * (size_t)(n_nodes > 0 ? n_nodes : 1) * ldb, &pX)) != GIGL_OK) return rc;
+        float* xb = (float*)pX;
+        const int32_t* n_dev = b->d_ctr + kLevelBase + b->n_levels_done;
+        const unsigned sgrid = (unsigned)(ctx->sm_count * 8);
+        int th = gigl_timer_begin(ctx, GIGL_T_HALO_STAGE);
+        const bool vec = (F0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) && (ldx0 % 4 == 0);
+        if (vec && F0 <= 128)
+            halo_stage_kernel<1><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+        else if (vec && F0 <= 256)
+            halo_stage_kernel<2><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+        else if (vec && F0 <= 512)
+            halo_stage_kernel<4><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+        else
+            halo_stage_scalar_kernel<<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+        GIGL_LAUNCHED(ctx);
+        gigl_timer_end(ctx, th);
+        xin = xb;
+        ldx = ldb;
+        staged = true;
+    }
     for (int l = 1; l <= n_layers; ++l) {
         const int Fi = m->dims[l - 1], Fo = m->dims[l];
         const int64_t rows = b->level_end_host[n_layers - l + 1];
         const int32_t* rows_dev = b->d_ctr + kLevelBase + (n_layers - l + 1);
         const int64_t lda = m->ldw[l - 1];
-        const int32_t* lidmap = (l == 1) ? nullptr : b->lid;
+        const int32_t* lidmap = (l == 1 && !staged) ? nullptr : b->lid;
         const int wpb = 8;
         const int64_t gfull = ceil_div64(rows, wpb), gcap = (int64_t)ctx->sm_count * 3;  // 80 registers -> 3 CTAs per SM
         const unsigned grid = (unsigned)(gfull < gcap ? gfull : gcap);  // persistent warps (grid-stride over rows)
@@ -1111,6 +1192,8 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
 }
 
 gigl_ctx* batch_ctx(gigl_batch* b) { return b->ctx; }
+
+void batch_set_halo_staging(gigl_batch* b, bool enabled) { b->halo_staging = enabled; }
 
 namespace gigl {
 // compacted unique keys (dst << 32 | src, global ids) -> edge_index rows in local ids

@@ -82,7 +82,7 @@ void gigl_timer_end(gigl_ctx* ctx, int handle) {
 }
 
 static const char* kTimerNames[GIGL_T_COUNT] = {"sample", "collate_keys", "collate_sort", "collate_maps", "gather_l1",
-                                                "gather_deep", "gemm_l1", "gemm_deep", "gather_full", "gemm_full"};
+                                                "gather_deep", "gemm_l1", "gemm_deep", "gather_full", "gemm_full", "halo_stage"};
 
 static int ctx_check_device_error(gigl_ctx* ctx) {
     GIGL_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -807,6 +807,12 @@ int gigl_batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges)
     if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
     GIGL_CUDA(batch_ctx(b), cudaSetDevice(batch_ctx(b)->device));
     return batch_finalize_nodes(b, n_nodes, n_edges);
+}
+
+int gigl_batch_set_halo_staging(gigl_batch* b, int32_t enabled) {
+    if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
+    batch_set_halo_staging(b, enabled != 0);
+    return GIGL_OK;
 }
 
 int gigl_batch_export_dev(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev) {

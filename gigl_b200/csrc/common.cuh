@@ -33,6 +33,7 @@ enum {
     GIGL_T_GEMM_DEEP,      // projections of layers >= 2
     GIGL_T_GATHER_FULL,    // full-graph gather (gigl_sage_conv_dev / gigl_gather_mean_dev)
     GIGL_T_GEMM_FULL,
+    GIGL_T_HALO_STAGE,     // per-batch copy of the unique nodes' feature rows (sharded feature table: the NVLink halo)
     GIGL_T_COUNT
 };
 
@@ -166,6 +167,7 @@ void batch_destroy(gigl_batch* b);
 int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
                   const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes_host, int64_t* n_edges_host);
 int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges);
+void batch_set_halo_staging(gigl_batch* b, bool enabled);
 int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev);
 int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx, float* out_dev);
 gigl_ctx* batch_ctx(gigl_batch* b);

@@ -469,6 +469,11 @@ class Batch:
         self._device = roots.device
         return self.level_sizes
 
+    def set_halo_staging(self, enabled: bool) -> None:
+        """Sharded feature table: copy every unique batch node's row into local HBM once (one row per node over NVLink)
+        and let layer 1 gather from that copy, instead of one peer load per unique edge (gigl_batch_set_halo_staging)."""
+        check(self.ctx._L.gigl_batch_set_halo_staging(self.handle, int(bool(enabled))), self.ctx.handle)
+
     def sage_forward(self, model: SageModel, x, out=None):
         import torch
 

@@ -376,6 +376,15 @@ int gigl_batch_export_dev(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_in
  */
 int gigl_batch_sage_forward_dev(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx,
                                 float* out_dev);
+/*
+ * The remote-neighbour feature halo of a sharded feature table (gigl_shared_table_*).  Off
+ * (default): the layer-1 gather loads every source row straight from x_dev - one row per unique batch EDGE, remote rows
+ * over NVLink.  On: gigl_batch_sage_forward_dev first copies the row of every unique batch NODE into a per-batch table in
+ * local HBM (one row per node crosses NVLink; this is the ids -> rows exchange an all_to_all halo performs, done with
+ * peer loads) and layer 1 gathers from that copy through the local-id map.  Same embeddings bit for bit; worth it when
+ * most rows are remote (a batch has several times more unique edges than unique nodes), a loss on a local table.
+ */
+int gigl_batch_set_halo_staging(gigl_batch* b, int32_t enabled);
 
 /*
  * One call from host buffers: roots (host) -> k-hop sample -> collate -> GraphSAGE forward ->

@@ -178,3 +178,37 @@ def test_large_batch_properties(env):
     ctx.sync()
     assert torch.equal(c, a[perm])
     assert bool(torch.isfinite(a).all())
+
+
+@pytest.mark.parametrize("F", [100, 37, 300])
+def test_halo_staging_gives_identical_embeddings(env, F):
+    """gigl_batch_set_halo_staging: layer 1 gathers from a per-batch copy of the unique nodes' rows (what a sharded feature
+    table uses to move one row per node over NVLink) - bit-identical to gathering from the table itself, and repeatable
+    across batches on one workspace."""
+    import torch
+
+    from gigl_b200 import SageModel, synth
+
+    ctx, dev = env
+    orc = _orc()
+    n, fan = 5000, [6, 4]
+    g, batch, rowptr, col, x, xt, rng = _setup(ctx, dev, n, 60000, F, False, 23)
+    layers = synth.sage_weights(rng, [F, 48, 9])
+    model = SageModel(ctx, layers)
+    for it in range(3):
+        roots = rng.permutation(n)[:400 + 50 * it].astype(np.int32)
+        roots_t = torch.from_numpy(roots).to(dev)
+        nbr, _ = g.sample_khop(roots_t, fan)
+        batch.set_halo_staging(False)
+        batch.collate(roots_t, fan, nbr, 2)
+        direct = batch.sage_forward(model, xt).clone()
+        batch.set_halo_staging(True)
+        staged = batch.sage_forward(model, xt).clone()       # same collation, staged layer 1
+        batch.collate(roots_t, fan, nbr, 2)
+        staged2 = batch.sage_forward(model, xt).clone()      # staging from a fresh collation
+        ctx.sync()
+        assert torch.equal(direct, staged) and torch.equal(direct, staged2)
+        onbr, _ = orc.c_sample_khop(rowptr, col, roots, fan)
+        ref = orc.batch_sage_embeddings(x, roots, onbr, fan, layers, f64=True)
+        assert _rel(staged.cpu().numpy(), ref) < RTOL
+    batch.set_halo_staging(False)

@@ -97,6 +97,9 @@ def _worker_body(rank, world, port, q):
     emb_sharded = b.sage_forward(model, t.table[:n]).clone()
     emb_replica = b.sage_forward(model, torch.from_numpy(x).cuda())
     same = bool(torch.equal(emb_sharded, emb_replica))  # same kernel, same order: bit-identical
+    b.set_halo_staging(True)  # one peer load per unique batch node, then a local gather: the same sums in the same order
+    emb_staged = b.sage_forward(model, t.table[:n])
+    same = same and bool(torch.equal(emb_staged, emb_replica))
     torch.cuda.synchronize()
     dist.barrier()
     q.put((rank, table_ok, same, int(roots.numel()), ""))
