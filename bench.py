@@ -372,12 +372,16 @@ def run_ours(args):
     # edges aggregated per step: layer 1 reduces every unique batch edge, layer 2 those into roots (untimed recount)
     e2_total = 0
     n1_total = 0
+    nodes_total = 0
+    sampled_total = 0
     for i in range(W, W + K):
         g.sample_khop(roots_dev[i], fan, out=(nbr, cnt))
         sizes = batch.collate(roots_dev[i], fan, nbr, 2)
         n1_total += sizes[1]
-        _, ei = batch.export()
+        node_ids, ei = batch.export()
         e2_total += int((ei[1] < B).sum().item())
+        nodes_total += int(node_ids.numel())
+        sampled_total += sum(int((t >= 0).sum().item()) for t in nbr)
     agg_edges = e1_total + e2_total
 
     # ---- roofline of the dominant kernel: the layer-1 gather ------------------------------------
@@ -471,6 +475,7 @@ def run_ours(args):
                                                                               ("gather_l1", "gather_deep", "gemm_l1", "gemm_deep")) * 1e-3),
                 "sample_only_subgraphs_per_sec": B / max(1e-9, phase_ms.get("sample", 0.0) * 1e-3),
                 "phase_ms_per_step": phase_ms, "unique_edges_per_step": e1_total / K, "layer1_rows_per_step": n1_total / K,
+                "batch_nodes_per_step": nodes_total / K, "sampled_edges_per_step": sampled_total / K,
                 "roofline": roofline, "full_graph_aggregate": full, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
     if table is not None:
