@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-graph", action="store_true")
+    ap.add_argument("--e2e-padded", action="store_true", help="e2e returns the padded-tree index sets instead of the packed form")
     ap.add_argument("--pitch-features", action="store_true", help="experiment: replicated feature rows pitched to 128-byte multiples")
     ap.add_argument("--shard-features", action="store_true",
                     help="features sharded by node range over the N GPUs and mapped as one flat table (remote rows over NVLink) "
@@ -426,30 +427,50 @@ def run_ours(args):
         del agg
 
     # ---- end to end through the host entry point (pinned host buffers, copies inside the timed region) ----
+    # index sets come back packed (one-byte counts + the filled slots only: same edges, ~2/3 of the bytes; --e2e-padded
+    # returns the padded tree instead)
     e2e = None
     if not args.no_e2e:
         roots_pin = [torch.from_numpy(b).pin_memory() for b in batches]
         out_pin = torch.empty((B, O_dim), dtype=torch.float32).pin_memory()
-        nbr_pin, cnt_pin, width = [], [], 1
+        nbr_pin, cnt_pin, cnt8_pin, width = [], [], [], 1
         for f in fan:
             cnt_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
+            cnt8_pin.append(torch.empty(B * width, dtype=torch.uint8).pin_memory())
             width *= f
             nbr_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
-        s_out = ([t.numpy() for t in nbr_pin], [t.numpy() for t in cnt_pin])
+        d2h_steps = []
+        if args.e2e_padded:
+            s_out = ([t.numpy() for t in nbr_pin], [t.numpy() for t in cnt_pin])
+
+            def host_step(i):
+                g.infer_khop_sage_host(batch, model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(), samples_out=s_out)
+                d2h_steps.append(B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin))
+        else:
+            packed_pin = torch.empty(sum(t.numel() for t in nbr_pin), dtype=torch.int32).pin_memory()
+            p_out = (packed_pin.numpy(), [t.numpy() for t in cnt8_pin])
+
+            def host_step(i):
+                _, packed, _ = g.infer_khop_sage_packed_host(batch, model, roots_pin[i].numpy(), fan, out=out_pin.numpy(), packed_out=p_out)
+                d2h_steps.append(B * O_dim * 4 + packed.size * 4 + sum(t.numel() for t in cnt8_pin))
         for i in range(W):
-            g.infer_khop_sage_host(batch, model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(), samples_out=s_out)
+            host_step(i)
+        d2h_steps.clear()
         barrier()
         ev0.record()
         for i in range(W, W + K):
-            g.infer_khop_sage_host(batch, model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(), samples_out=s_out)
+            host_step(i)
         ev1.record()
         barrier()
         ms_e = ev0.elapsed_time(ev1)  # device time on the launching stream (the host call itself is synchronous)
         ms_e = max_over_ranks(ms_e, dev)
-        d2h = B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin)
+        d2h = int(sum(d2h_steps) / max(len(d2h_steps), 1))
         e2e = {"value": world * B * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e / K, "host_cpus_bound": numa_cpus, "api": "gigl_infer_khop_sage_host (roots in pinned host memory -> padded-tree index sets + "
-                                              "root embeddings back in pinned host memory)"}
+               "ms_per_step": ms_e / K, "host_cpus_bound": numa_cpus,
+               "api": ("gigl_infer_khop_sage_host (roots in pinned host memory -> padded-tree index sets + root embeddings back in pinned "
+                       "host memory)" if args.e2e_padded else
+                       "gigl_infer_khop_sage_packed_host (roots in pinned host memory -> packed index sets [one-byte counts + filled "
+                       "slots] + root embeddings back in pinned host memory)")}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None

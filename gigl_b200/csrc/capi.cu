@@ -204,6 +204,8 @@ void gigl_ctx_destroy(gigl_ctx* ctx) {
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->copy_ready) cudaEventDestroy(ctx->copy_ready);
+    if (ctx->pack_ready) cudaEventDestroy(ctx->pack_ready);
+    if (ctx->h_pack_total) cudaFreeHost(ctx->h_pack_total);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -830,34 +832,46 @@ int gigl_batch_sage_forward_dev(gigl_batch* b, const gigl_sage_model* m, const f
     return batch_sage_forward(b, m, x_dev, ldx, out_dev);
 }
 
-int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots,
-                              int64_t n_roots, const int32_t* fanouts, int32_t n_hops, int32_t base_seed,
-                              int32_t first_call_no, float* out, int32_t* const* nbr, int32_t* const* cnt) {
+// Shared body of the two host entry points.  packed == nullptr: padded-tree index sets into nbr / cnt (either may be
+// NULL).  packed != nullptr: one-byte counts into cnt_u8[h] and the filled slots into packed (tree_pack.cu).
+static int infer_khop_sage_host_impl(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots, int64_t n_roots,
+                                     const int32_t* fanouts, int32_t n_hops, int32_t base_seed, int32_t first_call_no, float* out,
+                                     int32_t* const* nbr, int32_t* const* cnt, uint8_t* const* cnt_u8, int32_t* packed,
+                                     int64_t packed_cap, int64_t* n_packed) {
     if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
     gigl_ctx* ctx = g->ctx;
     GIGL_CHECK(ctx, b != nullptr && m != nullptr && batch_ctx(b) == ctx, "batch / model must belong to the graph's ctx");
     GIGL_CHECK(ctx, g->x != nullptr, "the graph holds no features (gigl_graph_set_features_*)");
     GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS && fanouts, "n_hops must be in [1, 8]");
     GIGL_CHECK(ctx, n_roots >= 0 && (roots || n_roots == 0) && (out || n_roots == 0), "bad roots / out");
+    const bool packing = packed != nullptr;
+    GIGL_CHECK(ctx, !packing || (cnt_u8 != nullptr && n_packed != nullptr && packed_cap >= 0), "packed output needs cnt_u8, n_packed");
     int32_t n_layers = 0, dims[GIGL_MAX_HOPS + 1];
     sage_model_dims(m, &n_layers, dims);
     GIGL_CHECK(ctx, dims[0] == g->F, "model input width != feature width");
+    if (n_packed) *n_packed = 0;
     if (n_roots == 0) return GIGL_OK;
     GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t total = (size_t)n_roots, width = 1;
+    // device layout: roots | cnt[0] .. cnt[H-1] (back to back: tree_pack scans them as one array) | nbr[0] .. nbr[H-1]
+    size_t total = (size_t)n_roots, width = 1, n_parents = 0;
     size_t off_cnt[GIGL_MAX_HOPS], off_nbr[GIGL_MAX_HOPS];
     for (int h = 0; h < n_hops; ++h) {
         GIGL_CHECK(ctx, fanouts[h] >= 1 && fanouts[h] <= GIGL_MAX_FANOUT, "fanout must be in [1, 128]");
         off_cnt[h] = total;
         total += (size_t)n_roots * width;
+        n_parents += (size_t)n_roots * width;
         width *= (size_t)fanouts[h];
         if ((double)n_roots * (double)width > 2147483647.0)
             return gigl_fail(ctx, GIGL_E_INVALID, "frontier exceeds 2^31-1 slots; split the roots");
+    }
+    width = 1;
+    for (int h = 0; h < n_hops; ++h) {
+        width *= (size_t)fanouts[h];
         off_nbr[h] = total;
         total += (size_t)n_roots * width;
     }
     void *buf = nullptr, *pout = nullptr;
-    int rc = gigl_scratch(ctx, GIGL_SLOT_IO0, sizeof(int32_t) * total, &buf);
+    int rc = gigl_scratch(ctx, GIGL_SLOT_IO0, sizeof(int32_t) * (total + 1), &buf);
     if (rc != GIGL_OK) return rc;
     const int O = dims[n_layers];
     if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO1, sizeof(float) * (size_t)n_roots * O, &pout)) != GIGL_OK) return rc;
@@ -869,12 +883,12 @@ int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_mode
         nbr_dev[h] = d + off_nbr[h];
         cnt_dev[h] = d + off_cnt[h];
     }
-    // The index sets (59.5 MB for B = 65536, [15, 10]) leave on a second stream while the aggregate runs.  Measured
-    // on B200: a device-to-host copy that overlaps the SAMPLER or the collation sort slows them by about the copy's
-    // own duration (both live on L2-resident tables - the 56 MB hash-key table, the radix-sort buffers - and the copy
-    // streams 48 MB through the same L2), while the gather / projection kernels stream gigabytes through L2 anyway.
+    // The index sets (59.5 MB for B = 65536, [15, 10]; ~40 MB packed) leave on a second stream while the aggregate runs.
+    // Measured on B200: a device-to-host copy that overlaps the SAMPLER or the collation sort slows them by about the
+    // copy's own duration (both live on L2-resident tables - the 56 MB hash-key table, the radix-sort buffers - and the
+    // copy streams 48 MB through the same L2), while the gather / projection kernels stream gigabytes through L2 anyway.
     // So the copies are released after collation and ride under the aggregate (0.9 ms of PCIe under 1.4 ms of kernels).
-    const bool copying = nbr && cnt;
+    const bool copying = packing || (nbr && cnt);
     static const bool dbg = getenv("GIGL_DEBUG_TIMELINE") != nullptr;
     cudaEvent_t ev[8] = {};
     if (dbg) {
@@ -885,19 +899,56 @@ int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_mode
         GIGL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         GIGL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ready, cudaEventDisableTiming));
     }
+    if (packing && !ctx->pack_ready) {
+        GIGL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pack_ready, cudaEventDisableTiming));
+        GIGL_CUDA(ctx, cudaMallocHost(&ctx->h_pack_total, sizeof(int32_t)));
+    }
     if ((rc = khop_sample_launch(g, d, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev)) != GIGL_OK) return rc;
     if (dbg) cudaEventRecord(ev[2], ctx->stream);
-    if ((rc = batch_collate(b, d, n_roots, fanouts, n_hops, nbr_dev, n_layers, nullptr, nullptr)) != GIGL_OK) return rc;
+    int32_t* goff_dev = nullptr;
+    uint8_t* u8_dev = nullptr;
+    int32_t* packed_dev = nullptr;
+    if (packing) {
+        // the pack kernels (one scan + ~70 MB of traffic, tens of microseconds) run on the copy stream beside the collation
+        GIGL_CUDA(ctx, cudaEventRecord(ctx->copy_ready, ctx->stream));
+        GIGL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ready, 0));
+        if ((rc = tree_pack_launch(ctx, ctx->copy_stream, n_roots, fanouts, n_hops, nbr_dev, cnt_dev[0], GIGL_SLOT_IO2, &goff_dev, &u8_dev,
+                                   &packed_dev)) != GIGL_OK)
+            return rc;
+        GIGL_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack_total, goff_dev + n_parents, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        GIGL_CUDA(ctx, cudaEventRecord(ctx->pack_ready, ctx->copy_stream));
+    }
+    if ((rc = batch_collate(b, d, n_roots, fanouts, n_hops, nbr_dev, n_layers, nullptr, nullptr)) != GIGL_OK) {
+        if (packing) cudaStreamSynchronize(ctx->copy_stream);
+        return rc;
+    }
     if (dbg) cudaEventRecord(ev[4], ctx->stream);
     if (copying) {
         GIGL_CUDA(ctx, cudaEventRecord(ctx->copy_ready, ctx->stream));
         GIGL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ready, 0));
         if (dbg) cudaEventRecord(ev[1], ctx->copy_stream);
-        width = 1;
-        for (int h = 0; h < n_hops; ++h) {
-            if (cnt[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(cnt[h], cnt_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            width *= (size_t)fanouts[h];
-            if (nbr[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(nbr[h], nbr_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (packing) {
+            GIGL_CUDA(ctx, cudaEventSynchronize(ctx->pack_ready));  // long done: the collation synchronised the main stream twice
+            const int64_t filled = *ctx->h_pack_total;
+            *n_packed = filled;
+            if (filled > packed_cap) return gigl_fail(ctx, GIGL_E_INVALID, "packed buffer too small for the sampled index sets");
+            size_t p0 = 0;
+            width = 1;
+            for (int h = 0; h < n_hops; ++h) {
+                const size_t parents = (size_t)n_roots * width;
+                if (cnt_u8[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(cnt_u8[h], u8_dev + p0, parents, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                p0 += parents;
+                width *= (size_t)fanouts[h];
+            }
+            if (filled > 0)
+                GIGL_CUDA(ctx, cudaMemcpyAsync(packed, packed_dev, sizeof(int32_t) * (size_t)filled, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        } else {
+            width = 1;
+            for (int h = 0; h < n_hops; ++h) {
+                if (cnt[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(cnt[h], cnt_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                width *= (size_t)fanouts[h];
+                if (nbr[h]) GIGL_CUDA(ctx, cudaMemcpyAsync(nbr[h], nbr_dev[h], sizeof(int32_t) * (size_t)n_roots * width, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
         }
         if (dbg) cudaEventRecord(ev[3], ctx->copy_stream);
     }
@@ -925,6 +976,21 @@ int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_mode
         for (auto& e : ev) cudaEventDestroy(e);
     }
     return ctx_check_device_error(ctx);
+}
+
+int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots,
+                              int64_t n_roots, const int32_t* fanouts, int32_t n_hops, int32_t base_seed,
+                              int32_t first_call_no, float* out, int32_t* const* nbr, int32_t* const* cnt) {
+    return infer_khop_sage_host_impl(g, b, m, roots, n_roots, fanouts, n_hops, base_seed, first_call_no, out, nbr, cnt, nullptr, nullptr, 0,
+                                     nullptr);
+}
+
+int gigl_infer_khop_sage_packed_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots, int64_t n_roots,
+                                     const int32_t* fanouts, int32_t n_hops, int32_t base_seed, int32_t first_call_no, float* out,
+                                     uint8_t* const* cnt_u8, int32_t* packed, int64_t packed_cap, int64_t* n_packed) {
+    if (g && !packed) return gigl_fail(g->ctx, GIGL_E_INVALID, "null packed buffer");
+    return infer_khop_sage_host_impl(g, b, m, roots, n_roots, fanouts, n_hops, base_seed, first_call_no, out, nullptr, nullptr, cnt_u8, packed,
+                                     packed_cap, n_packed);
 }
 
 }  // extern "C"

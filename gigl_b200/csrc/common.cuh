@@ -49,6 +49,8 @@ struct gigl_ctx {
     // second stream + event for device->host copies that overlap the kernels of the same call (host entry points)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ready = nullptr;
+    cudaEvent_t pack_ready = nullptr;   // the packed index sets (tree_pack.cu) are complete on copy_stream
+    int32_t* h_pack_total = nullptr;    // pinned: filled slots of the packed tree
     int sm_count = 148;
     int64_t launches = 0;
     std::string err;
@@ -158,6 +160,11 @@ int sage_conv_launch(gigl_ctx* ctx, int64_t n, int64_t n_rows_out, int32_t F, in
                      float* out, int32_t relu);
 int gcn_conv_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_t* rowptr, const int32_t* col,
                     const float* x, const float* W, const float* b, float* out, int32_t relu);
+
+// tree_pack.cu: padded tree -> goff (exclusive scan of the counts; goff[n_parents] = filled slots), one-byte counts, packed children
+int tree_pack_launch(gigl_ctx* ctx, cudaStream_t st, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
+                     const int32_t* const* nbr_dev, const int32_t* cnt_all_dev, int slot, int32_t** goff_dev, uint8_t** cnt_u8_dev,
+                     int32_t** packed_dev);
 
 // batch_collate.cu
 struct gigl_batch;

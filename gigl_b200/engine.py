@@ -390,6 +390,32 @@ class Graph:
                                                     n_hops, base_seed, first_call_no, _hp(out), pn, pc), self.ctx.handle)
         return (out, nbr, cnt) if return_samples else out
 
+    def infer_khop_sage_packed_host(self, batch: "Batch", model: "SageModel", roots, fanouts: Sequence[int], base_seed: int = 42,
+                                    first_call_no: int = 1, out=None, packed_out=None):
+        """As :meth:`infer_khop_sage_host` with the index sets PACKED (gigl_infer_khop_sage_packed_host): returns
+        (embeddings, packed int32 [n_filled], [cnt_u8 per hop]); :func:`unpack_tree` restores the padded layout.
+        packed_out = (packed buffer of capacity >= the tree's slot count, [cnt_u8 buffers]) to reuse (pinned) host memory."""
+        roots = _np(roots, np.int32)
+        fan = _np(fanouts, np.int32)
+        n_roots, n_hops = len(roots), len(fan)
+        if out is None:
+            out = np.empty((n_roots, model.dims[-1]), dtype=np.float32)
+        if packed_out is None:
+            cnt_u8, width, slots = [], 1, 0
+            for f in fan:
+                cnt_u8.append(np.empty(n_roots * width, dtype=np.uint8))
+                width *= int(f)
+                slots += n_roots * width
+            packed = np.empty(max(slots, 1), dtype=np.int32)
+        else:
+            packed, cnt_u8 = packed_out
+        pc = (C.c_void_p * n_hops)(*[a.ctypes.data for a in cnt_u8])
+        n_packed = C.c_int64()
+        check(self.ctx._L.gigl_infer_khop_sage_packed_host(self.handle, batch.handle, model.handle, _hp(roots), n_roots, _hp(fan), n_hops,
+                                                           base_seed, first_call_no, _hp(out), pc, _hp(packed), packed.size,
+                                                           C.byref(n_packed)), self.ctx.handle)
+        return out, packed[: n_packed.value], cnt_u8
+
     def close(self) -> None:
         if self.handle and self.ctx.handle:
             self.ctx._L.gigl_graph_destroy(self.handle)
@@ -400,6 +426,23 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+
+def unpack_tree(packed, cnt_u8: Sequence[np.ndarray], fanouts: Sequence[int]):
+    """Packed index sets (gigl_infer_khop_sage_packed_host) -> the padded tree of `Graph.sample_khop_host`:
+    (nbr per hop with -1 padding, cnt per hop as int32)."""
+    packed = np.asarray(packed, dtype=np.int32)
+    nbr, cnt, pos = [], [], 0
+    for c8, f in zip(cnt_u8, fanouts):
+        c = np.asarray(c8).astype(np.int32)
+        total = int(c.sum(dtype=np.int64))
+        lvl = np.full((len(c), int(f)), -1, dtype=np.int32)
+        lvl[np.arange(int(f), dtype=np.int32)[None, :] < c[:, None]] = packed[pos:pos + total]
+        pos += total
+        nbr.append(lvl.reshape(-1))
+        cnt.append(c)
+    assert pos == len(packed), "packed length does not match the counts"
+    return nbr, cnt
 
 
 class SageModel:

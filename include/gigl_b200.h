@@ -398,6 +398,20 @@ int gigl_infer_khop_sage_host(gigl_graph* g, gigl_batch* b, const gigl_sage_mode
                               int64_t n_roots, const int32_t* fanouts, int32_t n_hops, int32_t base_seed,
                               int32_t first_call_no, float* out, int32_t* const* nbr, int32_t* const* cnt);
 
+/*
+ * Same call, index sets returned PACKED (csrc/tree_pack.cu): cnt_u8[h][p] = number of children under parent slot p of
+ * hop h + 1 as one byte (fanout <= 128; n_roots * prod(fanouts[0..h-1]) entries), packed = the filled slots only - hop
+ * after hop, parent slots in order, each parent's children in the order of the padded layout (a parent's filled slots
+ * are its first cnt slots), *n_packed entries in all (<= packed_cap, else GIGL_E_INVALID).  The padded layout of
+ * gigl_sample_khop_host is recovered by writing each parent's cnt children back at slot p * fanout (gigl_b200.engine.
+ * unpack_tree).  Same sampled edges, ~2/3 of the bytes on the products-like graph: with 8 ranks on one host the
+ * device-to-host copies, not the GPUs, bound the end-to-end rate.  This is the un-padded Seq a
+ * KHopSamplerService.getKHopSubgraphForRootNodes returns (KHopSamplerService.scala:17-20).
+ */
+int gigl_infer_khop_sage_packed_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots, int64_t n_roots,
+                                     const int32_t* fanouts, int32_t n_hops, int32_t base_seed, int32_t first_call_no, float* out,
+                                     uint8_t* const* cnt_u8 /* [n_hops] host */, int32_t* packed, int64_t packed_cap, int64_t* n_packed);
+
 /* ---- the sampler's file contract: TFRecord + tf.Example + sample protos (host code) ----------- */
 
 /* masked crc32c of TFRecord framing: rotr15(crc32c(data)) + 0xA282EAD8 */

@@ -142,6 +142,41 @@ def test_host_entry_point_end_to_end(env):
     assert _rel(out, orc.batch_sage_embeddings(x, roots, onbr, fan, layers, f64=True)) < RTOL
 
 
+@pytest.mark.parametrize("fan,directed", [([10, 5], False), ([7], True), ([4, 3, 2], True), ([128, 2], False)])
+def test_host_entry_point_packed_index_sets(env, fan, directed):
+    """gigl_infer_khop_sage_packed_host: one-byte counts + the filled slots only; unpacking restores the padded tree of
+    the oracle exactly, the embeddings are those of the padded call bit for bit, and the call repeats on one workspace."""
+    from gigl_b200 import SageModel, synth, unpack_tree
+
+    ctx, dev = env
+    orc = _orc()
+    n = 3000
+    g, batch, rowptr, col, x, xt, rng = _setup(ctx, dev, n, 50000, 32, directed, 29)
+    g.set_features_host(x)
+    layers = synth.sage_weights(rng, [32, 24, 8])
+    model = SageModel(ctx, layers)
+    for step in range(2):
+        roots = rng.permutation(n)[:500 + 37 * step].astype(np.int32)
+        out_p, packed, cnt_u8 = g.infer_khop_sage_packed_host(batch, model, roots, fan)
+        out, nbr, cnt = g.infer_khop_sage_host(batch, model, roots, fan, return_samples=True)
+        assert np.array_equal(out, out_p)
+        onbr, ocnt = orc.c_sample_khop(rowptr, col, roots, fan)
+        unbr, ucnt = unpack_tree(packed, cnt_u8, fan)
+        assert len(packed) == sum(int((a >= 0).sum()) for a in onbr) and len(packed) < sum(len(a) for a in onbr)
+        for h in range(len(fan)):
+            assert cnt_u8[h].dtype == np.uint8
+            assert np.array_equal(unbr[h], onbr[h]) and np.array_equal(ucnt[h], ocnt[h])
+            assert np.array_equal(nbr[h], onbr[h]) and np.array_equal(cnt[h], ocnt[h])
+    # a packed buffer that is too small is an error, not a truncated result
+    from gigl_b200 import GiglError
+
+    small = (np.empty(10, dtype=np.int32), [np.empty(len(c), dtype=np.uint8) for c in cnt_u8])
+    with pytest.raises(GiglError):
+        g.infer_khop_sage_packed_host(batch, model, roots, fan, packed_out=small)
+    out2, _, _ = g.infer_khop_sage_packed_host(batch, model, roots, fan)  # the ctx is usable after the error
+    assert np.array_equal(out2, out_p)
+
+
 def test_large_batch_properties(env):
     """BASELINE-size style: 65k roots on a 1M-node power-law graph; size-independent properties:
     idempotence (bit-identical embeddings run to run despite atomics in the id assignment),
