@@ -379,6 +379,18 @@ __device__ __forceinline__ bool scan_threshold(const HopArgs& a, bool use_tab, u
     return true;
 }
 
+// The same scan over hash inputs x in [x_first, x_last], all below 2^31 (index-covered rows): 32-bit arithmetic only.
+__device__ __forceinline__ bool scan_threshold32(const HopArgs& a, bool use_tab, uint32_t base, uint32_t x_first, uint32_t x_last,
+                                                 uint64_t T, uint64_t* ck, int32_t* ci, int& c, int lane) {
+    for (uint32_t x0 = x_first; x0 <= x_last; x0 += 32) {
+        const uint32_t x = x0 + (uint32_t)lane;
+        uint64_t k = kKeyInf;
+        if (x <= x_last) k = use_tab ? __ldg(a.hk_table + x) : ordered_key((int32_t)x);
+        if (!push_cands(ck, ci, c, k < T, k, (int32_t)(x - base), lane)) return false;
+    }
+    return true;
+}
+
 // Returns true with best.key[0] / best.idx[0] = the row's keys in ascending order (>= f of them, or all).
 __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& best, int64_t size, uint32_t base, int f,
                                                  int lane, uint64_t* ck, int32_t* ci) {
@@ -386,37 +398,39 @@ __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& 
     if (m > 48.f) m = 48.f;
     uint64_t T = kKeyInf;
     if ((float)size > m) T = __float2ull_rz(m / (float)size * 18446744073709551616.0f);
-    const uint64_t lo = (uint64_t)base + 1, hi = (uint64_t)base + (uint64_t)size;
+    const uint64_t hi = (uint64_t)base + (uint64_t)size;
     const bool use_tab = a.hk_table != nullptr && hi < a.hk_limit;
     int c = 0;
     bool done = false;
     if (a.hx_keys != nullptr && hi < a.hx_limit) {
+        // Every hash input of the window lies below hx_limit <= 2^31: the window, its blocks and the candidates'
+        // positions are 32-bit quantities (ncu: 52 % of this kernel's issue slots were 64-bit index arithmetic).
+        const uint32_t lo32 = base + 1u, hi32 = (uint32_t)hi;
         const int lg = a.hx_l_log2;
-        const uint64_t b0 = (lo + ((1ULL << lg) - 1)) >> lg, b1 = (hi + 1) >> lg;  // full blocks [b0, b1)
+        const uint32_t b0 = (lo32 + ((1u << lg) - 1u)) >> lg, b1 = (hi32 + 1u) >> lg;  // full blocks [b0, b1)
         if (b0 < b1) {
-            const int64_t head_end = (int64_t)((b0 << lg) - lo);
-            const int64_t tail_begin = (int64_t)((b1 << lg) - (uint64_t)base);
-            if (!scan_threshold(a, use_tab, base, 1, head_end, T, ck, ci, c, lane)) return false;
-            if (!scan_threshold(a, use_tab, base, tail_begin, size, T, ck, ci, c, lane)) return false;
-            const int cap = a.hx_cap;
-            for (uint64_t bb = b0; bb < b1; bb += 32) {
-                const uint64_t myb = bb + lane;
+            if (!scan_threshold32(a, use_tab, base, lo32, (b0 << lg) - 1u, T, ck, ci, c, lane)) return false;   // head
+            if (!scan_threshold32(a, use_tab, base, b1 << lg, hi32, T, ck, ci, c, lane)) return false;          // tail
+            const uint32_t cap = (uint32_t)a.hx_cap;
+            for (uint32_t bb = b0; bb < b1; bb += 32) {
+                const uint32_t myb = bb + (uint32_t)lane;
                 bool active = myb < b1;
-                for (int j = 0; __any_sync(0xffffffffu, active); ++j) {
+                const uint64_t* bk = a.hx_keys + (size_t)myb * cap;
+                const uint16_t* bo = a.hx_offs + (size_t)myb * cap;
+                for (uint32_t j = 0; __any_sync(0xffffffffu, active); ++j) {
                     uint64_t ek = kKeyInf;
-                    uint32_t eo = 0;
-                    if (active) {
-                        ek = __ldg(a.hx_keys + myb * cap + j);
-                        eo = __ldg(a.hx_offs + myb * cap + j);
-                    }
+                    if (active) ek = __ldg(bk + j);
                     const bool cand = active && ek < T;
-                    const uint32_t x = (uint32_t)(myb << lg) + eo;
+                    uint32_t x = 0;
+                    if (cand) x = (myb << lg) + (uint32_t)__ldg(bo + j);  // offsets are read for candidates only
                     if (!push_cands(ck, ci, c, cand, ek, (int32_t)(x - base), lane)) return false;
                     active = cand && (j + 1 < cap);
                 }
             }
-            done = true;
+        } else if (!scan_threshold32(a, use_tab, base, lo32, hi32, T, ck, ci, c, lane)) {
+            return false;
         }
+        done = true;
     }
     if (!done && !scan_threshold(a, use_tab, base, 1, size, T, ck, ci, c, lane)) return false;
     const int64_t need = size < f ? size : f;

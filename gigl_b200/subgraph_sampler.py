@@ -113,13 +113,49 @@ def _feature_matrix(table: "sio.ExampleTable", keys) -> Optional[np.ndarray]:
     return np.concatenate(cols, axis=1) if cols else None
 
 
+_SHARD = (0, 1)  # (rank, world) of this process, set by run()
+
+
 def _write(dir_: str, part: int, data: bytes) -> None:
-    with open(os.path.join(dir_, f"part-{part:05d}.tfrecord"), "wb") as f:
+    rank, world = _SHARD
+    name = f"part-{part:05d}.tfrecord" if world == 1 else f"part-r{rank:03d}-{part:05d}.tfrecord"
+    with open(os.path.join(dir_, name), "wb") as f:
         f.write(data)
 
 
+def _my_share(ids: np.ndarray) -> np.ndarray:
+    """This rank's contiguous slice of the (sorted) root ids: the units are independent, so ranks share nothing and no
+    collective is needed (the rule of gigl_b200.sharding.root_range / distributed_neighborloader.py:195-216)."""
+    rank, world = _SHARD
+    if world == 1:
+        return ids
+    lo, hi = (len(ids) * rank) // world, (len(ids) * (rank + 1)) // world
+    return ids[lo:hi]
+
+
+def _my_quota(limit: int) -> int:
+    """numMaxTrainingSamplesToOutput split over the ranks (the reference keeps an arbitrary subset of that size)."""
+    rank, world = _SHARD
+    if limit <= 0 or world == 1:
+        return limit
+    return limit // world + (1 if rank < limit % world else 0)
+
+
 def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] = None, root: Optional[str] = None,
-        device: int = 0, batch_roots: int = 1 << 20, log=print) -> dict:
+        device: Optional[int] = None, batch_roots: int = 1 << 20, log=print, rank: Optional[int] = None,
+        world: Optional[int] = None) -> dict:
+    """One process per GPU.  Launched under torchrun (`python -m torch.distributed.run --nproc-per-node N -m
+    gigl_b200.subgraph_sampler ...`) every rank loads the graph onto its own GPU (LOCAL_RANK), samples a contiguous share
+    of the roots and writes its own `part-r<rank>-*.tfrecord` files into the same output prefixes; rank / world default to
+    RANK / WORLD_SIZE of the environment (0 / 1 outside torchrun)."""
+    global _SHARD
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world {world}")
+    _SHARD = (rank, world)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
     root = root or os.getcwd()
     t0 = time.time()
     cfg = _load_yaml(task_config_uri, root)
@@ -128,7 +164,7 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
     sgs = cfg.get("datasetConfig", {}).get("subgraphSamplerConfig", {})
     directed = bool(shared.get("isGraphDirected", False))
     skip_main = bool(shared.get("shouldSkipTraining", False)) and bool(shared.get("shouldSkipModelEvaluation", False))
-    max_train = int(sgs.get("numMaxTrainingSamplesToOutput", 0) or 0)
+    max_train = _my_quota(int(sgs.get("numMaxTrainingSamplesToOutput", 0) or 0))
     task_meta = cfg.get("taskMetadata", {})
     is_nablp = "nodeAnchorBasedLinkPredictionTaskMetadata" in task_meta
     flat = shared["flattenedGraphMetadata"]
@@ -173,8 +209,8 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
     csr = g.csr_host() if (ef is not None or directed) else None
     edge_rows = ctx.edge_rows_host(n_nodes, src32, dst32, directed) if ef is not None else None
     hyd = dict(condensed_node_type=ntype, condensed_edge_type=etype, csr=csr, edge_rows=edge_rows, edge_feat=ef)
-    roots_all = np.sort(node_id).astype(np.int32)  # every node of the node table gets exactly one RootedNodeNeighborhood
-    stats = {"n_nodes": n_nodes, "n_edges_csr": g.n_edges, "rnn": 0, "snc": 0, "nablp": 0, "fanouts": fanouts}
+    roots_all = _my_share(np.sort(node_id).astype(np.int32))  # every node of the node table gets exactly one RootedNodeNeighborhood
+    stats = {"rank": rank, "world": world, "n_nodes": n_nodes, "n_edges_csr": g.n_edges, "rnn": 0, "snc": 0, "nablp": 0, "fanouts": fanouts}
     t1 = time.time()
     if is_nablp:
         _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32, n_nodes, directed, sgs, skip_main, max_train,
@@ -339,7 +375,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
         out_dirs = {sup[0]: flat["supervisedNodeClassificationOutput"]["unlabeledTfrecordUriPrefix"]}
     skip_main = bool(shared.get("shouldSkipTraining", False)) and bool(shared.get("shouldSkipModelEvaluation", False))
     include_isolated = bool(shared.get("shouldIncludeIsolatedNodesInTraining", False))
-    max_train = int(sgs.get("numMaxTrainingSamplesToOutput", 0) or 0)
+    max_train = _my_quota(int(sgs.get("numMaxTrainingSamplesToOutput", 0) or 0))
     # ---- node tables per condensed node type
     ids, tables, n_max = {}, [None] * (max(node_type_of) + 1), 0
     for k, nmeta in meta["condensedNodeTypeToPreprocessedMetadata"].items():
@@ -413,7 +449,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
             continue
         out_dir = _resolve(out_dirs[rtype], root)
         os.makedirs(out_dir, exist_ok=True)
-        roots_all = ids[cnt_of[rtype]]
+        roots_all = _my_share(ids[cnt_of[rtype]])
         hydrate = dags[rtype][2]
         for part, s in enumerate(range(0, len(roots_all), batch_roots)):
             roots = roots_all[s:s + batch_roots]
@@ -437,7 +473,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
         pos_call = len(dags[a_type][0]) + 1  # the positives are drawn after the anchor's own ops (= call 3 after a 2-hop chain)
         main_dir = _resolve(flat["nodeAnchorBasedLinkPredictionOutput"]["tfrecordUriPrefix"], root)
         os.makedirs(main_dir, exist_ok=True)
-        anchors_all = ids[cnt_of[a_type]]
+        anchors_all = _my_share(ids[cnt_of[a_type]])
         if max_train > 0:
             # numMaxTrainingSamplesToOutput: the reference draws a random `.sample(fraction)` of the anchors' RNNs before the
             # join with the positives (:232-262); this keeps the first n by node id

@@ -429,3 +429,33 @@ def test_typed_component_hydrates_edge_features_and_isolated_anchors(tmp_path):
         assert canon(got[r], "pos_edges") == wpe
         assert canon(got[r]) == sorted(we, key=lambda e: (e[0], e[1], e[2], e[3] or ()))
         assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == wn
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_component_sharded_over_ranks_writes_the_same_records(tmp_path, directed):
+    """One process per GPU: rank r of `world` samples its contiguous share of the roots and writes part-r<rank>-* files.
+    The union of the ranks' records is exactly the single-process output (the units are independent: no collective)."""
+    import shutil
+
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+
+    one, many = tmp_path / "one", tmp_path / "many"
+    one.mkdir()
+    _nablp_fixture(one, directed)
+    shutil.copytree(one, many)
+    s1 = subgraph_sampler.run("frozen_gbml_config.yaml", "j", None, root=str(one), batch_roots=16, log=lambda *_: None)
+    world, tot = 3, {"rnn": 0, "nablp": 0}
+    for rank in range(world):
+        st = subgraph_sampler.run("frozen_gbml_config.yaml", "j", None, root=str(many), batch_roots=16, log=lambda *_: None,
+                                  rank=rank, world=world, device=0)
+        assert st["rank"] == rank and st["world"] == world
+        for k in tot:
+            tot[k] += st[k]
+    assert tot["rnn"] == s1["rnn"] and tot["nablp"] == s1["nablp"] and s1["nablp"] > 0
+    for sub in ("output/random_negatives/user/", "output/nablp/samples/"):
+        files = sio.list_tfrecord_files(str(many / sub))
+        assert {os.path.basename(f).split("-")[1] for f in files} == {"r000", "r001", "r002"}
+        a = sorted(sio.split_tfrecords(b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(one / sub))), verify=True))
+        b = sorted(sio.split_tfrecords(b"".join(open(f, "rb").read() for f in files), verify=True))
+        assert a == b
