@@ -436,12 +436,15 @@ def unpack_tree(packed, cnt_u8: Sequence[np.ndarray], fanouts: Sequence[int]):
     for c8, f in zip(cnt_u8, fanouts):
         c = np.asarray(c8).astype(np.int32)
         total = int(c.sum(dtype=np.int64))
+        if pos + total > len(packed):
+            raise ValueError("packed index sets are shorter than their counts say")
         lvl = np.full((len(c), int(f)), -1, dtype=np.int32)
         lvl[np.arange(int(f), dtype=np.int32)[None, :] < c[:, None]] = packed[pos:pos + total]
         pos += total
         nbr.append(lvl.reshape(-1))
         cnt.append(c)
-    assert pos == len(packed), "packed length does not match the counts"
+    if pos != len(packed):
+        raise ValueError("packed index sets are longer than their counts say")
     return nbr, cnt
 
 
