@@ -20,6 +20,12 @@ What is captured
 * ``nablp16_sgs_output.json`` - the reference's NABLP + random-negative RNN outputs under
   split_generator/node_anchor_based_link_prediction/sgs_output; these were sampled from the
   16-node graph above (16 RNN, 14 NABLP samples), not from the 27-node one.
+* ``hetero_graph.json`` / ``hetero_sgs_output.json`` / ``hetero_*.tfrecord.b64`` - the reference's heterogeneous fixture
+  (scala_spark35/common/src/test/assets/subgraph_sampler/heterogeneous/node_anchor_based_link_prediction: 15 authors,
+  19 papers, two featured edge types, the frozen config with ``messagePassingPaths``) and the typed, hydrated
+  RootedNodeNeighborhood outputs the reference holds for it
+  (.../split_generator/hetero_node_anchor_based_link_prediction/sgs_output/random_negative_rooted_neighborhood_samples).
+  ``python make_golden.py hetero`` regenerates only these.
 * ``xxh64_kat.json`` - known answers for Spark's ``xxhash64`` (XXH64.hashInt, seed 42)
   computed with the independent python ``xxhash`` package, incl. Spark's documented
   ``xxhash64('Spark', array(123), 2) = 5602566077635097486`` chain check.
@@ -142,8 +148,55 @@ def dump(name, obj):
     print("wrote", name)
 
 
+def hetero():
+    """The heterogeneous fixture of the spark35 sampler and the reference's typed outputs for it."""
+    import glob
+
+    from snapchat.research.gbml import training_samples_schema_pb2 as ts
+
+    assets35 = os.path.join(REF, "scala_spark35/common/src/test/assets")
+    base = os.path.join(assets35, "subgraph_sampler/heterogeneous/node_anchor_based_link_prediction")
+    tables = {"nodes_author": "node_features_dir/user/features", "nodes_paper": "node_features_dir/story/features",
+              "edges_author_to_paper": "edge_features_dir/user-to-story/main_edges/features",
+              "edges_paper_to_author": "edge_features_dir/story-to-user/main_edges/features"}
+    graph = {"source": "scala_spark35/common/src/test/assets/subgraph_sampler/heterogeneous/node_anchor_based_link_prediction",
+             "condensed_node_types": {"0": "author", "1": "paper"},
+             "condensed_edge_types": {"0": ["author", "to", "paper"], "1": ["paper", "to", "author"]}}
+    for name, sub in tables.items():
+        files = sorted(glob.glob(os.path.join(base, sub, "*.tfrecord")))
+        recs = [decode_example(r) for f in files for r in read_tfrecords(f)]
+        graph[name] = [{k: v[0] for k, v in r.items()} for r in recs]
+        with open(os.path.join(HERE, "hetero_" + name + ".tfrecord.b64"), "w") as g:
+            g.write(base64.encodebytes(b"".join(open(f, "rb").read() for f in files)).decode())
+        print("wrote", "hetero_" + name + ".tfrecord.b64")
+    import yaml
+
+    graph["frozen_gbml_config"] = yaml.safe_load(open(os.path.join(base, "frozen_gbml_config_graphdb_dblp_local.yaml")))
+    graph["preprocessed_metadata"] = yaml.safe_load(open(os.path.join(base, "preprocessed_metadata.yaml")))
+    dump("hetero_graph.json", graph)
+    sg = os.path.join(assets35, "split_generator/hetero_node_anchor_based_link_prediction/sgs_output")
+    out = {"source": "scala_spark35/common/src/test/assets/split_generator/hetero_node_anchor_based_link_prediction/sgs_output",
+           "note": "typed RootedNodeNeighborhoods as the reference holds them (uniform samples of a non-reproducible sampler: "
+                   "structure and hydration are pinned, not which neighbours were drawn)"}
+    for key, sub in (("rnn_author", "random_negative_rooted_neighborhood_samples/user/samples"),
+                     ("rnn_paper", "random_negative_rooted_neighborhood_samples/story/samples")):
+        lst = []
+        for f in sorted(glob.glob(os.path.join(sg, sub, "*.tfrecord"))):
+            for r in read_tfrecords(f):
+                m = ts.RootedNodeNeighborhood()
+                m.ParseFromString(r)
+                lst.append({"root_node": node_to_dict(m.root_node), "neighborhood": graph_to_dict(m.neighborhood),
+                            "bytes_b64": base64.b64encode(r).decode()})
+        out[key] = lst
+    dump("hetero_sgs_output.json", out)
+
+
 def main():
     from snapchat.research.gbml import training_samples_schema_pb2 as ts
+
+    if len(sys.argv) > 1 and sys.argv[1] == "hetero":
+        return hetero()
+    hetero()
 
     # ---- 16-node SNC graph -------------------------------------------------
     base = os.path.join(ASSETS, "subgraph_sampler/supervised_node_classification")

@@ -459,3 +459,90 @@ def test_component_sharded_over_ranks_writes_the_same_records(tmp_path, directed
         a = sorted(sio.split_tfrecords(b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(one / sub))), verify=True))
         b = sorted(sio.split_tfrecords(b"".join(open(f, "rb").read() for f in files), verify=True))
         assert a == b
+
+
+def _hetero_reference_fixture(tmp):
+    """The reference's heterogeneous sampler fixture (tests/golden/hetero_*: 15 authors, 19 papers, two featured edge types,
+    its frozen config with messagePassingPaths) written out as the files its URIs name."""
+    import base64
+    import copy
+
+    from helpers import load_golden
+
+    g = load_golden("hetero_graph.json")
+    cfg, meta = copy.deepcopy(g["frozen_gbml_config"]), copy.deepcopy(g["preprocessed_metadata"])
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for sub in ("nodes_author", "nodes_paper", "edges_author_to_paper", "edges_paper_to_author"):
+        os.makedirs(tmp / sub, exist_ok=True)
+        (tmp / sub / "data.tfrecord").write_bytes(base64.decodebytes(open(os.path.join(golden, f"hetero_{sub}.tfrecord.b64"), "rb").read()))
+    meta["condensedNodeTypeToPreprocessedMetadata"]["0"]["tfrecordUriPrefix"] = "nodes_author/"
+    meta["condensedNodeTypeToPreprocessedMetadata"]["1"]["tfrecordUriPrefix"] = "nodes_paper/"
+    meta["condensedEdgeTypeToPreprocessedMetadata"]["0"]["mainEdgeInfo"]["tfrecordUriPrefix"] = "edges_author_to_paper/"
+    meta["condensedEdgeTypeToPreprocessedMetadata"]["1"]["mainEdgeInfo"]["tfrecordUriPrefix"] = "edges_paper_to_author/"
+    shared = cfg["sharedConfig"]
+    shared["preprocessedMetadataUri"] = "preprocessed_metadata.yaml"
+    outp = shared["flattenedGraphMetadata"]["nodeAnchorBasedLinkPredictionOutput"]
+    outp["tfrecordUriPrefix"] = "out/nablp/"
+    outp["nodeTypeToRandomNegativeTfrecordUriPrefix"] = {"author": "out/rnn/author/", "paper": "out/rnn/paper/"}
+    (tmp / "preprocessed_metadata.yaml").write_text(yaml.safe_dump(meta))
+    (tmp / "frozen_gbml_config.yaml").write_text(yaml.safe_dump(cfg))
+    x = {t: np.array([[r["f0"], r["f1"]] for r in sorted(g[k], key=lambda r: r["node_id"])], dtype=np.float32)
+         for t, k in ((0, "nodes_author"), (1, "nodes_paper"))}
+    edges = {t: (np.array([r["src"] for r in g[k]]), np.array([r["dst"] for r in g[k]]), np.array([[r["f0"], r["f1"]] for r in g[k]], dtype=np.float32))
+             for t, k in ((0, "edges_author_to_paper"), (1, "edges_paper_to_author"))}
+    return x, edges
+
+
+def test_typed_component_on_the_reference_heterogeneous_fixture(tmp_path):
+    """The reference's own heterogeneous config (scala_spark35/.../subgraph_sampler/heterogeneous/node_anchor_based_link_
+    prediction/frozen_gbml_config_graphdb_dblp_local.yaml) end to end: typed hydrated RootedNodeNeighborhoods for authors and
+    papers, then the main samples of the author -to-> paper supervision edge type (numPositiveSamples 1,
+    numMaxTrainingSamplesToOutput 10), against the oracle's restatement; every hop takes min(fanout, in-degree) neighbours."""
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+    from oracle import oracle as O
+
+    x, edges = _hetero_reference_fixture(tmp_path)
+    stats = subgraph_sampler.run("frozen_gbml_config.yaml", "hetero_ref", None, root=str(tmp_path), batch_roots=8, log=lambda *_: None)
+    n_a, n_p = len(x[0]), len(x[1])
+    assert (n_a, n_p) == (15, 19) and stats["rnn_per_node_type"] == {"author": n_a, "paper": n_p}
+    n = max(n_a, n_p)
+    inc = {t: O.np_build_in_csr(e[0], e[1], n, True) for t, e in edges.items()}
+    outg = {t: O.np_build_in_csr(e[1], e[0], n, True) for t, e in edges.items()}
+    records = O.np_typed_edge_records({t: e for t, e in edges.items()})
+
+    def canon(sample, key="edges"):
+        return sorted(((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"], tuple(np.float32(e["feature_values"]).tolist()) or None)
+                       for e in sample[key]), key=lambda e: (e[0], e[1], e[2], e[3] or ()))
+
+    sets = {}
+    # author roots: op_4 = papers <- (paper to author), op_6 = authors <- (author to paper); paper roots: op_1, op_3 mirrored
+    for name, rt, n_roots, t1, t2 in (("author", 0, n_a, 1, 0), ("paper", 1, n_p, 0, 1)):
+        roots = np.arange(n_roots, dtype=np.int32)
+        ch, cc = O.np_sample_chain([inc[t1], inc[t2]], roots, [10, 10], [1, 2])
+        deg1 = np.diff(inc[t1][0])[roots]
+        assert np.array_equal(cc[0], np.minimum(deg1, 10))  # every hop takes min(fanout, in-degree) neighbours
+        ops = [dict(parent=-1, fanout=10, condensed_edge_type=t1, result_node_type=1 - rt, nbr=ch[0]),
+               dict(parent=0, fanout=10, condensed_edge_type=t2, result_node_type=rt, nbr=ch[1])]
+        sets[rt] = O.np_assemble_dag_rnn(roots, rt, ops)
+        want = O.np_hydrate_typed_rnn(sets[rt], records)
+        raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / f"out/rnn/{name}/")))
+        got = {s["root_node"]["node_id"]: s for s in map(sio.parse_sample, sio.split_tfrecords(raw, verify=True))}
+        assert sorted(got) == list(range(n_roots))
+        for r in range(n_roots):
+            assert got[r]["root_node"]["condensed_node_type"] == rt and np.array_equal(np.float32(got[r]["root_node"]["feature_values"]), x[rt][r])
+            assert canon(got[r]) == want[r][0] and sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == want[r][1]
+            for v in got[r]["nodes"]:
+                assert np.array_equal(np.float32(v["feature_values"]), x[v["condensed_node_type"]][v["node_id"]])
+    # main samples: anchors = the first 10 authors (numMaxTrainingSamplesToOutput), one positive each over author -to-> paper,
+    # drawn as call 3 (after the author path's two ops); anchors without an out-edge emit nothing
+    authors = np.arange(10, dtype=np.int32)
+    pos, _ = O.np_sample_chain([outg[0]], authors, [1], [3])
+    want = O.np_assemble_typed_nablp({a: sets[0][a] for a in range(10)}, sets[1], 1, {int(a): [int(pos[0][a])] for a in authors}, 0, records)
+    raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "out/nablp/")))
+    got = {s["root_node"]["node_id"]: s for s in map(sio.parse_nablp_sample, sio.split_tfrecords(raw, verify=True))} if raw else {}
+    assert sorted(got) == sorted(want) and stats["nablp"] == len(want) and len(want) > 0
+    for a, (wpe, we, wn) in want.items():
+        assert canon(got[a], "pos_edges") == wpe and len(wpe) == 1 and wpe[0][3] is not None  # the supervision edge carries its features
+        assert canon(got[a]) == sorted(we, key=lambda e: (e[0], e[1], e[2], e[3] or ()))
+        assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[a]["nodes"]) == wn
