@@ -109,3 +109,41 @@ def test_sampler_component_root_shares_partition_the_roots():
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     finally:
         ss._SHARD = (0, 1)
+
+
+# ---- batch collation semantics pinned by the reference's own data-loader tests ---------------------------------------
+# python/tests/unit/src/training/lib/data_loaders/rooted_node_neighborhood_batching_test.py builds three samples and
+# asserts the node / edge counts of their collation; python/tests/unit/src/common/graph_builder/pyg_graph_builder_test.py
+# asserts that adding the same graph twice changes nothing.  Here the same graphs in the sampler's tree form (an edge
+# src -> dst hangs src under dst), fanouts [2, 1]:
+#   triangle 0->1, 0->2, 1->2 : root 2, hop 1 = {0, 1}, hop 2 under 1 = {0}
+#   line     3->4            : root 4, hop 1 = {3}
+#   chain    1->2, 2->3      : root 3, hop 1 = {2}, hop 2 under 2 = {1}
+_TREES = {"triangle": (2, [0, 1], [-1, 0]), "line": (4, [3, -1], [-1, -1]), "chain": (3, [2, -1], [1, -1])}
+
+
+def _collate(names):
+    from oracle import oracle as O
+
+    roots = np.array([_TREES[n][0] for n in names], dtype=np.int32)
+    nbr = [np.array(sum((_TREES[n][1] for n in names), []), dtype=np.int32), np.array(sum((_TREES[n][2] for n in names), []), dtype=np.int32)]
+    node_ids, ei, root_idx = O.np_collate(roots, nbr, [2, 1])
+    edges = sorted((int(node_ids[s]), int(node_ids[d])) for s, d in zip(ei[0], ei[1]))
+    return node_ids, edges, root_idx, roots
+
+
+def test_collation_counts_of_the_reference_batching_tests():
+    # test_can_collate_correctly_without_edge_overlap: triangle + line -> 5 nodes, 4 edges
+    node_ids, edges, root_idx, roots = _collate(["triangle", "line"])
+    assert len(node_ids) == 5 and edges == [(0, 1), (0, 2), (1, 2), (3, 4)]
+    assert np.array_equal(node_ids[root_idx], roots)
+    # test_can_collate_correctly_with_edge_overlap: triangle + chain share 1->2 -> 4 nodes, 4 edges (the edge is not duplicated)
+    node_ids, edges, root_idx, roots = _collate(["triangle", "chain"])
+    assert sorted(node_ids.tolist()) == [0, 1, 2, 3] and edges == [(0, 1), (0, 2), (1, 2), (2, 3)]
+    assert np.array_equal(node_ids[root_idx], roots)
+    # pyg_graph_builder_test.test_can_create_with_preexisting_data_objects_filtering_existing_nodes_and_edges:
+    # the same graph added twice is the graph itself
+    once = _collate(["triangle"])
+    twice = _collate(["triangle", "triangle"])
+    assert sorted(once[0].tolist()) == sorted(twice[0].tolist()) == [0, 1, 2] and once[1] == twice[1] == [(0, 1), (0, 2), (1, 2)]
+    assert len(np.unique(twice[0])) == len(twice[0])  # local ids are one per distinct node
