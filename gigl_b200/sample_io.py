@@ -92,11 +92,61 @@ class ExampleTable:
 _KINDS = {"rnn": 0, "snc": 1, "nablp": 2}
 
 
+class NativeBuffer:
+    """The encoder's malloc'd output, handed over WITHOUT a copy (`zero_copy=True` of the encode_* functions): a
+    bytes-like object (`memoryview(buf)`, `file.write(buf.view)`, `len(buf)`) that frees the native memory when it is
+    closed or collected.  Copying 1.2 GB into a Python `bytes` costs seven times the encoding itself."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self._ptr, self.nbytes = ptr, int(nbytes)
+        self._arr = (C.c_ubyte * max(self.nbytes, 1)).from_address(ptr) if ptr else None
+
+    @property
+    def view(self) -> memoryview:
+        if self._arr is None:
+            raise ValueError("buffer is closed")
+        return memoryview(self._arr).cast("B")[: self.nbytes]
+
+    def __len__(self) -> int:
+        return self.nbytes
+
+    def __bytes__(self) -> bytes:
+        return bytes(self.view)
+
+    def close(self) -> None:
+        if self._ptr:
+            self._arr = None
+            _capi.lib().gigl_free_host(C.c_void_p(self._ptr))
+            self._ptr = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _take(out: "C.c_void_p", nbytes: int, zero_copy: bool):
+    """The encoder's output buffer as `bytes` (copied, then freed) or as a :class:`NativeBuffer` (no copy)."""
+    if zero_copy:
+        return NativeBuffer(out.value or 0, nbytes)
+    try:
+        return C.string_at(out.value, nbytes)
+    finally:
+        _capi.lib().gigl_free_host(out)
+
+
 def encode_samples(roots, fanouts, nbr, x: Optional[np.ndarray] = None, kind: str = "rnn", condensed_node_type: int = 0,
                    condensed_edge_type: int = 0, labels: Optional[np.ndarray] = None, label_type: str = "",
                    tfrecord_framing: bool = True, csr: Optional[Tuple[np.ndarray, np.ndarray]] = None,
                    edge_rows: Optional[np.ndarray] = None, edge_feat: Optional[np.ndarray] = None, n_emit: Optional[int] = None,
-                   pos: Optional[np.ndarray] = None, pos_tree: Optional[np.ndarray] = None) -> Tuple[bytes, np.ndarray]:
+                   pos: Optional[np.ndarray] = None, pos_tree: Optional[np.ndarray] = None, zero_copy: bool = False) -> Tuple[bytes, np.ndarray]:
     """Padded-tree index sets -> serialized RootedNodeNeighborhood ('rnn'), SupervisedNodeClassificationSample ('snc') or
     NodeAnchorBasedLinkPredictionSample ('nablp') messages, one per emitting root (include/gigl_b200.h,
     gigl_encode_samples_ex_host).  `csr` = host (rowptr, col) of the in-CSR turns every sampled pair into one Edge per
@@ -146,11 +196,7 @@ def encode_samples(roots, fanouts, nbr, x: Optional[np.ndarray] = None, kind: st
                                        condensed_node_type, condensed_edge_type, rp, cl, er, efp, Fe, lp, label_type.encode(),
                                        num_pos, pp, ptp, int(tfrecord_framing), C.byref(out), C.byref(nbytes), offs.ctypes.data)
     _check(rc, "gigl_encode_samples_ex_host")
-    try:
-        data = C.string_at(out.value, nbytes.value)
-    finally:
-        L.gigl_free_host(out)
-    return data, offs
+    return _take(out, nbytes.value, zero_copy), offs
 
 
 class HostEdgeTable:
@@ -175,7 +221,8 @@ class HostEdgeTable:
 
 def encode_link_samples(roots, fanouts, nbr, x: Optional[np.ndarray], n_emit: int, pos, pos_tree, main: HostEdgeTable,
                         pos_table: Optional[HostEdgeTable] = None, neg=None, neg_tree=None, neg_table: Optional[HostEdgeTable] = None,
-                        condensed_node_type: int = 0, condensed_edge_type: int = 0, tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
+                        condensed_node_type: int = 0, condensed_edge_type: int = 0, tfrecord_framing: bool = True,
+                        zero_copy: bool = False) -> Tuple[bytes, np.ndarray]:
     """NodeAnchorBasedLinkPredictionSample messages with positives (and optional hard negatives) that were sampled
     from - and are hydrated against - their own edge tables (gigl_encode_link_samples_host).  `pos_table` None = the
     main table.  Returns (bytes, record_offsets [n_emit + 1])."""
@@ -206,15 +253,11 @@ def encode_link_samples(roots, fanouts, nbr, x: Optional[np.ndarray], n_emit: in
                                          C.addressof(tn) if tn is not None else None, pos.shape[1], pos.ctypes.data, pos_tree.ctypes.data,
                                          num_neg, ngp, ntp, int(tfrecord_framing), C.byref(out), C.byref(nbytes), offs.ctypes.data)
     _check(rc, "gigl_encode_link_samples_host")
-    try:
-        data = C.string_at(out.value, nbytes.value)
-    finally:
-        L.gigl_free_host(out)
-    return data, offs
+    return _take(out, nbytes.value, zero_copy), offs
 
 
 def encode_dag_samples(roots, root_node_type: int, ops: Sequence[dict], node_tables: Sequence[Optional[np.ndarray]],
-                       tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
+                       tfrecord_framing: bool = True, zero_copy: bool = False) -> Tuple[bytes, np.ndarray]:
     """Typed RootedNodeNeighborhood messages from the ops of a SamplingOp DAG (gigl_encode_dag_samples_host).
     ops (topological order): dicts with parent (index or -1), fanout, condensed_edge_type, result_node_type, outgoing,
     nbr (the op's padded-tree output).  node_tables[t] = feature matrix of condensed node type t (or None)."""
@@ -241,11 +284,7 @@ def encode_dag_samples(roots, root_node_type: int, ops: Sequence[dict], node_tab
     rc = L.gigl_encode_dag_samples_host(len(roots), roots.ctypes.data, int(root_node_type), len(ops), C.addressof(c_ops), len(node_tables),
                                         C.addressof(c_tabs), int(tfrecord_framing), C.byref(out), C.byref(nbytes), offs.ctypes.data)
     _check(rc, "gigl_encode_dag_samples_host")
-    try:
-        data = C.string_at(out.value, nbytes.value)
-    finally:
-        L.gigl_free_host(out)
-    return data, offs
+    return _take(out, nbytes.value, zero_copy), offs
 
 
 def _dag_tree(roots, root_node_type: int, ops: Sequence[dict], keep: list) -> "_capi.DagTree":
@@ -264,7 +303,7 @@ def encode_typed_samples(roots, root_node_type: int, ops: Sequence[dict], node_t
                          edge_tables: Optional[Sequence[Optional["HostEdgeTable"]]] = None, kind: str = "rnn", pos=None, pos_tree=None,
                          pos_condensed_edge_type: int = -1, target_roots=None, target_node_type: int = 0,
                          target_ops: Optional[Sequence[dict]] = None, include_isolated: bool = False, hydrate_edges: bool = True,
-                         hydrate_pos_edges: bool = True, tfrecord_framing: bool = True) -> Tuple[bytes, np.ndarray]:
+                         hydrate_pos_edges: bool = True, tfrecord_framing: bool = True, zero_copy: bool = False) -> Tuple[bytes, np.ndarray]:
     """Typed RootedNodeNeighborhood (kind "rnn") / NodeAnchorBasedLinkPredictionSample (kind "nablp") messages from sampled
     SamplingOp DAGs, with edge hydration (gigl_encode_typed_samples_host).  ops as in :func:`encode_dag_samples`;
     edge_tables[t] = :class:`HostEdgeTable` of condensed edge type t (None entries / None = not hydrated).  nablp: pos
@@ -307,11 +346,7 @@ def encode_typed_samples(roots, root_node_type: int, ops: Sequence[dict], node_t
                                           n_et, C.addressof(c_et) if c_et is not None else None, int(tfrecord_framing), C.byref(out),
                                           C.byref(nbytes), offs.ctypes.data)
     _check(rc, "gigl_encode_typed_samples_host")
-    try:
-        data = C.string_at(out.value, nbytes.value)
-    finally:
-        L.gigl_free_host(out)
-    return data, offs
+    return _take(out, nbytes.value, zero_copy), offs
 
 
 # ---- a minimal protobuf wire reader (tests, tooling): no generated code needed --------------------

@@ -116,11 +116,23 @@ def _feature_matrix(table: "sio.ExampleTable", keys) -> Optional[np.ndarray]:
 _SHARD = (0, 1)  # (rank, world) of this process, set by run()
 
 
-def _write(dir_: str, part: int, data: bytes) -> None:
+def _roots_to_device(roots: np.ndarray, device: int):
+    """int32 root ids -> the CUDA tensor the device-side SamplingOp entry points take."""
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(roots, dtype=np.int32)).to(torch.device("cuda", device))
+
+
+def _write(dir_: str, part: int, data) -> None:
+    """data: bytes, or the encoder's NativeBuffer (written straight from the native memory, then released)."""
     rank, world = _SHARD
     name = f"part-{part:05d}.tfrecord" if world == 1 else f"part-r{rank:03d}-{part:05d}.tfrecord"
     with open(os.path.join(dir_, name), "wb") as f:
-        f.write(data)
+        if isinstance(data, sio.NativeBuffer):
+            f.write(data.view)
+            data.close()
+        else:
+            f.write(data)
 
 
 def _my_share(ids: np.ndarray) -> np.ndarray:
@@ -239,7 +251,7 @@ def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n
     for part, s in enumerate(range(0, len(roots_all), batch_roots)):
         roots = roots_all[s:s + batch_roots]
         nbr, cnt = g.sample_khop_host(roots, fanouts, base_seed=SAMPLING_SEED, first_call_no=1)
-        data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="rnn", **hyd)
+        data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="rnn", zero_copy=True, **hyd)
         _write(unl_dir, part, data)  # RootedNodeNeighborhood first
         stats["rnn"] += len(roots)
         if labels is not None:
@@ -249,7 +261,7 @@ def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n
             if max_train > 0:
                 keep = roots[(cnt[0] > 0) & (labels[roots] != sio.INT32_MIN)][max(0, max_train - stats["snc"]):]
                 lab[keep] = sio.INT32_MIN
-            data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="snc", labels=lab, label_type=label_key, **hyd)
+            data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="snc", labels=lab, label_type=label_key, zero_copy=True, **hyd)
             _write(lab_dir, part, data)
             stats["snc"] += int((np.diff(offs) > 0).sum())
 
@@ -324,7 +336,7 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
         for f in fanouts:
             width *= f
             own.append(nbr[len(own)][: n * width])
-        data, _ = sio.encode_samples(roots, fanouts, own, x, kind="rnn", **hyd)
+        data, _ = sio.encode_samples(roots, fanouts, own, x, kind="rnn", zero_copy=True, **hyd)
         _write(rnn_dir, part, data)  # RootedNodeNeighborhood (random negatives) first
         stats["rnn"] += n
         if pos is not None:
@@ -337,7 +349,8 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
 
             data, offs = sio.encode_link_samples(sample_roots, fanouts, nbr, x, n, pos, tree_of(pos), main_tab, pos_tab, neg,
                                                  tree_of(neg) if neg is not None else None, neg_tab,
-                                                 condensed_node_type=hyd["condensed_node_type"], condensed_edge_type=hyd["condensed_edge_type"])
+                                                 condensed_node_type=hyd["condensed_node_type"], condensed_edge_type=hyd["condensed_edge_type"],
+                                                 zero_copy=True)
             _write(main_dir, part, data)
             stats["nablp"] += int((np.diff(offs) > 0).sum())
 
@@ -350,8 +363,6 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
     RootedNodeNeighborhood TFRecords per anchor / target node type FIRST, then - for a link-prediction task that trains or
     evaluates - NodeAnchorBasedLinkPredictionSample TFRecords for the first supervision edge type: positives = an OUTGOING
     uniform sample of `numPositiveSamples` over that edge type, neighbourhood = the anchor's merged with its positives'."""
-    import torch
-
     from . import dag
 
     shared = cfg["sharedConfig"]
@@ -402,7 +413,6 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
             tables[tt] = np.concatenate([x, np.zeros((n_max - x.shape[0], x.shape[1]), np.float32)])
     log(f"[{job_name}] loaded {len(ids)} node types, {len(edges)} edge types in {time.time() - t0:.2f}s")
     ctx = Context.on_torch_stream(device)
-    dev = torch.device("cuda", device)
     graphs = {}
 
     def graph_of(edge_type, direction):
@@ -438,7 +448,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
 
     def sample(rtype, roots):
         ops, planned, _ = dags[rtype]
-        res = dag.sample_dag(graphs, torch.from_numpy(roots).to(dev), ops, rtype, base_seed=SAMPLING_SEED)
+        res = dag.sample_dag(graphs, _roots_to_device(roots, device), ops, rtype, base_seed=SAMPLING_SEED)
         ctx.sync()
         return dag.encoder_ops(planned, res, cet_of, cnt_of)
 
@@ -454,7 +464,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
         for part, s in enumerate(range(0, len(roots_all), batch_roots)):
             roots = roots_all[s:s + batch_roots]
             data, _ = sio.encode_typed_samples(roots, cnt_of[rtype], sample(rtype, roots), tables, edge_tables() if hydrate else None,
-                                               kind="rnn", hydrate_edges=hydrate)
+                                               kind="rnn", hydrate_edges=hydrate, zero_copy=True)
             _write(out_dir, part, data)
             stats["rnn"] += len(roots)
             stats["rnn_per_node_type"][rtype] = stats["rnn_per_node_type"].get(rtype, 0) + len(roots)
@@ -480,7 +490,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
             anchors_all = anchors_all[:max_train]
         for part, s in enumerate(range(0, len(anchors_all), batch_roots)):
             roots = anchors_all[s:s + batch_roots]
-            pos, _ = g_pos.sample_op(torch.from_numpy(roots).to(dev), [num_pos], [], pos_call, SAMPLING_SEED)
+            pos, _ = g_pos.sample_op(_roots_to_device(roots, device), [num_pos], [], pos_call, SAMPLING_SEED)
             ctx.sync()
             pos = pos.cpu().numpy().reshape(len(roots), num_pos)
             t_roots = np.unique(pos[pos >= 0]).astype(np.int32)
@@ -490,7 +500,8 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
                                                   kind="nablp", pos=pos, pos_tree=tree, pos_condensed_edge_type=pos_cet,
                                                   target_roots=t_roots, target_node_type=cnt_of[t_type],
                                                   target_ops=sample(t_type, t_roots) if len(t_roots) else [],
-                                                  include_isolated=include_isolated, hydrate_edges=hyd_graph, hydrate_pos_edges=hyd_pos)
+                                                  include_isolated=include_isolated, hydrate_edges=hyd_graph, hydrate_pos_edges=hyd_pos,
+                                                  zero_copy=True)
             _write(main_dir, part, data)
             stats["nablp"] += int((np.diff(offs) > 0).sum())
     stats["seconds_sample_and_write"] = time.time() - t1

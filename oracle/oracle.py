@@ -258,6 +258,46 @@ def np_sample_chain(csrs, roots, fanouts, call_nos, base_seed=42):
     return nbr, cnt
 
 
+def np_sample_op(csr, roots, fanouts, chain_nbr, call_no, base_seed=42):
+    """ONE op of a SamplingOp DAG given its ancestors' padded trees (the inputs of gigl_sample_op_*): the last hop of
+    np_sample_chain.  fanouts = the ancestors' fanouts followed by this op's; chain_nbr = the ancestors' outputs."""
+    n_roots = len(roots)
+    depth = len(fanouts)
+    f = int(fanouts[-1])
+    rowptr, col = csr
+    width_prev = 1
+    for g in fanouts[:-1]:
+        width_prev *= int(g)
+    prev_vals = [int(r) for r in roots] if depth == 1 else [int(v) for v in chain_nbr[-1]]
+    prev_sums = [0] * (n_roots * width_prev)
+    for ps in range(n_roots * width_prev):  # wrapping int32 sum of the path ids root .. parent
+        tot, s_ = 0, ps
+        for h in range(depth - 1, 0, -1):
+            tot = _wrap32(tot + int(chain_nbr[h - 1][s_]))
+            s_ //= int(fanouts[h - 1])
+        prev_sums[ps] = _wrap32(tot + int(roots[s_]))
+    cur_seed = _wrap32(base_seed * _wrap32(call_no))
+    out = np.full(n_roots * width_prev * f, -1, dtype=np.int32)
+    oc = np.zeros(n_roots * width_prev, dtype=np.int32)
+    for ps in range(n_roots * width_prev):
+        v = prev_vals[ps]
+        if v < 0:
+            continue
+        m = 1
+        if depth > 1:
+            fp = int(fanouts[-2])
+            sib0 = (ps // fp) * fp
+            sib = prev_vals[sib0 : sib0 + fp]
+            if sib.index(v) + sib0 != ps:
+                continue
+            m = sib.count(v)
+        arr = np.repeat(col[rowptr[v] : rowptr[v + 1]], m)
+        sel = arr[np_perm(len(arr), prev_sums[ps], cur_seed)[:f]]
+        out[ps * f : ps * f + len(sel)] = sel
+        oc[ps] = len(sel)
+    return out, oc
+
+
 def tree_to_edges(roots, nbr, fanouts):
     """Padded tree -> per-root list of (src, dst) index pairs, src = hop-k node, dst = hop-(k-1)
     node (SGSPureSparkV1Task.scala:615-629), one pair per sampled slot (explode semantics)."""
