@@ -57,3 +57,51 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
                 assert "libgigl_oracle" not in src and "gigl_oracle.c" not in src, fn
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C11 with no C++ / torch types, and a C program linked against the
+    library calls it (host-only entry points here: the TFRecord framing checksum and the record splitter)."""
+    import shutil
+    import subprocess
+
+    from gigl_b200 import _capi
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "gigl_b200.h")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    _capi.lib()
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gigl_b200.h"
+int main(void) {
+    /* one TFRecord: u64 length, masked crc32c(length), payload, masked crc32c(payload) */
+    unsigned char rec[8 + 4 + 5 + 4];
+    const unsigned long long n = 5;
+    memcpy(rec, &n, 8);
+    unsigned int c = gigl_crc32c_masked(rec, 8);
+    memcpy(rec + 8, &c, 4);
+    memcpy(rec + 12, "hello", 5);
+    c = gigl_crc32c_masked(rec + 12, 5);
+    memcpy(rec + 17, &c, 4);
+    int64_t off = -1, len = -1;
+    const int64_t k = gigl_tfrecord_index_host(rec, (int64_t)sizeof rec, 1, &off, &len, 1);
+    rec[13] ^= 1; /* corrupt the payload: the checksum must catch it */
+    const int64_t bad = gigl_tfrecord_index_host(rec, (int64_t)sizeof rec, 1, &off, &len, 1);
+    printf("%s|%lld|%lld|%lld|%lld|%u\n", gigl_version(), (long long)k, (long long)off, (long long)len, (long long)bad,
+           gigl_crc32c_masked("123456789", 9));
+    return 0;
+}
+''')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                           "-lgigl_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)]).decode().strip().split("|")
+    assert "sm_100a" in out[0] and out[1:4] == ["1", "12", "5"] and int(out[4]) < 0
+    # crc32c("123456789") = 0xE3069283 (the Castagnoli check value), masked as TFRecord does
+    crc = 0xE3069283
+    assert int(out[5]) == ((((crc >> 15) | (crc << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
