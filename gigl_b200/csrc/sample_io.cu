@@ -882,10 +882,6 @@ int gigl_encode_typed_samples_host(int32_t kind, const gigl_dag_tree* anchors, c
 int64_t gigl_tfrecord_index_host(const uint8_t* data, int64_t n_bytes, int32_t verify, int64_t* offsets, int64_t* lengths,
                                  int64_t max_records) {
     if (!data || n_bytes < 0) return GIGL_E_INVALID;
-    const bool fill = offsets && lengths;
-    // the framing walk is serial (every record's position depends on the previous length) and touches 12 bytes per
-    // record; with the arrays filled the payload checksums - all of the bytes - are then verified in parallel
-    const bool inline_payload_crc = verify && !fill;
     int64_t pos = 0, n = 0;
     while (pos < n_bytes) {
         if (pos + 12 > n_bytes) return GIGL_E_INVALID;
@@ -895,27 +891,17 @@ int64_t gigl_tfrecord_index_host(const uint8_t* data, int64_t n_bytes, int32_t v
         memcpy(&c, data + pos + 8, 4);
         if (verify && c != mask_crc(crc32c(data + pos, 8))) return GIGL_E_INVALID;
         if (len > (uint64_t)(n_bytes - pos - 16)) return GIGL_E_INVALID;
-        if (inline_payload_crc) {
+        if (verify) {
             memcpy(&c, data + pos + 12 + len, 4);
             if (c != mask_crc(crc32c(data + pos + 12, (size_t)len))) return GIGL_E_INVALID;
         }
-        if (fill) {
+        if (offsets && lengths) {
             if (n >= max_records) return GIGL_E_OVERFLOW;
             offsets[n] = pos + 12;
             lengths[n] = (int64_t)len;
         }
         ++n;
         pos += 16 + (int64_t)len;
-    }
-    if (verify && fill) {
-        int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
-        for (int64_t r = 0; r < n; ++r) {
-            uint32_t c;
-            memcpy(&c, data + offsets[r] + lengths[r], 4);
-            bad |= (c != mask_crc(crc32c(data + offsets[r], (size_t)lengths[r])));
-        }
-        if (bad) return GIGL_E_INVALID;
     }
     return n;
 }

@@ -46,18 +46,15 @@ class ExampleTable:
     def __init__(self, data: bytes, verify: bool = True):
         self._L = _capi.lib()
         self.data = np.frombuffer(data, dtype=np.uint8)
-        # pass 1 counts the records (framing walk only), pass 2 fills the arrays and verifies the checksums in parallel
-        n = self._L.gigl_tfrecord_index_host(self.data.ctypes.data, len(self.data), 0, None, None, 0)
+        n = self._L.gigl_tfrecord_index_host(self.data.ctypes.data, len(self.data), int(verify), None, None, 0)
         if n < 0:
-            raise GiglError(int(n), "malformed TFRecord stream (framing)")
+            raise GiglError(int(n), "malformed TFRecord stream (framing or crc32c)")
         self.n = int(n)
         self.offsets = np.zeros(max(self.n, 1), dtype=np.int64)
         self.lengths = np.zeros(max(self.n, 1), dtype=np.int64)
         if self.n:
-            m = self._L.gigl_tfrecord_index_host(self.data.ctypes.data, len(self.data), int(verify), self.offsets.ctypes.data,
+            m = self._L.gigl_tfrecord_index_host(self.data.ctypes.data, len(self.data), 0, self.offsets.ctypes.data,
                                                  self.lengths.ctypes.data, self.n)
-            if m < 0:
-                raise GiglError(int(m), "malformed TFRecord stream (framing or crc32c)")
             assert m == self.n
 
     @classmethod
