@@ -26,6 +26,10 @@ What is captured
   RootedNodeNeighborhood outputs the reference holds for it
   (.../split_generator/hetero_node_anchor_based_link_prediction/sgs_output/random_negative_rooted_neighborhood_samples).
   ``python make_golden.py hetero`` regenerates only these.
+* ``encoder_pb2_views.json`` - the bytes the repo's host encoder writes for every sample type (tests/encoder_cases.py:
+  RootedNodeNeighborhood with / without features, SupervisedNodeClassificationSample with negative / zero labels,
+  NodeAnchorBasedLinkPredictionSample with main-edge and user-defined positives / hard negatives, the typed variants)
+  as the REFERENCE's generated protobuf classes parse them (``python make_golden.py encoder`` regenerates it).
 * ``xxh64_kat.json`` - known answers for Spark's ``xxhash64`` (XXH64.hashInt, seed 42)
   computed with the independent python ``xxhash`` package, incl. Spark's documented
   ``xxhash64('Spark', array(123), 2) = 5602566077635097486`` chain check.
@@ -191,12 +195,50 @@ def hetero():
     dump("hetero_sgs_output.json", out)
 
 
+def encoder_views():
+    """The host encoder's bytes seen through the reference's own generated protobuf classes."""
+    from snapchat.research.gbml import training_samples_schema_pb2 as ts
+
+    sys.path.insert(0, os.path.dirname(HERE))               # tests/
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))  # repo root
+    import encoder_cases
+
+    from gigl_b200 import sample_io as sio
+
+    cls = {"rnn": ts.RootedNodeNeighborhood, "snc": ts.SupervisedNodeClassificationSample, "nablp": ts.NodeAnchorBasedLinkPredictionSample}
+    out = {"generator": "tests/encoder_cases.py -> gigl_encode_*_host -> snapchat.research.gbml.training_samples_schema_pb2"}
+    for name, (kind, data) in encoder_cases.cases().items():
+        views = []
+        for rec in sio.split_tfrecords(data, verify=True):
+            m = cls[kind]()
+            m.ParseFromString(rec)
+            # nothing the reference's schema does not know: re-serialising what it parsed gives back a record of the same size
+            assert len(m.SerializeToString()) == len(rec), (name, len(m.SerializeToString()), len(rec))
+            v = {"root_node": node_to_dict(m.root_node), "neighborhood": graph_to_dict(m.neighborhood),
+                 "has_neighborhood": m.HasField("neighborhood")}
+            if kind == "snc":
+                v["root_node_labels"] = [{"label_type": l.label_type, "label": l.label} for l in m.root_node_labels]
+            if kind == "nablp":
+                v["pos_edges"] = [edge_to_dict(e) for e in m.pos_edges]
+                v["hard_neg_edges"] = [edge_to_dict(e) for e in m.hard_neg_edges]
+                v["neg_edges"] = [edge_to_dict(e) for e in m.neg_edges]
+            views.append(v)
+        out[name] = {"kind": kind, "bytes_b64": base64.b64encode(data).decode(), "records": views}
+    with open(os.path.join(HERE, "encoder_pb2_views.json"), "w") as f:  # compact: half a megabyte when indented
+        json.dump(out, f, sort_keys=True, separators=(",", ":"))
+        f.write("\n")
+    print("wrote encoder_pb2_views.json")
+
+
 def main():
     from snapchat.research.gbml import training_samples_schema_pb2 as ts
 
     if len(sys.argv) > 1 and sys.argv[1] == "hetero":
         return hetero()
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        return encoder_views()
     hetero()
+    encoder_views()
 
     # ---- 16-node SNC graph -------------------------------------------------
     base = os.path.join(ASSETS, "subgraph_sampler/supervised_node_classification")
