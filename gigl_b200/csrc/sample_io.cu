@@ -618,7 +618,6 @@ struct TNode {
     int32_t type;
     uint32_t id;
     bool operator<(const TNode& b) const { return type != b.type ? type < b.type : id < b.id; }
-    bool operator==(const TNode& b) const { return type == b.type && id == b.id; }
 };
 struct TEdge {
     int32_t type;
@@ -627,7 +626,6 @@ struct TEdge {
     bool operator<(const TEdge& b) const {
         return type != b.type ? type < b.type : src != b.src ? src < b.src : dst != b.dst ? dst < b.dst : row < b.row;
     }
-    bool same_key(const TEdge& b) const { return type == b.type && src == b.src && dst == b.dst; }
 };
 
 struct TypedCtx {
