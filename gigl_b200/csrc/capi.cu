@@ -201,6 +201,8 @@ void gigl_ctx_destroy(gigl_ctx* ctx) {
         }
         delete[] ctx->t_pool;
     }
+    if (ctx->lad.blob_a) cudaFree(ctx->lad.blob_a);
+    if (ctx->lad.blob_b) cudaFree(ctx->lad.blob_b);
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->copy_ready) cudaEventDestroy(ctx->copy_ready);
@@ -432,13 +434,6 @@ void gigl_graph_destroy(gigl_graph* g) {
         cudaStreamSynchronize(g->ctx->stream);
         cudaFree((void*)g->rowptr);
         cudaFree((void*)g->col);
-    }
-    if (g->hx_keys || g->hx_offs) {
-        cudaSetDevice(g->ctx->device);
-        cudaStreamSynchronize(g->ctx->stream);
-        if (g->hx_keys) cudaFree(g->hx_keys);
-        if (g->hx_offs) cudaFree(g->hx_offs);
-        if (g->hk_table) cudaFree(g->hk_table);
     }
     if (g->x_owned && g->x) {
         cudaSetDevice(g->ctx->device);

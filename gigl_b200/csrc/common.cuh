@@ -42,6 +42,22 @@ struct gigl_timer_pair {
     int tag;
 };
 
+// Hash ladder of the sampler (khop_sample.cu): the permutation key of hash input x is a fixed sequence H(x), so the
+// "f smallest keys of a window" query is indexed once per context, for every graph sampled through it.
+//   level 0: tk0[x] = top 32 bits of ordered_key(x), every x in [0, limit);
+//   level j >= 1: the inputs whose key has j leading zero bits (a 2^-j sample of the inputs), as entries
+//   (key >> (32 - j)) << 32 | x grouped by block x >> j; bs[j][b] = first entry of block b.
+constexpr int GIGL_LAD_MAX_LEVELS = 25;
+struct gigl_ladder {
+    uint32_t* tk0 = nullptr;
+    uint32_t* bs[GIGL_LAD_MAX_LEVELS + 1] = {};
+    uint64_t* ent[GIGL_LAD_MAX_LEVELS + 1] = {};
+    uint64_t limit = 0;  // inputs [0, limit) are covered, limit <= 2^31
+    int levels = 0;
+    void* blob_a = nullptr;  // tk0 + block starts
+    void* blob_b = nullptr;  // entries
+};
+
 struct gigl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -66,6 +82,7 @@ struct gigl_ctx {
     int t_cap = 0, t_used = 0;
     double t_ms[GIGL_T_COUNT] = {};
     int64_t t_n[GIGL_T_COUNT] = {};
+    gigl_ladder lad;  // sampler's hash ladder, built lazily on the first sampling call
 };
 
 // Begin / end of a timed phase on the ctx stream (no-ops unless timing is enabled).
@@ -89,15 +106,7 @@ struct gigl_graph {
     int32_t F = 0;
     int64_t ldx = 0;
     bool x_owned = false;
-    // hash-window index of the sampler (khop_sample.cu), built lazily on the first sampling call
-    uint64_t* hx_keys = nullptr;
-    uint16_t* hx_offs = nullptr;
-    uint64_t* hk_table = nullptr;  // every key of the indexed range
-    uint64_t hk_limit = 0;
-    uint64_t hx_limit = 0;
-    int32_t hx_l_log2 = 0;
-    int32_t hx_cap = 0;
-    bool hx_enabled = true;
+    bool hx_enabled = true;  // sample through the context's hash ladder (gigl_graph_set_hash_index)
 };
 
 int gigl_fail(gigl_ctx* ctx, int code, const std::string& msg);

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 #include "xxh64.cuh"
 
@@ -45,16 +47,12 @@ struct HopArgs {
     int32_t* heavy_count;
     int32_t heavy_cap;
     unsigned long long* tile_counter;  // next tile of khop_tile_kernel (zeroed per launch)
-    // hash-window index (see build_hash_index_kernel): per block of 2^l_log2 consecutive hash inputs
-    // the `cap` smallest keys, ascending, with their offsets inside the block; nullptr = disabled
-    const uint64_t* hx_keys;
-    const uint16_t* hx_offs;
-    uint64_t hx_limit;  // inputs [0, hx_limit) are covered
-    int32_t hx_l_log2;
-    int32_t hx_cap;
-    // full key table: hk_table[x] = ordered_key(x) for x in [0, hk_limit); nullptr = hash on the fly
-    const uint64_t* hk_table;
-    uint64_t hk_limit;
+    // hash ladder (see the "hash ladder" section below); lad_limit == 0 = disabled
+    const uint32_t* lad_tk0;
+    const uint32_t* lad_bs[GIGL_LAD_MAX_LEVELS + 1];
+    const uint64_t* lad_ent[GIGL_LAD_MAX_LEVELS + 1];
+    uint64_t lad_limit;
+    int32_t lad_levels;
 };
 
 // Sorted (ascending) best-`f` list held by one warp: position p lives in lane p%32, register p/32.
@@ -223,87 +221,11 @@ __device__ __forceinline__ void write_result(const HopArgs& a, int64_t pslot, co
     if (lane == 0) a.out_cnt[pslot] = n_out;
 }
 
-// ---- hash-window index ----------------------------------------------------------------------
-// The permutation key of window position i is H(base + i): a row of `size` entries asks for the f
-// smallest values of the FIXED sequence H(x) over the window x in [base+1, base+size].  For long
-// rows (hubs) almost all of that hashing is shared between windows, so the sequence is indexed
-// once per graph: for every aligned block of L = 2^l_log2 inputs the `cap` smallest keys (sorted)
-// and their offsets.  A window then costs < 2L hashes (its unaligned head and tail) plus one
-// 8-byte read per covered block (the block minimum prunes nearly all of them), instead of `size`
-// hashes.  Bit-exact by construction: the same keys, the same (key, idx) order.
-template <int KPL>
-__global__ void __launch_bounds__(256) build_hash_index_kernel(int64_t n_blocks, int l_log2, int cap,
-                                                               uint64_t* __restrict__ keys,
-                                                               uint16_t* __restrict__ offs) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
-        WarpTopK<KPL> best;
-        best.init();
-        const uint32_t base = (uint32_t)((b << l_log2) - 1);  // x = base + i, i = 1..L
-        best.scan(0, (int64_t)1 << l_log2, 32, base, cap, lane);
-#pragma unroll
-        for (int k = 0; k < KPL; ++k) {
-            const int p = k * 32 + lane;
-            if (p < cap) {
-                keys[b * cap + p] = best.key[k];
-                offs[b * cap + p] = (uint16_t)(best.idx[k] - 1);
-            }
-        }
-    }
-}
-
-// Top-f of one row's window, through the index when it covers the window.
+// Exact top-f of one row's window by streaming every key through the sorted list (the path every other one falls
+// back to).
 template <int KPL>
 __device__ __forceinline__ void select_row(const HopArgs& a, WarpTopK<KPL>& best, int64_t size, uint32_t base, int f,
                                            int lane) {
-    if (a.hx_keys != nullptr) {
-        const uint64_t lo = (uint64_t)base + 1, hi = (uint64_t)base + (uint64_t)size;
-        const int lg = a.hx_l_log2;
-        if (hi < a.hx_limit && (size >> lg) != 0) {
-            const uint64_t b0 = (lo + ((1ULL << lg) - 1)) >> lg, b1 = (hi + 1) >> lg;  // full blocks [b0, b1)
-            if (b0 < b1) {
-                const int64_t head_end = (int64_t)((b0 << lg) - lo);             // i in [1, head_end]
-                const int64_t tail_begin = (int64_t)((b1 << lg) - (uint64_t)base);  // first tail i
-                best.scan(0, head_end, 32, base, f, lane);
-                best.scan(tail_begin - 1, size, 32, base, f, lane);
-                const int cap = a.hx_cap;
-                for (uint64_t bb = b0; bb < b1; bb += 32) {
-                    const uint64_t myb = bb + lane;
-                    uint64_t head = kKeyInf;
-                    if (myb < b1) head = __ldg(a.hx_keys + myb * cap);
-                    uint32_t cand = __ballot_sync(0xffffffffu, head < best.kth);
-                    while (cand) {
-                        const int src = __ffs(cand) - 1;
-                        cand &= cand - 1;
-                        if (__shfl_sync(0xffffffffu, head, src) >= best.kth) continue;
-                        const uint64_t blk = bb + src;
-#pragma unroll
-                        for (int k = 0; k < KPL; ++k) {
-                            const int p = k * 32 + lane;
-                            uint64_t ek = kKeyInf;
-                            uint32_t eo = 0;
-                            if (p < cap) {
-                                ek = __ldg(a.hx_keys + blk * cap + p);
-                                eo = __ldg(a.hx_offs + blk * cap + p);
-                            }
-                            uint32_t c2 = __ballot_sync(0xffffffffu, ek < best.kth);
-                            while (c2) {
-                                const int s2 = __ffs(c2) - 1;
-                                c2 &= c2 - 1;
-                                const uint64_t ck = __shfl_sync(0xffffffffu, ek, s2);
-                                const uint32_t co = __shfl_sync(0xffffffffu, eo, s2);
-                                if (ck >= best.kth) break;  // entries are ascending
-                                const uint32_t x = (uint32_t)(blk << lg) + co;
-                                best.insert(ck, (int32_t)(x - base), f, lane);
-                            }
-                        }
-                    }
-                }
-                return;
-            }
-        }
-    }
     best.scan(0, size, 32, base, f, lane);
 }
 
@@ -312,9 +234,10 @@ __device__ __forceinline__ void select_row(const HopArgs& a, WarpTopK<KPL>& best
 // One pass collects every key below T = (m / size) * 2^64, m a little above f, into a per-warp
 // shared-memory buffer (no serial insertions), one bitonic sort orders the <= 64 candidates, the
 // first f are the answer.  If fewer than f keys fell below T, or more than the buffer holds (both
-// rare by the Poisson tail), the exact streaming path above redoes the row - the result is always
-// the exact top-f of the exact keys.
-constexpr int kCandCap = 64;
+// rare by the Poisson tail), an exact path redoes the row - the result is always the exact top-f of
+// the exact keys.
+constexpr int kCandCap = 64;        // candidates of a threshold pass
+constexpr int kCandCapWide = 160;   // candidates of the ladder's exact second attempt
 
 struct PairKI {
     uint64_t k;
@@ -350,6 +273,30 @@ __device__ __forceinline__ void sort32_u32(uint32_t& v, int lane) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) cmpx_u32(v, stride, ((lane & size) == 0) == ((lane & stride) == 0));
 }
 
+// Orders c <= 64 buffered candidates on ONE 32-bit word each: 26 significant key bits (word_of(slot), < 2^26) over the
+// candidate's 6-bit buffer slot.  A 32-lane bitonic network on such words is one shuffle and one min/max per stage
+// instead of three shuffles and a 64-bit compare.  On return lane l < need holds the buffer slot of the l-th smallest
+// key in v0 & 63.  Two candidates agreeing on the 26 bits inside the first need + 1 positions (about 1e-5 of the rows)
+// would make the order ambiguous: returns false and the row is redone by an exact path.
+template <class WordOf>
+__device__ __forceinline__ bool order_cands_u32(int c, int need, int lane, WordOf word_of, uint32_t& v0) {
+    uint32_t v1 = 0xFFFFFFFFu;
+    v0 = 0xFFFFFFFFu;
+    if (lane < c) v0 = (word_of(lane) << 6) | (uint32_t)lane;
+    sort32_u32(v0, lane);
+    if (c > 32) {  // warp-uniform
+        if (lane + 32 < c) v1 = (word_of(lane + 32) << 6) | (uint32_t)(lane + 32);
+        sort32_u32(v1, lane);
+        // 32 smallest of two ascending runs: min(v0[l], v1[31 - l]) is bitonic; one merge sorts it
+        v0 = min(v0, __shfl_sync(0xffffffffu, v1, 31 - lane));
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) cmpx_u32(v0, stride, (lane & stride) == 0);
+    }
+    const uint32_t up = __shfl_up_sync(0xffffffffu, v0, 1);
+    const bool tie = lane >= 1 && lane <= need && v0 != 0xFFFFFFFFu && (v0 >> 6) == (up >> 6);
+    return !__any_sync(0xffffffffu, tie);
+}
+
 __device__ __forceinline__ bool push_cands(uint64_t* __restrict__ ck, int32_t* __restrict__ ci, int& c, bool is_cand,
                                            uint64_t k, int32_t i, int lane) {
     const uint32_t m = __ballot_sync(0xffffffffu, is_cand);
@@ -365,32 +312,7 @@ __device__ __forceinline__ bool push_cands(uint64_t* __restrict__ ck, int32_t* _
     return true;
 }
 
-__device__ __forceinline__ bool scan_threshold(const HopArgs& a, bool use_tab, uint32_t base, int64_t i_first, int64_t i_last,
-                                               uint64_t T, uint64_t* ck, int32_t* ci, int& c, int lane) {
-    for (int64_t c0 = i_first - 1; c0 < i_last; c0 += 32) {
-        const int64_t i = c0 + lane + 1;
-        uint64_t k = kKeyInf;
-        if (i <= i_last) {
-            const uint32_t x = base + (uint32_t)i;
-            k = use_tab ? __ldg(a.hk_table + x) : ordered_key((int32_t)x);
-        }
-        if (!push_cands(ck, ci, c, k < T, k, (int32_t)i, lane)) return false;
-    }
-    return true;
-}
-
-// The same scan over hash inputs x in [x_first, x_last], all below 2^31 (index-covered rows): 32-bit arithmetic only.
-__device__ __forceinline__ bool scan_threshold32(const HopArgs& a, bool use_tab, uint32_t base, uint32_t x_first, uint32_t x_last,
-                                                 uint64_t T, uint64_t* ck, int32_t* ci, int& c, int lane) {
-    for (uint32_t x0 = x_first; x0 <= x_last; x0 += 32) {
-        const uint32_t x = x0 + (uint32_t)lane;
-        uint64_t k = kKeyInf;
-        if (x <= x_last) k = use_tab ? __ldg(a.hk_table + x) : ordered_key((int32_t)x);
-        if (!push_cands(ck, ci, c, k < T, k, (int32_t)(x - base), lane)) return false;
-    }
-    return true;
-}
-
+// Rows the ladder does not cover (hash inputs at or beyond its limit, or no ladder): keys hashed on the fly.
 // Returns true with best.key[0] / best.idx[0] = the row's keys in ascending order (>= f of them, or all).
 __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& best, int64_t size, uint32_t base, int f,
                                                  int lane, uint64_t* ck, int32_t* ci) {
@@ -398,75 +320,30 @@ __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& 
     if (m > 48.f) m = 48.f;
     uint64_t T = kKeyInf;
     if ((float)size > m) T = __float2ull_rz(m / (float)size * 18446744073709551616.0f);
-    const uint64_t hi = (uint64_t)base + (uint64_t)size;
-    const bool use_tab = a.hk_table != nullptr && hi < a.hk_limit;
     int c = 0;
-    bool done = false;
-    if (a.hx_keys != nullptr && hi < a.hx_limit) {
-        // Every hash input of the window lies below hx_limit <= 2^31: the window, its blocks and the candidates'
-        // positions are 32-bit quantities (ncu: 52 % of this kernel's issue slots were 64-bit index arithmetic).
-        const uint32_t lo32 = base + 1u, hi32 = (uint32_t)hi;
-        const int lg = a.hx_l_log2;
-        const uint32_t b0 = (lo32 + ((1u << lg) - 1u)) >> lg, b1 = (hi32 + 1u) >> lg;  // full blocks [b0, b1)
-        if (b0 < b1) {
-            if (!scan_threshold32(a, use_tab, base, lo32, (b0 << lg) - 1u, T, ck, ci, c, lane)) return false;   // head
-            if (!scan_threshold32(a, use_tab, base, b1 << lg, hi32, T, ck, ci, c, lane)) return false;          // tail
-            const uint32_t cap = (uint32_t)a.hx_cap;
-            for (uint32_t bb = b0; bb < b1; bb += 32) {
-                const uint32_t myb = bb + (uint32_t)lane;
-                bool active = myb < b1;
-                const uint64_t* bk = a.hx_keys + (size_t)myb * cap;
-                const uint16_t* bo = a.hx_offs + (size_t)myb * cap;
-                for (uint32_t j = 0; __any_sync(0xffffffffu, active); ++j) {
-                    uint64_t ek = kKeyInf;
-                    if (active) ek = __ldg(bk + j);
-                    const bool cand = active && ek < T;
-                    uint32_t x = 0;
-                    if (cand) x = (myb << lg) + (uint32_t)__ldg(bo + j);  // offsets are read for candidates only
-                    if (!push_cands(ck, ci, c, cand, ek, (int32_t)(x - base), lane)) return false;
-                    active = cand && (j + 1 < cap);
-                }
-            }
-        } else if (!scan_threshold32(a, use_tab, base, lo32, hi32, T, ck, ci, c, lane)) {
-            return false;
-        }
-        done = true;
+    for (int64_t c0 = 0; c0 < size; c0 += 32) {
+        const int64_t i = c0 + lane + 1;
+        uint64_t k = kKeyInf;
+        if (i <= size) k = ordered_key((int32_t)(base + (uint32_t)i));
+        if (!push_cands(ck, ci, c, k < T, k, (int32_t)i, lane)) return false;
     }
-    if (!done && !scan_threshold(a, use_tab, base, 1, size, T, ck, ci, c, lane)) return false;
     const int64_t need = size < f ? size : f;
     if (c < need) return false;
     __syncwarp();
     if (need < 32) {
-        // Order the candidates on ONE 32-bit word each: the top 26 significant bits of the key (every candidate is
-        // below T, so bits above T's highest bit are zero) over the candidate's 6-bit buffer slot.  A 32-lane bitonic
-        // network on such words is one shuffle and one min/max per stage instead of three shuffles and a 64-bit
-        // compare.  Two candidates agreeing on those 26 bits inside the first need + 1 positions (about 1e-5 of the
-        // rows) would make the order ambiguous: the row is then redone by the exact streaming path.
         int shift = 38;
         if (T != kKeyInf) {
             const int nbits = 64 - __clzll((long long)T);
             shift = nbits > 26 ? nbits - 26 : 0;
         }
-        uint32_t v0 = 0xFFFFFFFFu, v1 = 0xFFFFFFFFu;
-        if (lane < c) v0 = ((uint32_t)(ck[lane] >> shift) << 6) | (uint32_t)lane;
-        sort32_u32(v0, lane);
-        if (c > 32) {  // warp-uniform
-            if (lane + 32 < c) v1 = ((uint32_t)(ck[lane + 32] >> shift) << 6) | (uint32_t)(lane + 32);
-            sort32_u32(v1, lane);
-            // 32 smallest of two ascending runs: min(v0[l], v1[31 - l]) is bitonic; one merge sorts it
-            v0 = min(v0, __shfl_sync(0xffffffffu, v1, 31 - lane));
-#pragma unroll
-            for (int stride = 16; stride > 0; stride >>= 1) cmpx_u32(v0, stride, (lane & stride) == 0);
-        }
-        const uint32_t up = __shfl_up_sync(0xffffffffu, v0, 1);
-        const bool tie = lane >= 1 && lane <= need && v0 != 0xFFFFFFFFu && (v0 >> 6) == (up >> 6);
-        if (__any_sync(0xffffffffu, tie)) return false;
-        if (lane < need) {
+        uint32_t v0;
+        const bool ok = order_cands_u32(c, (int)need, lane, [&](int slot) { return (uint32_t)(ck[slot] >> shift); }, v0);
+        if (ok && lane < need) {
             best.key[0] = ck[v0 & 63u];
             best.idx[0] = ci[v0 & 63u];
         }
         __syncwarp();
-        return true;
+        return ok;
     }
     PairKI v0{kKeyInf, 0}, v1{kKeyInf, 0};
     if (lane < c) {
@@ -480,7 +357,6 @@ __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& 
             v1.i = ci[lane + 32];
         }
         sort32(v1, lane);
-        // 32 smallest of two ascending runs: min(v0[l], v1[31 - l]) is bitonic; one merge sorts it
         const uint64_t ok = __shfl_sync(0xffffffffu, v1.k, 31 - lane);
         const int32_t oi = __shfl_sync(0xffffffffu, v1.i, 31 - lane);
         if (ok < v0.k) {
@@ -496,11 +372,130 @@ __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& 
     return true;
 }
 
-__device__ __forceinline__ bool row_uses_index(const HopArgs& a, int64_t size, uint32_t base) {
-    if (a.hx_keys == nullptr) return false;
-    const uint64_t lo = (uint64_t)base + 1, hi = (uint64_t)base + (uint64_t)size;
-    const int lg = a.hx_l_log2;
-    return hi < a.hx_limit && ((lo + ((1ULL << lg) - 1)) >> lg) < ((hi + 1) >> lg);
+// ---- hash ladder ------------------------------------------------------------------------------
+// The permutation key of window position i is H(base + i): a row of `size` entries asks for the f smallest values of
+// the FIXED sequence H(x) over the window x in [base + 1, base + size].  The sequence is indexed once per context
+// (gigl_ladder, common.cuh): level j holds exactly the inputs whose key is below 2^(64 - j) - a 2^-j sample of the
+// inputs - grouped by block x >> j, each as (key >> (32 - j)) << 32 | x.  A row of size s picks the level where
+// s >> j is in [32, 64): the f smallest keys of its window are, but for a Poisson tail, among the level's entries
+// inside the window, and those entries are ONE contiguous run of 32 .. 66 eight-byte words between two block starts.
+// So a row costs two 4-byte block-start reads (lane-parallel for the 32 rows of a tile) and two or three coalesced
+// 256-byte reads, whatever its length - a 91 701-entry hub row reads what a 64-entry row reads.  Rows under 64 entries
+// read their 4-byte truncated keys at level 0.  Candidates are cut by the same expected-count threshold as above (on
+// the truncated key: any threshold is valid, the candidates are then exactly the keys below it), ordered on 26 bits,
+// and every failure (too few / too many candidates, a 26-bit tie) is redone from the level's whole run with exact
+// 64-bit keys; a level with fewer than f keys inside the window (probability < 1e-4 at s >> j = 32, vanishing above)
+// falls through to the streaming scan.  Bit-exact by construction: the same keys, the same (key, idx) order.
+__device__ __forceinline__ void lad_plan(const HopArgs& a, uint32_t base, uint32_t s, int f, int& lvl, uint32_t& beg, uint32_t& end) {
+    lvl = -1;
+    beg = end = 0;
+    if (a.lad_limit == 0 || s == 0 || (uint64_t)base + (uint64_t)s >= a.lad_limit) return;
+    const uint32_t lo = base + 1u, hi = base + s;
+    const int wide = f <= 16 ? 0 : 1;  // fanouts over 16 read a level with twice the entries (s >> j in [64, 128))
+    if (s < (64u << wide)) {
+        lvl = 0;
+        beg = lo;
+        end = hi + 1u;
+        return;
+    }
+    int j = 26 - __clz((int)s) - wide;  // s >> j in [32, 64)
+    if (j > a.lad_levels) j = a.lad_levels;
+    lvl = j;
+    const uint32_t* bs = a.lad_bs[j];
+    beg = __ldg(bs + (lo >> j));
+    end = __ldg(bs + (hi >> j) + 1);
+}
+
+// entry e of the level as (truncated key) << 32 | x; ~0 past the run (never inside a window: x = 2^32 - 1)
+__device__ __forceinline__ uint64_t lad_load(const HopArgs& a, int lvl, uint32_t e, uint32_t end) {
+    if (e >= end) return ~0ULL;
+    if (lvl == 0) return ((uint64_t)__ldg(a.lad_tk0 + e) << 32) | e;
+    return __ldg(a.lad_ent[lvl] + e);
+}
+
+__device__ __forceinline__ bool push_cands32(uint32_t* __restrict__ ctk, uint32_t* __restrict__ cx, int& c, bool is_cand,
+                                             uint32_t tk, uint32_t x, int lane, int cap) {
+    const uint32_t m = __ballot_sync(0xffffffffu, is_cand);
+    if (m == 0) return true;
+    const int n = __popc(m);
+    if (c + n > cap) return false;
+    if (is_cand) {
+        const int p = c + __popc(m & ((1u << lane) - 1u));
+        ctk[p] = tk;
+        cx[p] = x;
+    }
+    c += n;
+    return true;
+}
+
+// `first` = lad_load of the run's first 32 entries (the caller has it in flight while the previous row is selected).
+// Returns true with best.idx[0] of lane l < min(s, f) = window position of the l-th smallest key.
+__device__ __forceinline__ bool select_ladder(const HopArgs& a, WarpTopK<1>& best, uint32_t s, uint32_t base, int f, int lane,
+                                              int lvl, uint32_t beg, uint32_t end, uint64_t first, uint32_t* ctk, uint32_t* cx) {
+    const uint32_t lo = base + 1u;
+    const int need = (int)(s < (uint32_t)f ? s : (uint32_t)f);
+    if (need < 32) {
+        float m = (float)f + fmaxf(14.f, 1.2f * (float)f);
+        if (m > 48.f) m = 48.f;
+        const float r = m * (float)(1u << lvl) / (float)s;  // wanted share of the level's entries inside the window
+        const bool all = !(r < 1.f);
+        const uint32_t Ttk = all ? 0xFFFFFFFFu : __float2uint_rz(r * 4294967296.f);
+        int c = 0;
+        bool ok = true;
+        for (uint32_t e0 = beg; e0 < end; e0 += 32) {
+            const uint64_t ent = (e0 == beg) ? first : lad_load(a, lvl, e0 + lane, end);
+            const uint32_t x = (uint32_t)ent, tk = (uint32_t)(ent >> 32);
+            const bool cand = (x - lo) < s && (all || tk < Ttk);
+            if (!push_cands32(ctk, cx, c, cand, tk, x, lane, kCandCap)) {
+                ok = false;
+                break;
+            }
+        }
+        if (ok && c >= need) {
+            __syncwarp();
+            const int nb = all ? 32 : 32 - __clz((int)Ttk);
+            const int shift = nb > 26 ? nb - 26 : 0;
+            uint32_t v0;
+            ok = order_cands_u32(c, need, lane, [&](int slot) { return ctk[slot] >> shift; }, v0);
+            if (ok && lane < need) best.idx[0] = (int32_t)(cx[v0 & 63u] - base);
+            __syncwarp();
+            if (ok) return true;
+        }
+    }
+    // second attempt: every entry of the level inside the window, exact 64-bit keys through the sorted list
+    int c = 0;
+    for (uint32_t e0 = beg; e0 < end; e0 += 32) {
+        const uint64_t ent = (e0 == beg) ? first : lad_load(a, lvl, e0 + lane, end);
+        const uint32_t x = (uint32_t)ent;
+        if (!push_cands32(ctk, cx, c, (x - lo) < s, (uint32_t)(ent >> 32), x, lane, kCandCapWide)) return false;
+    }
+    if (c < need) return false;
+    __syncwarp();
+    best.init();
+    for (int p0 = 0; p0 < c; p0 += 32) {
+        const int p = p0 + lane;
+        uint64_t k = kKeyInf;
+        int32_t i = 0;
+        if (p < c) {
+            const uint32_t x = cx[p];
+            k = ordered_key((int32_t)x);
+            i = (int32_t)(x - base);
+        }
+        if (best.empty) {  // warp-uniform
+            best.seed_sorted32(k, i, f, lane);
+            continue;
+        }
+        uint32_t cand = __ballot_sync(0xffffffffu, k < best.kth);
+        while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint64_t ck = __shfl_sync(0xffffffffu, k, src);
+            const int32_t ci = __shfl_sync(0xffffffffu, i, src);
+            if (ck < best.kth) best.insert(ck, ci, f, lane);
+        }
+    }
+    __syncwarp();
+    return true;
 }
 
 template <int KPL>
@@ -534,7 +529,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop
         return;
     }
     const uint32_t base = ssum + (uint32_t)a.cur_seed;
-    if (size > kHeavyThreshold && a.heavy_list != nullptr && !row_uses_index(a, size, base)) {
+    int lvl = -1;
+    uint32_t e_beg = 0, e_end = 0;
+    if (KPL == 1) lad_plan(a, base, (uint32_t)size, f, lvl, e_beg, e_end);
+    if (size > kHeavyThreshold && a.heavy_list != nullptr && lvl < 0) {
         int slot = 0;
         if (lane == 0) slot = atomicAdd(a.heavy_count, 1);
         slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -547,10 +545,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop
     WarpTopK<KPL> best;
     best.init();
     if constexpr (KPL == 1) {
-        __shared__ uint64_t s_ck[kWarpsPerBlock][kCandCap];
-        __shared__ int32_t s_ci[kWarpsPerBlock][kCandCap];
+        __shared__ uint64_t s_cand[kWarpsPerBlock][kCandCapWide];
         const int w = threadIdx.x >> 5;
-        if (size <= 32 || !select_threshold(a, best, size, base, f, lane, s_ck[w], s_ci[w])) {
+        uint32_t* ctk = reinterpret_cast<uint32_t*>(s_cand[w]);
+        bool done = false;
+        if (lvl >= 0)
+            done = select_ladder(a, best, (uint32_t)size, base, f, lane, lvl, e_beg, e_end, lad_load(a, lvl, e_beg + lane, e_end), ctk,
+                                 ctk + kCandCapWide);
+        if (!done && (size <= 32 || !select_threshold(a, best, size, base, f, lane, s_cand[w], reinterpret_cast<int32_t*>(s_cand[w] + kCandCap)))) {
             best.init();
             select_row<KPL>(a, best, size, base, f, lane);
         }
@@ -561,13 +563,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop
 }
 
 // ---- tile form of the hop kernel (fanout <= 32) ---------------------------------------------------
-// khop_hop_kernel is latency-bound (ncu: 41 % of the stall samples wait on global loads, DRAM 7 % busy): every warp
-// walks ONE row through four dependent round trips (parent slot -> rowptr pair -> key window -> winning col entries).
-// Here a warp owns a tile of 32 consecutive parent slots:
-//   A. lane l resolves slot l's metadata (parent vertex, path-id sum, sibling multiplicity, rowptr pair): the same
-//      loads, but 32 rows share each round trip;
-//   B. the rows are selected one after the other by the whole warp (metadata broadcast with shuffles); the winners'
-//      col offsets go to shared memory instead of being dereferenced;
+// A warp-per-row kernel is latency-bound (ncu: 41 % of the stall samples wait on global loads, DRAM 7 % busy): every
+// warp walks ONE row through its dependent round trips (parent slot -> rowptr pair -> block starts -> ladder run ->
+// winning col entries).  Here a warp owns a tile of 32 consecutive parent slots:
+//   A. lane l resolves slot l's metadata (parent vertex, path-id sum, sibling multiplicity, rowptr pair, ladder level
+//      and block starts): the same loads, but 32 rows share each round trip;
+//   B. the rows are selected one after the other by the whole warp (metadata broadcast with shuffles), the first 32
+//      ladder entries of row r + 1 in flight while row r is selected; the winners' col offsets go to shared memory
+//      instead of being dereferenced;
 //   C. the tile's col entries are loaded in one batch (up to f independent loads per lane) and written as one
 //      contiguous run of 32 * f outputs.
 // Same keys, same (key, idx) order, same outputs as khop_hop_kernel.
@@ -578,13 +581,18 @@ constexpr int kTileRows = 32;
 
 template <int MAXF>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) khop_tile_kernel(const HopArgs a) {
-    __shared__ uint64_t s_ck[kWarpsPerBlock][kCandCap];
-    __shared__ int32_t s_ci[kWarpsPerBlock][kCandCap];
+    // per warp: the ladder's candidates (truncated keys [160] | hash inputs [160]) or, for rows it does not cover,
+    // (keys [64] | positions [64])
+    __shared__ uint64_t s_cand[kWarpsPerBlock][kCandCapWide];
     __shared__ int32_t s_off[kWarpsPerBlock][kTileRows * MAXF];  // winner's offset inside its row, -1 = empty, -2 = row deferred
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
     const int f = a.fanouts[a.h - 1];
     const int64_t n_tiles = (a.n_parent + kTileRows - 1) / kTileRows;
+    uint32_t* ctk = reinterpret_cast<uint32_t*>(s_cand[w]);
+    uint32_t* cx = ctk + kCandCapWide;
+    uint64_t* ck = s_cand[w];
+    int32_t* ci = reinterpret_cast<int32_t*>(s_cand[w] + kCandCap);
     // persistent warps: tiles are handed out by an atomic counter, so a launch has no tail of half-empty waves and the
     // cheap tiles (empty parents) do not leave SMs idle behind the expensive ones
     for (;;) {
@@ -644,19 +652,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) kho
         }
     }
     const uint32_t base = ssum + (uint32_t)a.cur_seed;
-    if (state == 1 && size > kHeavyThreshold && a.heavy_list != nullptr && !row_uses_index(a, size, base)) {
+    const uint32_t size32 = (uint32_t)size;  // state == 1: size < 2^31
+    int lvl = -1;
+    uint32_t e_beg = 0, e_end = 0;
+    if (state == 1) lad_plan(a, base, size32, f, lvl, e_beg, e_end);
+    if (state == 1 && lvl < 0 && size > kHeavyThreshold && a.heavy_list != nullptr) {
         const int slot = atomicAdd(a.heavy_count, 1);
         if (slot < a.heavy_cap) {
             a.heavy_list[slot] = (int32_t)pslot;
             state = 2;
         }
     }
+    const int code = state | ((lvl + 1) << 2);
 
-    // ---- B: one row at a time, whole warp
+    // ---- B: one row at a time, whole warp; the next row's first ladder entries are in flight meanwhile
     int32_t* off = s_off[w];
+    int n_code = __shfl_sync(0xffffffffu, code, 0);
+    uint32_t n_beg = __shfl_sync(0xffffffffu, e_beg, 0), n_end = __shfl_sync(0xffffffffu, e_end, 0);
+    uint64_t pre = 0;
+    if (n_code >> 2) pre = lad_load(a, (n_code >> 2) - 1, n_beg + lane, n_end);
     for (int r = 0; r < n_rows; ++r) {
-        const int r_state = __shfl_sync(0xffffffffu, state, r);
-        const int64_t r_size = __shfl_sync(0xffffffffu, size, r);
+        const int r_code = n_code;
+        const uint32_t r_beg = n_beg, r_end = n_end;
+        const uint64_t cur = pre;
+        if (r + 1 < n_rows) {
+            n_code = __shfl_sync(0xffffffffu, code, r + 1);
+            n_beg = __shfl_sync(0xffffffffu, e_beg, r + 1);
+            n_end = __shfl_sync(0xffffffffu, e_end, r + 1);
+            if (n_code >> 2) pre = lad_load(a, (n_code >> 2) - 1, n_beg + lane, n_end);
+        }
+        const int r_state = r_code & 3;
+        const uint32_t r_size = __shfl_sync(0xffffffffu, size32, r);
         if (r_state != 1 || r_size == 0) {
             if (lane < f) off[r * f + lane] = (r_state == 2) ? -2 : -1;
             continue;
@@ -665,13 +691,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) kho
         const int32_t r_mult = __shfl_sync(0xffffffffu, mult, r);
         WarpTopK<1> best;
         best.init();
-        if (!select_threshold(a, best, r_size, r_base, f, lane, s_ck[w], s_ci[w])) {
+        bool done = false;
+        if (r_code >> 2) done = select_ladder(a, best, r_size, r_base, f, lane, (r_code >> 2) - 1, r_beg, r_end, cur, ctk, cx);
+        if (!done && !select_threshold(a, best, (int64_t)r_size, r_base, f, lane, ck, ci)) {
             best.init();
-            select_row<1>(a, best, r_size, r_base, f, lane);
+            select_row<1>(a, best, (int64_t)r_size, r_base, f, lane);
         }
         int32_t q = best.idx[0] - 1;
         if (r_mult != 1) q /= r_mult;  // sorted(m copies)[q] = row[q / m]
-        if (lane < f) off[r * f + lane] = (lane < r_size) ? q : -1;
+        if (lane < f) off[r * f + lane] = ((uint32_t)lane < r_size) ? q : -1;
     }
     __syncwarp();
 
@@ -739,62 +767,125 @@ __global__ void __launch_bounds__(kHeavyWarps * 32) khop_heavy_kernel(const HopA
     }
 }
 
-__global__ void build_key_table_kernel(int64_t n, uint64_t* __restrict__ table) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) table[x] = ordered_key((int32_t)(uint32_t)x);
+
+// ---- hash ladder: build -------------------------------------------------------------------------
+struct LadderPtrs {
+    uint32_t* tk0;
+    uint32_t* bs[GIGL_LAD_MAX_LEVELS + 1];   // pass 1: per-block counts shifted by one; after the scans: block starts
+    uint32_t* cur[GIGL_LAD_MAX_LEVELS + 1];  // pass 2: fill cursors (a copy of the block starts)
+    uint64_t* ent[GIGL_LAD_MAX_LEVELS + 1];
+};
+
+// pass 1: level-0 truncated keys and, for every level an input belongs to, its block's count (at index block + 1)
+__global__ void __launch_bounds__(256) ladder_count_kernel(uint32_t limit, int levels, const LadderPtrs p) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < limit; x += stride) {
+        const uint64_t key = ordered_key((int32_t)x);
+        p.tk0[x] = (uint32_t)(key >> 32);
+        int z = key ? __clzll((long long)key) : 64;
+        if (z > levels) z = levels;
+        for (int j = 1; j <= z; ++j) atomicAdd(p.bs[j] + (x >> j) + 1, 1u);
+    }
 }
 
-static int ensure_hash_index(gigl_graph* g, int fmax, int n_hops) {
-    gigl_ctx* ctx = g->ctx;
-    if (!g->hx_enabled) return GIGL_OK;
-    const int cap = fmax <= 16 ? 16 : fmax <= 32 ? 32 : fmax <= 64 ? 64 : 128;
-    int lg = 0;
-    static const int lmul = getenv("GIGL_HX_LMUL") ? atoi(getenv("GIGL_HX_LMUL")) : 8;  // block length / cap (experiments)
-    while ((1 << lg) < lmul * cap) ++lg;
-    uint64_t want = (uint64_t)n_hops * (uint64_t)g->n_nodes + (1ULL << 21);
+// pass 2: the entries, grouped by block (their order inside a block is free: a row's candidates are re-ordered by key)
+__global__ void __launch_bounds__(256) ladder_fill_kernel(uint32_t limit, int levels, const LadderPtrs p) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < limit; x += stride) {
+        const uint64_t key = ordered_key((int32_t)x);
+        int z = key ? __clzll((long long)key) : 64;
+        if (z > levels) z = levels;
+        for (int j = 1; j <= z; ++j) {
+            const uint32_t pos = atomicAdd(p.cur[j] + (x >> j), 1u);
+            p.ent[j][pos] = ((key >> (32 - j)) << 32) | x;
+        }
+    }
+}
+
+static void ladder_free(gigl_ladder& lad) {
+    if (lad.blob_a) cudaFree(lad.blob_a);
+    if (lad.blob_b) cudaFree(lad.blob_b);
+    lad = gigl_ladder();
+}
+
+// Covers hash inputs [0, want).  The ladder is an accelerator, not a requirement: if it cannot be allocated the
+// sampler hashes every window on the fly.
+static int ensure_ladder(gigl_ctx* ctx, uint64_t want) {
     if (want > (1ULL << 31)) want = 1ULL << 31;
-    const int64_t n_blocks = (int64_t)(want >> lg);
-    const uint64_t limit = (uint64_t)n_blocks << lg;
-    if (g->hx_keys && g->hx_cap == cap && g->hx_limit >= limit) return GIGL_OK;
+    if (ctx->lad.limit >= want) return GIGL_OK;
     GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (g->hx_keys) cudaFree(g->hx_keys);
-    if (g->hx_offs) cudaFree(g->hx_offs);
-    g->hx_keys = nullptr;
-    g->hx_offs = nullptr;
-    g->hx_limit = 0;
-    if (n_blocks == 0) return GIGL_OK;
-    cudaError_t e = cudaMalloc(&g->hx_keys, sizeof(uint64_t) * (size_t)n_blocks * cap);
-    if (e == cudaSuccess) e = cudaMalloc(&g->hx_offs, sizeof(uint16_t) * (size_t)n_blocks * cap);
-    if (e != cudaSuccess) {  // the index is an accelerator, not a requirement: run without it
-        if (g->hx_keys) cudaFree(g->hx_keys);
-        g->hx_keys = nullptr;
-        g->hx_offs = nullptr;
+    ladder_free(ctx->lad);
+    const uint32_t limit = (uint32_t)want;  // 2^31 fits
+    const int levels = GIGL_LAD_MAX_LEVELS;
+    auto up = [](size_t v) { return (v + 63) & ~(size_t)63; };
+    size_t bs_elems = 0, bs_off[GIGL_LAD_MAX_LEVELS + 1] = {};
+    for (int j = 1; j <= levels; ++j) {
+        bs_off[j] = bs_elems;
+        bs_elems += up((size_t)(limit >> j) + 2);
+    }
+    const size_t tk_elems = up(limit);
+    gigl_ladder lad;
+    uint32_t* cursors = nullptr;
+    cudaError_t e = cudaMalloc(&lad.blob_a, sizeof(uint32_t) * (tk_elems + bs_elems));
+    if (e == cudaSuccess) e = cudaMalloc(&cursors, sizeof(uint32_t) * bs_elems);
+    if (e != cudaSuccess) {
+        ladder_free(lad);
+        if (cursors) cudaFree(cursors);
         cudaGetLastError();
         return GIGL_OK;
     }
-    const int grid = ctx->sm_count * 8;
-    if (cap <= 32)
-        build_hash_index_kernel<1><<<grid, 256, 0, ctx->stream>>>(n_blocks, lg, cap, g->hx_keys, g->hx_offs);
-    else if (cap == 64)
-        build_hash_index_kernel<2><<<grid, 256, 0, ctx->stream>>>(n_blocks, lg, cap, g->hx_keys, g->hx_offs);
-    else
-        build_hash_index_kernel<4><<<grid, 256, 0, ctx->stream>>>(n_blocks, lg, cap, g->hx_keys, g->hx_offs);
-    GIGL_LAUNCHED(ctx);
-    g->hx_cap = cap;
-    g->hx_l_log2 = lg;
-    g->hx_limit = limit;
-    // the full key table (8 bytes per hash input): short windows read their keys instead of hashing them
-    if (g->hk_table) cudaFree(g->hk_table);
-    g->hk_table = nullptr;
-    g->hk_limit = 0;
-    if (cudaMalloc(&g->hk_table, sizeof(uint64_t) * (size_t)limit) == cudaSuccess) {
-        build_key_table_kernel<<<grid, 256, 0, ctx->stream>>>((int64_t)limit, g->hk_table);
-        GIGL_LAUNCHED(ctx);
-        g->hk_limit = limit;
-    } else {
-        g->hk_table = nullptr;
-        cudaGetLastError();
+    LadderPtrs p{};
+    p.tk0 = lad.tk0 = (uint32_t*)lad.blob_a;
+    for (int j = 1; j <= levels; ++j) {
+        p.bs[j] = lad.bs[j] = lad.tk0 + tk_elems + bs_off[j];
+        p.cur[j] = cursors + bs_off[j];
     }
+    cudaStream_t st = ctx->stream;
+    const int grid = ctx->sm_count * 8;
+    GIGL_CUDA(ctx, cudaMemsetAsync(lad.tk0 + tk_elems, 0, sizeof(uint32_t) * bs_elems, st));
+    ladder_count_kernel<<<grid, 256, 0, st>>>(limit, levels, p);
+    GIGL_LAUNCHED(ctx);
+    // counts -> block starts (inclusive sum of the shifted counts; CUB scan = plumbing), one scan per level
+    size_t temp_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, temp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)(limit >> 1) + 2, st);
+    void* temp = nullptr;
+    int rc = gigl_scratch(ctx, GIGL_SLOT_WORK, temp_bytes + 256, &temp);
+    if (rc != GIGL_OK) {
+        ladder_free(lad);
+        cudaFree(cursors);
+        return rc;
+    }
+    uint32_t totals[GIGL_LAD_MAX_LEVELS + 1] = {};
+    for (int j = 1; j <= levels; ++j) {
+        const int64_t n = (int64_t)(limit >> j) + 2;
+        size_t tb = temp_bytes;
+        e = cub::DeviceScan::InclusiveSum(temp, tb, lad.bs[j], lad.bs[j], n, st);
+        ctx->launches++;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&totals[j], lad.bs[j] + n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) break;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cursors, lad.tk0 + tk_elems, sizeof(uint32_t) * bs_elems, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    size_t ent_elems = 0, ent_off[GIGL_LAD_MAX_LEVELS + 1] = {};
+    for (int j = 1; j <= levels; ++j) {
+        ent_off[j] = ent_elems;
+        ent_elems += up((size_t)totals[j] + 1);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&lad.blob_b, sizeof(uint64_t) * ent_elems);
+    if (e != cudaSuccess) {
+        ladder_free(lad);
+        cudaFree(cursors);
+        cudaGetLastError();
+        return GIGL_OK;
+    }
+    for (int j = 1; j <= levels; ++j) p.ent[j] = lad.ent[j] = (uint64_t*)lad.blob_b + ent_off[j];
+    ladder_fill_kernel<<<grid, 256, 0, st>>>(limit, levels, p);
+    GIGL_LAUNCHED(ctx);
+    GIGL_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(cursors);
+    lad.limit = limit;
+    lad.levels = levels;
+    ctx->lad = lad;
     return GIGL_OK;
 }
 
@@ -842,24 +933,26 @@ int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
 
     // heavy-row worklist: one int32 counter + up to heavy_cap slots, reused hop after hop
     const int32_t heavy_cap = 1 << 22;
+    int rc;
+    // hash inputs of a window: path-id sum (< n_hops * n_nodes) + seed * call number + position; the margin covers the
+    // seed term and the row length of all but the longest rows' tails
+    if (g->hx_enabled && (rc = ensure_ladder(ctx, (uint64_t)n_hops * (uint64_t)g->n_nodes + (1ULL << 21))) != GIGL_OK) return rc;
     void* scratch = nullptr;
-    int rc = gigl_scratch(ctx, GIGL_SLOT_WORK, sizeof(int32_t) * ((size_t)heavy_cap + 64), &scratch);
+    rc = gigl_scratch(ctx, GIGL_SLOT_WORK, sizeof(int32_t) * ((size_t)heavy_cap + 64), &scratch);
     if (rc != GIGL_OK) return rc;
     int32_t* heavy_count = (int32_t*)scratch;
     int32_t* heavy_list = heavy_count + 64;
 
-    int fmax = 0;
-    for (int h = 0; h < n_hops; ++h) fmax = fanouts[h] > fmax ? fanouts[h] : fmax;
-    if ((rc = ensure_hash_index(g, fmax, n_hops)) != GIGL_OK) return rc;
-
     HopArgs a{};
-    a.hx_keys = g->hx_enabled ? g->hx_keys : nullptr;
-    a.hx_offs = g->hx_offs;
-    a.hx_limit = g->hx_limit;
-    a.hx_l_log2 = g->hx_l_log2;
-    a.hx_cap = g->hx_cap;
-    a.hk_table = (g->hx_enabled && a.hx_keys) ? g->hk_table : nullptr;
-    a.hk_limit = g->hk_limit;
+    if (g->hx_enabled && ctx->lad.limit) {
+        a.lad_tk0 = ctx->lad.tk0;
+        for (int j = 1; j <= ctx->lad.levels; ++j) {
+            a.lad_bs[j] = ctx->lad.bs[j];
+            a.lad_ent[j] = ctx->lad.ent[j];
+        }
+        a.lad_limit = ctx->lad.limit;
+        a.lad_levels = ctx->lad.levels;
+    }
     a.rowptr = g->rowptr;
     a.col = g->col;
     a.n_nodes = g->n_nodes;

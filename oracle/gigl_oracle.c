@@ -32,6 +32,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <omp.h>
 
 #define P64_1 0x9E3779B185EBCA87ULL
 #define P64_2 0xC2B2AE3D27D4EB4FULL
@@ -405,4 +406,143 @@ int oracle_gcn_conv_f64(int64_t n, int64_t e, int32_t F, int32_t O, const int64_
 #define SQRT sqrt
     GCN_BODY(double)
 #undef SQRT
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Batch collation for the TIMED CPU baseline (bench.py): the union of B sampled subgraphs with nodes de-duplicated by
+ * id and edges by (src, dst), as the reference's GraphBuilder / collate fns build it
+ * (python/gigl/src/common/graph_builder/abstract_graph_builder.py:49-197, pyg_graph_builder.py:20-69,
+ * training/v1/lib/data_loaders/rooted_node_neighborhood_data_loader.py:78-) - the same result as
+ * oracle.np_collate_fast (unique roots in first-occurrence order, then the other nodes ascending; edges ascending by
+ * (dst, src) global id), with every core of the host: a parallel LSD radix sort of the edge keys and dense per-vertex
+ * maps.  Returns 0, or -1 on a bad argument / allocation failure.
+ *   nbr[h]: int32 [n_roots * prod fanouts[0..h]] padded tree (-1 = empty slot), level h + 1 children of level h
+ *   node_ids (cap n_roots + slots), edge_src / edge_dst (cap slots, local ids), root_index [n_roots]            */
+static void radix_pass_u64(const uint64_t* in, uint64_t* out, int64_t n, int shift, int n_threads, int64_t* hist /* [T][256] */) {
+#pragma omp parallel num_threads(n_threads)
+    {
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();  /* the team may be smaller than asked for */
+        const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        int64_t* h = hist + (int64_t)t * 256;
+        for (int d = 0; d < 256; ++d) h[d] = 0;
+        for (int64_t i = lo; i < hi; ++i) h[(in[i] >> shift) & 255]++;
+#pragma omp barrier
+#pragma omp single
+        {
+            int64_t run = 0;
+            for (int d = 0; d < 256; ++d)
+                for (int tt = 0; tt < nt; ++tt) {
+                    const int64_t c = hist[(int64_t)tt * 256 + d];
+                    hist[(int64_t)tt * 256 + d] = run;
+                    run += c;
+                }
+        }
+        for (int64_t i = lo; i < hi; ++i) out[h[(in[i] >> shift) & 255]++] = in[i];
+    }
+}
+
+int oracle_collate(int64_t n_graph_nodes, const int32_t* roots, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
+                   const int32_t* const* nbr, int64_t* node_ids, int64_t* n_nodes_out, int64_t* edge_src, int64_t* edge_dst,
+                   int64_t* n_edges_out, int64_t* root_index, int32_t n_threads) {
+    if (n_graph_nodes <= 0 || n_roots < 0 || n_hops < 1 || !fanouts || !nbr) return -1;
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    int64_t slots = 0, width = n_roots;
+    for (int h = 0; h < n_hops; ++h) {
+        width *= fanouts[h];
+        slots += width;
+    }
+    uint64_t* ka = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(slots > 0 ? slots : 1));
+    uint64_t* kb = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(slots > 0 ? slots : 1));
+    int64_t* hist = (int64_t*)malloc(sizeof(int64_t) * 256 * (size_t)n_threads);
+    int32_t* lid = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_graph_nodes);
+    if (!ka || !kb || !hist || !lid) {
+        free(ka); free(kb); free(hist); free(lid);
+        return -1;
+    }
+    /* 1. keys dst << 32 | src of the filled slots */
+    int64_t n_keys = 0;
+    width = n_roots;
+    for (int h = 0; h < n_hops; ++h) {
+        const int32_t* parents = h == 0 ? roots : nbr[h - 1];
+        const int32_t f = fanouts[h];
+        width *= f;
+        for (int64_t s = 0; s < width; ++s) {
+            const int32_t c = nbr[h][s];
+            if (c >= 0) ka[n_keys++] = ((uint64_t)(uint32_t)parents[s / f] << 32) | (uint32_t)c;
+        }
+    }
+    /* 2. sort (bytes that can be non-zero only), unique */
+    int id_bits = 1;
+    while (id_bits < 32 && ((int64_t)1 << id_bits) < n_graph_nodes) ++id_bits;
+    uint64_t *in = ka, *out = kb;
+    for (int part = 0; part < 2; ++part)
+        for (int b = 0; b * 8 < id_bits; ++b) {
+            radix_pass_u64(in, out, n_keys, part * 32 + b * 8, n_threads, hist);
+            uint64_t* t = in; in = out; out = t;
+        }
+    int64_t n_edges = 0;
+    for (int64_t i = 0; i < n_keys; ++i)
+        if (i == 0 || in[i] != in[i - 1]) out[n_edges++] = in[i];
+    const uint64_t* uk = out;
+    /* 3. nodes: unique roots in first-occurrence order, then every other endpoint ascending (dense maps) */
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int64_t v = 0; v < n_graph_nodes; ++v) lid[v] = -1;
+    int64_t n_nodes = 0;
+    for (int64_t i = 0; i < n_roots; ++i) {
+        const int32_t r = roots[i];
+        if (r < 0 || r >= n_graph_nodes) { free(ka); free(kb); free(hist); free(lid); return -1; }
+        if (lid[r] < 0) {
+            lid[r] = (int32_t)n_nodes;
+            node_ids[n_nodes++] = r;
+        }
+    }
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int64_t i = 0; i < n_edges; ++i) {  /* -2 = endpoint that is not a root (racing writers store the same value) */
+        const int32_t s = (int32_t)(uk[i] & 0xffffffffu), d = (int32_t)(uk[i] >> 32);
+        int32_t cur;
+#pragma omp atomic read
+        cur = lid[s];
+        if (cur == -1) {
+#pragma omp atomic write
+            lid[s] = -2;
+        }
+#pragma omp atomic read
+        cur = lid[d];
+        if (cur == -1) {
+#pragma omp atomic write
+            lid[d] = -2;
+        }
+    }
+    {
+        int64_t* cnt = hist;  /* reuse: per-thread counts */
+        for (int t = 0; t < n_threads; ++t) cnt[t] = 0;
+#pragma omp parallel num_threads(n_threads)
+        {
+            const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+            const int64_t lo = n_graph_nodes * t / nt, hi = n_graph_nodes * (t + 1) / nt;
+            int64_t c = 0;
+            for (int64_t v = lo; v < hi; ++v) c += lid[v] == -2;
+            cnt[t] = c;
+#pragma omp barrier
+            int64_t base = n_nodes;
+            for (int tt = 0; tt < t; ++tt) base += cnt[tt];
+            for (int64_t v = lo; v < hi; ++v)
+                if (lid[v] == -2) {
+                    lid[v] = (int32_t)base;
+                    node_ids[base++] = v;
+                }
+        }
+        for (int t = 0; t < n_threads; ++t) n_nodes += cnt[t];
+    }
+    /* 4. edge_index in local ids, root rows */
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int64_t i = 0; i < n_edges; ++i) {
+        edge_src[i] = lid[(int32_t)(uk[i] & 0xffffffffu)];
+        edge_dst[i] = lid[(int32_t)(uk[i] >> 32)];
+    }
+    for (int64_t i = 0; i < n_roots; ++i) root_index[i] = lid[roots[i]];
+    *n_nodes_out = n_nodes;
+    *n_edges_out = n_edges;
+    free(ka); free(kb); free(hist); free(lid);
+    return 0;
 }

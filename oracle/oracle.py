@@ -57,6 +57,8 @@ def lib():
             f = getattr(L, nm)
             f.restype = C.c_int
             f.argtypes = [i64, i64, i32, i32, p, p, p, p, p, p, i32]
+        L.oracle_collate.restype = C.c_int
+        L.oracle_collate.argtypes = [i64, p, i64, p, i32, p, p, p, p, p, p, p, i32]
         _lib = L
     return _lib
 
@@ -647,6 +649,25 @@ def np_collate_fast(roots, nbr, fanouts):
 
     ei = np.stack([loc(src), loc(dst)]) if len(keys) else np.zeros((2, 0), np.int64)
     return node_ids, ei, loc(roots) if len(roots) else np.zeros(0, np.int64)
+
+
+def c_collate(n_graph_nodes, roots, nbr, fanouts, n_threads=None):
+    """np_collate_fast in C + OpenMP (oracle_collate): the collation of the TIMED CPU baseline, every host core."""
+    roots = np.ascontiguousarray(roots, dtype=np.int32)
+    fan = np.ascontiguousarray(fanouts, dtype=np.int32)
+    levels = [np.ascontiguousarray(t, dtype=np.int32) for t in nbr]
+    slots = int(sum(t.size for t in levels))
+    node_ids = np.empty(len(roots) + slots, dtype=np.int64)
+    es = np.empty(max(slots, 1), dtype=np.int64)
+    ed = np.empty(max(slots, 1), dtype=np.int64)
+    ridx = np.empty(max(len(roots), 1), dtype=np.int64)
+    nn, ne = C.c_int64(), C.c_int64()
+    ptrs = (C.c_void_p * len(levels))(*[t.ctypes.data for t in levels])
+    rc = lib().oracle_collate(int(n_graph_nodes), _ptr(roots), len(roots), _ptr(fan), len(fan), ptrs, _ptr(node_ids), C.byref(nn),
+                              _ptr(es), _ptr(ed), C.byref(ne), _ptr(ridx), int(n_threads or 0))
+    if rc != 0:
+        raise ValueError("oracle_collate: bad argument")
+    return node_ids[:nn.value], np.stack([es[:ne.value], ed[:ne.value]]), ridx[:len(roots)]
 
 
 def torch_sage_forward(x, edge_index, layers, n_threads=None):
