@@ -3,10 +3,14 @@
 
 A "step" = one batch of B roots through the whole path: k-hop rooted-neighbourhood sampling
 (fanout [15, 10], GiGL's deterministic hash permutation) -> batch collation -> 2-layer GraphSAGE
-over the coalesced batch graph -> root embeddings.  Workload at N = 1 is BASELINE.json configs[1]:
-the ogbn-products-shaped synthetic graph (N = 2,449,029, 61.86M undirected pairs mirrored,
-F = 100 fp32, 100 -> 256 -> 47), whole CSR + features HBM-resident.  At N > 1 every rank holds a
-replica and samples its own contiguous range of roots (weak scaling, no data-path collective).
+over the coalesced batch graph -> root embeddings.
+
+  N = 1   BASELINE.json configs[1]: the ogbn-products-shaped synthetic graph (N = 2,449,029, 61.86M undirected pairs
+          mirrored, F = 100 fp32, 100 -> 256 -> 47), whole CSR + features HBM-resident.
+  N > 1   the PARTITIONED path of north_star: CSR replicated, the feature table sharded 1/N by node range and mapped
+          flat over NVLink, every rank samples its own contiguous range of roots and pulls its batch's remote rows
+          (the remote-neighbour feature halo) once per unique node; the replicated variant is measured beside it
+          (key "replicated").  At N = 8 the 1e8-node / 1e9-edge graph of configs[3] is run as well (key "g1b").
 
     python bench.py --gpus N --steps K --warmup W            # the CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
@@ -16,6 +20,8 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 from __future__ import annotations
 
 import argparse
+import glob
+import hashlib
 import json
 import os
 import sys
@@ -35,33 +41,38 @@ WORKLOADS = {
     "products-like": dict(nodes=2_449_029, pairs=61_859_140, F=100, H=256, O=47, directed=False, cfg="configs[1]"),
     "products-like-f128": dict(nodes=2_449_029, pairs=61_859_140, F=128, H=256, O=47, directed=False, cfg="configs[1] (F = 128 variant)"),
     "toy-1k": dict(nodes=1_000, pairs=5_000, F=16, H=16, O=7, directed=False, cfg="configs[0]"),
-    # N = 1e8, E = 1e9 directed RMAT, F = 128; every GPU holds the whole CSR (4.8 GB) + features (51 GB)
+    # N = 1e8, E = 1e9 directed RMAT, F = 128; CSR (4.8 GB) on every GPU, features (51 GB) sharded or replicated
     "g1b": dict(nodes=100_000_000, pairs=1_000_000_000, F=128, H=128, O=128, directed=True, cfg="configs[3]"),
+    # a 1/64 scale model of g1b for quick checks of the same code path
+    "g1b-small": dict(nodes=1_562_500, pairs=15_625_000, F=128, H=128, O=128, directed=True, cfg="configs[3] at 1/64 scale"),
 }
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gigl_b200", choices=["gigl_b200", "reference"])
     ap.add_argument("--workload", default="products-like", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=65536, help="roots per step per GPU")
+    ap.add_argument("--batch", type=int, default=65536, help="roots per step per GPU (both arms)")
     ap.add_argument("--fanout", default="15,10")
-    ap.add_argument("--cpu-sample-roots", type=int, default=8192, help="roots per CPU-baseline step")
+    ap.add_argument("--cpu-steps", type=int, default=2, help="timed steps of the cpu_baseline leg of the product arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-graph", action="store_true")
     ap.add_argument("--e2e-padded", action="store_true", help="e2e returns the padded-tree index sets instead of the packed form")
-    ap.add_argument("--pitch-features", action="store_true", help="experiment: replicated feature rows pitched to 128-byte multiples")
-    ap.add_argument("--shard-features", action="store_true",
-                    help="features sharded by node range over the N GPUs and mapped as one flat table (remote rows over NVLink) "
-                         "instead of replicated")
+    ap.add_argument("--features", default="auto", choices=["auto", "sharded", "replicated"],
+                    help="auto = local table at N = 1, sharded over the N GPUs (NVLink halo) at N > 1")
     ap.add_argument("--halo", default="staged", choices=["staged", "direct"],
-                    help="--shard-features only: 'staged' copies each unique batch node's row into local HBM once per step and "
+                    help="sharded features: 'staged' copies each unique batch node's row into local HBM once per step and "
                          "gathers from the copy; 'direct' loads one (mostly remote) row per unique edge inside the gather kernel")
-    return ap.parse_args()
+    ap.add_argument("--hot-rows", type=float, default=None,
+                    help="sharded features: fraction of the table (highest in-degree vertices) replicated on every GPU "
+                         "(default: GIGL_HOT_ROWS or 0.125)")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the replicated variant and the g1b record")
+    ap.add_argument("--with-g1b", action="store_true", help="run the g1b record at any N (default: N = 8 only)")
+    return ap.parse_args(argv)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -129,17 +140,41 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, where from).  Kernels here are timed inside a step, never alone."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained") or d.get("bf16_tflops") or 2250.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 2250.0, "fallback (B200_PROFILING.md: 6.65 TB/s HBM, 2.25 PFLOP/s dense bf16)"
+
+
+def source_digest():
+    """sha256 over the CUDA sources: ties a committed ncu DRAM-traffic record to the kernels it was measured on."""
+    h = hashlib.sha256()
+    for p in sorted(glob.glob(os.path.join(ROOT, "gigl_b200", "csrc", "*.cu*"))):
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """{kernel phase: DRAM read+write bytes per launch} from the round's ncu capture (profiles/r2_traffic.json, written
+    by scripts/ncu_traffic.py from the committed CSV) - only if it was taken on the CUDA sources that are running now."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        if d.get("source_digest") == source_digest():
+            return d
+    except Exception:
+        pass
+    return None
 
 
 def bind_to_gpu_numa_node(device_index: int):
     """N > 1 only: pins this rank's threads to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is
-    allocated, so the e2e path's host buffers live on the socket the GPU's PCIe link hangs off (with 8 ranks placed by
-    the scheduler, half of the device-to-host copies otherwise cross the socket interconnect).  Best effort."""
+    allocated, so the e2e path's host buffers live on the socket the GPU's PCIe link hangs off.  Best effort."""
     try:
         import pynvml
 
@@ -168,42 +203,52 @@ from gigl_b200.sharding import max_over_ranks, root_batches  # noqa: E402
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU pipeline = the reference algorithm restated (oracle/): sampler in C + OpenMP, collation in
-# numpy, aggregate with torch's own CPU kernels.  Timed as the baseline; never the product path.
+# CPU pipeline = the reference algorithm restated (oracle/): sampler and collation in C + OpenMP,
+# feature lookup and aggregate with torch's own CPU kernels.  Timed as the baseline; never the product path.
 # ----------------------------------------------------------------------------------------------
-def cpu_step(O, rowptr, col, x, roots, fan, layers, threads):
+def cpu_step(O, rowptr, col, x, roots, fan, layers, threads, n_nodes):
+    import torch
+
     nbr, _ = O.c_sample_khop(rowptr, col, roots, fan, n_threads=threads)
     t1 = time.perf_counter()
-    node_ids, ei, root_idx = O.np_collate_fast(roots, nbr, fan)
-    xb = x(node_ids) if callable(x) else x[node_ids]
+    node_ids, ei, root_idx = O.c_collate(n_nodes, roots, nbr, fan, n_threads=threads)
+    xb = x(node_ids) if callable(x) else x.index_select(0, torch.from_numpy(node_ids)).numpy()
     t2 = time.perf_counter()
     out = O.torch_sage_forward(xb, ei, layers, n_threads=threads)[root_idx]
     return out, ei.shape[1], t1, t2
 
 
 def run_cpu_baseline(rowptr, col, x, fan, layers, n_nodes, n_roots, steps, warmup):
+    import torch
+
     from oracle import oracle as O
 
     threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    if not callable(x):
+        x = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
     batches = root_batches(n_nodes, 0, 1, n_roots, steps + warmup)
     for b in batches[:warmup]:
-        cpu_step(O, rowptr, col, x, b, fan, layers, threads)
+        cpu_step(O, rowptr, col, x, b, fan, layers, threads, n_nodes)
     t_s = t_c = t_a = 0.0
     edges = 0
+    per_step = []
     t0 = time.perf_counter()
     for b in batches[warmup:]:
         ta = time.perf_counter()
-        _, e, t1, t2 = cpu_step(O, rowptr, col, x, b, fan, layers, threads)
+        _, e, t1, t2 = cpu_step(O, rowptr, col, x, b, fan, layers, threads, n_nodes)
         tb = time.perf_counter()
         t_s += t1 - ta
         t_c += t2 - t1
         t_a += tb - t2
+        per_step.append((tb - ta) * 1e3)
         edges += e * len(layers)
     dt = time.perf_counter() - t0
     return {"value": n_roots * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{steps} step(s) x {n_roots} roots (ids in order) of the same graph/fanout/model; C+OpenMP sampler, numpy collate, "
-                      f"torch-CPU SAGE on the whole batch graph as the reference does",
-            "seconds": dt, "phase_seconds": {"sample": t_s, "collate": t_c, "aggregate": t_a},
+            "sample": f"{steps} step(s) x {n_roots} roots (ids in order) of the same graph/fanout/model, every host core: C+OpenMP sampler "
+                      f"and collation, torch-CPU feature lookup and SAGE on the whole batch graph as the reference does",
+            "seconds": dt, "phase_seconds": {"sample": t_s, "collate_and_lookup": t_c, "aggregate": t_a},
+            "ms_per_step_min": float(np.min(per_step)), "ms_per_step_median": float(np.median(per_step)),
             "aggregated_edges_per_s": edges / max(t_a, 1e-9)}
 
 
@@ -219,19 +264,32 @@ def cpu_model():
 
 
 # ----------------------------------------------------------------------------------------------
-def build_inputs_torch(wl, dev):
+def build_inputs_torch(wl, dev, with_features=True):
     """Synthetic graph + features + weights (seeded; identical on every box)."""
     from gigl_b200 import synth
 
     src, dst = synth.rmat_edges_torch(wl["nodes"], wl["pairs"], dev)
-    x = synth.features_torch(wl["nodes"], wl["F"], dev)
+    x = synth.features_torch(wl["nodes"], wl["F"], dev) if with_features else None
     layers = synth.sage_weights(np.random.default_rng(synth.GEN_SEED), [wl["F"], wl["H"], wl["O"]])
     return src, dst, x, layers
 
 
+def workload_config(wl_name, wl, fan, batch, world):
+    """The same dict for both arms (--impl gigl_b200 / reference) of one (workload, N)."""
+    edges = (f"{wl['pairs']} directed edges (duplicates kept)" if wl["directed"] else
+             f"{wl['pairs']} undirected pairs de-duplicated+mirrored")
+    return {"workload": f"BASELINE.json {wl['cfg']} shape: {wl_name} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
+                        f"N={wl['nodes']}, {edges}, F={wl['F']} fp32, "
+                        f"2-hop fanout {fan}, GraphSAGE {wl['F']}->{wl['H']}->{wl['O']} inference on the coalesced batch graph",
+            "roots_per_step_per_gpu": batch, "fanout": fan, "seed": {"generator": 20260101, "sampler_base_seed": 42, "first_call_no": 1},
+            "roots": "rank r of N takes the contiguous id range [r*N_nodes/N, (r+1)*N_nodes/N), step s its next B ids",
+            "l2": f"every step reads different roots from a {wl['nodes'] * wl['F'] * 4 / 1e9:.2f} GB feature table + the CSR "
+                  "(>> 126 MB L2); no flush needed"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; Spark / PyG are not runnable
-    here) on the host cores, same workload / metric."""
+    here) on the host cores, same workload / metric / roots per step."""
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -241,17 +299,20 @@ def run_reference(args):
 
     wl = WORKLOADS[args.workload]
     fan = [int(v) for v in args.fanout.split(",")]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     src, dst, x, layers = build_inputs_torch(wl, dev)  # input preparation only (torch ops, not timed)
     rowptr, col = O.torch_build_in_csr(src, dst, wl["nodes"], wl["directed"])
-    rowptr, col, x = rowptr.cpu().numpy(), col.cpu().numpy(), x.cpu().numpy()
+    rowptr, col, x = rowptr.cpu().numpy(), col.cpu().numpy(), x.cpu()
     del src, dst
-    n_roots = args.cpu_sample_roots
+    n_roots = min(args.batch, wl["nodes"] // max(world, 1))
     res = run_cpu_baseline(rowptr, col, x, fan, layers, wl["nodes"], n_roots, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / args.steps * 1e3,
+            "ms_per_step_min": res["ms_per_step_min"], "ms_per_step_median": res["ms_per_step_median"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, wl, fan, n_roots, "each step is a bounded sample of the workload"),
+            "config": workload_config(args.workload, wl, fan, n_roots, world),
+            "note": "the reference's CPU pipeline restated (oracle port) on rank 0's host cores; each step = one batch of the workload",
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "phase_seconds": res["phase_seconds"], "aggregated_edges_per_s": res["aggregated_edges_per_s"],
@@ -259,254 +320,397 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, wl, fan, batch, note):
-    residency = ("whole CSR + feature table resident in HBM on every GPU (replicated); roots sharded by contiguous id range"
-                 if not getattr(args, "shard_features", False) else
-                 "CSR replicated; feature table sharded by contiguous node range over the GPUs and mapped as one flat array "
-                 "(cuMemMap of peer shards, rows pitched to 128-byte multiples): " +
-                 ("the row of every unique batch node is copied over NVLink into a per-batch table once per step (halo staging), "
-                  "layer 1 gathers from the copy" if getattr(args, "halo", "staged") == "staged" else
-                  "remote neighbour rows are loaded over NVLink inside the gather kernel, one per unique edge"))
-    edges = (f"{wl['pairs']} directed edges (duplicates kept)" if wl["directed"] else
-             f"{wl['pairs']} undirected pairs de-duplicated+mirrored")
-    return {"workload": f"BASELINE.json {wl['cfg']} shape: {args.workload} synthetic RMAT(0.57,0.19,0.19,0.05) graph, "
-                        f"N={wl['nodes']}, {edges}, F={wl['F']} fp32, "
-                        f"2-hop fanout {fan}, GraphSAGE {wl['F']}->{wl['H']}->{wl['O']} inference on the coalesced batch graph",
-            "roots_per_step_per_gpu": batch, "fanout": fan, "seed": {"generator": 20260101, "sampler_base_seed": 42, "first_call_no": 1},
-            "residency": residency,
-            "l2": f"every step reads different roots from a {wl['nodes'] * wl['F'] * 4 / 1e9:.2f} GB feature table + the CSR "
-                  "(>> 126 MB L2); no flush needed",
-            "note": note}
+# ----------------------------------------------------------------------------------------------
+# the CUDA path
+# ----------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.numa_cpus = bind_to_gpu_numa_node(self.local) if self.world > 1 else None  # before CUDA / pinned allocations
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL's banner must not land on stdout beside the JSON line
+                os.environ["NCCL_DEBUG"] = "WARN"
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.dist = dist
+        self.torch = torch
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Run:
+    """One workload resident on this rank's GPU: graph, features (local / sharded / replicated), model, batch workspace."""
 
-    from gigl_b200 import Batch, Context, Graph, SageModel
+    def __init__(self, env: Env, wl_name: str, features: str, halo: str, batch: int, fan, hot_rows: float, tag: str):
+        import torch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None  # before CUDA / pinned allocations
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL's banner must not land on stdout beside the JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.workload]
-    fan = [int(v) for v in args.fanout.split(",")]
-    B = min(args.batch, wl["nodes"] // world)
-    K, W = args.steps, args.warmup
+        from gigl_b200 import Batch, Context, Graph, SageModel, synth
 
-    ctx = Context.on_torch_stream(local)
-    src, dst, x, layers = build_inputs_torch(wl, dev)
-    g = Graph.from_edges_dev(ctx, wl["nodes"], src, dst, is_graph_directed=wl["directed"])
-    del src, dst
-    table = None
-    if args.shard_features:
-        from gigl_b200.sharding import ShardedFeatureTable
+        self.env, self.wl_name, self.wl = env, wl_name, WORKLOADS[wl_name]
+        wl, dev = self.wl, env.dev
+        self.fan = fan
+        self.B = min(batch, wl["nodes"] // env.world)
+        self.sharded = features == "sharded"
+        self.halo = halo if self.sharded else None
+        self.ctx = Context.on_torch_stream(env.local)
+        big = wl["nodes"] * wl["F"] * 4 > (8 << 30)
+        src, dst, x, self.layers = build_inputs_torch(wl, dev, with_features=not (self.sharded and big))
+        self.g = Graph.from_edges_dev(self.ctx, wl["nodes"], src, dst, is_graph_directed=wl["directed"])
+        del src, dst
+        self.table = None
+        self.hot = None
+        if self.sharded:
+            from gigl_b200.sharding import ShardedFeatureTable
 
-        # rows pitched to whole 128-byte lines: remote rows cross NVLink as full lines (2x the link efficiency at F = 100)
-        pitch = -(-wl["F"] // 32) * 32
-        table = ShardedFeatureTable(ctx, wl["nodes"], pitch, rank, world, tag=os.environ.get("MASTER_PORT", "0"))
-        table.local[: table.row_hi - table.row_lo, : wl["F"]].copy_(x[table.row_lo:table.row_hi])  # this rank keeps only its rows
-        del x
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        x = table.table[: wl["nodes"], : wl["F"]]
-    if args.pitch_features and not args.shard_features:
-        xp = torch.zeros((wl["nodes"], -(-wl["F"] // 32) * 32), dtype=torch.float32, device=dev)
-        xp[:, : wl["F"]] = x
-        x = xp[:, : wl["F"]]
-    g.set_features(x)
-    model = SageModel(ctx, layers)
-    batch = Batch(ctx, wl["nodes"])
-    if args.shard_features and args.halo == "staged":
-        batch.set_halo_staging(True)
-    ctx.sync()
-    torch.cuda.empty_cache()
+            # rows pitched to whole 128-byte lines: remote rows cross NVLink as full lines (2x the link efficiency at F = 100)
+            pitch = -(-wl["F"] // 32) * 32
+            self.table = ShardedFeatureTable(self.ctx, wl["nodes"], pitch, env.rank, env.world, tag=tag)
+            t = self.table
+            if x is not None:
+                t.local[: t.row_hi - t.row_lo, : wl["F"]].copy_(x[t.row_lo:t.row_hi])  # this rank keeps only its rows
+            else:  # too large to generate whole: every rank fills its own shard
+                gen = torch.Generator(device=dev).manual_seed(synth.GEN_SEED + 1 + env.rank)
+                rows = t.row_hi - t.row_lo
+                for r0 in range(0, rows, 1 << 22):
+                    r1 = min(rows, r0 + (1 << 22))
+                    t.local[r0:r1, : wl["F"]].copy_(torch.randn(r1 - r0, wl["F"], device=dev, dtype=torch.float32, generator=gen))
+            del x
+            torch.cuda.synchronize()
+            if env.world > 1:
+                env.dist.barrier()
+            x = t.table[: wl["nodes"], : wl["F"]]
+        self.x = x
+        self.g.set_features(x)
+        self.model = SageModel(self.ctx, self.layers)
+        self.batch = Batch(self.ctx, wl["nodes"])
+        self.hot_rows = 0
+        if self.sharded and self.halo == "staged":
+            self.batch.set_halo_staging(True)
+            if hot_rows > 0 and env.world > 1 and hasattr(self.batch, "set_hot_rows"):
+                self.hot_rows = self.batch.set_hot_rows(self.g, x, hot_rows)
+        self.ctx.sync()
+        torch.cuda.empty_cache()
+        self.out = torch.empty((self.B, wl["O"]), dtype=torch.float32, device=dev)
+        self._batches = {}
+        self.nbr = self.cnt = None
 
-    batches = root_batches(wl["nodes"], rank, world, B, K + W)
-    roots_dev = [torch.from_numpy(b).to(dev) for b in batches]
-    O_dim = wl["O"]
-    out = torch.empty((B, O_dim), dtype=torch.float32, device=dev)
-    nbr, cnt = g.sample_khop(roots_dev[0], fan)
+    def roots(self, n_steps):
+        key = n_steps
+        if key not in self._batches:
+            host = root_batches(self.wl["nodes"], self.env.rank, self.env.world, self.B, n_steps)
+            self._batches[key] = (host, [self.env.torch.from_numpy(b).to(self.env.dev) for b in host])
+        return self._batches[key]
 
-    def step(i):
-        g.sample_khop(roots_dev[i], fan, out=(nbr, cnt))
-        batch.collate(roots_dev[i], fan, nbr, 2)
-        batch.sage_forward(model, x, out=out)
-        return batch.n_edges
+    def step(self, roots_dev):
+        if self.nbr is None:
+            self.nbr, self.cnt = self.g.sample_khop(roots_dev, self.fan)
+        self.g.sample_khop(roots_dev, self.fan, out=(self.nbr, self.cnt))
+        self.batch.collate(roots_dev, self.fan, self.nbr, 2)
+        self.batch.sage_forward(self.model, self.x, out=self.out)
+        return self.batch.n_edges
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- device-resident measurement (value) --------------------------------------------------
+    def measure_device(self, K, W):
+        torch, env, ctx = self.env.torch, self.env, self.ctx
+        _, roots_dev = self.roots(K + W)
+        for i in range(W):
+            self.step(roots_dev[i])
+        ctx.set_timing(True)
+        ctx.reset_timing()
+        l0 = ctx.launch_count
+        clocks = ClockSampler(env.local)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        env.barrier()
+        clocks.start()
+        evs[0].record()
+        e1_total = 0
+        for i in range(W, W + K):
+            e1_total += self.step(roots_dev[i])
+            evs[i - W + 1].record()
+        env.barrier()
+        ms = evs[0].elapsed_time(evs[K])
+        per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+        clk = clocks.stop()
+        launches = ctx.launch_count - l0
+        timings = ctx.timings()
+        ctx.set_timing(False)
+        ms = max_over_ranks(ms, env.dev)
+        return {"ms": ms, "per_step": per_step, "clocks": clk, "launches": int(launches), "timings": timings, "e1_total": e1_total}
 
-    # ---- device-resident measurement (value) ---------------------------------------------------
-    for i in range(W):
-        step(i)
-    ctx.set_timing(True)
-    ctx.reset_timing()
-    l0 = ctx.launch_count
-    clocks = ClockSampler(local)
-    barrier()
-    clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    e1_total = 0
-    for i in range(W, W + K):
-        e1_total += step(i)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop()
-    launches = ctx.launch_count - l0
-    timings = ctx.timings()
-    ctx.set_timing(False)
-    ms = max_over_ranks(ms, dev)
-    value = world * B * K / (ms * 1e-3)
+    def counts(self, K, W):
+        """what a step touches (untimed recount): unique edges, rows per layer, batch nodes, sampled edges, frontier rows"""
+        _, roots_dev = self.roots(K + W)
+        tot = dict(e1=0, e2=0, n1=0, nodes=0, sampled=0, frontier=0, slots=0)
+        for i in range(W, W + K):
+            self.g.sample_khop(roots_dev[i], self.fan, out=(self.nbr, self.cnt))
+            sizes = self.batch.collate(roots_dev[i], self.fan, self.nbr, 2)
+            tot["e1"] += self.batch.n_edges
+            tot["n1"] += sizes[1]
+            node_ids, ei = self.batch.export()
+            tot["e2"] += int((ei[1] < self.B).sum().item())
+            tot["nodes"] += int(node_ids.numel())
+            valid = [int((t >= 0).sum().item()) for t in self.nbr]
+            tot["sampled"] += sum(valid)
+            tot["frontier"] += self.B + sum(valid[:-1])  # rows the sampler resolves: the roots + every filled slot above the last hop
+            tot["slots"] += sum(int(t.numel()) for t in self.nbr)
+        return {k: v / K for k, v in tot.items()}
 
-    # edges aggregated per step: layer 1 reduces every unique batch edge, layer 2 those into roots (untimed recount)
-    e2_total = 0
-    n1_total = 0
-    nodes_total = 0
-    sampled_total = 0
-    for i in range(W, W + K):
-        g.sample_khop(roots_dev[i], fan, out=(nbr, cnt))
-        sizes = batch.collate(roots_dev[i], fan, nbr, 2)
-        n1_total += sizes[1]
-        node_ids, ei = batch.export()
-        e2_total += int((ei[1] < B).sum().item())
-        nodes_total += int(node_ids.numel())
-        sampled_total += sum(int((t >= 0).sum().item()) for t in nbr)
-    agg_edges = e1_total + e2_total
-
-    # ---- roofline of the dominant kernel: the layer-1 gather ------------------------------------
-    peak, peak_src = measured_peaks()
-    F = wl["F"]
-    g_ms, g_n = timings.get("gather_l1", (0.0, 0))
-    # algorithmic bytes per launch: per unique edge one source row + its sorted key, per output row the
-    # segment descriptor + node id + self row read + [mean | self] row written
-    alg_bytes = (e1_total * (4 * F + 8) + n1_total * (8 + 4 + 4 * F + 8 * F)) / max(K, 1)
-    achieved = alg_bytes / (g_ms / max(g_n, 1) * 1e-3) / 1e9 if g_n else None
-    phase_ms = {k: v[0] / K for k, v in timings.items()}
-    roofline = {"kernel": "batch_gather_async_kernel<1, 8> (layer-1 gather over the coalesced batch graph; + split-row parts/finish launches)",
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "ms_per_launch": g_ms / max(g_n, 1), "share_of_step": (g_ms / K) / (ms / K)}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof) and args.workload == "products-like" and B == 65536 and not args.shard_features:
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("gather_l1_dram_bytes_per_launch")
-        except Exception:
-            pass
-
-    # ---- the aggregate over the WHOLE graph (every node a row, every CSR edge reduced once): the full-graph form the
-    # Trainer's nn modules and layer-wise inference use; reported beside the batch numbers, outside the timed step
-    full = None
-    if not args.no_full_graph and not args.shard_features:
-        rowptr_t, col_t = g.csr_tensors()
-        agg = torch.empty((wl["nodes"], F), dtype=torch.float32, device=dev)
-        ctx.gather_mean(x, rowptr_t, col_t, out=agg)
-        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        fe0.record()
-        for _ in range(5):
-            ctx.gather_mean(x, rowptr_t, col_t, out=agg)
-        fe1.record()
-        barrier()
-        f_ms = max_over_ranks(fe0.elapsed_time(fe1) / 5, dev)
-        f_bytes = g.n_edges * (4 * F + 4) + (wl["nodes"] + 1) * 8 + wl["nodes"] * 4 * F  # SURVEY 8(d) bytes_A without the projection
-        full = {"op": "gigl_gather_mean_dev over the whole CSR (SAGEConv mean aggregate of every node)", "edges": int(g.n_edges),
-                "ms": f_ms, "aggregated_edges_per_sec": world * g.n_edges / (f_ms * 1e-3), "algorithmic_GBps_per_gpu": f_bytes / f_ms / 1e6,
-                "frac_of_hbm_peak": f_bytes / f_ms / 1e6 / peak}
-        del agg
-
-    # ---- end to end through the host entry point (pinned host buffers, copies inside the timed region) ----
-    # index sets come back packed (one-byte counts + the filled slots only: same edges, ~2/3 of the bytes; --e2e-padded
-    # returns the padded tree instead)
-    e2e = None
-    if not args.no_e2e:
-        roots_pin = [torch.from_numpy(b).pin_memory() for b in batches]
+    # ---- end to end through the host entry points ----------------------------------------------
+    def measure_e2e(self, K, W, padded=False, embeddings_only=False):
+        torch, env = self.env.torch, self.env
+        host, _ = self.roots(K + W)
+        B, O_dim, fan = self.B, self.wl["O"], self.fan
+        roots_pin = [torch.from_numpy(b).pin_memory() for b in host]
         out_pin = torch.empty((B, O_dim), dtype=torch.float32).pin_memory()
-        nbr_pin, cnt_pin, cnt8_pin, width = [], [], [], 1
-        for f in fan:
-            cnt_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
-            cnt8_pin.append(torch.empty(B * width, dtype=torch.uint8).pin_memory())
-            width *= f
-            nbr_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
         d2h_steps = []
-        if args.e2e_padded:
-            s_out = ([t.numpy() for t in nbr_pin], [t.numpy() for t in cnt_pin])
-
+        if embeddings_only:
             def host_step(i):
-                g.infer_khop_sage_host(batch, model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(), samples_out=s_out)
-                d2h_steps.append(B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin))
+                self.g.infer_khop_sage_host(self.batch, self.model, roots_pin[i].numpy(), fan, out=out_pin.numpy())
+                d2h_steps.append(B * O_dim * 4)
+            api = "gigl_infer_khop_sage_host(nbr_out = NULL): roots in pinned host memory -> root embeddings back in pinned host memory"
         else:
-            packed_pin = torch.empty(sum(t.numel() for t in nbr_pin), dtype=torch.int32).pin_memory()
-            p_out = (packed_pin.numpy(), [t.numpy() for t in cnt8_pin])
+            nbr_pin, cnt_pin, cnt8_pin, width = [], [], [], 1
+            for f in fan:
+                cnt_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
+                cnt8_pin.append(torch.empty(B * width, dtype=torch.uint8).pin_memory())
+                width *= f
+                nbr_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
+            if padded:
+                s_out = ([t.numpy() for t in nbr_pin], [t.numpy() for t in cnt_pin])
 
-            def host_step(i):
-                _, packed, _ = g.infer_khop_sage_packed_host(batch, model, roots_pin[i].numpy(), fan, out=out_pin.numpy(), packed_out=p_out)
-                d2h_steps.append(B * O_dim * 4 + packed.size * 4 + sum(t.numel() for t in cnt8_pin))
+                def host_step(i):
+                    self.g.infer_khop_sage_host(self.batch, self.model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(),
+                                                samples_out=s_out)
+                    d2h_steps.append(B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin))
+                api = "gigl_infer_khop_sage_host: roots in pinned host memory -> padded-tree index sets + root embeddings in pinned host memory"
+            else:
+                packed_pin = torch.empty(sum(t.numel() for t in nbr_pin), dtype=torch.int32).pin_memory()
+                p_out = (packed_pin.numpy(), [t.numpy() for t in cnt8_pin])
+
+                def host_step(i):
+                    _, packed, _ = self.g.infer_khop_sage_packed_host(self.batch, self.model, roots_pin[i].numpy(), fan, out=out_pin.numpy(),
+                                                                      packed_out=p_out)
+                    d2h_steps.append(B * O_dim * 4 + packed.size * 4 + sum(t.numel() for t in cnt8_pin))
+                api = ("gigl_infer_khop_sage_packed_host: roots in pinned host memory -> packed index sets [one-byte counts + filled "
+                       "slots] + root embeddings in pinned host memory")
         for i in range(W):
             host_step(i)
         d2h_steps.clear()
-        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.barrier()
         ev0.record()
+        t0 = time.perf_counter()
         for i in range(W, W + K):
             host_step(i)
         ev1.record()
-        barrier()
-        ms_e = ev0.elapsed_time(ev1)  # device time on the launching stream (the host call itself is synchronous)
-        ms_e = max_over_ranks(ms_e, dev)
+        env.barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_e = max_over_ranks(ev0.elapsed_time(ev1), env.dev)  # device time on the launching stream (the host call is synchronous)
         d2h = int(sum(d2h_steps) / max(len(d2h_steps), 1))
-        e2e = {"value": world * B * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e / K, "host_cpus_bound": numa_cpus,
-               "api": ("gigl_infer_khop_sage_host (roots in pinned host memory -> padded-tree index sets + root embeddings back in pinned "
-                       "host memory)" if args.e2e_padded else
-                       "gigl_infer_khop_sage_packed_host (roots in pinned host memory -> packed index sets [one-byte counts + filled "
-                       "slots] + root embeddings back in pinned host memory)")}
+        return {"value": env.world * B * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e / K, "host_wall_ms_per_step": wall_ms / K, "host_cpus_bound": env.numa_cpus, "api": api}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rowptr_t, col_t = g.csr_tensors()
-        if x.numel() * 4 > (8 << 30):
-            # a table this large is not copied to the host: the baseline's feature lookup reads the device copy
-            x_host = lambda ids: x[torch.from_numpy(ids).to(dev)].cpu().numpy()  # noqa: E731
+    def full_graph(self):
+        """the aggregate over the WHOLE graph (every node a row, every CSR edge reduced once): the form the Trainer's nn
+        modules and layer-wise inference use; reported beside the batch numbers, outside the timed step"""
+        torch, env, wl = self.env.torch, self.env, self.wl
+        F = wl["F"]
+        peak, _, _ = measured_peaks()
+        rowptr_t, col_t = self.g.csr_tensors()
+        agg = torch.empty((wl["nodes"], F), dtype=torch.float32, device=env.dev)
+        self.ctx.gather_mean(self.x, rowptr_t, col_t, out=agg)
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.barrier()
+        fe0.record()
+        for _ in range(5):
+            self.ctx.gather_mean(self.x, rowptr_t, col_t, out=agg)
+        fe1.record()
+        env.barrier()
+        f_ms = max_over_ranks(fe0.elapsed_time(fe1) / 5, env.dev)
+        f_bytes = self.g.n_edges * (4 * F + 4) + (wl["nodes"] + 1) * 8 + wl["nodes"] * 4 * F  # SURVEY 8(d) bytes_A without the projection
+        return {"op": "gigl_gather_mean_dev over the whole CSR (SAGEConv mean aggregate of every node)", "edges": int(self.g.n_edges),
+                "ms": f_ms, "aggregated_edges_per_sec": env.world * self.g.n_edges / (f_ms * 1e-3),
+                "algorithmic_GBps_per_gpu": f_bytes / f_ms / 1e6, "frac_of_hbm_peak": f_bytes / f_ms / 1e6 / peak}
+
+    def cpu_baseline(self, steps):
+        torch, wl = self.env.torch, self.wl
+        rowptr_t, col_t = self.g.csr_tensors()
+        x = self.x
+        if x.numel() * 4 > (8 << 30) or self.sharded:
+            # a table this large (or sharded) is not copied to the host: the baseline's feature lookup reads the device copy
+            x_host = lambda ids: x[torch.from_numpy(ids).to(self.env.dev)].cpu().numpy()  # noqa: E731
         else:
-            x_host = x.cpu().numpy()
-        cpu = run_cpu_baseline(rowptr_t.cpu().numpy(), col_t.cpu().numpy(), x_host, fan, layers, wl["nodes"],
-                               args.cpu_sample_roots, 3, 1)
+            x_host = x.cpu()
+        cpu = run_cpu_baseline(rowptr_t.cpu().numpy(), col_t.cpu().numpy(), x_host, self.fan, self.layers, wl["nodes"], self.B, steps, 1)
         if callable(x_host):
             cpu["sample"] += "; batch feature rows fetched from the device-resident table"
         cpu["cpu_model"] = cpu_model()
+        return cpu
 
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, wl, fan, B, "value: roots already on the device; e2e: host buffers"),
-                "aggregated_edges_per_sec": world * agg_edges / (ms * 1e-3),
-                "aggregate_only_edges_per_sec": agg_edges / K / max(1e-9, sum(phase_ms.get(k, 0.0) for k in
-                                                                              ("gather_l1", "gather_deep", "gemm_l1", "gemm_deep")) * 1e-3),
-                "sample_only_subgraphs_per_sec": B / max(1e-9, phase_ms.get("sample", 0.0) * 1e-3),
-                "phase_ms_per_step": phase_ms, "unique_edges_per_step": e1_total / K, "layer1_rows_per_step": n1_total / K,
-                "batch_nodes_per_step": nodes_total / K, "sampled_edges_per_step": sampled_total / K,
-                "roofline": roofline, "full_graph_aggregate": full, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+    def residency(self):
+        if not self.sharded:
+            return "whole CSR + feature table resident in HBM on every GPU (replicated); roots sharded by contiguous id range"
+        s = ("CSR replicated; feature table sharded by contiguous node range over the GPUs and mapped as one flat array "
+             "(cuMemMap of peer shards, rows pitched to 128-byte multiples): ")
+        if self.halo == "staged":
+            s += ("the row of every unique batch node is copied over NVLink into a per-batch table once per step (halo staging), "
+                  "layer 1 gathers from the copy")
+            if self.hot_rows:
+                s += f"; the {self.hot_rows} highest in-degree rows ({self.hot_rows / self.wl['nodes']:.3f} of the table) are replicated on every GPU"
+        else:
+            s += "remote neighbour rows are loaded over NVLink inside the gather kernel, one per unique edge"
+        return s
+
+    def close(self):
+        self.ctx.sync()
+        if self.env.world > 1:
+            self.env.dist.barrier()
+        self.batch.close()
+        self.model.close()
+        self.g.close()
+        if self.table is not None:
+            self.table.close()
+        self.nbr = self.cnt = self.out = self.x = None
+        self._batches = {}
+        self.ctx.close()
+        self.env.torch.cuda.empty_cache()
+
+
+def roofline_blocks(run: Run, dev_res, cnt, K):
+    """One block per hot kernel: SURVEY.md 8(d) algorithmic bytes (no cache credit, no private byte model) / the kernel's
+    CUDA-event time inside the timed region, against the measured peak; `traffic` = ncu DRAM bytes per launch of the same
+    kernels, taken this round on the same sources (else null)."""
+    wl = run.wl
+    F, H = wl["F"], wl["H"]
+    hbm, bf16, src = measured_peaks()
+    tr = measured_traffic() if (run.wl_name == "products-like" and run.B == 65536 and not run.sharded) else None
+    timings, step_ms = dev_res["timings"], dev_res["ms"] / K
+
+    def phase(*names):
+        ms = sum(timings.get(n, (0.0, 0))[0] for n in names) / K
+        return ms if ms > 0 else None
+
+    def hbm_block(kernel, names, bytes_, formula, key):
+        ms = phase(*names)
+        ach = bytes_ / (ms * 1e-3) / 1e9 if ms else None
+        t = tr.get(key) if tr else None
+        return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if ach else None,
+                "traffic": t.get("dram_bytes") if t else None,
+                "dram_read_frac_of_peak": (t["dram_read_bytes"] / (ms * 1e-3) / 1e9 / hbm) if (t and ms and t.get("dram_read_bytes")) else None,
+                "algorithmic_bytes_per_launch": bytes_, "formula": formula, "ms_per_launch": ms, "share_of_step": ms / step_ms if ms else None,
+                "peak_source": src}
+
+    e1, n1, nE, rows_s, nodes, slots = cnt["e1"], cnt["n1"], cnt["sampled"], cnt["frontier"], cnt["nodes"], cnt["slots"]
+    blocks = []
+    blocks.append(hbm_block("khop_tile_kernel<16> (all hops of the sampler)", ["sample"], 16 * rows_s + 12 * nE + 8 * run.B,
+                            "8(d) bytes_S = sum over frontier rows (16 + 4 min(deg, f)) + 8 nE_sampled + 8 per root = 16 rows + 12 nE + 8 B",
+                            "sample"))
+    blocks.append(hbm_block("batch_gather_async_kernel<1, 8> + split-row parts / finish (layer-1 gather over the coalesced batch graph)",
+                            ["gather_l1"], e1 * (4 * F + 4) + (n1 + 1) * 8 + n1 * 4 * F,
+                            "8(d) bytes_A gather terms: e (4 F + 4) + (n + 1) 8 + n 4 F", "gather_l1"))
+    ms_g = phase("gemm_l1")
+    if ms_g:
+        flops = 2.0 * n1 * (2 * F) * H
+        peak_tf32 = bf16 / 2.0
+        blocks.append({"kernel": "linear_tf32x3_kernel (layer-1 projection, 3 tcgen05 kind::tf32 passes per product)", "bound": "tensor",
+                       "achieved": 3 * flops / (ms_g * 1e-3) / 1e12, "peak": peak_tf32, "unit": "TFLOP/s",
+                       "frac": 3 * flops / (ms_g * 1e-3) / 1e12 / peak_tf32, "traffic": (tr or {}).get("gemm_l1", {}).get("dram_bytes"),
+                       "algorithmic_flops_per_launch": flops, "executed_flops_per_launch": 3 * flops,
+                       "formula": "8(d) flops_A = 2 n (2 F) H; executed = 3 x (hi*hi + hi*lo + lo*hi)", "ms_per_launch": ms_g,
+                       "share_of_step": ms_g / step_ms, "peak_source": src + "; tf32 dense peak taken as bf16 / 2"})
+    blocks.append(hbm_block("layer-1 gather-SpMM as a whole (gather + projection)", ["gather_l1", "gemm_l1"],
+                            e1 * (4 * F + 4) + (n1 + 1) * 8 + n1 * 4 * F + n1 * 4 * H + 4 * (2 * F * H + H),
+                            "8(d) bytes_A = e (4 F + 4) + (n + 1) 8 + n 4 F + n 4 F_out + 4 (2 F F_out + F_out)", "gather_spmm_l1"))
+    blocks.append(hbm_block("batch collation (tree_rows / rows_alloc / rows_sort_* / expand_level kernels)",
+                            ["collate_keys", "collate_sort", "collate_maps"], 4 * slots + 8 * nE + 12 * nodes,
+                            "not in 8(d); minimum traffic: 4 B per tree slot read + 8 B per sorted key written + 12 B of map per batch node",
+                            "collate"))
+    if run.sharded and phase("halo_stage"):
+        blocks.append(hbm_block("halo_stage_kernel (remote-neighbour feature halo: one row per unique batch node, NVLink for the remote ones)",
+                                ["halo_stage"], nodes * (4 * F + 4) + nodes * 4 * F,
+                                "one row read (local HBM or NVLink) + one row written per unique batch node; bound is NVLink, HBM peak shown",
+                                "halo_stage"))
+    return blocks
+
+
+def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_full, tag):
+    fan = [int(v) for v in args.fanout.split(",")]
+    hot = args.hot_rows if args.hot_rows is not None else float(os.environ.get("GIGL_HOT_ROWS", "0.125"))
+    run = Run(env, wl_name, features, args.halo, args.batch, fan, hot, tag)
+    wl, B, world = run.wl, run.B, env.world
+    dev_res = run.measure_device(K, W)
+    ms = dev_res["ms"]
+    value = world * B * K / (ms * 1e-3)
+    cnt = run.counts(min(K, 8), W)
+    agg_edges = (cnt["e1"] + cnt["e2"])
+    blocks = roofline_blocks(run, dev_res, cnt, K)
+    timed = [b for b in blocks if b.get("ms_per_launch") and not b["kernel"].startswith("layer-1 gather-SpMM as a whole")]
+    head = max(timed, key=lambda b: b["ms_per_launch"]) if timed else None
+    phase_ms = {k: v[0] / K for k, v in dev_res["timings"].items()}
+    rec = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "ms_per_step_min": float(np.min(dev_res["per_step"])), "ms_per_step_median": float(np.median(dev_res["per_step"])),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(wl_name, wl, fan, B, world), "residency": run.residency(),
+           "aggregated_edges_per_sec": world * agg_edges / (ms / K * 1e-3),
+           "aggregate_only_edges_per_sec": agg_edges / max(1e-9, sum(phase_ms.get(k, 0.0) for k in
+                                                                     ("gather_l1", "gather_deep", "gemm_l1", "gemm_deep", "halo_stage")) * 1e-3),
+           "sample_only_subgraphs_per_sec": B / max(1e-9, phase_ms.get("sample", 0.0) * 1e-3),
+           "phase_ms_per_step": phase_ms, "unique_edges_per_step": cnt["e1"], "layer1_rows_per_step": cnt["n1"],
+           "batch_nodes_per_step": cnt["nodes"], "sampled_edges_per_step": cnt["sampled"],
+           "roofline": head, "rooflines": blocks, "gpu_launches": dev_res["launches"], "clocks": dev_res["clocks"]}
+    if run.sharded and phase_ms.get("halo_stage"):
+        F = wl["F"]
+        remote = cnt["nodes"] * (1.0 - 1.0 / world)
+        if run.hot_rows:
+            remote = None  # depends on the hot set; the library's counters would be needed
+        rec["halo"] = {"ms_per_step": phase_ms["halo_stage"], "rows_per_step": cnt["nodes"], "row_bytes": 4 * (-(-F // 32) * 32),
+                       "remote_rows_per_step_if_uniform": cnt["nodes"] * (1.0 - 1.0 / world),
+                       "nvlink_GBps_if_uniform": (remote * 4 * (-(-F // 32) * 32) / (phase_ms["halo_stage"] * 1e-3) / 1e9) if remote else None,
+                       "hot_rows_replicated": run.hot_rows}
+    if want_full and not run.sharded:
+        rec["full_graph_aggregate"] = run.full_graph()
+    if want_e2e:
+        rec["e2e"] = run.measure_e2e(K, W, padded=args.e2e_padded)
+        rec["e2e_embeddings_only"] = run.measure_e2e(K, W, embeddings_only=True)
+    if want_cpu:
+        if env.rank == 0:
+            rec["cpu_baseline"] = run.cpu_baseline(args.cpu_steps)
+        env.barrier()
+    run.close()
+    return rec
+
+
+def run_ours(args):
+    env = Env()
+    K, W = args.steps, args.warmup
+    features = args.features
+    if features == "auto":
+        features = "sharded" if env.world > 1 else "replicated"
+    port = os.environ.get("MASTER_PORT", "0")
+    line = measure(env, args, args.workload, features, K, W, want_e2e=not args.no_e2e,
+                   want_cpu=(env.world == 1 and not args.no_cpu_baseline), want_full=not args.no_full_graph, tag=port + "a")
+    if env.world > 1 and not args.no_extras and features == "sharded":
+        rep = measure(env, args, args.workload, "replicated", K, W, want_e2e=False, want_cpu=False, want_full=False, tag=port + "b")
+        line["replicated"] = {k: rep[k] for k in ("value", "ms_per_step", "ms_per_step_median", "phase_ms_per_step", "residency")}
+        line["sharded_over_replicated"] = line["value"] / rep["value"]
+    if (env.world == 8 and not args.no_extras and args.workload == "products-like") or args.with_g1b:
+        wl_name = "g1b"
+        g1b = measure(env, args, wl_name, features if env.world > 1 else "replicated", max(5, K // 2), W, want_e2e=not args.no_e2e,
+                      want_cpu=False, want_full=False, tag=port + "c")
+        line["g1b"] = g1b
+    if env.rank == 0:
         print(json.dumps(line), flush=True)
-    if table is not None:
-        ctx.sync()
-        if world > 1:
-            dist.barrier()
-        g.close()
-        table.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 def main():

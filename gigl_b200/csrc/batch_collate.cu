@@ -24,6 +24,7 @@
 //      (layer 1: straight from the graph-wide feature table by global id; deeper layers: through
 //      the local-id map) and writes [mean | self] rows that the projection GEMM consumes.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
@@ -123,6 +124,300 @@ __global__ void seg_clear_kernel(int64_t n_keys, const uint64_t* __restrict__ ke
     }
 }
 
+// ---- 1' / 2'. bucketed form: edges grouped by destination row first, every row sorted on its own ------------------
+// One global radix sort of (dst, src) keys moves every key six times (0.48 ms of a 2.5 ms step).  Grouping by dst is a
+// counting sort on a dense per-vertex array (HBM is large), and what remains are 375 k INDEPENDENT sorts of 17 sources
+// on average - a warp's registers for rows of <= 512, a CTA's shared memory beyond, value-range partitions for hubs:
+//   count:    one atomicAdd(segmap[dst].x, children) per (warp, parent slot); the first toucher lists the row;
+//   alloc:    block scan of the listed rows' counts, one cursor atomic per block -> row [beg, end) in the key array;
+//   scatter:  the same walk, cursor atomic on segmap[dst].y, 4-byte sources into the row's bucket;
+//   sort:     per row, ascending by source; the 64-bit keys (dst << shift | src) are written once, in place.
+// Duplicate edges stay adjacent in the sorted row (consumers skip equal neighbours), exactly what the global sort gave.
+// Counters in d_ctr: [0] listed rows, [1] unique edges, [2] node counter, [3] valid keys, [4 + j] level ends, [16] long items.
+constexpr int kCtrRows = 0, kCtrUnique = 1, kCtrNodes = 2, kCtrValid = 3, kCtrLong = 16;
+constexpr int kWarpSortMax = 512;   // rows up to this many entries are sorted in one warp's registers
+constexpr int kLongCap = 4096;      // shared-memory sort capacity of a long-row CTA
+constexpr int kLongPart = 1024;     // expected entries per value-range partition of a row longer than kLongCap
+constexpr int kLongThreads = 512;
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) tree_rows_kernel(uint32_t n_slots, uint32_t f, const int32_t* __restrict__ parents,
+                                                        const int32_t* __restrict__ children, int64_t n_graph_nodes,
+                                                        int2* __restrict__ segmap, int32_t* __restrict__ rows,
+                                                        int32_t* __restrict__ ctr, uint32_t* __restrict__ srcs, int32_t* err) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * 256u;
+    for (uint32_t w0 = blockIdx.x * 256u + (threadIdx.x & ~31u); w0 < n_slots; w0 += stride) {  // warp-uniform
+        const uint32_t s = w0 + lane;
+        const bool in = s < n_slots;
+        const uint32_t p = (in ? s : w0) / f;
+        const int32_t c = in ? __ldg(children + s) : -1;
+        const int32_t v = __ldg(parents + p);
+        bool valid = in && c >= 0 && v >= 0;
+        if (valid && ((int64_t)c >= n_graph_nodes || (int64_t)v >= n_graph_nodes)) {
+            atomicExch(err, GIGL_E_RANGE);
+            valid = false;
+        }
+        // the lanes of my parent inside this warp: [l0, l1)
+        const int64_t seg_lo = (int64_t)p * f - (int64_t)w0;
+        const int l0 = seg_lo < 0 ? 0 : (int)seg_lo;
+        const int l1 = seg_lo + f > 32 ? 32 : (int)(seg_lo + f);
+        const uint32_t segmask = (l1 - l0 >= 32) ? 0xffffffffu : (((1u << (l1 - l0)) - 1u) << l0);
+        const uint32_t vm = __ballot_sync(0xffffffffu, valid) & segmask;
+        const int cnt = __popc(vm);
+        if (!SCATTER) {
+            bool first = false;
+            if (lane == l0 && cnt > 0) first = atomicAdd(&segmap[v].x, cnt) == 0;
+            const uint32_t fm = __ballot_sync(0xffffffffu, first);
+            if (fm) {
+                int pos = 0;
+                if (lane == __ffs(fm) - 1) pos = atomicAdd(ctr + kCtrRows, __popc(fm));
+                pos = __shfl_sync(0xffffffffu, pos, __ffs(fm) - 1);
+                if (first) rows[pos + __popc(fm & ((1u << lane) - 1u))] = v;
+            }
+        } else {
+            int base = 0;
+            if (lane == l0 && cnt > 0) base = atomicAdd(&segmap[v].y, cnt);
+            base = __shfl_sync(0xffffffffu, base, l0);
+            if (valid) srcs[base + __popc(vm & ((1u << lane) - 1u))] = (uint32_t)c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) rows_alloc_kernel(const int32_t* __restrict__ rows, int2* __restrict__ segmap,
+                                                         int32_t* __restrict__ ctr, int4* __restrict__ long_items, int long_cap) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_rows = ctr[kCtrRows];
+    for (int i0 = blockIdx.x * 256; i0 < n_rows; i0 += gridDim.x * 256) {  // block-uniform
+        const int i = i0 + threadIdx.x;
+        int v = -1, c = 0;
+        if (i < n_rows) {
+            v = rows[i];
+            c = segmap[v].x;
+        }
+        int incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int t = s_warp[w];
+                s_warp[w] = tot;
+                tot += t;
+            }
+            s_base = tot ? atomicAdd(ctr + kCtrValid, tot) : 0;
+        }
+        __syncthreads();
+        if (i < n_rows) {
+            const int beg = s_base + s_warp[warp] + incl - c;
+            segmap[v] = make_int2(beg, beg);  // .y = fill cursor of the scatter, ends as the row's end
+            if (c > kWarpSortMax) {
+                const int R = c > kLongCap ? (c + kLongPart - 1) / kLongPart : 1;
+                const int slot = atomicAdd(ctr + kCtrLong, R);
+                for (int k = 0; k < R; ++k)
+                    if (slot + k < long_cap) long_items[slot + k] = make_int4(v, k, R, c);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Bitonic sort of R * 32 values held by a warp, element r * 32 + lane in e[r] of lane `lane`, ascending.
+template <int R>
+__device__ __forceinline__ void bitonic_warp(uint32_t (&e)[R], int lane) {
+#pragma unroll
+    for (int k = 2; k <= R * 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rj) == 0) {
+                        const bool up = ((r * 32) & k) == 0;
+                        const uint32_t a = e[r], b = e[r | rj];
+                        const uint32_t lo = min(a, b), hi = max(a, b);
+                        e[r] = up ? lo : hi;
+                        e[r | rj] = up ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, e[r], j);
+                    const bool up = (((r * 32) | lane) & k) == 0;
+                    const bool take_min = up == ((lane & j) == 0);
+                    e[r] = take_min ? min(e[r], o) : max(e[r], o);
+                }
+            }
+        }
+    }
+}
+
+// Loads a row of c <= R * 32 sources, sorts it, writes its keys; returns this lane's count of first occurrences.
+template <int R>
+__device__ __forceinline__ int sort_row_warp(const uint32_t* __restrict__ src, uint64_t* __restrict__ dst, int c, uint64_t hi_bits,
+                                             int lane) {
+    uint32_t e[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) e[r] = (r * 32 + lane < c) ? src[r * 32 + lane] : 0xFFFFFFFFu;
+    bitonic_warp<R>(e, lane);
+    int uniq = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        uint32_t prev = __shfl_up_sync(0xffffffffu, e[r], 1);
+        if (r > 0) {
+            const uint32_t carry = __shfl_sync(0xffffffffu, e[r - 1], 31);
+            if (lane == 0) prev = carry;
+        }
+        const int i = r * 32 + lane;
+        if (i < c) {
+            dst[i] = hi_bits | e[r];
+            uniq += (i == 0) || (prev != e[r]);
+        }
+    }
+    return uniq;
+}
+
+__global__ void __launch_bounds__(256) rows_sort_warp_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ segmap,
+                                                             int32_t* __restrict__ ctr, const uint32_t* __restrict__ srcs,
+                                                             uint64_t* __restrict__ keys, int shift) {
+    const int lane = threadIdx.x & 31;
+    const int n_rows = ctr[kCtrRows];
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    int uniq = 0;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_rows; i += warps) {
+        const int32_t v = __ldg(rows + i);
+        const int2 seg = segmap[v];
+        const int c = seg.y - seg.x;
+        const uint64_t hi_bits = (uint64_t)(uint32_t)v << shift;
+        const uint32_t* src = srcs + seg.x;
+        uint64_t* dst = keys + seg.x;
+        if (c <= 32)
+            uniq += sort_row_warp<1>(src, dst, c, hi_bits, lane);
+        else if (c <= 64)
+            uniq += sort_row_warp<2>(src, dst, c, hi_bits, lane);
+        else if (c <= 128)
+            uniq += sort_row_warp<4>(src, dst, c, hi_bits, lane);
+        else if (c <= 256)
+            uniq += sort_row_warp<8>(src, dst, c, hi_bits, lane);
+        else if (c <= kWarpSortMax)
+            uniq += sort_row_warp<16>(src, dst, c, hi_bits, lane);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, off);
+    if (lane == 0 && uniq) atomicAdd(ctr + kCtrUnique, uniq);
+}
+
+// One CTA per long-row work item (row v, partition k of R).  The CTA reads the whole row, keeps the sources inside its
+// value range [lo, hi) in shared memory and counts those below lo: that count IS the output offset of its sorted run,
+// so the partitions of one row are independent CTAs.  A range holding more than kLongCap sources is split in four and
+// redone (a width-1 range is a run of one repeated source); R = 1 for rows that fit as a whole.
+__global__ void __launch_bounds__(kLongThreads) rows_sort_long_kernel(const int32_t* __restrict__ ctr, const int4* __restrict__ long_items,
+                                                                      int long_cap, const int2* __restrict__ segmap,
+                                                                      const uint32_t* __restrict__ srcs, uint64_t* __restrict__ keys,
+                                                                      int shift, int32_t* __restrict__ ctr_out) {
+    __shared__ uint32_t s_buf[kLongCap];
+    __shared__ uint2 s_stack[64];
+    __shared__ int s_sp, s_cnt, s_below;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int n_items = ctr[kCtrLong];
+    if (n_items > long_cap) n_items = long_cap;
+    int uniq = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int4 it = long_items[item];
+        const int2 seg = segmap[it.x];
+        const int c = seg.y - seg.x;
+        const uint32_t* src = srcs + seg.x;
+        uint64_t* dst = keys + seg.x;
+        const uint64_t hi_bits = (uint64_t)(uint32_t)it.x << shift;
+        const uint64_t space = 1ULL << shift;
+        if (tid == 0) {
+            s_stack[0] = make_uint2((uint32_t)(space * (uint64_t)it.y / (uint64_t)it.z), (uint32_t)(space * (uint64_t)(it.y + 1) / (uint64_t)it.z - 1));
+            s_sp = 1;  // ranges are [lo, hi] inclusive (hi = 2^32 - 1 must be representable)
+        }
+        __syncthreads();
+        while (s_sp > 0) {  // block-uniform: s_sp only changes between barriers
+            const uint2 rg = s_stack[s_sp - 1];
+            __syncthreads();
+            if (tid == 0) {
+                s_sp -= 1;
+                s_cnt = 0;
+                s_below = 0;
+            }
+            __syncthreads();
+            int below = 0;
+            for (int e0 = 0; e0 < c; e0 += kLongThreads) {
+                const int e = e0 + tid;
+                const uint32_t x = e < c ? src[e] : 0xFFFFFFFFu;
+                const bool inr = e < c && x >= rg.x && x <= rg.y;
+                below += e < c && x < rg.x;
+                const uint32_t m = __ballot_sync(0xffffffffu, inr);
+                if (m) {
+                    int pos = 0;
+                    if (lane == __ffs(m) - 1) pos = atomicAdd(&s_cnt, __popc(m));
+                    pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+                    if (inr && pos < kLongCap) s_buf[pos] = x;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) below += __shfl_xor_sync(0xffffffffu, below, off);
+            if (lane == 0 && below) atomicAdd(&s_below, below);
+            __syncthreads();
+            const int n = s_cnt, off0 = s_below;
+            if (n <= kLongCap) {
+                int m = 32;
+                while (m < n) m <<= 1;
+                for (int i = n + tid; i < m; i += kLongThreads) s_buf[i] = 0xFFFFFFFFu;
+                __syncthreads();
+                for (int k = 2; k <= m; k <<= 1)
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int t = tid; t < (m >> 1); t += kLongThreads) {
+                            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                            const uint32_t a = s_buf[i], b = s_buf[i | j];
+                            if ((a > b) == ((i & k) == 0)) {
+                                s_buf[i] = b;
+                                s_buf[i | j] = a;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                for (int i = tid; i < n; i += kLongThreads) {
+                    const uint32_t x = s_buf[i];
+                    dst[off0 + i] = hi_bits | x;
+                    uniq += (i == 0) || (s_buf[i - 1] != x);
+                }
+            } else if (rg.x == rg.y) {
+                for (int i = tid; i < n; i += kLongThreads) dst[off0 + i] = hi_bits | rg.x;
+                uniq += tid == 0;
+            } else if (tid == 0) {
+                const uint64_t w = (uint64_t)rg.y - rg.x + 1;
+                const int parts = w < 4 ? (int)w : 4;
+                for (int q = 0; q < parts; ++q)
+                    s_stack[s_sp++] = make_uint2(rg.x + (uint32_t)(w * q / parts), rg.x + (uint32_t)(w * (q + 1) / parts - 1));
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, off);
+    if (lane == 0 && uniq) atomicAdd(ctr_out + kCtrUnique, uniq);
+}
+
+__global__ void rows_clear_kernel(const int32_t* __restrict__ ctr, const int32_t* __restrict__ rows, int2* __restrict__ segmap) {
+    const int n = ctr[kCtrRows];
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) segmap[rows[i]] = make_int2(0, 0);
+}
+
 // ---- 3. local ids, level by level ------------------------------------------------------------
 // level_end[0] = 0, level_end[1] = n_roots, level_end[j + 1] = nodes after the j-th expansion
 __global__ void roots_assign_kernel(int64_t n_roots, const int32_t* __restrict__ roots, int64_t n_nodes,
@@ -148,12 +443,14 @@ __global__ void roots_assign_kernel(int64_t n_roots, const int32_t* __restrict__
 constexpr int kStageCap = 1024;
 constexpr int kExpandKpt = kStageCap / 256;  // keys per thread per block iteration
 __global__ void __launch_bounds__(256) expand_level_kernel(const int32_t* __restrict__ level_end, int level, int64_t n_keys,
+                                                           const int32_t* __restrict__ n_keys_dev,
                                                            const uint64_t* __restrict__ keys, int shift, uint64_t src_mask,
                                                            int32_t* __restrict__ lid, int32_t* __restrict__ list,
                                                            int32_t* __restrict__ n_nodes_ctr) {
     __shared__ int s_cnt, s_base;
     __shared__ int32_t s_stage[kStageCap];
     const int lane = threadIdx.x & 31;
+    if (n_keys_dev != nullptr && *n_keys_dev < n_keys) n_keys = *n_keys_dev;  // the host passed an upper bound
     const int32_t lo = level_end[level - 1], hi = level_end[level];
     const int64_t step = (int64_t)gridDim.x * kStageCap;
     for (int64_t base = (int64_t)blockIdx.x * kStageCap; base < n_keys; base += step) {  // block-uniform trip count
@@ -797,6 +1094,8 @@ struct gigl_batch {
     int64_t level_end_host[GIGL_MAX_HOPS + 2] = {};
     int64_t n_valid_host = 0, n_unique_host = 0;
     bool halo_staging = false;  // layer 1 reads a per-batch copy of the unique nodes' rows (batch_set_halo_staging)
+    int32_t* rows = nullptr;    // bucketed collation: the batch's distinct destination vertices (inside `buf`)
+    bool bucketed = false;      // the current batch was collated by the bucketed path
 };
 
 static constexpr int kCtrInts = 32;
@@ -843,7 +1142,10 @@ static int batch_clear(gigl_batch* b) {
     using namespace gigl;
     gigl_ctx* ctx = b->ctx;
     if (!b->dirty) return GIGL_OK;
-    if (b->n_valid_host > 0) {
+    if (b->bucketed) {
+        rows_clear_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(b->d_ctr, b->rows, b->segmap);
+        GIGL_LAUNCHED(ctx);
+    } else if (b->n_valid_host > 0) {
         seg_clear_kernel<<<grid1d(ctx, b->n_valid_host, 256), 256, 0, ctx->stream>>>(b->n_valid_host, b->keys, b->shift, b->segmap);
         GIGL_LAUNCHED(ctx);
     }
@@ -891,10 +1193,77 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     b->src_mask = (1ULL << b->shift) - 1ULL;
     const int end_bit = 2 * b->shift;
     const size_t ns = ((size_t)(n_slots > 0 ? n_slots : 1) + 31) & ~(size_t)31;
+    static const bool use_sort = [] {  // GIGL_COLLATE=sort: one global radix sort of the keys (A/B measurements)
+        const char* e = getenv("GIGL_COLLATE");
+        return e && e[0] == 's';
+    }();
+    const size_t list_bytes = (sizeof(int32_t) * (size_t)(list_cap > 0 ? list_cap : 1) + 255) & ~(size_t)255;
+    cudaStream_t st = ctx->stream;
+    int th;
+    int64_t n_valid = 0;
+    if (!use_sort) {
+        // ---- bucketed path: keys | sources | rows | list | long-row work items
+        const int64_t parents_total = n_slots > 0 ? n_slots : 1;  // >= parent slots with children
+        const int64_t rows_cap = parents_total < b->n_graph_nodes ? parents_total : b->n_graph_nodes;
+        const size_t rows_bytes = (sizeof(int32_t) * (size_t)(rows_cap > 0 ? rows_cap : 1) + 255) & ~(size_t)255;
+        const int64_t long_cap = n_slots / 64 + 64;
+        const size_t need = sizeof(uint64_t) * ns + sizeof(uint32_t) * ns + rows_bytes + list_bytes + sizeof(int4) * (size_t)long_cap + 256;
+        if (b->buf_bytes < need) {
+            if (b->buf) GIGL_CUDA(ctx, cudaFree(b->buf));
+            b->buf = nullptr;
+            b->buf_bytes = 0;
+            GIGL_CUDA(ctx, cudaMalloc(&b->buf, need + need / 8));
+            b->buf_bytes = need + need / 8;
+        }
+        uint64_t* keys = (uint64_t*)b->buf;
+        uint32_t* srcs = (uint32_t*)(keys + ns);
+        b->rows = (int32_t*)(srcs + ns);
+        b->list = (int32_t*)((char*)b->rows + rows_bytes);
+        int4* long_items = (int4*)((char*)b->list + list_bytes);
+        b->keys = keys;
+        b->n_slots = n_slots;
+        b->list_cap = list_cap;
+        b->n_roots = n_roots;
+        b->dirty = true;
+        b->bucketed = true;
+        GIGL_CUDA(ctx, cudaMemsetAsync(b->d_ctr, 0, sizeof(int32_t) * kCtrInts, st));
+        th = gigl_timer_begin(ctx, GIGL_T_COLLATE_KEYS);
+        for (int pass = 0; pass < 2; ++pass) {
+            width = n_roots;
+            for (int h = 0; h < n_hops; ++h) {
+                const int32_t* parents = (h == 0) ? roots_dev : nbr_dev[h - 1];
+                width *= fanouts[h];
+                if (width > 0) {
+                    const unsigned grid = grid1d(ctx, width, 256);
+                    if (pass == 0)
+                        tree_rows_kernel<false><<<grid, 256, 0, st>>>((uint32_t)width, (uint32_t)fanouts[h], parents, nbr_dev[h], b->n_graph_nodes,
+                                                                     b->segmap, b->rows, b->d_ctr, srcs, ctx->d_err);
+                    else
+                        tree_rows_kernel<true><<<grid, 256, 0, st>>>((uint32_t)width, (uint32_t)fanouts[h], parents, nbr_dev[h], b->n_graph_nodes,
+                                                                    b->segmap, b->rows, b->d_ctr, srcs, ctx->d_err);
+                    GIGL_LAUNCHED(ctx);
+                }
+            }
+            if (pass == 0 && n_slots > 0) {
+                rows_alloc_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(b->rows, b->segmap, b->d_ctr, long_items, (int)long_cap);
+                GIGL_LAUNCHED(ctx);
+            }
+        }
+        gigl_timer_end(ctx, th);
+        th = gigl_timer_begin(ctx, GIGL_T_COLLATE_SORT);
+        if (n_slots > 0) {
+            rows_sort_warp_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->rows, b->segmap, b->d_ctr, srcs, keys, b->shift);
+            GIGL_LAUNCHED(ctx);
+            rows_sort_long_kernel<<<ctx->sm_count * 4, kLongThreads, 0, st>>>(b->d_ctr, long_items, (int)long_cap, b->segmap, srcs, keys, b->shift, b->d_ctr);
+            GIGL_LAUNCHED(ctx);
+        }
+        gigl_timer_end(ctx, th);
+        n_valid = n_slots;  // device-side count in d_ctr[kCtrValid]; the launches below are sized by the bound
+        th = gigl_timer_begin(ctx, GIGL_T_COLLATE_MAPS);
+    } else {
     size_t temp_bytes = 0;
     GIGL_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                                   (int64_t)n_slots, 0, end_bit, ctx->stream));
-    const size_t list_bytes = (sizeof(int32_t) * (size_t)(list_cap > 0 ? list_cap : 1) + 255) & ~(size_t)255;
     const size_t need = sizeof(uint64_t) * 2 * ns + list_bytes + temp_bytes + 256;
     if (b->buf_bytes < need) {
         if (b->buf) GIGL_CUDA(ctx, cudaFree(b->buf));
@@ -912,11 +1281,11 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     b->list_cap = list_cap;
     b->n_roots = n_roots;
     b->dirty = true;
-    cudaStream_t st = ctx->stream;
+    b->bucketed = false;
 
     // 1. keys: filled slots only, densely (one host read of the count: the sort then skips the empty slots)
     width = n_roots;
-    int th = gigl_timer_begin(ctx, GIGL_T_COLLATE_KEYS);
+    th = gigl_timer_begin(ctx, GIGL_T_COLLATE_KEYS);
     GIGL_CUDA(ctx, cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), st));
     for (int h = 0; h < n_hops; ++h) {
         const int32_t* parents = (h == 0) ? roots_dev : nbr_dev[h - 1];
@@ -930,7 +1299,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_cursor, b->d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     GIGL_CUDA(ctx, cudaMemsetAsync(b->d_ctr, 0, sizeof(int32_t) * kCtrInts, st));
     GIGL_CUDA(ctx, cudaStreamSynchronize(st));
-    const int64_t n_valid = (int64_t)*b->h_cursor;
+    n_valid = (int64_t)*b->h_cursor;
     b->n_valid_host = n_valid;
     // 2. sort + row bounds
     if (n_valid > 0) {
@@ -944,6 +1313,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
         seg_bounds_kernel<<<grid1d(ctx, n_valid, 256), 256, 0, st>>>(n_valid, keys_b, b->shift, b->segmap, b->d_ctr);
         GIGL_LAUNCHED(ctx);
     }
+    }
     // 3. levels: level_end[1] = n_roots, then n_layers - 1 expansions
     if (n_roots > 0) {
         roots_assign_kernel<<<(unsigned)ceil_div64(n_roots, 256), 256, 0, st>>>(n_roots, roots_dev, b->n_graph_nodes, b->lid, b->list, ctx->d_err);
@@ -954,8 +1324,9 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + kLevelBase, &init[1], sizeof(int32_t) * 2, cudaMemcpyHostToDevice, st));
     for (int j = 1; j < n_layers; ++j) {
         if (n_valid > 0) {
-            expand_level_kernel<<<grid1d(ctx, ceil_div64(n_valid, kExpandKpt), 256), 256, 0, st>>>(b->d_ctr + kLevelBase, j, n_valid, b->keys, b->shift,
-                                                                                                      b->src_mask, b->lid, b->list, b->d_ctr + 2);
+            expand_level_kernel<<<grid1d(ctx, ceil_div64(n_valid, kExpandKpt), 256), 256, 0, st>>>(
+                b->d_ctr + kLevelBase, j, n_valid, b->bucketed ? b->d_ctr + kCtrValid : nullptr, b->keys, b->shift, b->src_mask, b->lid, b->list,
+                b->d_ctr + 2);
             GIGL_LAUNCHED(ctx);
         }
         level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);
@@ -968,6 +1339,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(int32_t) * kCtrInts, cudaMemcpyDeviceToHost, st));
     GIGL_CUDA(ctx, cudaStreamSynchronize(st));
     b->n_unique_host = b->h_ctr[1];
+    if (b->bucketed) b->n_valid_host = b->h_ctr[kCtrValid];
     for (int j = 0; j <= n_layers; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
     if (level_sizes_host)
         for (int j = 0; j < n_layers; ++j) level_sizes_host[j] = b->level_end_host[j + 1];
@@ -1218,7 +1590,7 @@ int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges) {
         for (int j = b->n_levels_done; j < want; ++j) {
             if (b->n_valid_host > 0) {
                 expand_level_kernel<<<grid1d(ctx, ceil_div64(b->n_valid_host, kExpandKpt), 256), 256, 0, st>>>(
-                    b->d_ctr + kLevelBase, j, b->n_valid_host, b->keys, b->shift, b->src_mask, b->lid, b->list, b->d_ctr + 2);
+                    b->d_ctr + kLevelBase, j, b->n_valid_host, nullptr, b->keys, b->shift, b->src_mask, b->lid, b->list, b->d_ctr + 2);
                 GIGL_LAUNCHED(ctx);
             }
             level_snapshot_kernel<<<1, 1, 0, st>>>(b->d_ctr + kLevelBase, j + 1, b->d_ctr + 2);

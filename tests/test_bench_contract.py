@@ -15,7 +15,7 @@ def _run(args, env=None):
 
 
 def test_reference_arm_prints_the_contract_line():
-    p = _run(["--impl", "reference", "--workload", "toy-1k", "--steps", "2", "--warmup", "1", "--cpu-sample-roots", "128"])
+    p = _run(["--impl", "reference", "--workload", "toy-1k", "--steps", "2", "--warmup", "1", "--batch", "128"])
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -25,6 +25,22 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "configs[0]" in d["config"]["workload"]
+    assert d["config"]["roots_per_step_per_gpu"] == 128  # the reference arm runs the product arm's roots per step
+
+
+def test_both_arms_describe_the_same_config():
+    """`config` is built by one function from (workload, fanout, roots per step, N): the two arms of one driver run print
+    the same dict."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    a = bench.parse_args(["--gpus", "2", "--impl", "reference"])
+    b = bench.parse_args(["--gpus", "2"])
+    assert a.batch == b.batch and a.fanout == b.fanout and a.workload == b.workload
+    wl = bench.WORKLOADS[a.workload]
+    fan = [int(v) for v in a.fanout.split(",")]
+    assert bench.workload_config(a.workload, wl, fan, min(a.batch, wl["nodes"] // 2), 2) == \
+        bench.workload_config(b.workload, wl, fan, min(b.batch, wl["nodes"] // 2), 2)
 
 
 def test_reference_arm_runs_on_rank_zero_only():
