@@ -133,53 +133,100 @@ __global__ void seg_clear_kernel(int64_t n_keys, const uint64_t* __restrict__ ke
 //   scatter:  the same walk, cursor atomic on segmap[dst].y, 4-byte sources into the row's bucket;
 //   sort:     per row, ascending by source; the 64-bit keys (dst << shift | src) are written once, in place.
 // Duplicate edges stay adjacent in the sorted row (consumers skip equal neighbours), exactly what the global sort gave.
-// Counters in d_ctr: [0] listed rows, [1] unique edges, [2] node counter, [3] valid keys, [4 + j] level ends, [16] long items.
+// Counters in d_ctr: [0] listed rows, [1] unique edges, [2] node counter, [3] valid keys, [4 + j] level ends, [16] long
+// items, [17] / [18] work-queue cursors of the sort launch.
 constexpr int kCtrRows = 0, kCtrUnique = 1, kCtrNodes = 2, kCtrValid = 3, kCtrLong = 16;
-constexpr int kWarpSortMax = 512;   // rows up to this many entries are sorted in one warp's registers
+constexpr int kWarpSortMax = 1024;  // rows up to this many entries are sorted in one warp's registers
 constexpr int kLongCap = 4096;      // shared-memory sort capacity of a long-row CTA
 constexpr int kLongPart = 1024;     // expected entries per value-range partition of a row longer than kLongCap
 constexpr int kLongThreads = 512;
 
+// Slot-parallel walk of one tree level, kRowsUnroll x 32 consecutive slots per warp and iteration (the loads of all
+// of them are issued before the first atomic: the walk is bound by round trips, not by bytes).  The lanes of one parent
+// slot inside a warp form a segment; its lowest lane speaks for it.
+constexpr int kRowsUnroll = 4;
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) tree_rows_kernel(uint32_t n_slots, uint32_t f, const int32_t* __restrict__ parents,
                                                         const int32_t* __restrict__ children, int64_t n_graph_nodes,
                                                         int2* __restrict__ segmap, int32_t* __restrict__ rows,
                                                         int32_t* __restrict__ ctr, uint32_t* __restrict__ srcs, int32_t* err) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * 256u;
-    for (uint32_t w0 = blockIdx.x * 256u + (threadIdx.x & ~31u); w0 < n_slots; w0 += stride) {  // warp-uniform
-        const uint32_t s = w0 + lane;
-        const bool in = s < n_slots;
-        const uint32_t p = (in ? s : w0) / f;
-        const int32_t c = in ? __ldg(children + s) : -1;
-        const int32_t v = __ldg(parents + p);
-        bool valid = in && c >= 0 && v >= 0;
-        if (valid && ((int64_t)c >= n_graph_nodes || (int64_t)v >= n_graph_nodes)) {
-            atomicExch(err, GIGL_E_RANGE);
-            valid = false;
-        }
-        // the lanes of my parent inside this warp: [l0, l1)
-        const int64_t seg_lo = (int64_t)p * f - (int64_t)w0;
-        const int l0 = seg_lo < 0 ? 0 : (int)seg_lo;
-        const int l1 = seg_lo + f > 32 ? 32 : (int)(seg_lo + f);
-        const uint32_t segmask = (l1 - l0 >= 32) ? 0xffffffffu : (((1u << (l1 - l0)) - 1u) << l0);
-        const uint32_t vm = __ballot_sync(0xffffffffu, valid) & segmask;
-        const int cnt = __popc(vm);
+    __shared__ int s_cnt, s_base;
+    __shared__ int32_t s_stage[256 * kRowsUnroll];  // first-touched rows of one block iteration (<= one per lane and unroll step)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t kPerBlock = 256u * kRowsUnroll;
+    const uint32_t n_iter = (n_slots + kPerBlock - 1) / kPerBlock;
+    for (uint32_t it = blockIdx.x; it < n_iter; it += gridDim.x) {  // block-uniform
         if (!SCATTER) {
-            bool first = false;
-            if (lane == l0 && cnt > 0) first = atomicAdd(&segmap[v].x, cnt) == 0;
-            const uint32_t fm = __ballot_sync(0xffffffffu, first);
-            if (fm) {
-                int pos = 0;
-                if (lane == __ffs(fm) - 1) pos = atomicAdd(ctr + kCtrRows, __popc(fm));
-                pos = __shfl_sync(0xffffffffu, pos, __ffs(fm) - 1);
-                if (first) rows[pos + __popc(fm & ((1u << lane) - 1u))] = v;
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+        }
+        const uint32_t wbase = it * kPerBlock + (uint32_t)warp * (32u * kRowsUnroll);
+        int32_t c[kRowsUnroll], v[kRowsUnroll];
+        uint32_t p[kRowsUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowsUnroll; ++u) {
+            const uint32_t s = wbase + u * 32u + lane;
+            const bool in = s < n_slots;
+            p[u] = (in ? s : 0u) / f;
+            c[u] = in ? __ldg(children + s) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kRowsUnroll; ++u) v[u] = __ldg(parents + p[u]);
+        int base[kRowsUnroll];
+        uint32_t vm[kRowsUnroll];
+        int l0[kRowsUnroll];
+        bool first[kRowsUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowsUnroll; ++u) {
+            const uint32_t w0 = wbase + u * 32u;
+            const bool in = w0 + lane < n_slots;
+            bool valid = in && c[u] >= 0 && v[u] >= 0;
+            if (valid && ((int64_t)c[u] >= n_graph_nodes || (int64_t)v[u] >= n_graph_nodes)) {
+                atomicExch(err, GIGL_E_RANGE);
+                valid = false;
             }
+            // the lanes of my parent inside this group of 32 slots: [l0, l1)
+            const int64_t seg_lo = (int64_t)p[u] * f - (int64_t)w0;
+            l0[u] = seg_lo < 0 ? 0 : (int)seg_lo;
+            const int l1 = seg_lo + f > 32 ? 32 : (int)(seg_lo + f);
+            uint32_t segmask = (l1 - l0[u] >= 32) ? 0xffffffffu : (((1u << (l1 > l0[u] ? l1 - l0[u] : 0)) - 1u) << l0[u]);
+            if (!in) segmask = 0;
+            vm[u] = __ballot_sync(0xffffffffu, valid) & segmask;  // the filled slots of my parent inside this group
+            const int cnt = __popc(vm[u]);
+            base[u] = 0;
+            first[u] = false;
+            if (in && lane == l0[u] && cnt > 0) {
+                if (!SCATTER)
+                    first[u] = atomicAdd(&segmap[v[u]].x, cnt) == 0;
+                else
+                    base[u] = atomicAdd(&segmap[v[u]].y, cnt);
+            }
+        }
+        if (!SCATTER) {
+            // rows touched for the first time: staged per block, ONE global cursor atomic per block iteration (a cursor
+            // atomic per warp made 3e5 same-address atomics the critical path of the launch)
+#pragma unroll
+            for (int u = 0; u < kRowsUnroll; ++u) {
+                const uint32_t fm = __ballot_sync(0xffffffffu, first[u]);
+                if (fm) {
+                    int pos = 0;
+                    if (lane == __ffs(fm) - 1) pos = atomicAdd(&s_cnt, __popc(fm));
+                    pos = __shfl_sync(0xffffffffu, pos, __ffs(fm) - 1);
+                    if (first[u]) s_stage[pos + __popc(fm & ((1u << lane) - 1u))] = v[u];
+                }
+            }
+            __syncthreads();
+            const int n_staged = s_cnt;
+            if (threadIdx.x == 0 && n_staged > 0) s_base = atomicAdd(ctr + kCtrRows, n_staged);
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_staged; i += 256) rows[s_base + i] = s_stage[i];
+            __syncthreads();
         } else {
-            int base = 0;
-            if (lane == l0 && cnt > 0) base = atomicAdd(&segmap[v].y, cnt);
-            base = __shfl_sync(0xffffffffu, base, l0);
-            if (valid) srcs[base + __popc(vm & ((1u << lane) - 1u))] = (uint32_t)c;
+#pragma unroll
+            for (int u = 0; u < kRowsUnroll; ++u) {
+                const int b = __shfl_sync(0xffffffffu, base[u], l0[u]);
+                if (vm[u] >> lane & 1u) srcs[b + __popc(vm[u] & ((1u << lane) - 1u))] = (uint32_t)c[u];
+            }
         }
     }
 }
@@ -287,129 +334,182 @@ __device__ __forceinline__ int sort_row_warp(const uint32_t* __restrict__ src, u
     return uniq;
 }
 
-__global__ void __launch_bounds__(256) rows_sort_warp_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ segmap,
-                                                             int32_t* __restrict__ ctr, const uint32_t* __restrict__ srcs,
-                                                             uint64_t* __restrict__ keys, int shift) {
-    const int lane = threadIdx.x & 31;
-    const int n_rows = ctr[kCtrRows];
-    const int warps = gridDim.x * (blockDim.x >> 5);
+// The per-row sorts of a batch, one launch.  Every CTA first takes LONG-row work items (row v, partition k of R) from a
+// queue: it reads the whole row, keeps the sources inside its value range [lo, hi] in shared memory and counts those
+// below lo - that count IS the output offset of its sorted run, so the partitions of one row are independent work items.
+// A range holding more than kLongCap sources is split in four and redone (a width-1 range is a run of one repeated
+// source); R = 1 for rows that fit as a whole.  Then its warps take TILES of 32 listed rows: lane l resolves row l's
+// vertex and bounds (one round trip for 32 rows), the first 32 sources of every row are loaded into 32 registers per
+// lane (32 independent loads in flight), and ONE bitonic network - 15 stages, each a shuffle and a min/max per register -
+// sorts the 32 rows side by side: 15 compare-exchanges per row of <= 32 entries, with no dependent stall between
+// them.  Rows of 33 .. kWarpSortMax entries of the tile are then sorted one at a time in 2 .. 16 registers per lane.
+__device__ __forceinline__ void sort_long_item(const int4 it, const int2* __restrict__ segmap, const uint32_t* __restrict__ srcs,
+                                               uint64_t* __restrict__ keys, int shift, uint32_t* s_buf, uint2* s_stack, int* s_sp,
+                                               int* s_cnt, int* s_below, int& uniq) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int2 seg = segmap[it.x];
+    const int c = seg.y - seg.x;
+    const uint32_t* src = srcs + seg.x;
+    uint64_t* dst = keys + seg.x;
+    const uint64_t hi_bits = (uint64_t)(uint32_t)it.x << shift;
+    const uint64_t space = 1ULL << shift;
+    if (tid == 0) {
+        // ranges are [lo, hi] inclusive (hi = 2^32 - 1 must be representable)
+        s_stack[0] = make_uint2((uint32_t)(space * (uint64_t)it.y / (uint64_t)it.z), (uint32_t)(space * (uint64_t)(it.y + 1) / (uint64_t)it.z - 1));
+        *s_sp = 1;
+    }
+    __syncthreads();
+    while (*s_sp > 0) {  // block-uniform: s_sp only changes between barriers
+        const uint2 rg = s_stack[*s_sp - 1];
+        __syncthreads();
+        if (tid == 0) {
+            *s_sp -= 1;
+            *s_cnt = 0;
+            *s_below = 0;
+        }
+        __syncthreads();
+        int below = 0;
+        for (int e0 = 0; e0 < c; e0 += kLongThreads) {
+            const int e = e0 + tid;
+            const uint32_t x = e < c ? src[e] : 0xFFFFFFFFu;
+            const bool inr = e < c && x >= rg.x && x <= rg.y;
+            below += e < c && x < rg.x;
+            const uint32_t m = __ballot_sync(0xffffffffu, inr);
+            if (m) {
+                int pos = 0;
+                if (lane == __ffs(m) - 1) pos = atomicAdd(s_cnt, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+                if (inr && pos < kLongCap) s_buf[pos] = x;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) below += __shfl_xor_sync(0xffffffffu, below, off);
+        if (lane == 0 && below) atomicAdd(s_below, below);
+        __syncthreads();
+        const int n = *s_cnt, off0 = *s_below;
+        if (n <= kLongCap) {
+            int m = 32;
+            while (m < n) m <<= 1;
+            for (int i = n + tid; i < m; i += kLongThreads) s_buf[i] = 0xFFFFFFFFu;
+            __syncthreads();
+            for (int k = 2; k <= m; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (m >> 1); t += kLongThreads) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const uint32_t a = s_buf[i], b = s_buf[i | j];
+                        if ((a > b) == ((i & k) == 0)) {
+                            s_buf[i] = b;
+                            s_buf[i | j] = a;
+                        }
+                    }
+                    __syncthreads();
+                }
+            for (int i = tid; i < n; i += kLongThreads) {
+                const uint32_t x = s_buf[i];
+                dst[off0 + i] = hi_bits | x;
+                uniq += (i == 0) || (s_buf[i - 1] != x);
+            }
+        } else if (rg.x == rg.y) {
+            for (int i = tid; i < n; i += kLongThreads) dst[off0 + i] = hi_bits | rg.x;
+            uniq += tid == 0;
+        } else if (tid == 0) {
+            const uint64_t w = (uint64_t)rg.y - rg.x + 1;
+            const int parts = w < 4 ? (int)w : 4;
+            for (int q = 0; q < parts; ++q)
+                s_stack[(*s_sp)++] = make_uint2(rg.x + (uint32_t)(w * q / parts), rg.x + (uint32_t)(w * (q + 1) / parts - 1));
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int kCtrLongNext = 17, kCtrTileNext = 18;
+
+__global__ void __launch_bounds__(kLongThreads, 2) rows_sort_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ segmap,
+                                                                    int32_t* __restrict__ ctr, const int4* __restrict__ long_items,
+                                                                    int long_cap, const uint32_t* __restrict__ srcs,
+                                                                    uint64_t* __restrict__ keys, int shift) {
+    __shared__ uint32_t s_buf[kLongCap];
+    __shared__ uint2 s_stack[64];
+    __shared__ int s_sp, s_cnt, s_below, s_item;
+    const int tid = threadIdx.x, lane = tid & 31;
     int uniq = 0;
-    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_rows; i += warps) {
-        const int32_t v = __ldg(rows + i);
-        const int2 seg = segmap[v];
+    // ---- long rows first (the longest single work items of the launch)
+    int n_items = ctr[kCtrLong];
+    if (n_items > long_cap) n_items = long_cap;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(ctr + kCtrLongNext, 1);
+        __syncthreads();
+        const int item = s_item;
+        __syncthreads();
+        if (item >= n_items) break;
+        sort_long_item(long_items[item], segmap, srcs, keys, shift, s_buf, s_stack, &s_sp, &s_cnt, &s_below, uniq);
+    }
+    // ---- tiles of 32 listed rows per warp
+    const int n_rows = ctr[kCtrRows];
+    const int n_tiles = (n_rows + 31) >> 5;
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(ctr + kCtrTileNext, 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int i = tile * 32 + lane;
+        int32_t v = 0;
+        int2 seg = make_int2(0, 0);
+        if (i < n_rows) {
+            v = __ldg(rows + i);
+            seg = segmap[v];
+        }
         const int c = seg.y - seg.x;
-        const uint64_t hi_bits = (uint64_t)(uint32_t)v << shift;
-        const uint32_t* src = srcs + seg.x;
-        uint64_t* dst = keys + seg.x;
-        if (c <= 32)
-            uniq += sort_row_warp<1>(src, dst, c, hi_bits, lane);
-        else if (c <= 64)
-            uniq += sort_row_warp<2>(src, dst, c, hi_bits, lane);
-        else if (c <= 128)
-            uniq += sort_row_warp<4>(src, dst, c, hi_bits, lane);
-        else if (c <= 256)
-            uniq += sort_row_warp<8>(src, dst, c, hi_bits, lane);
-        else if (c <= kWarpSortMax)
-            uniq += sort_row_warp<16>(src, dst, c, hi_bits, lane);
+        uint32_t e[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int cr = __shfl_sync(0xffffffffu, c, r), br = __shfl_sync(0xffffffffu, seg.x, r);
+            e[r] = (cr <= 32 && lane < cr) ? srcs[br + lane] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, e[r], j);
+                    e[r] = take_min ? min(e[r], o) : max(e[r], o);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int cr = __shfl_sync(0xffffffffu, c, r), br = __shfl_sync(0xffffffffu, seg.x, r);
+            const int32_t vr = __shfl_sync(0xffffffffu, v, r);
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, e[r], 1);
+            if (cr <= 32 && lane < cr) {
+                keys[br + lane] = ((uint64_t)(uint32_t)vr << shift) | e[r];
+                uniq += (lane == 0) || (prev != e[r]);
+            }
+        }
+        // the tile's rows of 33 .. kWarpSortMax entries, one at a time
+        uint32_t mid = __ballot_sync(0xffffffffu, c > 32 && c <= kWarpSortMax);
+        while (mid) {
+            const int r = __ffs(mid) - 1;
+            mid &= mid - 1;
+            const int cr = __shfl_sync(0xffffffffu, c, r), br = __shfl_sync(0xffffffffu, seg.x, r);
+            const uint64_t hi_bits = (uint64_t)(uint32_t)__shfl_sync(0xffffffffu, v, r) << shift;
+            if (cr <= 64)
+                uniq += sort_row_warp<2>(srcs + br, keys + br, cr, hi_bits, lane);
+            else if (cr <= 128)
+                uniq += sort_row_warp<4>(srcs + br, keys + br, cr, hi_bits, lane);
+            else if (cr <= 256)
+                uniq += sort_row_warp<8>(srcs + br, keys + br, cr, hi_bits, lane);
+            else if (cr <= 512)
+                uniq += sort_row_warp<16>(srcs + br, keys + br, cr, hi_bits, lane);
+            else
+                uniq += sort_row_warp<32>(srcs + br, keys + br, cr, hi_bits, lane);
+        }
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, off);
     if (lane == 0 && uniq) atomicAdd(ctr + kCtrUnique, uniq);
-}
-
-// One CTA per long-row work item (row v, partition k of R).  The CTA reads the whole row, keeps the sources inside its
-// value range [lo, hi) in shared memory and counts those below lo: that count IS the output offset of its sorted run,
-// so the partitions of one row are independent CTAs.  A range holding more than kLongCap sources is split in four and
-// redone (a width-1 range is a run of one repeated source); R = 1 for rows that fit as a whole.
-__global__ void __launch_bounds__(kLongThreads) rows_sort_long_kernel(const int32_t* __restrict__ ctr, const int4* __restrict__ long_items,
-                                                                      int long_cap, const int2* __restrict__ segmap,
-                                                                      const uint32_t* __restrict__ srcs, uint64_t* __restrict__ keys,
-                                                                      int shift, int32_t* __restrict__ ctr_out) {
-    __shared__ uint32_t s_buf[kLongCap];
-    __shared__ uint2 s_stack[64];
-    __shared__ int s_sp, s_cnt, s_below;
-    const int tid = threadIdx.x, lane = tid & 31;
-    int n_items = ctr[kCtrLong];
-    if (n_items > long_cap) n_items = long_cap;
-    int uniq = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int4 it = long_items[item];
-        const int2 seg = segmap[it.x];
-        const int c = seg.y - seg.x;
-        const uint32_t* src = srcs + seg.x;
-        uint64_t* dst = keys + seg.x;
-        const uint64_t hi_bits = (uint64_t)(uint32_t)it.x << shift;
-        const uint64_t space = 1ULL << shift;
-        if (tid == 0) {
-            s_stack[0] = make_uint2((uint32_t)(space * (uint64_t)it.y / (uint64_t)it.z), (uint32_t)(space * (uint64_t)(it.y + 1) / (uint64_t)it.z - 1));
-            s_sp = 1;  // ranges are [lo, hi] inclusive (hi = 2^32 - 1 must be representable)
-        }
-        __syncthreads();
-        while (s_sp > 0) {  // block-uniform: s_sp only changes between barriers
-            const uint2 rg = s_stack[s_sp - 1];
-            __syncthreads();
-            if (tid == 0) {
-                s_sp -= 1;
-                s_cnt = 0;
-                s_below = 0;
-            }
-            __syncthreads();
-            int below = 0;
-            for (int e0 = 0; e0 < c; e0 += kLongThreads) {
-                const int e = e0 + tid;
-                const uint32_t x = e < c ? src[e] : 0xFFFFFFFFu;
-                const bool inr = e < c && x >= rg.x && x <= rg.y;
-                below += e < c && x < rg.x;
-                const uint32_t m = __ballot_sync(0xffffffffu, inr);
-                if (m) {
-                    int pos = 0;
-                    if (lane == __ffs(m) - 1) pos = atomicAdd(&s_cnt, __popc(m));
-                    pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
-                    if (inr && pos < kLongCap) s_buf[pos] = x;
-                }
-            }
-#pragma unroll
-            for (int off = 16; off; off >>= 1) below += __shfl_xor_sync(0xffffffffu, below, off);
-            if (lane == 0 && below) atomicAdd(&s_below, below);
-            __syncthreads();
-            const int n = s_cnt, off0 = s_below;
-            if (n <= kLongCap) {
-                int m = 32;
-                while (m < n) m <<= 1;
-                for (int i = n + tid; i < m; i += kLongThreads) s_buf[i] = 0xFFFFFFFFu;
-                __syncthreads();
-                for (int k = 2; k <= m; k <<= 1)
-                    for (int j = k >> 1; j > 0; j >>= 1) {
-                        for (int t = tid; t < (m >> 1); t += kLongThreads) {
-                            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                            const uint32_t a = s_buf[i], b = s_buf[i | j];
-                            if ((a > b) == ((i & k) == 0)) {
-                                s_buf[i] = b;
-                                s_buf[i | j] = a;
-                            }
-                        }
-                        __syncthreads();
-                    }
-                for (int i = tid; i < n; i += kLongThreads) {
-                    const uint32_t x = s_buf[i];
-                    dst[off0 + i] = hi_bits | x;
-                    uniq += (i == 0) || (s_buf[i - 1] != x);
-                }
-            } else if (rg.x == rg.y) {
-                for (int i = tid; i < n; i += kLongThreads) dst[off0 + i] = hi_bits | rg.x;
-                uniq += tid == 0;
-            } else if (tid == 0) {
-                const uint64_t w = (uint64_t)rg.y - rg.x + 1;
-                const int parts = w < 4 ? (int)w : 4;
-                for (int q = 0; q < parts; ++q)
-                    s_stack[s_sp++] = make_uint2(rg.x + (uint32_t)(w * q / parts), rg.x + (uint32_t)(w * (q + 1) / parts - 1));
-            }
-            __syncthreads();
-        }
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) uniq += __shfl_xor_sync(0xffffffffu, uniq, off);
-    if (lane == 0 && uniq) atomicAdd(ctr_out + kCtrUnique, uniq);
 }
 
 __global__ void rows_clear_kernel(const int32_t* __restrict__ ctr, const int32_t* __restrict__ rows, int2* __restrict__ segmap) {
@@ -558,6 +658,10 @@ __device__ __forceinline__ void gather_range(int row_beg, int e_beg, int e_end, 
 // The projection runs as 3xTF32 on the tensor cores (gemm_tcgen05.cu): its A operand is stored
 // already split, hi = the value rounded to TF32, lo = (v - hi) rounded to TF32 (gigl_split_tf32).
 __device__ __forceinline__ void store_split4(float* __restrict__ hi, float* __restrict__ lo, int64_t off, float4 v) {
+    if (lo == nullptr) {  // raw operand: the projection splits it in shared memory (gemm_tcgen05.cu, split_a)
+        *reinterpret_cast<float4*>(hi + off) = v;
+        return;
+    }
     float4 h, l;
     gigl_split_tf32(v.x, h.x, l.x);
     gigl_split_tf32(v.y, h.y, l.y);
@@ -1007,8 +1111,13 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
             }
             const float m = acc * (1.0f / (float)(n_uniq > 1 ? n_uniq : 1));
             const float sv = __ldg(xsrc + self * ldx + c);
-            gigl_split_tf32(m, A_hi[row * ldA + c], A_lo[row * ldA + c]);
-            gigl_split_tf32(sv, A_hi[row * ldA + F + c], A_lo[row * ldA + F + c]);
+            if (A_lo == nullptr) {
+                A_hi[row * ldA + c] = m;
+                A_hi[row * ldA + F + c] = sv;
+            } else {
+                gigl_split_tf32(m, A_hi[row * ldA + c], A_lo[row * ldA + c]);
+                gigl_split_tf32(sv, A_hi[row * ldA + F + c], A_lo[row * ldA + F + c]);
+            }
         }
     }
 }
@@ -1234,7 +1343,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
                 const int32_t* parents = (h == 0) ? roots_dev : nbr_dev[h - 1];
                 width *= fanouts[h];
                 if (width > 0) {
-                    const unsigned grid = grid1d(ctx, width, 256);
+                    const unsigned grid = grid1d(ctx, ceil_div64(width, kRowsUnroll), 256);
                     if (pass == 0)
                         tree_rows_kernel<false><<<grid, 256, 0, st>>>((uint32_t)width, (uint32_t)fanouts[h], parents, nbr_dev[h], b->n_graph_nodes,
                                                                      b->segmap, b->rows, b->d_ctr, srcs, ctx->d_err);
@@ -1252,9 +1361,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
         gigl_timer_end(ctx, th);
         th = gigl_timer_begin(ctx, GIGL_T_COLLATE_SORT);
         if (n_slots > 0) {
-            rows_sort_warp_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->rows, b->segmap, b->d_ctr, srcs, keys, b->shift);
-            GIGL_LAUNCHED(ctx);
-            rows_sort_long_kernel<<<ctx->sm_count * 4, kLongThreads, 0, st>>>(b->d_ctr, long_items, (int)long_cap, b->segmap, srcs, keys, b->shift, b->d_ctr);
+            rows_sort_kernel<<<ctx->sm_count * 2, kLongThreads, 0, st>>>(b->rows, b->segmap, b->d_ctr, long_items, (int)long_cap, srcs, keys, b->shift);
             GIGL_LAUNCHED(ctx);
         }
         gigl_timer_end(ctx, th);
@@ -1444,10 +1551,10 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
     void *pA = nullptr, *pH = nullptr;
     int rc;
     a_elems = (a_elems + 63) & ~(size_t)63;
-    if ((rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * 2 * a_elems, &pA)) != GIGL_OK) return rc;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_AGG, sizeof(float) * a_elems, &pA)) != GIGL_OK) return rc;
     if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO3, sizeof(float) * (2 * h_elems + 8), &pH)) != GIGL_OK) return rc;
-    float* A_hi = (float*)pA;
-    float* A_lo = A_hi + a_elems;
+    float* A_hi = (float*)pA;  // [mean | self] rows, fp32: the projection splits them into TF32 halves in shared memory
+    float* A_lo = nullptr;
     float* hbuf[2] = {(float*)pH, (float*)pH + h_elems};
     const float* xin = x_dev;
     int64_t ldx = ldx0;
@@ -1554,8 +1661,8 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         gigl_timer_end(ctx, tg);
         float* C = (l == n_layers) ? out_dev : hbuf[l & 1];
         gigl_timed tgemm(ctx, l == 1 ? GIGL_T_GEMM_L1 : GIGL_T_GEMM_DEEP);
-        rc = linear_tc_launch(ctx, rows, Fo, 2 * Fi, A_hi, A_lo, lda, m->w_hi[l - 1], m->w_lo[l - 1], lda, m->bias[l - 1], C, Fo,
-                              l < n_layers ? 1 : 0);
+        rc = linear_tc_launch_ex(ctx, rows, nullptr, Fo, 2 * Fi, A_hi, A_lo, lda, m->w_hi[l - 1], m->w_lo[l - 1], lda, m->bias[l - 1], C, Fo,
+                                 l < n_layers ? 1 : 0);
         if (rc != GIGL_OK) return rc;
         xin = C;
         ldx = Fo;

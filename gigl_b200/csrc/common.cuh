@@ -195,6 +195,8 @@ int sage_model_dims(const gigl_sage_model* m, int32_t* n_layers, int32_t* dims);
 // gemm_tcgen05.cu: C[M, N] = (A_hi + A_lo)[M, K] @ (W_hi + W_lo)[N, K]^T + bias as 3xTF32 on tcgen05 (TMA-fed, TMEM accumulators)
 int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, const float* A_lo, int64_t lda,
                      const float* W_hi, const float* W_lo, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);
+int linear_tc_launch_ex(gigl_ctx* ctx, int64_t M, const int32_t* m_dev, int N, int K, const float* A_hi, const float* A_lo, int64_t lda,
+                        const float* W_hi, const float* W_lo, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu);
 int split_tf32_launch(gigl_ctx* ctx, int64_t rows, int cols, const float* x, int64_t ldx, float* hi, float* lo, int64_t ldo);
 // gemm_tn_tcgen05.cu: C = G^T A (weight gradients; split-K over the rows, deterministic), column sums (bias gradient)
 int linear_tn_tc_launch(gigl_ctx* ctx, int64_t R, int M, int N, const float* G_hi, const float* G_lo, int64_t ldg, const float* A_hi,

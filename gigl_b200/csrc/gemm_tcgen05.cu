@@ -9,14 +9,17 @@
 // (10-bit mantissa) cannot meet, so every operand is split into two TF32 terms
 // (x ~ hi + lo, hi = x rounded to TF32, lo = (x - hi) rounded to TF32; common.cuh gigl_split_tf32) and
 // three tensor-core products are accumulated in fp32 in TMEM:  hi*hi + lo*hi + hi*lo  (3xTF32,
-// relative error ~2^-21).  The split of A is done by the producer of A (the gather kernel writes
-// both halves), the split of W once at model-creation time, so this kernel is a pure
-// TMA -> tcgen05.mma -> TMEM -> epilogue pipeline:
+// relative error ~2^-21).  W is split once at model-creation time.  A arrives either already split (two tensors, the
+// full-graph forms) or RAW (split_a: the batch path) - then the fp32 tile TMA drops into shared memory is split in
+// place by four converter warps (hi over the raw tile, lo beside it) before the MMA warp sees it, so the intermediate
+// [mean | self] rows cross HBM once in each direction instead of twice:
 //
-//   warp 0      : TMA producer - four 128-byte-swizzled K-major tiles per stage (A_hi, A_lo, W_hi, W_lo)
+//   warp 0      : TMA producer - 128-byte-swizzled K-major tiles per stage (A_hi, A_lo | A raw; W_hi, W_lo)
 //   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N<=256, K=8)
 //   warps 2..5  : epilogue - tcgen05.ld the accumulator (each warp its own 32-lane quarter),
 //                 bias + ReLU, fp32 rows to global memory
+//   warps 6..9  : (split_a only) TF32 split of the A tile, elementwise, so the swizzle is untouched;
+//                 fence.proxy.async hands the tile from the generic to the async proxy
 //
 // Persistent over the M tiles (grid = min(tiles, SMs)), accumulators double-buffered in TMEM so
 // the epilogue of tile t overlaps the MMAs of tile t+1, smem ring of 2..4 stages.
@@ -33,6 +36,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;              // 32 fp32 = 128 bytes = one swizzle span
 constexpr int kUmmaK = 8;                // tf32
 constexpr int kGemmThreads = 192;
+constexpr int kGemmThreadsSplit = 320;   // + 4 converter warps
 constexpr int kEpiPitch = 36;             // floats per row of an epilogue warp's 32 x 32 staging tile
 constexpr size_t kEpiBytes = 4 * 32 * kEpiPitch * sizeof(float);
 
@@ -50,10 +54,12 @@ struct GemmParams {
     float* C;
     int64_t ldc;
     int relu;
+    int split_a;           // A is raw fp32 (tm_a_hi maps it, tm_a_lo is unused): split in shared memory
+    const int32_t* m_dev;  // optional device-side row count (<= M): the host sized buffers and maps by an upper bound
     int dbg;  // GIGL_GEMM_DBG (timing experiments only): 1 = no MMA, 2 = no W loads, 4 = no A loads, 8 = no epilogue stores
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsSplit, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                      const GemmParams p) {
@@ -64,16 +70,22 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     const uint32_t w_bytes = (uint32_t)p.n_pad * kBlockK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-    // bars: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2]
+    // bars: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | conv[stages]
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * p.stages;
     const uint32_t bar_tfull = bar_empty + 8 * p.stages;
     const uint32_t bar_tempty = bar_tfull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+    const uint32_t bar_conv = bar_tempty + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 4);
     const uint32_t smem_base = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles_m = (p.M + kBlockM - 1) / kBlockM;
+    int64_t M = p.M;
+    if (p.m_dev != nullptr) {
+        const int64_t m = *p.m_dev;
+        if (m < M) M = m;
+    }
+    const int64_t n_tiles_m = (M + kBlockM - 1) / kBlockM;
     const int64_t n_tiles = n_tiles_m * p.n_tiles_n;
     const int num_kb = (p.K + kBlockK - 1) / kBlockK;
 
@@ -81,6 +93,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 4);  // one arrive per converter warp
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
@@ -110,10 +123,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    mbar_expect_tx(full, ((p.dbg & 4) ? 0 : 2 * a_bytes) + ((p.dbg & 2) ? 0 : 2 * w_bytes));
+                    mbar_expect_tx(full, ((p.dbg & 4) ? 0 : (p.split_a ? a_bytes : 2 * a_bytes)) + ((p.dbg & 2) ? 0 : 2 * w_bytes));
                     if (!(p.dbg & 4)) {
                         tma_load_2d(sa, &tm_a_hi, full, kb * kBlockK, m0);
-                        tma_load_2d(sa + a_bytes, &tm_a_lo, full, kb * kBlockK, m0);
+                        if (!p.split_a) tma_load_2d(sa + a_bytes, &tm_a_lo, full, kb * kBlockK, m0);
                     }
                     if (!(p.dbg & 2)) {
                         tma_load_2d(sa + 2 * a_bytes, &tm_w_hi, full, kb * kBlockK, n0);
@@ -143,7 +156,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                 const uint32_t tmem_d = tmem_base + acc * acc_cols;
                 const uint32_t tmem_s = tmem_d + (uint32_t)p.n_pad;  // small-term accumulator (split_acc only)
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase);
+                    mbar_wait((p.split_a ? bar_conv : bar_full) + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint64_t d_ah = umma_desc_sw128(sa), d_al = umma_desc_sw128(sa + a_bytes);
@@ -170,6 +183,39 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                     }
                 }
                 umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== converter warps 6..9 (split_a): raw fp32 A tile -> TF32 hi (in place) + lo =====
+        if (p.split_a) {
+            const int t = threadIdx.x - 192;  // 0..127: eight float4 each, consecutive threads on consecutive 16 bytes
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    float4* hi = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
+                    float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + a_bytes);
+#pragma unroll
+                    for (int q = 0; q < (int)(kBlockM * kBlockK / 4 / 128); ++q) {
+                        const int idx = q * 128 + t;
+                        const float4 v = hi[idx];
+                        float4 h, l;
+                        gigl_split_tf32(v.x, h.x, l.x);
+                        gigl_split_tf32(v.y, h.y, l.y);
+                        gigl_split_tf32(v.z, h.z, l.z);
+                        gigl_split_tf32(v.w, h.w, l.w);
+                        hi[idx] = h;
+                        lo[idx] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_conv + 8 * stage);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
             }
         }
     } else {
@@ -232,12 +278,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                                 o.z = fmaxf(o.z, 0.f);
                                 o.w = fmaxf(o.w, 0.f);
                             }
-                            if (row < p.M) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = o;
+                            if (row < M) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = o;
                         }
                     } else if (ncol > 0 && c0 + cc < p.n_pad) {
                         for (int r = 0; r < 32; r += 4) {
                             const int64_t row = row0 + r + rr;
-                            if (row >= p.M) continue;
+                            if (row >= M) continue;
                             for (int j = 0; j < 4 && j < ncol; ++j) {
                                 float f = stg[(r + rr) * kEpiPitch + cc + j] + (p.bias ? __ldg(p.bias + col + j) : 0.f);
                                 if (p.relu) f = fmaxf(f, 0.f);
@@ -296,6 +342,13 @@ static int make_map(gigl_ctx* ctx, CUtensorMap* map, const float* base, int64_t 
 // A_hi / A_lo: [M, K] with pitch lda; W_hi / W_lo: [N, K] with pitch ldw; all 16-byte aligned, pitches % 4 == 0.
 int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, const float* A_lo, int64_t lda,
                      const float* W_hi, const float* W_lo, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu) {
+    return linear_tc_launch_ex(ctx, M, nullptr, N, K, A_hi, A_lo, lda, W_hi, W_lo, ldw, bias, C, ldc, relu);
+}
+
+// A_lo == nullptr: A_hi is the RAW fp32 operand, split inside the kernel.  m_dev: optional device-side row count <= M
+// (M then is the bound the buffers were sized by; rows at and beyond *m_dev are neither computed nor stored).
+int linear_tc_launch_ex(gigl_ctx* ctx, int64_t M, const int32_t* m_dev, int N, int K, const float* A_hi, const float* A_lo, int64_t lda,
+                        const float* W_hi, const float* W_lo, int64_t ldw, const float* bias, float* C, int64_t ldc, int relu) {
     using namespace gigl;
     if (M == 0 || N == 0) return GIGL_OK;
     GIGL_CHECK(ctx, K >= 1 && lda % 4 == 0 && ldw % 4 == 0, "tensor-core projection needs pitches that are multiples of 4 floats");
@@ -323,12 +376,14 @@ int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, 
     p.C = C;
     p.ldc = ldc;
     p.relu = relu;
+    p.split_a = A_lo == nullptr ? 1 : 0;
+    p.m_dev = m_dev;
     static const int dbg = getenv("GIGL_GEMM_DBG") ? atoi(getenv("GIGL_GEMM_DBG")) : 0;
     p.dbg = dbg;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
     int rc;
     if ((rc = make_map(ctx, &ta_hi, A_hi, M, K, lda, kBlockM, false)) != GIGL_OK) return rc;
-    if ((rc = make_map(ctx, &ta_lo, A_lo, M, K, lda, kBlockM, false)) != GIGL_OK) return rc;
+    if ((rc = make_map(ctx, &ta_lo, A_lo ? A_lo : A_hi, M, K, lda, kBlockM, false)) != GIGL_OK) return rc;
     if ((rc = make_map(ctx, &tw_hi, W_hi, N, K, ldw, p.n_pad, true)) != GIGL_OK) return rc;
     if ((rc = make_map(ctx, &tw_lo, W_lo, N, K, ldw, p.n_pad, true)) != GIGL_OK) return rc;
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/ + kEpiBytes;
@@ -339,7 +394,7 @@ int linear_tc_launch(gigl_ctx* ctx, int64_t M, int N, int K, const float* A_hi, 
     }
     const int64_t n_tiles = ((M + kBlockM - 1) / kBlockM) * p.n_tiles_n;
     const int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
-    linear_tf32x3_kernel<<<grid, kGemmThreads, smem, ctx->stream>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+    linear_tf32x3_kernel<<<grid, p.split_a ? kGemmThreadsSplit : kGemmThreads, smem, ctx->stream>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
     GIGL_LAUNCHED(ctx);
     return GIGL_OK;
 }

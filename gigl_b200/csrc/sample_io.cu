@@ -882,7 +882,7 @@ int64_t gigl_tfrecord_index_host(const uint8_t* data, int64_t n_bytes, int32_t v
     if (!data || n_bytes < 0) return GIGL_E_INVALID;
     int64_t pos = 0, n = 0;
     while (pos < n_bytes) {
-        if (pos + 12 > n_bytes) return GIGL_E_INVALID;
+        if (n_bytes - pos < 16) return GIGL_E_INVALID;  // length (8) + its crc (4) + the payload crc (4): a truncated tail
         uint64_t len;
         uint32_t c;
         memcpy(&len, data + pos, 8);

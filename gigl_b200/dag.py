@@ -6,7 +6,10 @@ Every op expands the result nodes of its input ops (or the root) over ONE edge t
 most one input (tree-shaped DAGs: chains that branch) map one to one onto `gigl_sample_op_*` launches - one kernel
 launch per op over that edge type's CSR, ancestors' padded trees as the frontier.  An op with several inputs (the union
 of several parents' results, GraphDBSampler.scala:66-82) runs once per input - one launch per (op, input) instance -
-and its result set is the union of the instances' outputs.
+and its result set is the union of the instances' outputs.  Like the reference, an op expands every DISTINCT frontier
+node once per root: the parents' results are a HashSet[Node] there; here the parent level is passed through
+`Context.frontier_distinct` (gigl_frontier_distinct_dev), which keeps the first slot of every node - also against the
+op's earlier input instances - so a node reached along several paths contributes at most `numNodesToSample` edges per op.
 
 The reference's graph-DB clients do not sample reproducibly (`LocalDbClient.scala:186,204` takes `Set.take(n)`; Nebula
 samples server-side), so there is nothing bit-level to match: each op draws GiGL's seeded hash permutation with the op's
@@ -109,16 +112,34 @@ def plan(ops: Sequence[SamplingOp], root_node_type: str) -> List[PlannedOp]:
     return order
 
 
+def frontier_of(p: PlannedOp, res: dict, frontiers: dict, distinct):
+    """The level instance `p` expands: its parent's padded tree with, per root, only the first slot of every distinct node
+    kept - against the parent's own lower slots and against the frontiers of the same op's earlier instances
+    (GraphDBSampler.scala:66-82: one HashSet[Node] over all the parents' results).  `distinct(cur, slots, prev)` is
+    `Context.frontier_distinct` on the device or `oracle.np_frontier_distinct` in the CPU tests."""
+    slots = 1
+    for f in p.fanouts[:-1]:
+        slots *= f
+    prev = frontiers.setdefault(p.op.op_name, [])
+    level = distinct(res[p.parent][0], slots, list(prev))
+    prev.append((level, slots))
+    return level
+
+
 def sample_dag(graphs: Dict[Tuple[Tuple[str, str, str], str], "object"], roots, ops: Sequence[SamplingOp], root_node_type: str,
-               base_seed: int = 42, call_no_offset: int = 0):
+               base_seed: int = 42, call_no_offset: int = 0, distinct_frontier: bool = True):
     """Runs every op instance on the device.  `graphs[(edge_type, direction)]` = the :class:`gigl_b200.Graph` of that edge
     type, built by destination for INCOMING ops and `by_source=True` for OUTGOING ones.  `roots`: int32 CUDA tensor.
     Returns {instance key: (nbr, cnt, chain_fanouts)} with the padded-tree layout of `Graph.sample_khop` (the key is the op
-    name unless the op has several inputs, see :func:`plan`)."""
+    name unless the op has several inputs, see :func:`plan`).  distinct_frontier = False expands every slot of the parent
+    level (one expansion per PATH, the pure-Spark GROUP BY semantics) instead of every distinct node."""
     res = {}
+    frontiers: dict = {}
     for p in plan(ops, root_node_type):
         chain_nbr = [res[k][0] for k in p.chain[:-1]]
         g = graphs[(p.op.edge_type, p.op.sampling_direction)]
+        if distinct_frontier and p.parent is not None:
+            chain_nbr[-1] = frontier_of(p, res, frontiers, g.ctx.frontier_distinct)
         nbr, cnt = g.sample_op(roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, base_seed)
         res[p.key] = (nbr, cnt, p.fanouts)
     return res

@@ -183,6 +183,20 @@ class Context:
                                          out.stride(0), int(accumulate)), self.handle)
         return out
 
+    def frontier_distinct(self, cur, cur_slots: int, prev: Sequence = ()):
+        """cur: int32 CUDA tensor [n_roots * cur_slots] (a parent level of a SamplingOp); prev: [(tensor, slots), ...] the
+        levels of the op's earlier input instances.  Returns a copy with, per root, only the first slot of every distinct
+        node kept (gigl_frontier_distinct_dev; GraphDBSampler.scala:66-82 expands the SET of the parents' results)."""
+        import torch
+
+        n_roots = cur.numel() // cur_slots
+        out = torch.empty_like(cur)
+        n_prev = len(prev)
+        pp = (C.c_void_p * max(n_prev, 1))(*[t.data_ptr() for t, _ in prev])
+        ps = _np([s for _, s in prev] or [1], np.int32)
+        check(self._L.gigl_frontier_distinct_dev(self.handle, n_roots, n_prev, pp, _hp(ps), _dp(cur), cur_slots, _dp(out)), self.handle)
+        return out
+
     def gather_mean(self, x, rowptr, col, n_rows_out: Optional[int] = None, out=None):
         import torch
 

@@ -40,30 +40,64 @@ def shard_rows(n_nodes: int, world: int, granule: int) -> int:
     return -(-per // granule) * granule
 
 
-def _uds_name(tag: str, rank: int) -> str:
-    return f"\0gigl_b200_{tag}_{rank}"  # abstract namespace: no file to clean up
+def _uds_dir(tag: str) -> str:
+    """Directory of the job's fd sockets: private to this user (0700, ownership checked), one per job tag."""
+    import os
+    import stat
+    import tempfile
+
+    d = os.path.join(tempfile.gettempdir(), f"gigl_b200_{os.getuid()}_{tag}")
+    try:
+        os.mkdir(d, 0o700)
+    except FileExistsError:
+        pass
+    st = os.lstat(d)
+    if not stat.S_ISDIR(st.st_mode) or st.st_uid != os.getuid() or (st.st_mode & 0o077):
+        raise PermissionError(f"{d} is not a private directory of this user")
+    return d
+
+
+def _peer_uid(conn) -> int:
+    import socket
+    import struct
+
+    cred = conn.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i"))
+    return struct.unpack("3i", cred)[1]
 
 
 def exchange_fds(my_fd: int, rank: int, world: int, tag: str, timeout: float = 120.0):
     """Every rank hands a duplicate of ``my_fd`` to every peer over Unix sockets (SCM_RIGHTS) and gets theirs:
-    returns {peer_rank: fd}.  All processes must be on one host (one box = one NVSwitch domain)."""
+    returns {peer_rank: fd}.  All processes must be on one host (one box = one NVSwitch domain).  The fd maps this GPU's
+    feature shard read/write, so the sockets live in a 0700 directory of this user and a server only answers a peer
+    whose SO_PEERCRED uid is its own."""
+    import os
     import socket
     import threading
     import time
 
     if world == 1:
         return {}
+    d = _uds_dir(tag)
+    path = os.path.join(d, f"{rank}.sock")
+    try:
+        os.unlink(path)
+    except FileNotFoundError:
+        pass
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    srv.bind(_uds_name(tag, rank))
+    srv.bind(path)
     srv.listen(world)
     srv.settimeout(timeout)
 
     def serve():
-        for _ in range(world - 1):
+        served = 0
+        while served < world - 1:
             conn, _ = srv.accept()
             with conn:
+                if _peer_uid(conn) != os.getuid():
+                    continue
                 conn.recv(4)
                 socket.send_fds(conn, [b"fd"], [my_fd])
+                served += 1
 
     th = threading.Thread(target=serve, daemon=True)
     th.start()
@@ -75,7 +109,7 @@ def exchange_fds(my_fd: int, rank: int, world: int, tag: str, timeout: float = 1
         while True:
             c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
             try:
-                c.connect(_uds_name(tag, peer))
+                c.connect(os.path.join(d, f"{peer}.sock"))
                 break
             except (ConnectionRefusedError, FileNotFoundError):
                 c.close()
@@ -88,6 +122,10 @@ def exchange_fds(my_fd: int, rank: int, world: int, tag: str, timeout: float = 1
             got[peer] = fds[0]
     th.join(timeout)
     srv.close()
+    try:
+        os.unlink(path)
+    except FileNotFoundError:
+        pass
     return got
 
 

@@ -37,6 +37,7 @@ valid uniform sample; bit-exact to the reference's `permutation_strategy: determ
 from __future__ import annotations
 
 import os
+import re
 import sys
 import time
 from typing import List, Optional
@@ -121,6 +122,34 @@ def _roots_to_device(roots: np.ndarray, device: int):
     import torch
 
     return torch.from_numpy(np.ascontiguousarray(roots, dtype=np.int32)).to(torch.device("cuda", device))
+
+
+_PART_RE = re.compile(r"^part-(?:r(\d+)-)?\d+\.tfrecord$")
+
+
+def _prepare_dir(dir_: str) -> None:
+    """mode("overwrite") of the reference's writer (TFRecordIO.scala:62): part files of an earlier run under this prefix
+    are removed before anything is written, so a re-run with another world size / batch size / sample limit leaves no
+    stale samples for downstream globs.  No collective: every stale file has exactly one remover - rank r its own
+    `part-r<r>-*`, rank 0 the un-ranked files and those of ranks >= world - and each rank removes before it writes."""
+    rank, world = _SHARD
+    os.makedirs(dir_, exist_ok=True)
+    for name in os.listdir(dir_):
+        m = _PART_RE.match(name)
+        if not m:
+            continue
+        owner = None if m.group(1) is None else int(m.group(1))
+        if world == 1:
+            mine = True
+        elif owner is None or owner >= world:
+            mine = rank == 0
+        else:
+            mine = owner == rank
+        if mine:
+            try:
+                os.remove(os.path.join(dir_, name))
+            except FileNotFoundError:
+                pass
 
 
 def _write(dir_: str, part: int, data) -> None:
@@ -245,9 +274,9 @@ def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n
         labels[node_id] = nodes.column(label_key, "int64").astype(np.int32)
     unl_dir = _resolve(out["unlabeledTfrecordUriPrefix"], root)
     lab_dir = _resolve(out["labeledTfrecordUriPrefix"], root)
-    os.makedirs(unl_dir, exist_ok=True)
+    _prepare_dir(unl_dir)
     if labels is not None:
-        os.makedirs(lab_dir, exist_ok=True)
+        _prepare_dir(lab_dir)
     for part, s in enumerate(range(0, len(roots_all), batch_roots)):
         roots = roots_all[s:s + batch_roots]
         nbr, cnt = g.sample_khop_host(roots, fanouts, base_seed=SAMPLING_SEED, first_call_no=1)
@@ -287,12 +316,12 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
                        "edge type")  # the reference throws here too (NodeAnchorBasedLinkPredictionTask.scala:101-108)
     rnn_dir = _resolve(neg_map[dst_type], root)
     main_dir = _resolve(out["tfrecordUriPrefix"], root)
-    os.makedirs(rnn_dir, exist_ok=True)
+    _prepare_dir(rnn_dir)
     g_pos = g_neg = pos_tab = neg_tab = None
     num_pos = num_neg = 0
     main_tab = sio.HostEdgeTable(hyd["csr"], hyd["edge_rows"], hyd["edge_feat"])
     if not skip_main:
-        os.makedirs(main_dir, exist_ok=True)
+        _prepare_dir(main_dir)
         if "pos" in label_tables:
             num_pos = int(sgs.get("numUserDefinedPositiveSamples", 0))
             if num_pos < 1:  # the reference asserts this (UserDefinedLabelsNodeAnchorBasedLinkPredictionTask.scala:81-88)
@@ -458,7 +487,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
         if rtype not in out_dirs:
             continue
         out_dir = _resolve(out_dirs[rtype], root)
-        os.makedirs(out_dir, exist_ok=True)
+        _prepare_dir(out_dir)
         roots_all = _my_share(ids[cnt_of[rtype]])
         hydrate = dags[rtype][2]
         for part, s in enumerate(range(0, len(roots_all), batch_roots)):
@@ -482,7 +511,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
         hyd_pos = edge_feat[pos_cet] is not None  # posEdgeHasEdgeFeatures (:344-346)
         pos_call = len(dags[a_type][0]) + 1  # the positives are drawn after the anchor's own ops (= call 3 after a 2-hop chain)
         main_dir = _resolve(flat["nodeAnchorBasedLinkPredictionOutput"]["tfrecordUriPrefix"], root)
-        os.makedirs(main_dir, exist_ok=True)
+        _prepare_dir(main_dir)
         anchors_all = _my_share(ids[cnt_of[a_type]])
         if max_train > 0:
             # numMaxTrainingSamplesToOutput: the reference draws a random `.sample(fraction)` of the anchors' RNNs before the

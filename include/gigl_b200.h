@@ -189,6 +189,17 @@ int gigl_sample_op_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, in
                         const int32_t* const* chain_nbr, int32_t base_seed, int32_t call_no, int32_t* nbr_out, int32_t* cnt_out);
 
 /*
+ * Distinct frontier of a SamplingOp (replaces the HashSet[Node] the reference's graph-DB sampler collects the parents'
+ * result nodes into before an op's query runs, scala_spark35/subgraph_sampler/src/main/scala/libs/sampler/
+ * GraphDBSampler.scala:66-82): out = cur ([n_roots * cur_slots], a parent level in the padded-tree layout) with, per
+ * root, every node that already occurs at a lower slot of cur, or anywhere in one of the n_prev (<= 8) earlier lists
+ * prev[p] ([n_roots * prev_slots[p]], the op's earlier input instances), replaced by -1.  gigl_sample_op_* expands
+ * the copy: each distinct frontier node is then expanded once per op, as the reference does.
+ */
+int gigl_frontier_distinct_dev(gigl_ctx* ctx, int64_t n_roots, int32_t n_prev, const int32_t* const* prev_dev,
+                               const int32_t* prev_slots, const int32_t* cur_dev, int32_t cur_slots, int32_t* out_dev);
+
+/*
  * Positive (out-edge) sampling for node-anchor link prediction: `g_out` is the CSR by SOURCE;
  * for every src u: P(u) = first num_pos of perm(OUT(u), internal_seed = u, call_no) - the NABLP
  * task calls it third, so call_no = 3.  pos: int32[n_srcs * num_pos] (-1 padded), pos_cnt: int32[n_srcs].

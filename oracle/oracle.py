@@ -300,6 +300,49 @@ def np_sample_op(csr, roots, fanouts, chain_nbr, call_no, base_seed=42):
     return out, oc
 
 
+def np_frontier_distinct(cur, cur_slots: int, prev=()):
+    """The frontier a SamplingOp expands: per root, the SET of its parents' result nodes
+    (GraphDBSampler.scala:66-82 collects them into a HashSet[Node]).  cur: [n_roots * cur_slots] parent level; prev:
+    [(level, slots), ...] of the op's earlier input instances.  Returns cur with every later occurrence of a node (per
+    root; -1 = empty) replaced by -1."""
+    cur = np.asarray(cur, dtype=np.int32).reshape(-1, cur_slots)
+    out = cur.copy()
+    prev = [(np.asarray(p, dtype=np.int32).reshape(-1, s)) for p, s in prev]
+    for r in range(cur.shape[0]):
+        seen = set()
+        for p in prev:
+            seen.update(int(v) for v in p[r] if v >= 0)
+        for s in range(cur_slots):
+            v = int(cur[r, s])
+            if v < 0:
+                continue
+            if v in seen:
+                out[r, s] = -1
+            else:
+                seen.add(v)
+    return out.reshape(-1)
+
+
+def np_sample_dag(planned, csr_of, roots, base_seed=42, call_no_offset=0, distinct=True):
+    """A whole SamplingOp DAG on the CPU, the way gigl_b200.dag.sample_dag runs it on the device: the planned op instances
+    in order, each ONE np_sample_op over csr_of(instance) = (rowptr, col) of its edge type and direction, expanding its
+    parent's level reduced to the distinct nodes per root (np_frontier_distinct: the HashSet[Node] of
+    GraphDBSampler.scala:66-82), also against the earlier instances of the same op.  `planned`: objects with .key,
+    .parent, .chain, .fanouts, .call_no and .op.op_name (gigl_b200.dag.plan output).  -> {key: (nbr, cnt, fanouts)}"""
+    res, frontiers = {}, {}
+    for p in planned:
+        chain_nbr = [res[k][0] for k in p.chain[:-1]]
+        if distinct and p.parent is not None:
+            slots = int(np.prod(p.fanouts[:-1], dtype=np.int64))
+            prev = frontiers.setdefault(p.op.op_name, [])
+            level = np_frontier_distinct(res[p.parent][0], slots, list(prev))
+            prev.append((level, slots))
+            chain_nbr[-1] = level
+        nbr, cnt = np_sample_op(csr_of(p), roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, base_seed)
+        res[p.key] = (nbr, cnt, list(p.fanouts))
+    return res
+
+
 def tree_to_edges(roots, nbr, fanouts):
     """Padded tree -> per-root list of (src, dst) index pairs, src = hop-k node, dst = hop-(k-1)
     node (SGSPureSparkV1Task.scala:615-629), one pair per sampled slot (explode semantics)."""

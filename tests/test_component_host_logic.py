@@ -26,17 +26,23 @@ class _Ctx:
     def edge_rows_host(self, n, src, dst, directed):
         return np_edge_rows(src, dst, n, directed)
 
+    def frontier_distinct(self, cur, cur_slots, prev=()):
+        import torch
+
+        return torch.from_numpy(O.np_frontier_distinct(cur.numpy(), cur_slots, [(t.numpy(), s) for t, s in prev]))
+
 
 class _Graph:
-    def __init__(self, rowptr, col):
+    def __init__(self, rowptr, col, ctx=None):
         self.rowptr, self.col = rowptr, col
         self.n_edges = len(col)
+        self.ctx = ctx or _Ctx()
 
     @classmethod
     def from_edges_host(cls, ctx, n, src, dst, is_graph_directed=True, by_source=False):
         if by_source:  # out-CSR: row u = sorted destinations of u
-            return cls(*O.np_build_in_csr(dst, src, n, is_graph_directed))
-        return cls(*O.np_build_in_csr(src, dst, n, is_graph_directed))
+            return cls(*O.np_build_in_csr(dst, src, n, is_graph_directed), ctx=ctx)
+        return cls(*O.np_build_in_csr(src, dst, n, is_graph_directed), ctx=ctx)
 
     def csr_host(self):
         return self.rowptr, self.col

@@ -115,6 +115,17 @@ def _nablp_fixture(tmp, directed, n=40, e=220, with_edge_feat=True, strategy=Non
     return src, dst, x, ef
 
 
+def _dag_levels(path, roots, csr_by_op, keys):
+    """The oracle's run of one messagePassingPaths entry (the config dict the component reads): op instance key -> padded
+    tree, every op expanding the distinct result nodes of its inputs once (oracle.np_sample_dag)."""
+    from gigl_b200 import dag
+    from oracle import oracle as O
+
+    planned = dag.plan(dag.ops_from_config(path), path["rootNodeType"])
+    res = O.np_sample_dag(planned, lambda p: csr_by_op[p.op.op_name], roots)
+    return [res[k][0] for k in keys]
+
+
 def _canon(sample, key="edges"):
     return sorted((e["src_node_id"], e["dst_node_id"], tuple(np.float32(e["feature_values"]).tolist())) for e in sample[key])
 
@@ -295,7 +306,7 @@ def test_typed_component_writes_rnn_per_node_type(tmp_path):
     outg = lambda e: O.np_build_in_csr(e[1], e[0], n, True)  # noqa: E731
     # paper roots: writers <- author_to_paper (call 1), their_papers <- paper_to_author (call 2)
     roots = np.arange(n_p, dtype=np.int32)
-    ch, _ = O.np_sample_chain([inc(a2p), inc(p2a)], roots, [3, 2], [1, 2])
+    ch = _dag_levels(paths[0], roots, {"writers": inc(a2p), "their_papers": inc(p2a)}, ["writers", "their_papers"])
     want = O.np_assemble_dag_rnn(roots, 1, [dict(parent=-1, fanout=3, condensed_edge_type=0, result_node_type=0, nbr=ch[0]),
                                             dict(parent=0, fanout=2, condensed_edge_type=1, result_node_type=1, nbr=ch[1])])
     raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / "out/rnn/paper/")))
@@ -390,16 +401,14 @@ def test_typed_component_hydrates_edge_features_and_isolated_anchors(tmp_path):
     outg = lambda e: O.np_build_in_csr(e[1], e[0], n, True)  # noqa: E731
     records = O.np_typed_edge_records({0: (follows[0], follows[1], None), 1: (clicks[0], clicks[1], cf)})
     users = np.arange(n_u, dtype=np.int32)
-    liked, _ = O.np_sample_chain([outg(clicks)], users, [2], [1])
-    friends, _ = O.np_sample_chain([inc(follows)], users, [2], [2])
-    co, _ = O.np_sample_chain([outg(clicks), inc(clicks)], users, [2, 2], [1, 3])
-    fans_a, _ = O.np_sample_chain([inc(follows), inc(follows)], users, [2, 2], [2, 4])
-    fans_b, _ = O.np_sample_chain([outg(clicks), inc(clicks), inc(follows)], users, [2, 2, 2], [1, 3, 4])
-    uops = [dict(parent=-1, fanout=2, condensed_edge_type=1, result_node_type=1, outgoing=True, nbr=liked[0]),
-            dict(parent=-1, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=friends[0]),
-            dict(parent=0, fanout=2, condensed_edge_type=1, result_node_type=0, nbr=co[1]),
-            dict(parent=1, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=fans_a[1]),
-            dict(parent=2, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=fans_b[2])]
+    # every op expands the distinct result nodes of its inputs once (GraphDBSampler.scala:66-82); `fans` has two inputs
+    lv = _dag_levels(paths[0], users, {"liked": outg(clicks), "friends": inc(follows), "co_clickers": inc(clicks), "fans": inc(follows)},
+                     ["liked", "friends", "co_clickers", "fans@friends", "fans@co_clickers"])
+    uops = [dict(parent=-1, fanout=2, condensed_edge_type=1, result_node_type=1, outgoing=True, nbr=lv[0]),
+            dict(parent=-1, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=lv[1]),
+            dict(parent=0, fanout=2, condensed_edge_type=1, result_node_type=0, nbr=lv[2]),
+            dict(parent=1, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=lv[3]),
+            dict(parent=2, fanout=2, condensed_edge_type=0, result_node_type=0, nbr=lv[4])]
     items = np.arange(n_i, dtype=np.int32)
     clk, _ = O.np_sample_chain([inc(clicks)], items, [3], [1])
     iops = [dict(parent=-1, fanout=3, condensed_edge_type=1, result_node_type=0, nbr=clk[0])]
@@ -498,6 +507,7 @@ def test_typed_component_on_the_reference_heterogeneous_fixture(tmp_path):
     prediction/frozen_gbml_config_graphdb_dblp_local.yaml) end to end: typed hydrated RootedNodeNeighborhoods for authors and
     papers, then the main samples of the author -to-> paper supervision edge type (numPositiveSamples 1,
     numMaxTrainingSamplesToOutput 10), against the oracle's restatement; every hop takes min(fanout, in-degree) neighbours."""
+    from gigl_b200 import dag
     from gigl_b200 import sample_io as sio
     from gigl_b200 import subgraph_sampler
     from oracle import oracle as O
@@ -519,7 +529,10 @@ def test_typed_component_on_the_reference_heterogeneous_fixture(tmp_path):
     # author roots: op_4 = papers <- (paper to author), op_6 = authors <- (author to paper); paper roots: op_1, op_3 mirrored
     for name, rt, n_roots, t1, t2 in (("author", 0, n_a, 1, 0), ("paper", 1, n_p, 0, 1)):
         roots = np.arange(n_roots, dtype=np.int32)
-        ch, cc = O.np_sample_chain([inc[t1], inc[t2]], roots, [10, 10], [1, 2])
+        types = ["author", "paper"]
+        two_ops = [dag.SamplingOp("o1", (types[1 - rt], "r1", types[rt]), 10), dag.SamplingOp("o2", (types[rt], "r2", types[1 - rt]), 10, ["o1"])]
+        lv = O.np_sample_dag(dag.plan(two_ops, types[rt]), lambda p: inc[t1] if p.op.op_name == "o1" else inc[t2], roots)
+        ch, cc = [lv["o1"][0], lv["o2"][0]], [lv["o1"][1], lv["o2"][1]]
         deg1 = np.diff(inc[t1][0])[roots]
         assert np.array_equal(cc[0], np.minimum(deg1, 10))  # every hop takes min(fanout, in-degree) neighbours
         ops = [dict(parent=-1, fanout=10, condensed_edge_type=t1, result_node_type=1 - rt, nbr=ch[0]),

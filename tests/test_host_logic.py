@@ -1,5 +1,7 @@
 """CPU: host-side logic that needs no GPU - the SamplingOp DAG planner, the packed index-set layout, the sampler
 component's root sharding."""
+import os
+
 import numpy as np
 import pytest
 
@@ -147,3 +149,36 @@ def test_collation_counts_of_the_reference_batching_tests():
     twice = _collate(["triangle", "triangle"])
     assert sorted(once[0].tolist()) == sorted(twice[0].tolist()) == [0, 1, 2] and once[1] == twice[1] == [(0, 1), (0, 2), (1, 2)]
     assert len(np.unique(twice[0])) == len(twice[0])  # local ids are one per distinct node
+
+
+def test_output_prefix_is_overwritten_not_appended_to(tmp_path):
+    """TFRecordIO.scala:62 writes with mode("overwrite"): part files of an earlier run (another world size, batch size or
+    sample limit) must not survive beside the new ones.  Every stale file has exactly one remover, so ranks need no
+    collective: rank r its own files, rank 0 the un-ranked ones and those of ranks >= world."""
+    from gigl_b200 import subgraph_sampler as S
+
+    d = str(tmp_path / "samples")
+    os.makedirs(d)
+    stale = ["part-00000.tfrecord", "part-00007.tfrecord", "part-r000-00000.tfrecord", "part-r001-00003.tfrecord",
+             "part-r005-00000.tfrecord", "_SUCCESS", "notes.txt"]
+
+    def fill():
+        for n in stale:
+            open(os.path.join(d, n), "wb").write(b"x")
+
+    old = S._SHARD
+    try:
+        fill()
+        S._SHARD = (0, 1)
+        S._prepare_dir(d)
+        assert sorted(os.listdir(d)) == ["_SUCCESS", "notes.txt"]
+        fill()
+        S._SHARD = (1, 2)
+        S._prepare_dir(d)  # rank 1 of 2 removes only its own
+        assert "part-r001-00003.tfrecord" not in os.listdir(d) and "part-r000-00000.tfrecord" in os.listdir(d)
+        assert "part-00000.tfrecord" in os.listdir(d) and "part-r005-00000.tfrecord" in os.listdir(d)
+        S._SHARD = (0, 2)
+        S._prepare_dir(d)  # rank 0 removes its own, the un-ranked files and those of ranks that no longer exist
+        assert sorted(os.listdir(d)) == ["_SUCCESS", "notes.txt"]
+    finally:
+        S._SHARD = old

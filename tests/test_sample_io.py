@@ -31,6 +31,35 @@ def test_crc32c_and_tfrecord_framing_of_a_reference_file():
         pass
 
 
+def test_truncated_tfrecord_tail_is_an_error_not_a_crash():
+    """A partially written part file: every cut of 1..15 bytes into a record's 16 bytes of framing (and cuts inside the
+    payload, and a length field pointing far past the buffer) raises GiglError in both verify modes - the bounds check
+    once underflowed when 12..15 bytes remained."""
+    import struct
+
+    raw = _b64("snc16_node_data.tfrecord.b64")
+    t = sio.ExampleTable(raw, verify=True)
+    first_len = int(t.lengths[0])
+    rec0 = 16 + first_len
+    for verify in (True, False):
+        for extra in list(range(1, 16)) + [16, 16 + first_len // 2, rec0 - 1]:
+            try:
+                sio.ExampleTable(raw[: rec0 + extra], verify=verify)
+                assert False, f"truncated tail of {extra} bytes accepted (verify={verify})"
+            except sio.GiglError:
+                pass
+        assert sio.ExampleTable(raw[:rec0], verify=verify).n == 1
+    # a 14-byte stream: valid length crc, length 2^33
+    hdr = struct.pack("<Q", 1 << 33)
+    bogus = hdr + struct.pack("<I", sio.crc32c_masked(hdr)) + b"\x00\x00"
+    for verify in (True, False):
+        try:
+            sio.ExampleTable(bogus, verify=verify)
+            assert False
+        except sio.GiglError:
+            pass
+
+
 def test_example_columns_match_the_fixture_graph():
     g = load_golden("snc16_graph.json")
     nodes = sio.ExampleTable(_b64("snc16_node_data.tfrecord.b64"))
