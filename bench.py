@@ -70,6 +70,9 @@ def parse_args(argv=None):
     ap.add_argument("--hot-rows", type=float, default=None,
                     help="sharded features: fraction of the table (highest in-degree vertices) replicated on every GPU "
                          "(default: GIGL_HOT_ROWS or 0.125)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="batches in flight per GPU: step i runs on stream i %% S with its own context / workspace, so the host "
+                         "reads and kernel tails of one batch are covered by the other's kernels (1 = strictly one after the other)")
     ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the replicated variant and the g1b record")
     ap.add_argument("--with-g1b", action="store_true", help="run the g1b record at any N (default: N = 8 only)")
     return ap.parse_args(argv)
@@ -350,7 +353,7 @@ class Env:
 class Run:
     """One workload resident on this rank's GPU: graph, features (local / sharded / replicated), model, batch workspace."""
 
-    def __init__(self, env: Env, wl_name: str, features: str, halo: str, batch: int, fan, hot_rows: float, tag: str):
+    def __init__(self, env: Env, wl_name: str, features: str, halo: str, batch: int, fan, hot_rows: float, tag: str, streams: int = 1):
         import torch
 
         from gigl_b200 import Batch, Context, Graph, SageModel, synth
@@ -402,6 +405,23 @@ class Run:
         self.out = torch.empty((self.B, wl["O"]), dtype=torch.float32, device=dev)
         self._batches = {}
         self.nbr = self.cnt = None
+        # pipes: pipe 0 = the objects above; every further pipe has its own stream, context (scratch, sampler index), graph
+        # handle over the SAME resident CSR / feature table, model copy and batch workspace
+        self.pipes = [dict(ctx=self.ctx, g=self.g, model=self.model, batch=self.batch, out=self.out, nbr=None, cnt=None, stream=None)]
+        for _ in range(1, max(1, streams)):
+            st = torch.cuda.Stream(device=dev)
+            c = Context(env.local, stream=st.cuda_stream)
+            rowptr_t, col_t = self.g.csr_tensors()
+            g2 = Graph.wrap_dev(c, rowptr_t, col_t)
+            g2.set_features(x)
+            b2 = Batch(c, wl["nodes"])
+            if self.sharded and self.halo == "staged":
+                b2.set_halo_staging(True)
+                if self.hot_rows and getattr(self.batch, "_hot", None) is not None:
+                    b2.share_hot_rows(self.batch, x.shape[1])
+            self.pipes.append(dict(ctx=c, g=g2, model=SageModel(c, self.layers), batch=b2,
+                                   out=torch.empty((self.B, wl["O"]), dtype=torch.float32, device=dev), nbr=None, cnt=None, stream=st))
+            c.sync()
 
     def roots(self, n_steps):
         key = n_steps
@@ -410,41 +430,61 @@ class Run:
             self._batches[key] = (host, [self.env.torch.from_numpy(b).to(self.env.dev) for b in host])
         return self._batches[key]
 
-    def step(self, roots_dev):
-        if self.nbr is None:
-            self.nbr, self.cnt = self.g.sample_khop(roots_dev, self.fan)
-        self.g.sample_khop(roots_dev, self.fan, out=(self.nbr, self.cnt))
-        self.batch.collate(roots_dev, self.fan, self.nbr, 2)
-        self.batch.sage_forward(self.model, self.x, out=self.out)
-        return self.batch.n_edges
+    def step(self, roots_dev, pipe: int = 0):
+        p = self.pipes[pipe]
+        if p["nbr"] is None:
+            p["nbr"], p["cnt"] = p["g"].sample_khop(roots_dev, self.fan)
+            if pipe == 0:
+                self.nbr, self.cnt = p["nbr"], p["cnt"]
+        p["g"].sample_khop(roots_dev, self.fan, out=(p["nbr"], p["cnt"]))
+        p["batch"].collate(roots_dev, self.fan, p["nbr"], 2)
+        p["batch"].sage_forward(p["model"], self.x, out=p["out"])
+        return p["batch"].n_edges
 
     # ---- device-resident measurement (value) --------------------------------------------------
-    def measure_device(self, K, W):
-        torch, env, ctx = self.env.torch, self.env, self.ctx
+    def measure_device(self, K, W, streams=1):
+        """K timed steps after W warm-up steps, step i on pipe i % streams.  streams = 1 also collects the per-phase device
+        times (with several batches in flight the phases of different batches overlap, so they are taken from this form)."""
+        torch, env = self.env.torch, self.env
+        S = max(1, min(streams, len(self.pipes)))
+        pipes = self.pipes[:S]
         _, roots_dev = self.roots(K + W)
-        for i in range(W):
-            self.step(roots_dev[i])
-        ctx.set_timing(True)
-        ctx.reset_timing()
-        l0 = ctx.launch_count
+        for i in range(max(W, S)):
+            self.step(roots_dev[i % (K + W)], i % S)
+        if S == 1:
+            self.ctx.set_timing(True)
+            self.ctx.reset_timing()
+        l0 = sum(p["ctx"].launch_count for p in pipes)
         clocks = ClockSampler(env.local)
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        main = torch.cuda.current_stream(env.dev)
+        ev0 = torch.cuda.Event(enable_timing=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
         env.barrier()
         clocks.start()
-        evs[0].record()
+        ev0.record(main)
+        for p in pipes[1:]:
+            p["stream"].wait_event(ev0)
         e1_total = 0
         for i in range(W, W + K):
-            e1_total += self.step(roots_dev[i])
-            evs[i - W + 1].record()
+            k = (i - W) % S
+            e1_total += self.step(roots_dev[i], k)
+            evs[i - W].record(pipes[k]["stream"] or main)
+        for p in pipes[1:]:
+            main.wait_stream(p["stream"])
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(main)
         env.barrier()
-        ms = evs[0].elapsed_time(evs[K])
-        per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+        ms = ev0.elapsed_time(ev1)
+        done = sorted(ev0.elapsed_time(e) for e in evs)
+        per_step = [done[0]] + [done[i] - done[i - 1] for i in range(1, K)]  # time between consecutive batch completions
         clk = clocks.stop()
-        launches = ctx.launch_count - l0
-        timings = ctx.timings()
-        ctx.set_timing(False)
+        launches = sum(p["ctx"].launch_count for p in pipes) - l0
+        timings = self.ctx.timings() if S == 1 else {}
+        if S == 1:
+            self.ctx.set_timing(False)
         ms = max_over_ranks(ms, env.dev)
-        return {"ms": ms, "per_step": per_step, "clocks": clk, "launches": int(launches), "timings": timings, "e1_total": e1_total}
+        return {"ms": ms, "per_step": per_step, "clocks": clk, "launches": int(launches), "timings": timings, "e1_total": e1_total,
+                "streams": S}
 
     def counts(self, K, W):
         """what a step touches (untimed recount): unique edges, rows per layer, batch nodes, sampled edges, frontier rows"""
@@ -465,59 +505,83 @@ class Run:
         return {k: v / K for k, v in tot.items()}
 
     # ---- end to end through the host entry points ----------------------------------------------
-    def measure_e2e(self, K, W, padded=False, embeddings_only=False):
+    def measure_e2e(self, K, W, padded=False, embeddings_only=False, streams=1):
+        """The same K batches through the blocking host entry points: one caller thread per pipe (the call is synchronous -
+        roots in, results in host memory out - so several batches are in flight only if several callers are)."""
         torch, env = self.env.torch, self.env
+        S = max(1, min(streams, len(self.pipes)))
         host, _ = self.roots(K + W)
         B, O_dim, fan = self.B, self.wl["O"], self.fan
         roots_pin = [torch.from_numpy(b).pin_memory() for b in host]
-        out_pin = torch.empty((B, O_dim), dtype=torch.float32).pin_memory()
         d2h_steps = []
-        if embeddings_only:
-            def host_step(i):
-                self.g.infer_khop_sage_host(self.batch, self.model, roots_pin[i].numpy(), fan, out=out_pin.numpy())
-                d2h_steps.append(B * O_dim * 4)
-            api = "gigl_infer_khop_sage_host(nbr_out = NULL): roots in pinned host memory -> root embeddings back in pinned host memory"
-        else:
-            nbr_pin, cnt_pin, cnt8_pin, width = [], [], [], 1
-            for f in fan:
-                cnt_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
-                cnt8_pin.append(torch.empty(B * width, dtype=torch.uint8).pin_memory())
-                width *= f
-                nbr_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
-            if padded:
-                s_out = ([t.numpy() for t in nbr_pin], [t.numpy() for t in cnt_pin])
-
-                def host_step(i):
-                    self.g.infer_khop_sage_host(self.batch, self.model, roots_pin[i].numpy(), fan, return_samples=True, out=out_pin.numpy(),
-                                                samples_out=s_out)
-                    d2h_steps.append(B * O_dim * 4 + sum(t.numel() * 4 for t in nbr_pin + cnt_pin))
-                api = "gigl_infer_khop_sage_host: roots in pinned host memory -> padded-tree index sets + root embeddings in pinned host memory"
+        steps_of = []
+        for k in range(S):
+            p = self.pipes[k]
+            out_pin = torch.empty((B, O_dim), dtype=torch.float32).pin_memory()
+            if embeddings_only:
+                def host_step(i, p=p, out_pin=out_pin):
+                    p["g"].infer_khop_sage_host(p["batch"], p["model"], roots_pin[i].numpy(), fan, out=out_pin.numpy())
+                    d2h_steps.append(B * O_dim * 4)
+                api = "gigl_infer_khop_sage_host(nbr_out = NULL): roots in pinned host memory -> root embeddings back in pinned host memory"
             else:
-                packed_pin = torch.empty(sum(t.numel() for t in nbr_pin), dtype=torch.int32).pin_memory()
-                p_out = (packed_pin.numpy(), [t.numpy() for t in cnt8_pin])
+                nbr_pin, cnt_pin, cnt8_pin, width = [], [], [], 1
+                for f in fan:
+                    cnt_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
+                    cnt8_pin.append(torch.empty(B * width, dtype=torch.uint8).pin_memory())
+                    width *= f
+                    nbr_pin.append(torch.empty(B * width, dtype=torch.int32).pin_memory())
+                if padded:
+                    s_out = ([t.numpy() for t in nbr_pin], [t.numpy() for t in cnt_pin])
 
-                def host_step(i):
-                    _, packed, _ = self.g.infer_khop_sage_packed_host(self.batch, self.model, roots_pin[i].numpy(), fan, out=out_pin.numpy(),
-                                                                      packed_out=p_out)
-                    d2h_steps.append(B * O_dim * 4 + packed.size * 4 + sum(t.numel() for t in cnt8_pin))
-                api = ("gigl_infer_khop_sage_packed_host: roots in pinned host memory -> packed index sets [one-byte counts + filled "
-                       "slots] + root embeddings in pinned host memory")
-        for i in range(W):
-            host_step(i)
+                    def host_step(i, p=p, out_pin=out_pin, s_out=s_out, n_ints=sum(t.numel() for t in nbr_pin + cnt_pin)):
+                        p["g"].infer_khop_sage_host(p["batch"], p["model"], roots_pin[i].numpy(), fan, return_samples=True,
+                                                    out=out_pin.numpy(), samples_out=s_out)
+                        d2h_steps.append(B * O_dim * 4 + n_ints * 4)
+                    api = "gigl_infer_khop_sage_host: roots in pinned host memory -> padded-tree index sets + root embeddings in pinned host memory"
+                else:
+                    packed_pin = torch.empty(sum(t.numel() for t in nbr_pin), dtype=torch.int32).pin_memory()
+                    p_out = (packed_pin.numpy(), [t.numpy() for t in cnt8_pin])
+
+                    def host_step(i, p=p, out_pin=out_pin, p_out=p_out, n_cnt=sum(t.numel() for t in cnt8_pin)):
+                        _, packed, _ = p["g"].infer_khop_sage_packed_host(p["batch"], p["model"], roots_pin[i].numpy(), fan,
+                                                                          out=out_pin.numpy(), packed_out=p_out)
+                        d2h_steps.append(B * O_dim * 4 + packed.size * 4 + n_cnt)
+                    api = ("gigl_infer_khop_sage_packed_host: roots in pinned host memory -> packed index sets [one-byte counts + filled "
+                           "slots] + root embeddings in pinned host memory")
+            steps_of.append(host_step)
+        for i in range(max(W, S)):
+            steps_of[i % S](i % (K + W))
         d2h_steps.clear()
+
+        def caller(k):
+            for i in range(W + k, W + K, S):
+                steps_of[k](i)
+
+        main = torch.cuda.current_stream(env.dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         env.barrier()
-        ev0.record()
+        ev0.record(main)
+        for p in self.pipes[1:S]:
+            p["stream"].wait_event(ev0)
         t0 = time.perf_counter()
-        for i in range(W, W + K):
-            host_step(i)
-        ev1.record()
+        if S == 1:
+            caller(0)
+        else:
+            ths = [threading.Thread(target=caller, args=(k,)) for k in range(S)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        for p in self.pipes[1:S]:
+            main.wait_stream(p["stream"])
+        ev1.record(main)
         env.barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        ms_e = max_over_ranks(ev0.elapsed_time(ev1), env.dev)  # device time on the launching stream (the host call is synchronous)
+        ms_e = max_over_ranks(ev0.elapsed_time(ev1), env.dev)  # device time from the first call's start to the last result's arrival
         d2h = int(sum(d2h_steps) / max(len(d2h_steps), 1))
         return {"value": env.world * B * K / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e / K, "host_wall_ms_per_step": wall_ms / K, "host_cpus_bound": env.numa_cpus, "api": api}
+                "ms_per_step": ms_e / K, "host_wall_ms_per_step": wall_ms / K, "host_cpus_bound": env.numa_cpus, "api": api,
+                "callers": S}
 
     def full_graph(self):
         """the aggregate over the WHOLE graph (every node a row, every CSR edge reduced once): the form the Trainer's nn
@@ -574,6 +638,13 @@ class Run:
         self.ctx.sync()
         if self.env.world > 1:
             self.env.dist.barrier()
+        for p in self.pipes[1:]:
+            p["ctx"].sync()
+            p["batch"].close()
+            p["model"].close()
+            p["g"].close()
+            p["ctx"].close()
+        self.pipes = []
         self.batch.close()
         self.model.close()
         self.g.close()
@@ -645,17 +716,18 @@ def roofline_blocks(run: Run, dev_res, cnt, K):
 def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_full, tag):
     fan = [int(v) for v in args.fanout.split(",")]
     hot = args.hot_rows if args.hot_rows is not None else float(os.environ.get("GIGL_HOT_ROWS", "0.125"))
-    run = Run(env, wl_name, features, args.halo, args.batch, fan, hot, tag)
+    run = Run(env, wl_name, features, args.halo, args.batch, fan, hot, tag, streams=args.streams)
     wl, B, world = run.wl, run.B, env.world
-    dev_res = run.measure_device(K, W)
+    one = run.measure_device(K, W, streams=1)  # one batch at a time: the per-phase device times (rooflines) come from this form
+    dev_res = run.measure_device(K, W, streams=args.streams) if args.streams > 1 else one
     ms = dev_res["ms"]
     value = world * B * K / (ms * 1e-3)
     cnt = run.counts(min(K, 8), W)
     agg_edges = (cnt["e1"] + cnt["e2"])
-    blocks = roofline_blocks(run, dev_res, cnt, K)
+    blocks = roofline_blocks(run, one, cnt, K)
     timed = [b for b in blocks if b.get("ms_per_launch") and not b["kernel"].startswith("layer-1 gather-SpMM as a whole")]
     head = max(timed, key=lambda b: b["ms_per_launch"]) if timed else None
-    phase_ms = {k: v[0] / K for k, v in dev_res["timings"].items()}
+    phase_ms = {k: v[0] / K for k, v in one["timings"].items()}
     rec = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
            "ms_per_step_min": float(np.min(dev_res["per_step"])), "ms_per_step_median": float(np.median(dev_res["per_step"])),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -666,6 +738,9 @@ def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_fu
            "sample_only_subgraphs_per_sec": B / max(1e-9, phase_ms.get("sample", 0.0) * 1e-3),
            "phase_ms_per_step": phase_ms, "unique_edges_per_step": cnt["e1"], "layer1_rows_per_step": cnt["n1"],
            "batch_nodes_per_step": cnt["nodes"], "sampled_edges_per_step": cnt["sampled"],
+           "batches_in_flight": dev_res["streams"],
+           "one_batch_at_a_time": {"ms_per_step": one["ms"] / K, "value": world * B * K / (one["ms"] * 1e-3),
+                                   "ms_per_step_median": float(np.median(one["per_step"]))},
            "roofline": head, "rooflines": blocks, "gpu_launches": dev_res["launches"], "clocks": dev_res["clocks"]}
     if run.sharded and phase_ms.get("halo_stage"):
         F = wl["F"]
@@ -679,8 +754,8 @@ def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_fu
     if want_full and not run.sharded:
         rec["full_graph_aggregate"] = run.full_graph()
     if want_e2e:
-        rec["e2e"] = run.measure_e2e(K, W, padded=args.e2e_padded)
-        rec["e2e_embeddings_only"] = run.measure_e2e(K, W, embeddings_only=True)
+        rec["e2e"] = run.measure_e2e(K, W, padded=args.e2e_padded, streams=args.streams)
+        rec["e2e_embeddings_only"] = run.measure_e2e(K, W, embeddings_only=True, streams=args.streams)
     if want_cpu:
         if env.rank == 0:
             rec["cpu_baseline"] = run.cpu_baseline(args.cpu_steps)

@@ -136,7 +136,7 @@ __global__ void seg_clear_kernel(int64_t n_keys, const uint64_t* __restrict__ ke
 // Counters in d_ctr: [0] listed rows, [1] unique edges, [2] node counter, [3] valid keys, [4 + j] level ends, [16] long
 // items, [17] / [18] work-queue cursors of the sort launch.
 constexpr int kCtrRows = 0, kCtrUnique = 1, kCtrNodes = 2, kCtrValid = 3, kCtrLong = 16;
-constexpr int kWarpSortMax = 1024;  // rows up to this many entries are sorted in one warp's registers
+constexpr int kWarpSortMax = 512;   // rows up to this many entries are sorted in one warp's registers
 constexpr int kLongCap = 4096;      // shared-memory sort capacity of a long-row CTA
 constexpr int kLongPart = 1024;     // expected entries per value-range partition of a row longer than kLongCap
 constexpr int kLongThreads = 512;
@@ -424,11 +424,13 @@ __device__ __forceinline__ void sort_long_item(const int4 it, const int2* __rest
 
 constexpr int kCtrLongNext = 17, kCtrTileNext = 18;
 
+constexpr int kSubTile = 8;  // rows sorted side by side per pass of a tile (registers per lane)
+
 __global__ void __launch_bounds__(kLongThreads, 2) rows_sort_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ segmap,
                                                                     int32_t* __restrict__ ctr, const int4* __restrict__ long_items,
                                                                     int long_cap, const uint32_t* __restrict__ srcs,
                                                                     uint64_t* __restrict__ keys, int shift) {
-    __shared__ uint32_t s_buf[kLongCap];
+    __shared__ uint32_t s_buf[kLongCap];  // a long item's range
     __shared__ uint2 s_stack[64];
     __shared__ int s_sp, s_cnt, s_below, s_item;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -460,35 +462,40 @@ __global__ void __launch_bounds__(kLongThreads, 2) rows_sort_kernel(const int32_
             seg = segmap[v];
         }
         const int c = seg.y - seg.x;
-        uint32_t e[32];
+        // rows of <= 32 sources: kSubTile rows side by side, one register each; the 15 stages of one bitonic network sort
+        // them all (a shuffle and a min / max per register and stage, the kSubTile chains independent)
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += kSubTile) {
+            uint32_t e[kSubTile];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const int cr = __shfl_sync(0xffffffffu, c, r), br = __shfl_sync(0xffffffffu, seg.x, r);
-            e[r] = (cr <= 32 && lane < cr) ? srcs[br + lane] : 0xFFFFFFFFu;
-        }
+            for (int r = 0; r < kSubTile; ++r) {
+                const int cr = __shfl_sync(0xffffffffu, c, r0 + r), br = __shfl_sync(0xffffffffu, seg.x, r0 + r);
+                e[r] = (cr <= 32 && lane < cr) ? srcs[br + lane] : 0xFFFFFFFFu;
+            }
 #pragma unroll
-        for (int k = 2; k <= 32; k <<= 1) {
+            for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const uint32_t o = __shfl_xor_sync(0xffffffffu, e[r], j);
-                    e[r] = take_min ? min(e[r], o) : max(e[r], o);
+                    for (int r = 0; r < kSubTile; ++r) {
+                        const uint32_t o = __shfl_xor_sync(0xffffffffu, e[r], j);
+                        e[r] = take_min ? min(e[r], o) : max(e[r], o);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kSubTile; ++r) {
+                const int cr = __shfl_sync(0xffffffffu, c, r0 + r), br = __shfl_sync(0xffffffffu, seg.x, r0 + r);
+                const int32_t vr = __shfl_sync(0xffffffffu, v, r0 + r);
+                const uint32_t prev = __shfl_up_sync(0xffffffffu, e[r], 1);
+                if (cr <= 32 && lane < cr) {
+                    keys[br + lane] = ((uint64_t)(uint32_t)vr << shift) | e[r];
+                    uniq += (lane == 0) || (prev != e[r]);
                 }
             }
         }
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            const int cr = __shfl_sync(0xffffffffu, c, r), br = __shfl_sync(0xffffffffu, seg.x, r);
-            const int32_t vr = __shfl_sync(0xffffffffu, v, r);
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, e[r], 1);
-            if (cr <= 32 && lane < cr) {
-                keys[br + lane] = ((uint64_t)(uint32_t)vr << shift) | e[r];
-                uniq += (lane == 0) || (prev != e[r]);
-            }
-        }
-        // the tile's rows of 33 .. kWarpSortMax entries, one at a time
+        // the tile's rows of 33 .. kWarpSortMax sources, one at a time in 2 .. 16 registers per lane
         uint32_t mid = __ballot_sync(0xffffffffu, c > 32 && c <= kWarpSortMax);
         while (mid) {
             const int r = __ffs(mid) - 1;
@@ -501,10 +508,8 @@ __global__ void __launch_bounds__(kLongThreads, 2) rows_sort_kernel(const int32_
                 uniq += sort_row_warp<4>(srcs + br, keys + br, cr, hi_bits, lane);
             else if (cr <= 256)
                 uniq += sort_row_warp<8>(srcs + br, keys + br, cr, hi_bits, lane);
-            else if (cr <= 512)
-                uniq += sort_row_warp<16>(srcs + br, keys + br, cr, hi_bits, lane);
             else
-                uniq += sort_row_warp<32>(srcs + br, keys + br, cr, hi_bits, lane);
+                uniq += sort_row_warp<16>(srcs + br, keys + br, cr, hi_bits, lane);
         }
     }
 #pragma unroll
@@ -682,6 +687,27 @@ __device__ __forceinline__ void reduce_groups(float4& acc) {
     }
 }
 
+// Accumulate form of the gather's output (project-first layers, see batch_sage_forward): instead of writing
+// [mean | self] rows for a projection, the mean of the gathered rows is ADDED to out[row, 0 .. n_cols) (+ ReLU).
+struct AccOut {
+    float* out;  // nullptr = the [mean | self] form
+    int64_t ldo;
+    int32_t n_cols;
+    int32_t relu;
+};
+
+__device__ __forceinline__ void acc_row4(const AccOut& ao, int64_t row, int c, float4 m) {
+    const float v[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (c + j < ao.n_cols) {
+            float* o = ao.out + row * ao.ldo + c + j;
+            const float t = *o + v[j];
+            *o = ao.relu ? fmaxf(t, 0.f) : t;
+        }
+    }
+}
+
 // Work lists of the split path: hctr[0] = parts claimed, hctr[1] = heavy rows claimed.
 struct HeavyLists {
     int32_t* hctr;
@@ -732,7 +758,8 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
                                                            const uint64_t* __restrict__ keys, uint64_t src_mask,
                                                            const float* __restrict__ xsrc, int64_t ldx,
                                                            const int32_t* __restrict__ lid, float* __restrict__ A_hi,
-                                                           float* __restrict__ A_lo, int64_t ldA, const HeavyLists hl) {
+                                                           float* __restrict__ A_lo, int64_t ldA, const HeavyLists hl,
+                                                           const AccOut ao) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, g = lane / LPR;
     int64_t n_rows = *n_rows_dev;
@@ -787,7 +814,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
                 const int c = c0 + sub * 4;
                 const bool active = c < F;
                 float4 selfv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g == 0 && active) selfv = ldg4(xsrc + self * ldx + c);
+                if (g == 0 && active && ao.out == nullptr) selfv = ldg4(xsrc + self * ldx + c);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 int n_uniq = __popc(__ballot_sync(0xffffffffu, myA >= 0));
                 gather_chunk<LPR>(myA, cnt0, c, active, xsrc, ldx, g, acc);
@@ -796,8 +823,13 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
                 reduce_groups<LPR>(acc);
                 if (g == 0 && active) {
                     const float scale = 1.0f / (float)(n_uniq > 1 ? n_uniq : 1);
-                    store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
-                    store_split4(A_hi, A_lo, row * ldA + F + c, selfv);
+                    const float4 mean = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+                    if (ao.out != nullptr) {
+                        acc_row4(ao, row, c, mean);
+                    } else {
+                        store_split4(A_hi, A_lo, row * ldA + c, mean);
+                        store_split4(A_hi, A_lo, row * ldA + F + c, selfv);
+                    }
                 }
             }
         }
@@ -1031,7 +1063,7 @@ __global__ void __launch_bounds__(kFinishWarps * 32) batch_gather_finish_kernel(
                                                                               const int32_t* __restrict__ list,
                                                                               const int32_t* __restrict__ lid,
                                                                               float* __restrict__ A_hi, float* __restrict__ A_lo,
-                                                                              int64_t ldA, const HeavyLists hl) {
+                                                                              int64_t ldA, const HeavyLists hl, const AccOut ao) {
     __shared__ float4 s_acc[kFinishWarps][32];
     __shared__ int s_cnt[kFinishWarps];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1072,8 +1104,13 @@ __global__ void __launch_bounds__(kFinishWarps * 32) batch_gather_finish_kernel(
                     acc.z += t.z;
                     acc.w += t.w;
                 }
-                store_split4(A_hi, A_lo, row * ldA + c, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
-                store_split4(A_hi, A_lo, row * ldA + F + c, ldg4(xsrc + self * ldx + c));
+                const float4 mean = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+                if (ao.out != nullptr) {
+                    acc_row4(ao, row, c, mean);
+                } else {
+                    store_split4(A_hi, A_lo, row * ldA + c, mean);
+                    store_split4(A_hi, A_lo, row * ldA + F + c, ldg4(xsrc + self * ldx + c));
+                }
             }
             __syncthreads();
         }
@@ -1089,7 +1126,7 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
                                                                   const float* __restrict__ xsrc, int64_t ldx,
                                                                   const int32_t* __restrict__ lid,
                                                                   float* __restrict__ A_hi, float* __restrict__ A_lo,
-                                                                  int64_t ldA) {
+                                                                  int64_t ldA, const AccOut ao) {
     const int lane = threadIdx.x & 31;
     int64_t n_rows = *n_rows_dev;
     if (n_rows > row_cap) n_rows = row_cap;
@@ -1110,6 +1147,14 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
                 ++n_uniq;
             }
             const float m = acc * (1.0f / (float)(n_uniq > 1 ? n_uniq : 1));
+            if (ao.out != nullptr) {
+                if (c < ao.n_cols) {
+                    float* o = ao.out + row * ao.ldo + c;
+                    const float t = *o + m;
+                    *o = ao.relu ? fmaxf(t, 0.f) : t;
+                }
+                continue;
+            }
             const float sv = __ldg(xsrc + self * ldx + c);
             if (A_lo == nullptr) {
                 A_hi[row * ldA + c] = m;
@@ -1129,10 +1174,14 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
 // for every local id l, local or over NVLink, after which the gather runs on local memory through `lid`.  One warp per
 // row, U rows per warp in flight (a remote row is a ~2 us round trip; 148 SMs x 64 warps x 4 rows x 400 B ~ 15 MB
 // in flight).
+// Hot rows: the rows of the vertices a batch meets most often (highest degree) are replicated on every GPU
+// (gigl_batch_set_hot_rows_dev); hot_slot[v] >= 0 names v's row in that local copy, and only the cold tail crosses NVLink.
 template <int CPL>
 __global__ void __launch_bounds__(256) halo_stage_kernel(const int32_t* __restrict__ n_nodes_dev, int64_t row_cap, int F,
                                                          const int32_t* __restrict__ list, const float* __restrict__ x,
-                                                         int64_t ldx, float* __restrict__ xb, int64_t ldb) {
+                                                         int64_t ldx, float* __restrict__ xb, int64_t ldb,
+                                                         const int32_t* __restrict__ hot_slot, const float* __restrict__ hot,
+                                                         int64_t ldh) {
     constexpr int U = 4;
     const int lane = threadIdx.x & 31;
     int64_t n = *n_nodes_dev;
@@ -1140,16 +1189,25 @@ __global__ void __launch_bounds__(256) halo_stage_kernel(const int32_t* __restri
     const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * U; r0 < n; r0 += W * U) {
         int32_t v[U];
+        const float* src[U];
         float4 val[U][CPL];
 #pragma unroll
         for (int u = 0; u < U; ++u) v[u] = (r0 + u < n) ? __ldg(list + r0 + u) : -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            src[u] = x + (int64_t)(v[u] >= 0 ? v[u] : 0) * ldx;
+            if (hot_slot != nullptr && v[u] >= 0) {
+                const int32_t hs = __ldg(hot_slot + v[u]);
+                if (hs >= 0) src[u] = hot + (int64_t)hs * ldh;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
                 const int c = (q * 32 + lane) * 4;
                 val[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v[u] >= 0 && c < F) val[u][q] = ldg4(x + (int64_t)v[u] * ldx + c);
+                if (v[u] >= 0 && c < F) val[u][q] = ldg4(src[u] + c);
             }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -1163,14 +1221,21 @@ __global__ void __launch_bounds__(256) halo_stage_kernel(const int32_t* __restri
 
 __global__ void __launch_bounds__(256) halo_stage_scalar_kernel(const int32_t* __restrict__ n_nodes_dev, int64_t row_cap, int F,
                                                                 const int32_t* __restrict__ list, const float* __restrict__ x,
-                                                                int64_t ldx, float* __restrict__ xb, int64_t ldb) {
+                                                                int64_t ldx, float* __restrict__ xb, int64_t ldb,
+                                                                const int32_t* __restrict__ hot_slot, const float* __restrict__ hot,
+                                                                int64_t ldh) {
     int64_t n = *n_nodes_dev;
     if (n > row_cap) n = row_cap;
     const int lane = threadIdx.x & 31;
     const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += W) {
         const int32_t v = __ldg(list + r);
-        for (int c = lane; c < F; c += 32) xb[r * ldb + c] = __ldg(x + (int64_t)v * ldx + c);
+        const float* src = x + (int64_t)v * ldx;
+        if (hot_slot != nullptr) {
+            const int32_t hs = __ldg(hot_slot + v);
+            if (hs >= 0) src = hot + (int64_t)hs * ldh;
+        }
+        for (int c = lane; c < F; c += 32) xb[r * ldb + c] = __ldg(src + c);
     }
 }
 
@@ -1203,6 +1268,10 @@ struct gigl_batch {
     int64_t level_end_host[GIGL_MAX_HOPS + 2] = {};
     int64_t n_valid_host = 0, n_unique_host = 0;
     bool halo_staging = false;  // layer 1 reads a per-batch copy of the unique nodes' rows (batch_set_halo_staging)
+    const int32_t* hot_slot = nullptr;  // halo staging: dense [n_graph_nodes] map vertex -> row of the replicated hot table, -1 = cold
+    const float* hot = nullptr;
+    int64_t ldh = 0;
+    int32_t hot_F = 0;
     int32_t* rows = nullptr;    // bucketed collation: the batch's distinct destination vertices (inside `buf`)
     bool bucketed = false;      // the current batch was collated by the bucketed path
 };
@@ -1465,8 +1534,29 @@ struct gigl_sage_model {
     float* w_hi[GIGL_MAX_HOPS] = {};      // TF32 split of wcat (3xTF32 projection, gemm_tcgen05.cu)
     float* w_lo[GIGL_MAX_HOPS] = {};
     float* bias[GIGL_MAX_HOPS] = {};      // lin_l.bias or nullptr
+    // project-first form of a layer l >= 1 whose output is much narrower than its input (4 * Fo <= Fi): lin_l and lin_r as
+    // separate operands [o4 | Fo, ldk], so the layer runs as  Z = h @ Wl^T  over the previous level's rows, out = h[rows] @
+    // Wr^T + b, out += mean_j Z[j]  - the gather then moves Fo floats per edge instead of Fi (see batch_sage_forward)
+    bool pf[GIGL_MAX_HOPS] = {};
+    int o4[GIGL_MAX_HOPS] = {};
+    int64_t ldk[GIGL_MAX_HOPS] = {};
+    float* pl_hi[GIGL_MAX_HOPS] = {};
+    float* pl_lo[GIGL_MAX_HOPS] = {};
+    float* pr_hi[GIGL_MAX_HOPS] = {};
+    float* pr_lo[GIGL_MAX_HOPS] = {};
     float* blob = nullptr;
 };
+
+static bool layer_projects_first(int l, int Fi, int Fo) {
+    // Off unless GIGL_PROJECT_FIRST=1.  Measured on the bench step (products-like, 256 -> 47 last layer): the gather
+    // drops from 0.26 to 0.15 ms but the two skinny projections (N = 48) cost 0.19 ms against 0.07 - a wash
+    // (profiles/r2g_*), the M = 128 x N = 48 tcgen05 tiles are bound by the per-stage hand-off, not by flops.
+    static const bool enabled = [] {
+        const char* e = getenv("GIGL_PROJECT_FIRST");
+        return e && e[0] == '1';
+    }();
+    return enabled && l >= 1 && 4 * Fo <= Fi && Fi % 4 == 0 && ((Fo + 3) & ~3) <= 64;
+}
 
 int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, const float* const* Wl, const float* const* bl,
                       const float* const* Wr, int weights_on_device, gigl_sage_model** out) {
@@ -1476,6 +1566,8 @@ int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
         GIGL_CHECK(ctx, dims[l] >= 1 && dims[l + 1] >= 1 && Wl[l] && Wr[l], "bad layer");
         const size_t ld = ((size_t)2 * dims[l] + 3) & ~(size_t)3;
         total += 3 * (size_t)dims[l + 1] * ld + (((size_t)dims[l + 1] + 3) & ~(size_t)3);
+        if (layer_projects_first(l, dims[l], dims[l + 1]))
+            total += 3 * (size_t)(2 * ((dims[l + 1] + 3) & ~3)) * (size_t)((dims[l] + 3) & ~3);
     }
     gigl_sage_model* m = new (std::nothrow) gigl_sage_model();
     if (!m) return gigl_fail(ctx, GIGL_E_NOMEM, "out of host memory");
@@ -1503,6 +1595,25 @@ int sage_model_create(gigl_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
             if (e == cudaSuccess) e = cudaMemcpyAsync(m->bias[l], bl[l], sizeof(float) * Fo, kind, ctx->stream);
         }
         off += ((size_t)Fo + 3) & ~(size_t)3;
+        if (layer_projects_first(l, Fi, Fo)) {
+            const int o4 = (Fo + 3) & ~3;
+            const size_t ldk = ((size_t)Fi + 3) & ~(size_t)3, blk = (size_t)o4 * ldk;
+            float* raw_l = m->blob + off;            // [o4, ldk] lin_l.weight, rows Fo .. o4 zero
+            float* raw_r = raw_l + blk;              // [o4, ldk] lin_r.weight
+            m->pl_hi[l] = raw_r + blk;
+            m->pl_lo[l] = m->pl_hi[l] + blk;
+            m->pr_hi[l] = m->pl_lo[l] + blk;
+            m->pr_lo[l] = m->pr_hi[l] + blk;
+            off += 6 * blk;
+            m->pf[l] = true;
+            m->o4[l] = o4;
+            m->ldk[l] = (int64_t)ldk;
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync(raw_l, sizeof(float) * ldk, Wl[l], sizeof(float) * Fi, sizeof(float) * Fi, Fo, kind, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync(raw_r, sizeof(float) * ldk, Wr[l], sizeof(float) * Fi, sizeof(float) * Fi, Fo, kind, ctx->stream);
+            if (e == cudaSuccess && (split_tf32_launch(ctx, o4, (int)ldk, raw_l, (int64_t)ldk, m->pl_hi[l], m->pl_lo[l], (int64_t)ldk) != GIGL_OK ||
+                                     split_tf32_launch(ctx, o4, (int)ldk, raw_r, (int64_t)ldk, m->pr_hi[l], m->pr_lo[l], (int64_t)ldk) != GIGL_OK))
+                e = cudaErrorUnknown;
+        }
     }
     for (int l = 0; l < n_layers && e == cudaSuccess; ++l)
         if (split_tf32_launch(ctx, dims[l + 1], (int)m->ldw[l], m->wcat[l], m->ldw[l], m->w_hi[l], m->w_lo[l], m->ldw[l]) != GIGL_OK)
@@ -1529,6 +1640,85 @@ int sage_model_dims(const gigl_sage_model* m, int32_t* n_layers, int32_t* dims) 
     if (n_layers) *n_layers = m->n_layers;
     if (dims)
         for (int l = 0; l <= m->n_layers; ++l) dims[l] = m->dims[l];
+    return GIGL_OK;
+}
+
+// The gather over the first `rows` local ids of the collated batch: [mean | self] rows of width 2 F into A (a projection
+// follows), or - ao.out set - the mean ADDED to ao.out (project-first layers).  xsrc rows are indexed by global vertex id
+// (lidmap == nullptr: layer 1 on the graph-wide feature table) or through the local-id map.
+static int batch_gather_launch(gigl_batch* b, const int32_t* rows_dev, int64_t rows, int F, const float* xsrc, int64_t ldx,
+                               const int32_t* lidmap, float* A_hi, float* A_lo, int64_t lda, const gigl::AccOut ao) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    const int wpb = 8;
+    const int64_t gfull = ceil_div64(rows, wpb), gcap = (int64_t)ctx->sm_count * 3;  // 80 registers -> 3 CTAs per SM
+    const unsigned grid = (unsigned)(gfull < gcap ? gfull : gcap);  // persistent warps (grid-stride over rows)
+    if (grid == 0) return GIGL_OK;
+    const bool vec = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(xsrc) & 15) == 0) && (ldx % 4 == 0);
+    if (!vec) {
+        batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, F, b->list, b->segmap, b->keys, b->src_mask, xsrc, ldx, lidmap, A_hi,
+                                                             A_lo, lda, ao);
+        GIGL_LAUNCHED(ctx);
+        return GIGL_OK;
+    }
+    // split-row work lists (sized from the collate's valid-key count; see kSplitThreshold)
+    const int part_edges = F > 128 ? kPartEdges / 2 : kPartEdges;
+    const int64_t part_cap = b->n_valid_host / part_edges + b->n_valid_host / kSplitThreshold + 16;
+    const size_t o_items = 256;
+    const size_t o_rows = o_items + ((sizeof(int2) * (size_t)part_cap + 255) & ~(size_t)255);
+    const size_t o_pcnt = o_rows + ((sizeof(int4) * (size_t)part_cap + 255) & ~(size_t)255);
+    const size_t o_part = o_pcnt + ((sizeof(int32_t) * (size_t)part_cap + 255) & ~(size_t)255);
+    const size_t hbytes = o_part + sizeof(float) * (size_t)part_cap * F;
+    void* ph = nullptr;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_WORK, hbytes, &ph)) != GIGL_OK) return rc;
+    HeavyLists hl;
+    hl.hctr = (int32_t*)ph;
+    hl.items = (int2*)((char*)ph + o_items);
+    hl.rows = (int4*)((char*)ph + o_rows);
+    hl.pcnt = (int32_t*)((char*)ph + o_pcnt);
+    hl.partial = (float*)((char*)ph + o_part);
+    hl.part_cap = (int32_t)part_cap;
+    hl.part_edges = part_edges;
+    GIGL_CUDA(ctx, cudaMemsetAsync(hl.hctr, 0, 2 * sizeof(int32_t), st));
+    const int hgrid = ctx->sm_count * 4;
+#define GIGL_GATHER(LPR)                                                                                                  \
+    do {                                                                                                                  \
+        batch_gather_kernel<LPR><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, F, b->list, b->segmap, b->keys, b->src_mask,  \
+                                                            xsrc, ldx, lidmap, A_hi, A_lo, lda, hl, ao);                  \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+        batch_gather_parts_kernel<LPR><<<hgrid, 256, 0, st>>>(F, b->list, b->segmap, b->keys, b->src_mask, xsrc, ldx, lidmap, hl); \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+    } while (0)
+#define GIGL_GATHER_ASYNC(CPL, SB)                                                                                        \
+    do {                                                                                                                  \
+        const size_t shm = (size_t)wpb * 2 * SB * CPL * 32 * sizeof(float4);                                              \
+        GIGL_CUDA(ctx, cudaFuncSetAttribute(batch_gather_async_kernel<CPL, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
+        batch_gather_async_kernel<CPL, SB><<<grid, wpb * 32, shm, st>>>(rows_dev, rows, F, b->list, b->segmap, b->keys,   \
+                                                                        b->src_mask, xsrc, ldx, lidmap, A_hi, A_lo, lda, hl); \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+        batch_gather_parts_kernel<32><<<hgrid, 256, 0, st>>>(F, b->list, b->segmap, b->keys, b->src_mask, xsrc, ldx, lidmap, hl); \
+        GIGL_LAUNCHED(ctx);                                                                                               \
+    } while (0)
+    if (F <= 16)
+        GIGL_GATHER(4);
+    else if (F <= 32)
+        GIGL_GATHER(8);
+    else if (F <= 64 || ao.out != nullptr)  // the accumulate form exists in the register-staged kernels only
+        GIGL_GATHER(16);
+    else if (F <= 128)
+        GIGL_GATHER_ASYNC(1, 8);
+    else if (F <= 256)
+        GIGL_GATHER_ASYNC(2, 4);
+    else if (F <= 512)
+        GIGL_GATHER_ASYNC(4, 2);
+    else
+        GIGL_GATHER(32);
+#undef GIGL_GATHER
+#undef GIGL_GATHER_ASYNC
+    batch_gather_finish_kernel<<<hgrid, 256, 0, st>>>(F, xsrc, ldx, b->list, lidmap, A_hi, A_lo, lda, hl, ao);
+    GIGL_LAUNCHED(ctx);
     return GIGL_OK;
 }
 
@@ -1571,15 +1761,17 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         const int32_t* n_dev = b->d_ctr + kLevelBase + b->n_levels_done;
         const unsigned sgrid = (unsigned)(ctx->sm_count * 8);
         int th = gigl_timer_begin(ctx, GIGL_T_HALO_STAGE);
-        const bool vec = (F0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) && (ldx0 % 4 == 0);
+        const int32_t* hs = (b->hot_slot && b->hot_F == F0) ? b->hot_slot : nullptr;
+        const bool vec = (F0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) && (ldx0 % 4 == 0) &&
+                         (!hs || (((reinterpret_cast<uintptr_t>(b->hot) & 15) == 0) && b->ldh % 4 == 0));
         if (vec && F0 <= 128)
-            halo_stage_kernel<1><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+            halo_stage_kernel<1><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
         else if (vec && F0 <= 256)
-            halo_stage_kernel<2><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+            halo_stage_kernel<2><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
         else if (vec && F0 <= 512)
-            halo_stage_kernel<4><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+            halo_stage_kernel<4><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
         else
-            halo_stage_scalar_kernel<<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb);
+            halo_stage_scalar_kernel<<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
         GIGL_LAUNCHED(ctx);
         gigl_timer_end(ctx, th);
         xin = xb;
@@ -1592,74 +1784,35 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         const int32_t* rows_dev = b->d_ctr + kLevelBase + (n_layers - l + 1);
         const int64_t lda = m->ldw[l - 1];
         const int32_t* lidmap = (l == 1 && !staged) ? nullptr : b->lid;
-        const int wpb = 8;
-        const int64_t gfull = ceil_div64(rows, wpb), gcap = (int64_t)ctx->sm_count * 3;  // 80 registers -> 3 CTAs per SM
-        const unsigned grid = (unsigned)(gfull < gcap ? gfull : gcap);  // persistent warps (grid-stride over rows)
-        int tg = gigl_timer_begin(ctx, l == 1 ? GIGL_T_GATHER_L1 : GIGL_T_GATHER_DEEP);
-        const bool vec = (Fi % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0) && (ldx % 4 == 0);
-        if (!vec) {
-            batch_gather_scalar_kernel<<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, b->src_mask, xin, ldx, lidmap, A_hi, A_lo, lda);
-            GIGL_LAUNCHED(ctx);
-        } else {
-            // split-row work lists (sized from the collate's valid-key count; see kSplitThreshold)
-            const int part_edges = Fi > 128 ? kPartEdges / 2 : kPartEdges;
-            const int64_t part_cap = b->n_valid_host / part_edges + b->n_valid_host / kSplitThreshold + 16;
-            const size_t o_items = 256;
-            const size_t o_rows = o_items + ((sizeof(int2) * (size_t)part_cap + 255) & ~(size_t)255);
-            const size_t o_pcnt = o_rows + ((sizeof(int4) * (size_t)part_cap + 255) & ~(size_t)255);
-            const size_t o_part = o_pcnt + ((sizeof(int32_t) * (size_t)part_cap + 255) & ~(size_t)255);
-            const size_t hbytes = o_part + sizeof(float) * (size_t)part_cap * Fi;
-            void* ph = nullptr;
-            if ((rc = gigl_scratch(ctx, GIGL_SLOT_WORK, hbytes, &ph)) != GIGL_OK) return rc;
-            HeavyLists hl;
-            hl.hctr = (int32_t*)ph;
-            hl.items = (int2*)((char*)ph + o_items);
-            hl.rows = (int4*)((char*)ph + o_rows);
-            hl.pcnt = (int32_t*)((char*)ph + o_pcnt);
-            hl.partial = (float*)((char*)ph + o_part);
-            hl.part_cap = (int32_t)part_cap;
-            hl.part_edges = part_edges;
-            GIGL_CUDA(ctx, cudaMemsetAsync(hl.hctr, 0, 2 * sizeof(int32_t), st));
-            const int hgrid = ctx->sm_count * 4;
-#define GIGL_GATHER(LPR)                                                                                                  \
-    do {                                                                                                                  \
-        batch_gather_kernel<LPR><<<grid, wpb * 32, 0, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys, b->src_mask, \
-                                                            xin, ldx, lidmap, A_hi, A_lo, lda, hl);                       \
-        GIGL_LAUNCHED(ctx);                                                                                               \
-        batch_gather_parts_kernel<LPR><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, b->src_mask, xin, ldx, lidmap, hl);     \
-        GIGL_LAUNCHED(ctx);                                                                                               \
-    } while (0)
-#define GIGL_GATHER_ASYNC(CPL, SB)                                                                                        \
-    do {                                                                                                                  \
-        const size_t shm = (size_t)wpb * 2 * SB * CPL * 32 * sizeof(float4);                                              \
-        GIGL_CUDA(ctx, cudaFuncSetAttribute(batch_gather_async_kernel<CPL, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); \
-        batch_gather_async_kernel<CPL, SB><<<grid, wpb * 32, shm, st>>>(rows_dev, rows, Fi, b->list, b->segmap, b->keys,  \
-                                                                        b->src_mask, xin, ldx, lidmap, A_hi, A_lo, lda, hl); \
-        GIGL_LAUNCHED(ctx);                                                                                               \
-        batch_gather_parts_kernel<32><<<hgrid, 256, 0, st>>>(Fi, b->list, b->segmap, b->keys, b->src_mask, xin, ldx, lidmap, hl); \
-        GIGL_LAUNCHED(ctx);                                                                                               \
-    } while (0)
-            if (Fi <= 16)
-                GIGL_GATHER(4);
-            else if (Fi <= 32)
-                GIGL_GATHER(8);
-            else if (Fi <= 64)
-                GIGL_GATHER(16);
-            else if (Fi <= 128)
-                GIGL_GATHER_ASYNC(1, 8);
-            else if (Fi <= 256)
-                GIGL_GATHER_ASYNC(2, 4);
-            else if (Fi <= 512)
-                GIGL_GATHER_ASYNC(4, 2);
-            else
-                GIGL_GATHER(32);
-#undef GIGL_GATHER
-#undef GIGL_GATHER_ASYNC
-            batch_gather_finish_kernel<<<hgrid, 256, 0, st>>>(Fi, xin, ldx, b->list, lidmap, A_hi, A_lo, lda, hl);
-            GIGL_LAUNCHED(ctx);
-        }
-        gigl_timer_end(ctx, tg);
         float* C = (l == n_layers) ? out_dev : hbuf[l & 1];
+        if (l >= 2 && m->pf[l - 1] && (reinterpret_cast<uintptr_t>(xin) & 15) == 0 && ldx % 4 == 0) {
+            // ---- project first: Z = h @ Wl^T over every row of the previous level, C = h[rows] @ Wr^T + b, then the
+            // gather adds mean_j Z[j] - Fo floats per edge instead of Fi (W mean(h) = mean(W h))
+            const int o4 = m->o4[l - 1];
+            const int64_t ldk = m->ldk[l - 1];
+            const int64_t rows_prev = b->level_end_host[n_layers - l + 2];
+            void* pZ = nullptr;
+            if ((rc = gigl_scratch(ctx, GIGL_SLOT_IO4, sizeof(float) * (size_t)(rows_prev > 0 ? rows_prev : 1) * o4, &pZ)) != GIGL_OK) return rc;
+            float* Z = (float*)pZ;
+            int tg = gigl_timer_begin(ctx, GIGL_T_GEMM_DEEP);
+            rc = linear_tc_launch_ex(ctx, rows_prev, nullptr, o4, Fi, xin, nullptr, ldx, m->pl_hi[l - 1], m->pl_lo[l - 1], ldk, nullptr, Z, o4, 0);
+            if (rc == GIGL_OK)
+                rc = linear_tc_launch_ex(ctx, rows, nullptr, Fo, Fi, xin, nullptr, ldx, m->pr_hi[l - 1], m->pr_lo[l - 1], ldk, m->bias[l - 1], C, Fo, 0);
+            gigl_timer_end(ctx, tg);
+            if (rc != GIGL_OK) return rc;
+            const AccOut ao{C, (int64_t)Fo, Fo, l < n_layers ? 1 : 0};
+            tg = gigl_timer_begin(ctx, GIGL_T_GATHER_DEEP);
+            rc = batch_gather_launch(b, rows_dev, rows, o4, Z, o4, b->lid, nullptr, nullptr, 0, ao);
+            gigl_timer_end(ctx, tg);
+            if (rc != GIGL_OK) return rc;
+            xin = C;
+            ldx = Fo;
+            continue;
+        }
+        int tg = gigl_timer_begin(ctx, l == 1 ? GIGL_T_GATHER_L1 : GIGL_T_GATHER_DEEP);
+        rc = batch_gather_launch(b, rows_dev, rows, Fi, xin, ldx, lidmap, A_hi, A_lo, lda, AccOut{nullptr, 0, 0, 0});
+        gigl_timer_end(ctx, tg);
+        if (rc != GIGL_OK) return rc;
         gigl_timed tgemm(ctx, l == 1 ? GIGL_T_GEMM_L1 : GIGL_T_GEMM_DEEP);
         rc = linear_tc_launch_ex(ctx, rows, nullptr, Fo, 2 * Fi, A_hi, A_lo, lda, m->w_hi[l - 1], m->w_lo[l - 1], lda, m->bias[l - 1], C, Fo,
                                  l < n_layers ? 1 : 0);
@@ -1673,6 +1826,17 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
 gigl_ctx* batch_ctx(gigl_batch* b) { return b->ctx; }
 
 void batch_set_halo_staging(gigl_batch* b, bool enabled) { b->halo_staging = enabled; }
+
+int batch_set_hot_rows(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld) {
+    gigl_ctx* ctx = b->ctx;
+    GIGL_CHECK(ctx, (hot_slot_dev == nullptr) == (hot_dev == nullptr), "hot_slot and hot table must be given together");
+    GIGL_CHECK(ctx, hot_dev == nullptr || (F >= 1 && ld >= F), "bad hot table shape");
+    b->hot_slot = hot_slot_dev;
+    b->hot = hot_dev;
+    b->hot_F = F;
+    b->ldh = ld;
+    return GIGL_OK;
+}
 
 namespace gigl {
 // compacted unique keys (dst << 32 | src, global ids) -> edge_index rows in local ids

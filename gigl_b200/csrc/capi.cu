@@ -812,6 +812,11 @@ int gigl_batch_set_halo_staging(gigl_batch* b, int32_t enabled) {
     return GIGL_OK;
 }
 
+int gigl_batch_set_hot_rows_dev(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld) {
+    if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
+    return batch_set_hot_rows(b, hot_slot_dev, hot_dev, F, ld);
+}
+
 int gigl_batch_export_dev(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev) {
     if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
     GIGL_CUDA(batch_ctx(b), cudaSetDevice(batch_ctx(b)->device));

@@ -184,6 +184,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
                   const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes_host, int64_t* n_edges_host);
 int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges);
 void batch_set_halo_staging(gigl_batch* b, bool enabled);
+int batch_set_hot_rows(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld);
 int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev);
 int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx, float* out_dev);
 gigl_ctx* batch_ctx(gigl_batch* b);

@@ -70,13 +70,15 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     const uint32_t w_bytes = (uint32_t)p.n_pad * kBlockK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-    // bars: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | conv[stages]
+    // bars: full[stages] (A tiles) | empty[stages] | tmem_full[2] | tmem_empty[2] | conv[stages] | fullw[stages] (W tiles)
+    // A and W land on separate barriers: the converter warps split A while the (larger) W tiles are still in flight
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * p.stages;
     const uint32_t bar_tfull = bar_empty + 8 * p.stages;
     const uint32_t bar_tempty = bar_tfull + 16;
     const uint32_t bar_conv = bar_tempty + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 4);
+    const uint32_t bar_fullw = bar_conv + 8 * p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * p.stages + 4);
     const uint32_t smem_base = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,6 +96,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
             mbar_init(bar_conv + 8 * s, 4);  // one arrive per converter warp
+            mbar_init(bar_fullw + 8 * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
@@ -121,16 +124,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                 const int n0 = (int)((tile % p.n_tiles_n) * p.n_pad);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t full = bar_full + 8 * stage, fullw = bar_fullw + 8 * stage;
                     const uint32_t sa = smem_base + stage * stage_bytes;
-                    mbar_expect_tx(full, ((p.dbg & 4) ? 0 : (p.split_a ? a_bytes : 2 * a_bytes)) + ((p.dbg & 2) ? 0 : 2 * w_bytes));
+                    mbar_expect_tx(full, (p.dbg & 4) ? 0 : (p.split_a ? a_bytes : 2 * a_bytes));
                     if (!(p.dbg & 4)) {
                         tma_load_2d(sa, &tm_a_hi, full, kb * kBlockK, m0);
                         if (!p.split_a) tma_load_2d(sa + a_bytes, &tm_a_lo, full, kb * kBlockK, m0);
                     }
+                    mbar_expect_tx(fullw, (p.dbg & 2) ? 0 : 2 * w_bytes);
                     if (!(p.dbg & 2)) {
-                        tma_load_2d(sa + 2 * a_bytes, &tm_w_hi, full, kb * kBlockK, n0);
-                        tma_load_2d(sa + 2 * a_bytes + w_bytes, &tm_w_lo, full, kb * kBlockK, n0);
+                        tma_load_2d(sa + 2 * a_bytes, &tm_w_hi, fullw, kb * kBlockK, n0);
+                        tma_load_2d(sa + 2 * a_bytes + w_bytes, &tm_w_lo, fullw, kb * kBlockK, n0);
                     }
                     if (++stage == p.stages) {
                         stage = 0;
@@ -157,6 +161,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                 const uint32_t tmem_s = tmem_d + (uint32_t)p.n_pad;  // small-term accumulator (split_acc only)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait((p.split_a ? bar_conv : bar_full) + 8 * stage, phase);
+                    mbar_wait(bar_fullw + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * stage_bytes;
                     const uint64_t d_ah = umma_desc_sw128(sa), d_al = umma_desc_sw128(sa + a_bytes);

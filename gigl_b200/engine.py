@@ -534,6 +534,28 @@ class Batch:
         and let layer 1 gather from that copy, instead of one peer load per unique edge (gigl_batch_set_halo_staging)."""
         check(self.ctx._L.gigl_batch_set_halo_staging(self.handle, int(bool(enabled))), self.ctx.handle)
 
+    def set_hot_rows(self, graph: "Graph", x, fraction: float) -> int:
+        """Staged halo of a sharded feature table: replicate the rows of the `fraction` of the vertices with the highest
+        degree on this GPU (gigl_batch_set_hot_rows_dev), so only a batch's cold tail crosses NVLink.  x = the flat
+        [n_nodes, F] table (peer rows are read once, here).  Returns the number of replicated rows."""
+        from .sharding import hot_rows
+
+        slot, table = hot_rows(graph, x, fraction)
+        n_hot = int(table.shape[0])
+        if n_hot == 0:
+            check(self.ctx._L.gigl_batch_set_hot_rows_dev(self.handle, None, None, 0, 0), self.ctx.handle)
+            self._hot = None
+            return 0
+        check(self.ctx._L.gigl_batch_set_hot_rows_dev(self.handle, _dp(slot), _dp_any(table), x.shape[1], table.stride(0)), self.ctx.handle)
+        self._hot = (slot, table)  # owned here: the library keeps the pointers
+        return n_hot
+
+    def share_hot_rows(self, other: "Batch", F: int) -> None:
+        """Use the hot-row replica another batch workspace of the same GPU already built (one copy per GPU, not per stream)."""
+        slot, table = other._hot
+        check(self.ctx._L.gigl_batch_set_hot_rows_dev(self.handle, _dp(slot), _dp_any(table), F, table.stride(0)), self.ctx.handle)
+        self._hot = other._hot
+
     def sage_forward(self, model: SageModel, x, out=None):
         import torch
 

@@ -129,6 +129,35 @@ def exchange_fds(my_fd: int, rank: int, world: int, tag: str, timeout: float = 1
     return got
 
 
+def hot_rows(graph, x, fraction: float):
+    """The hot set of a sharded feature table: the ceil(fraction * N) vertices that occur most often as a SOURCE of the
+    graph's edges (a vertex is drawn into a batch through the in-edge rows it sits in, so its out-degree is its weight;
+    on an undirected graph that is its degree).  Returns (slot int32 [N]: vertex -> row of the copy or -1, table
+    [n_hot, pitch] with the rows copied out of `x` - peer rows cross NVLink once, here)."""
+    import torch
+
+    n = graph.n_nodes
+    n_hot = min(n, int(-(-fraction * n // 1))) if fraction > 0 else 0
+    dev = x.device
+    slot = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    if n_hot == 0:
+        return slot, torch.empty((0, x.shape[1]), dtype=torch.float32, device=dev)
+    _, col = graph.csr_tensors()
+    deg = torch.zeros(n, dtype=torch.int64, device=dev)
+    step = 1 << 27
+    for s0 in range(0, col.numel(), step):  # out-degree, in chunks (a 1e9-edge column list is 8 GB as int64)
+        deg += torch.bincount(col[s0:s0 + step].long(), minlength=n)
+    ids = torch.topk(deg, n_hot, sorted=False).indices.sort().values
+    del deg
+    slot[ids] = torch.arange(n_hot, dtype=torch.int32, device=dev)
+    pitch = -(-x.shape[1] // 32) * 32
+    table = torch.zeros((n_hot, pitch), dtype=torch.float32, device=dev)
+    for r0 in range(0, n_hot, 1 << 20):
+        r1 = min(n_hot, r0 + (1 << 20))
+        table[r0:r1, : x.shape[1]] = x[ids[r0:r1]]
+    return slot, table[:, : x.shape[1]]
+
+
 class ShardedFeatureTable:
     """The [n_nodes, F] fp32 feature table with shard ``rank`` resident on this GPU and every other shard mapped from
     its owner's memory, as ONE flat CUDA array (``.table``, a torch view usable by ``Graph.set_features`` /

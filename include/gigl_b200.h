@@ -396,6 +396,16 @@ int gigl_batch_sage_forward_dev(gigl_batch* b, const gigl_sage_model* m, const f
  * most rows are remote (a batch has several times more unique edges than unique nodes), a loss on a local table.
  */
 int gigl_batch_set_halo_staging(gigl_batch* b, int32_t enabled);
+/*
+ * Hot rows of the staged halo: hot_dev [n_hot, ld] holds a LOCAL copy of the feature rows of the vertices batches meet
+ * most often (the caller picks them - gigl_b200.sharding.hot_rows takes the highest-degree vertices - and fills the copy
+ * once, from the sharded table), hot_slot_dev [n_graph_nodes] maps a vertex to its row there (-1 = not replicated).
+ * The staging kernel then reads those rows from local HBM and only the cold tail of a batch crosses NVLink; the
+ * embeddings are unchanged (the same bytes from another address).  NULL / NULL switches it off.  Both arrays stay owned
+ * by the caller and must outlive the batch's forward calls.  This is the replicate-the-hubs / shard-the-tail residency
+ * between "replicated" and "sharded" of SURVEY.md section 8(e): per-GPU memory = 1/N of the table + the hot fraction.
+ */
+int gigl_batch_set_hot_rows_dev(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld);
 
 /*
  * One call from host buffers: roots (host) -> k-hop sample -> collate -> GraphSAGE forward ->
