@@ -69,7 +69,7 @@ def parse_args(argv=None):
                          "gathers from the copy; 'direct' loads one (mostly remote) row per unique edge inside the gather kernel")
     ap.add_argument("--hot-rows", type=float, default=None,
                     help="sharded features: fraction of the table (highest in-degree vertices) replicated on every GPU "
-                         "(default: GIGL_HOT_ROWS or 0.125)")
+                         "(default: GIGL_HOT_ROWS or 0 = off)")
     ap.add_argument("--streams", type=int, default=2,
                     help="batches in flight per GPU: step i runs on stream i %% S with its own context / workspace, so the host "
                          "reads and kernel tails of one batch are covered by the other's kernels (1 = strictly one after the other)")
@@ -338,7 +338,9 @@ class Env:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL's banner must not land on stdout beside the JSON line
+            # NCCL's version banner must not land on stdout beside the JSON line: an explicit level also wins over a
+            # NCCL_DEBUG=VERSION from /etc/nccl.conf (the file only fills variables that are unset)
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
                 os.environ["NCCL_DEBUG"] = "WARN"
             dist.init_process_group("nccl", device_id=self.dev)
         self.dist = dist
@@ -715,7 +717,7 @@ def roofline_blocks(run: Run, dev_res, cnt, K):
 
 def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_full, tag):
     fan = [int(v) for v in args.fanout.split(",")]
-    hot = args.hot_rows if args.hot_rows is not None else float(os.environ.get("GIGL_HOT_ROWS", "0.125"))
+    hot = args.hot_rows if args.hot_rows is not None else float(os.environ.get("GIGL_HOT_ROWS", "0"))
     run = Run(env, wl_name, features, args.halo, args.batch, fan, hot, tag, streams=args.streams)
     wl, B, world = run.wl, run.B, env.world
     one = run.measure_device(K, W, streams=1)  # one batch at a time: the per-phase device times (rooflines) come from this form

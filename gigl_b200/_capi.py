@@ -55,6 +55,7 @@ SIGNATURES = {
     "gigl_sample_op_dev": (C.c_int, [vp, vp, i64, i32, vp, pvp, i32, i32, vp, vp]),
     "gigl_sample_op_host": (C.c_int, [vp, vp, i64, i32, vp, pvp, i32, i32, vp, vp]),
     "gigl_sample_positives_host": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp]),
+    "gigl_validate_samples_host": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp]),
     "gigl_frontier_distinct_dev": (C.c_int, [vp, i64, i32, pvp, vp, vp, i32, vp]),
     "gigl_csr_from_coo_dev": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
     "gigl_sage_conv_dev": (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32]),

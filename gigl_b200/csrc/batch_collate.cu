@@ -1759,7 +1759,11 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         if ((rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, sizeof(float) * (size_t)(n_nodes > 0 ? n_nodes : 1) * ldb, &pX)) != GIGL_OK) return rc;
         float* xb = (float*)pX;
         const int32_t* n_dev = b->d_ctr + kLevelBase + b->n_levels_done;
-        const unsigned sgrid = (unsigned)(ctx->sm_count * 8);
+        // The copy is bound by NVLink round trips, not by SM work: 2 CTAs per SM x 8 warps x 4 rows in flight keep ~5 MB on
+        // the wire (bandwidth x latency of the link is under 2 MB) and leave the SMs to whatever else is resident - with
+        // several batches in flight (one stream each) the other batch's kernels run under this one.  GIGL_HALO_CTAS: experiments.
+        static const int halo_ctas = getenv("GIGL_HALO_CTAS") ? atoi(getenv("GIGL_HALO_CTAS")) : 2;
+        const unsigned sgrid = (unsigned)(ctx->sm_count * (halo_ctas > 0 ? halo_ctas : 2));
         int th = gigl_timer_begin(ctx, GIGL_T_HALO_STAGE);
         const int32_t* hs = (b->hot_slot && b->hot_F == F0) ? b->hot_slot : nullptr;
         const bool vec = (F0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) && (ldx0 % 4 == 0) &&

@@ -904,6 +904,165 @@ int64_t gigl_tfrecord_index_host(const uint8_t* data, int64_t n_bytes, int32_t v
     return n;
 }
 
+// ---- TaskOutputValidator (scala/subgraph_sampler/src/main/scala/libs/task/TaskOutputValidator.scala:29-108) ------------
+// Every sample the component is about to write is parsed back from its OWN bytes and held to the reference's check: both
+// endpoints of every neighbourhood edge - and, for NodeAnchorBasedLinkPredictionSample, of every pos / neg / hard-neg edge -
+// are among the neighbourhood's nodes, compared as (node id, condensed node type) with the types an edge's condensed edge
+// type implies (GraphMetadataPbWrapper.getFeaturelessNodePbsFromEdge :75-83); a sample without a neighbourhood fails.
+namespace {
+struct PbField {
+    uint32_t num;
+    uint32_t wire;
+    uint64_t val;          // varint / fixed value
+    const uint8_t* data;   // length-delimited payload
+    uint64_t len;
+};
+// next field of a message; false at the end or on malformed input (ok = false)
+inline bool pb_next(const uint8_t*& p, const uint8_t* end, PbField& f, bool& ok) {
+    if (p >= end) return false;
+    uint64_t key;
+    if (!get_varint(p, end, key)) {
+        ok = false;
+        return false;
+    }
+    f.num = (uint32_t)(key >> 3);
+    f.wire = (uint32_t)(key & 7);
+    f.val = 0;
+    f.data = nullptr;
+    f.len = 0;
+    switch (f.wire) {
+        case 0:
+            if (!get_varint(p, end, f.val)) ok = false;
+            break;
+        case 1:
+            if (end - p < 8) ok = false; else p += 8;
+            break;
+        case 5:
+            if (end - p < 4) ok = false; else p += 4;
+            break;
+        case 2:
+            if (!get_varint(p, end, f.len) || f.len > (uint64_t)(end - p)) {
+                ok = false;
+            } else {
+                f.data = p;
+                p += f.len;
+            }
+            break;
+        default:
+            ok = false;
+    }
+    return ok;
+}
+inline uint64_t node_key(uint64_t id, uint64_t type) { return (type << 32) | (id & 0xffffffffULL); }
+struct EdgeEnds {
+    uint64_t src = 0, dst = 0, type = 0;
+};
+inline bool parse_edge(const uint8_t* p, const uint8_t* end, EdgeEnds& e) {
+    bool ok = true;
+    PbField f;
+    while (pb_next(p, end, f, ok)) {
+        if (f.num == 1 && f.wire == 0) e.src = f.val;
+        if (f.num == 2 && f.wire == 0) e.dst = f.val;
+        if (f.num == 3 && f.wire == 0) e.type = f.val;
+    }
+    return ok;
+}
+// 0 = valid, 1 = malformed bytes, 2 = no neighbourhood, 3 = an edge endpoint is not among the neighbourhood nodes
+int validate_sample(const uint8_t* p, const uint8_t* end, int32_t kind, int32_t n_edge_types, const int32_t* src_type,
+                    const int32_t* dst_type, std::vector<uint64_t>& nodes, std::vector<EdgeEnds>& edges) {
+    nodes.clear();
+    edges.clear();
+    bool ok = true, has_graph = false;
+    PbField f;
+    const uint32_t graph_field = (kind == 2) ? 3u : 2u;  // training_samples_schema.proto: neighborhood = 2 (RNN / SNC), 3 (NABLP)
+    while (pb_next(p, end, f, ok)) {
+        if (f.wire != 2) continue;
+        if (f.num == graph_field) {
+            has_graph = true;
+            const uint8_t* q = f.data;
+            const uint8_t* qe = f.data + f.len;
+            PbField g;
+            while (pb_next(q, qe, g, ok)) {
+                if (g.wire != 2) continue;
+                if (g.num == 2) {  // Graph.nodes
+                    const uint8_t* r = g.data;
+                    const uint8_t* re = g.data + g.len;
+                    uint64_t id = 0, type = 0;
+                    PbField h;
+                    while (pb_next(r, re, h, ok)) {
+                        if (h.num == 1 && h.wire == 0) id = h.val;
+                        if (h.num == 2 && h.wire == 0) type = h.val;
+                    }
+                    nodes.push_back(node_key(id, type));
+                } else if (g.num == 3) {  // Graph.edges
+                    EdgeEnds e;
+                    if (!parse_edge(g.data, g.data + g.len, e)) ok = false;
+                    edges.push_back(e);
+                }
+            }
+        } else if (kind == 2 && (f.num == 2 || f.num == 4 || f.num == 5)) {  // hard_neg_edges / pos_edges / neg_edges
+            EdgeEnds e;
+            if (!parse_edge(f.data, f.data + f.len, e)) ok = false;
+            edges.push_back(e);
+        }
+    }
+    if (!ok) return 1;
+    if (!has_graph) return 2;
+    std::sort(nodes.begin(), nodes.end());
+    for (const EdgeEnds& e : edges) {
+        uint64_t st = 0, dt = 0;  // DefaultCondensedNodeType
+        if (src_type && dst_type) {
+            if (e.type >= (uint64_t)n_edge_types) return 3;
+            st = (uint64_t)(uint32_t)src_type[e.type];
+            dt = (uint64_t)(uint32_t)dst_type[e.type];
+        }
+        if (!std::binary_search(nodes.begin(), nodes.end(), node_key(e.src, st)) ||
+            !std::binary_search(nodes.begin(), nodes.end(), node_key(e.dst, dt)))
+            return 3;
+    }
+    return 0;
+}
+}  // namespace
+
+// data: the encoder's output (TFRecord-framed when tfrecord_framing != 0, else n_records payloads given by offsets /
+// lengths).  kind: 0 = RootedNodeNeighborhood, 1 = SupervisedNodeClassificationSample, 2 = NodeAnchorBasedLinkPredictionSample.
+// edge_src_type / edge_dst_type: condensed node types of every condensed edge type's endpoints (NULL = homogeneous: every
+// node type 0).  Returns GIGL_OK, or GIGL_E_INVALID with *bad_record = the first offending record and *reason = 1 malformed,
+// 2 neighbourhood missing, 3 edge endpoint outside the neighbourhood nodes.
+int gigl_validate_samples_host(const uint8_t* data, int64_t n_bytes, int32_t kind, int32_t n_edge_types, const int32_t* edge_src_type,
+                               const int32_t* edge_dst_type, int64_t* n_records_out, int64_t* bad_record, int32_t* reason) {
+    if (!data || n_bytes < 0 || kind < 0 || kind > 2 || ((edge_src_type == nullptr) != (edge_dst_type == nullptr))) return GIGL_E_INVALID;
+    const int64_t n = gigl_tfrecord_index_host(data, n_bytes, 0, nullptr, nullptr, 0);
+    if (n < 0) return (int)n;
+    std::vector<int64_t> off((size_t)(n > 0 ? n : 1)), len((size_t)(n > 0 ? n : 1));
+    if (n > 0 && gigl_tfrecord_index_host(data, n_bytes, 0, off.data(), len.data(), n) != n) return GIGL_E_INVALID;
+    int64_t first_bad = n;
+    int32_t why = 0;
+#pragma omp parallel
+    {
+        std::vector<uint64_t> nodes;
+        std::vector<EdgeEnds> edges;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < n; ++i) {
+            const int r = validate_sample(data + off[i], data + off[i] + len[i], kind, n_edge_types, edge_src_type, edge_dst_type, nodes, edges);
+            if (r != 0) {
+#pragma omp critical
+                if (i < first_bad) {
+                    first_bad = i;
+                    why = r;
+                }
+            }
+        }
+    }
+    if (n_records_out) *n_records_out = n;
+    if (first_bad < n) {
+        if (bad_record) *bad_record = first_bad;
+        if (reason) *reason = why;
+        return GIGL_E_INVALID;
+    }
+    return GIGL_OK;
+}
+
 // Decodes one named feature of every tf.Example record into a dense column.
 // dtype: 0 = int64 (Int64List, written to out_i64), 1 = float (FloatList -> out_f32; an Int64List is cast, which is what
 // `cast(col as array<float>)` does in loadNodeDataframeIntoSparkSql :90-104).  width = values per record (records with a

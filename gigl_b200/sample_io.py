@@ -40,6 +40,40 @@ def list_tfrecord_files(uri_prefix: str) -> List[str]:
     return files
 
 
+def validate_samples(data, kind: str, edge_node_types=None) -> int:
+    """The reference's TaskOutputValidator (scala/subgraph_sampler/src/main/scala/libs/task/TaskOutputValidator.scala:29-108)
+    on a TFRecord stream of encoded samples, natively (gigl_validate_samples_host): both endpoints of every neighbourhood
+    edge - for kind "nablp" also of every pos / neg / hard-neg edge - must be among the neighbourhood nodes as
+    (node id, condensed node type).  edge_node_types: {condensed edge type: (src condensed node type, dst condensed node
+    type)} or None (homogeneous).  data: bytes or the encoder's NativeBuffer.  Returns the number of records; raises
+    GiglError naming the first offending record (the reference throws RuntimeException)."""
+    L = _capi.lib()
+    if isinstance(data, NativeBuffer):
+        ptr, n = data._ptr, data.nbytes
+        keep = data
+    else:
+        keep = np.frombuffer(data, dtype=np.uint8)
+        ptr, n = keep.ctypes.data, len(keep)
+    st = dt = None
+    n_types = 0
+    if edge_node_types:
+        n_types = max(edge_node_types) + 1
+        st = np.zeros(n_types, dtype=np.int32)
+        dt = np.zeros(n_types, dtype=np.int32)
+        for t, (a, b) in edge_node_types.items():
+            st[t], dt[t] = a, b
+    n_rec, bad, why = C.c_int64(), C.c_int64(-1), C.c_int32(0)
+    rc = L.gigl_validate_samples_host(C.c_void_p(ptr), n, {"rnn": 0, "snc": 1, "nablp": 2}[kind], n_types,
+                                      None if st is None else st.ctypes.data, None if dt is None else dt.ctypes.data,
+                                      C.byref(n_rec), C.byref(bad), C.byref(why))
+    del keep
+    if rc != 0:
+        reason = {1: "malformed sample bytes", 2: "neighborhood not present in sample",
+                  3: "a node of an edge is not present in the neighborhood graph"}.get(why.value, "invalid stream")
+        raise GiglError(int(rc), f"Output Validation failed: record {bad.value}: {reason}")
+    return int(n_rec.value)
+
+
 class ExampleTable:
     """All tf.Example records of a set of TFRecord files, decoded column by column in native code."""
 

@@ -152,8 +152,11 @@ def _prepare_dir(dir_: str) -> None:
                 pass
 
 
-def _write(dir_: str, part: int, data) -> None:
-    """data: bytes, or the encoder's NativeBuffer (written straight from the native memory, then released)."""
+def _write(dir_: str, part: int, data, kind: str = "rnn", edge_node_types=None) -> None:
+    """data: bytes, or the encoder's NativeBuffer (written straight from the native memory, then released).  Before anything
+    reaches the file the samples are held to the reference's TaskOutputValidator (TaskOutputValidator.scala:29-108, run by
+    every task before `writeDatasetToTfrecord`): a failure raises and the part is not written."""
+    sio.validate_samples(data, kind, edge_node_types)
     rank, world = _SHARD
     name = f"part-{part:05d}.tfrecord" if world == 1 else f"part-r{rank:03d}-{part:05d}.tfrecord"
     with open(os.path.join(dir_, name), "wb") as f:
@@ -162,6 +165,12 @@ def _write(dir_: str, part: int, data) -> None:
             data.close()
         else:
             f.write(data)
+
+
+def _edge_node_types(hyd: dict) -> dict:
+    """Homogeneous graph: the validator's map condensed edge type -> (src, dst) condensed node types."""
+    nt = max(int(hyd["condensed_node_type"]), 0)
+    return {max(int(hyd["condensed_edge_type"]), 0): (nt, nt)}
 
 
 def _my_share(ids: np.ndarray) -> np.ndarray:
@@ -267,6 +276,7 @@ def run(task_config_uri: str, job_name: str, resource_config_uri: Optional[str] 
 
 def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n_nodes, skip_main, max_train, batch_roots, stats):
     out = flat["supervisedNodeClassificationOutput"]
+    ent = _edge_node_types(hyd)
     labels = None
     label_key = (nmeta.get("labelKeys") or [None])[0]
     if label_key and not skip_main:
@@ -281,7 +291,7 @@ def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n
         roots = roots_all[s:s + batch_roots]
         nbr, cnt = g.sample_khop_host(roots, fanouts, base_seed=SAMPLING_SEED, first_call_no=1)
         data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="rnn", zero_copy=True, **hyd)
-        _write(unl_dir, part, data)  # RootedNodeNeighborhood first
+        _write(unl_dir, part, data, "rnn", ent)  # RootedNodeNeighborhood first
         stats["rnn"] += len(roots)
         if labels is not None:
             # isolated nodes (no sampled in-edge) are NOT training samples (includeIsolatedNodesInTrainingSamples = false, :43-44)
@@ -291,7 +301,7 @@ def _run_snc(g, flat, root, roots_all, fanouts, x, hyd, nodes, node_id, nmeta, n
                 keep = roots[(cnt[0] > 0) & (labels[roots] != sio.INT32_MIN)][max(0, max_train - stats["snc"]):]
                 lab[keep] = sio.INT32_MIN
             data, offs = sio.encode_samples(roots, fanouts, nbr, x, kind="snc", labels=lab, label_type=label_key, zero_copy=True, **hyd)
-            _write(lab_dir, part, data)
+            _write(lab_dir, part, data, "snc", ent)
             stats["snc"] += int((np.diff(offs) > 0).sum())
 
 
@@ -308,6 +318,7 @@ def _label_table(ctx, n_nodes, ls, ld, feat):
 def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32, n_nodes, directed, sgs, skip_main, max_train,
                batch_roots, stats, label_tables):
     out = flat["nodeAnchorBasedLinkPredictionOutput"]
+    ent = _edge_node_types(hyd)
     sup = cfg["taskMetadata"]["nodeAnchorBasedLinkPredictionTaskMetadata"]["supervisionEdgeTypes"]
     dst_type = sup[0]["dstNodeType"]
     neg_map = out.get("nodeTypeToRandomNegativeTfrecordUriPrefix") or {}
@@ -366,7 +377,7 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
             width *= f
             own.append(nbr[len(own)][: n * width])
         data, _ = sio.encode_samples(roots, fanouts, own, x, kind="rnn", zero_copy=True, **hyd)
-        _write(rnn_dir, part, data)  # RootedNodeNeighborhood (random negatives) first
+        _write(rnn_dir, part, data, "rnn", ent)  # RootedNodeNeighborhood (random negatives) first
         stats["rnn"] += n
         if pos is not None:
             order = np.argsort(sample_roots, kind="stable")
@@ -380,7 +391,7 @@ def _run_nablp(g, ctx, cfg, flat, root, roots_all, fanouts, x, hyd, src32, dst32
                                                  tree_of(neg) if neg is not None else None, neg_tab,
                                                  condensed_node_type=hyd["condensed_node_type"], condensed_edge_type=hyd["condensed_edge_type"],
                                                  zero_copy=True)
-            _write(main_dir, part, data)
+            _write(main_dir, part, data, "nablp", ent)
             stats["nablp"] += int((np.diff(offs) > 0).sum())
 
 
@@ -482,6 +493,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
         return dag.encoder_ops(planned, res, cet_of, cnt_of)
 
     stats = {"rnn": 0, "snc": 0, "nablp": 0, "rnn_per_node_type": {}, "n_nodes": n_max}
+    ent = {c: (cnt_of[t[0]], cnt_of[t[2]]) for t, c in cet_of.items()}  # the validator's edge type -> endpoint node types
     t1 = time.time()
     for rtype in dags:
         if rtype not in out_dirs:
@@ -494,7 +506,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
             roots = roots_all[s:s + batch_roots]
             data, _ = sio.encode_typed_samples(roots, cnt_of[rtype], sample(rtype, roots), tables, edge_tables() if hydrate else None,
                                                kind="rnn", hydrate_edges=hydrate, zero_copy=True)
-            _write(out_dir, part, data)
+            _write(out_dir, part, data, "rnn", ent)
             stats["rnn"] += len(roots)
             stats["rnn_per_node_type"][rtype] = stats["rnn_per_node_type"].get(rtype, 0) + len(roots)
     # ---- main samples of the link-prediction task
@@ -531,7 +543,7 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
                                                   target_ops=sample(t_type, t_roots) if len(t_roots) else [],
                                                   include_isolated=include_isolated, hydrate_edges=hyd_graph, hydrate_pos_edges=hyd_pos,
                                                   zero_copy=True)
-            _write(main_dir, part, data)
+            _write(main_dir, part, data, "nablp", ent)
             stats["nablp"] += int((np.diff(offs) > 0).sum())
     stats["seconds_sample_and_write"] = time.time() - t1
     stats["seconds_total"] = time.time() - t0

@@ -566,6 +566,18 @@ int gigl_encode_typed_samples_host(int32_t kind, const gigl_dag_tree* anchors, c
 int64_t gigl_tfrecord_index_host(const uint8_t* data, int64_t n_bytes, int32_t verify, int64_t* offsets, int64_t* lengths,
                                  int64_t max_records);
 /*
+ * TaskOutputValidator.validateRootedNodeNeighborhoodSamples / validateMainSamples (scala/subgraph_sampler/src/main/scala/
+ * libs/task/TaskOutputValidator.scala:29-108) on the bytes about to be written: every sample of a TFRecord stream is parsed
+ * back and both endpoints of every neighbourhood edge (kind 2: also of every pos / neg / hard-neg edge) must be among the
+ * neighbourhood's nodes, compared as (node id, condensed node type) with the node types the edge's condensed edge type
+ * implies (edge_src_type / edge_dst_type per condensed edge type; NULL = homogeneous, type 0); a sample without a
+ * neighbourhood fails.  kind: 0 RootedNodeNeighborhood, 1 SupervisedNodeClassificationSample, 2 NodeAnchorBasedLink-
+ * PredictionSample.  GIGL_OK, or GIGL_E_INVALID with *bad_record = the first offending record and *reason = 1 malformed
+ * bytes, 2 neighbourhood missing, 3 endpoint outside the neighbourhood nodes (the reference throws RuntimeException).
+ */
+int gigl_validate_samples_host(const uint8_t* data, int64_t n_bytes, int32_t kind, int32_t n_edge_types, const int32_t* edge_src_type,
+                               const int32_t* edge_dst_type, int64_t* n_records_out, int64_t* bad_record, int32_t* reason);
+/*
  * Decodes feature `name` of every tf.Example record into a dense column of `width` values per record: dtype 0 = int64
  * (out_i64), dtype 1 = float (out_f32; an Int64List is cast, as `cast(col as array<float>)` does at
  * SGSPureSparkV1Task.scala:90-104).  GIGL_E_RANGE if a record lacks the feature.

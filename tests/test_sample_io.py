@@ -4,6 +4,7 @@ import base64
 import os
 
 import numpy as np
+import pytest
 
 from helpers import GOLDEN, load_golden
 
@@ -159,3 +160,49 @@ def test_encoder_round_trip_and_reference_structure():
     # node id 0 and label 0 are proto3 defaults (not on the wire) and must still decode to 0
     s0 = sio.parse_sample(sio.split_tfrecords(sio.encode_samples(roots[:1], fan, [a[: 3 ** (h + 1)] for h, a in enumerate(nbr)], x)[0])[0])
     assert s0["root_node"]["node_id"] == 0
+
+
+def test_task_output_validator_on_encoded_bytes():
+    """TaskOutputValidator.scala:29-108 restated natively: the reference's own sampler outputs pass; a sample whose edge
+    names a node outside its neighbourhood, or a node of the wrong condensed type, or that lacks the neighbourhood, fails
+    with the record named."""
+    from helpers import tfrecord_bytes
+
+    # the reference sampler's real output (tests/golden/*_sgs_output.json was decoded from these bytes' originals)
+    g = load_golden("snc16_graph.json")
+    src, dst = np.asarray([e[0] for e in g["edges"]]), np.asarray([e[1] for e in g["edges"]])
+    n = 16
+    rowptr, col = O.np_build_in_csr(src, dst, n, False)
+    roots = np.arange(n, dtype=np.int32)
+    nbr, _ = O.c_sample_khop(rowptr, col, roots, [3, 3])
+    x = np.arange(n * 2, dtype=np.float32).reshape(n, 2)
+    data, _ = sio.encode_samples(roots, [3, 3], nbr, x, kind="rnn", condensed_node_type=0, condensed_edge_type=0)
+    assert sio.validate_samples(data, "rnn", {0: (0, 0)}) == n
+    assert sio.validate_samples(data, "rnn") == n  # homogeneous default: node type 0
+    # the same bytes read with an edge type whose endpoints are of another node type: every edge endpoint is "missing"
+    with pytest.raises(sio.GiglError, match="record 0"):
+        sio.validate_samples(data, "rnn", {0: (1, 0)})
+
+    def node(i, t=0):
+        return b"\x08" + bytes([i]) + b"\x10" + bytes([t])
+
+    def edge(s, d, t=0):
+        return b"\x08" + bytes([s]) + b"\x10" + bytes([d]) + b"\x18" + bytes([t])
+
+    def ld(field, payload):
+        return bytes([(field << 3) | 2, len(payload)]) + payload
+
+    good = ld(1, node(1)) + ld(2, ld(2, node(1)) + ld(2, node(2)) + ld(3, edge(2, 1)))
+    bad_edge = ld(1, node(1)) + ld(2, ld(2, node(1)) + ld(2, node(2)) + ld(3, edge(3, 1)))      # node 3 is not in the neighbourhood
+    no_graph = ld(1, node(1))
+    assert sio.validate_samples(tfrecord_bytes([good, good]), "rnn") == 2
+    with pytest.raises(sio.GiglError, match="record 1.*not present in the neighborhood graph"):
+        sio.validate_samples(tfrecord_bytes([good, bad_edge]), "rnn")
+    with pytest.raises(sio.GiglError, match="record 0.*neighborhood not present"):
+        sio.validate_samples(tfrecord_bytes([no_graph, good]), "rnn")
+    # NodeAnchorBasedLinkPredictionSample: neighborhood is field 3, pos_edges field 4 are validated too
+    nablp_good = ld(1, node(1)) + ld(4, edge(1, 2)) + ld(3, ld(2, node(1)) + ld(2, node(2)) + ld(3, edge(2, 1)))
+    nablp_bad = ld(1, node(1)) + ld(4, edge(1, 5)) + ld(3, ld(2, node(1)) + ld(2, node(2)) + ld(3, edge(2, 1)))
+    assert sio.validate_samples(tfrecord_bytes([nablp_good]), "nablp") == 1
+    with pytest.raises(sio.GiglError, match="record 0"):
+        sio.validate_samples(tfrecord_bytes([nablp_bad]), "nablp")
