@@ -399,7 +399,7 @@ class Run:
         self.batch = Batch(self.ctx, wl["nodes"])
         self.hot_rows = 0
         if self.sharded and self.halo == "staged":
-            self.batch.set_halo_staging(True)
+            self.batch.set_halo_staging(True, x if os.environ.get("GIGL_HALO_EARLY", "1") != "0" else None)
             if hot_rows > 0 and env.world > 1 and hasattr(self.batch, "set_hot_rows"):
                 self.hot_rows = self.batch.set_hot_rows(self.g, x, hot_rows)
         self.ctx.sync()
@@ -418,7 +418,7 @@ class Run:
             g2.set_features(x)
             b2 = Batch(c, wl["nodes"])
             if self.sharded and self.halo == "staged":
-                b2.set_halo_staging(True)
+                b2.set_halo_staging(True, x if os.environ.get("GIGL_HALO_EARLY", "1") != "0" else None)
                 if self.hot_rows and getattr(self.batch, "_hot", None) is not None:
                     b2.share_hot_rows(self.batch, x.shape[1])
             self.pipes.append(dict(ctx=c, g=g2, model=SageModel(c, self.layers), batch=b2,

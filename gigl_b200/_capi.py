@@ -88,6 +88,7 @@ SIGNATURES = {
     "gigl_batch_sage_forward_dev": (C.c_int, [vp, vp, vp, i64, vp]),
     "gigl_batch_set_halo_staging": (C.c_int, [vp, i32]),
     "gigl_batch_set_hot_rows_dev": (C.c_int, [vp, vp, vp, i32, i64]),
+    "gigl_batch_set_halo_table_dev": (C.c_int, [vp, vp, i32, i64]),
     "gigl_crc32c_masked": (C.c_uint32, [vp, i64]),
     "gigl_free_host": (None, [vp]),
     "gigl_encode_samples_host": (C.c_int, [i32, i64, vp, vp, i32, pvp, vp, i32, i32, i32, vp, cp, i32, pvp, C.POINTER(i64), vp]),

@@ -786,8 +786,11 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
     int2 segA = __ldg(segmap + vA), segB = __ldg(segmap + vB), segC = __ldg(segmap + vC);
     uint64_t kB = load_keys(segB);
     int32_t myA = resolve(load_keys(segA));
+    // the row's own source row: through the same map as its neighbours' (the staged table of the halo is not in local-id order)
+    int32_t sA = lid ? __ldg(lid + vA) : vA;
     for (; row < n_rows; row += W) {
         // ---- prefetch stage of the pipeline ----
+        const int32_t sB = lid ? __ldg(lid + vB) : vB;
         const int32_t vE = __ldg(list + GIGL_ROW(row + 4 * W));
         const int2 segD = __ldg(segmap + vD);
         const uint64_t kC = load_keys(segC);
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
             // else: lists full (cannot happen with the host-side sizing): do the long row here
         }
         if (!deferred) {
-            const int64_t self = lid ? row : (int64_t)vA;
+            const int64_t self = sA;
             const int cnt0 = len < 32 ? len : 32;
             for (int c0 = 0; c0 < F; c0 += LPR * 4) {
                 const int c = c0 + sub * 4;
@@ -843,6 +846,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const int32_t* __rest
         segC = segD;
         kB = kC;
         myA = myB;
+        sA = sB;
     }
 #undef GIGL_ROW
 }
@@ -920,10 +924,12 @@ __global__ void __launch_bounds__(256) batch_gather_async_kernel(const int32_t* 
     int2 segA = __ldg(segmap + vA), segB = __ldg(segmap + vB), segC = __ldg(segmap + vC);
     uint64_t kB = load_keys(segB.x, segB.y);
     int32_t myA = resolve(load_keys(segA.x, segA.y), kKeyNone);
+    int32_t sA = lid ? __ldg(lid + vA) : vA;  // the row's own source row, through the same map as its neighbours'
     int ub = 0;              // buffer the next unit of the current row goes to / comes from
     bool pre_issued = false; // unit 0 of row A is already in flight in buffer `ub`
     for (; row < n_rows; row += W) {
         // ---- prefetch stage of the metadata pipeline ----
+        const int32_t sB = lid ? __ldg(lid + vB) : vB;
         const int32_t vE = __ldg(list + GIGL_ROW(row + 4 * W));
         const int2 segD = __ldg(segmap + vD);
         const uint64_t kC = load_keys(segC.x, segC.y);
@@ -946,7 +952,7 @@ __global__ void __launch_bounds__(256) batch_gather_async_kernel(const int32_t* 
         }
         bool next_pre = false;
         if (!deferred) {
-            const int64_t self = lid ? row : (int64_t)vA;
+            const int64_t self = sA;
             float4 selfv[CPL], acc[CPL];
 #pragma unroll
             for (int q = 0; q < CPL; ++q) {
@@ -1021,6 +1027,7 @@ __global__ void __launch_bounds__(256) batch_gather_async_kernel(const int32_t* 
         segC = segD;
         kB = kC;
         myA = myB;
+        sA = sB;
     }
 #undef GIGL_ROW
 }
@@ -1071,7 +1078,8 @@ __global__ void __launch_bounds__(kFinishWarps * 32) batch_gather_finish_kernel(
     for (int hr = blockIdx.x; hr < n_heavy; hr += gridDim.x) {
         const int4 r = hl.rows[hr];
         const int64_t row = r.x;
-        const int64_t self = lid ? row : (int64_t)__ldg(list + row);
+        const int32_t vrow = __ldg(list + row);
+        const int64_t self = lid ? (int64_t)__ldg(lid + vrow) : (int64_t)vrow;
         int cnt = 0;
         for (int p = w * 32 + lane; p < r.z; p += kFinishWarps * 32) cnt += hl.pcnt[r.y + p];
 #pragma unroll
@@ -1134,7 +1142,7 @@ __global__ void __launch_bounds__(256) batch_gather_scalar_kernel(const int32_t*
     for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
         const int32_t v = __ldg(list + row);
         const int2 seg = __ldg(segmap + v);
-        const int64_t self = lid ? row : (int64_t)v;
+        const int64_t self = lid ? (int64_t)__ldg(lid + v) : (int64_t)v;
         for (int c = lane; c < F; c += 32) {
             float acc = 0.f;
             int n_uniq = 0;
@@ -1239,6 +1247,52 @@ __global__ void __launch_bounds__(256) halo_stage_scalar_kernel(const int32_t* _
     }
 }
 
+// Early staging (gigl_batch_set_halo_table_dev): the rows a batch needs are known as soon as it is SAMPLED - the roots and
+// every filled tree slot - so their copy does not have to wait for the collation.  This kernel claims a stage slot for
+// every distinct vertex of one id array (atomicCAS on a dense map, winners handed out in blocks like expand_level_kernel);
+// halo_stage_kernel then copies x[slist[s]] -> xs[s] on a second stream while the collation runs on the first, and layer 1
+// gathers through `sslot` instead of the local-id map.
+constexpr int kClaimPerThread = 4;
+__global__ void __launch_bounds__(256) stage_claim_kernel(int64_t n, const int32_t* __restrict__ ids, int64_t n_graph_nodes,
+                                                          int32_t* __restrict__ sslot, int32_t* __restrict__ slist,
+                                                          int32_t* __restrict__ sctr) {
+    __shared__ int s_cnt, s_base;
+    __shared__ int32_t s_stage[256 * kClaimPerThread];
+    const int lane = threadIdx.x & 31;
+    const int64_t per_block = 256 * kClaimPerThread;
+    const int64_t n_iter = (n + per_block - 1) / per_block;
+    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {  // block-uniform
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kClaimPerThread; ++u) {
+            const int64_t i = it * per_block + u * 256 + threadIdx.x;
+            int32_t v = -1;
+            bool won = false;
+            if (i < n) {
+                v = __ldg(ids + i);
+                if (v >= 0 && v < n_graph_nodes && sslot[v] == kLidAbsent) won = atomicCAS(sslot + v, kLidAbsent, kLidPending) == kLidAbsent;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, won);
+            if (m == 0) continue;
+            int slot = 0;
+            if (lane == __ffs(m) - 1) slot = atomicAdd(&s_cnt, __popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+            if (won) s_stage[slot + __popc(m & ((1u << lane) - 1u))] = v;
+        }
+        __syncthreads();
+        const int n_staged = s_cnt;
+        if (threadIdx.x == 0 && n_staged > 0) s_base = atomicAdd(sctr, n_staged);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_staged; i += 256) {
+            const int32_t v = s_stage[i];
+            slist[s_base + i] = v;
+            sslot[v] = s_base + i;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace gigl
 
 // =================================================================================================
@@ -1268,6 +1322,21 @@ struct gigl_batch {
     int64_t level_end_host[GIGL_MAX_HOPS + 2] = {};
     int64_t n_valid_host = 0, n_unique_host = 0;
     bool halo_staging = false;  // layer 1 reads a per-batch copy of the unique nodes' rows (batch_set_halo_staging)
+    // early staging of the halo (batch_set_halo_table): the registered feature table, the dense vertex -> stage slot map, the
+    // staged vertices, their counter, the side stream the claim + copy run on while the collation runs on the ctx stream
+    const float* halo_x = nullptr;
+    int64_t halo_ldx = 0;
+    int32_t halo_F = 0;
+    int32_t* sslot = nullptr;
+    int32_t* slist = nullptr;
+    int64_t slist_cap = 0;
+    int32_t* d_sctr = nullptr;
+    float* xs = nullptr;
+    int64_t lds = 0;
+    cudaStream_t halo_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_claimed = nullptr, ev_staged = nullptr;
+    bool early_staged = false;   // this batch's rows are (being) copied into xs
+    bool stage_dirty = false;    // sslot holds entries of slist[0 .. *d_sctr)
     const int32_t* hot_slot = nullptr;  // halo staging: dense [n_graph_nodes] map vertex -> row of the replicated hot table, -1 = cold
     const float* hot = nullptr;
     int64_t ldh = 0;
@@ -1333,6 +1402,19 @@ static int batch_clear(gigl_batch* b) {
     return GIGL_OK;
 }
 
+// the stage map of the previous batch: cleared on the ctx stream once that batch's copy has finished
+static int stage_clear(gigl_batch* b) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    if (!b->stage_dirty) return GIGL_OK;
+    GIGL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_staged, 0));
+    lid_clear_kernel<<<grid1d(ctx, b->slist_cap, 256), 256, 0, ctx->stream>>>(b->d_sctr, b->slist, b->sslot);
+    GIGL_LAUNCHED(ctx);
+    b->stage_dirty = false;
+    b->early_staged = false;
+    return GIGL_OK;
+}
+
 void batch_destroy(gigl_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
@@ -1344,7 +1426,89 @@ void batch_destroy(gigl_batch* b) {
     if (b->d_cursor) cudaFree(b->d_cursor);
     if (b->h_cursor) cudaFreeHost(b->h_cursor);
     if (b->buf) cudaFree(b->buf);
+    if (b->halo_stream) {
+        cudaStreamSynchronize(b->halo_stream);
+        cudaStreamDestroy(b->halo_stream);
+    }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_claimed) cudaEventDestroy(b->ev_claimed);
+    if (b->ev_staged) cudaEventDestroy(b->ev_staged);
+    if (b->sslot) cudaFree(b->sslot);
+    if (b->slist) cudaFree(b->slist);
+    if (b->d_sctr) cudaFree(b->d_sctr);
     delete b;
+}
+
+static int halo_copy_launch(gigl_batch* b, cudaStream_t st, const int32_t* n_dev, int64_t row_cap, const int32_t* list, const float* x,
+                            int64_t ldx, int F0, float* xb, int64_t ldb) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    // The copy is bound by NVLink round trips, not by SM work; GIGL_HALO_CTAS CTAs per SM (8 = every warp slot: measured best,
+    // 1 / 2 / 8 -> 0.73 / 0.40 / 0.33 ms for 1.07 M rows, half of them remote)
+    static const int halo_ctas = getenv("GIGL_HALO_CTAS") ? atoi(getenv("GIGL_HALO_CTAS")) : 8;
+    const unsigned sgrid = (unsigned)(ctx->sm_count * (halo_ctas > 0 ? halo_ctas : 8));
+    const int32_t* hs = (b->hot_slot && b->hot_F == F0) ? b->hot_slot : nullptr;
+    const bool vec = (F0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0) &&
+                     (!hs || (((reinterpret_cast<uintptr_t>(b->hot) & 15) == 0) && b->ldh % 4 == 0));
+    if (vec && F0 <= 128)
+        halo_stage_kernel<1><<<sgrid, 256, 0, st>>>(n_dev, row_cap, F0, list, x, ldx, xb, ldb, hs, b->hot, b->ldh);
+    else if (vec && F0 <= 256)
+        halo_stage_kernel<2><<<sgrid, 256, 0, st>>>(n_dev, row_cap, F0, list, x, ldx, xb, ldb, hs, b->hot, b->ldh);
+    else if (vec && F0 <= 512)
+        halo_stage_kernel<4><<<sgrid, 256, 0, st>>>(n_dev, row_cap, F0, list, x, ldx, xb, ldb, hs, b->hot, b->ldh);
+    else
+        halo_stage_scalar_kernel<<<sgrid, 256, 0, st>>>(n_dev, row_cap, F0, list, x, ldx, xb, ldb, hs, b->hot, b->ldh);
+    GIGL_LAUNCHED(ctx);
+    return GIGL_OK;
+}
+
+// Forks the halo copy of this batch onto the side stream: claim a stage slot per distinct vertex of the roots and of every
+// tree level, then copy the rows.  The ctx stream goes on with the collation; batch_sage_forward joins on ev_staged.
+static int stage_early(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
+                       const int32_t* const* nbr_dev, int64_t n_slots) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    int rc;
+    const int64_t cap = (n_roots + n_slots < b->n_graph_nodes) ? n_roots + n_slots : b->n_graph_nodes;
+    if (b->slist_cap < cap) {
+        GIGL_CUDA(ctx, cudaStreamSynchronize(b->halo_stream));
+        if (b->slist) GIGL_CUDA(ctx, cudaFree(b->slist));
+        b->slist = nullptr;
+        b->slist_cap = 0;
+        GIGL_CUDA(ctx, cudaMalloc(&b->slist, sizeof(int32_t) * (size_t)cap));
+        b->slist_cap = cap;
+    }
+    const int F0 = b->halo_F;
+    const int64_t ldb = (F0 + 3) & ~3;
+    void* pX = nullptr;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, sizeof(float) * (size_t)cap * ldb, &pX)) != GIGL_OK) return rc;
+    b->xs = (float*)pX;
+    b->lds = ldb;
+    cudaStream_t hs = b->halo_stream;
+    GIGL_CUDA(ctx, cudaEventRecord(b->ev_fork, ctx->stream));   // the sampler's output (and the cleared stage map) are ready
+    GIGL_CUDA(ctx, cudaStreamWaitEvent(hs, b->ev_fork, 0));
+    int th = gigl_timer_begin_on(ctx, GIGL_T_HALO_STAGE, hs);
+    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, sizeof(int32_t), hs));
+    int64_t width = n_roots;
+    const int32_t* level = roots_dev;
+    for (int h = 0; h <= n_hops; ++h) {
+        if (width > 0) {
+            const unsigned grid = grid1d(ctx, ceil_div64(width, kClaimPerThread), 256);
+            stage_claim_kernel<<<grid, 256, 0, hs>>>(width, level, b->n_graph_nodes, b->sslot, b->slist, b->d_sctr);
+            GIGL_LAUNCHED(ctx);
+        }
+        if (h < n_hops) {
+            width *= fanouts[h];
+            level = nbr_dev[h];
+        }
+    }
+    GIGL_CUDA(ctx, cudaEventRecord(b->ev_claimed, hs));  // the tree is not read after this point on the side stream
+    if ((rc = halo_copy_launch(b, hs, b->d_sctr, cap, b->slist, b->halo_x, b->halo_ldx, F0, b->xs, ldb)) != GIGL_OK) return rc;
+    gigl_timer_end_on(ctx, th, hs);
+    GIGL_CUDA(ctx, cudaEventRecord(b->ev_staged, hs));
+    b->early_staged = true;
+    b->stage_dirty = true;
+    return GIGL_OK;
 }
 
 int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
@@ -1357,6 +1521,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CHECK(ctx, fanouts && nbr_dev && (roots_dev || n_roots == 0), "null pointer");
     int tc = gigl_timer_begin(ctx, GIGL_T_COLLATE_MAPS);
     int rc = batch_clear(b);
+    if (rc == GIGL_OK) rc = stage_clear(b);
     gigl_timer_end(ctx, tc);
     if (rc != GIGL_OK) return rc;
     int64_t n_slots = 0, width = n_roots;
@@ -1370,6 +1535,8 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     b->shift = bits_for64(b->n_graph_nodes);
     b->src_mask = (1ULL << b->shift) - 1ULL;
     const int end_bit = 2 * b->shift;
+    if (b->halo_staging && b->halo_x != nullptr && n_roots > 0 && (rc = stage_early(b, roots_dev, n_roots, fanouts, n_hops, nbr_dev, n_slots)) != GIGL_OK)
+        return rc;
     const size_t ns = ((size_t)(n_slots > 0 ? n_slots : 1) + 31) & ~(size_t)31;
     static const bool use_sort = [] {  // GIGL_COLLATE=sort: one global radix sort of the keys (A/B measurements)
         const char* e = getenv("GIGL_COLLATE");
@@ -1498,7 +1665,10 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     const int32_t init[3] = {(int32_t)n_roots, 0, (int32_t)n_roots};
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + 2, &init[0], sizeof(int32_t), cudaMemcpyHostToDevice, st));
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_ctr + kLevelBase, &init[1], sizeof(int32_t) * 2, cudaMemcpyHostToDevice, st));
-    for (int j = 1; j < n_layers; ++j) {
+    // the staged halo copies the row of EVERY batch node, so it needs local ids for all of them: expand through the last
+    // hop here (one host read for all the sizes) instead of in the forward (a second expansion launch + host read)
+    const int n_expand = (b->halo_staging && !b->early_staged) ? (n_hops > n_layers ? n_hops : n_layers) + 1 : n_layers;
+    for (int j = 1; j < n_expand; ++j) {
         if (n_valid > 0) {
             expand_level_kernel<<<grid1d(ctx, ceil_div64(n_valid, kExpandKpt), 256), 256, 0, st>>>(
                 b->d_ctr + kLevelBase, j, n_valid, b->bucketed ? b->d_ctr + kCtrValid : nullptr, b->keys, b->shift, b->src_mask, b->lid, b->list,
@@ -1510,13 +1680,14 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     }
     gigl_timer_end(ctx, th);
     b->n_levels = n_layers;
-    b->n_levels_done = n_layers;
+    b->n_levels_done = n_expand;
     b->n_hops = n_hops;
+    if (b->early_staged) GIGL_CUDA(ctx, cudaStreamWaitEvent(st, b->ev_claimed, 0));  // the tree may be overwritten after this call
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(int32_t) * kCtrInts, cudaMemcpyDeviceToHost, st));
     GIGL_CUDA(ctx, cudaStreamSynchronize(st));
     b->n_unique_host = b->h_ctr[1];
     if (b->bucketed) b->n_valid_host = b->h_ctr[kCtrValid];
-    for (int j = 0; j <= n_layers; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
+    for (int j = 0; j <= n_expand; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
     if (level_sizes_host)
         for (int j = 0; j < n_layers; ++j) level_sizes_host[j] = b->level_end_host[j + 1];
     if (n_edges_host) *n_edges_host = b->n_unique_host;
@@ -1749,7 +1920,17 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
     const float* xin = x_dev;
     int64_t ldx = ldx0;
     bool staged = false;
-    if (b->halo_staging) {
+    const int32_t* stage_map = nullptr;  // layer 1 reads a staged copy through this map (local ids, or the early stage slots)
+    if (b->halo_staging && b->early_staged && b->halo_x == x_dev && b->halo_F == m->dims[0]) {
+        // the copy was forked inside the collation (stage_early): join it here
+        int tw = gigl_timer_begin(ctx, GIGL_T_HALO_WAIT);
+        GIGL_CUDA(ctx, cudaStreamWaitEvent(st, b->ev_staged, 0));
+        gigl_timer_end(ctx, tw);
+        xin = b->xs;
+        ldx = b->lds;
+        stage_map = b->sslot;
+        staged = true;
+    } else if (b->halo_staging) {
         // every batch node gets a local id (the levels above stop at what the root outputs need), then one row per node
         int64_t n_nodes = 0;
         if ((rc = batch_finalize_nodes(b, &n_nodes, nullptr)) != GIGL_OK) return rc;
@@ -1759,27 +1940,12 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         if ((rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, sizeof(float) * (size_t)(n_nodes > 0 ? n_nodes : 1) * ldb, &pX)) != GIGL_OK) return rc;
         float* xb = (float*)pX;
         const int32_t* n_dev = b->d_ctr + kLevelBase + b->n_levels_done;
-        // The copy is bound by NVLink round trips, not by SM work: 2 CTAs per SM x 8 warps x 4 rows in flight keep ~5 MB on
-        // the wire (bandwidth x latency of the link is under 2 MB) and leave the SMs to whatever else is resident - with
-        // several batches in flight (one stream each) the other batch's kernels run under this one.  GIGL_HALO_CTAS: experiments.
-        static const int halo_ctas = getenv("GIGL_HALO_CTAS") ? atoi(getenv("GIGL_HALO_CTAS")) : 2;
-        const unsigned sgrid = (unsigned)(ctx->sm_count * (halo_ctas > 0 ? halo_ctas : 2));
         int th = gigl_timer_begin(ctx, GIGL_T_HALO_STAGE);
-        const int32_t* hs = (b->hot_slot && b->hot_F == F0) ? b->hot_slot : nullptr;
-        const bool vec = (F0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) && (ldx0 % 4 == 0) &&
-                         (!hs || (((reinterpret_cast<uintptr_t>(b->hot) & 15) == 0) && b->ldh % 4 == 0));
-        if (vec && F0 <= 128)
-            halo_stage_kernel<1><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
-        else if (vec && F0 <= 256)
-            halo_stage_kernel<2><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
-        else if (vec && F0 <= 512)
-            halo_stage_kernel<4><<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
-        else
-            halo_stage_scalar_kernel<<<sgrid, 256, 0, st>>>(n_dev, n_nodes, F0, b->list, x_dev, ldx0, xb, ldb, hs, b->hot, b->ldh);
-        GIGL_LAUNCHED(ctx);
+        if ((rc = halo_copy_launch(b, st, n_dev, n_nodes, b->list, x_dev, ldx0, F0, xb, ldb)) != GIGL_OK) return rc;
         gigl_timer_end(ctx, th);
         xin = xb;
         ldx = ldb;
+        stage_map = b->lid;
         staged = true;
     }
     for (int l = 1; l <= n_layers; ++l) {
@@ -1787,7 +1953,7 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
         const int64_t rows = b->level_end_host[n_layers - l + 1];
         const int32_t* rows_dev = b->d_ctr + kLevelBase + (n_layers - l + 1);
         const int64_t lda = m->ldw[l - 1];
-        const int32_t* lidmap = (l == 1 && !staged) ? nullptr : b->lid;
+        const int32_t* lidmap = (l == 1) ? (staged ? stage_map : nullptr) : b->lid;
         float* C = (l == n_layers) ? out_dev : hbuf[l & 1];
         if (l >= 2 && m->pf[l - 1] && (reinterpret_cast<uintptr_t>(xin) & 15) == 0 && ldx % 4 == 0) {
             // ---- project first: Z = h @ Wl^T over every row of the previous level, C = h[rows] @ Wr^T + b, then the
@@ -1830,6 +1996,32 @@ int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_d
 gigl_ctx* batch_ctx(gigl_batch* b) { return b->ctx; }
 
 void batch_set_halo_staging(gigl_batch* b, bool enabled) { b->halo_staging = enabled; }
+
+int batch_set_halo_table(gigl_batch* b, const float* x_dev, int32_t F, int64_t ldx) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    GIGL_CHECK(ctx, x_dev == nullptr || (F >= 1 && ldx >= F), "bad feature table shape");
+    GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (b->halo_stream) GIGL_CUDA(ctx, cudaStreamSynchronize(b->halo_stream));
+    b->halo_x = x_dev;
+    b->halo_F = F;
+    b->halo_ldx = ldx;
+    if (x_dev == nullptr) return GIGL_OK;
+    if (!b->halo_stream) {
+        GIGL_CUDA(ctx, cudaStreamCreateWithFlags(&b->halo_stream, cudaStreamNonBlocking));
+        GIGL_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+        GIGL_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_claimed, cudaEventDisableTiming));
+        GIGL_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_staged, cudaEventDisableTiming));
+        const size_t nn = (size_t)(b->n_graph_nodes > 0 ? b->n_graph_nodes : 1);
+        GIGL_CUDA(ctx, cudaMalloc(&b->sslot, sizeof(int32_t) * nn));
+        GIGL_CUDA(ctx, cudaMalloc(&b->d_sctr, sizeof(int32_t)));
+        GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, sizeof(int32_t), ctx->stream));
+        fill_i32_kernel<<<grid1d(ctx, b->n_graph_nodes, 256), 256, 0, ctx->stream>>>(b->n_graph_nodes, kLidAbsent, b->sslot);
+        GIGL_LAUNCHED(ctx);
+        GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GIGL_OK;
+}
 
 int batch_set_hot_rows(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld) {
     gigl_ctx* ctx = b->ctx;

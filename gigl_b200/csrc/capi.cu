@@ -81,8 +81,22 @@ void gigl_timer_end(gigl_ctx* ctx, int handle) {
     cudaEventRecord(ctx->t_pool[handle].b, ctx->stream);
 }
 
+int gigl_timer_begin_on(gigl_ctx* ctx, int tag, cudaStream_t stream) {
+    if (!ctx->timing) return -1;
+    if (ctx->t_used == ctx->t_cap) timer_flush(ctx);
+    const int h = ctx->t_used++;
+    ctx->t_pool[h].tag = tag;
+    cudaEventRecord(ctx->t_pool[h].a, stream);
+    return h;
+}
+
+void gigl_timer_end_on(gigl_ctx* ctx, int handle, cudaStream_t stream) {
+    if (handle < 0) return;
+    cudaEventRecord(ctx->t_pool[handle].b, stream);
+}
+
 static const char* kTimerNames[GIGL_T_COUNT] = {"sample", "collate_keys", "collate_sort", "collate_maps", "gather_l1",
-                                                "gather_deep", "gemm_l1", "gemm_deep", "gather_full", "gemm_full", "halo_stage"};
+                                                "gather_deep", "gemm_l1", "gemm_deep", "gather_full", "gemm_full", "halo_stage", "halo_wait"};
 
 static int ctx_check_device_error(gigl_ctx* ctx) {
     GIGL_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -810,6 +824,12 @@ int gigl_batch_set_halo_staging(gigl_batch* b, int32_t enabled) {
     if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
     batch_set_halo_staging(b, enabled != 0);
     return GIGL_OK;
+}
+
+int gigl_batch_set_halo_table_dev(gigl_batch* b, const float* x_dev, int32_t F, int64_t ldx) {
+    if (!b) return gigl_fail(nullptr, GIGL_E_INVALID, "null batch");
+    GIGL_CUDA(batch_ctx(b), cudaSetDevice(batch_ctx(b)->device));
+    return batch_set_halo_table(b, x_dev, F, ldx);
 }
 
 int gigl_batch_set_hot_rows_dev(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld) {

@@ -34,6 +34,7 @@ enum {
     GIGL_T_GATHER_FULL,    // full-graph gather (gigl_sage_conv_dev / gigl_gather_mean_dev)
     GIGL_T_GEMM_FULL,
     GIGL_T_HALO_STAGE,     // per-batch copy of the unique nodes' feature rows (sharded feature table: the NVLink halo)
+    GIGL_T_HALO_WAIT,      // early staging: what the ctx stream still waits for the side stream's copy before layer 1
     GIGL_T_COUNT
 };
 
@@ -88,6 +89,8 @@ struct gigl_ctx {
 // Begin / end of a timed phase on the ctx stream (no-ops unless timing is enabled).
 int gigl_timer_begin(gigl_ctx* ctx, int tag);
 void gigl_timer_end(gigl_ctx* ctx, int handle);
+int gigl_timer_begin_on(gigl_ctx* ctx, int tag, cudaStream_t stream);  // the same on a side stream of the context
+void gigl_timer_end_on(gigl_ctx* ctx, int handle, cudaStream_t stream);
 struct gigl_timed {  // RAII helper
     gigl_ctx* ctx;
     int h;
@@ -184,6 +187,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
                   const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes_host, int64_t* n_edges_host);
 int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges);
 void batch_set_halo_staging(gigl_batch* b, bool enabled);
+int batch_set_halo_table(gigl_batch* b, const float* x_dev, int32_t F, int64_t ldx);
 int batch_set_hot_rows(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld);
 int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev);
 int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx, float* out_dev);

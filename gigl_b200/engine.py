@@ -529,10 +529,19 @@ class Batch:
         self._device = roots.device
         return self.level_sizes
 
-    def set_halo_staging(self, enabled: bool) -> None:
+    def set_halo_staging(self, enabled: bool, x=None) -> None:
         """Sharded feature table: copy every unique batch node's row into local HBM once (one row per node over NVLink)
-        and let layer 1 gather from that copy, instead of one peer load per unique edge (gigl_batch_set_halo_staging)."""
+        and let layer 1 gather from that copy, instead of one peer load per unique edge (gigl_batch_set_halo_staging).
+        With the feature table `x` (the tensor later passed to sage_forward) the copy is forked onto a side stream inside
+        collate() and runs under the collation (gigl_batch_set_halo_table_dev)."""
         check(self.ctx._L.gigl_batch_set_halo_staging(self.handle, int(bool(enabled))), self.ctx.handle)
+        if enabled and x is not None:
+            assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+            check(self.ctx._L.gigl_batch_set_halo_table_dev(self.handle, _dp_any(x), x.shape[1], x.stride(0)), self.ctx.handle)
+            self._halo_x = x
+        else:
+            check(self.ctx._L.gigl_batch_set_halo_table_dev(self.handle, None, 0, 0), self.ctx.handle)
+            self._halo_x = None
 
     def set_hot_rows(self, graph: "Graph", x, fraction: float) -> int:
         """Staged halo of a sharded feature table: replicate the rows of the `fraction` of the vertices with the highest

@@ -397,6 +397,16 @@ int gigl_batch_sage_forward_dev(gigl_batch* b, const gigl_sage_model* m, const f
  */
 int gigl_batch_set_halo_staging(gigl_batch* b, int32_t enabled);
 /*
+ * Early staging: registers the feature table the staged halo copies from (x_dev [n_graph_nodes, F], row pitch ldx floats;
+ * the table gigl_batch_sage_forward_dev will be called with; must outlive the batch; NULL unregisters).  With a registered
+ * table gigl_batch_collate_dev forks the halo onto a side stream as soon as it is called: the rows a batch needs are the
+ * roots and every filled slot of the sampled tree, known BEFORE the collation, so a stage slot is claimed per distinct
+ * vertex and the rows are copied (NVLink for the remote ones) WHILE the collation's kernels run on the context's stream;
+ * the forward joins the copy before layer 1 and gathers through the stage-slot map.  Same embeddings bit for bit (the same
+ * rows summed in the same order); the exposed cost of the halo drops by the duration of the collation.
+ */
+int gigl_batch_set_halo_table_dev(gigl_batch* b, const float* x_dev, int32_t F, int64_t ldx);
+/*
  * Hot rows of the staged halo: hot_dev [n_hot, ld] holds a LOCAL copy of the feature rows of the vertices batches meet
  * most often (the caller picks them - gigl_b200.sharding.hot_rows takes the highest-degree vertices - and fills the copy
  * once, from the sharded table), hot_slot_dev [n_graph_nodes] maps a vertex to its row there (-1 = not replicated).

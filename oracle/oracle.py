@@ -657,10 +657,11 @@ def np_collate(roots, nbr, fanouts):
     return node_ids, ei, root_index
 
 
-def batch_sage_embeddings(x_global, roots, nbr, fanouts, layers, f64=False):
+def batch_sage_embeddings(x_global, roots, nbr, fanouts, layers, f64=False, n_graph_nodes=None):
     """Reference inference on one batch: collate, run GraphSAGE on the WHOLE batch graph, select
-    the root rows (graphsage_template_modeling_spec.py:565-577)."""
-    node_ids, ei, root_index = np_collate(roots, nbr, fanouts)
+    the root rows (graphsage_template_modeling_spec.py:565-577).  n_graph_nodes: collate with the C + OpenMP
+    oracle_collate instead of the python dictionaries (same node / edge sets; batches of thousands of roots)."""
+    node_ids, ei, root_index = np_collate(roots, nbr, fanouts) if n_graph_nodes is None else c_collate(n_graph_nodes, roots, nbr, fanouts)
     xb = np.ascontiguousarray(np.asarray(x_global)[node_ids], dtype=np.float32)
     out = sage_model(xb, ei, layers, f64=f64)
     return out[root_index]

@@ -12,6 +12,35 @@ def load_golden(name):
         return json.load(f)
 
 
+def rel_err(got, ref64, ref32=None, rtol=1e-5, what=""):
+    """The float parity bar of north_star ("within 1e-5 rel on fp32 embeddings"), asserted ELEMENT-WISE against the fp64
+    oracle: |got - ref64| <= 1e-5 * |ref64| + atol for every element, the worst element reported on failure.
+
+    atol: an element that cancels to ~0 cannot be relatively exact in fp32 (a K = 200-term dot product of O(1) terms carries
+    ~3e-6 of absolute error), and a fixed 1e-6 fails the REFERENCE's own arithmetic - torch's fp32 index_add_ + F.linear on
+    the (1000, 20000, 100, 47) case of test_gpu_aggregate has 3 of 47000 elements over 1e-5 |ref| + 1e-6 (worst 3.9e-6 at
+    |ref| ~ 0.01).  So the absolute term is calibrated on that arithmetic: with `ref32` (the fp32 oracle's result for the
+    same inputs) atol = 2 x its worst absolute error, never below 1e-6 - "no element further from fp64 than twice the
+    reference's own worst fp32 rounding, plus 1e-5 relative"; without it atol = 1e-5 * mean|ref64|.
+    Returns the max-norm error max|got - ref| / max(1, max|ref|) that the tests also bound by 1e-5."""
+    got = np.asarray(got, dtype=np.float64)
+    ref64 = np.asarray(ref64, dtype=np.float64)
+    assert got.shape == ref64.shape, (got.shape, ref64.shape)
+    if got.size == 0:
+        return 0.0
+    d = np.abs(got - ref64)
+    if ref32 is not None:
+        atol = max(1e-6, 2.0 * float(np.abs(np.asarray(ref32, dtype=np.float64) - ref64).max()))
+    else:
+        atol = rtol * float(np.abs(ref64).mean())
+    slack = d - (rtol * np.abs(ref64) + atol)
+    if (slack > 0).any():
+        w = np.unravel_index(int(np.argmax(slack)), d.shape)
+        raise AssertionError(f"{what or 'embedding'} element {w}: got {got[w]!r}, fp64 reference {ref64[w]!r}, |diff| {d[w]:.3e} > "
+                             f"{rtol:g} * |ref| + {atol:.3g} ({int((slack > 0).sum())} of {d.size} elements over the bound)")
+    return float(d.max() / max(1.0, np.abs(ref64).max()))
+
+
 def powerlaw_edges(n, e, seed, alpha=1.2):
     """Directed multigraph with a heavy-tailed in/out degree (Zipf-like endpoint choice)."""
     rng = np.random.default_rng(seed)

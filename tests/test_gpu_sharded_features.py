@@ -1,5 +1,7 @@
 """GPU: the node-feature table sharded over the GPUs of the box and mapped as one flat array (csrc/shared_table.cu).
-world = 1 runs on any B200; the 2-process test needs two GPUs (`gpurun --gpus 2`) and is skipped otherwise."""
+world = 1 and the two-ranks-on-one-GPU test run on any B200 (the shards of both ranks live on the same device, every other
+step - fd exchange, mapping of the peer's allocation, staged halo, hot rows - is the multi-GPU code path); the two-GPU test
+needs `gpurun --gpus 2` and is skipped otherwise."""
 import os
 import socket
 
@@ -55,9 +57,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, devices):
     try:
-        _worker_body(rank, world, port, q)
+        _worker_body(rank, world, port, q, devices)
     except Exception as e:  # surface the failure in the parent instead of a queue timeout
         import traceback
 
@@ -65,20 +67,24 @@ def _worker(rank, world, port, q):
         raise
 
 
-def _worker_body(rank, world, port, q):
+def _worker_body(rank, world, port, q, devices):
     import torch
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    device = devices[rank]
+    torch.cuda.set_device(device)
+    if len(set(devices)) == world:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", device))
+    else:  # several ranks on one GPU: NCCL refuses duplicate devices; the table itself only needs a barrier
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     from gigl_b200 import Batch, Context, Graph, SageModel
     from gigl_b200.sharding import ShardedFeatureTable, root_range
 
     rng = np.random.default_rng(7)  # same graph / features / weights on every rank
     n, F, fan = 40000, 32, [8, 5]  # F = 32 -> 16384-row mapping granule -> shards of 32768 rows: both ranks own rows
     src, dst, x, layers = _graph_and_model(rng, n, F)
-    ctx = Context.on_torch_stream(rank)
+    ctx = Context.on_torch_stream(device)
     t = ShardedFeatureTable(ctx, n, F, rank, world, tag=str(port))
     lo, hi = t.row_lo, t.row_hi
     assert hi > lo, "test sizes must give every rank rows"
@@ -100,6 +106,9 @@ def _worker_body(rank, world, port, q):
     b.set_halo_staging(True)  # one peer load per unique batch node, then a local gather: the same sums in the same order
     emb_staged = b.sage_forward(model, t.table[:n])
     same = same and bool(torch.equal(emb_staged, emb_replica))
+    n_hot = b.set_hot_rows(g, t.table[:n], 0.25)  # the highest-degree quarter of the rows replicated locally: the same bytes
+    emb_hot = b.sage_forward(model, t.table[:n])
+    same = same and n_hot == n // 4 and bool(torch.equal(emb_hot, emb_replica))
     torch.cuda.synchronize()
     dist.barrier()
     q.put((rank, table_ok, same, int(roots.numel()), ""))
@@ -107,17 +116,28 @@ def _worker_body(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_two_ranks_on_one_gpu_share_one_flat_table():
+    """The whole sharded-table path on a one-GPU box: two processes, each owns a shard (on the same device), exports it,
+    maps the other's, and the direct / staged / hot-row forwards all equal the forward on a private full copy."""
+    _run_two_ranks([0, 0])
+
+
 def test_two_gpu_shards_are_one_flat_table_and_give_identical_embeddings():
     import torch
-    import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _run_two_ranks([0, 1])
+
+
+def _run_two_ranks(devices):
+    import torch.multiprocessing as mp
+
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, devices)) for r in range(world)]
     for p in procs:
         p.start()
     res = []
