@@ -45,6 +45,16 @@ WORKLOADS = {
     "g1b": dict(nodes=100_000_000, pairs=1_000_000_000, F=128, H=128, O=128, directed=True, cfg="configs[3]"),
     # a 1/64 scale model of g1b for quick checks of the same code path
     "g1b-small": dict(nodes=1_562_500, pairs=15_625_000, F=128, H=128, O=128, directed=True, cfg="configs[3] at 1/64 scale"),
+    # BASELINE.json configs[2], MAG240M as the reference runs it (examples/MAG240M/preprocessor_config.py:72-106,
+    # task_config.yaml: papers and authors cast to ONE node type, directed, numNeighborsToSample = 15 for both hops,
+    # F = 1 degree column + 768 paper features, author rows zero behind column 0) at 1/64 of its 244 M nodes / 1.68 B edges;
+    # the 769 columns are stored as 772 (3 zero columns and zero weight columns: the same sums)
+    "mag-like": dict(nodes=3_814_606, pairs=26_250_000, F=772, H=256, O=128, directed=True, fanout="15,15", zero_upper_half=True,
+                     cfg="configs[2] (homogeneous cast, 1/64 scale)"),
+    # BASELINE.json configs[4]: Inferencer full-graph embedding export = layer-wise inference over EVERY node:
+    # N = 1e8 / E = 2e9, 128 -> 128 -> 128; g2b-small = 1/64 scale.  Metric of these two: aggregated-edges/sec.
+    "g2b": dict(nodes=100_000_000, pairs=2_000_000_000, F=128, H=128, O=128, directed=True, layerwise=True, cfg="configs[4]"),
+    "g2b-small": dict(nodes=1_562_500, pairs=31_250_000, F=128, H=128, O=128, directed=True, layerwise=True, cfg="configs[4] at 1/64 scale"),
 }
 
 
@@ -56,7 +66,7 @@ def parse_args(argv=None):
     ap.add_argument("--impl", default="gigl_b200", choices=["gigl_b200", "reference"])
     ap.add_argument("--workload", default="products-like", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=65536, help="roots per step per GPU (both arms)")
-    ap.add_argument("--fanout", default="15,10")
+    ap.add_argument("--fanout", default=None, help="per-hop fanouts (default: the workload's, 15,10 unless it says otherwise)")
     ap.add_argument("--cpu-steps", type=int, default=2, help="timed steps of the cpu_baseline leg of the product arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -267,12 +277,19 @@ def cpu_model():
 
 
 # ----------------------------------------------------------------------------------------------
+def fanout_of(args, wl):
+    return [int(v) for v in (args.fanout or wl.get("fanout", "15,10")).split(",")]
+
+
 def build_inputs_torch(wl, dev, with_features=True):
     """Synthetic graph + features + weights (seeded; identical on every box)."""
     from gigl_b200 import synth
 
     src, dst = synth.rmat_edges_torch(wl["nodes"], wl["pairs"], dev)
     x = synth.features_torch(wl["nodes"], wl["F"], dev) if with_features else None
+    if x is not None and wl.get("zero_upper_half"):  # MAG240M cast: the author rows carry the degree column only
+        x[wl["nodes"] // 2:, 1:] = 0
+        x[:, 769:] = 0
     layers = synth.sage_weights(np.random.default_rng(synth.GEN_SEED), [wl["F"], wl["H"], wl["O"]])
     return src, dst, x, layers
 
@@ -301,7 +318,7 @@ def run_reference(args):
     from oracle import oracle as O
 
     wl = WORKLOADS[args.workload]
-    fan = [int(v) for v in args.fanout.split(",")]
+    fan = fanout_of(args, wl)
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
     src, dst, x, layers = build_inputs_torch(wl, dev)  # input preparation only (torch ops, not timed)
@@ -716,7 +733,7 @@ def roofline_blocks(run: Run, dev_res, cnt, K):
 
 
 def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_full, tag):
-    fan = [int(v) for v in args.fanout.split(",")]
+    fan = fanout_of(args, WORKLOADS[wl_name])
     hot = args.hot_rows if args.hot_rows is not None else float(os.environ.get("GIGL_HOT_ROWS", "0"))
     run = Run(env, wl_name, features, args.halo, args.batch, fan, hot, tag, streams=args.streams)
     wl, B, world = run.wl, run.B, env.world
@@ -766,8 +783,129 @@ def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_fu
     return rec
 
 
+def measure_layerwise(env: Env, args, wl_name, K, W, tag):
+    """BASELINE.json configs[4], the Inferencer's full-graph embedding export as layer-wise inference: a
+    2-layer GraphSAGE over EVERY node, one layer at a time over the whole CSR - rank r computes the rows of its contiguous
+    node range, reads its neighbours' rows from the flat sharded table (input features for layer 1, the hidden rows every
+    rank just wrote for layer 2: the hidden-row halo, peer loads over NVLink) and writes its rows of the next table.  The
+    only collective is the barrier between the layers (a rank may not read hidden rows before their owner wrote them).
+    step = one pass over the graph; metric = aggregated edges / s (every CSR edge reduced once per layer)."""
+    import torch
+
+    from gigl_b200 import Context, Graph, synth
+    from gigl_b200.sharding import ShardedFeatureTable, root_range
+
+    wl, dev, world, rank = WORKLOADS[wl_name], env.dev, env.world, env.rank
+    N, F, H, O = wl["nodes"], wl["F"], wl["H"], wl["O"]
+    ctx = Context.on_torch_stream(env.local)
+    src, dst, _, layers = build_inputs_torch(wl, dev, with_features=False)
+    g = Graph.from_edges_dev(ctx, N, src, dst, is_graph_directed=wl["directed"])
+    del src, dst
+    rowptr, col = g.csr_tensors()
+    lo, hi = root_range(N, rank, world)
+    rows = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(synth.GEN_SEED + 1 + rank)
+    tables = []
+    if world > 1:
+        tx = ShardedFeatureTable(ctx, N, F, rank, world, tag=tag + "x")
+        th = ShardedFeatureTable(ctx, N, H, rank, world, tag=tag + "h")
+        tables = [tx, th]
+        assert (tx.row_lo, tx.row_hi) != (None, None)
+        x_flat, h_flat = tx.table[:N], th.table[:N]
+        x_mine, h_mine = tx.local, th.local
+        own_lo, own_hi = tx.row_lo, tx.row_hi  # the table's shards follow its mapping granule, not root_range
+        lo, hi, rows = own_lo, own_hi, own_hi - own_lo
+    else:
+        x_flat = torch.empty((N, F), dtype=torch.float32, device=dev)
+        h_flat = torch.empty((N, H), dtype=torch.float32, device=dev)
+        x_mine, h_mine = x_flat, h_flat
+    for r0 in range(0, rows, 1 << 22):
+        r1 = min(rows, r0 + (1 << 22))
+        x_mine[r0:r1].copy_(torch.randn(r1 - r0, F, device=dev, dtype=torch.float32, generator=gen))
+    W1 = torch.from_numpy(np.concatenate([layers[0][0], layers[0][2]], axis=1)).to(dev)  # [H, 2F] = [lin_l | lin_r]
+    W2 = torch.from_numpy(np.concatenate([layers[1][0], layers[1][2]], axis=1)).to(dev)
+    b1, b2 = torch.from_numpy(layers[0][1]).to(dev), torch.from_numpy(layers[1][1]).to(dev)
+    out = torch.empty((rows, O), dtype=torch.float32, device=dev)
+    A = torch.empty((rows, 2 * max(F, H)), dtype=torch.float32, device=dev)
+    my_rowptr = rowptr[lo:hi + 1]
+    my_edges = int((rowptr[hi] - rowptr[lo]).item())
+    ctx.sync()
+    env.barrier()
+
+    def layer(table_flat, mine, Fin, Wc, b, relu, dst_rows):
+        agg = ctx.gather_mean(table_flat, my_rowptr, col, n_rows_out=rows)   # mean of the in-neighbours' rows, local or peer
+        a = A[:, : 2 * Fin]
+        a[:, :Fin].copy_(agg)
+        a[:, Fin:].copy_(mine[:rows])
+        ctx.linear(a, Wc, b, relu=relu, out=dst_rows)
+
+    def step():
+        layer(x_flat, x_mine, F, W1, b1, True, h_mine[:rows])
+        if world > 1:
+            env.dist.barrier()  # every rank's hidden rows are written before anyone gathers them
+        layer(h_flat, h_mine, H, W2, b2, False, out)
+        if world > 1:
+            env.dist.barrier()  # ... and read before the next pass overwrites them
+
+    for _ in range(W):
+        step()
+    ctx.set_timing(True)
+    ctx.reset_timing()
+    l0 = ctx.launch_count
+    clocks = ClockSampler(env.local)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    env.barrier()
+    clocks.start()
+    evs[0].record()
+    for i in range(K):
+        step()
+        evs[i + 1].record()
+    env.barrier()
+    ms = max_over_ranks(evs[0].elapsed_time(evs[K]), dev)
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+    clk = clocks.stop()
+    timings = ctx.timings()
+    ctx.set_timing(False)
+    launches = ctx.launch_count - l0
+    total_edges = int(g.n_edges)
+    hbm, _, src_peak = measured_peaks()
+    g_ms = timings.get("gather_full", (0.0, 0))[0] / K / 2  # per layer
+    bytes_layer = my_edges * (4 * F + 4) + (rows + 1) * 8  # SURVEY 8(d) gather terms of bytes_A (the self rows are read by the copy)
+    ach = bytes_layer / (g_ms * 1e-3) / 1e9 if g_ms else None
+    rec = {"metric": "aggregated-edges/sec", "value": 2.0 * total_edges * K / (ms * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": K,
+           "warmup": W, "ms_per_step": ms / K, "ms_per_step_min": float(np.min(per_step)), "ms_per_step_median": float(np.median(per_step)),
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"BASELINE.json {wl['cfg']} shape: {wl_name} synthetic RMAT graph, N={N}, {wl['pairs']} directed edges, "
+                                  f"layer-wise full-graph GraphSAGE {F}->{H}->{O} (every node's embedding)",
+                      "rows_per_gpu": rows, "edges_per_gpu": my_edges,
+                      "residency": "CSR replicated; input and hidden tables sharded by node range and mapped flat (peer loads over NVLink)"
+                                   if world > 1 else "CSR, input, hidden and output tables resident on the one GPU"},
+           "phase_ms_per_step": {k: v[0] / K for k, v in timings.items()},
+           "roofline": {"kernel": "gather_rows_kernel / gather_heavy_kernel (full-graph mean aggregate of one layer)", "bound": "hbm" if world == 1 else "nvlink (remote rows) / hbm",
+                        "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if ach else None, "traffic": None,
+                        "algorithmic_bytes_per_launch": bytes_layer, "formula": "8(d) bytes_A gather terms: e (4 F + 4) + (n + 1) 8",
+                        "ms_per_launch": g_ms, "peak_source": src_peak},
+           "gpu_launches": int(launches), "clocks": clk}
+    for t in tables:
+        ctx.sync()
+        env.barrier()
+    g.close()
+    for t in tables:
+        t.close()
+    ctx.close()
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_ours(args):
     env = Env()
+    if WORKLOADS[args.workload].get("layerwise"):
+        rec = measure_layerwise(env, args, args.workload, args.steps, args.warmup, os.environ.get("MASTER_PORT", "0") + "l")
+        if env.rank == 0:
+            print(json.dumps(rec), flush=True)
+        if env.world > 1:
+            env.dist.destroy_process_group()
+        return
     K, W = args.steps, args.warmup
     features = args.features
     if features == "auto":

@@ -1884,6 +1884,8 @@ static int batch_gather_launch(gigl_batch* b, const int32_t* rows_dev, int64_t r
         GIGL_GATHER_ASYNC(2, 4);
     else if (F <= 512)
         GIGL_GATHER_ASYNC(4, 2);
+    else if (F <= 1024)  // MAG240M-wide rows (F = 769 stored as 772): one 3 KB row per ring slot
+        GIGL_GATHER_ASYNC(8, 1);
     else
         GIGL_GATHER(32);
 #undef GIGL_GATHER

@@ -11,22 +11,37 @@ Reference interfaces mirrored (state_dict keys are PyG 2.5.3's, so checkpoints i
   (keys ``conv{1,2}.lin.weight``, ``conv{1,2}.bias``).
 
 torch is used for parameters, autograd bookkeeping, memory and streams; every FLOP of the layers runs in
-``libgigl_b200.so`` (gather kernels + tcgen05 GEMMs).  There is no CPU path: CPU tensors raise.
+``libgigl_b200.so`` (gather kernels + tcgen05 GEMMs).  The layers are dispatcher ops - ``torch.ops.gigl_b200.sage_conv`` /
+``gcn_conv`` / ``csr_from_coo``, registered by the C++ extension ``csrc/torch_ops.cpp`` (built in-tree as
+``lib/libgigl_b200_torch.so`` over the same C-ABI) with CUDA, Meta and Autograd implementations - so DDP, which the
+reference wraps the model in (``training_process.py:298-303``), and graph capture see ordinary ops.  There is no CPU
+path: CPU tensors raise in the dispatcher, and a missing extension fails the import.
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import List, Optional, Sequence
 
 import torch
 from torch import nn
 
-from . import _capi
-from ._capi import check
-from .engine import Context, _dp
+from .engine import Context
 
 _CTX = {}
+
+
+def _load_torch_ops():
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgigl_b200_torch.so")
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python __graft_entry__.py` (make -C gigl_b200/csrc torch); "
+                          "gigl_b200.nn has no fallback implementation")
+    torch.ops.load_library(path)
+    return torch.ops.gigl_b200
+
+
+_OPS = _load_torch_ops()
 
 
 def context_for(device: torch.device) -> Context:
@@ -55,11 +70,9 @@ class GraphIndex:
         self._t = None
 
     def _build(self, src, dst):
-        rowptr = torch.empty(self.n + 1, dtype=torch.int64, device=src.device)
-        col = torch.empty(max(self.e, 1), dtype=torch.int32, device=src.device)
-        L = self.ctx._L
-        check(L.gigl_csr_from_coo_dev(self.ctx.handle, self.n, self.e, _dp(src), _dp(dst), _dp(rowptr), _dp(col)), self.ctx.handle)
-        return rowptr, col
+        if src.device.type != "cuda":
+            raise RuntimeError("gigl_b200.nn layers run on CUDA tensors only (there is no CPU fallback)")
+        return _OPS.csr_from_coo(src, dst, self.n)
 
     @property
     def transposed(self):
@@ -79,76 +92,6 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise TypeError("gigl_b200.nn computes in fp32")
     return t.contiguous()
-
-
-class _SageConvFn(torch.autograd.Function):
-    @staticmethod
-    def forward(fctx, x, Wl, bl, Wr, gi: GraphIndex, relu: bool, m: int):
-        x, Wl, Wr = _f32c(x), _f32c(Wl), _f32c(Wr)
-        bl = None if bl is None else _f32c(bl)
-        n, F = x.shape
-        O = Wl.shape[0]
-        Fp = (F + 3) & ~3
-        out = torch.empty((m, O), dtype=torch.float32, device=x.device)
-        saved = torch.empty((m, 2 * Fp), dtype=torch.float32, device=x.device)
-        ctx = gi.ctx
-        check(ctx._L.gigl_sage_conv_train_fwd_dev(ctx.handle, n, m, F, O, _dp(gi.rowptr), _dp(gi.col), _dp(x), _dp(Wl), _dp(bl),
-                                                  _dp(Wr), _dp(out), _dp(saved), int(relu)), ctx.handle)
-        fctx.save_for_backward(saved, Wl, Wr, out)
-        fctx.gi, fctx.relu, fctx.dims, fctx.has_bias = gi, relu, (n, m, F, O), bl is not None
-        return out
-
-    @staticmethod
-    def backward(fctx, grad_out):
-        saved, Wl, Wr, out = fctx.saved_tensors
-        gi, relu = fctx.gi, fctx.relu
-        n, m, F, O = fctx.dims
-        grad_out = _f32c(grad_out)
-        need_x, need_w = fctx.needs_input_grad[0], (fctx.needs_input_grad[1] or fctx.needs_input_grad[3])
-        dev = grad_out.device
-        gx = torch.empty((n, F), dtype=torch.float32, device=dev) if need_x else None
-        gWl = torch.empty_like(Wl) if need_w else None
-        gWr = torch.empty_like(Wr) if need_w else None
-        gbl = torch.empty(O, dtype=torch.float32, device=dev) if (fctx.has_bias and fctx.needs_input_grad[2]) else None
-        t_rowptr, t_col = gi.transposed if need_x else (None, None)
-        ctx = gi.ctx
-        check(ctx._L.gigl_sage_conv_bwd_dev(ctx.handle, n, m, F, O, _dp(gi.rowptr), _dp(t_rowptr), _dp(t_col), _dp(saved), _dp(Wl),
-                                            _dp(Wr), _dp(out), _dp(grad_out), _dp(gx), _dp(gWl), _dp(gbl), _dp(gWr), int(relu)),
-              ctx.handle)
-        return gx, gWl, gbl, gWr, None, None, None
-
-
-class _GcnConvFn(torch.autograd.Function):
-    @staticmethod
-    def forward(fctx, x, W, b, gi: GraphIndex, relu: bool):
-        x, W = _f32c(x), _f32c(W)
-        b = None if b is None else _f32c(b)
-        n, F = x.shape
-        O = W.shape[0]
-        out = torch.empty((n, O), dtype=torch.float32, device=x.device)
-        ctx = gi.ctx
-        check(ctx._L.gigl_gcn_conv_dev(ctx.handle, n, F, O, _dp(gi.rowptr), _dp(gi.col), _dp(x), _dp(W), _dp(b), _dp(out), int(relu)),
-              ctx.handle)
-        fctx.save_for_backward(x, W, out)
-        fctx.gi, fctx.relu, fctx.has_bias = gi, relu, b is not None
-        return out
-
-    @staticmethod
-    def backward(fctx, grad_out):
-        x, W, out = fctx.saved_tensors
-        gi = fctx.gi
-        n, F = x.shape
-        O = W.shape[0]
-        grad_out = _f32c(grad_out)
-        dev = grad_out.device
-        gx = torch.empty_like(x) if fctx.needs_input_grad[0] else None
-        gW = torch.empty_like(W) if fctx.needs_input_grad[1] else None
-        gb = torch.empty(O, dtype=torch.float32, device=dev) if (fctx.has_bias and fctx.needs_input_grad[2]) else None
-        t_rowptr, t_col = gi.transposed
-        ctx = gi.ctx
-        check(ctx._L.gigl_gcn_conv_bwd_dev(ctx.handle, n, F, O, _dp(gi.rowptr), _dp(gi.col), _dp(t_rowptr), _dp(t_col), _dp(x), _dp(W),
-                                           _dp(out), _dp(grad_out), _dp(gx), _dp(gW), _dp(gb), int(fctx.relu)), ctx.handle)
-        return gx, gW, gb, None, None
 
 
 class Linear(nn.Module):
@@ -187,7 +130,9 @@ class SAGEConv(nn.Module):
         (what the next layer / the root read-out needs); ``relu`` fuses the inter-layer activation."""
         gi = _as_index(edge_index, x.shape[0])
         m = x.shape[0] if num_rows_out is None else int(num_rows_out)
-        return _SageConvFn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, gi, relu, m)
+        # the CSR by source is what the gradient w.r.t. x gathers over: built (once per GraphIndex) only when needed
+        t_rowptr, t_col = gi.transposed if (x.requires_grad and torch.is_grad_enabled()) else (None, None)
+        return _OPS.sage_conv(_f32c(x), gi.rowptr, gi.col, t_rowptr, t_col, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, relu, m)
 
 
 class GraphSAGE(nn.Module):
@@ -244,7 +189,8 @@ class GCNConv(nn.Module):
 
     def forward(self, x, edge_index, relu: bool = False):
         gi = _as_index(edge_index, x.shape[0])
-        return _GcnConvFn.apply(x, self.lin.weight, self.bias, gi, relu)
+        t_rowptr, t_col = gi.transposed
+        return _OPS.gcn_conv(_f32c(x), gi.rowptr, gi.col, t_rowptr, t_col, self.lin.weight, self.bias, relu)
 
 
 class TwoLayerGCN(nn.Module):

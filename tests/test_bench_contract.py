@@ -38,7 +38,8 @@ def test_both_arms_describe_the_same_config():
     b = bench.parse_args(["--gpus", "2"])
     assert a.batch == b.batch and a.fanout == b.fanout and a.workload == b.workload
     wl = bench.WORKLOADS[a.workload]
-    fan = [int(v) for v in a.fanout.split(",")]
+    fan = bench.fanout_of(a, wl)
+    assert fan == bench.fanout_of(b, wl) == [15, 10]
     assert bench.workload_config(a.workload, wl, fan, min(a.batch, wl["nodes"] // 2), 2) == \
         bench.workload_config(b.workload, wl, fan, min(b.batch, wl["nodes"] // 2), 2)
 
