@@ -415,6 +415,7 @@ class Run:
         self.model = SageModel(self.ctx, self.layers)
         self.batch = Batch(self.ctx, wl["nodes"])
         self.hot_rows = 0
+        self.stage_in_sampler = self.sharded and self.halo == "staged" and os.environ.get("GIGL_HALO_EARLY", "1") not in ("0", "collate")
         if self.sharded and self.halo == "staged":
             self.batch.set_halo_staging(True, x if os.environ.get("GIGL_HALO_EARLY", "1") != "0" else None)
             if hot_rows > 0 and env.world > 1 and hasattr(self.batch, "set_hot_rows"):
@@ -455,7 +456,7 @@ class Run:
             p["nbr"], p["cnt"] = p["g"].sample_khop(roots_dev, self.fan)
             if pipe == 0:
                 self.nbr, self.cnt = p["nbr"], p["cnt"]
-        p["g"].sample_khop(roots_dev, self.fan, out=(p["nbr"], p["cnt"]))
+        p["g"].sample_khop(roots_dev, self.fan, out=(p["nbr"], p["cnt"]), stage_into=p["batch"] if self.stage_in_sampler else None)
         p["batch"].collate(roots_dev, self.fan, p["nbr"], 2)
         p["batch"].sage_forward(p["model"], self.x, out=p["out"])
         return p["batch"].n_edges
@@ -763,13 +764,16 @@ def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_fu
            "roofline": head, "rooflines": blocks, "gpu_launches": dev_res["launches"], "clocks": dev_res["clocks"]}
     if run.sharded and phase_ms.get("halo_stage"):
         F = wl["F"]
-        remote = cnt["nodes"] * (1.0 - 1.0 / world)
-        if run.hot_rows:
-            remote = None  # depends on the hot set; the library's counters would be needed
-        rec["halo"] = {"ms_per_step": phase_ms["halo_stage"], "rows_per_step": cnt["nodes"], "row_bytes": 4 * (-(-F // 32) * 32),
-                       "remote_rows_per_step_if_uniform": cnt["nodes"] * (1.0 - 1.0 / world),
-                       "nvlink_GBps_if_uniform": (remote * 4 * (-(-F // 32) * 32) / (phase_ms["halo_stage"] * 1e-3) / 1e9) if remote else None,
-                       "hot_rows_replicated": run.hot_rows}
+        moved = -(-4 * F // 32) * 32  # bytes of a row that cross the link: whole 32-byte sectors of its F floats
+        remote = None if run.hot_rows else cnt["nodes"] * (1.0 - 1.0 / world)  # with a hot set the share depends on the batch
+        rec["halo"] = {"ms_per_step_on_the_side_stream": phase_ms["halo_stage"], "exposed_wait_ms_per_step": phase_ms.get("halo_wait"),
+                       "rows_per_step": cnt["nodes"], "row_bytes_moved": moved, "remote_rows_per_step_if_uniform": cnt["nodes"] * (1.0 - 1.0 / world),
+                       "nvlink_GBps_if_uniform": (remote * moved / (phase_ms["halo_stage"] * 1e-3) / 1e9) if remote else None,
+                       "hot_rows_replicated": run.hot_rows,
+                       "staging": ("forked level by level inside the sampling call" if run.stage_in_sampler else
+                                   "forked inside the collation" if os.environ.get("GIGL_HALO_EARLY", "1") != "0" else "inside the forward"),
+                       "note": "the copy runs on a side stream beside the sampler / collation kernels, so its own duration is stretched by "
+                               "them; what the step pays is the difference of one_batch_at_a_time to the replicated variant"}
     if want_full and not run.sharded:
         rec["full_graph_aggregate"] = run.full_graph()
     if want_e2e:

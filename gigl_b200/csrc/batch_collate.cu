@@ -30,6 +30,7 @@
 #include <cub/device/device_select.cuh>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace gigl {
 
@@ -1247,6 +1248,53 @@ __global__ void __launch_bounds__(256) halo_stage_scalar_kernel(const int32_t* _
     }
 }
 
+// ---- the same copy on the bulk-copy engine (TMA, 1-D) ------------------------------------------------------------------
+// halo_stage_kernel keeps its bytes in flight in REGISTERS, so a copy that saturates NVLink needs every warp slot of
+// every SM (measured 1 / 2 / 8 CTAs per SM -> 0.73 / 0.40 / 0.33 ms) and nothing else runs beside it.  Here every lane owns
+// one shared-memory slot and one mbarrier and drives rows through them with cp.async.bulk: global (local HBM or a peer's,
+// over NVLink) -> slot, then slot -> the staged table.  The bytes in flight live in shared memory, the kernel occupies
+// four warps and a handful of registers per SM, and the collation kernels of the same batch / the other batch's kernels
+// keep the rest of the SM.
+__global__ void __launch_bounds__(128) halo_stage_tma_kernel(const int32_t* __restrict__ n_nodes_dev, const int32_t* __restrict__ first_dev,
+                                                             int64_t row_cap, uint32_t row_bytes,
+                                                             uint32_t slot_bytes, const int32_t* __restrict__ list,
+                                                             const float* __restrict__ x, int64_t ldx, float* __restrict__ xb,
+                                                             int64_t ldb, const int32_t* __restrict__ hot_slot,
+                                                             const float* __restrict__ hot, int64_t ldh) {
+    extern __shared__ __align__(128) uint8_t s_halo[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_halo);                      // one mbarrier per lane
+    const uint32_t slot = smem_u32(s_halo + 128 * 8 + (size_t)threadIdx.x * slot_bytes);
+    const uint32_t bar = smem_u32(bars + threadIdx.x);
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    int64_t n = *n_nodes_dev;
+    if (n > row_cap) n = row_cap;
+    const int64_t first = first_dev ? (int64_t)*first_dev : 0;  // rows [first, n): the ones claimed since the last copy
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t phase = 0;
+    for (int64_t r = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const int32_t v = __ldg(list + r);
+        const float* src = x + (int64_t)v * ldx;
+        if (hot_slot != nullptr) {
+            const int32_t hs = __ldg(hot_slot + v);
+            if (hs >= 0) src = hot + (int64_t)hs * ldh;
+        }
+        // the slot's previous store must have read it out
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_expect_tx(bar, row_bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(slot), "l"(src),
+                     "r"(row_bytes), "r"(bar)
+                     : "memory");
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(xb + r * ldb), "r"(slot), "r"(row_bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // Early staging (gigl_batch_set_halo_table_dev): the rows a batch needs are known as soon as it is SAMPLED - the roots and
 // every filled tree slot - so their copy does not have to wait for the collation.  This kernel claims a stage slot for
 // every distinct vertex of one id array (atomicCAS on a dense map, winners handed out in blocks like expand_level_kernel);
@@ -1336,6 +1384,8 @@ struct gigl_batch {
     cudaStream_t halo_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_claimed = nullptr, ev_staged = nullptr;
     bool early_staged = false;   // this batch's rows are (being) copied into xs
+    bool prestaged = false;      // ... level by level from inside the sampling call (batch_stage_begin / _level / _end)
+    bool stage_open = false;
     bool stage_dirty = false;    // sslot holds entries of slist[0 .. *d_sctr)
     const int32_t* hot_slot = nullptr;  // halo staging: dense [n_graph_nodes] map vertex -> row of the replicated hot table, -1 = cold
     const float* hot = nullptr;
@@ -1440,7 +1490,7 @@ void batch_destroy(gigl_batch* b) {
 }
 
 static int halo_copy_launch(gigl_batch* b, cudaStream_t st, const int32_t* n_dev, int64_t row_cap, const int32_t* list, const float* x,
-                            int64_t ldx, int F0, float* xb, int64_t ldb) {
+                            int64_t ldx, int F0, float* xb, int64_t ldb, const int32_t* first_dev = nullptr) {
     using namespace gigl;
     gigl_ctx* ctx = b->ctx;
     // The copy is bound by NVLink round trips, not by SM work; GIGL_HALO_CTAS CTAs per SM (8 = every warp slot: measured best,
@@ -1450,6 +1500,19 @@ static int halo_copy_launch(gigl_batch* b, cudaStream_t st, const int32_t* n_dev
     const int32_t* hs = (b->hot_slot && b->hot_F == F0) ? b->hot_slot : nullptr;
     const bool vec = (F0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0) &&
                      (!hs || (((reinterpret_cast<uintptr_t>(b->hot) & 15) == 0) && b->ldh % 4 == 0));
+    // bulk-copy form: rows of whole 16-byte units, 16-byte aligned at both ends, a slot per lane within 64 KB per CTA
+    static const bool use_tma = !(getenv("GIGL_HALO_TMA") && getenv("GIGL_HALO_TMA")[0] == '0');
+    static const int tma_ctas = getenv("GIGL_HALO_TMA_CTAS") ? atoi(getenv("GIGL_HALO_TMA_CTAS")) : 1;
+    const uint32_t row_bytes = (uint32_t)F0 * 4u, slot_bytes = (row_bytes + 127u) & ~127u;
+    if (use_tma && vec && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) && slot_bytes <= 512) {
+        const size_t shm = 128 * 8 + 128 * (size_t)slot_bytes + 128;
+        GIGL_CUDA(ctx, cudaFuncSetAttribute(halo_stage_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        halo_stage_tma_kernel<<<(unsigned)(ctx->sm_count * (tma_ctas > 0 ? tma_ctas : 1)), 128, shm, st>>>(n_dev, first_dev, row_cap, row_bytes, slot_bytes, list,
+                                                                                                  x, ldx, xb, ldb, hs, b->hot, b->ldh);
+        GIGL_LAUNCHED(ctx);
+        return GIGL_OK;
+    }
+    GIGL_CHECK(ctx, first_dev == nullptr, "level-by-level staging needs the bulk-copy form of the halo (rows of at most 512 bytes, 16-byte aligned)");
     if (vec && F0 <= 128)
         halo_stage_kernel<1><<<sgrid, 256, 0, st>>>(n_dev, row_cap, F0, list, x, ldx, xb, ldb, hs, b->hot, b->ldh);
     else if (vec && F0 <= 256)
@@ -1488,7 +1551,7 @@ static int stage_early(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots,
     GIGL_CUDA(ctx, cudaEventRecord(b->ev_fork, ctx->stream));   // the sampler's output (and the cleared stage map) are ready
     GIGL_CUDA(ctx, cudaStreamWaitEvent(hs, b->ev_fork, 0));
     int th = gigl_timer_begin_on(ctx, GIGL_T_HALO_STAGE, hs);
-    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, sizeof(int32_t), hs));
+    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, 2 * sizeof(int32_t), hs));
     int64_t width = n_roots;
     const int32_t* level = roots_dev;
     for (int h = 0; h <= n_hops; ++h) {
@@ -1511,6 +1574,71 @@ static int stage_early(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots,
     return GIGL_OK;
 }
 
+// Level-by-level staging, driven by the sampling call (gigl_sample_khop_staged_dev): hop h's rows are claimed and copied on
+// the side stream as soon as hop h is sampled - the roots' and hop-1 rows travel under the hop-2 sampling kernel, the hop-2
+// rows under the collation.  d_sctr[0] = claimed so far, d_sctr[1] = copied so far.
+bool batch_stages_early(const gigl_batch* b, const float* x_dev) {
+    return b->halo_staging && b->halo_x != nullptr && b->halo_x == x_dev;
+}
+
+int batch_stage_begin(gigl_batch* b, int64_t n_roots, const int32_t* fanouts, int32_t n_hops) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    int rc;
+    if ((rc = stage_clear(b)) != GIGL_OK) return rc;
+    int64_t n_slots = 0, width = n_roots;
+    for (int h = 0; h < n_hops; ++h) {
+        width *= fanouts[h];
+        n_slots += width;
+    }
+    const int64_t cap = (n_roots + n_slots < b->n_graph_nodes) ? n_roots + n_slots : b->n_graph_nodes;
+    if (b->slist_cap < cap) {
+        GIGL_CUDA(ctx, cudaStreamSynchronize(b->halo_stream));
+        if (b->slist) GIGL_CUDA(ctx, cudaFree(b->slist));
+        b->slist = nullptr;
+        b->slist_cap = 0;
+        GIGL_CUDA(ctx, cudaMalloc(&b->slist, sizeof(int32_t) * (size_t)cap));
+        b->slist_cap = cap;
+    }
+    const int64_t ldb = (b->halo_F + 3) & ~3;
+    void* pX = nullptr;
+    if ((rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, sizeof(float) * (size_t)cap * ldb, &pX)) != GIGL_OK) return rc;
+    b->xs = (float*)pX;
+    b->lds = ldb;
+    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, 2 * sizeof(int32_t), ctx->stream));
+    b->stage_open = true;
+    b->stage_dirty = true;
+    return GIGL_OK;
+}
+
+// ids: one level of the tree (or the roots), just written on the ctx stream
+int batch_stage_level(gigl_batch* b, const int32_t* ids_dev, int64_t n) {
+    using namespace gigl;
+    gigl_ctx* ctx = b->ctx;
+    GIGL_CHECK(ctx, b->stage_open, "batch_stage_begin first");
+    if (n <= 0) return GIGL_OK;
+    cudaStream_t hs = b->halo_stream;
+    GIGL_CUDA(ctx, cudaEventRecord(b->ev_fork, ctx->stream));
+    GIGL_CUDA(ctx, cudaStreamWaitEvent(hs, b->ev_fork, 0));
+    int th = gigl_timer_begin_on(ctx, GIGL_T_HALO_STAGE, hs);
+    stage_claim_kernel<<<grid1d(ctx, ceil_div64(n, kClaimPerThread), 256), 256, 0, hs>>>(n, ids_dev, b->n_graph_nodes, b->sslot, b->slist, b->d_sctr);
+    GIGL_LAUNCHED(ctx);
+    GIGL_CUDA(ctx, cudaEventRecord(b->ev_claimed, hs));  // `ids` is not read after this point on the side stream
+    int rc = halo_copy_launch(b, hs, b->d_sctr, b->slist_cap, b->slist, b->halo_x, b->halo_ldx, b->halo_F, b->xs, b->lds, b->d_sctr + 1);
+    if (rc != GIGL_OK) return rc;
+    GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_sctr + 1, b->d_sctr, sizeof(int32_t), cudaMemcpyDeviceToDevice, hs));  // copied = claimed
+    gigl_timer_end_on(ctx, th, hs);
+    GIGL_CUDA(ctx, cudaEventRecord(b->ev_staged, hs));
+    return GIGL_OK;
+}
+
+int batch_stage_end(gigl_batch* b) {
+    b->stage_open = false;
+    b->early_staged = true;
+    b->prestaged = true;
+    return GIGL_OK;
+}
+
 int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
                   const int32_t* const* nbr_dev, int32_t n_layers, int64_t* level_sizes_host, int64_t* n_edges_host) {
     using namespace gigl;
@@ -1521,7 +1649,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     GIGL_CHECK(ctx, fanouts && nbr_dev && (roots_dev || n_roots == 0), "null pointer");
     int tc = gigl_timer_begin(ctx, GIGL_T_COLLATE_MAPS);
     int rc = batch_clear(b);
-    if (rc == GIGL_OK) rc = stage_clear(b);
+    if (rc == GIGL_OK && !b->prestaged) rc = stage_clear(b);  // prestaged: the sampling call already staged THIS batch
     gigl_timer_end(ctx, tc);
     if (rc != GIGL_OK) return rc;
     int64_t n_slots = 0, width = n_roots;
@@ -1535,7 +1663,9 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     b->shift = bits_for64(b->n_graph_nodes);
     b->src_mask = (1ULL << b->shift) - 1ULL;
     const int end_bit = 2 * b->shift;
-    if (b->halo_staging && b->halo_x != nullptr && n_roots > 0 && (rc = stage_early(b, roots_dev, n_roots, fanouts, n_hops, nbr_dev, n_slots)) != GIGL_OK)
+    if (b->prestaged)
+        b->prestaged = false;  // consumed: early_staged stays set for the forward
+    else if (b->halo_staging && b->halo_x != nullptr && n_roots > 0 && (rc = stage_early(b, roots_dev, n_roots, fanouts, n_hops, nbr_dev, n_slots)) != GIGL_OK)
         return rc;
     const size_t ns = ((size_t)(n_slots > 0 ? n_slots : 1) + 31) & ~(size_t)31;
     static const bool use_sort = [] {  // GIGL_COLLATE=sort: one global radix sort of the keys (A/B measurements)
@@ -2016,8 +2146,8 @@ int batch_set_halo_table(gigl_batch* b, const float* x_dev, int32_t F, int64_t l
         GIGL_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_staged, cudaEventDisableTiming));
         const size_t nn = (size_t)(b->n_graph_nodes > 0 ? b->n_graph_nodes : 1);
         GIGL_CUDA(ctx, cudaMalloc(&b->sslot, sizeof(int32_t) * nn));
-        GIGL_CUDA(ctx, cudaMalloc(&b->d_sctr, sizeof(int32_t)));
-        GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, sizeof(int32_t), ctx->stream));
+        GIGL_CUDA(ctx, cudaMalloc(&b->d_sctr, 2 * sizeof(int32_t)));
+        GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, 2 * sizeof(int32_t), ctx->stream));
         fill_i32_kernel<<<grid1d(ctx, b->n_graph_nodes, 256), 256, 0, ctx->stream>>>(b->n_graph_nodes, kLidAbsent, b->sslot);
         GIGL_LAUNCHED(ctx);
         GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -473,6 +473,35 @@ int gigl_sample_khop_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_root
     return khop_sample_launch(g, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
 }
 
+// Samples hop by hop and forks the halo staging of every level as soon as it exists (batch_stage_*): the roots' and hop-h
+// rows travel over NVLink while hop h + 1 is being sampled, the last hop's rows while the batch is collated.
+static int khop_sample_staged(gigl_graph* g, gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
+                              int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev, int32_t* const* cnt_dev) {
+    int rc;
+    if ((rc = batch_stage_begin(b, n_roots, fanouts, n_hops)) != GIGL_OK) return rc;
+    if ((rc = batch_stage_level(b, roots_dev, n_roots)) != GIGL_OK) return rc;
+    int64_t width = n_roots;
+    for (int h = 1; h <= n_hops; ++h) {
+        if ((rc = khop_sample_launch(g, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev, h, h)) != GIGL_OK) return rc;
+        width *= fanouts[h - 1];
+        if ((rc = batch_stage_level(b, nbr_dev[h - 1], width)) != GIGL_OK) return rc;
+    }
+    return batch_stage_end(b);
+}
+
+int gigl_sample_khop_staged_dev(gigl_graph* g, gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                                int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
+                                int32_t* const* cnt_dev) {
+    if (!g || !b) return gigl_fail(g ? g->ctx : nullptr, GIGL_E_INVALID, "null graph / batch");
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, batch_ctx(b) == ctx, "graph and batch must share one context");
+    GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS && fanouts && nbr_dev && cnt_dev, "bad sampling arguments");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!batch_stages_early(b, g->x) || n_roots <= 0)  // nothing registered to stage from: plain sampling
+        return khop_sample_launch(g, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
+    return khop_sample_staged(g, b, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
+}
+
 int gigl_sample_op_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
                        const int32_t* const* chain_nbr_dev, int32_t base_seed, int32_t call_no, int32_t* nbr_out_dev,
                        int32_t* cnt_out_dev) {
@@ -923,7 +952,11 @@ static int infer_khop_sage_host_impl(gigl_graph* g, gigl_batch* b, const gigl_sa
         GIGL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pack_ready, cudaEventDisableTiming));
         GIGL_CUDA(ctx, cudaMallocHost(&ctx->h_pack_total, sizeof(int32_t)));
     }
-    if ((rc = khop_sample_launch(g, d, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev)) != GIGL_OK) return rc;
+    if (batch_stages_early(b, g->x) && n_roots > 0)
+        rc = khop_sample_staged(g, b, d, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
+    else
+        rc = khop_sample_launch(g, d, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev);
+    if (rc != GIGL_OK) return rc;
     if (dbg) cudaEventRecord(ev[2], ctx->stream);
     int32_t* goff_dev = nullptr;
     uint8_t* u8_dev = nullptr;

@@ -188,6 +188,10 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
 int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges);
 void batch_set_halo_staging(gigl_batch* b, bool enabled);
 int batch_set_halo_table(gigl_batch* b, const float* x_dev, int32_t F, int64_t ldx);
+bool batch_stages_early(const gigl_batch* b, const float* x_dev);
+int batch_stage_begin(gigl_batch* b, int64_t n_roots, const int32_t* fanouts, int32_t n_hops);
+int batch_stage_level(gigl_batch* b, const int32_t* ids_dev, int64_t n);
+int batch_stage_end(gigl_batch* b);
 int batch_set_hot_rows(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld);
 int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev);
 int batch_sage_forward(gigl_batch* b, const gigl_sage_model* m, const float* x_dev, int64_t ldx, float* out_dev);

@@ -302,9 +302,11 @@ class Graph:
                                                 pn, pc), self.ctx.handle)
         return nbr, cnt
 
-    def sample_khop(self, roots, fanouts: Sequence[int], base_seed: int = 42, first_call_no: int = 1, out=None):
+    def sample_khop(self, roots, fanouts: Sequence[int], base_seed: int = 42, first_call_no: int = 1, out=None, stage_into=None):
         """Device variant: ``roots`` int32 CUDA tensor -> (nbr, cnt) lists of int32 CUDA tensors.
-        Asynchronous; device-side errors surface at ``ctx.sync()``."""
+        Asynchronous; device-side errors surface at ``ctx.sync()``.  ``stage_into``: the :class:`Batch` this sample is
+        collated into next - with a halo table registered there (``Batch.set_halo_staging(True, x)``) every sampled level's
+        feature rows start their way over NVLink while the next hop is sampled (gigl_sample_khop_staged_dev)."""
         import torch
 
         assert roots.dtype == torch.int32
@@ -320,8 +322,12 @@ class Graph:
             nbr, cnt = out
         pn = (C.c_void_p * max(n_hops, 1))(*[t.data_ptr() for t in nbr])
         pc = (C.c_void_p * max(n_hops, 1))(*[t.data_ptr() for t in cnt])
-        check(self.ctx._L.gigl_sample_khop_dev(self.handle, _dp(roots), n_roots, _hp(fan), n_hops, base_seed, first_call_no,
-                                               pn, pc), self.ctx.handle)
+        if stage_into is not None:
+            check(self.ctx._L.gigl_sample_khop_staged_dev(self.handle, stage_into.handle, _dp(roots), n_roots, _hp(fan), n_hops, base_seed,
+                                                          first_call_no, pn, pc), self.ctx.handle)
+        else:
+            check(self.ctx._L.gigl_sample_khop_dev(self.handle, _dp(roots), n_roots, _hp(fan), n_hops, base_seed, first_call_no,
+                                                   pn, pc), self.ctx.handle)
         return nbr, cnt
 
     def sample_op(self, roots, chain_fanouts: Sequence[int], chain_nbr: Sequence, call_no: int, base_seed: int = 42):

@@ -407,6 +407,16 @@ int gigl_batch_set_halo_staging(gigl_batch* b, int32_t enabled);
  */
 int gigl_batch_set_halo_table_dev(gigl_batch* b, const float* x_dev, int32_t F, int64_t ldx);
 /*
+ * gigl_sample_khop_dev that starts the halo even earlier: `b` is the batch workspace the sample will be collated into next,
+ * with a table registered by gigl_batch_set_halo_table_dev that is also the graph's feature table.  The hops are sampled one
+ * launch sequence at a time and after each one the rows of the level just sampled (first the roots) are claimed and copied
+ * on the batch's side stream: hop h's rows cross NVLink under the sampling of hop h + 1, the last hop's under the collation.
+ * Without a registered table it is gigl_sample_khop_dev.  Same index sets, same embeddings.
+ */
+int gigl_sample_khop_staged_dev(gigl_graph* g, gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
+                                int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
+                                int32_t* const* cnt_dev);
+/*
  * Hot rows of the staged halo: hot_dev [n_hot, ld] holds a LOCAL copy of the feature rows of the vertices batches meet
  * most often (the caller picks them - gigl_b200.sharding.hot_rows takes the highest-degree vertices - and fills the copy
  * once, from the sharded table), hot_slot_dev [n_graph_nodes] maps a vertex to its row there (-1 = not replicated).

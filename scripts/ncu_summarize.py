@@ -4,7 +4,7 @@
 
 Writes profiles/<tag>_launches.md (every kernel's share of the profiled command, from the
 `--metrics gpu__time_duration.sum` pass), profiles/<tag>_kernels.md (the `--set full` metrics of the
-hot kernels) and profiles/traffic.json (DRAM bytes per launch of the layer-1 gather, read by bench.py)."""
+hot kernels).  The DRAM bytes bench.py reports as `roofline.traffic` come from scripts/ncu_traffic.py (profiles/r2_traffic.json)."""
 import collections
 import csv
 import json
@@ -67,25 +67,10 @@ def gb(v, u):
     return v * {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}.get(u, 1.0)
 
 
-traffic = collections.defaultdict(list)
 with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md"), "w") as f:
     f.write(f"# {tag}: `ncu --set full --clock-control none` of the hot kernels inside `bench.py` (products-like, B=65536, fanout [15,10])\n\n")
     f.write("| kernel | " + " | ".join(w for w, _ in idx) + " |\n|---|" + "---:|" * len(idx) + "\n")
     for r in rows[2:]:
         name = re.sub(r"\(.*", "", r[ni]).replace("void ", "")
         f.write(f"| `{name[:60]}` | " + " | ".join(f"{r[i]} {units[i]}" for _, i in idx) + " |\n")
-        rd_i, wr_i, g_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("launch__grid_size")
-        traffic[name].append((int(float(r[g_i])), gb(r[rd_i], units[rd_i]) + gb(r[wr_i], units[wr_i])))
-# layer-1 gather = the LARGER of the two main gather launches per step (+ its parts launch)
-out = {}
-main = [t for k, v in traffic.items() if ("batch_gather_kernel" in k or "batch_gather_async_kernel" in k) for t in v]
-parts = [t for k, v in traffic.items() if "batch_gather_parts" in k for t in v]
-if main:
-    l1 = max(t[1] for t in main)
-    p1 = max((t[1] for t in parts), default=0.0)
-    out["gather_l1_dram_bytes_per_launch"] = (l1 + p1) * 1e9
-    out["gather_l1_main_kernel_dram_GB"] = l1
-    out["gather_l1_parts_kernel_dram_GB"] = p1
-    out["source"] = f"profiles/{tag}_kernels.md"
-json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
-print(json.dumps(out))
+print("wrote", f"profiles/{tag}_launches.md", f"profiles/{tag}_kernels.md")

@@ -106,6 +106,17 @@ def _worker_body(rank, world, port, q, devices):
     b.set_halo_staging(True)  # one peer load per unique batch node, then a local gather: the same sums in the same order
     emb_staged = b.sage_forward(model, t.table[:n])
     same = same and bool(torch.equal(emb_staged, emb_replica))
+    # early staging: the copy forked inside the collation, then level by level from inside the sampling call
+    flat = t.table[:n]
+    g.set_features(flat)
+    b2 = Batch(ctx, n)
+    b2.set_halo_staging(True, flat)
+    for staged_sampler in (False, True, True):  # twice: the second run re-uses (and must have cleared) the stage maps
+        nbr2, _ = g.sample_khop(roots, fan, stage_into=b2 if staged_sampler else None)
+        for a_, b_ in zip(nbr, nbr2):
+            same = same and bool(torch.equal(a_, b_))
+        b2.collate(roots, fan, nbr2, 2)
+        same = same and bool(torch.equal(b2.sage_forward(model, flat), emb_replica))
     n_hot = b.set_hot_rows(g, t.table[:n], 0.25)  # the highest-degree quarter of the rows replicated locally: the same bytes
     emb_hot = b.sage_forward(model, t.table[:n])
     same = same and n_hot == n // 4 and bool(torch.equal(emb_hot, emb_replica))
