@@ -386,20 +386,35 @@ __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& 
 // and every failure (too few / too many candidates, a 26-bit tie) is redone from the level's whole run with exact
 // 64-bit keys; a level with fewer than f keys inside the window (probability < 1e-4 at s >> j = 32, vanishing above)
 // falls through to the streaming scan.  Bit-exact by construction: the same keys, the same (key, idx) order.
-__device__ __forceinline__ void lad_plan(const HopArgs& a, uint32_t base, uint32_t s, int f, int& lvl, uint32_t& beg, uint32_t& end) {
+// tmax: a truncated key is a candidate iff it is <= tmax (2^32 - 1 = every entry inside the window)
+__device__ __forceinline__ void lad_plan(const HopArgs& a, uint32_t base, uint32_t s, int f, int& lvl, uint32_t& beg, uint32_t& end,
+                                         uint32_t& tmax) {
     lvl = -1;
     beg = end = 0;
+    tmax = 0xFFFFFFFFu;
     if (a.lad_limit == 0 || s == 0 || (uint64_t)base + (uint64_t)s >= a.lad_limit) return;
     const uint32_t lo = base + 1u, hi = base + s;
     const int wide = f <= 16 ? 0 : 1;  // fanouts over 16 read a level with twice the entries (s >> j in [64, 128))
-    if (s < (64u << wide)) {
+    int j = 0;
+    if (s >= (64u << wide)) {
+        j = 26 - __clz((int)s) - wide;  // s >> j in [32, 64)
+        if (j > a.lad_levels) j = a.lad_levels;
+    }
+    {   // expected-count threshold on the level's truncated keys: m / (s >> j) of them are wanted
+        float m = (float)f + fmaxf(14.f, 1.2f * (float)f);
+        if (m > 48.f) m = 48.f;
+        const float r = m * (float)(1u << j) / (float)s;
+        if (r < 1.f) {
+            const uint32_t t = __float2uint_rz(r * 4294967296.f);
+            tmax = t ? t - 1u : 0u;
+        }
+    }
+    if (j == 0) {
         lvl = 0;
         beg = lo;
         end = hi + 1u;
         return;
     }
-    int j = 26 - __clz((int)s) - wide;  // s >> j in [32, 64)
-    if (j > a.lad_levels) j = a.lad_levels;
     lvl = j;
     const uint32_t* bs = a.lad_bs[j];
     beg = __ldg(bs + (lo >> j));
@@ -431,21 +446,17 @@ __device__ __forceinline__ bool push_cands32(uint32_t* __restrict__ ctk, uint32_
 // `first` = lad_load of the run's first 32 entries (the caller has it in flight while the previous row is selected).
 // Returns true with best.idx[0] of lane l < min(s, f) = window position of the l-th smallest key.
 __device__ __forceinline__ bool select_ladder(const HopArgs& a, WarpTopK<1>& best, uint32_t s, uint32_t base, int f, int lane,
-                                              int lvl, uint32_t beg, uint32_t end, uint64_t first, uint32_t* ctk, uint32_t* cx) {
+                                              int lvl, uint32_t beg, uint32_t end, uint32_t tmax, uint64_t first, uint32_t* ctk,
+                                              uint32_t* cx) {
     const uint32_t lo = base + 1u;
     const int need = (int)(s < (uint32_t)f ? s : (uint32_t)f);
     if (need < 32) {
-        float m = (float)f + fmaxf(14.f, 1.2f * (float)f);
-        if (m > 48.f) m = 48.f;
-        const float r = m * (float)(1u << lvl) / (float)s;  // wanted share of the level's entries inside the window
-        const bool all = !(r < 1.f);
-        const uint32_t Ttk = all ? 0xFFFFFFFFu : __float2uint_rz(r * 4294967296.f);
         int c = 0;
         bool ok = true;
         for (uint32_t e0 = beg; e0 < end; e0 += 32) {
             const uint64_t ent = (e0 == beg) ? first : lad_load(a, lvl, e0 + lane, end);
             const uint32_t x = (uint32_t)ent, tk = (uint32_t)(ent >> 32);
-            const bool cand = (x - lo) < s && (all || tk < Ttk);
+            const bool cand = (x - lo) < s && tk <= tmax;
             if (!push_cands32(ctk, cx, c, cand, tk, x, lane, kCandCap)) {
                 ok = false;
                 break;
@@ -453,7 +464,7 @@ __device__ __forceinline__ bool select_ladder(const HopArgs& a, WarpTopK<1>& bes
         }
         if (ok && c >= need) {
             __syncwarp();
-            const int nb = all ? 32 : 32 - __clz((int)Ttk);
+            const int nb = 32 - __clz((int)tmax);  // candidates are <= tmax: their bits above its highest are zero
             const int shift = nb > 26 ? nb - 26 : 0;
             uint32_t v0;
             ok = order_cands_u32(c, need, lane, [&](int slot) { return ctk[slot] >> shift; }, v0);
@@ -530,8 +541,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop
     }
     const uint32_t base = ssum + (uint32_t)a.cur_seed;
     int lvl = -1;
-    uint32_t e_beg = 0, e_end = 0;
-    if (KPL == 1) lad_plan(a, base, (uint32_t)size, f, lvl, e_beg, e_end);
+    uint32_t e_beg = 0, e_end = 0, tmax = 0;
+    if (KPL == 1) lad_plan(a, base, (uint32_t)size, f, lvl, e_beg, e_end, tmax);
     if (size > kHeavyThreshold && a.heavy_list != nullptr && lvl < 0) {
         int slot = 0;
         if (lane == 0) slot = atomicAdd(a.heavy_count, 1);
@@ -550,7 +561,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop
         uint32_t* ctk = reinterpret_cast<uint32_t*>(s_cand[w]);
         bool done = false;
         if (lvl >= 0)
-            done = select_ladder(a, best, (uint32_t)size, base, f, lane, lvl, e_beg, e_end, lad_load(a, lvl, e_beg + lane, e_end), ctk,
+            done = select_ladder(a, best, (uint32_t)size, base, f, lane, lvl, e_beg, e_end, tmax, lad_load(a, lvl, e_beg + lane, e_end), ctk,
                                  ctk + kCandCapWide);
         if (!done && (size <= 32 || !select_threshold(a, best, size, base, f, lane, s_cand[w], reinterpret_cast<int32_t*>(s_cand[w] + kCandCap)))) {
             best.init();
@@ -576,7 +587,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop
 // Same keys, same (key, idx) order, same outputs as khop_hop_kernel.
 constexpr int kTileRows = 32;
 #ifndef KHOP_TILE_MIN_BLOCKS
-#define KHOP_TILE_MIN_BLOCKS 6
+#define KHOP_TILE_MIN_BLOCKS 5  // 46 registers, 40 resident warps per SM: measured 6 / 5 / 4 / 3 blocks -> 0.367 / 0.361 / 0.361 / 0.380 ms per step
 #endif
 
 template <int MAXF>
@@ -654,8 +665,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) kho
     const uint32_t base = ssum + (uint32_t)a.cur_seed;
     const uint32_t size32 = (uint32_t)size;  // state == 1: size < 2^31
     int lvl = -1;
-    uint32_t e_beg = 0, e_end = 0;
-    if (state == 1) lad_plan(a, base, size32, f, lvl, e_beg, e_end);
+    uint32_t e_beg = 0, e_end = 0, tmax = 0;
+    if (state == 1) lad_plan(a, base, size32, f, lvl, e_beg, e_end, tmax);
     if (state == 1 && lvl < 0 && size > kHeavyThreshold && a.heavy_list != nullptr) {
         const int slot = atomicAdd(a.heavy_count, 1);
         if (slot < a.heavy_cap) {
@@ -692,7 +703,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) kho
         WarpTopK<1> best;
         best.init();
         bool done = false;
-        if (r_code >> 2) done = select_ladder(a, best, r_size, r_base, f, lane, (r_code >> 2) - 1, r_beg, r_end, cur, ctk, cx);
+        if (r_code >> 2)
+            done = select_ladder(a, best, r_size, r_base, f, lane, (r_code >> 2) - 1, r_beg, r_end, __shfl_sync(0xffffffffu, tmax, r), cur, ctk, cx);
         if (!done && !select_threshold(a, best, (int64_t)r_size, r_base, f, lane, ck, ci)) {
             best.init();
             select_row<1>(a, best, (int64_t)r_size, r_base, f, lane);

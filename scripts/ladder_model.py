@@ -60,11 +60,12 @@ def select(lad, key, base, s, f, stats):
         m = min(48.0, f + max(14.0, 1.2 * f))
         r = np.float32(m) * np.float32(1 << lvl) / np.float32(s)
         all_ = not (r < 1.0)
-        ttk = 0xFFFFFFFF if all_ else int(np.float32(r) * np.float32(4294967296.0))
-        cand = inwin & (all_ | (tk < ttk))
+        t = 0 if all_ else int(np.float32(r) * np.float32(4294967296.0))
+        tmax = 0xFFFFFFFF if all_ else (t - 1 if t else 0)
+        cand = inwin & (tk <= tmax)
         c = int(cand.sum())
         if need <= c <= 64:
-            nb = 32 if all_ else ttk.bit_length()
+            nb = tmax.bit_length()
             shift = max(0, nb - 26)
             w = tk[cand] >> shift
             order = np.argsort(w, kind="stable")

@@ -40,12 +40,13 @@ for r in rd:
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += t
-ours = {k: v for k, v in agg.items() if "gigl::" in k or "DeviceRadixSort" in k or "DeviceSelect" in k}
+ours = dict(agg)  # the capture is already restricted to the library's kernels (--kernel-name regex)
 tot = sum(v[1] for v in ours.values())
 with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
-    f.write(f"# {tag}: launch list of `bench.py --steps 2 --warmup 1` under `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n")
-    f.write("Library kernels only (gigl::* and the CUB sort/select they call); torch kernels of the synthetic-input generation are left out. "
-            "Times are cold-cache and serialised: compare SHARES, not absolutes. Includes the one-time graph build / index build launches.\n\n")
+    f.write(f"# {tag}: launch list of `bench.py --steps 1 --warmup 1 --streams 1` under `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n")
+    f.write("The library's step kernels (--kernel-name regex, scripts/final_profiles.sh); torch kernels of the synthetic-input generation and the "
+            "one-time CUB sorts of the graph build are left out. Times are cold-cache and serialised: compare SHARES, not absolutes. The capture "
+            "covers the warm-up step, the timed step and the untimed recount pass (sampling + collation + export only).\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
     for k, (n, t) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k[:100]}` | {n} | {t:.1f} | {100 * t / tot:.1f}% |\n")
