@@ -781,7 +781,7 @@ def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_fu
         rec["e2e_embeddings_only"] = run.measure_e2e(K, W, embeddings_only=True, streams=args.streams)
     if want_cpu:
         if env.rank == 0:
-            rec["cpu_baseline"] = run.cpu_baseline(args.cpu_steps)
+            rec["cpu_baseline"] = run.cpu_baseline(max(1, args.cpu_steps))
         env.barrier()
     run.close()
     return rec

@@ -3,7 +3,7 @@
 The product path is the CUDA library ``gigl_b200/lib/libgigl_b200.so`` (C-ABI: include/gigl_b200.h);
 importing this package does not load it, the first use does, and raises if it is missing.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 from ._capi import GiglError  # noqa: F401
 from .engine import Batch, Context, Graph, SageModel, unpack_tree  # noqa: F401

@@ -1255,6 +1255,7 @@ __global__ void __launch_bounds__(256) halo_stage_scalar_kernel(const int32_t* _
 // over NVLink) -> slot, then slot -> the staged table.  The bytes in flight live in shared memory, the kernel occupies
 // four warps and a handful of registers per SM, and the collation kernels of the same batch / the other batch's kernels
 // keep the rest of the SM.
+constexpr int kHaloBarBytes = 128 * 8;
 __global__ void __launch_bounds__(128) halo_stage_tma_kernel(const int32_t* __restrict__ n_nodes_dev, const int32_t* __restrict__ first_dev,
                                                              int64_t row_cap, uint32_t row_bytes,
                                                              uint32_t slot_bytes, const int32_t* __restrict__ list,
@@ -1263,7 +1264,7 @@ __global__ void __launch_bounds__(128) halo_stage_tma_kernel(const int32_t* __re
                                                              const float* __restrict__ hot, int64_t ldh) {
     extern __shared__ __align__(128) uint8_t s_halo[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_halo);                      // one mbarrier per lane
-    const uint32_t slot = smem_u32(s_halo + 128 * 8 + (size_t)threadIdx.x * slot_bytes);
+    const uint32_t slot = smem_u32(s_halo + kHaloBarBytes + (size_t)threadIdx.x * slot_bytes);
     const uint32_t bar = smem_u32(bars + threadIdx.x);
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1301,6 +1302,9 @@ __global__ void __launch_bounds__(128) halo_stage_tma_kernel(const int32_t* __re
 // halo_stage_kernel then copies x[slist[s]] -> xs[s] on a second stream while the collation runs on the first, and layer 1
 // gathers through `sslot` instead of the local-id map.
 constexpr int kClaimPerThread = 4;
+// d_sctr: [0] = stage slots claimed so far, [1] = copied so far (collate-time staging), [2 + k] = the claim count after the
+// k-th staged level (level-by-level staging: the copy of level k moves slots [snap k-1, snap k))
+constexpr int kStageCtrInts = 2 + GIGL_MAX_HOPS + 2;
 __global__ void __launch_bounds__(256) stage_claim_kernel(int64_t n, const int32_t* __restrict__ ids, int64_t n_graph_nodes,
                                                           int32_t* __restrict__ sslot, int32_t* __restrict__ slist,
                                                           int32_t* __restrict__ sctr) {
@@ -1387,6 +1391,7 @@ struct gigl_batch {
     bool prestaged = false;      // ... level by level from inside the sampling call (batch_stage_begin / _level / _end)
     bool stage_open = false;
     bool stage_dirty = false;    // sslot holds entries of slist[0 .. *d_sctr)
+    int stage_level = 0;         // levels staged so far by the open batch_stage_begin / _level sequence
     const int32_t* hot_slot = nullptr;  // halo staging: dense [n_graph_nodes] map vertex -> row of the replicated hot table, -1 = cold
     const float* hot = nullptr;
     int64_t ldh = 0;
@@ -1503,11 +1508,14 @@ static int halo_copy_launch(gigl_batch* b, cudaStream_t st, const int32_t* n_dev
     // bulk-copy form: rows of whole 16-byte units, 16-byte aligned at both ends, a slot per lane within 64 KB per CTA
     static const bool use_tma = !(getenv("GIGL_HALO_TMA") && getenv("GIGL_HALO_TMA")[0] == '0');
     static const int tma_ctas = getenv("GIGL_HALO_TMA_CTAS") ? atoi(getenv("GIGL_HALO_TMA_CTAS")) : 1;
-    const uint32_t row_bytes = (uint32_t)F0 * 4u, slot_bytes = (row_bytes + 127u) & ~127u;
+    // GIGL_HALO_TMA_THREADS rows in flight per CTA, a shared-memory slot each: the footprint decides what can co-run on the SM
+    static const int tma_threads_env = getenv("GIGL_HALO_TMA_THREADS") ? atoi(getenv("GIGL_HALO_TMA_THREADS")) : 128;
+    const int tma_threads = tma_threads_env >= 32 && tma_threads_env <= 128 ? (tma_threads_env & ~31) : 128;
+    const uint32_t row_bytes = (uint32_t)F0 * 4u, slot_bytes = (row_bytes + 15u) & ~15u;
     if (use_tma && vec && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) && slot_bytes <= 512) {
-        const size_t shm = 128 * 8 + 128 * (size_t)slot_bytes + 128;
-        GIGL_CUDA(ctx, cudaFuncSetAttribute(halo_stage_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        halo_stage_tma_kernel<<<(unsigned)(ctx->sm_count * (tma_ctas > 0 ? tma_ctas : 1)), 128, shm, st>>>(n_dev, first_dev, row_cap, row_bytes, slot_bytes, list,
+        const size_t shm = kHaloBarBytes + (size_t)tma_threads * slot_bytes;
+        GIGL_CUDA(ctx, cudaFuncSetAttribute(halo_stage_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kHaloBarBytes + 128 * 512)));
+        halo_stage_tma_kernel<<<(unsigned)(ctx->sm_count * (tma_ctas > 0 ? tma_ctas : 1)), tma_threads, shm, st>>>(n_dev, first_dev, row_cap, row_bytes, slot_bytes, list,
                                                                                                   x, ldx, xb, ldb, hs, b->hot, b->ldh);
         GIGL_LAUNCHED(ctx);
         return GIGL_OK;
@@ -1605,28 +1613,57 @@ int batch_stage_begin(gigl_batch* b, int64_t n_roots, const int32_t* fanouts, in
     if ((rc = gigl_scratch(ctx, GIGL_SLOT_SAVE, sizeof(float) * (size_t)cap * ldb, &pX)) != GIGL_OK) return rc;
     b->xs = (float*)pX;
     b->lds = ldb;
-    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, 2 * sizeof(int32_t), ctx->stream));
+    GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, kStageCtrInts * sizeof(int32_t), ctx->stream));
     b->stage_open = true;
     b->stage_dirty = true;
+    b->stage_level = 0;
     return GIGL_OK;
 }
 
-// ids: one level of the tree (or the roots), just written on the ctx stream
-int batch_stage_level(gigl_batch* b, const int32_t* ids_dev, int64_t n) {
+int batch_stage_args(gigl_batch* b, gigl_stage_args* out) {
+    GIGL_CHECK(b->ctx, b->stage_open && out, "batch_stage_begin first");
+    out->slot = b->sslot;
+    out->list = b->slist;
+    out->ctr = b->d_sctr;
+    return GIGL_OK;
+}
+
+// ids: one level of the tree (or the roots), just written on the ctx stream.
+//   claimed == false (default): a claim pass over `ids` and the copy of what it claimed, both on the side stream.
+//   claimed == true: the kernel that wrote `ids` claimed the stage slots as it went (khop_sample_launch with
+//   gigl_stage_args; the roots get a claim pass on the ctx stream); the next hop's kernel goes on claiming while this level
+//   is copied, so the copy works on a snapshot of the claim count taken between the two.  Measured slower (the claims
+//   stretch the sampling kernel by more than the pass costs beside it: profiles/r2_multi_gpu.md) - GIGL_STAGE_CLAIM=sampler.
+int batch_stage_level(gigl_batch* b, const int32_t* ids_dev, int64_t n, bool claimed) {
     using namespace gigl;
     gigl_ctx* ctx = b->ctx;
     GIGL_CHECK(ctx, b->stage_open, "batch_stage_begin first");
+    GIGL_CHECK(ctx, b->stage_level <= GIGL_MAX_HOPS, "more staged levels than hops");
     if (n <= 0) return GIGL_OK;
-    cudaStream_t hs = b->halo_stream;
-    GIGL_CUDA(ctx, cudaEventRecord(b->ev_fork, ctx->stream));
+    cudaStream_t st = ctx->stream, hs = b->halo_stream;
+    const int k = b->stage_level++;
+    const int32_t *n_dev = b->d_sctr, *first_dev = b->d_sctr + 1;
+    if (claimed) {
+        if (k == 0) {  // the roots: nobody claimed them
+            stage_claim_kernel<<<grid1d(ctx, ceil_div64(n, kClaimPerThread), 256), 256, 0, st>>>(n, ids_dev, b->n_graph_nodes, b->sslot, b->slist, b->d_sctr);
+            GIGL_LAUNCHED(ctx);
+        }
+        int32_t* snap = b->d_sctr + 2 + k;
+        GIGL_CUDA(ctx, cudaMemcpyAsync(snap, b->d_sctr, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        n_dev = snap;
+        first_dev = k > 0 ? snap - 1 : nullptr;
+    }
+    GIGL_CUDA(ctx, cudaEventRecord(b->ev_fork, st));
     GIGL_CUDA(ctx, cudaStreamWaitEvent(hs, b->ev_fork, 0));
     int th = gigl_timer_begin_on(ctx, GIGL_T_HALO_STAGE, hs);
-    stage_claim_kernel<<<grid1d(ctx, ceil_div64(n, kClaimPerThread), 256), 256, 0, hs>>>(n, ids_dev, b->n_graph_nodes, b->sslot, b->slist, b->d_sctr);
-    GIGL_LAUNCHED(ctx);
-    GIGL_CUDA(ctx, cudaEventRecord(b->ev_claimed, hs));  // `ids` is not read after this point on the side stream
-    int rc = halo_copy_launch(b, hs, b->d_sctr, b->slist_cap, b->slist, b->halo_x, b->halo_ldx, b->halo_F, b->xs, b->lds, b->d_sctr + 1);
+    if (!claimed) {
+        stage_claim_kernel<<<grid1d(ctx, ceil_div64(n, kClaimPerThread), 256), 256, 0, hs>>>(n, ids_dev, b->n_graph_nodes, b->sslot, b->slist, b->d_sctr);
+        GIGL_LAUNCHED(ctx);
+        GIGL_CUDA(ctx, cudaEventRecord(b->ev_claimed, hs));  // `ids` is not read after this point on the side stream
+    }
+    int rc = halo_copy_launch(b, hs, n_dev, b->slist_cap, b->slist, b->halo_x, b->halo_ldx, b->halo_F, b->xs, b->lds, first_dev);
     if (rc != GIGL_OK) return rc;
-    GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_sctr + 1, b->d_sctr, sizeof(int32_t), cudaMemcpyDeviceToDevice, hs));  // copied = claimed
+    if (!claimed) GIGL_CUDA(ctx, cudaMemcpyAsync(b->d_sctr + 1, b->d_sctr, sizeof(int32_t), cudaMemcpyDeviceToDevice, hs));  // copied = claimed
     gigl_timer_end_on(ctx, th, hs);
     GIGL_CUDA(ctx, cudaEventRecord(b->ev_staged, hs));
     return GIGL_OK;
@@ -1814,7 +1851,7 @@ int batch_collate(gigl_batch* b, const int32_t* roots_dev, int64_t n_roots, cons
     b->n_hops = n_hops;
     if (b->early_staged) GIGL_CUDA(ctx, cudaStreamWaitEvent(st, b->ev_claimed, 0));  // the tree may be overwritten after this call
     GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(int32_t) * kCtrInts, cudaMemcpyDeviceToHost, st));
-    GIGL_CUDA(ctx, cudaStreamSynchronize(st));
+    GIGL_CUDA(ctx, gigl_host_wait(ctx, st));
     b->n_unique_host = b->h_ctr[1];
     if (b->bucketed) b->n_valid_host = b->h_ctr[kCtrValid];
     for (int j = 0; j <= n_expand; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
@@ -2140,14 +2177,18 @@ int batch_set_halo_table(gigl_batch* b, const float* x_dev, int32_t F, int64_t l
     b->halo_ldx = ldx;
     if (x_dev == nullptr) return GIGL_OK;
     if (!b->halo_stream) {
-        GIGL_CUDA(ctx, cudaStreamCreateWithFlags(&b->halo_stream, cudaStreamNonBlocking));
+        // highest priority: the copy's few CTAs should get SM slots ahead of the collation's grids they run under
+        int prio_lo = 0, prio_hi = 0;
+        GIGL_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        static const bool halo_prio = !(getenv("GIGL_HALO_PRIORITY") && getenv("GIGL_HALO_PRIORITY")[0] == '0');
+        GIGL_CUDA(ctx, cudaStreamCreateWithPriority(&b->halo_stream, cudaStreamNonBlocking, halo_prio ? prio_hi : prio_lo));
         GIGL_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
         GIGL_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_claimed, cudaEventDisableTiming));
         GIGL_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_staged, cudaEventDisableTiming));
         const size_t nn = (size_t)(b->n_graph_nodes > 0 ? b->n_graph_nodes : 1);
         GIGL_CUDA(ctx, cudaMalloc(&b->sslot, sizeof(int32_t) * nn));
-        GIGL_CUDA(ctx, cudaMalloc(&b->d_sctr, 2 * sizeof(int32_t)));
-        GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, 2 * sizeof(int32_t), ctx->stream));
+        GIGL_CUDA(ctx, cudaMalloc(&b->d_sctr, kStageCtrInts * sizeof(int32_t)));
+        GIGL_CUDA(ctx, cudaMemsetAsync(b->d_sctr, 0, kStageCtrInts * sizeof(int32_t), ctx->stream));
         fill_i32_kernel<<<grid1d(ctx, b->n_graph_nodes, 256), 256, 0, ctx->stream>>>(b->n_graph_nodes, kLidAbsent, b->sslot);
         GIGL_LAUNCHED(ctx);
         GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2197,7 +2238,7 @@ int batch_finalize_nodes(gigl_batch* b, int64_t* n_nodes, int64_t* n_edges) {
         }
         b->n_levels_done = want;
         GIGL_CUDA(ctx, cudaMemcpyAsync(b->h_ctr, b->d_ctr, sizeof(int32_t) * kCtrInts, cudaMemcpyDeviceToHost, st));
-        GIGL_CUDA(ctx, cudaStreamSynchronize(st));
+        GIGL_CUDA(ctx, gigl_host_wait(ctx, st));
         for (int j = 0; j <= want; ++j) b->level_end_host[j] = b->h_ctr[kLevelBase + j];
     }
     if (n_nodes) *n_nodes = b->n_roots > 0 ? b->level_end_host[b->n_levels_done] : 0;

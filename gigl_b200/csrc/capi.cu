@@ -100,7 +100,7 @@ static const char* kTimerNames[GIGL_T_COUNT] = {"sample", "collate_keys", "colla
 
 static int ctx_check_device_error(gigl_ctx* ctx) {
     GIGL_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    GIGL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GIGL_CUDA(ctx, gigl_host_wait(ctx, ctx->stream));
     const int32_t code = *ctx->h_err;
     if (code != 0) {
         GIGL_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream));
@@ -155,7 +155,7 @@ static int conv_host_common(gigl_ctx* ctx, int64_t n, int64_t e, int32_t F, int3
 
 extern "C" {
 
-const char* gigl_version(void) { return "gigl_b200 0.1.0 sm_100a"; }
+const char* gigl_version(void) { return "gigl_b200 0.2.0 sm_100a"; }
 
 static int ctx_create_common(int device, void* stream, bool own, gigl_ctx** out) {
     if (!out) return gigl_fail(nullptr, GIGL_E_INVALID, "null out pointer");
@@ -192,6 +192,12 @@ static int ctx_create_common(int device, void* stream, bool own, gigl_ctx** out)
     if ((e = cudaMemset(ctx->d_err, 0, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMemset(err)");
     if ((e = cudaMallocHost(&ctx->h_err, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMallocHost(err)");
     *ctx->h_err = 0;
+    const char* sync_mode = getenv("GIGL_SYNC");
+    if (sync_mode && sync_mode[0] == 'b') {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess)
+            return bail(e, "cudaEventCreate(blocking)");
+        ctx->block_sync = true;
+    }
     *out = ctx;
     return GIGL_OK;
 }
@@ -206,6 +212,7 @@ void gigl_ctx_destroy(gigl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     for (int s = 0; s < GIGL_SCRATCH_SLOTS; ++s)
         if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
     if (ctx->t_pool) {
@@ -479,12 +486,19 @@ static int khop_sample_staged(gigl_graph* g, gigl_batch* b, const int32_t* roots
                               int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev, int32_t* const* cnt_dev) {
     int rc;
     if ((rc = batch_stage_begin(b, n_roots, fanouts, n_hops)) != GIGL_OK) return rc;
-    if ((rc = batch_stage_level(b, roots_dev, n_roots)) != GIGL_OK) return rc;
+    gigl_stage_args stage{};
+    if ((rc = batch_stage_args(b, &stage)) != GIGL_OK) return rc;
+    // GIGL_STAGE_CLAIM=sampler: the sampling kernels claim the stage slots themselves (A/B; default = a claim pass per level
+    // on the side stream)
+    static const bool claim_in_sampler = getenv("GIGL_STAGE_CLAIM") && getenv("GIGL_STAGE_CLAIM")[0] == 's';
+    if ((rc = batch_stage_level(b, roots_dev, n_roots, claim_in_sampler)) != GIGL_OK) return rc;
     int64_t width = n_roots;
     for (int h = 1; h <= n_hops; ++h) {
-        if ((rc = khop_sample_launch(g, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev, h, h)) != GIGL_OK) return rc;
+        if ((rc = khop_sample_launch(g, roots_dev, n_roots, fanouts, n_hops, base_seed, first_call_no, nbr_dev, cnt_dev, h, h,
+                                     claim_in_sampler ? &stage : nullptr)) != GIGL_OK)
+            return rc;
         width *= fanouts[h - 1];
-        if ((rc = batch_stage_level(b, nbr_dev[h - 1], width)) != GIGL_OK) return rc;
+        if ((rc = batch_stage_level(b, nbr_dev[h - 1], width, claim_in_sampler)) != GIGL_OK) return rc;
     }
     return batch_stage_end(b);
 }

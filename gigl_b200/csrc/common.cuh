@@ -84,7 +84,18 @@ struct gigl_ctx {
     double t_ms[GIGL_T_COUNT] = {};
     int64_t t_n[GIGL_T_COUNT] = {};
     gigl_ladder lad;  // sampler's hash ladder, built lazily on the first sampling call
+    // host waits inside the entry points: GIGL_SYNC=block sleeps on a blocking-sync event instead of spinning in
+    // cudaStreamSynchronize - for boxes with fewer host cores than caller threads (8 GPUs x batches in flight)
+    bool block_sync = false;
+    cudaEvent_t ev_block = nullptr;
 };
+
+// The host waits for everything queued on `s` (a stream of this context).
+static inline cudaError_t gigl_host_wait(gigl_ctx* ctx, cudaStream_t s) {
+    if (!ctx->block_sync) return cudaStreamSynchronize(s);
+    const cudaError_t e = cudaEventRecord(ctx->ev_block, s);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_block);
+}
 
 // Begin / end of a timed phase on the ctx stream (no-ops unless timing is enabled).
 int gigl_timer_begin(gigl_ctx* ctx, int tag);
@@ -155,9 +166,19 @@ __device__ __forceinline__ void gigl_split_tf32(float v, float& hi, float& lo) {
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- entry points implemented in the .cu files, called from capi.cu ---------------------
+// Stage-slot claims done by the sampling kernels themselves (sharded feature table, batch_stage_*): every vertex a hop writes
+// into the tree is claimed in `slot` (dense map, kStageAbsent = free) and appended to `list`; *ctr = claimed so far.
+struct gigl_stage_args {
+    int32_t* slot;
+    int32_t* list;
+    int32_t* ctr;
+};
+constexpr int32_t kStageAbsent = 0x7fffffff;   // == kLidAbsent of batch_collate.cu
+constexpr int32_t kStagePending = 0x7ffffffe;  // claimed, slot number not written yet
 int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
                        int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
-                       int32_t* const* cnt_dev, int32_t hop_first = 1, int32_t hop_last = 0);  // hops [hop_first, hop_last], 0 = n_hops
+                       int32_t* const* cnt_dev, int32_t hop_first = 1, int32_t hop_last = 0,  // hops [hop_first, hop_last], 0 = n_hops
+                       const gigl_stage_args* stage = nullptr);
 int csr_from_coo_launch(gigl_ctx* ctx, int64_t n, int64_t e, const int64_t* src, const int64_t* dst,
                         int64_t* rowptr, int32_t* col);
 int graph_from_edges_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,
@@ -190,7 +211,8 @@ void batch_set_halo_staging(gigl_batch* b, bool enabled);
 int batch_set_halo_table(gigl_batch* b, const float* x_dev, int32_t F, int64_t ldx);
 bool batch_stages_early(const gigl_batch* b, const float* x_dev);
 int batch_stage_begin(gigl_batch* b, int64_t n_roots, const int32_t* fanouts, int32_t n_hops);
-int batch_stage_level(gigl_batch* b, const int32_t* ids_dev, int64_t n);
+int batch_stage_args(gigl_batch* b, gigl_stage_args* out);
+int batch_stage_level(gigl_batch* b, const int32_t* ids_dev, int64_t n, bool claimed);  // claimed: by the kernel that wrote ids
 int batch_stage_end(gigl_batch* b);
 int batch_set_hot_rows(gigl_batch* b, const int32_t* hot_slot_dev, const float* hot_dev, int32_t F, int64_t ld);
 int batch_export(gigl_batch* b, int32_t* node_ids_dev, int64_t* edge_index_dev);

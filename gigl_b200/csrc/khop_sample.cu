@@ -53,7 +53,16 @@ struct HopArgs {
     const uint64_t* lad_ent[GIGL_LAD_MAX_LEVELS + 1];
     uint64_t lad_limit;
     int32_t lad_levels;
+    // stage-slot claims of the vertices this hop writes (gigl_stage_args); st_slot == nullptr = none
+    int32_t* st_slot;
+    int32_t* st_list;
+    int32_t* st_ctr;
 };
+
+// First writer of vertex v into the tree claims its stage slot (the slot NUMBER is assigned by the caller, in bulk).
+__device__ __forceinline__ bool stage_try_claim(const HopArgs& a, int32_t v) {
+    return v >= 0 && a.st_slot[v] == kStageAbsent && atomicCAS(a.st_slot + v, kStageAbsent, kStagePending) == kStageAbsent;
+}
 
 // Sorted (ascending) best-`f` list held by one warp: position p lives in lane p%32, register p/32.
 template <int KPL>
@@ -209,13 +218,26 @@ __device__ __forceinline__ void write_result(const HopArgs& a, int64_t pslot, co
 #pragma unroll
     for (int k = 0; k < KPL; ++k) {
         const int p = k * 32 + lane;
+        int32_t r = -1;
         if (p < f) {
-            int32_t r = -1;
             if (p < n_out) {
                 const int64_t j = (int64_t)(best.idx[k] - 1) / mult;  // sorted(m copies)[q] = row[q / m]
                 r = __ldg(a.col + row_begin + j);
             }
             o[p] = r;
+        }
+        if (a.st_slot != nullptr) {  // warp-uniform; rows of this path are rare (long rows, fanouts over 32)
+            const bool won = p < f && stage_try_claim(a, r);
+            const uint32_t m = __ballot_sync(0xffffffffu, won);
+            if (m) {
+                int s0 = 0;
+                if (lane == __ffs(m) - 1) s0 = atomicAdd(a.st_ctr, __popc(m));
+                s0 = __shfl_sync(0xffffffffu, s0, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+                if (won) {
+                    a.st_list[s0] = r;
+                    a.st_slot[r] = s0;
+                }
+            }
         }
     }
     if (lane == 0) a.out_cnt[pslot] = n_out;
@@ -321,6 +343,7 @@ __device__ __forceinline__ bool select_threshold(const HopArgs& a, WarpTopK<1>& 
     uint64_t T = kKeyInf;
     if ((float)size > m) T = __float2ull_rz(m / (float)size * 18446744073709551616.0f);
     int c = 0;
+    __syncwarp();  // a previous row that gave up early left its candidate writes unordered against these
     for (int64_t c0 = 0; c0 < size; c0 += 32) {
         const int64_t i = c0 + lane + 1;
         uint64_t k = kKeyInf;
@@ -450,6 +473,7 @@ __device__ __forceinline__ bool select_ladder(const HopArgs& a, WarpTopK<1>& bes
                                               uint32_t* cx) {
     const uint32_t lo = base + 1u;
     const int need = (int)(s < (uint32_t)f ? s : (uint32_t)f);
+    __syncwarp();  // orders this row's candidate writes after whatever the previous row left (it may have given up early)
     if (need < 32) {
         int c = 0;
         bool ok = true;
@@ -475,6 +499,7 @@ __device__ __forceinline__ bool select_ladder(const HopArgs& a, WarpTopK<1>& bes
     }
     // second attempt: every entry of the level inside the window, exact 64-bit keys through the sorted list
     int c = 0;
+    __syncwarp();
     for (uint32_t e0 = beg; e0 < end; e0 += 32) {
         const uint64_t ent = (e0 == beg) ? first : lad_load(a, lvl, e0 + lane, end);
         const uint32_t x = (uint32_t)ent;
@@ -718,6 +743,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) kho
     // ---- C: batched col loads, contiguous writes
     int32_t* out = a.out_nbr + tile0 * f;
     const int total = n_rows * f;
+    uint32_t won = 0;  // bit k: this lane's slot of the tile's k-th run of 32 claimed its vertex's stage slot (k < f <= 32)
     for (int i0 = 0; i0 < total; i0 += 32 * 4) {
         int32_t val[4], o[4];
 #pragma unroll
@@ -731,6 +757,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_TILE_MIN_BLOCKS) kho
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * 32 + lane;
             if (o[u] != -2) out[i] = val[u];  // -2: past the tile, or a row the heavy pass writes
+        }
+        if (a.st_slot != nullptr) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (stage_try_claim(a, val[u])) won |= 1u << ((i0 >> 5) + u);
+        }
+    }
+    if (a.st_slot != nullptr) {  // one counter atomic per tile: the winners' slots are handed out by a warp scan
+        const int mine = __popc(won);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int n_won = __shfl_sync(0xffffffffu, incl, 31);
+        if (n_won > 0) {  // warp-uniform
+            int s0 = 0;
+            if (lane == 31) s0 = atomicAdd(a.st_ctr, n_won);
+            s0 = __shfl_sync(0xffffffffu, s0, 31) + incl - mine;
+            while (won) {
+                const int k = __ffs(won) - 1;
+                won &= won - 1;
+                const int32_t v = out[k * 32 + lane];  // this lane's own write
+                a.st_list[s0] = v;
+                a.st_slot[v] = s0;
+                ++s0;
+            }
         }
     }
     if (lane < n_rows && state != 2) a.out_cnt[pslot] = (state == 1) ? (int32_t)min(size, (int64_t)f) : 0;
@@ -930,7 +984,7 @@ static int launch_hop(gigl_ctx* ctx, const HopArgs& a, bool tiled) {
 
 int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
                        int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
-                       int32_t* const* cnt_dev, int32_t hop_first, int32_t hop_last) {
+                       int32_t* const* cnt_dev, int32_t hop_first, int32_t hop_last, const gigl_stage_args* stage) {
     using namespace gigl;
     gigl_ctx* ctx = g->ctx;
     GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS, "n_hops must be in [1, 8]");
@@ -974,6 +1028,11 @@ int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
     a.heavy_count = heavy_count;
     a.heavy_cap = heavy_cap;
     a.tile_counter = (unsigned long long*)(heavy_count + 2);
+    if (stage != nullptr) {
+        a.st_slot = stage->slot;
+        a.st_list = stage->list;
+        a.st_ctr = stage->ctr;
+    }
     int64_t n_parent = n_roots;
     static const bool tiled = [] {  // GIGL_KHOP_TILE=0: the warp-per-row kernel (A/B measurements)
         const char* e = getenv("GIGL_KHOP_TILE");
