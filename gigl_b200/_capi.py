@@ -54,6 +54,7 @@ SIGNATURES = {
     "gigl_sample_khop_dev": (C.c_int, [vp, vp, i64, vp, i32, i32, i32, pvp, pvp]),
     "gigl_sample_khop_staged_dev": (C.c_int, [vp, vp, vp, i64, vp, i32, i32, i32, pvp, pvp]),
     "gigl_sample_op_dev": (C.c_int, [vp, vp, i64, i32, vp, pvp, i32, i32, vp, vp]),
+    "gigl_sample_op_weighted_dev": (C.c_int, [vp, vp, i64, i32, vp, pvp, vp, i32, i32, i32, vp, vp]),
     "gigl_sample_op_host": (C.c_int, [vp, vp, i64, i32, vp, pvp, i32, i32, vp, vp]),
     "gigl_sample_positives_host": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp]),
     "gigl_validate_samples_host": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp]),

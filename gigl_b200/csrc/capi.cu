@@ -538,6 +538,32 @@ int gigl_sample_op_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
     return khop_sample_launch(g, roots_dev, n_roots, chain_fanouts, depth, base_seed, first_call_no, nbr, cnt, depth, depth);
 }
 
+int gigl_sample_op_weighted_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
+                                const int32_t* const* chain_nbr_dev, const float* weights_dev, int32_t method, int32_t base_seed,
+                                int32_t call_no, int32_t* nbr_out_dev, int32_t* cnt_out_dev) {
+    if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
+    gigl_ctx* ctx = g->ctx;
+    GIGL_CHECK(ctx, depth >= 1 && depth <= GIGL_MAX_HOPS && chain_fanouts, "depth must be in [1, 8]");
+    GIGL_CHECK(ctx, (nbr_out_dev && cnt_out_dev) || n_roots == 0, "null output");
+    GIGL_CHECK(ctx, depth == 1 || chain_nbr_dev, "null ancestor levels");
+    GIGL_CHECK(ctx, method == GIGL_SAMPLE_TOP_K || method == GIGL_SAMPLE_RANDOM_WEIGHTED, "method must be GIGL_SAMPLE_TOP_K or GIGL_SAMPLE_RANDOM_WEIGHTED");
+    GIGL_CHECK(ctx, weights_dev || g->n_edges == 0, "null edge weights");
+    GIGL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int32_t* nbr[GIGL_MAX_HOPS];
+    int32_t* cnt[GIGL_MAX_HOPS];
+    for (int h = 0; h + 1 < depth; ++h) {
+        GIGL_CHECK(ctx, chain_nbr_dev[h] || n_roots == 0, "null ancestor level");
+        nbr[h] = const_cast<int32_t*>(chain_nbr_dev[h]);  // read only
+        cnt[h] = cnt_out_dev;                              // never written
+    }
+    nbr[depth - 1] = nbr_out_dev;
+    cnt[depth - 1] = cnt_out_dev;
+    const int32_t first_call_no = (int32_t)((uint32_t)call_no - (uint32_t)(depth - 1));
+    static const float no_weights = 0.f;  // an edgeless graph: the kernel never dereferences it
+    return khop_sample_launch(g, roots_dev, n_roots, chain_fanouts, depth, base_seed, first_call_no, nbr, cnt, depth, depth, nullptr,
+                              weights_dev ? weights_dev : &no_weights, method);
+}
+
 int gigl_sample_op_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
                         const int32_t* const* chain_nbr, int32_t base_seed, int32_t call_no, int32_t* nbr_out, int32_t* cnt_out) {
     if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");

@@ -178,7 +178,8 @@ constexpr int32_t kStagePending = 0x7ffffffe;  // claimed, slot number not writt
 int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
                        int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
                        int32_t* const* cnt_dev, int32_t hop_first = 1, int32_t hop_last = 0,  // hops [hop_first, hop_last], 0 = n_hops
-                       const gigl_stage_args* stage = nullptr);
+                       const gigl_stage_args* stage = nullptr,
+                       const float* weights_dev = nullptr, int32_t method = 0);  // method: GIGL_SAMPLE_* (weights by CSR position)
 int csr_from_coo_launch(gigl_ctx* ctx, int64_t n, int64_t e, const int64_t* src, const int64_t* dst,
                         int64_t* rowptr, int32_t* col);
 int graph_from_edges_build(gigl_ctx* ctx, int64_t n_nodes, int64_t n_edges, const int32_t* src_dev,

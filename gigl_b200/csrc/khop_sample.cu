@@ -14,6 +14,7 @@
 // Layout in HBM: rowptr int64[n+1], col int32[E] (rows sorted ascending), padded-tree outputs
 // nbr[h] int32[n_roots * prod f], cnt[h] int32[n_roots * prod f_{<h}]  (see include/gigl_b200.h).
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdlib.h>
 
 #include <cub/device/device_scan.cuh>
@@ -88,6 +89,37 @@ struct WarpTopK {
         int pos = 0;
 #pragma unroll
         for (int k = 0; k < KPL; ++k) pos += __popc(__ballot_sync(0xffffffffu, key[k] < ck));
+#pragma unroll
+        for (int k = KPL - 1; k >= 0; --k) {
+            uint64_t upk = __shfl_up_sync(0xffffffffu, key[k], 1);
+            int32_t upi = __shfl_up_sync(0xffffffffu, idx[k], 1);
+            if (k > 0) {
+                uint64_t pk = __shfl_sync(0xffffffffu, key[k - 1], 31);
+                int32_t pi = __shfl_sync(0xffffffffu, idx[k - 1], 31);
+                if (lane == 0) {
+                    upk = pk;
+                    upi = pi;
+                }
+            }
+            const int p = k * 32 + lane;
+            if (p > pos) {
+                key[k] = upk;
+                idx[k] = upi;
+            } else if (p == pos) {
+                key[k] = ck;
+                idx[k] = ci;
+            }
+        }
+        refresh_kth(f);
+    }
+
+    // insert() places a key BEFORE the equal keys already held; this one places it after them, so that candidates offered in
+    // ascending position order end up ordered by (key, position) - the weighted ops' tie rule.
+    __device__ __forceinline__ void insert_stable(uint64_t ck, int32_t ci, int f, int lane) {
+        empty = false;
+        int pos = 0;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) pos += __popc(__ballot_sync(0xffffffffu, key[k] <= ck));
 #pragma unroll
         for (int k = KPL - 1; k >= 0; --k) {
             uint64_t upk = __shfl_up_sync(0xffffffffu, key[k], 1);
@@ -598,6 +630,74 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, KHOP_MIN_BLOCKS) khop_hop
     write_result<KPL>(a, pslot, best, size, row_begin, mult, lane);
 }
 
+// ---- weighted SamplingOps --------------------------------------------------------------------------
+// TopK and RandomWeighted of subgraph_sampling_strategy.proto as the reference's Nebula translator words them
+// (NebulaQueryResponseTranslator.scala:73-105): "ORDER BY <edge feature> DESC | LIMIT k", and for RandomWeighted the same
+// with the feature multiplied by rand().  One warp per frontier slot streams the row's weights once; score = w (top-k) or
+// w * u, u in (0, 1) drawn from the op's seeded hash permutation key of the window position (the reference's rand() is
+// unseeded); the f largest scores win, ties to the lower CSR position (= lower neighbour id), NaN weights last.
+__device__ __forceinline__ uint64_t desc_key_f64(double s) {  // ascending order of the result = descending order of s
+    if (s != s) s = -CUDART_INF;
+    s += 0.0;  // -0.0 -> +0.0
+    uint64_t b = (uint64_t)__double_as_longlong(s);
+    b ^= (b >> 63) ? ~0ULL : 0x8000000000000000ULL;
+    return ~b;  // never kKeyInf: the largest result is that of -inf, 0xFFF0000000000000
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) khop_weighted_kernel(const HopArgs a, const float* __restrict__ w, int method) {
+    const int lane = threadIdx.x & 31;
+    const int64_t pslot = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (pslot >= a.n_parent) return;
+    const int f = a.fanouts[a.h - 1];
+    int32_t v, mult;
+    uint32_t ssum;
+    bool ok = resolve_parent(a, pslot, lane, v, ssum, mult);  // a repeated sibling is expanded once (its first slot)
+    int64_t size = 0, row_begin = 0;
+    if (ok) {
+        if (v < 0 || v >= a.n_nodes) {
+            if (lane == 0) atomicExch(a.err, GIGL_E_RANGE);
+            ok = false;
+        } else {
+            row_begin = __ldg(a.rowptr + v);
+            size = __ldg(a.rowptr + v + 1) - row_begin;
+            if (size > 2147483647LL) {
+                if (lane == 0) atomicExch(a.err, GIGL_E_OVERFLOW);
+                ok = false;
+            }
+        }
+    }
+    if (!ok) {
+        int32_t* o = a.out_nbr + pslot * f;
+        for (int p = lane; p < f; p += 32) o[p] = -1;
+        if (lane == 0) a.out_cnt[pslot] = 0;
+        return;
+    }
+    const uint32_t base = ssum + (uint32_t)a.cur_seed;
+    WarpTopK<KPL> best;
+    best.init();
+    for (int64_t c0 = 0; c0 < size; c0 += 32) {
+        const int64_t i = c0 + lane + 1;
+        uint64_t k = kKeyInf;
+        if (i <= size) {
+            double sc = (double)__ldg(w + row_begin + i - 1);
+            if (method == GIGL_SAMPLE_RANDOM_WEIGHTED) {
+                const uint64_t hk = ordered_key((int32_t)(base + (uint32_t)i));
+                sc *= ((double)(hk >> 12) + 0.5) * (1.0 / 4503599627370496.0);  // u = (top 52 bits + 1/2) * 2^-52, exact in fp64
+            }
+            k = desc_key_f64(sc);
+        }
+        uint32_t cand = __ballot_sync(0xffffffffu, k < best.kth);
+        while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const uint64_t ck = __shfl_sync(0xffffffffu, k, src);
+            if (ck < best.kth) best.insert_stable(ck, (int32_t)(c0 + src + 1), f, lane);
+        }
+    }
+    write_result<KPL>(a, pslot, best, size, row_begin, 1, lane);
+}
+
 // ---- tile form of the hop kernel (fanout <= 32) ---------------------------------------------------
 // A warp-per-row kernel is latency-bound (ncu: 41 % of the stall samples wait on global loads, DRAM 7 % busy): every
 // warp walks ONE row through its dependent round trips (parent slot -> rowptr pair -> block starts -> ladder run ->
@@ -984,13 +1084,16 @@ static int launch_hop(gigl_ctx* ctx, const HopArgs& a, bool tiled) {
 
 int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, const int32_t* fanouts,
                        int32_t n_hops, int32_t base_seed, int32_t first_call_no, int32_t* const* nbr_dev,
-                       int32_t* const* cnt_dev, int32_t hop_first, int32_t hop_last, const gigl_stage_args* stage) {
+                       int32_t* const* cnt_dev, int32_t hop_first, int32_t hop_last, const gigl_stage_args* stage,
+                       const float* weights_dev, int32_t method) {
     using namespace gigl;
     gigl_ctx* ctx = g->ctx;
     GIGL_CHECK(ctx, n_hops >= 1 && n_hops <= GIGL_MAX_HOPS, "n_hops must be in [1, 8]");
     GIGL_CHECK(ctx, n_roots >= 0, "n_roots < 0");
     GIGL_CHECK(ctx, fanouts && nbr_dev && cnt_dev, "null fanouts / output tables");
     GIGL_CHECK(ctx, roots_dev || n_roots == 0, "null roots");
+    GIGL_CHECK(ctx, method == GIGL_SAMPLE_UNIFORM || ((method == GIGL_SAMPLE_TOP_K || method == GIGL_SAMPLE_RANDOM_WEIGHTED) && weights_dev),
+               "sampling method must be uniform, or top-k / random-weighted with an edge-weight array");
     for (int h = 0; h < n_hops; ++h) {
         GIGL_CHECK(ctx, fanouts[h] >= 1 && fanouts[h] <= GIGL_MAX_FANOUT, "fanout must be in [1, 128]");
         GIGL_CHECK(ctx, (nbr_dev[h] && cnt_dev[h]) || n_roots == 0, "null output level");
@@ -1055,7 +1158,20 @@ int khop_sample_launch(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots,
         a.n_parent = n_parent;
         if (n_parent > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "frontier exceeds 2^31-1 slots; split the roots");
         GIGL_CUDA(ctx, cudaMemsetAsync(heavy_count, 0, sizeof(int32_t) * 4, ctx->stream));  // + the tile counter
-        if (f <= 32)
+        if (method != GIGL_SAMPLE_UNIFORM) {
+            const int64_t blocks = ceil_div64(n_parent, kWarpsPerBlock);
+            if (blocks > 0x7fffffffLL) return gigl_fail(ctx, GIGL_E_INVALID, "too many frontier slots for one launch");
+            if (blocks > 0) {
+                if (f <= 32)
+                    khop_weighted_kernel<1><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, weights_dev, method);
+                else if (f <= 64)
+                    khop_weighted_kernel<2><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, weights_dev, method);
+                else
+                    khop_weighted_kernel<4><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, weights_dev, method);
+                GIGL_LAUNCHED(ctx);
+            }
+            rc = GIGL_OK;
+        } else if (f <= 32)
             rc = launch_hop<1>(ctx, a, tiled);
         else if (f <= 64)
             rc = launch_hop<2>(ctx, a, false);

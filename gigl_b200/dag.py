@@ -2,7 +2,9 @@
 only the reference's spark35 graph-DB path expresses (`SamplingOpDAG.from`, scala_spark35/common/src/main/scala/types/
 SamplingOpDAG.scala:19-51; `GraphDBSampler.getKHopSubgraphForRootNode`, .../libs/sampler/GraphDBSampler.scala:40-148).
 
-Every op expands the result nodes of its input ops (or the root) over ONE edge type with a uniform fanout.  Ops with at
+Every op expands the result nodes of its input ops (or the root) over ONE edge type: a uniform sample of `numNodesToSample`
+edges per frontier node, or - RandomWeighted / TopK (proto :17-36; NebulaQueryResponseTranslator.scala:73-105) - the
+`numNodesToSample` edges with the largest edge feature (times a seeded uniform draw for RandomWeighted).  Ops with at
 most one input (tree-shaped DAGs: chains that branch) map one to one onto `gigl_sample_op_*` launches - one kernel
 launch per op over that edge type's CSR, ancestors' padded trees as the frontier.  An op with several inputs (the union
 of several parents' results, GraphDBSampler.scala:66-82) runs once per input - one launch per (op, input) instance -
@@ -31,6 +33,8 @@ class SamplingOp:
     num_nodes_to_sample: int
     input_op_names: List[str] = field(default_factory=list)
     sampling_direction: str = INCOMING
+    sampling_method: str = "random_uniform"   # | "top_k" | "random_weighted" (SamplingOp.sampling_method, proto :38-58)
+    edge_feat_name: str = ""                   # the edge feature a weighted method orders by (RandomWeighted / TopK .edge_feat_name)
 
     @property
     def frontier_node_type(self) -> str:
@@ -42,16 +46,23 @@ class SamplingOp:
         return self.edge_type[0] if self.sampling_direction == INCOMING else self.edge_type[2]
 
 
+_METHOD_KEYS = {"randomUniform": "random_uniform", "randomWeighted": "random_weighted", "topK": "top_k"}
+
+
 def ops_from_config(path: dict) -> List[SamplingOp]:
     """`MessagePassingPath.samplingOps` (YAML / JSON form of the proto) -> SamplingOp list."""
     out = []
     for o in path.get("samplingOps") or []:
-        if "randomUniform" not in o:
-            raise ValueError(f"sampling op {o.get('opName')!r}: only randomUniform sampling is supported")
+        given = [k for k in _METHOD_KEYS if k in o]
+        if "userDefined" in o or len(given) != 1:  # the reference throws NotImplementedError for both (NebulaQueryResponseTranslator.scala:106-111)
+            raise ValueError(f"sampling op {o.get('opName')!r}: exactly one of randomUniform / randomWeighted / topK is supported")
+        m = o[given[0]]
+        feat = str(m.get("edgeFeatName") or "")
+        if given[0] != "randomUniform" and not feat:
+            raise ValueError(f"sampling op {o.get('opName')!r}: {given[0]} needs an edgeFeatName")
         et = o["edgeType"]
-        out.append(SamplingOp(o["opName"], (et["srcNodeType"], et["relation"], et["dstNodeType"]),
-                              int(o["randomUniform"]["numNodesToSample"]), list(o.get("inputOpNames") or []),
-                              o.get("samplingDirection", INCOMING)))
+        out.append(SamplingOp(o["opName"], (et["srcNodeType"], et["relation"], et["dstNodeType"]), int(m["numNodesToSample"]),
+                              list(o.get("inputOpNames") or []), o.get("samplingDirection", INCOMING), _METHOD_KEYS[given[0]], feat))
     return out
 
 
@@ -127,12 +138,14 @@ def frontier_of(p: PlannedOp, res: dict, frontiers: dict, distinct):
 
 
 def sample_dag(graphs: Dict[Tuple[Tuple[str, str, str], str], "object"], roots, ops: Sequence[SamplingOp], root_node_type: str,
-               base_seed: int = 42, call_no_offset: int = 0, distinct_frontier: bool = True):
+               base_seed: int = 42, call_no_offset: int = 0, distinct_frontier: bool = True, weights=None):
     """Runs every op instance on the device.  `graphs[(edge_type, direction)]` = the :class:`gigl_b200.Graph` of that edge
     type, built by destination for INCOMING ops and `by_source=True` for OUTGOING ones.  `roots`: int32 CUDA tensor.
     Returns {instance key: (nbr, cnt, chain_fanouts)} with the padded-tree layout of `Graph.sample_khop` (the key is the op
     name unless the op has several inputs, see :func:`plan`).  distinct_frontier = False expands every slot of the parent
-    level (one expansion per PATH, the pure-Spark GROUP BY semantics) instead of every distinct node."""
+    level (one expansion per PATH, the pure-Spark GROUP BY semantics) instead of every distinct node.
+    weights[(edge_type, direction, edge_feat_name)] = float32 CUDA tensor with that edge feature per CSR position of
+    graphs[(edge_type, direction)] - needed by the top_k / random_weighted ops only."""
     res = {}
     frontiers: dict = {}
     for p in plan(ops, root_node_type):
@@ -140,7 +153,12 @@ def sample_dag(graphs: Dict[Tuple[Tuple[str, str, str], str], "object"], roots, 
         g = graphs[(p.op.edge_type, p.op.sampling_direction)]
         if distinct_frontier and p.parent is not None:
             chain_nbr[-1] = frontier_of(p, res, frontiers, g.ctx.frontier_distinct)
-        nbr, cnt = g.sample_op(roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, base_seed)
+        w = None
+        if p.op.sampling_method != "random_uniform":
+            w = (weights or {}).get((p.op.edge_type, p.op.sampling_direction, p.op.edge_feat_name))
+            if w is None:
+                raise ValueError(f"op {p.op.op_name!r}: no weights for edge feature {p.op.edge_feat_name!r} of {p.op.edge_type}")
+        nbr, cnt = g.sample_op(roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, base_seed, weights=w, method=p.op.sampling_method)
         res[p.key] = (nbr, cnt, p.fanouts)
     return res
 

@@ -32,6 +32,10 @@ def _dp(t):
     return C.c_void_p(t.data_ptr())
 
 
+# SamplingOp.sampling_method (subgraph_sampling_strategy.proto:38-58) -> GIGL_SAMPLE_* of include/gigl_b200.h
+SAMPLING_METHODS = {"random_uniform": 0, "top_k": 1, "random_weighted": 2}
+
+
 class Context:
     """gigl_ctx: device + stream + scratch.  Not thread-safe; use one per thread/GPU
     (mirrors the per-partition setup()/teardown() of the reference's KHopSamplerService,
@@ -330,11 +334,16 @@ class Graph:
                                                    pn, pc), self.ctx.handle)
         return nbr, cnt
 
-    def sample_op(self, roots, chain_fanouts: Sequence[int], chain_nbr: Sequence, call_no: int, base_seed: int = 42):
+    def sample_op(self, roots, chain_fanouts: Sequence[int], chain_nbr: Sequence, call_no: int, base_seed: int = 42, weights=None,
+                  method: str = "random_uniform"):
         """One SamplingOp over this graph's edge type (gigl_sample_op_dev): expands the frontier `chain_nbr[-1]` (or the
         roots when the chain is empty).  chain_fanouts = the ancestors' fanouts followed by this op's.  Device tensors in,
-        (nbr, cnt) device tensors out."""
+        (nbr, cnt) device tensors out.  method "top_k" / "random_weighted" (gigl_sample_op_weighted_dev) takes `weights`:
+        a float32 CUDA tensor with the op's edge feature per CSR position of this graph."""
         import torch
+
+        if method not in SAMPLING_METHODS:
+            raise ValueError(f"sampling method {method!r}: expected one of {sorted(SAMPLING_METHODS)}")
 
         fan = _np(chain_fanouts, np.int32)
         depth = len(fan)
@@ -344,6 +353,13 @@ class Graph:
         nbr = torch.empty(parents * int(fan[-1]), dtype=torch.int32, device=roots.device)
         cnt = torch.empty(parents, dtype=torch.int32, device=roots.device)
         pn = (C.c_void_p * max(depth - 1, 1))(*[t.data_ptr() for t in chain_nbr])
+        if SAMPLING_METHODS[method] != 0:
+            if weights is None or weights.dtype != torch.float32 or not weights.is_cuda or weights.numel() != self.n_edges:
+                raise ValueError(f"{method} sampling needs a float32 CUDA tensor of {self.n_edges} edge weights (one per CSR position)")
+            weights = weights.contiguous()
+            check(self.ctx._L.gigl_sample_op_weighted_dev(self.handle, _dp(roots), n_roots, depth, _hp(fan), pn, _dp(weights),
+                                                          SAMPLING_METHODS[method], base_seed, call_no, _dp(nbr), _dp(cnt)), self.ctx.handle)
+            return nbr, cnt
         check(self.ctx._L.gigl_sample_op_dev(self.handle, _dp(roots), n_roots, depth, _hp(fan), pn, base_seed, call_no, _dp(nbr), _dp(cnt)),
               self.ctx.handle)
         return nbr, cnt

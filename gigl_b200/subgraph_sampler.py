@@ -124,6 +124,13 @@ def _roots_to_device(roots: np.ndarray, device: int):
     return torch.from_numpy(np.ascontiguousarray(roots, dtype=np.int32)).to(torch.device("cuda", device))
 
 
+def _floats_to_device(values: np.ndarray, device: int):
+    """float32 values (an edge feature per CSR position) -> the CUDA tensor the weighted SamplingOp entry point takes."""
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32)).to(torch.device("cuda", device))
+
+
 _PART_RE = re.compile(r"^part-(?:r(\d+)-)?\d+\.tfrecord$")
 
 
@@ -440,13 +447,18 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
             tables[int(k)] = x
         n_max = max(n_max, int(nid.max(initial=-1)) + 1)
     # ---- edge tables per condensed edge type (+ features)
-    edges, edge_feat = {}, {}
+    edges, edge_feat, edge_feat_cols = {}, {}, {}
     for k, emeta in meta["condensedEdgeTypeToPreprocessedMetadata"].items():
         main = emeta["mainEdgeInfo"]
         t = sio.ExampleTable.from_files(sio.list_tfrecord_files(_resolve(main["tfrecordUriPrefix"], root)))
         es, ed = t.column(emeta["srcNodeIdKey"], "int64"), t.column(emeta["dstNodeIdKey"], "int64")
         edges[int(k)] = (es.astype(np.int32), ed.astype(np.int32))
         edge_feat[int(k)] = _feature_matrix(t, main.get("featureKeys"))
+        off, cols = 0, {}
+        for fk in main.get("featureKeys") or []:  # feature name -> (first column, width) in the matrix above
+            cols[fk] = (off, t.width(fk))
+            off += t.width(fk)
+        edge_feat_cols[int(k)] = cols
         n_max = max(n_max, int(es.max(initial=-1)) + 1, int(ed.max(initial=-1)) + 1)
     for tt, x in enumerate(tables):  # ids above a type's own table (seen only as edge endpoints) hydrate as zeros
         if x is not None and x.shape[0] < n_max:
@@ -476,19 +488,39 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
                 g_in.close()
         return edge_tabs
 
+    op_weights = {}
+
+    def weights_of(edge_type, direction, name):
+        """The edge feature `name` of every edge of `edge_type`, laid out by CSR position of graph_of(edge_type, direction):
+        what a TopK / RandomWeighted op orders by (NebulaQueryResponseTranslator.scala:73-105)."""
+        key = (edge_type, direction, name)
+        if key not in op_weights:
+            k = cet_of[edge_type]
+            if edge_feat[k] is None or name not in edge_feat_cols[k]:
+                raise ValueError(f"sampling op orders {edge_type} by {name!r}, which is not among the edge type's featureKeys")
+            col0, width = edge_feat_cols[k][name]
+            if width != 1:
+                raise ValueError(f"edge feature {name!r} of {edge_type} has {width} values per edge; a weighted sampling op needs a scalar")
+            es, ed = edges[k]
+            rows = ctx.edge_rows_host(n_max, es, ed, True) if direction == dag.INCOMING else ctx.edge_rows_host(n_max, ed, es, True)
+            op_weights[key] = _floats_to_device(edge_feat[k][rows, col0], device)
+        return op_weights[key]
+
     dags = {}
     for path in strat.get("paths") or []:
         ops = dag.ops_from_config(path)
         planned = dag.plan(ops, path["rootNodeType"])
         for p in planned:
             graph_of(p.op.edge_type, p.op.sampling_direction)
+            if p.op.sampling_method != "random_uniform":
+                weights_of(p.op.edge_type, p.op.sampling_direction, p.op.edge_feat_name)
         # hydrateRnn joins the edges only if an edge type of the DAG's ROOT ops carries features (:186-193, 283-291)
         hydrate = any(edge_feat[cet_of[p.op.edge_type]] is not None for p in planned if p.parent is None)
         dags[path["rootNodeType"]] = (ops, planned, hydrate)
 
     def sample(rtype, roots):
         ops, planned, _ = dags[rtype]
-        res = dag.sample_dag(graphs, _roots_to_device(roots, device), ops, rtype, base_seed=SAMPLING_SEED)
+        res = dag.sample_dag(graphs, _roots_to_device(roots, device), ops, rtype, base_seed=SAMPLING_SEED, weights=op_weights)
         ctx.sync()
         return dag.encoder_ops(planned, res, cet_of, cnt_of)
 

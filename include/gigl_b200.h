@@ -189,6 +189,25 @@ int gigl_sample_op_host(gigl_graph* g, const int32_t* roots, int64_t n_roots, in
                         const int32_t* const* chain_nbr, int32_t base_seed, int32_t call_no, int32_t* nbr_out, int32_t* cnt_out);
 
 /*
+ * The weighted sampling methods of a SamplingOp (subgraph_sampling_strategy.proto:17-36 `RandomWeighted`, `TopK`), as the
+ * reference's Nebula translator words them (scala_spark35/common/src/main/scala/graphdb/nebula/
+ * NebulaQueryResponseTranslator.scala:73-105): TopK = "ORDER BY <edgeFeatName> DESC | LIMIT numNodesToSample";
+ * RandomWeighted = the same on "<edgeFeatName> * rand()" (its own comment: not true weighted sampling).
+ * weights_dev[p] = the op's edge feature of the edge at CSR position p of `g` (gigl_edge_rows_host maps positions to input
+ * edge records).  Every frontier slot keeps the numNodesToSample largest scores of its row: score = weight (top-k) or
+ * weight * u with u in (0, 1) taken from the op's seeded permutation key of the position, (top 52 bits + 1/2) * 2^-52 - the
+ * reference's rand() is unseeded, so RandomWeighted is reproducible here and not there.  Ties go to the lower CSR position
+ * (= lower neighbour id; Nebula leaves them unspecified), NaN weights sort last, a frontier node repeated among its siblings
+ * is expanded once.  Other arguments and the output layout as gigl_sample_op_dev.
+ */
+#define GIGL_SAMPLE_UNIFORM 0
+#define GIGL_SAMPLE_TOP_K 1
+#define GIGL_SAMPLE_RANDOM_WEIGHTED 2
+int gigl_sample_op_weighted_dev(gigl_graph* g, const int32_t* roots_dev, int64_t n_roots, int32_t depth, const int32_t* chain_fanouts,
+                                const int32_t* const* chain_nbr_dev, const float* weights_dev, int32_t method, int32_t base_seed,
+                                int32_t call_no, int32_t* nbr_out_dev, int32_t* cnt_out_dev);
+
+/*
  * Distinct frontier of a SamplingOp (replaces the HashSet[Node] the reference's graph-DB sampler collects the parents'
  * result nodes into before an op's query runs, scala_spark35/subgraph_sampler/src/main/scala/libs/sampler/
  * GraphDBSampler.scala:66-82): out = cur ([n_roots * cur_slots], a parent level in the padded-tree layout) with, per

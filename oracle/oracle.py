@@ -300,6 +300,53 @@ def np_sample_op(csr, roots, fanouts, chain_nbr, call_no, base_seed=42):
     return out, oc
 
 
+def np_sample_op_weighted(csr, weights, roots, fanouts, chain_nbr, call_no, method, base_seed=42):
+    """ONE TopK / RandomWeighted op (subgraph_sampling_strategy.proto:17-36) as NebulaQueryResponseTranslator.scala:73-105
+    words it - ORDER BY score DESC LIMIT numNodesToSample over the frontier node's edges of one type, score = the edge feature
+    (method "top_k") or the feature times a uniform draw ("random_weighted").  The reference's rand() is unseeded; the draw
+    here is u = (top 52 bits of the op's permutation key of the window position + 1/2) * 2^-52 (the key of np_perm with its
+    sign bit flipped = the unsigned order of the signed hash).  Ties: lower CSR position first; NaN scores last; a frontier
+    node repeated among its siblings is expanded at its first slot only.  weights: float32 per CSR position."""
+    assert method in ("top_k", "random_weighted")
+    n_roots = len(roots)
+    depth = len(fanouts)
+    f = int(fanouts[-1])
+    rowptr, col = csr
+    weights = np.asarray(weights, dtype=np.float32)
+    width_prev = 1
+    for g in fanouts[:-1]:
+        width_prev *= int(g)
+    prev_vals = [int(r) for r in roots] if depth == 1 else [int(v) for v in chain_nbr[-1]]
+    cur_seed = _wrap32(base_seed * _wrap32(call_no))
+    out = np.full(n_roots * width_prev * f, -1, dtype=np.int32)
+    oc = np.zeros(n_roots * width_prev, dtype=np.int32)
+    for ps in range(n_roots * width_prev):
+        v = prev_vals[ps]
+        if v < 0:
+            continue
+        if depth > 1:
+            fp = int(fanouts[-2])
+            sib0 = (ps // fp) * fp
+            if prev_vals[sib0 : sib0 + fp].index(v) + sib0 != ps:
+                continue
+        tot, s_ = 0, ps
+        for h in range(depth - 1, 0, -1):
+            tot = _wrap32(tot + int(chain_nbr[h - 1][s_]))
+            s_ //= int(fanouts[h - 1])
+        path_sum = _wrap32(tot + int(roots[s_]))
+        lo, hi = int(rowptr[v]), int(rowptr[v + 1])
+        score = weights[lo:hi].astype(np.float64)
+        if method == "random_weighted":
+            i = np.arange(1, hi - lo + 1, dtype=np.int64)
+            key = np_xxh64_int(i + path_sum + cur_seed).view(np.uint64) ^ np.uint64(1 << 63)
+            score = score * (((key >> np.uint64(12)).astype(np.float64) + 0.5) * 2.0 ** -52)
+        score = np.where(np.isnan(score), -np.inf, score)
+        sel = col[lo:hi][np.argsort(-score, kind="stable")[:f]]
+        out[ps * f : ps * f + len(sel)] = sel
+        oc[ps] = len(sel)
+    return out, oc
+
+
 def np_frontier_distinct(cur, cur_slots: int, prev=()):
     """The frontier a SamplingOp expands: per root, the SET of its parents' result nodes
     (GraphDBSampler.scala:66-82 collects them into a HashSet[Node]).  cur: [n_roots * cur_slots] parent level; prev:
@@ -323,7 +370,7 @@ def np_frontier_distinct(cur, cur_slots: int, prev=()):
     return out.reshape(-1)
 
 
-def np_sample_dag(planned, csr_of, roots, base_seed=42, call_no_offset=0, distinct=True):
+def np_sample_dag(planned, csr_of, roots, base_seed=42, call_no_offset=0, distinct=True, weights_of=None):
     """A whole SamplingOp DAG on the CPU, the way gigl_b200.dag.sample_dag runs it on the device: the planned op instances
     in order, each ONE np_sample_op over csr_of(instance) = (rowptr, col) of its edge type and direction, expanding its
     parent's level reduced to the distinct nodes per root (np_frontier_distinct: the HashSet[Node] of
@@ -338,7 +385,11 @@ def np_sample_dag(planned, csr_of, roots, base_seed=42, call_no_offset=0, distin
             level = np_frontier_distinct(res[p.parent][0], slots, list(prev))
             prev.append((level, slots))
             chain_nbr[-1] = level
-        nbr, cnt = np_sample_op(csr_of(p), roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, base_seed)
+        method = getattr(p.op, "sampling_method", "random_uniform")
+        if method == "random_uniform":
+            nbr, cnt = np_sample_op(csr_of(p), roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, base_seed)
+        else:  # weights_of(instance) = the op's edge feature per CSR position of csr_of(instance)
+            nbr, cnt = np_sample_op_weighted(csr_of(p), weights_of(p), roots, p.fanouts, chain_nbr, p.call_no + call_no_offset, method, base_seed)
         res[p.key] = (nbr, cnt, list(p.fanouts))
     return res
 

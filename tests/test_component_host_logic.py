@@ -60,10 +60,15 @@ class _Graph:
             cnt[i] = len(lst)
         return pos.reshape(-1), cnt
 
-    def sample_op(self, roots, chain_fanouts, chain_nbr, call_no, base_seed=42):
+    def sample_op(self, roots, chain_fanouts, chain_nbr, call_no, base_seed=42, weights=None, method="random_uniform"):
         import torch
 
-        nbr, cnt = O.np_sample_op((self.rowptr, self.col), roots.numpy(), list(chain_fanouts), [t.numpy() for t in chain_nbr], call_no, base_seed)
+        chain = [t.numpy() for t in chain_nbr]
+        if method == "random_uniform":
+            nbr, cnt = O.np_sample_op((self.rowptr, self.col), roots.numpy(), list(chain_fanouts), chain, call_no, base_seed)
+        else:
+            nbr, cnt = O.np_sample_op_weighted((self.rowptr, self.col), weights.cpu().numpy(), roots.numpy(), list(chain_fanouts), chain, call_no,
+                                               method, base_seed)
         return torch.from_numpy(nbr), torch.from_numpy(cnt)
 
     def close(self):
@@ -77,6 +82,7 @@ def oracle_backed_sampler(monkeypatch):
     monkeypatch.setattr(subgraph_sampler, "Context", _Ctx)
     monkeypatch.setattr(subgraph_sampler, "Graph", _Graph)
     monkeypatch.setattr(subgraph_sampler, "_roots_to_device", lambda roots, device: torch.from_numpy(np.ascontiguousarray(roots, dtype=np.int32)))
+    monkeypatch.setattr(subgraph_sampler, "_floats_to_device", lambda v, device: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)))
 
 
 def test_node_classification_component(tmp_path):
@@ -111,3 +117,7 @@ def test_typed_component_edge_features_and_isolated_anchors(tmp_path):
 
 def test_typed_component_on_the_reference_heterogeneous_fixture(tmp_path):
     G.test_typed_component_on_the_reference_heterogeneous_fixture(tmp_path)
+
+
+def test_typed_component_weighted_sampling_ops(tmp_path):
+    G.test_typed_component_weighted_sampling_ops(tmp_path)

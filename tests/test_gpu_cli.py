@@ -440,6 +440,81 @@ def test_typed_component_hydrates_edge_features_and_isolated_anchors(tmp_path):
         assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == wn
 
 
+def test_typed_component_weighted_sampling_ops(tmp_path):
+    """TopK / RandomWeighted ops in the component's config (subgraph_sampling_strategy.proto:17-58): the op orders the edges
+    of its type by the SCALAR edge feature it names - the second of two feature keys here, so the column offset matters -
+    and the written RootedNodeNeighborhoods are the oracle's (np_sample_op_weighted over the same CSR positions)."""
+    from helpers import tf_example, tfrecord_bytes
+    from gigl_b200 import dag
+    from gigl_b200 import sample_io as sio
+    from gigl_b200 import subgraph_sampler
+    from oracle import oracle as O
+    from test_sample_assembly import np_edge_rows
+
+    rng = np.random.default_rng(23)
+    n_u, n_i = 30, 18
+    n = max(n_u, n_i)
+    clicks = (rng.integers(0, n_u, 150), rng.integers(0, n_i, 150))
+    cf = np.concatenate([rng.standard_normal((150, 2)), rng.integers(0, 4, (150, 1))], axis=1).astype(np.float32)   # [v0, v1 | w], w with ties
+    for sub, recs in (("nodes_user", [tf_example({"node_id": int(i)}) for i in range(n_u)]),
+                      ("nodes_item", [tf_example({"node_id": int(i)}) for i in range(n_i)]),
+                      ("edges_clicks", [tf_example({"src": int(u), "dst": int(v), "v": cf[j, :2].tolist(), "w": float(cf[j, 2])})
+                                        for j, (u, v) in enumerate(zip(*clicks))])):
+        os.makedirs(tmp_path / sub, exist_ok=True)
+        (tmp_path / sub / "data.tfrecord").write_bytes(tfrecord_bytes(recs))
+    et1 = {"srcNodeType": "user", "relation": "clicks", "dstNodeType": "item"}
+    meta = {"condensedNodeTypeToPreprocessedMetadata": {"0": {"nodeIdKey": "node_id", "tfrecordUriPrefix": "nodes_user"},
+                                                        "1": {"nodeIdKey": "node_id", "tfrecordUriPrefix": "nodes_item"}},
+            "condensedEdgeTypeToPreprocessedMetadata": {
+                "0": {"srcNodeIdKey": "src", "dstNodeIdKey": "dst", "mainEdgeInfo": {"tfrecordUriPrefix": "edges_clicks", "featureKeys": ["v", "w"]}}}}
+    paths = [{"rootNodeType": "user", "samplingOps": [
+                 {"opName": "top_liked", "edgeType": et1, "topK": {"numNodesToSample": 2, "edgeFeatName": "w"}, "samplingDirection": "OUTGOING"},
+                 {"opName": "lucky_clickers", "edgeType": et1, "inputOpNames": ["top_liked"], "randomWeighted": {"numNodesToSample": 2, "edgeFeatName": "w"}}]},
+             {"rootNodeType": "item", "samplingOps": [
+                 {"opName": "top_clickers", "edgeType": et1, "topK": {"numNodesToSample": 3, "edgeFeatName": "w"}}]}]
+    cfg = {"graphMetadata": {"condensedEdgeTypeMap": {"0": et1}, "condensedNodeTypeMap": {"0": "user", "1": "item"},
+                             "edgeTypes": [et1], "nodeTypes": ["user", "item"]},
+           "taskMetadata": {"nodeAnchorBasedLinkPredictionTaskMetadata": {"supervisionEdgeTypes": [et1]}},
+           "datasetConfig": {"subgraphSamplerConfig": {"numPositiveSamples": 1, "subgraphSamplingStrategy": {"messagePassingPaths": {"paths": paths}}}},
+           "sharedConfig": {"isGraphDirected": True, "preprocessedMetadataUri": "preprocessed_metadata.yaml",
+                            "shouldIncludeIsolatedNodesInTraining": True,
+                            "flattenedGraphMetadata": {"nodeAnchorBasedLinkPredictionOutput": {
+                                "tfrecordUriPrefix": "out/nablp/",
+                                "nodeTypeToRandomNegativeTfrecordUriPrefix": {"user": "out/rnn/user/", "item": "out/rnn/item/"}}}}}
+    (tmp_path / "preprocessed_metadata.yaml").write_text(yaml.safe_dump(meta))
+    (tmp_path / "frozen_gbml_config.yaml").write_text(yaml.safe_dump(cfg))
+    stats = subgraph_sampler.run("frozen_gbml_config.yaml", "weighted_job", None, root=str(tmp_path), batch_roots=16, log=lambda *_: None)
+    assert stats["rnn_per_node_type"] == {"user": n_u, "item": n_i}
+    inc, outg = O.np_build_in_csr(clicks[0], clicks[1], n, True), O.np_build_in_csr(clicks[1], clicks[0], n, True)
+    w_in, w_out = cf[np_edge_rows(clicks[0], clicks[1], n, True), 2], cf[np_edge_rows(clicks[1], clicks[0], n, True), 2]
+    records = O.np_typed_edge_records({0: (clicks[0], clicks[1], cf)})
+    for rtype, path, n_roots, out_dir in (("user", paths[0], n_u, "out/rnn/user/"), ("item", paths[1], n_i, "out/rnn/item/")):
+        planned = dag.plan(dag.ops_from_config(path), rtype)
+        roots = np.arange(n_roots, dtype=np.int32)
+        res = O.np_sample_dag(planned, lambda p: outg if p.op.sampling_direction == dag.OUTGOING else inc, roots,
+                              weights_of=lambda p: w_out if p.op.sampling_direction == dag.OUTGOING else w_in)
+        ops = [dict(parent=-1 if p.parent is None else [q.key for q in planned].index(p.parent), fanout=p.op.num_nodes_to_sample,
+                    condensed_edge_type=0, result_node_type=1 if p.op.sampling_direction == dag.OUTGOING else 0,
+                    outgoing=p.op.sampling_direction == dag.OUTGOING, nbr=res[p.key][0]) for p in planned]
+        want = O.np_hydrate_typed_rnn(O.np_assemble_dag_rnn(roots, 0 if rtype == "user" else 1, ops), records)
+        raw = b"".join(open(f, "rb").read() for f in sio.list_tfrecord_files(str(tmp_path / out_dir)))
+        got = {s["root_node"]["node_id"]: s for s in map(sio.parse_sample, sio.split_tfrecords(raw, verify=True))}
+        n_edges = 0
+        for r in range(n_roots):
+            have = sorted(((e["condensed_edge_type"], e["src_node_id"], e["dst_node_id"], tuple(np.float32(e["feature_values"]).tolist()) or None)
+                           for e in got[r]["edges"]), key=lambda e: (e[0], e[1], e[2], e[3] or ()))
+            assert have == want[r][0], (rtype, r)
+            assert sorted((v["condensed_node_type"], v["node_id"]) for v in got[r]["nodes"]) == want[r][1]
+            n_edges += len(have)
+        assert n_edges > 0
+    # the item DAG really is "the 3 heaviest clicks of every item": no dropped in-edge is heavier than a kept one
+    rowptr, col = inc
+    for it in range(n_i):
+        row_w = np.sort(w_in[rowptr[it]:rowptr[it + 1]])[::-1]
+        kept = sorted((e["feature_values"][2] for e in got[it]["edges"]), reverse=True)
+        assert len(row_w) == 0 or kept[0] == row_w[0]
+
+
 @pytest.mark.parametrize("directed", [False, True])
 def test_component_sharded_over_ranks_writes_the_same_records(tmp_path, directed):
     """One process per GPU: rank r of `world` samples its contiguous share of the roots and writes part-r<rank>-* files.

@@ -192,3 +192,52 @@ def test_distinct_frontier_set_semantics_beyond_two_hops():
     assert np.array_equal(ctx.frontier_distinct(cur_d, 24).cpu().numpy(), O.np_frontier_distinct(cur, 24))
     assert np.array_equal(ctx.frontier_distinct(cur_d, 24, [(p1_d, 5), (p2_d, 3)]).cpu().numpy(),
                           O.np_frontier_distinct(cur, 24, [(p1, 5), (p2, 3)]))
+
+
+@pytest.mark.parametrize("fanout", [3, 40])
+def test_weighted_ops_match_oracle(fanout):
+    """TopK / RandomWeighted ops (subgraph_sampling_strategy.proto:17-36, NebulaQueryResponseTranslator.scala:73-105): every
+    op instance of a DAG that mixes the three sampling methods, bit-exact against oracle.np_sample_op_weighted; weights
+    with ties, negatives, zeros, a NaN and an infinity."""
+    import torch
+    from gigl_b200 import Context, Graph, dag
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(31)
+    n, n_user, et = _typed_graph(rng, n_user=90, n_item=50)
+    hub = (np.full(300, 7), rng.integers(0, n_user, 300))   # user 7 OUTGOING hub / a long in-row for its followers' view
+    s0, d0 = et[("user", "follows", "user")]
+    et[("user", "follows", "user")] = (np.concatenate([s0, hub[1]]), np.concatenate([d0, hub[0]]))
+    ctx = Context.on_torch_stream(0)
+    ops = [dag.SamplingOp("best_friends", ("user", "follows", "user"), fanout, [], dag.INCOMING, "top_k", "w"),
+           dag.SamplingOp("seen", ("item", "shown_to", "user"), 2),
+           dag.SamplingOp("lucky_clickers", ("user", "clicks", "item"), 2, ["seen"], dag.INCOMING, "random_weighted", "w"),
+           dag.SamplingOp("fof", ("user", "follows", "user"), 2, ["best_friends"], dag.INCOMING, "random_weighted", "w"),
+           dag.SamplingOp("their_top_clicks", ("user", "clicks", "item"), 2, ["best_friends"], dag.OUTGOING, "top_k", "w")]
+    graphs, csrs, wts, wts_np = {}, {}, {}, {}
+    for key, (s, d) in et.items():
+        rec_w = rng.integers(-3, 6, len(s)).astype(np.float32) / 2      # many ties, zeros, negatives
+        rec_w[rng.integers(0, len(s), 3)] = [np.nan, np.inf, -0.0]
+        for direction in (dag.INCOMING, dag.OUTGOING):
+            a, b = (s, d) if direction == dag.INCOMING else (d, s)
+            graphs[(key, direction)] = Graph.from_edges_host(ctx, n, s, d, is_graph_directed=True, by_source=direction == dag.OUTGOING)
+            csrs[(key, direction)] = O.np_build_in_csr(a, b, n, True)
+            rows = ctx.edge_rows_host(n, a, b, True)
+            assert np.array_equal(np.asarray(a)[rows], csrs[(key, direction)][1])   # position -> record is the CSR's own order
+            wts_np[(key, direction, "w")] = rec_w[rows]
+            wts[(key, direction, "w")] = torch.from_numpy(rec_w[rows]).cuda()
+    roots = np.arange(0, n_user, 2, dtype=np.int32)
+    res = dag.sample_dag(graphs, torch.from_numpy(roots).cuda(), ops, "user", weights=wts)
+    ctx.sync()
+    planned = dag.plan(ops, "user")
+    want = O.np_sample_dag(planned, lambda p: csrs[(p.op.edge_type, p.op.sampling_direction)], roots,
+                           weights_of=lambda p: wts_np[(p.op.edge_type, p.op.sampling_direction, p.op.edge_feat_name)])
+    for name, (nbr, cnt, fan) in res.items():
+        assert np.array_equal(nbr.cpu().numpy(), want[name][0]), name
+        assert np.array_equal(cnt.cpu().numpy(), want[name][1]), name
+        assert (cnt.cpu().numpy() > 0).any(), name
+    cnt = res["best_friends"][1].cpu().numpy()
+    rowptr = csrs[(("user", "follows", "user"), dag.INCOMING)][0]
+    assert np.array_equal(cnt, np.minimum(fanout, rowptr[roots + 1] - rowptr[roots]))   # LIMIT k of the row, NaN edges included
+    with pytest.raises(ValueError):
+        dag.sample_dag(graphs, torch.from_numpy(roots).cuda(), ops, "user")   # weighted ops without weights

@@ -164,3 +164,51 @@ def test_reference_sgs_output_structural_rules_nablp16():
             assert pe["src"] == r and (pe["src"], pe["dst"]) in und  # positives are out-edges of the root
         ids = {x["node_id"] for x in s["neighborhood"]["nodes"]}
         assert r in ids and all(pe["dst"] in ids for pe in s["pos_edges"])
+
+
+def test_weighted_ops_oracle_semantics():
+    """np_sample_op_weighted (the checker of gigl_sample_op_weighted_dev): ORDER BY weight DESC LIMIT k of
+    NebulaQueryResponseTranslator.scala:90-105 on a hand graph, and the seeded RandomWeighted draw."""
+    from oracle import oracle as O
+
+    #          in-neighbours of 0: 1..6 with weights; of 1: one edge; 2: none
+    src = np.array([1, 2, 3, 4, 5, 6, 0])
+    dst = np.array([0, 0, 0, 0, 0, 0, 1])
+    w_rec = np.array([0.5, 2.0, 2.0, np.nan, -1.0, 0.5, 9.0], dtype=np.float32)
+    rowptr, col = O.np_build_in_csr(src, dst, 7, True)
+    w = w_rec[np.lexsort((src, dst))]  # CSR order: by dst, then src
+    roots = np.array([0, 1, 2], dtype=np.int32)
+    nbr, cnt = O.np_sample_op_weighted((rowptr, col), w, roots, [4], [], 1, "top_k")
+    assert cnt.tolist() == [4, 1, 0]
+    assert nbr.reshape(3, 4)[0].tolist() == [2, 3, 1, 6]      # 2.0 (lower id first), 2.0, then the two 0.5s by id
+    assert nbr.reshape(3, 4)[1].tolist() == [0, -1, -1, -1]
+    nbr, cnt = O.np_sample_op_weighted((rowptr, col), w, roots, [8], [], 1, "top_k")
+    assert nbr.reshape(3, 8)[0].tolist() == [2, 3, 1, 6, 5, 4, -1, -1]   # the NaN edge last
+    # RandomWeighted: deterministic, a subset of the row, depends on the call number, zero-weight edges never beat positive ones
+    a, _ = O.np_sample_op_weighted((rowptr, col), w, roots, [3], [], 1, "random_weighted")
+    b, _ = O.np_sample_op_weighted((rowptr, col), w, roots, [3], [], 1, "random_weighted")
+    assert np.array_equal(a, b) and set(a.reshape(3, 3)[0]) <= {1, 2, 3, 4, 5, 6}
+    diff = [not np.array_equal(a, O.np_sample_op_weighted((rowptr, col), w, roots, [3], [], c, "random_weighted")[0]) for c in range(2, 12)]
+    assert any(diff)
+    w0 = np.where(np.isnan(w) | (w < 1), 0, w).astype(np.float32)
+    z, _ = O.np_sample_op_weighted((rowptr, col), w0, roots, [2], [], 5, "random_weighted")
+    assert set(z.reshape(3, 2)[0]) == {2, 3}
+
+
+def test_sampling_op_config_methods():
+    """The three sampling methods of a SamplingOp in the YAML / JSON form (the op names and fields of the reference's
+    SamplingOpToNebulaQueryTranslatorTest.scala:44-118); userDefined is rejected like the reference's NotImplementedError."""
+    from gigl_b200 import dag
+
+    et = {"srcNodeType": "user", "relation": "to", "dstNodeType": "story"}
+    ops = dag.ops_from_config({"samplingOps": [
+        {"opName": "SamplingOpRandomUniform", "edgeType": et, "randomUniform": {"numNodesToSample": 10}},
+        {"opName": "SamplingOpRandomWeighted", "edgeType": et, "randomWeighted": {"numNodesToSample": 10, "edgeFeatName": "edgeFeatName"}},
+        {"opName": "SamplingOpTopK", "edgeType": et, "topK": {"numNodesToSample": 10, "edgeFeatName": "edgeFeatName"}}]})
+    assert [(o.sampling_method, o.edge_feat_name, o.num_nodes_to_sample) for o in ops] == [
+        ("random_uniform", "", 10), ("random_weighted", "edgeFeatName", 10), ("top_k", "edgeFeatName", 10)]
+    for bad in ({"opName": "u", "edgeType": et, "userDefined": {"pathToUdf": "x"}},
+                {"opName": "t", "edgeType": et, "topK": {"numNodesToSample": 3}},
+                {"opName": "n", "edgeType": et}):
+        with pytest.raises(ValueError):
+            dag.ops_from_config({"samplingOps": [bad]})
