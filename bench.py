@@ -72,6 +72,8 @@ def parse_args(argv=None):
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-graph", action="store_true")
     ap.add_argument("--e2e-padded", action="store_true", help="e2e returns the padded-tree index sets instead of the packed form")
+    ap.add_argument("--e2e-ids", choices=["bits", "int32"], default="bits",
+                    help="packed e2e form: ids as a ceil(log2 n)-bit stream (gigl_infer_khop_sage_bitpacked_host) or as int32")
     ap.add_argument("--features", default="auto", choices=["auto", "sharded", "replicated"],
                     help="auto = local table at N = 1, sharded over the N GPUs (NVLink halo) at N > 1")
     ap.add_argument("--halo", default="staged", choices=["staged", "direct"],
@@ -525,7 +527,7 @@ class Run:
         return {k: v / K for k, v in tot.items()}
 
     # ---- end to end through the host entry points ----------------------------------------------
-    def measure_e2e(self, K, W, padded=False, embeddings_only=False, streams=1):
+    def measure_e2e(self, K, W, padded=False, embeddings_only=False, streams=1, ids="bits"):
         """The same K batches through the blocking host entry points: one caller thread per pipe (the call is synchronous -
         roots in, results in host memory out - so several batches are in flight only if several callers are)."""
         torch, env = self.env.torch, self.env
@@ -558,6 +560,16 @@ class Run:
                                                     out=out_pin.numpy(), samples_out=s_out)
                         d2h_steps.append(B * O_dim * 4 + n_ints * 4)
                     api = "gigl_infer_khop_sage_host: roots in pinned host memory -> padded-tree index sets + root embeddings in pinned host memory"
+                elif ids == "bits":
+                    words_pin = torch.empty(sum(t.numel() for t in nbr_pin) + 1, dtype=torch.int32).pin_memory()
+                    w_out = (words_pin.numpy().view(np.uint32), [t.numpy() for t in cnt8_pin])
+
+                    def host_step(i, p=p, out_pin=out_pin, w_out=w_out, n_cnt=sum(t.numel() for t in cnt8_pin)):
+                        _, words, _, _, _ = p["g"].infer_khop_sage_bitpacked_host(p["batch"], p["model"], roots_pin[i].numpy(), fan,
+                                                                                  out=out_pin.numpy(), packed_out=w_out)
+                        d2h_steps.append(B * O_dim * 4 + words.size * 4 + n_cnt)
+                    api = ("gigl_infer_khop_sage_bitpacked_host: roots in pinned host memory -> packed index sets [one-byte counts + filled "
+                           "slots as a ceil(log2 n_nodes)-bit stream] + root embeddings in pinned host memory")
                 else:
                     packed_pin = torch.empty(sum(t.numel() for t in nbr_pin), dtype=torch.int32).pin_memory()
                     p_out = (packed_pin.numpy(), [t.numpy() for t in cnt8_pin])
@@ -777,7 +789,7 @@ def measure(env: Env, args, wl_name, features, K, W, want_e2e, want_cpu, want_fu
     if want_full and not run.sharded:
         rec["full_graph_aggregate"] = run.full_graph()
     if want_e2e:
-        rec["e2e"] = run.measure_e2e(K, W, padded=args.e2e_padded, streams=args.streams)
+        rec["e2e"] = run.measure_e2e(K, W, padded=args.e2e_padded, streams=args.streams, ids=args.e2e_ids)
         rec["e2e_embeddings_only"] = run.measure_e2e(K, W, embeddings_only=True, streams=args.streams)
     if want_cpu:
         if env.rank == 0:

@@ -6,4 +6,4 @@ importing this package does not load it, the first use does, and raises if it is
 __version__ = "0.2.0"
 
 from ._capi import GiglError  # noqa: F401
-from .engine import Batch, Context, Graph, SageModel, unpack_tree  # noqa: F401
+from .engine import Batch, Context, Graph, SageModel, unpack_bits, unpack_tree  # noqa: F401

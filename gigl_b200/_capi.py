@@ -104,6 +104,8 @@ SIGNATURES = {
     "gigl_examples_column_host": (C.c_int, [vp, i64, vp, vp, cp, i32, i32, vp, vp]),
     "gigl_infer_khop_sage_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, pvp, pvp]),
     "gigl_infer_khop_sage_packed_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, pvp, vp, i64, C.POINTER(i64)]),
+    "gigl_infer_khop_sage_bitpacked_host": (C.c_int, [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, pvp, vp, i64, C.POINTER(i64), C.POINTER(i32)]),
+    "gigl_unpack_bits_host": (C.c_int, [vp, i64, i32, vp]),
 }
 
 

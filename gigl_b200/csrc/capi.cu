@@ -926,7 +926,8 @@ int gigl_batch_sage_forward_dev(gigl_batch* b, const gigl_sage_model* m, const f
 static int infer_khop_sage_host_impl(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots, int64_t n_roots,
                                      const int32_t* fanouts, int32_t n_hops, int32_t base_seed, int32_t first_call_no, float* out,
                                      int32_t* const* nbr, int32_t* const* cnt, uint8_t* const* cnt_u8, int32_t* packed,
-                                     int64_t packed_cap, int64_t* n_packed) {
+                                     int64_t packed_cap, int64_t* n_packed, int32_t id_bits = 0) {
+    // id_bits > 0: `packed` is a bit stream of id_bits-bit ids in 32-bit words (packed_cap counts words)
     if (!g) return gigl_fail(nullptr, GIGL_E_INVALID, "null graph");
     gigl_ctx* ctx = g->ctx;
     GIGL_CHECK(ctx, b != nullptr && m != nullptr && batch_ctx(b) == ctx, "batch / model must belong to the graph's ctx");
@@ -1001,12 +1002,13 @@ static int infer_khop_sage_host_impl(gigl_graph* g, gigl_batch* b, const gigl_sa
     int32_t* goff_dev = nullptr;
     uint8_t* u8_dev = nullptr;
     int32_t* packed_dev = nullptr;
+    uint32_t* words_dev = nullptr;
     if (packing) {
         // the pack kernels (one scan + ~70 MB of traffic, tens of microseconds) run on the copy stream beside the collation
         GIGL_CUDA(ctx, cudaEventRecord(ctx->copy_ready, ctx->stream));
         GIGL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ready, 0));
         if ((rc = tree_pack_launch(ctx, ctx->copy_stream, n_roots, fanouts, n_hops, nbr_dev, cnt_dev[0], GIGL_SLOT_IO2, &goff_dev, &u8_dev,
-                                   &packed_dev)) != GIGL_OK)
+                                   &packed_dev, id_bits, &words_dev)) != GIGL_OK)
             return rc;
         GIGL_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack_total, goff_dev + n_parents, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
         GIGL_CUDA(ctx, cudaEventRecord(ctx->pack_ready, ctx->copy_stream));
@@ -1024,7 +1026,8 @@ static int infer_khop_sage_host_impl(gigl_graph* g, gigl_batch* b, const gigl_sa
             GIGL_CUDA(ctx, cudaEventSynchronize(ctx->pack_ready));  // long done: the collation synchronised the main stream twice
             const int64_t filled = *ctx->h_pack_total;
             *n_packed = filled;
-            if (filled > packed_cap) return gigl_fail(ctx, GIGL_E_INVALID, "packed buffer too small for the sampled index sets");
+            const int64_t n_words = id_bits > 0 ? (filled * id_bits + 31) / 32 : filled;
+            if (n_words > packed_cap) return gigl_fail(ctx, GIGL_E_INVALID, "packed buffer too small for the sampled index sets");
             size_t p0 = 0;
             width = 1;
             for (int h = 0; h < n_hops; ++h) {
@@ -1034,7 +1037,8 @@ static int infer_khop_sage_host_impl(gigl_graph* g, gigl_batch* b, const gigl_sa
                 width *= (size_t)fanouts[h];
             }
             if (filled > 0)
-                GIGL_CUDA(ctx, cudaMemcpyAsync(packed, packed_dev, sizeof(int32_t) * (size_t)filled, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                GIGL_CUDA(ctx, cudaMemcpyAsync(packed, id_bits > 0 ? (const void*)words_dev : (const void*)packed_dev, sizeof(int32_t) * (size_t)n_words,
+                                               cudaMemcpyDeviceToHost, ctx->copy_stream));
         } else {
             width = 1;
             for (int h = 0; h < n_hops; ++h) {
@@ -1084,6 +1088,35 @@ int gigl_infer_khop_sage_packed_host(gigl_graph* g, gigl_batch* b, const gigl_sa
     if (g && !packed) return gigl_fail(g->ctx, GIGL_E_INVALID, "null packed buffer");
     return infer_khop_sage_host_impl(g, b, m, roots, n_roots, fanouts, n_hops, base_seed, first_call_no, out, nullptr, nullptr, cnt_u8, packed,
                                      packed_cap, n_packed);
+}
+
+static int32_t id_bits_of(int64_t n_nodes) {
+    int32_t bits = 1;
+    while (bits < 31 && (1LL << bits) < n_nodes) ++bits;
+    return bits;
+}
+
+int gigl_infer_khop_sage_bitpacked_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots, int64_t n_roots,
+                                        const int32_t* fanouts, int32_t n_hops, int32_t base_seed, int32_t first_call_no, float* out,
+                                        uint8_t* const* cnt_u8, uint32_t* words, int64_t words_cap, int64_t* n_packed, int32_t* id_bits) {
+    if (g && (!words || !id_bits)) return gigl_fail(g->ctx, GIGL_E_INVALID, "null words / id_bits");
+    if (g) *id_bits = id_bits_of(g->n_nodes);
+    return infer_khop_sage_host_impl(g, b, m, roots, n_roots, fanouts, n_hops, base_seed, first_call_no, out, nullptr, nullptr, cnt_u8,
+                                     reinterpret_cast<int32_t*>(words), words_cap, n_packed, g ? *id_bits : 0);
+}
+
+int gigl_unpack_bits_host(const uint32_t* words, int64_t n, int32_t bits, int32_t* out) {
+    if (n < 0 || bits < 1 || bits > 31 || ((!words || !out) && n > 0)) return GIGL_E_INVALID;
+    const uint32_t mask = (1u << bits) - 1u;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t bit = i * bits;
+        const int64_t w = bit >> 5;
+        const int s = (int)(bit & 31);
+        uint32_t v = words[w] >> s;
+        if (s + bits > 32) v |= words[w + 1] << (32 - s);
+        out[i] = (int32_t)(v & mask);
+    }
+    return GIGL_OK;
 }
 
 }  // extern "C"

@@ -198,7 +198,7 @@ int gcn_conv_launch(gigl_ctx* ctx, int64_t n, int32_t F, int32_t O, const int64_
 // tree_pack.cu: padded tree -> goff (exclusive scan of the counts; goff[n_parents] = filled slots), one-byte counts, packed children
 int tree_pack_launch(gigl_ctx* ctx, cudaStream_t st, int64_t n_roots, const int32_t* fanouts, int32_t n_hops,
                      const int32_t* const* nbr_dev, const int32_t* cnt_all_dev, int slot, int32_t** goff_dev, uint8_t** cnt_u8_dev,
-                     int32_t** packed_dev);
+                     int32_t** packed_dev, int id_bits = 0, uint32_t** words_dev = nullptr);
 
 // batch_collate.cu
 struct gigl_batch;

@@ -452,6 +452,32 @@ class Graph:
                                                            C.byref(n_packed)), self.ctx.handle)
         return out, packed[: n_packed.value], cnt_u8
 
+    def infer_khop_sage_bitpacked_host(self, batch: "Batch", model: "SageModel", roots, fanouts: Sequence[int], base_seed: int = 42,
+                                       first_call_no: int = 1, out=None, packed_out=None):
+        """As :meth:`infer_khop_sage_packed_host` with the ids as a bit stream (gigl_infer_khop_sage_bitpacked_host): returns
+        (embeddings, words uint32 [ceil(n * bits / 32)], [cnt_u8 per hop], n, bits); `unpack_bits(words, n, bits)` gives the
+        int32 `packed` array of the packed form.  packed_out = (uint32 word buffer, [cnt_u8 buffers]) to reuse host memory."""
+        roots = _np(roots, np.int32)
+        fan = _np(fanouts, np.int32)
+        n_roots, n_hops = len(roots), len(fan)
+        if out is None:
+            out = np.empty((n_roots, model.dims[-1]), dtype=np.float32)
+        if packed_out is None:
+            cnt_u8, width, slots = [], 1, 0
+            for f in fan:
+                cnt_u8.append(np.empty(n_roots * width, dtype=np.uint8))
+                width *= int(f)
+                slots += n_roots * width
+            words = np.empty(max(slots, 1) + 1, dtype=np.uint32)
+        else:
+            words, cnt_u8 = packed_out
+        pc = (C.c_void_p * n_hops)(*[a.ctypes.data for a in cnt_u8])
+        n_packed, bits = C.c_int64(), C.c_int32()
+        check(self.ctx._L.gigl_infer_khop_sage_bitpacked_host(self.handle, batch.handle, model.handle, _hp(roots), n_roots, _hp(fan), n_hops,
+                                                              base_seed, first_call_no, _hp(out), pc, _hp(words), words.size,
+                                                              C.byref(n_packed), C.byref(bits)), self.ctx.handle)
+        return out, words[: (n_packed.value * bits.value + 31) // 32], cnt_u8, n_packed.value, bits.value
+
     def close(self) -> None:
         if self.handle and self.ctx.handle:
             self.ctx._L.gigl_graph_destroy(self.handle)
@@ -462,6 +488,15 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+
+def unpack_bits(words, n: int, bits: int) -> np.ndarray:
+    """The bit stream of gigl_infer_khop_sage_bitpacked_host -> int32 ids (what gigl_unpack_bits_host does, vectorised)."""
+    w = np.concatenate([np.asarray(words, dtype=np.uint32), np.zeros(1, np.uint32)]).astype(np.uint64)
+    bit = np.arange(n, dtype=np.int64) * bits
+    wi, s = bit >> 5, (bit & 31).astype(np.uint64)
+    v = (w[wi] >> s) | (w[wi + 1] << (np.uint64(32) - s))
+    return (v & np.uint64((1 << bits) - 1)).astype(np.int32)
 
 
 def unpack_tree(packed, cnt_u8: Sequence[np.ndarray], fanouts: Sequence[int]):

@@ -472,6 +472,19 @@ int gigl_infer_khop_sage_packed_host(gigl_graph* g, gigl_batch* b, const gigl_sa
                                      const int32_t* fanouts, int32_t n_hops, int32_t base_seed, int32_t first_call_no, float* out,
                                      uint8_t* const* cnt_u8 /* [n_hops] host */, int32_t* packed, int64_t packed_cap, int64_t* n_packed);
 
+/*
+ * The packed form again with the ids as a BIT STREAM: every filled slot takes *id_bits = ceil(log2(n_nodes)) bits (22 instead
+ * of 32 on a 2.4 M-node graph), entry e in bits [e * id_bits, (e + 1) * id_bits) of the little-endian 32-bit words; counts
+ * and order as in gigl_infer_khop_sage_packed_host.  *n_packed = entries (filled slots); ceil(n_packed * id_bits / 32) words
+ * are written (<= words_cap, else GIGL_E_INVALID).  gigl_unpack_bits_host (pure host code) turns the stream back into int32
+ * ids.  Why: on an 8-GPU host the device-to-host copies bound the end-to-end rate (about 100 GB/s for the whole box measured,
+ * 12 GB/s per GPU), so bytes returned are throughput.
+ */
+int gigl_infer_khop_sage_bitpacked_host(gigl_graph* g, gigl_batch* b, const gigl_sage_model* m, const int32_t* roots, int64_t n_roots,
+                                        const int32_t* fanouts, int32_t n_hops, int32_t base_seed, int32_t first_call_no, float* out,
+                                        uint8_t* const* cnt_u8, uint32_t* words, int64_t words_cap, int64_t* n_packed, int32_t* id_bits);
+int gigl_unpack_bits_host(const uint32_t* words, int64_t n, int32_t bits, int32_t* out);
+
 /* ---- the sampler's file contract: TFRecord + tf.Example + sample protos (host code) ----------- */
 
 /* masked crc32c of TFRecord framing: rotr15(crc32c(data)) + 0xA282EAD8 */

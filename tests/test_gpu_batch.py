@@ -180,6 +180,17 @@ def test_host_entry_point_packed_index_sets(env, fan, directed):
         g.infer_khop_sage_packed_host(batch, model, roots, fan, packed_out=small)
     out2, _, _ = g.infer_khop_sage_packed_host(batch, model, roots, fan)  # the ctx is usable after the error
     assert np.array_equal(out2, out_p)
+    # the bit-stream form: ceil(log2(n)) bits per id, the same entries in the same order
+    from gigl_b200 import unpack_bits
+
+    out_b, words, cnt_b, n_ids, bits = g.infer_khop_sage_bitpacked_host(batch, model, roots, fan)
+    assert bits == 12 and n_ids == len(packed) and words.dtype == np.uint32 and len(words) == (n_ids * bits + 31) // 32
+    assert np.array_equal(out_b, out_p) and all(np.array_equal(a, c) for a, c in zip(cnt_b, cnt_u8))
+    assert np.array_equal(unpack_bits(words, n_ids, bits), packed)
+    ids = np.empty(n_ids, dtype=np.int32)
+    assert ctx._L.gigl_unpack_bits_host(words.ctypes.data, n_ids, bits, ids.ctypes.data) == 0 and np.array_equal(ids, packed)
+    with pytest.raises(GiglError):
+        g.infer_khop_sage_bitpacked_host(batch, model, roots, fan, packed_out=(np.empty(3, dtype=np.uint32), cnt_b))
 
 
 def test_large_batch_properties(env):

@@ -95,6 +95,30 @@ def test_unpack_tree_inverts_the_packed_layout(fan):
         unpack_tree(np.concatenate(packed)[:-1], [c.astype(np.uint8) for c in cnt], fan)
 
 
+@pytest.mark.parametrize("bits", [1, 7, 17, 22, 27, 31])
+def test_unpack_bits_inverts_the_bit_stream(bits):
+    """The bit stream of gigl_infer_khop_sage_bitpacked_host (entry e in bits [e * bits, (e + 1) * bits) of little-endian 32-bit
+    words): the numpy unpacker and the C-ABI's host helper against a bit-by-bit packer."""
+    import ctypes as C
+
+    from gigl_b200 import _capi, unpack_bits
+
+    rng = np.random.default_rng(bits)
+    for n in (0, 1, 33, 1000):
+        ids = rng.integers(0, 1 << bits, n, dtype=np.int64)
+        stream = 0
+        for e, v in enumerate(ids.tolist()):
+            stream |= v << (e * bits)
+        n_words = (n * bits + 31) // 32
+        words = np.array([(stream >> (32 * j)) & 0xFFFFFFFF for j in range(n_words)], dtype=np.uint32)
+        assert np.array_equal(unpack_bits(words, n, bits), ids.astype(np.int32))
+        out = np.full(max(n, 1), -1, dtype=np.int32)
+        buf = words if n_words else np.zeros(1, np.uint32)
+        assert _capi.lib().gigl_unpack_bits_host(C.c_void_p(buf.ctypes.data), n, bits, C.c_void_p(out.ctypes.data)) == 0
+        assert np.array_equal(out[:n], ids.astype(np.int32))
+    assert _capi.lib().gigl_unpack_bits_host(None, 5, 0, None) != 0
+
+
 def test_sampler_component_root_shares_partition_the_roots():
     from gigl_b200 import subgraph_sampler as ss
 
