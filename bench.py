@@ -82,7 +82,7 @@ def parse_args(argv=None):
     ap.add_argument("--hot-rows", type=float, default=None,
                     help="sharded features: fraction of the table (highest in-degree vertices) replicated on every GPU "
                          "(default: GIGL_HOT_ROWS or 0 = off)")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=3,
                     help="batches in flight per GPU: step i runs on stream i %% S with its own context / workspace, so the host "
                          "reads and kernel tails of one batch are covered by the other's kernels (1 = strictly one after the other)")
     ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the replicated variant and the g1b record")

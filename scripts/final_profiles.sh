@@ -5,7 +5,7 @@ LIGHT="--steps 1 --warmup 1 --streams 1 --no-e2e --no-cpu-baseline --no-full-gra
 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err
 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_reference_arm_1gpu.json 2> gpurun_out/r2_reference_arm_1gpu.err
 python bench.py --steps 20 --warmup 5 --streams 1 --no-cpu-baseline --no-full-graph > gpurun_out/r2_bench_1gpu_streams1.json 2> /dev/null
-python bench.py --steps 20 --warmup 5 --streams 3 --no-cpu-baseline --no-full-graph > gpurun_out/r2_bench_1gpu_streams3.json 2> /dev/null
+python bench.py --steps 20 --warmup 5 --streams 2 --no-cpu-baseline --no-full-graph > gpurun_out/r2_bench_1gpu_streams2.json 2> /dev/null
 # DRAM bytes + time of every launch of one step (roofline.traffic)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --kernel-name regex:"$KR" -c 400 --csv \
     --log-file gpurun_out/r2_traffic.csv python bench.py $LIGHT > /dev/null 2> gpurun_out/r2_traffic.err
