@@ -54,6 +54,8 @@ WORKLOADS = {
     # BASELINE.json configs[4]: Inferencer full-graph embedding export = layer-wise inference over EVERY node:
     # N = 1e8 / E = 2e9, 128 -> 128 -> 128; g2b-small = 1/64 scale.  Metric of these two: aggregated-edges/sec.
     "g2b": dict(nodes=100_000_000, pairs=2_000_000_000, F=128, H=128, O=128, directed=True, layerwise=True, cfg="configs[4]"),
+    "g2b-eighth": dict(nodes=12_500_000, pairs=250_000_000, F=128, H=128, O=128, directed=True, layerwise=True,
+                       cfg="configs[4] at 1/8 scale (one GPU's share of the 8-GPU run)"),
     "g2b-small": dict(nodes=1_562_500, pairs=31_250_000, F=128, H=128, O=128, directed=True, layerwise=True, cfg="configs[4] at 1/64 scale"),
 }
 
@@ -845,15 +847,50 @@ def measure_layerwise(env: Env, args, wl_name, K, W, tag):
     A = torch.empty((rows, 2 * max(F, H)), dtype=torch.float32, device=dev)
     my_rowptr = rowptr[lo:hi + 1]
     my_edges = int((rowptr[hi] - rowptr[lo]).item())
+    # N > 1: a rank's rows have in-neighbours all over the graph, so gathering straight from the sharded table moves one
+    # (mostly remote) row per EDGE over NVLink.  With room in HBM the layer's input table is pulled into a transient local
+    # replica first - one row per NODE, the all-gather volume - and the gather runs from local HBM.  GIGL_LAYERWISE=direct
+    # keeps the per-edge peer loads (and is what runs when the replica does not fit).
+    replica, ag_ms, parts = None, [], []
+    if world > 1 and os.environ.get("GIGL_LAYERWISE", "replica") != "direct":  # replica | replica_memcpy | direct
+        need = N * max(tx.table.shape[1], th.table.shape[1]) * 4
+        torch.cuda.empty_cache()  # the graph build's temporaries
+        free, _ = torch.cuda.mem_get_info(dev)
+        if need + (12 << 30) < free:
+            replica = torch.empty(need // 4, dtype=torch.float32, device=dev)
     ctx.sync()
     env.barrier()
 
     def layer(table_flat, mine, Fin, Wc, b, relu, dst_rows):
+        if replica is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rep = replica[: N * table_flat.shape[1]].view(N, table_flat.shape[1])
+            e0.record()
+            # peer reads through the flat mapping: (world - 1) / world of it crosses NVLink
+            if os.environ.get("GIGL_LAYERWISE", "replica") == "replica_memcpy":
+                rep.copy_(table_flat)   # cudaMemcpy over the peer mapping: measured 108 GB/s, the copy kernel below 540-650
+            else:
+                # ring order - rank r pulls shards r, r + 1, ... - so every owner serves ONE reader at a time; all ranks walking
+                # the table front to back queue up on one GPU's NVLink egress (measured: the step 2x longer at N = 8)
+                for k in range(world):
+                    s_lo = ((rank + k) % world) * tx.rows_per_shard
+                    s_hi = min(N, s_lo + tx.rows_per_shard)
+                    if s_hi > s_lo:
+                        torch.mul(table_flat[s_lo:s_hi], 1.0, out=rep[s_lo:s_hi])
+            e1.record()
+            ag_ms.append((e0, e1))
+            table_flat = rep
+        t0, t1, t2, t3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        t0.record()
         agg = ctx.gather_mean(table_flat, my_rowptr, col, n_rows_out=rows)   # mean of the in-neighbours' rows, local or peer
+        t1.record()
         a = A[:, : 2 * Fin]
         a[:, :Fin].copy_(agg)
         a[:, Fin:].copy_(mine[:rows])
+        t2.record()
         ctx.linear(a, Wc, b, relu=relu, out=dst_rows)
+        t3.record()
+        parts.append((t0, t1, t2, t3))
 
     def step():
         layer(x_flat, x_mine, F, W1, b1, True, h_mine[:rows])
@@ -865,6 +902,8 @@ def measure_layerwise(env: Env, args, wl_name, K, W, tag):
 
     for _ in range(W):
         step()
+    ag_ms.clear()
+    parts.clear()
     ctx.set_timing(True)
     ctx.reset_timing()
     l0 = ctx.launch_count
@@ -886,6 +925,18 @@ def measure_layerwise(env: Env, args, wl_name, K, W, tag):
     total_edges = int(g.n_edges)
     hbm, _, src_peak = measured_peaks()
     g_ms = timings.get("gather_full", (0.0, 0))[0] / K / 2  # per layer
+    torch.cuda.synchronize()
+    layer_ms = {"gather": float(np.mean([p[0].elapsed_time(p[1]) for p in parts])),
+                "assemble_mean_self": float(np.mean([p[1].elapsed_time(p[2]) for p in parts])),
+                "projection": float(np.mean([p[2].elapsed_time(p[3]) for p in parts]))}
+    allgather = None
+    if replica is not None:
+        torch.cuda.synchronize()
+        per_layer = float(np.mean([a.elapsed_time(b) for a, b in ag_ms]))
+        remote = (N - rows) * F * 4
+        allgather = {"ms_per_layer": per_layer, "remote_bytes_per_layer": remote, "nvlink_GBps_in": remote / (per_layer * 1e-3) / 1e9,
+                     "replica_bytes": int(replica.numel()) * 4,
+                     "note": "the layer's input table copied into a transient local replica (one row per node) before the gather"}
     bytes_layer = my_edges * (4 * F + 4) + (rows + 1) * 8  # SURVEY 8(d) gather terms of bytes_A (the self rows are read by the copy)
     ach = bytes_layer / (g_ms * 1e-3) / 1e9 if g_ms else None
     rec = {"metric": "aggregated-edges/sec", "value": 2.0 * total_edges * K / (ms * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": K,
@@ -894,10 +945,13 @@ def measure_layerwise(env: Env, args, wl_name, K, W, tag):
            "config": {"workload": f"BASELINE.json {wl['cfg']} shape: {wl_name} synthetic RMAT graph, N={N}, {wl['pairs']} directed edges, "
                                   f"layer-wise full-graph GraphSAGE {F}->{H}->{O} (every node's embedding)",
                       "rows_per_gpu": rows, "edges_per_gpu": my_edges,
-                      "residency": "CSR replicated; input and hidden tables sharded by node range and mapped flat (peer loads over NVLink)"
+                      "residency": ("CSR replicated; input and hidden tables sharded by node range and mapped flat; "
+                                    + ("each layer's input pulled into a transient local replica over NVLink, then gathered locally"
+                                       if replica is not None else "per-edge peer loads over NVLink"))
                                    if world > 1 else "CSR, input, hidden and output tables resident on the one GPU"},
+           "allgather": allgather, "ms_per_layer": layer_ms,
            "phase_ms_per_step": {k: v[0] / K for k, v in timings.items()},
-           "roofline": {"kernel": "gather_rows_kernel / gather_heavy_kernel (full-graph mean aggregate of one layer)", "bound": "hbm" if world == 1 else "nvlink (remote rows) / hbm",
+           "roofline": {"kernel": "gather_rows_kernel / gather_heavy_kernel (full-graph mean aggregate of one layer)", "bound": "hbm" if world == 1 or replica is not None else "nvlink (remote rows) / hbm",
                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm if ach else None, "traffic": None,
                         "algorithmic_bytes_per_launch": bytes_layer, "formula": "8(d) bytes_A gather terms: e (4 F + 4) + (n + 1) 8",
                         "ms_per_launch": g_ms, "peak_source": src_peak},
