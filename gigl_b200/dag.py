@@ -46,6 +46,15 @@ class SamplingOp:
         return self.edge_type[0] if self.sampling_direction == INCOMING else self.edge_type[2]
 
 
+class SamplingValidationError(ValueError):
+    """A SamplingOp DAG the reference's config validation rejects.  `error_type` carries the name of the reference's
+    SubgraphSamplingValidationErrorType member (python/gigl/src/common/types/exception.py:4-16)."""
+
+    def __init__(self, message: str, error_type: str):
+        super().__init__(message)
+        self.error_type = error_type
+
+
 _METHOD_KEYS = {"randomUniform": "random_uniform", "randomWeighted": "random_weighted", "topK": "top_k"}
 
 
@@ -83,7 +92,7 @@ def plan(ops: Sequence[SamplingOp], root_node_type: str) -> List[PlannedOp]:
     op's result set is the union of its instances' outputs.  Instances of one op share its call number."""
     by_name = {o.op_name: o for o in ops}
     if len(by_name) != len(ops):
-        raise ValueError("duplicate op names")
+        raise SamplingValidationError("duplicate op names", "REPEATED_OP_NAME")
     instances: Dict[str, List[PlannedOp]] = {}   # op name -> its planned instances
     order: List[PlannedOp] = []
     pending = list(ops)
@@ -97,19 +106,21 @@ def plan(ops: Sequence[SamplingOp], root_node_type: str) -> List[PlannedOp]:
                 raise ValueError(f"op {o.op_name!r} names an input op twice")
             for par in o.input_op_names:
                 if par not in by_name:
-                    raise ValueError(f"op {o.op_name!r} names an unknown input op {par!r}")
+                    raise SamplingValidationError(f"op {o.op_name!r} names an unknown input op {par!r}", "BAD_INPUT_OP_NAME")
             if any(par not in instances for par in o.input_op_names):
                 continue
             n_done += 1
             made = []
             if not o.input_op_names:
                 if o.frontier_node_type != root_node_type:
-                    raise ValueError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {root_node_type!r}")
+                    raise SamplingValidationError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {root_node_type!r}",
+                                                  "CONTAINS_INVALID_EDGE_IN_DAG")
                 made.append(PlannedOp(o, n_done, None, [o.op_name], o.op_name, [o.num_nodes_to_sample]))
             for par in o.input_op_names:
                 want = by_name[par].result_node_type
                 if o.frontier_node_type != want:
-                    raise ValueError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {want!r}")
+                    raise SamplingValidationError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {want!r}",
+                                                  "CONTAINS_INVALID_EDGE_IN_DAG")
                 for pi in instances[par]:
                     single = len(o.input_op_names) == 1 and len(instances[par]) == 1
                     key = o.op_name if single else f"{o.op_name}@{pi.key}"
@@ -119,8 +130,77 @@ def plan(ops: Sequence[SamplingOp], root_node_type: str) -> List[PlannedOp]:
             pending.remove(o)
             progressed = True
         if not progressed:
-            raise ValueError("sampling ops contain a cycle")
+            if not any(not o.input_op_names for o in ops):
+                raise SamplingValidationError("no sampling op expands the root node", "MISSING_ROOT_SAMPLING_OP")
+            raise SamplingValidationError("sampling ops contain a cycle", "DAG_CONTAINS_CYCLE")
     return order
+
+
+def task_root_node_types(task_metadata: dict) -> set:
+    """The node types a task roots its samples at (TaskMetadataPbWrapper.get_task_root_node_types,
+    python/gigl/src/common/types/pb_wrappers/task_metadata.py:123-145): both endpoints of every supervision edge type of a
+    link task, the supervision node types of a node task."""
+    for key in ("nodeAnchorBasedLinkPredictionTaskMetadata", "linkBasedTaskMetadata"):
+        if key in task_metadata:
+            out = set()
+            for e in task_metadata[key].get("supervisionEdgeTypes") or []:
+                out |= {e["srcNodeType"], e["dstNodeType"]}
+            return out
+    if "nodeBasedTaskMetadata" in task_metadata:
+        return set(task_metadata["nodeBasedTaskMetadata"].get("supervisionNodeTypes") or [])
+    raise ValueError("taskMetadata names no task")
+
+
+def validate_strategy(paths: Sequence[dict], graph_metadata: dict, task_metadata: dict) -> Dict[str, List[SamplingOp]]:
+    """The checks of the reference's config validation on `subgraphSamplingStrategy.messagePassingPaths.paths`
+    (SubgraphSamplingStrategyPbWrapper / MessagePassingPathPbWrapper, python/gigl/src/common/types/pb_wrappers/
+    subgraph_sampling_strategy.py:22-283; SamplingOpPbWrapper.check_sampling_op_edge_type_validity), in its order and with
+    its error types: per path unique op names and known input ops, one path per root node type; then per path the root type in
+    the graph metadata and among the task's root types, a root op unless the path has no ops at all (a 0-hop neighbourhood),
+    every op's edge type in the graph metadata and aligned with its inputs (an op expands the nodes its inputs yield - the
+    four INCOMING / OUTGOING parent / child rules in one), no cycle; finally every root type of the task has a path.
+    Returns {root node type: ops}."""
+    by_root: Dict[str, List[SamplingOp]] = {}
+    for path in paths:
+        ops = ops_from_config(path)
+        names = set()
+        for o in ops:
+            if o.op_name in names:
+                raise SamplingValidationError(f"repeated op name {o.op_name!r} in one path", "REPEATED_OP_NAME")
+            names.add(o.op_name)
+        for o in ops:
+            for par in o.input_op_names:
+                if par not in names:
+                    raise SamplingValidationError(f"op {o.op_name!r} names an unknown input op {par!r}", "BAD_INPUT_OP_NAME")
+        root = path["rootNodeType"]
+        if root in by_root:
+            raise SamplingValidationError(f"two paths for root node type {root!r}", "REPEATED_ROOT_NODE_TYPE")
+        by_root[root] = ops
+    node_types = set(graph_metadata.get("nodeTypes") or [])
+    edge_types = {(e["srcNodeType"], e["relation"], e["dstNodeType"]) for e in graph_metadata.get("edgeTypes") or []}
+    expected = task_root_node_types(task_metadata)
+    for root, ops in by_root.items():
+        if root not in node_types:
+            raise SamplingValidationError(f"root node type {root!r} is not in the graph metadata", "ROOT_NODE_TYPE_NOT_IN_GRAPH_METADATA")
+        if root not in expected:
+            raise SamplingValidationError(f"root node type {root!r} is neither in a supervision edge type nor a supervision node type",
+                                          "ROOT_NODE_TYPE_NOT_IN_TASK_METADATA")
+        expected.discard(root)
+        if ops and not any(not o.input_op_names for o in ops):
+            raise SamplingValidationError(f"the path of {root!r} has no sampling op from the root node", "MISSING_ROOT_SAMPLING_OP")
+        by_name = {o.op_name: o for o in ops}
+        for o in ops:
+            if o.edge_type not in edge_types:
+                raise SamplingValidationError(f"op {o.op_name!r}: edge type {o.edge_type} is not in the graph metadata",
+                                              "SAMPLING_OP_EDGE_TYPE_NOT_IN_GRAPH_METADATA")
+            for want in ([root] if not o.input_op_names else [by_name[par].result_node_type for par in o.input_op_names]):
+                if o.frontier_node_type != want:
+                    raise SamplingValidationError(f"op {o.op_name!r} expands {o.frontier_node_type!r} nodes but its input yields {want!r}",
+                                                  "CONTAINS_INVALID_EDGE_IN_DAG")
+        plan(ops, root)  # DAG_CONTAINS_CYCLE
+    if expected:
+        raise SamplingValidationError(f"no path for the task's root node types {sorted(expected)}", "MISSING_EXPECTED_ROOT_NODE_TYPE")
+    return by_root
 
 
 def frontier_of(p: PlannedOp, res: dict, frontiers: dict, distinct):

@@ -422,6 +422,8 @@ def _run_typed(cfg, meta, sgs, root, device, batch_roots, job_name, log, t0) -> 
         raise ValueError("graphs with several node / edge types need subgraphSamplingStrategy.messagePassingPaths")
     flat = shared["flattenedGraphMetadata"]
     task_meta = cfg.get("taskMetadata", {})
+    # what the reference's config validation rejects before any component runs (subgraph_sampling_strategy.py:160-283)
+    dag.validate_strategy(strat.get("paths") or [], gm, task_meta)
     sup_et = None
     if "nodeAnchorBasedLinkPredictionOutput" in flat:
         out_dirs = dict(flat["nodeAnchorBasedLinkPredictionOutput"].get("nodeTypeToRandomNegativeTfrecordUriPrefix") or {})
