@@ -116,6 +116,70 @@ def batch_from_sample_protos(samples: Iterable[dict], device, label_dtype=torch.
         node_ids=torch.from_numpy(inv).to(device))
 
 
+@dataclass
+class SupervisionEdges:
+    """NodeAnchorBasedLinkPredictionBatch.BatchSupervisionEdgeData of the reference
+    (node_anchor_based_link_prediction_data_loader.py:58-66) for ONE condensed edge type."""
+
+    root_node_to_target_node_id: Dict[int, torch.Tensor]                    # local root id -> int64 local ids of its targets
+    label_edge_features: Optional[Dict[int, torch.Tensor]] = None           # local root id -> [n_targets, Fe] (user-defined labels)
+
+
+@dataclass
+class SampledLinkBatch:
+    """NodeAnchorBasedLinkPredictionBatch of the reference (node_anchor_based_link_prediction_data_loader.py:68-230): the
+    coalesced batch graph in local ids + per condensed edge type the roots' positive and hard-negative targets."""
+
+    graph: SampledNodeBatch
+    root_nodes: torch.Tensor                                                 # int64 [B] local ids of the roots, in sample order
+    pos_supervision_edge_data: Dict[int, SupervisionEdges]
+    hard_neg_supervision_edge_data: Dict[int, SupervisionEdges]
+    edge_attr: Optional[torch.Tensor] = None                                 # [e, Fe] features of the message-passing edges
+
+
+def link_batch_from_sample_protos(samples: Iterable[dict], device) -> SampledLinkBatch:
+    """collate_pyg_node_anchor_based_link_prediction_minibatch (node_anchor_based_link_prediction_data_loader.py:90-230) on
+    parsed NodeAnchorBasedLinkPredictionSample protos (``sample_io.parse_nablp_sample`` dicts): the neighbourhoods are
+    unioned with the graph-builder rules of :func:`batch_from_sample_protos` - an edge shared by k samples is message-passed
+    once, a node of two samples keeps the union of its sampled edges - and every root is mapped to the local ids of the
+    targets of its pos / hard-neg edges, per condensed edge type, with the label edges' features when they carry any."""
+    samples = list(samples)
+    g = batch_from_sample_protos(samples, device)
+    local = {int(v): i for i, v in enumerate(g.node_ids.tolist())}
+    pos: Dict[int, SupervisionEdges] = {}
+    neg: Dict[int, SupervisionEdges] = {}
+
+    def fill(store, root, edges):
+        by_type: Dict[int, list] = {}
+        for e in edges:
+            by_type.setdefault(int(e.get("condensed_edge_type") or 0), []).append(e)
+        for cet, es in by_type.items():
+            d = store.setdefault(cet, SupervisionEdges({}))
+            d.root_node_to_target_node_id[root] = torch.tensor([local[e["dst_node_id"]] for e in es], dtype=torch.int64, device=device)
+            feats = [np.asarray(e.get("feature_values") or [], dtype=np.float32) for e in es]
+            if feats and all(len(f) > 0 for f in feats):
+                if d.label_edge_features is None:
+                    d.label_edge_features = {}
+                d.label_edge_features[root] = torch.from_numpy(np.stack(feats)).to(device)
+
+    roots = []
+    for s in samples:
+        r = local[s["root_node"]["node_id"]]
+        roots.append(r)
+        fill(pos, r, s.get("pos_edges") or [])
+        fill(neg, r, s.get("hard_neg_edges") or [])
+    feat_of = {}
+    for s in samples:
+        for ed in s["edges"]:
+            feat_of.setdefault((ed["src_node_id"], ed["dst_node_id"]), ed.get("feature_values") or [])
+    ids = g.node_ids.tolist()
+    ei = g.edge_index.cpu().numpy()
+    attrs = [np.asarray(feat_of[(ids[a], ids[b])], dtype=np.float32) for a, b in zip(ei[0], ei[1])]
+    edge_attr = torch.from_numpy(np.stack(attrs)).to(device) if attrs and all(len(a) > 0 for a in attrs) else None
+    return SampledLinkBatch(graph=g, root_nodes=torch.tensor(roots, dtype=torch.int64, device=device), pos_supervision_edge_data=pos,
+                            hard_neg_supervision_edge_data=neg, edge_attr=edge_attr)
+
+
 def _feature_dim(gbml_config_pb_wrapper, default: Optional[int]) -> int:
     w = gbml_config_pb_wrapper
     try:

@@ -119,3 +119,111 @@ def test_pruned_and_full_inference_agree_on_the_roots():
         ea = a.infer_batch(batch).embeddings
         eb = b.infer_batch(batch).embeddings
         assert float((ea - eb).abs().max()) <= 1e-5 * max(1.0, float(eb.abs().max()))
+
+
+# ---- the reference's NodeAnchorBasedLinkPrediction / SupervisedNodeClassification batching tests -----------------------
+def _node(i):
+    return {"node_id": i, "condensed_node_type": 0, "feature_values": [0.0]}
+
+
+def _edge(s, d, feat=None):
+    return {"src_node_id": s, "dst_node_id": d, "condensed_edge_type": 0, "feature_values": list(feat or [])}
+
+
+def _nablp(root, nodes, edges, pos, hard_neg):
+    return {"root_node": _node(root), "nodes": [_node(i) for i in nodes], "edges": [_edge(*e) for e in edges],
+            "pos_edges": [_edge(*e) for e in pos], "hard_neg_edges": [_edge(*e) for e in hard_neg], "neg_edges": []}
+
+
+# node_anchor_based_link_prediction_batching_test.py:60-190: triangle rooted at 0 (pos 0->1, hard neg 0->3), line rooted at 3
+# (pos 3->4, hard neg 3->0), chain rooted at 2 (pos 2->3, hard neg 2->4)
+_TRIANGLE = _nablp(0, [0, 1, 2, 3], [(0, 1), (0, 2), (1, 2)], [(0, 1)], [(0, 3)])
+_LINE = _nablp(3, [3, 4, 0], [(3, 4)], [(3, 4)], [(3, 0)])
+_CHAIN = _nablp(2, [1, 2, 3, 4], [(1, 2), (2, 3)], [(2, 3)], [(2, 4)])
+
+
+@pytest.mark.parametrize("pair,n_nodes,edges,pos,hard_neg", [
+    ((_TRIANGLE, _LINE), 5, {(0, 1), (0, 2), (1, 2), (3, 4)}, {0: [1], 3: [4]}, {0: [3], 3: [0]}),      # :391-445 without edge overlap
+    ((_TRIANGLE, _CHAIN), 5, {(0, 1), (0, 2), (1, 2), (2, 3)}, {0: [1], 2: [3]}, {0: [3], 2: [4]})])    # :447-502 edge 1->2 shared
+def test_link_batch_collation_on_the_reference_batching_cases(pair, n_nodes, edges, pos, hard_neg):
+    import torch
+
+    from gigl_b200.specs import link_batch_from_sample_protos
+
+    b = link_batch_from_sample_protos(pair, torch.device("cpu"))
+    ids = b.graph.node_ids.tolist()
+    assert len(ids) == n_nodes == len(set(ids))
+    ei = b.graph.edge_index.numpy()
+    got = [(ids[a], ids[c]) for a, c in zip(ei[0], ei[1])]
+    assert len(got) == len(edges) and set(got) == edges                      # the shared edge is message-passed once
+    assert [ids[r] for r in b.root_nodes.tolist()] == [s["root_node"]["node_id"] for s in pair]
+    for data, want in ((b.pos_supervision_edge_data, pos), (b.hard_neg_supervision_edge_data, hard_neg)):
+        assert list(data) == [0]                                             # one condensed edge type
+        m = data[0].root_node_to_target_node_id
+        assert {ids[r]: [ids[t] for t in tg.tolist()] for r, tg in m.items()} == want
+        assert data[0].label_edge_features is None and all(tg.dtype == torch.int64 for tg in m.values())
+    assert b.edge_attr is None
+
+
+def test_link_batch_carries_edge_features_of_user_defined_labels():
+    """:504-558 - a sample rooted at 5 with feature-rich message-passing edges (2 values) and user-defined label edges (3)."""
+    import torch
+
+    from gigl_b200.specs import link_batch_from_sample_protos
+
+    s = _nablp(5, [5, 6, 7], [(5, 6, [0, 1]), (6, 7, [0, 1])], [(5, 6, [0, 1, 2])], [(5, 7, [0, 1, 2])])
+    b = link_batch_from_sample_protos([s], torch.device("cpu"))
+    assert b.graph.node_ids.numel() == 3 and b.graph.edge_index.shape[1] == 2
+    pos, neg = b.pos_supervision_edge_data[0], b.hard_neg_supervision_edge_data[0]
+    assert len(pos.root_node_to_target_node_id) == 1 and len(neg.root_node_to_target_node_id) == 1
+    assert b.edge_attr.shape == (2, 2)
+    for d in (pos, neg):
+        for r in d.root_node_to_target_node_id:
+            assert d.label_edge_features[r].shape == (1, 3)
+
+
+def test_node_batch_labels_follow_the_sample_order():
+    """supervised_node_classification_batching_test.py:173-235: triangle + line -> 5 nodes / 4 edges, triangle + chain -> 4 / 4,
+    root labels in sample order."""
+    import torch
+
+    from gigl_b200.specs import batch_from_sample_protos
+
+    def snc(root, nodes, edges, label):
+        return {"root_node": _node(root), "nodes": [_node(i) for i in nodes], "edges": [_edge(*e) for e in edges],
+                "root_node_labels": [{"label_type": "cls", "label": label}]}
+
+    tri, line, chain = snc(0, [0, 1, 2], [(0, 1), (0, 2), (1, 2)], 7), snc(3, [3, 4], [(3, 4)], 2), snc(1, [1, 2, 3], [(1, 2), (2, 3)], 5)
+    for pair, n, e, labels in (((tri, line), 5, 4, [7, 2]), ((tri, chain), 4, 4, [7, 5])):
+        b = batch_from_sample_protos(pair, torch.device("cpu"))
+        assert b.node_ids.numel() == n and b.edge_index.shape[1] == e and b.root_node_labels.tolist() == labels
+
+
+def test_link_batch_on_the_reference_samplers_own_nablp_records():
+    """The 14 NodeAnchorBasedLinkPredictionSamples the reference's sampler wrote for its toy graph (tests/golden/
+    nablp16_sgs_output.json), collated as one batch: the union of their neighbourhoods, every root's positives located."""
+    import torch
+
+    from gigl_b200.specs import link_batch_from_sample_protos
+
+    def edge(e):
+        return {"src_node_id": e["src"], "dst_node_id": e["dst"], "condensed_edge_type": e["condensed_edge_type"], "feature_values": e["feature_values"]}
+
+    gold = load_golden("nablp16_sgs_output.json")["nablp"]
+    samples = [{"root_node": s["root_node"], "nodes": s["neighborhood"]["nodes"], "edges": [edge(e) for e in s["neighborhood"]["edges"]],
+                "pos_edges": [edge(e) for e in s["pos_edges"]], "hard_neg_edges": [edge(e) for e in s["hard_neg_edges"]], "neg_edges": []}
+               for s in gold]
+    b = link_batch_from_sample_protos(samples, torch.device("cpu"))
+    ids = b.graph.node_ids.tolist()
+    assert sorted(ids) == sorted({n["node_id"] for s in gold for n in s["neighborhood"]["nodes"]})
+    ei = b.graph.edge_index.numpy()
+    got = {(ids[a], ids[c]) for a, c in zip(ei[0], ei[1])}
+    assert got == {(e["src"], e["dst"]) for s in gold for e in s["neighborhood"]["edges"]} and len(got) == ei.shape[1]
+    assert [ids[r] for r in b.root_nodes.tolist()] == [s["root_node"]["node_id"] for s in gold]
+    pos = b.pos_supervision_edge_data[0].root_node_to_target_node_id
+    n_pos = 0
+    for s, r in zip(gold, b.root_nodes.tolist()):
+        if s["pos_edges"]:
+            assert [ids[t] for t in pos[r].tolist()] == [e["dst"] for e in s["pos_edges"]]
+            n_pos += len(s["pos_edges"])
+    assert n_pos > 0
